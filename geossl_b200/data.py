@@ -1,0 +1,98 @@
+"""Synthetic Molecule3D / MD17 / LBA-shaped conformer batches and the AtomTuple batch contract.
+
+Host-side mirror of the input layout the hot path consumes
+(/root/reference/Geom3D/dataloaders/dataloaders_AtomTuple.py:15-37 ``AtomTupleExtractor`` and
+:45-78 ``BatchAtomTuple.from_data_list``): ``x`` (N,2) int64 with the atom class in column 0
+(datasets_utils.py:131), ``positions`` (N,3) fp32, ``batch`` (N,) int64 sorted, and
+``super_edge_index`` (2,P) int64 -- all ordered atom pairs of each molecule, graph-major, either
+``combination`` (i<j, n(n-1)/2) or ``permutation`` (i!=j, n(n-1)), offset by the cumulative node
+count.  Data is synthetic (no datasets in this image): 9 atom classes (pretrain_GeoSSL.py:309),
+positions uniform in a cube at ~0.05 atoms/A^3.
+"""
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+
+@dataclass
+class AtomTupleBatch:
+    """Duck-type of ``BatchAtomTuple``: the attributes do_DDM / NCSN_version_03 read."""
+    x: torch.Tensor
+    positions: torch.Tensor
+    batch: torch.Tensor
+    super_edge_index: torch.Tensor
+    radius_edge_index: Optional[torch.Tensor] = None
+    n_graphs: Optional[int] = None          # cached; the reference syncs on batch[-1].item()+1
+    graph_ptr: Optional[torch.Tensor] = None  # (B+1,) int32 atom offsets (device CSR helper)
+    extras: dict = field(default_factory=dict)
+
+    @property
+    def num_graphs(self):
+        if self.n_graphs is None:
+            self.n_graphs = int(self.batch[-1].item()) + 1   # dataloaders_AtomTuple.py:75-78
+        return self.n_graphs
+
+    def to(self, device, non_blocking=False):
+        def mv(t):
+            return None if t is None else t.to(device, non_blocking=non_blocking)
+        return AtomTupleBatch(mv(self.x), mv(self.positions), mv(self.batch), mv(self.super_edge_index),
+                              mv(self.radius_edge_index), self.n_graphs, mv(self.graph_ptr), dict(self.extras))
+
+    def pin_memory(self):
+        def pm(t):
+            return None if t is None else t.pin_memory()
+        return AtomTupleBatch(pm(self.x), pm(self.positions), pm(self.batch), pm(self.super_edge_index),
+                              pm(self.radius_edge_index), self.n_graphs, pm(self.graph_ptr), dict(self.extras))
+
+
+def pair_count(n, option="combination"):
+    n = np.asarray(n, dtype=np.int64)
+    full = n * (n - 1)
+    return full // 2 if option == "combination" else full
+
+
+def super_edges_host(counts, option="combination"):
+    """All ordered atom pairs per molecule in ``itertools`` order, offset by cumulative atom count.
+    Vectorised numpy restatement of AtomTupleExtractor + the collate offset (ratio == 1)."""
+    counts = np.asarray(counts, dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    us, vs = [], []
+    cache = {}
+    for g, n in enumerate(counts.tolist()):
+        if n < 2:
+            continue
+        if n not in cache:
+            if option == "combination":
+                u, v = np.triu_indices(n, k=1)
+            else:
+                u = np.repeat(np.arange(n), n - 1)
+                v = np.concatenate([np.delete(np.arange(n), i) for i in range(n)])
+            cache[n] = (u.astype(np.int64), v.astype(np.int64))
+        u, v = cache[n]
+        us.append(u + offs[g])
+        vs.append(v + offs[g])
+    if not us:
+        return torch.empty((2, 0), dtype=torch.long)
+    return torch.from_numpy(np.stack([np.concatenate(us), np.concatenate(vs)]))
+
+
+def synthetic_batch(num_graphs=32, atoms=30, atoms_max=None, *, seed=0, option="combination",
+                    density=0.05, node_class=9, with_pairs=True):
+    """One synthetic batch on the host.  ``atoms_max`` set => n ~ U{atoms..atoms_max} per graph."""
+    rng = np.random.default_rng(seed)
+    if atoms_max is None:
+        counts = np.full(num_graphs, atoms, dtype=np.int64)
+    else:
+        counts = rng.integers(atoms, atoms_max + 1, size=num_graphs).astype(np.int64)
+    n_total = int(counts.sum())
+    z = rng.integers(0, node_class, size=n_total).astype(np.int64)
+    side = np.repeat((counts / density) ** (1.0 / 3.0), counts)
+    pos = (rng.random((n_total, 3)) * side[:, None]).astype(np.float32)
+    batch = np.repeat(np.arange(num_graphs, dtype=np.int64), counts)
+    x = np.stack([z, np.zeros_like(z)], axis=1)
+    sei = super_edges_host(counts, option) if with_pairs else torch.empty((2, 0), dtype=torch.long)
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return AtomTupleBatch(torch.from_numpy(x), torch.from_numpy(pos), torch.from_numpy(batch), sei,
+                          None, int(num_graphs), torch.from_numpy(ptr))

@@ -1,0 +1,123 @@
+"""CPU: the oracle restatement (oracle/models.py) against the fixtures produced by the unmodified
+reference modules (tests/golden/make_golden.py).  Same torch ops on the same CPU => tight bounds."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import models as O
+from oracle.radius import radius_graph, radius_neighbors, transpose_csr
+from _golden import Golden, rel_err
+
+TOL = 2e-6
+
+
+def leaf_sd(sd):
+    out = {}
+    for k, v in sd.items():
+        out[k] = v.clone().requires_grad_() if v.is_floating_point() and v.dtype == torch.float32 else v
+    return out
+
+
+def check_grads(sd, golden_grads, tol=TOL * 10):
+    for k, g in golden_grads.items():
+        assert sd[k].grad is not None, k
+        assert rel_err(sd[k].grad, g) <= tol, (k, rel_err(sd[k].grad, g))
+
+
+@pytest.mark.parametrize("name", ["schnet_small", "schnet_trunc"])
+def test_schnet_oracle(name):
+    g = Golden(name)
+    sd = leaf_sd(g.sd())
+    i = g["in"]
+    out, h, ei = O.schnet_forward(sd, i["z"], i["pos"], i["batch"], cutoff=g.cfg["cutoff"],
+                                  readout=g.cfg["readout"], return_edge_index=True)
+    assert torch.equal(ei, g["out"]["edge_index"])
+    assert rel_err(h, g["out"]["h"]) <= TOL and rel_err(out, g["out"]["out"]) <= TOL
+    ((h * i["w_h"]).sum() + (out * i["w_o"]).sum()).backward()
+    check_grads(sd, g["grad"])
+
+
+def test_schnet_trunc_has_truncated_rows():
+    g = Golden("schnet_trunc")
+    rowptr, src = radius_neighbors(g["in"]["pos"], g.cfg["cutoff"], g["in"]["batch"])
+    deg = rowptr[1:] - rowptr[:-1]
+    assert deg.max() == 33 and (deg == 32).any()      # rows of 32 *or* 33
+    t_rowptr, t_eid, t_tgt = transpose_csr(rowptr, src)
+    assert t_rowptr[-1] == src.size and (src[t_eid][1:] >= src[t_eid][:-1]).all()
+
+
+@pytest.mark.parametrize("name", ["painn_small", "painn_full"])
+def test_painn_oracle(name):
+    g = Golden(name)
+    sd = leaf_sd(g.sd())
+    i = g["in"]
+    h, q = O.painn_forward(sd, i["x"], i["pos"], i["radius_edge_index"], i["batch"], readout=g.cfg["readout"])
+    assert rel_err(q, g["out"]["q"]) <= TOL and rel_err(h, g["out"]["h"]) <= TOL
+    ((q * i["w_q"]).sum() + (h * i["w_h"]).sum()).backward()
+    check_grads(sd, g["grad"])
+    assert sd["embedding.weight"].grad[0].abs().max() == 0          # padding_idx=0 row (painn.py:174)
+
+
+@pytest.mark.parametrize("name", ["ncsn_h128", "ncsn_perm"])
+def test_ncsn_oracle(name):
+    g = Golden(name)
+    sd = leaf_sd(g.sd())
+    i = g["in"]
+    assert torch.equal(sd["sigmas"], O.ncsn_sigmas(10, 0.01, g.cfg["levels"]))
+    nf = i["node_feature"].clone().requires_grad_()
+    loss = O.ncsn_forward(sd, i["batch"], i["super_edge_index"], nf, i["distance"], i["noise_level"],
+                          i["distance_noise"], g.cfg["anneal_power"])
+    assert rel_err(loss, g["out"]["loss"]) <= TOL
+    loss.backward()
+    assert rel_err(nf.grad, g["grad"]["node_feature"]) <= TOL * 10
+    check_grads(sd, {k: v for k, v in g["grad"].items() if k != "node_feature"})
+
+
+@pytest.mark.parametrize("name", ["ddm_schnet_small", "ddm_schnet_cfg1", "ddm_painn_small"])
+def test_ddm_oracle(name):
+    g = Golden(name)
+    c, i = g.cfg, g["in"]
+    sd, sd1, sd2 = leaf_sd(g.sd()), leaf_sd(g.sd("sd1")), leaf_sd(g.sd("sd2"))
+    if c["model_3d"] == "schnet":
+        enc = lambda z, p: O.schnet_forward(sd, z, p, i["batch"], cutoff=c["cutoff"], readout="mean")[1]
+    else:
+        enc = lambda z, p: O.painn_forward(sd, z, p, i["radius_edge_index"], i["batch"], readout="add")[1]
+    _, pos2 = O.perturb(None, i["pos"], 0.0, c["sigma"], noise=i["pos_noise"])
+    loss, (r1, r2, l1, l2) = O.ddm_loss(enc, sd1, sd2, i["x"][:, 0], i["pos"], pos2, i["batch"],
+                                        i["super_edge_index"], (i["noise_level_1"], i["distance_noise_1"]),
+                                        (i["noise_level_2"], i["distance_noise_2"]), c["anneal_power"])
+    o = g["out"]
+    assert rel_err(r1, o["repr_01"]) <= TOL and rel_err(r2, o["repr_02"]) <= TOL
+    assert rel_err(l1, o["loss_01"]) <= TOL and rel_err(l2, o["loss_02"]) <= TOL and rel_err(loss, o["loss"]) <= TOL
+    loss.backward()
+    check_grads(sd, g["grad"]); check_grads(sd1, g["grad1"]); check_grads(sd2, g["grad2"])
+
+
+def test_md17_oracle_double_backward():
+    g = Golden("md17_small")
+    c, i = g.cfg, g["in"]
+    sd, sdl = leaf_sd(g.sd()), leaf_sd(g.sd("sdlin"))
+    pos = i["pos"].clone().requires_grad_()
+    rep, _ = O.schnet_forward(sd, i["z"], pos, i["batch"], cutoff=c["cutoff"], readout="mean")
+    energy = F.linear(rep, sdl["weight"], sdl["bias"]).squeeze(1)
+    force = -torch.autograd.grad(energy, pos, torch.ones_like(energy), create_graph=True, retain_graph=True)[0]
+    loss = 0.05 * F.l1_loss(energy, i["y"]) + 0.95 * F.l1_loss(force, i["force_target"])
+    loss.backward()
+    assert rel_err(energy, g["out"]["energy"]) <= TOL and rel_err(force, g["out"]["force"]) <= TOL * 10
+    check_grads(sd, g["grad"], 1e-4); check_grads(sdl, g["gradlin"], 1e-4)
+
+
+def test_reference_crosscheck_when_available():
+    """Where /root/reference exists, re-run the unmodified module against one fixture (guards drift
+    between the fixtures and the generating script)."""
+    from oracle import reference_loader
+    if not reference_loader.available():
+        pytest.skip("reference tree not present on this box")
+    SchNet, _, _ = reference_loader.load()
+    g = Golden("schnet_small")
+    c = g.cfg
+    m = SchNet(hidden_channels=c["hidden"], num_filters=c["filters"], num_interactions=c["layers"],
+               num_gaussians=c["gaussians"], cutoff=c["cutoff"], node_class=9, readout=c["readout"])
+    m.load_state_dict(g.sd(), strict=False)
+    out, h = m(g["in"]["z"], g["in"]["pos"], g["in"]["batch"], return_latent=True)
+    assert rel_err(h, g["out"]["h"]) <= TOL
