@@ -1,0 +1,117 @@
+"""PaiNN encoder -- drop-in for /root/reference/Geom3D/models/painn.py (same classes, signatures,
+parameter creation order and ``state_dict`` keys).
+
+Edge-wise work (geometry, rbf, cutoff, the 3F-wide filter, the scalar/vector message and its
+aggregation over ``idx_i``) runs in the CUDA message kernels of libgeossl_b200 (ops.PaiNNMessage);
+node-level Dense layers are library GEMMs through torch.
+"""
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from .painn_utils import CosineCutoff, Dense, GaussianRBF, build_mlp, replicate_module, scatter_add
+
+
+class PaiNNInteraction(nn.Module):
+    """Scalar/vector message block (painn.py:14-66)."""
+
+    def __init__(self, n_atom_basis: int, activation: Callable):
+        super().__init__()
+        self.n_atom_basis = n_atom_basis
+        self.interatomic_context_net = nn.Sequential(
+            Dense(n_atom_basis, n_atom_basis, activation=activation),
+            Dense(n_atom_basis, 3 * n_atom_basis, activation=None),
+        )
+
+    def forward(self, q, mu, Wij, dir_ij, idx_i, idx_j, n_atoms):
+        """Reference signature with a materialised filter ``Wij`` (E,1,3F) -- stand-alone API."""
+        x = self.interatomic_context_net(q)
+        xe = Wij * x[idx_j]
+        dq, dmuR, dmumu = torch.split(xe, self.n_atom_basis, dim=-1)
+        dq = scatter_add(dq, idx_i, dim_size=n_atoms)
+        dmu = scatter_add(dmuR * dir_ij[..., None] + dmumu * mu[idx_j], idx_i, dim_size=n_atoms)
+        return q + dq, mu + dmu
+
+
+class PaiNNMixing(nn.Module):
+    """Intra-atomic update block (painn.py:69-114)."""
+
+    def __init__(self, n_atom_basis: int, activation: Callable, epsilon: float = 1e-8):
+        super().__init__()
+        self.n_atom_basis = n_atom_basis
+        self.intraatomic_context_net = nn.Sequential(
+            Dense(2 * n_atom_basis, n_atom_basis, activation=activation),
+            Dense(n_atom_basis, 3 * n_atom_basis, activation=None),
+        )
+        self.mu_channel_mix = Dense(n_atom_basis, 2 * n_atom_basis, activation=None, bias=False)
+        self.epsilon = epsilon
+
+    def forward(self, q, mu):
+        mu_V, mu_W = torch.split(self.mu_channel_mix(mu), self.n_atom_basis, dim=-1)
+        mu_Vn = torch.sqrt(torch.sum(mu_V ** 2, dim=-2, keepdim=True) + self.epsilon)
+        x = self.intraatomic_context_net(torch.cat([q, mu_Vn], dim=-1))
+        dq_intra, dmu_intra, dqmu_intra = torch.split(x, self.n_atom_basis, dim=-1)
+        q = q + dq_intra + dqmu_intra * torch.sum(mu_V * mu_W, dim=1, keepdim=True)
+        mu = mu + dmu_intra * mu_W
+        return q, mu
+
+
+class PaiNN(nn.Module):
+    def __init__(self, n_atom_basis: int, n_interactions: int, n_rbf: int, cutoff: float, n_out: int, readout: str,
+                 n_out_hidden: int = None, n_out_layers: int = 2, activation: Optional[Callable] = F.silu,
+                 max_z: int = 100, shared_interactions: bool = False, shared_filters: bool = False,
+                 epsilon: float = 1e-8):
+        super().__init__()
+        self.n_atom_basis = n_atom_basis
+        self.n_interactions = n_interactions
+        self.n_out = n_out
+        self.n_out_hidden = n_out_hidden
+        self.n_out_layers = n_out_layers
+        self.activation = activation
+        self.cutoff = cutoff
+        self.cutoff_fn = CosineCutoff(cutoff)
+        self.radial_basis = GaussianRBF(n_rbf=n_rbf, cutoff=cutoff)
+        self.readout = readout
+        self.embedding = nn.Embedding(max_z, n_atom_basis, padding_idx=0)
+        self.share_filters = shared_filters
+        n_filter_out = 3 * n_atom_basis if shared_filters else self.n_interactions * n_atom_basis * 3
+        self.filter_net = Dense(self.radial_basis.n_rbf, n_filter_out, activation=None)
+        self.interactions = replicate_module(
+            lambda: PaiNNInteraction(n_atom_basis=self.n_atom_basis, activation=activation),
+            self.n_interactions, shared_interactions)
+        self.mixing = replicate_module(
+            lambda: PaiNNMixing(n_atom_basis=self.n_atom_basis, activation=activation, epsilon=epsilon),
+            self.n_interactions, shared_interactions)
+
+    def create_output_layers(self):
+        return build_mlp(n_in=self.n_atom_basis, n_out=self.n_out, n_hidden=self.n_out_hidden,
+                         n_layers=self.n_out_layers, activation=self.activation)
+
+    def forward(self, x, positions, radius_edge_index, batch, return_latent=False, num_graphs=None):
+        atomic_numbers = x[:, 0] if x.dim() == 2 else x
+        n_atoms = atomic_numbers.size(0)
+        Fd = self.n_atom_basis
+        q = self.embedding(atomic_numbers)                      # (N,F)
+        mu = torch.zeros((n_atoms, 3, Fd), dtype=q.dtype, device=q.device)
+        edges = ops.painn_edges(positions, radius_edge_index, n_atoms, batch, self.radial_basis.offsets,
+                                self.radial_basis.widths, self.cutoff, num_graphs=num_graphs)
+        for i, (interaction, mixing) in enumerate(zip(self.interactions, self.mixing)):
+            ctx = interaction.interatomic_context_net(q)        # (N,3F)
+            fo = 0 if self.share_filters else i * 3 * Fd
+            q, mu = ops.PaiNNMessage.apply(q, mu, ctx, self.filter_net.weight[fo:fo + 3 * Fd],
+                                           self.filter_net.bias[fo:fo + 3 * Fd], edges)
+            q, mu = mixing(q.unsqueeze(1), mu)
+            q = q.squeeze(1)
+        if num_graphs is None:
+            num_graphs = int(batch[-1].item()) + 1 if batch.numel() else 0
+        h = torch.zeros((num_graphs, Fd), dtype=q.dtype, device=q.device).index_add_(0, batch, q)
+        if self.readout == "mean":
+            cnt = torch.zeros(num_graphs, dtype=q.dtype, device=q.device).index_add_(
+                0, batch, torch.ones(n_atoms, dtype=q.dtype, device=q.device)).clamp_(min=1)
+            h = h / cnt.view(-1, 1)
+        if return_latent:
+            return h, q
+        return h

@@ -1,0 +1,227 @@
+"""SchNet encoder -- drop-in for /root/reference/Geom3D/models/schnet.py on sm_100a kernels.
+
+Same classes, constructor/forward signatures, parameter creation order (seeded init is bit-identical)
+and ``state_dict`` keys as the reference, including its quirks: ``mlp[2].bias`` keeps
+nn.Linear's default init (schnet.py:155-158 zeroes ``mlp[0].bias`` twice), the filter ``Sequential`` is
+registered twice (``mlp.*`` and ``conv.nn.*``), the float64 ``atomic_mass`` buffer, and a head whose
+output width is ``hidden_channels``.
+
+What runs where
+  radius graph ............ geossl_radius_csr (+ transpose)        [was torch_cluster.radius_graph, :91]
+  rbf + filter MLP + cutoff  geossl_filter_fwd / geossl_filter_bwd  [was :94, :141-145, :186-187]
+  gather * W, scatter-add .. geossl_cfconv_fwd / _bwd_x / _bwd_w    [was PyG propagate, :190,194-195]
+  node-level Linear layers . cuBLAS through torch (plain library GEMMs)
+When ``pos.requires_grad`` (force training, finetune_md17.py:32-54) the geometry and the filter MLP run as
+differentiable torch ops around the CFConvAggregate primitive, which is closed under differentiation.
+"""
+from math import pi as PI
+
+import torch
+import torch.nn.functional as F
+from torch.nn import Embedding, Linear, ModuleList, Sequential
+
+from ... import ops
+from ...atomic_data import ATOMIC_MASSES
+
+
+class ShiftedSoftplus(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.shift = torch.log(torch.tensor(2.0)).item()
+
+    def forward(self, x):
+        return F.softplus(x) - self.shift
+
+
+class GaussianSmearing(torch.nn.Module):
+    def __init__(self, start=0.0, stop=5.0, num_gaussians=50):
+        super().__init__()
+        offset = torch.linspace(start, stop, num_gaussians)
+        self.coeff = -0.5 / (offset[1] - offset[0]).item() ** 2
+        self.register_buffer("offset", offset)
+
+    def forward(self, dist):
+        # stand-alone API (differentiable torch ops); the training path fuses this into geossl_filter_fwd
+        delta = dist.view(-1, 1) - self.offset.view(1, -1)
+        return torch.exp(self.coeff * torch.pow(delta, 2))
+
+
+def _segment_reduce(src, index, dim_size, reduce):
+    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device).index_add_(0, index, src)
+    if reduce == "mean":
+        cnt = torch.zeros(dim_size, dtype=src.dtype, device=src.device).index_add_(
+            0, index, torch.ones(index.numel(), dtype=src.dtype, device=src.device)).clamp_(min=1)
+        out = out / cnt.view(-1, *([1] * (src.dim() - 1)))
+    return out
+
+
+class CFConv(torch.nn.Module):
+    """Continuous-filter convolution (schnet.py:170-195)."""
+
+    def __init__(self, in_channels, out_channels, num_filters, nn, cutoff):
+        super().__init__()
+        self.aggr = "add"
+        self.lin1 = Linear(in_channels, num_filters, bias=False)
+        self.lin2 = Linear(num_filters, out_channels)
+        self.nn = nn
+        self.cutoff = cutoff
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.lin1.weight)
+        torch.nn.init.xavier_uniform_(self.lin2.weight)
+        self.lin2.bias.data.fill_(0)
+
+    # ---- training fast path: everything edge-wise happens inside two kernels
+    def forward_graph(self, x, graph, smearing):
+        x = self.lin1(x)
+        x = ops.CFConvLayer.apply(x, self.nn[0].weight, self.nn[0].bias, self.nn[2].weight, self.nn[2].bias,
+                                  smearing.offset, graph, smearing.coeff, self.cutoff)
+        return self.lin2(x)
+
+    # ---- composable path (any derivative order): filter from torch ops, aggregate from the CUDA primitive
+    def forward_composed(self, x, graph, edge_weight, edge_attr):
+        C = 0.5 * (torch.cos(edge_weight * PI / self.cutoff) + 1.0)
+        W = self.nn(edge_attr) * C.view(-1, 1)
+        x = self.lin1(x)
+        x = ops.CFConvAggregate.apply(x, W, graph)
+        return self.lin2(x)
+
+    def forward(self, x, edge_index, edge_weight, edge_attr, batch=None):
+        """Reference signature (schnet.py:185).  ``edge_index`` must be target-sorted with ascending sources
+        (what radius_graph returns); ``batch`` defaults to a single graph."""
+        if batch is None:
+            batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
+        graph = ops.csr_from_edge_index(edge_index, x.size(0), batch)
+        return self.forward_composed(x, graph, edge_weight, edge_attr)
+
+    def propagate(self, edge_index, x, W, batch=None):
+        if batch is None:
+            batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
+        return ops.CFConvAggregate.apply(x, W, ops.csr_from_edge_index(edge_index, x.size(0), batch))
+
+    def message(self, x_j, W):
+        return x_j * W
+
+
+class InteractionBlock(torch.nn.Module):
+    def __init__(self, hidden_channels, num_gaussians, num_filters, cutoff):
+        super().__init__()
+        self.mlp = Sequential(
+            Linear(num_gaussians, num_filters),
+            ShiftedSoftplus(),
+            Linear(num_filters, num_filters),
+        )
+        self.conv = CFConv(hidden_channels, hidden_channels, num_filters, self.mlp, cutoff)
+        self.act = ShiftedSoftplus()
+        self.lin = Linear(hidden_channels, hidden_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.mlp[0].weight)
+        self.mlp[0].bias.data.fill_(0)
+        torch.nn.init.xavier_uniform_(self.mlp[2].weight)
+        self.mlp[0].bias.data.fill_(0)      # sic: the reference never zeroes mlp[2].bias (schnet.py:158)
+        self.conv.reset_parameters()
+        torch.nn.init.xavier_uniform_(self.lin.weight)
+        self.lin.bias.data.fill_(0)
+
+    def forward_graph(self, x, graph, smearing):
+        return self.lin(self.act(self.conv.forward_graph(x, graph, smearing)))
+
+    def forward_composed(self, x, graph, edge_weight, edge_attr):
+        return self.lin(self.act(self.conv.forward_composed(x, graph, edge_weight, edge_attr)))
+
+    def forward(self, x, edge_index, edge_weight, edge_attr, batch=None):
+        return self.lin(self.act(self.conv(x, edge_index, edge_weight, edge_attr, batch)))
+
+
+class SchNet(torch.nn.Module):
+    def __init__(self, hidden_channels=128, num_filters=128, num_interactions=6, num_gaussians=50, cutoff=10.0,
+                 node_class=None, readout="mean", dipole=False, mean=None, std=None, atomref=None):
+        super().__init__()
+        assert readout in ["add", "sum", "mean"]
+        self.hidden_channels = hidden_channels
+        self.num_filters = num_filters
+        self.num_interactions = num_interactions
+        self.num_gaussians = num_gaussians
+        self.cutoff = cutoff
+        self.dipole = dipole
+        self.readout = "add" if self.dipole else readout
+        self.mean = mean
+        self.std = std
+        self.scale = None
+
+        self.register_buffer("atomic_mass", torch.tensor(ATOMIC_MASSES, dtype=torch.float64))
+        self.embedding = Embedding(node_class, hidden_channels)
+        self.distance_expansion = GaussianSmearing(0.0, cutoff, num_gaussians)
+        self.interactions = ModuleList()
+        for _ in range(num_interactions):
+            self.interactions.append(InteractionBlock(hidden_channels, num_gaussians, num_filters, cutoff))
+        self.lin1 = Linear(hidden_channels, hidden_channels)
+        self.act = ShiftedSoftplus()
+        self.lin2 = Linear(hidden_channels, hidden_channels)
+
+        self.register_buffer("initial_atomref", atomref)
+        self.atomref = None
+        if atomref is not None:
+            self.atomref = Embedding(100, 1)
+            self.atomref.weight.data.copy_(atomref)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.embedding.reset_parameters()
+        for interaction in self.interactions:
+            interaction.reset_parameters()
+        torch.nn.init.xavier_uniform_(self.lin1.weight)
+        self.lin1.bias.data.fill_(0)
+        torch.nn.init.xavier_uniform_(self.lin2.weight)
+        self.lin2.bias.data.fill_(0)
+        if self.atomref is not None:
+            self.atomref.weight.data.copy_(self.initial_atomref)
+
+    def forward(self, z, pos, batch=None, return_latent=False, num_graphs=None, graph=None):
+        """``num_graphs`` / ``graph`` are optional extensions: passing the graph count avoids the host sync
+        on ``batch[-1]``; ``graph`` reuses a prebuilt RadiusCSR."""
+        assert z.dim() == 1 and z.dtype == torch.long
+        batch = torch.zeros_like(z) if batch is None else batch
+        h = self.embedding(z)
+        if graph is None:
+            graph = ops.radius_csr(pos, batch, self.cutoff, num_graphs=num_graphs)
+        if pos.requires_grad and torch.is_grad_enabled():
+            ge = graph.exact()
+            row, col = ge.src.long(), ge.tgt.long()
+            edge_weight = (pos[row] - pos[col]).norm(dim=-1)
+            edge_attr = self.distance_expansion(edge_weight)
+            for interaction in self.interactions:
+                h = h + interaction.forward_composed(h, ge, edge_weight, edge_attr)
+        else:
+            for interaction in self.interactions:
+                h = h + interaction.forward_graph(h, graph, self.distance_expansion)
+
+        h = self.lin1(h)
+        h = self.act(h)
+        h = self.lin2(h)
+
+        n_graphs = graph.graph_ptr.numel() - 1
+        if self.dipole:
+            mass = self.atomic_mass[z].view(-1, 1)
+            c = _segment_reduce(mass * pos, batch, n_graphs, "add") / _segment_reduce(mass, batch, n_graphs, "add")
+            h = h * (pos - c[batch])
+        if not self.dipole and self.mean is not None and self.std is not None:
+            h = h * self.std + self.mean
+        if not self.dipole and self.atomref is not None:
+            h = h + self.atomref(z)
+
+        out = _segment_reduce(h, batch, n_graphs, self.readout)
+        if self.dipole:
+            out = torch.norm(out, dim=-1, keepdim=True)
+        if self.scale is not None:
+            out = self.scale * out
+        if return_latent:
+            return out, h
+        return out
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(hidden_channels={self.hidden_channels}, num_filters={self.num_filters}, "
+                f"num_interactions={self.num_interactions}, num_gaussians={self.num_gaussians}, cutoff={self.cutoff})")

@@ -1,0 +1,177 @@
+// Continuous-filter convolution aggregate and its two adjoints over the destination-sorted CSR.
+//
+// Replaces PyG MessagePassing.propagate + CFConv.message (Geom3D/models/schnet.py:190,194-195):
+//   x_j = x[edge_index[0]] (materialised (E,F)), msg = x_j * W, torch_scatter atomicAdd by edge_index[1].
+// Here: one warp per destination row, W_e streamed once with 128-bit loads that bypass L1, x rows
+// gathered through L1/L2 (x is (N,F) = a few MB, L2 resident), fp32 accumulation in registers in
+// edge order, one coalesced store per row: atomic free and run-to-run deterministic.
+//
+// HBM roofline: bytes = 4F*E (W) + 2*4F*N (x, out) + 4E (src) + 4(N+1) (rowptr).
+#include "common.cuh"
+
+namespace geossl {
+
+__device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
+    a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
+}
+
+// LPR lanes cover one F-wide row with float4 each; a warp walks EPW = 32/LPR edges per step.
+template <int F, int UNROLL>
+__global__ void __launch_bounds__(256)
+cfconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ filt, const int32_t* __restrict__ rowptr,
+                  const int32_t* __restrict__ src, int n_atoms, float* __restrict__ out) {
+    constexpr int LPR = F / 4, EPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n_atoms) return;
+    const int f = (lane % LPR) * 4, sub = lane / LPR;
+    const int b = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e0 = b + sub; e0 < end; e0 += EPW * UNROLL) {
+        float4 w[UNROLL], xv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int e = e0 + u * EPW;
+            if (e < end) {
+                const int j = __ldg(src + e);
+                w[u] = ld_stream4(filt + (int64_t)e * F + f);
+                xv[u] = ldg4(x + (int64_t)j * F + f);
+            } else {
+                w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[u] = w[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) fma4(acc, xv[u], w[u]);
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
+}
+
+template <int F, int UNROLL>
+__global__ void __launch_bounds__(256)
+cfconv_bwd_x_kernel(const float* __restrict__ filt, const float* __restrict__ g, const int32_t* __restrict__ t_rowptr,
+                    const int32_t* __restrict__ t_eid, const int32_t* __restrict__ t_tgt, int n_atoms,
+                    float* __restrict__ dx) {
+    constexpr int LPR = F / 4, EPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n_atoms) return;
+    const int f = (lane % LPR) * 4, sub = lane / LPR;
+    const int b = __ldg(t_rowptr + row), end = __ldg(t_rowptr + row + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = b + sub; k0 < end; k0 += EPW * UNROLL) {
+        float4 w[UNROLL], gv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int k = k0 + u * EPW;
+            if (k < end) {
+                const int e = __ldg(t_eid + k), i = __ldg(t_tgt + k);
+                w[u] = ld_stream4(filt + (int64_t)e * F + f);
+                gv[u] = ldg4(g + (int64_t)i * F + f);
+            } else {
+                w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                gv[u] = w[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) fma4(acc, gv[u], w[u]);
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (sub == 0) *reinterpret_cast<float4*>(dx + (int64_t)row * F + f) = acc;
+}
+
+template <int F>
+__global__ void __launch_bounds__(256)
+cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, const int32_t* __restrict__ rowptr,
+                    const int32_t* __restrict__ src, int n_atoms, float* __restrict__ dfilt) {
+    constexpr int LPR = F / 4, EPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n_atoms) return;
+    const int f = (lane % LPR) * 4, sub = lane / LPR;
+    const int b = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const float4 gi = ldg4(g + (int64_t)row * F + f);
+    for (int e = b + sub; e < end; e += EPW) {
+        const int j = __ldg(src + e);
+        const float4 xv = ldg4(x + (int64_t)j * F + f);
+        st_stream4(dfilt + (int64_t)e * F + f, make_float4(xv.x * gi.x, xv.y * gi.y, xv.z * gi.z, xv.w * gi.w));
+    }
+}
+
+template <int F>
+int launch_fwd(const float* x, const float* filt, const int32_t* rowptr, const int32_t* src, int64_t n, float* out, cudaStream_t st) {
+    const int threads = 256;
+    const int blocks = (int)((n * 32 + threads - 1) / threads);
+    cfconv_fwd_kernel<F, 4><<<blocks, threads, 0, st>>>(x, filt, rowptr, src, (int)n, out);
+    return 0;
+}
+template <int F>
+int launch_bwd_x(const float* filt, const float* g, const int32_t* tr, const int32_t* te, const int32_t* tt, int64_t n, float* dx, cudaStream_t st) {
+    const int threads = 256;
+    const int blocks = (int)((n * 32 + threads - 1) / threads);
+    cfconv_bwd_x_kernel<F, 4><<<blocks, threads, 0, st>>>(filt, g, tr, te, tt, (int)n, dx);
+    return 0;
+}
+template <int F>
+int launch_bwd_w(const float* x, const float* g, const int32_t* rowptr, const int32_t* src, int64_t n, float* dfilt, cudaStream_t st) {
+    const int threads = 256;
+    const int blocks = (int)((n * 32 + threads - 1) / threads);
+    cfconv_bwd_w_kernel<F><<<blocks, threads, 0, st>>>(x, g, rowptr, src, (int)n, dfilt);
+    return 0;
+}
+
+}  // namespace geossl
+
+using namespace geossl;
+
+#define DISPATCH_F(F, CALL)                                          \
+    switch (F) {                                                     \
+        case 32: { constexpr int kF = 32; CALL; break; }             \
+        case 64: { constexpr int kF = 64; CALL; break; }             \
+        case 128: { constexpr int kF = 128; CALL; break; }           \
+        default: set_error("%s: unsupported width F=%d (32/64/128)", __func__, F); return GEOSSL_EINVAL; \
+    }
+
+extern "C" {
+
+int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* rowptr, const int32_t* src,
+                      int64_t n_atoms, int F, float* out, void* stream) {
+    if (n_atoms == 0) return 0;
+    GEOSSL_REQUIRE(x && filt && rowptr && src && out && n_atoms > 0, "null pointer");
+    DISPATCH_F(F, launch_fwd<kF>(x, filt, rowptr, src, n_atoms, out, as_stream(stream)));
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_cfconv_bwd_x(const float* filt, const float* grad_out, const int32_t* t_rowptr, const int32_t* t_eid,
+                        const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream) {
+    if (n_atoms == 0) return 0;
+    GEOSSL_REQUIRE(filt && grad_out && t_rowptr && t_eid && t_tgt && grad_x && n_atoms > 0, "null pointer");
+    DISPATCH_F(F, launch_bwd_x<kF>(filt, grad_out, t_rowptr, t_eid, t_tgt, n_atoms, grad_x, as_stream(stream)));
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_cfconv_bwd_w(const float* x, const float* grad_out, const int32_t* rowptr, const int32_t* src,
+                        int64_t n_atoms, int F, float* grad_filt, void* stream) {
+    if (n_atoms == 0) return 0;
+    GEOSSL_REQUIRE(x && grad_out && rowptr && src && grad_filt && n_atoms > 0, "null pointer");
+    DISPATCH_F(F, launch_bwd_w<kF>(x, grad_out, rowptr, src, n_atoms, grad_filt, as_stream(stream)));
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

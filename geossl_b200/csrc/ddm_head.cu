@@ -1,0 +1,590 @@
+// DDM (denoising distance matching) head, fp32 SIMT edition.
+//
+// Replaces the distance block of do_DDM (examples/pretrain_GeoSSL.py:197-205) and
+// NCSN_version_03.forward (examples/NCSN.py:183-212) with its two MultiLayerPerceptrons (NCSN.py:9-43):
+// sigma-indexed distance perturbation, 1->H->1 distance embedding, gather h[u]+h[v], score MLP
+// (H+1)->H->H/2->1, sigma^alpha weighted squared error, mean over graphs -- one kernel forward, one
+// backward (which recomputes the forward per 64-pair tile, so nothing per-pair is saved in HBM).
+//
+// Persistent CTAs (one per SM) walk 64-pair tiles; the score MLP runs as register-tiled SIMT GEMMs on
+// k-major shared-memory tiles (simt_tile.cuh).  Weight matrices sit in shared memory once, row-major with
+// an odd row stride (H+1), which serves both the forward (B[k][n] = W[n][k]) and the data-gradient
+// (B[k][n] = W[k][n]) orientation without bank conflicts.  Weight gradients accumulate in registers across
+// the CTA's tiles and are reduced over CTAs in a fixed order (deterministic); only dL/dh uses fp32
+// atomics (RED), because pairs scatter to both endpoints.
+#include "common.cuh"
+#include "simt_tile.cuh"
+
+namespace geossl {
+
+template <int H>
+struct HeadCfg {
+    static constexpr int HH = H / 2;
+    static constexpr int LD = H + 1;
+    static constexpr int TP = 64;
+    static constexpr int S = TP + 4;
+    using C1 = TileCfg<H>;      // (pairs x H) outputs
+    using C2 = TileCfg<HH>;     // (pairs x H/2) outputs
+    static constexpr int M0 = (H / C1::TY) > 0 ? (H / C1::TY) : 1;     // dW0 rows per thread
+    static constexpr int M1 = (HH / C1::TY) > 0 ? (HH / C1::TY) : 1;   // dW1 rows per thread
+    // shared memory (floats)
+    static constexpr int kW0 = 0;                        // [H][LD]    output_mlp.layers.0.weight
+    static constexpr int kW1 = kW0 + H * LD;             // [HH][LD]   output_mlp.layers.1.weight (padded rows)
+    static constexpr int kFeat = kW1 + HH * LD + 3;      // [H+1][S]   (offset keeps 16 B alignment below)
+    static constexpr int kFeatA = (kFeat + 3) / 4 * 4;
+    static constexpr int kZ1 = kFeatA + (H + 1) * S;     // [H][S]     z1, later dz1
+    static constexpr int kZ2 = kZ1 + H * S;              // [HH][S]    dz2 (backward only)
+    static constexpr int kVec = kZ2 + HH * S;            // small vectors
+    static constexpr int oB0 = kVec;                     // [H]
+    static constexpr int oB1 = oB0 + H;                  // [HH]
+    static constexpr int oW2 = oB1 + HH;                 // [HH]
+    static constexpr int oIW0 = oW2 + HH;                // [H] input mlp layer 0 weight
+    static constexpr int oIB0 = oIW0 + H;                // [H]
+    static constexpr int oIW1 = oIB0 + H;                // [H] input mlp layer 1 weight
+    static constexpr int oU = oIW1 + H;                  // int [TP]
+    static constexpr int oV = oU + TP;                   // int [TP]
+    static constexpr int oSig = oV + TP;                 // sigma
+    static constexpr int oDt = oSig + TP;                // perturbed distance
+    static constexpr int oEmb = oDt + TP;
+    static constexpr int oTgt = oEmb + TP;               // target
+    static constexpr int oSa = oTgt + TP;                // sigma^alpha (0 for invalid pairs)
+    static constexpr int oDemb = oSa + TP;
+    static constexpr int oRed = oDemb + TP;              // [64] reduction scratch
+    static constexpr int kFloats = oRed + 64;
+    // per-CTA partial gradient layout
+    static constexpr int pW0 = 0;                        // [H][H+1]
+    static constexpr int pB0 = pW0 + H * LD;
+    static constexpr int pW1 = pB0 + H;                  // [HH][H]
+    static constexpr int pB1 = pW1 + HH * H;
+    static constexpr int pW2 = pB1 + HH;                 // [HH]
+    static constexpr int pB2 = pW2 + HH;                 // [1]
+    static constexpr int pIW0 = pB2 + 1;                 // [H]
+    static constexpr int pIB0 = pIW0 + H;
+    static constexpr int pIW1 = pIB0 + H;
+    static constexpr int pIB1 = pIW1 + H;                // [1]
+    static constexpr int kPartial = pIB1 + 1;
+};
+
+struct HeadIn {
+    const float* h; const int64_t* sei; const int64_t* batch; int64_t n_pairs;
+    const float* dist; const float* noise; const int64_t* noise_level; const float* sigmas; int n_levels;
+    float anneal_power;
+    geossl_ddm_params p;
+};
+
+template <int H>
+__device__ __forceinline__ void head_load_weights(const HeadIn& in, float* smem) {
+    using K = HeadCfg<H>;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < H * K::LD; idx += 256) smem[K::kW0 + idx] = __ldg(in.p.out_w0 + idx);
+    for (int idx = tid; idx < K::HH * H; idx += 256) smem[K::kW1 + (idx / H) * K::LD + idx % H] = __ldg(in.p.out_w1 + idx);
+    if (tid < H) {
+        smem[K::oB0 + tid] = __ldg(in.p.out_b0 + tid);
+        smem[K::oIW0 + tid] = __ldg(in.p.in_w0 + tid);
+        smem[K::oIB0 + tid] = __ldg(in.p.in_b0 + tid);
+        smem[K::oIW1 + tid] = __ldg(in.p.in_w1 + tid);
+    }
+    if (tid < K::HH) {
+        smem[K::oB1 + tid] = __ldg(in.p.out_b1 + tid);
+        smem[K::oW2 + tid] = __ldg(in.p.out_w2 + tid);
+    }
+}
+
+// Per-pair scalars, distance embedding and the k-major feature tile.  Returns the largest graph id seen
+// by this thread (-1 if none).  Ends with a __syncthreads().
+template <int H>
+__device__ __forceinline__ int head_build_tile(const HeadIn& in, int64_t p0, float* smem) {
+    using K = HeadCfg<H>;
+    using C1 = typename K::C1;
+    const int tid = threadIdx.x;
+    int* sU = reinterpret_cast<int*>(smem + K::oU);
+    int* sV = reinterpret_cast<int*>(smem + K::oV);
+    int gmax = -1;
+    if (tid < K::TP) {
+        const int64_t p = p0 + tid;
+        int u = 0, v = 0;
+        float sigma = 1.f, dt = 0.f, tgt = 0.f, sa = 0.f;
+        if (p < in.n_pairs) {
+            u = (int)in.sei[p];
+            v = (int)in.sei[in.n_pairs + p];
+            const int g = (int)in.batch[u];
+            gmax = g;
+            int lvl = (int)in.noise_level[g];
+            lvl = lvl < 0 ? 0 : (lvl >= in.n_levels ? in.n_levels - 1 : lvl);
+            sigma = __ldg(in.sigmas + lvl);
+            const float d = __ldg(in.dist + p);
+            dt = __fadd_rn(d, __fmul_rn(__ldg(in.noise + p), sigma));           // NCSN.py:196
+            tgt = __fmul_rn(-(1.f / __fmul_rn(sigma, sigma)), __fsub_rn(dt, d)); // NCSN.py:199 (op order kept)
+            sa = (in.anneal_power == 2.f) ? sigma * sigma : powf(sigma, in.anneal_power);
+        }
+        sU[tid] = u; sV[tid] = v;
+        smem[K::oSig + tid] = sigma; smem[K::oDt + tid] = dt; smem[K::oTgt + tid] = tgt; smem[K::oSa + tid] = sa;
+    }
+    __syncthreads();
+    {   // distance embedding: 4 threads per pair
+        const int pl = tid >> 2, q = tid & 3;
+        const float dt = smem[K::oDt + pl];
+        float s = 0.f;
+        for (int k = q; k < H; k += 4) {
+            const float pre = fmaf(smem[K::oIW0 + k], dt, smem[K::oIB0 + k]);
+            s = fmaf(smem[K::oIW1 + k], fmaxf(pre, 0.f), s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0) {
+            const float emb = s + __ldg(in.p.in_b1);
+            smem[K::oEmb + pl] = emb;
+            smem[K::kFeatA + H * K::S + pl] = emb;
+        }
+    }
+    {   // feat[c][p] = h[u][c] + h[v][c]
+        const int tx = tid % C1::TX, ty = tid / C1::TX;
+#pragma unroll
+        for (int i = 0; i < C1::ME; ++i) {
+            const int pl = ty * C1::ME + i;
+            const float* hu = in.h + (int64_t)sU[pl] * H;
+            const float* hv = in.h + (int64_t)sV[pl] * H;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = tx + C1::TX * j;
+                smem[K::kFeatA + c * K::S + pl] = __ldg(hu + c) + __ldg(hv + c);
+            }
+        }
+    }
+    __syncthreads();
+    return gmax;
+}
+
+// z1 = relu(feat W0^T + b0) -> sZ1 (k-major).  Ends with a __syncthreads().
+template <int H>
+__device__ __forceinline__ void head_layer0(float* smem) {
+    using K = HeadCfg<H>;
+    using C1 = typename K::C1;
+    const int tid = threadIdx.x, tx = tid % C1::TX, r0 = (tid / C1::TX) * C1::ME;
+    float acc[C1::ME][4];
+    zero_acc(acc);
+    gemm_rows<H>(acc, smem + K::kFeatA, smem + K::kW0, 1, K::LD, H + 1, tx, r0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = tx + C1::TX * j;
+        const float b = smem[K::oB0 + n];
+#pragma unroll
+        for (int i = 0; i < C1::ME; ++i) smem[K::kZ1 + n * K::S + r0 + i] = fmaxf(acc[i][j] + b, 0.f);
+    }
+    __syncthreads();
+}
+
+// z2 = relu(z1 W1^T + b1) in registers (pairs r0.., columns tx2 + TX2*j); raw score reduced over the row.
+template <int H>
+__device__ __forceinline__ void head_layer1(float* smem, float (&z2)[HeadCfg<H>::C2::ME][4],
+                                            float (&score)[HeadCfg<H>::C2::ME], float out_b2) {
+    using K = HeadCfg<H>;
+    using C2 = typename K::C2;
+    const int tid = threadIdx.x, tx = tid % C2::TX, r0 = (tid / C2::TX) * C2::ME;
+    zero_acc(z2);
+    gemm_rows<K::HH>(z2, smem + K::kZ1, smem + K::kW1, 1, K::LD, H, tx, r0);
+#pragma unroll
+    for (int i = 0; i < C2::ME; ++i) score[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = tx + C2::TX * j;
+        const float b = smem[K::oB1 + n], w = smem[K::oW2 + n];
+#pragma unroll
+        for (int i = 0; i < C2::ME; ++i) {
+            z2[i][j] = fmaxf(z2[i][j] + b, 0.f);
+            score[i] = fmaf(z2[i][j], w, score[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < C2::ME; ++i) {
+#pragma unroll
+        for (int o = C2::TX / 2; o > 0; o >>= 1) score[i] += __shfl_xor_sync(0xffffffffu, score[i], o);
+        score[i] += out_b2;
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(256, 1) ddm_head_fwd_kernel(HeadIn in, float* __restrict__ workspace) {
+    using K = HeadCfg<H>;
+    using C2 = typename K::C2;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    head_load_weights<H>(in, smem);
+    __syncthreads();
+    const float out_b2 = __ldg(in.p.out_b2);
+    float loss_acc = 0.f;
+    int gmax = -1;
+    const int64_t n_tiles = (in.n_pairs + K::TP - 1) / K::TP;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        gmax = max(gmax, head_build_tile<H>(in, t * K::TP, smem));
+        head_layer0<H>(smem);
+        float z2[C2::ME][4], score[C2::ME];
+        head_layer1<H>(smem, z2, score, out_b2);
+        if (tid % C2::TX == 0) {
+            const int r0 = (tid / C2::TX) * C2::ME;
+#pragma unroll
+            for (int i = 0; i < C2::ME; ++i) {
+                const int pl = r0 + i;
+                const float s = score[i] * (1.f / smem[K::oSig + pl]);          // NCSN.py:205
+                const float diff = s - smem[K::oTgt + pl];
+                loss_acc += 0.5f * (diff * diff) * smem[K::oSa + pl];           // NCSN.py:209 (sa = 0 if invalid)
+            }
+        }
+        __syncthreads();
+    }
+    // block reduction (fixed order) of the loss partial and the largest graph id
+    __shared__ float red_l[8];
+    __shared__ int red_g[8];
+    loss_acc = warp_sum(loss_acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if ((tid & 31) == 0) { red_l[tid >> 5] = loss_acc; red_g[tid >> 5] = gmax; }
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        int g = -1;
+        for (int w = 0; w < 8; ++w) { s += red_l[w]; g = max(g, red_g[w]); }
+        workspace[2 * blockIdx.x] = s;
+        workspace[2 * blockIdx.x + 1] = (float)g;
+    }
+}
+
+__global__ void ddm_loss_finalize_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float s = 0.f, g = -1.f;
+        for (int p = 0; p < n_parts; ++p) { s += workspace[2 * p]; g = fmaxf(g, workspace[2 * p + 1]); }
+        const float ng = g + 1.f;
+        loss[0] = ng > 0.f ? s / ng : 0.f;
+        loss[1] = ng;
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(256, 1)
+ddm_head_bwd_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* __restrict__ grad_loss,
+                    float* __restrict__ grad_h, float* __restrict__ workspace) {
+    using K = HeadCfg<H>;
+    using C1 = typename K::C1;
+    using C2 = typename K::C2;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int tx1 = tid % C1::TX, ty1 = tid / C1::TX, r01 = ty1 * C1::ME;
+    const int tx2 = tid % C2::TX, ty2 = tid / C2::TX, r02 = ty2 * C2::ME;
+    int* sU = reinterpret_cast<int*>(smem + K::oU);
+    int* sV = reinterpret_cast<int*>(smem + K::oV);
+    head_load_weights<H>(in, smem);
+    __syncthreads();
+    const float out_b2 = __ldg(in.p.out_b2);
+    const float ng = __ldg(loss_aux + 1);
+    const float gscale = ng > 0.f ? __ldg(grad_loss) / ng : 0.f;
+
+    float aW0[K::M0][4], aW1[K::M1][4], aW2[4];
+    zero_acc(aW0); zero_acc(aW1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) aW2[j] = 0.f;
+    float aB2 = 0.f, aW0last = 0.f, aB0 = 0.f, aB1 = 0.f, aIW0 = 0.f, aIB0 = 0.f, aIW1 = 0.f, aIB1 = 0.f;
+
+    const int64_t n_tiles = (in.n_pairs + K::TP - 1) / K::TP;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        head_build_tile<H>(in, t * K::TP, smem);
+        head_layer0<H>(smem);
+        {
+            float z2[C2::ME][4], score[C2::ME];
+            head_layer1<H>(smem, z2, score, out_b2);
+#pragma unroll
+            for (int i = 0; i < C2::ME; ++i) {
+                const int pl = r02 + i;
+                const float inv = 1.f / smem[K::oSig + pl];
+                const float s = score[i] * inv;
+                const float dsr = (s - smem[K::oTgt + pl]) * smem[K::oSa + pl] * gscale * inv;   // d loss / d raw score
+                if (tx2 == 0) aB2 += dsr;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = tx2 + C2::TX * j;
+                    aW2[j] = fmaf(dsr, z2[i][j], aW2[j]);
+                    smem[K::kZ2 + n * K::S + pl] = z2[i][j] > 0.f ? dsr * smem[K::oW2 + n] : 0.f;
+                }
+            }
+        }
+        __syncthreads();
+        // dW1[k][i] += sum_p dz2[p][k] z1[p][i]; db1[k] += sum_p dz2[p][k]
+        gemm_wgrad<H, K::M1>(aW1, smem + K::kZ2, ty1 * K::M1, K::HH, smem + K::kZ1, tx1);
+        if (tid < K::HH) {
+            float s = 0.f;
+            for (int p = 0; p < K::TP; ++p) s += smem[K::kZ2 + tid * K::S + p];
+            aB1 += s;
+        }
+        // dz1 = (dz2 W1) * [z1 > 0]
+        float acc[C1::ME][4];
+        zero_acc(acc);
+        gemm_rows<H>(acc, smem + K::kZ2, smem + K::kW1, K::LD, 1, K::HH, tx1, r01);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < C1::ME; ++i)
+                if (!(smem[K::kZ1 + (tx1 + C1::TX * j) * K::S + r01 + i] > 0.f)) acc[i][j] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < C1::ME; ++i) smem[K::kZ1 + (tx1 + C1::TX * j) * K::S + r01 + i] = acc[i][j];
+        __syncthreads();
+        // dW0[k][i] += sum_p dz1[p][k] feat[p][i] (i < H), last column and db0 per thread k
+        gemm_wgrad<H, K::M0>(aW0, smem + K::kZ1, ty1 * K::M0, H, smem + K::kFeatA, tx1);
+        if (tid < H) {
+            float s = 0.f, sl = 0.f;
+            for (int p = 0; p < K::TP; ++p) {
+                const float v = smem[K::kZ1 + tid * K::S + p];
+                s += v;
+                sl = fmaf(v, smem[K::oEmb + p], sl);
+            }
+            aB0 += s;
+            aW0last += sl;
+        }
+        // dfeat[:, :H] = dz1 W0[:, :H]  -> scatter to both endpoints
+        zero_acc(acc);
+        gemm_rows<H>(acc, smem + K::kZ1, smem + K::kW0, K::LD, 1, H, tx1, r01);
+#pragma unroll
+        for (int i = 0; i < C1::ME; ++i) {
+            const int pl = r01 + i;
+            if (t * K::TP + pl < in.n_pairs) {
+                float* gu = grad_h + (int64_t)sU[pl] * H;
+                float* gv = grad_h + (int64_t)sV[pl] * H;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = tx1 + C1::TX * j;
+                    atomicAdd(gu + c, acc[i][j]);
+                    atomicAdd(gv + c, acc[i][j]);
+                }
+            }
+        }
+        {   // demb_p = sum_k dz1[p][k] W0[k][H]
+            const int pl = tid >> 2, q = tid & 3;
+            float s = 0.f;
+            for (int k = q; k < H; k += 4) s = fmaf(smem[K::kZ1 + k * K::S + pl], smem[K::kW0 + k * K::LD + H], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0) smem[K::oDemb + pl] = s;
+        }
+        __syncthreads();
+        if (tid < H) {   // distance-embedding MLP gradients, thread per hidden unit
+            const float w0 = smem[K::oIW0 + tid], b0 = smem[K::oIB0 + tid], w1 = smem[K::oIW1 + tid];
+            for (int p = 0; p < K::TP; ++p) {
+                const float dt = smem[K::oDt + p], de = smem[K::oDemb + p];
+                const float pre = fmaf(w0, dt, b0);
+                if (pre > 0.f) {
+                    aIW1 = fmaf(de, pre, aIW1);
+                    const float dpre = de * w1;
+                    aIW0 = fmaf(dpre, dt, aIW0);
+                    aIB0 += dpre;
+                }
+                if (tid == 0) aIB1 += de;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- per-CTA partials
+    float* ws = workspace + (int64_t)blockIdx.x * K::kPartial;
+    if (ty1 * K::M0 < H) {
+#pragma unroll
+        for (int i = 0; i < K::M0; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ws[K::pW0 + (ty1 * K::M0 + i) * K::LD + tx1 + C1::TX * j] = aW0[i][j];
+    }
+    if (ty1 * K::M1 < K::HH) {
+#pragma unroll
+        for (int i = 0; i < K::M1; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ws[K::pW1 + (ty1 * K::M1 + i) * H + tx1 + C1::TX * j] = aW1[i][j];
+    }
+    if (tid < H) {
+        ws[K::pW0 + tid * K::LD + H] = aW0last;
+        ws[K::pB0 + tid] = aB0;
+        ws[K::pIW0 + tid] = aIW0;
+        ws[K::pIB0 + tid] = aIB0;
+        ws[K::pIW1 + tid] = aIW1;
+    }
+    if (tid < K::HH) ws[K::pB1 + tid] = aB1;
+    if (tid == 0) ws[K::pIB1] = aIB1;
+    // out_w2 / out_b2: reduce over the TY2 row groups through shared memory
+    __syncthreads();
+    float* red = smem + K::kFeatA;     // [TY2][HH] and [TY2]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[ty2 * K::HH + tx2 + C2::TX * j] = aW2[j];
+    if (tx2 == 0) red[C2::TY * K::HH + ty2] = aB2;
+    __syncthreads();
+    if (tid < K::HH) {
+        float s = 0.f;
+        for (int r = 0; r < C2::TY; ++r) s += red[r * K::HH + tid];
+        ws[K::pW2 + tid] = s;
+    }
+    if (tid == 0) {
+        float s = 0.f;
+        for (int r = 0; r < C2::TY; ++r) s += red[C2::TY * K::HH + r];
+        ws[K::pB2] = s;
+    }
+}
+
+template <int H>
+__global__ void ddm_head_reduce_kernel(const float* __restrict__ workspace, int n_parts, geossl_ddm_grads g) {
+    using K = HeadCfg<H>;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K::kPartial) return;
+    float s = 0.f;
+    for (int p = 0; p < n_parts; ++p) s += workspace[(int64_t)p * K::kPartial + idx];
+    if (idx < K::pB0) g.out_w0[idx] = s;
+    else if (idx < K::pW1) g.out_b0[idx - K::pB0] = s;
+    else if (idx < K::pB1) g.out_w1[idx - K::pW1] = s;
+    else if (idx < K::pW2) g.out_b1[idx - K::pB1] = s;
+    else if (idx < K::pB2) g.out_w2[idx - K::pW2] = s;
+    else if (idx < K::pIW0) g.out_b2[0] = s;
+    else if (idx < K::pIB0) g.in_w0[idx - K::pIW0] = s;
+    else if (idx < K::pIW1) g.in_b0[idx - K::pIB0] = s;
+    else if (idx < K::pIB1) g.in_w1[idx - K::pIW1] = s;
+    else g.in_b1[0] = s;
+}
+
+__global__ void pair_distance_kernel(const float* __restrict__ pos, const int64_t* __restrict__ sei, int64_t n_pairs,
+                                     float* __restrict__ dist) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int64_t u = sei[p], v = sei[n_pairs + p];
+    const float dx = __fsub_rn(pos[3 * u], pos[3 * v]), dy = __fsub_rn(pos[3 * u + 1], pos[3 * v + 1]),
+                dz = __fsub_rn(pos[3 * u + 2], pos[3 * v + 2]);
+    // sqrt(sum((u - v) ** 2, dim=1))   (pretrain_GeoSSL.py:201)
+    dist[p] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
+
+static int head_grid(int64_t n_pairs) {
+    int64_t tiles = (n_pairs + 63) / 64;
+    return (int)(tiles < kNumSM ? (tiles > 0 ? tiles : 1) : kNumSM);
+}
+
+template <int H>
+int launch_head_fwd(const HeadIn& in, float* workspace, float* loss, cudaStream_t st) {
+    const size_t smem = HeadCfg<H>::kFloats * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ddm_head_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const int grid = head_grid(in.n_pairs);
+    ddm_head_fwd_kernel<H><<<grid, 256, smem, st>>>(in, workspace);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    count_launch();
+    ddm_loss_finalize_kernel<<<1, 32, 0, st>>>(workspace, grid, loss);
+    return 0;
+}
+
+template <int H>
+int launch_head_bwd(const HeadIn& in, int64_t n_atoms, const float* loss_aux, const float* grad_loss, float* workspace,
+                    float* grad_h, const geossl_ddm_grads& g, cudaStream_t st) {
+    const size_t smem = HeadCfg<H>::kFloats * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ddm_head_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    cudaError_t e = cudaMemsetAsync(grad_h, 0, sizeof(float) * (size_t)n_atoms * H, st);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = head_grid(in.n_pairs);
+    ddm_head_bwd_kernel<H><<<grid, 256, smem, st>>>(in, loss_aux, grad_loss, grad_h, workspace);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    count_launch();
+    const int n = HeadCfg<H>::kPartial;
+    ddm_head_reduce_kernel<H><<<(n + 255) / 256, 256, 0, st>>>(workspace, grid, g);
+    return 0;
+}
+
+static int64_t head_workspace(int H) {
+    switch (H) {
+        case 32: return (int64_t)kNumSM * HeadCfg<32>::kPartial;
+        case 64: return (int64_t)kNumSM * HeadCfg<64>::kPartial;
+        case 128: return (int64_t)kNumSM * HeadCfg<128>::kPartial;
+        default: return -1;
+    }
+}
+
+}  // namespace geossl
+
+using namespace geossl;
+
+extern "C" {
+
+int geossl_pair_distance(const float* pos, const int64_t* sei, int64_t n_pairs, float* dist, void* stream) {
+    if (n_pairs == 0) return 0;
+    GEOSSL_REQUIRE(pos && sei && dist && n_pairs > 0, "null pointer");
+    pair_distance_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, as_stream(stream)>>>(pos, sei, n_pairs, dist);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t geossl_ddm_workspace(int H) { return head_workspace(H); }
+
+static int fill_head_in(HeadIn& in, const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+                        const float* dist, const float* noise, const int64_t* noise_level, const float* sigmas,
+                        int n_levels, float anneal_power, const geossl_ddm_params* params) {
+    if (!(h && sei && batch && dist && noise && noise_level && sigmas && params) || n_levels < 1) return GEOSSL_EINVAL;
+    const geossl_ddm_params& p = *params;
+    if (!(p.in_w0 && p.in_b0 && p.in_w1 && p.in_b1 && p.out_w0 && p.out_b0 && p.out_w1 && p.out_b1 && p.out_w2 && p.out_b2))
+        return GEOSSL_EINVAL;
+    in.h = h; in.sei = sei; in.batch = batch; in.n_pairs = n_pairs; in.dist = dist; in.noise = noise;
+    in.noise_level = noise_level; in.sigmas = sigmas; in.n_levels = n_levels; in.anneal_power = anneal_power; in.p = p;
+    return 0;
+}
+
+int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+                        const float* dist, const float* noise, const int64_t* noise_level,
+                        const float* sigmas, int n_levels, float anneal_power, int H,
+                        const geossl_ddm_params* params, float* workspace, float* loss, void* stream) {
+    GEOSSL_REQUIRE(workspace && loss && n_pairs >= 0, "null workspace/loss");
+    HeadIn in;
+    if (n_pairs == 0) {
+        GEOSSL_CUDA(cudaMemsetAsync(loss, 0, 2 * sizeof(float), as_stream(stream)));
+        return 0;
+    }
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+                   "null input pointer");
+    int rc;
+    switch (H) {
+        case 32: rc = launch_head_fwd<32>(in, workspace, loss, as_stream(stream)); break;
+        case 64: rc = launch_head_fwd<64>(in, workspace, loss, as_stream(stream)); break;
+        case 128: rc = launch_head_fwd<128>(in, workspace, loss, as_stream(stream)); break;
+        default: set_error("%s: unsupported width H=%d (32/64/128)", __func__, H); return GEOSSL_EINVAL;
+    }
+    if (rc) { set_error("%s: %s", __func__, cudaGetErrorString((cudaError_t)rc)); return rc; }
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, int64_t n_atoms,
+                        const float* dist, const float* noise, const int64_t* noise_level,
+                        const float* sigmas, int n_levels, float anneal_power, int H,
+                        const geossl_ddm_params* params, const float* loss_aux, const float* grad_loss, float* workspace,
+                        float* grad_h, const geossl_ddm_grads* grads, void* stream) {
+    GEOSSL_REQUIRE(workspace && grad_h && grads && loss_aux && grad_loss && n_pairs >= 0 && n_atoms >= 0, "null pointer");
+    const geossl_ddm_grads& g = *grads;
+    GEOSSL_REQUIRE(g.in_w0 && g.in_b0 && g.in_w1 && g.in_b1 && g.out_w0 && g.out_b0 && g.out_w1 && g.out_b1 && g.out_w2 && g.out_b2,
+                   "null gradient pointer");
+    HeadIn in;
+    GEOSSL_REQUIRE(n_pairs > 0, "n_pairs must be > 0 (caller handles the empty case)");
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+                   "null input pointer");
+    int rc;
+    switch (H) {
+        case 32: rc = launch_head_bwd<32>(in, n_atoms, loss_aux, grad_loss, workspace, grad_h, g, as_stream(stream)); break;
+        case 64: rc = launch_head_bwd<64>(in, n_atoms, loss_aux, grad_loss, workspace, grad_h, g, as_stream(stream)); break;
+        case 128: rc = launch_head_bwd<128>(in, n_atoms, loss_aux, grad_loss, workspace, grad_h, g, as_stream(stream)); break;
+        default: set_error("%s: unsupported width H=%d (32/64/128)", __func__, H); return GEOSSL_EINVAL;
+    }
+    if (rc) { set_error("%s: %s", __func__, cudaGetErrorString((cudaError_t)rc)); return rc; }
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

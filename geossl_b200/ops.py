@@ -1,0 +1,446 @@
+"""Host-side operator layer: torch tensors in, C-ABI kernel launches (geossl_b200/_lib.py) out.
+
+Everything here is plumbing -- allocation through torch's caching allocator, the current CUDA stream,
+and ``torch.autograd.Function`` wrappers that pair each forward kernel with its backward kernel.  No
+numerics happen in Python and there is no CPU path: a non-CUDA tensor raises.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import DdmPtrs, check
+
+MAX_NEIGHBORS_DEFAULT = 32      # torch_cluster.radius_graph default, never overridden (schnet.py:91)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name, dim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"geossl_b200: `{name}` must be a CUDA tensor (no CPU fallback by design)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"geossl_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise RuntimeError(f"geossl_b200: `{name}` must be {dim}-D, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+# =====================================================================================================
+# graph construction
+# =====================================================================================================
+class RadiusCSR:
+    """Destination-sorted CSR of the radius graph (+ its source-sorted transpose), int32, capacity sized.
+
+    ``rowptr[n_atoms]`` is the device-resident edge count E; ``src``/``tgt``/``dist`` have ``capacity``
+    slots of which the first E are valid.  ``edge_index`` / ``num_edges`` synchronise with the host (the
+    reference's radius_graph does too); nothing on the training path needs them.
+    """
+
+    def __init__(self, n_atoms, capacity, rowptr, src, tgt, dist, batch, graph_ptr):
+        self.n_atoms, self.capacity = n_atoms, capacity
+        self.rowptr, self.src, self.tgt, self.dist = rowptr, src, tgt, dist
+        self.batch, self.graph_ptr = batch, graph_ptr
+        self.t_rowptr = self.t_eid = self.t_tgt = None
+        self._n_edges = None
+        self._exact = None
+
+    @property
+    def n_edges_dev(self):
+        return self.rowptr[self.n_atoms:]
+
+    @property
+    def num_edges(self):
+        if self._n_edges is None:
+            self._n_edges = int(self.rowptr[self.n_atoms].item())
+            if self._n_edges > self.capacity:
+                raise RuntimeError(f"radius graph has {self._n_edges} edges but capacity is {self.capacity}")
+        return self._n_edges
+
+    @property
+    def edge_index(self):
+        """(2,E) int64 ``[source; target]`` exactly as torch_geometric.nn.radius_graph returns it."""
+        e = self.num_edges
+        out = torch.empty((2, e), dtype=torch.int64, device=self.rowptr.device)
+        check(_lib.load().geossl_csr_to_edge_index(_p(self.src), _p(self.tgt), e, _p(out), _stream()), "edge_index")
+        return out
+
+    def ensure_transpose(self):
+        if self.t_rowptr is None:
+            dev = self.rowptr.device
+            n = self.n_atoms
+            self.t_rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            self.t_eid = torch.empty(self.capacity, dtype=torch.int32, device=dev)
+            self.t_tgt = torch.empty(self.capacity, dtype=torch.int32, device=dev)
+            scratch = torch.empty(n + 2, dtype=torch.int32, device=dev)
+            check(_lib.load().geossl_csr_transpose(_p(self.rowptr), _p(self.src), _p(self.batch), _p(self.graph_ptr), n,
+                                                   _p(scratch), _p(self.t_rowptr), _p(self.t_eid), _p(self.t_tgt),
+                                                   _stream()), "csr_transpose")
+        return self
+
+    def exact(self):
+        """Copy trimmed to exactly E edges (host sync) -- used by the general double-backward path."""
+        if self._exact is None:
+            e = self.num_edges
+            self.ensure_transpose()
+            g = RadiusCSR(self.n_atoms, e, self.rowptr, self.src[:e].contiguous(), self.tgt[:e].contiguous(),
+                          None if self.dist is None else self.dist[:e].contiguous(), self.batch, self.graph_ptr)
+            g.t_rowptr, g.t_eid, g.t_tgt = self.t_rowptr, self.t_eid[:e].contiguous(), self.t_tgt[:e].contiguous()
+            g._n_edges = e
+            g._exact = g
+            self._exact = g
+        return self._exact
+
+
+def graph_ptr_from_batch(batch, num_graphs=None):
+    batch = _req(batch, torch.int64, "batch", 1)
+    n = batch.numel()
+    if num_graphs is None:
+        num_graphs = int(batch[-1].item()) + 1 if n else 0     # same sync as dataloaders_AtomTuple.py:78
+    ptr = torch.empty(num_graphs + 1, dtype=torch.int32, device=batch.device)
+    check(_lib.load().geossl_graph_ptr(_p(batch), n, num_graphs, _p(ptr), _stream()), "graph_ptr")
+    return ptr
+
+
+def radius_csr(pos, batch, r, max_num_neighbors=MAX_NEIGHBORS_DEFAULT, *, graph_ptr=None, num_graphs=None,
+               capacity=None, transpose=True):
+    """Neighbour search -> RadiusCSR (torch_cluster.radius_graph semantics, see include/geossl_b200.h)."""
+    pos = _req(pos.detach(), torch.float32, "pos", 2)
+    if pos.size(1) != 3:
+        raise RuntimeError("geossl_b200: `pos` must be (N,3)")
+    n = pos.size(0)
+    if batch is None:
+        batch = torch.zeros(n, dtype=torch.int64, device=pos.device)
+        num_graphs = 1 if n else 0
+    batch = _req(batch, torch.int64, "batch", 1)
+    if graph_ptr is None:
+        graph_ptr = graph_ptr_from_batch(batch, num_graphs)
+    graph_ptr = _req(graph_ptr, torch.int32, "graph_ptr", 1)
+    if capacity is None:
+        capacity = (max_num_neighbors + 1) * n
+    dev = pos.device
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    src = torch.empty(capacity, dtype=torch.int32, device=dev)
+    tgt = torch.empty(capacity, dtype=torch.int32, device=dev)
+    dist = torch.empty(capacity, dtype=torch.float32, device=dev)
+    scratch = torch.empty(2 * n + 2, dtype=torch.int32, device=dev)
+    check(_lib.load().geossl_radius_csr(_p(pos), _p(batch), _p(graph_ptr), n, float(r), int(max_num_neighbors),
+                                        capacity, _p(scratch), _p(rowptr), _p(src), _p(tgt), _p(dist), _stream()),
+          "radius_csr")
+    g = RadiusCSR(n, capacity, rowptr, src, tgt, dist, batch, graph_ptr)
+    if transpose:
+        g.ensure_transpose()
+    return g
+
+
+def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=MAX_NEIGHBORS_DEFAULT, flow="source_to_target"):
+    """Drop-in for ``torch_geometric.nn.radius_graph`` (the signature schnet.py:91 uses)."""
+    if loop or flow != "source_to_target":
+        raise NotImplementedError("only loop=False, flow='source_to_target' (the reference's call) is built")
+    return radius_csr(x, batch, r, max_num_neighbors, transpose=False).edge_index
+
+
+def csr_from_edge_index(edge_index, n_atoms, batch, graph_ptr=None, num_graphs=None, dist=None):
+    """RadiusCSR view of a (2,E) ``[source; target]`` list that is sorted by target with ascending sources
+    inside a target (what radius_graph emits).  Used by the stand-alone CFConv / InteractionBlock API and
+    by PaiNN's precomputed ``radius_edge_index``."""
+    edge_index = _req(edge_index, torch.int64, "edge_index", 2)
+    e = edge_index.size(1)
+    dev = edge_index.device
+    batch = _req(batch, torch.int64, "batch", 1)
+    if graph_ptr is None:
+        graph_ptr = graph_ptr_from_batch(batch, num_graphs)
+    rowptr = torch.empty(n_atoms + 1, dtype=torch.int32, device=dev)
+    check(_lib.load().geossl_rowptr_from_sorted(_p(edge_index[1].contiguous()), e, n_atoms, _p(rowptr), _stream()), "rowptr")
+    g = RadiusCSR(n_atoms, e, rowptr, edge_index[0].to(torch.int32), edge_index[1].to(torch.int32), dist, batch, graph_ptr)
+    g._n_edges = e
+    return g
+
+
+# =====================================================================================================
+# cfconv primitives (closed under differentiation: A, A^T and the edge product)
+# =====================================================================================================
+def _cfconv_fwd(x, filt, g):
+    out = torch.empty((g.n_atoms, x.size(1)), dtype=torch.float32, device=x.device)
+    check(_lib.load().geossl_cfconv_fwd(_p(x), _p(filt), _p(g.rowptr), _p(g.src), g.n_atoms, x.size(1), _p(out), _stream()),
+          "cfconv_fwd")
+    return out
+
+
+def _cfconv_bwd_x(filt, grad_out, g):
+    g.ensure_transpose()
+    dx = torch.empty((g.n_atoms, grad_out.size(1)), dtype=torch.float32, device=grad_out.device)
+    check(_lib.load().geossl_cfconv_bwd_x(_p(filt), _p(grad_out), _p(g.t_rowptr), _p(g.t_eid), _p(g.t_tgt), g.n_atoms,
+                                          grad_out.size(1), _p(dx), _stream()), "cfconv_bwd_x")
+    return dx
+
+
+def _cfconv_bwd_w(x, grad_out, g):
+    dw = torch.empty((g.capacity, x.size(1)), dtype=torch.float32, device=x.device)
+    check(_lib.load().geossl_cfconv_bwd_w(_p(x), _p(grad_out), _p(g.rowptr), _p(g.src), g.n_atoms, x.size(1), _p(dw), _stream()),
+          "cfconv_bwd_w")
+    return dw
+
+
+class CFConvAggregate(torch.autograd.Function):
+    """m_i = sum_{e in row i} x[src_e] * W_e  -- differentiable to any order (schnet.py:190,194-195)."""
+
+    @staticmethod
+    def forward(ctx, x, filt, graph):
+        x, filt = _req(x, torch.float32, "x", 2), _req(filt, torch.float32, "filt", 2)
+        ctx.graph = graph
+        ctx.save_for_backward(x, filt)
+        return _cfconv_fwd(x, filt, graph)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, filt = ctx.saved_tensors
+        gx = CFConvAggregateT.apply(filt, grad_out, ctx.graph) if ctx.needs_input_grad[0] else None
+        gw = CFConvEdgeProduct.apply(x, grad_out, ctx.graph) if ctx.needs_input_grad[1] else None
+        return gx, gw, None
+
+
+class CFConvAggregateT(torch.autograd.Function):
+    """dx_j = sum_{e: src_e = j} W_e * g[tgt_e]."""
+
+    @staticmethod
+    def forward(ctx, filt, grad_out, graph):
+        filt, grad_out = _req(filt, torch.float32, "filt", 2), _req(grad_out, torch.float32, "grad_out", 2)
+        ctx.graph = graph
+        ctx.save_for_backward(filt, grad_out)
+        return _cfconv_bwd_x(filt, grad_out, graph)
+
+    @staticmethod
+    def backward(ctx, v):
+        filt, grad_out = ctx.saved_tensors
+        gw = CFConvEdgeProduct.apply(v, grad_out, ctx.graph) if ctx.needs_input_grad[0] else None
+        gg = CFConvAggregate.apply(v, filt, ctx.graph) if ctx.needs_input_grad[1] else None
+        return gw, gg, None
+
+
+class CFConvEdgeProduct(torch.autograd.Function):
+    """dW_e = x[src_e] * g[tgt_e]  (E,F)."""
+
+    @staticmethod
+    def forward(ctx, x, grad_out, graph):
+        x, grad_out = _req(x, torch.float32, "x", 2), _req(grad_out, torch.float32, "grad_out", 2)
+        ctx.graph = graph
+        ctx.save_for_backward(x, grad_out)
+        return _cfconv_bwd_w(x, grad_out, graph)
+
+    @staticmethod
+    def backward(ctx, v):
+        x, grad_out = ctx.saved_tensors
+        gx = CFConvAggregateT.apply(v, grad_out, ctx.graph) if ctx.needs_input_grad[0] else None
+        gg = CFConvAggregate.apply(x, v, ctx.graph) if ctx.needs_input_grad[1] else None
+        return gx, gg, None
+
+
+# =====================================================================================================
+# fused interaction filter + aggregate (training fast path, first order)
+# =====================================================================================================
+def filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2):
+    """W_e (capacity,F) from the edge distances held by ``graph`` (fused rbf + filter MLP + cutoff)."""
+    F_, G = w1.size(0), w1.size(1)
+    filt = torch.empty((graph.capacity, F_), dtype=torch.float32, device=w1.device)
+    check(_lib.load().geossl_filter_fwd(_p(graph.dist), _p(graph.n_edges_dev), graph.capacity, _p(offset), float(coeff),
+                                        float(cutoff), G, F_, _p(w1), _p(b1), _p(w2), _p(b2), _p(filt), _stream()),
+          "filter_fwd")
+    return filt
+
+
+class CFConvLayer(torch.autograd.Function):
+    """x (N,F), filter-network parameters, graph -> m (N,F):  rbf -> Lin1 -> ssp -> Lin2 -> *cutoff -> cfconv.
+
+    forward  : geossl_filter_fwd + geossl_cfconv_fwd (W_e materialised once, kept for the backward)
+    backward : geossl_cfconv_bwd_x + geossl_filter_bwd (dW_e = x[src]*g[tgt] formed on the fly)
+    First-order only; force training (positions require grad) takes the composable path in SchNet.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, offset, graph, coeff, cutoff):
+        x = _req(x, torch.float32, "x", 2)
+        w1, b1, w2, b2 = (_req(t, torch.float32, n) for t, n in ((w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")))
+        offset = _req(offset, torch.float32, "offset", 1)
+        filt = filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2)
+        out = _cfconv_fwd(x, filt, graph)
+        ctx.graph, ctx.coeff, ctx.cutoff = graph, coeff, cutoff
+        ctx.save_for_backward(x, filt, w1, b1, w2, b2, offset)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        x, filt, w1, b1, w2, b2, offset = ctx.saved_tensors
+        g = ctx.graph
+        grad_out = grad_out.contiguous()
+        lib = _lib.load()
+        F_, G = w1.size(0), w1.size(1)
+        gx = _cfconv_bwd_x(filt, grad_out, g) if ctx.needs_input_grad[0] else None
+        gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
+        ws = torch.empty(lib.geossl_filter_bwd_workspace(G, F_), dtype=torch.float32, device=x.device)
+        check(lib.geossl_filter_bwd(_p(g.dist), _p(g.n_edges_dev), g.capacity, _p(offset), float(ctx.coeff),
+                                    float(ctx.cutoff), G, F_, _p(w1), _p(b1), _p(w2), _p(b2), _p(x), _p(grad_out),
+                                    _p(g.src), _p(g.tgt), None, _p(ws), _p(gw1), _p(gb1), _p(gw2), _p(gb2), _stream()),
+              "filter_bwd")
+        return gx, gw1, gb1, gw2, gb2, None, None, None, None
+
+
+# =====================================================================================================
+# DDM head
+# =====================================================================================================
+def pair_distance(pos, super_edge_index):
+    """(P,1) distances over ``super_edge_index`` (pretrain_GeoSSL.py:199-205); no gradient."""
+    pos = _req(pos.detach(), torch.float32, "pos", 2)
+    sei = _req(super_edge_index, torch.int64, "super_edge_index", 2)
+    n_pairs = sei.size(1)
+    out = torch.empty((n_pairs, 1), dtype=torch.float32, device=pos.device)
+    check(_lib.load().geossl_pair_distance(_p(pos), _p(sei), n_pairs, _p(out), _stream()), "pair_distance")
+    return out
+
+
+def _ddm_ptrs(tensors):
+    s = DdmPtrs()
+    for name, t in zip([f[0] for f in DdmPtrs._fields_], tensors):
+        setattr(s, name, t.data_ptr())
+    return s
+
+
+class DDMHead(torch.autograd.Function):
+    """NCSN_version_03.forward with the random draws supplied (NCSN.py:183-212).  Returns the scalar loss.
+    Gradients: node_feature and the ten MLP parameters (distance carries none, as in the reference)."""
+
+    @staticmethod
+    def forward(ctx, node_feature, sei, batch, dist, noise, noise_level, sigmas, anneal_power, *params):
+        h = _req(node_feature, torch.float32, "node_feature", 2)
+        sei = _req(sei, torch.int64, "super_edge_index", 2)
+        batch = _req(batch, torch.int64, "batch", 1)
+        dist = _req(dist.detach(), torch.float32, "distance").view(-1)
+        noise = _req(noise, torch.float32, "distance_noise").view(-1)
+        noise_level = _req(noise_level, torch.int64, "noise_level", 1)
+        sigmas = _req(sigmas.detach(), torch.float32, "sigmas", 1)
+        params = tuple(_req(p, torch.float32, "mlp parameter") for p in params)
+        lib = _lib.load()
+        H = h.size(1)
+        n_pairs = sei.size(1)
+        ws = torch.empty(max(lib.geossl_ddm_workspace(H), 1), dtype=torch.float32, device=h.device)
+        loss = torch.empty(2, dtype=torch.float32, device=h.device)
+        pp = _ddm_ptrs(params)
+        check(lib.geossl_ddm_head_fwd(_p(h), _p(sei), _p(batch), n_pairs, _p(dist), _p(noise), _p(noise_level), _p(sigmas),
+                                      sigmas.numel(), float(anneal_power), H, ctypes.byref(pp), _p(ws), _p(loss), _stream()),
+              "ddm_head_fwd")
+        ctx.anneal_power = float(anneal_power)
+        ctx.save_for_backward(h, sei, batch, dist, noise, noise_level, sigmas, loss, *params)
+        return loss[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss):
+        h, sei, batch, dist, noise, noise_level, sigmas, loss, *params = ctx.saved_tensors
+        lib = _lib.load()
+        H, n_pairs = h.size(1), sei.size(1)
+        grad_h = torch.empty_like(h)
+        grads = [torch.empty_like(p) for p in params]
+        if n_pairs == 0:
+            return (torch.zeros_like(h), None, None, None, None, None, None, None, *[torch.zeros_like(p) for p in params])
+        ws = torch.empty(lib.geossl_ddm_workspace(H), dtype=torch.float32, device=h.device)
+        gl = grad_loss.contiguous().view(1).to(torch.float32)
+        pp, gp = _ddm_ptrs(params), _ddm_ptrs(grads)
+        check(lib.geossl_ddm_head_bwd(_p(h), _p(sei), _p(batch), n_pairs, h.size(0), _p(dist), _p(noise), _p(noise_level),
+                                      _p(sigmas), sigmas.numel(), ctx.anneal_power, H, ctypes.byref(pp), _p(loss), _p(gl),
+                                      _p(ws), _p(grad_h), ctypes.byref(gp), _stream()), "ddm_head_bwd")
+        return (grad_h, None, None, None, None, None, None, None, *grads)
+
+
+# =====================================================================================================
+# PaiNN message block
+# =====================================================================================================
+class PaiNNEdges:
+    """Per-edge geometry of one view + the two groupings of a ``radius_edge_index`` = [idx_i; idx_j]."""
+
+    def __init__(self, structure, dist, dir_, fcut, offsets, widths):
+        self.s, self.dist, self.dir, self.fcut = structure, dist, dir_, fcut
+        self.offsets, self.widths = offsets, widths
+
+
+_structure_cache = {}
+
+
+def _painn_structure(radius_edge_index, n_atoms, batch, num_graphs):
+    """CSR by idx_j (row 1) and its grouping by idx_i, cached per edge tensor (both DDM views share it,
+    pretrain_GeoSSL.py:190-191).  Falls back to a stable sort if the list is not (idx_j, idx_i)-sorted."""
+    key = (radius_edge_index.data_ptr(), radius_edge_index._version, tuple(radius_edge_index.shape), n_atoms)
+    hit = _structure_cache.get(key)
+    if hit is not None:
+        return hit
+    rei = _req(radius_edge_index, torch.int64, "radius_edge_index", 2)
+    if rei.size(1) > 1:
+        k = rei[1] * n_atoms + rei[0]
+        if not bool((k[1:] > k[:-1]).all().item()):
+            perm = torch.sort(k, stable=True).indices
+            rei = rei[:, perm].contiguous()
+    g = csr_from_edge_index(rei, n_atoms, batch, num_graphs=num_graphs).ensure_transpose()
+    g.rei = rei
+    if len(_structure_cache) > 8:
+        _structure_cache.clear()
+    _structure_cache[key] = g
+    return g
+
+
+def painn_edges(positions, radius_edge_index, n_atoms, batch, offsets, widths, cutoff, num_graphs=None):
+    pos = _req(positions.detach(), torch.float32, "positions", 2)
+    s = _painn_structure(radius_edge_index, n_atoms, batch, num_graphs)
+    e = s.rei.size(1)
+    dev = pos.device
+    dist = torch.empty(e, dtype=torch.float32, device=dev)
+    dir_ = torch.empty((e, 3), dtype=torch.float32, device=dev)
+    fcut = torch.empty(e, dtype=torch.float32, device=dev)
+    check(_lib.load().geossl_painn_edge_geometry(_p(pos), _p(s.rei), e, float(cutoff), _p(dist), _p(dir_), _p(fcut), _stream()),
+          "painn_edge_geometry")
+    return PaiNNEdges(s, dist, dir_, fcut, _req(offsets, torch.float32, "offsets", 1), _req(widths, torch.float32, "widths", 1))
+
+
+class PaiNNMessage(torch.autograd.Function):
+    """(q, mu, ctx, filter slice) -> (q + dq, mu + dmu)   (painn.py:53-64 with the filter of :241 fused in)."""
+
+    @staticmethod
+    def forward(ctx, q, mu, x, fw, fb, edges):
+        q, mu, x = _req(q, torch.float32, "q", 2), _req(mu, torch.float32, "mu", 3), _req(x, torch.float32, "ctx", 2)
+        fw, fb = _req(fw, torch.float32, "filter_w", 2), _req(fb, torch.float32, "filter_b", 1)
+        n, Fd = q.shape
+        s = edges.s
+        q_out, mu_out = torch.empty_like(q), torch.empty_like(mu)
+        check(_lib.load().geossl_painn_message_fwd(_p(q), _p(mu), _p(x), _p(fw), _p(fb), _p(edges.offsets), _p(edges.widths),
+                                                   edges.offsets.numel(), Fd, _p(edges.dist), _p(edges.dir), _p(edges.fcut),
+                                                   _p(s.t_rowptr), _p(s.t_eid), _p(s.t_tgt), n, _p(q_out), _p(mu_out),
+                                                   _stream()), "painn_message_fwd")
+        ctx.edges = edges
+        ctx.save_for_backward(mu, x, fw, fb)
+        return q_out, mu_out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gq_out, gmu_out):
+        mu, x, fw, fb = ctx.saved_tensors
+        edges, s = ctx.edges, ctx.edges.s
+        lib = _lib.load()
+        n, Fd = gq_out.shape
+        e = s.rei.size(1)
+        R = edges.offsets.numel()
+        gq_out, gmu_out = gq_out.contiguous(), gmu_out.contiguous()
+        gx, gmu = torch.empty_like(x), torch.empty_like(mu)
+        gw, gb = torch.empty_like(fw), torch.empty_like(fb)
+        scratch = torch.empty((max(e, 1), 3 * Fd), dtype=torch.float32, device=x.device)
+        ws = torch.empty(lib.geossl_painn_workspace(R, Fd), dtype=torch.float32, device=x.device)
+        check(lib.geossl_painn_message_bwd(_p(gq_out), _p(gmu_out), _p(mu), _p(x), _p(fw), _p(fb), _p(edges.offsets),
+                                           _p(edges.widths), R, Fd, _p(edges.dist), _p(edges.dir), _p(edges.fcut),
+                                           _p(s.rowptr), _p(s.src), n, e, _p(gx), _p(gmu), _p(scratch), _p(ws), _p(gw), _p(gb),
+                                           _stream()), "painn_message_bwd")
+        return gq_out, gmu, gx, gw, gb, None

@@ -1,0 +1,197 @@
+/*
+ * geossl_b200.h -- C ABI of libgeossl_b200.so: the sm_100a kernels behind the GeoSSL-DDM
+ * pretraining hot path (SchNet / PaiNN encoder fwd+bwd, DDM score loss).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked (host);
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work (no host sync);
+ *   - node/edge features are row-major fp32; reference-facing indices arrive as int64 (PyG
+ *     convention, schnet.py:86) and the internal CSR is int32;
+ *   - edge / pair counts that are data dependent live in device memory (`n_edges_dev` is usually
+ *     `rowptr + n_atoms`), buffers are sized at a host-known capacity, so a whole training step can be
+ *     captured in a CUDA graph;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative GEOSSL_E* argument error.
+ *     geossl_last_error() returns a thread-local message for the last failing call.
+ *
+ * Each entry cites the reference interface (file:line under chao1224/GeoSSL) it replaces.
+ */
+#ifndef GEOSSL_B200_H
+#define GEOSSL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEOSSL_ABI_VERSION 1
+#define GEOSSL_EINVAL (-1)   /* bad argument (null pointer, unsupported width, ...) */
+#define GEOSSL_ECAP   (-2)   /* capacity too small */
+
+int geossl_abi_version(void);
+const char* geossl_last_error(void);
+/* Number of kernel launches issued through this library by the calling process (bench.py's
+ * "gpu_launches" evidence).  reset: non-zero zeroes the counter after reading. */
+int64_t geossl_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph construction.  Replaces torch_cluster.radius_graph as called at Geom3D/models/schnet.py:91
+ * (every forward) and Geom3D/datasets/datasets_3D_Radius.py:120 (PaiNN, dataset time).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* graph_ptr[g] = first atom of graph g, graph_ptr[n_graphs] = n_atoms, from the sorted `batch`
+ * vector (dataloaders_AtomTuple.py:55,72).  Empty graphs are allowed. */
+int geossl_graph_ptr(const int64_t* batch, int64_t n_atoms, int64_t n_graphs, int32_t* graph_ptr, void* stream);
+
+/* Destination-sorted CSR of the fixed-radius graph with torch_cluster's semantics: candidates of the
+ * same graph scanned in ascending atom index, dist = ((dx*dx)+dy*dy)+dz*dz in fp32 without FMA, keep
+ * if dist < r*r, stop after max_num_neighbors+1 hits (self included), self removed.
+ *   rowptr (n_atoms+1) int32, rowptr[n_atoms] = E;  src (capacity) int32 ascending within a row;
+ *   edge_tgt (capacity) int32 = row of each edge;  edge_dist (capacity) fp32 = ||pos[src]-pos[tgt]||
+ *   (schnet.py:92-93), may be NULL.  capacity >= E is required; (max_num_neighbors+1)*n_atoms always
+ *   suffices.  scratch: (2*n_atoms + 2) int32. */
+int geossl_radius_csr(const float* pos, const int64_t* batch, const int32_t* graph_ptr, int64_t n_atoms,
+                      float r, int max_num_neighbors, int64_t capacity, int32_t* scratch,
+                      int32_t* rowptr, int32_t* src, int32_t* edge_tgt, float* edge_dist, void* stream);
+
+/* (2,E) int64 `edge_index` = [source; target] exactly as radius_graph returns it (host already knows E). */
+int geossl_csr_to_edge_index(const int32_t* src, const int32_t* edge_tgt, int64_t n_edges,
+                             int64_t* edge_index, void* stream);
+
+/* Source-sorted view of a destination-sorted CSR whose rows have ascending sources and whose graphs
+ * occupy contiguous rows (what geossl_radius_csr / radius_graph emit):
+ *   t_rowptr (n_atoms+1), t_eid (capacity) = edge ids grouped by source, ascending target within a
+ *   source, t_tgt (capacity) = target of each of those edges.  Deterministic, atomic free. */
+int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_t* batch,
+                         const int32_t* graph_ptr, int64_t n_atoms, int32_t* scratch,
+                         int32_t* t_rowptr, int32_t* t_eid, int32_t* t_tgt, void* stream);
+
+/* rowptr from a SORTED int64 key vector (row 1 of a radius_edge_index), keys in [0,n_rows). */
+int geossl_rowptr_from_sorted(const int64_t* keys, int64_t n_keys, int64_t n_rows, int32_t* rowptr, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SchNet continuous-filter convolution.  Replaces GaussianSmearing.forward (schnet.py:205-207),
+ * the filter network + cosine cutoff of CFConv.forward (schnet.py:141-145,186-187) and
+ * MessagePassing.propagate/message (schnet.py:190,194-195; torch_scatter atomics) and their autograd.
+ * F = num_filters in {32,64,128}; G = num_gaussians <= 64.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* W_e = (Lin2(ssp(Lin1(rbf(d_e))))) * 0.5*(cos(d_e*pi/cutoff)+1)   -> filt (E,F)
+ * w1 (F,G), b1 (F), w2 (F,F), b2 (F) are nn.Linear layouts (out,in). */
+int geossl_filter_fwd(const float* edge_dist, const int32_t* n_edges_dev, int64_t capacity,
+                      const float* offset, float coeff, float cutoff, int G, int F,
+                      const float* w1, const float* b1, const float* w2, const float* b2,
+                      float* filt, void* stream);
+
+/* m_i = sum_{e in row i} x[src_e] * W_e   (atomic-free segmented reduction, one warp per row). */
+int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* rowptr, const int32_t* src,
+                      int64_t n_atoms, int F, float* out, void* stream);
+
+/* dx_j = sum_{e: src_e = j} W_e * g[tgt_e]   over the source-sorted view. */
+int geossl_cfconv_bwd_x(const float* filt, const float* grad_out, const int32_t* t_rowptr, const int32_t* t_eid,
+                        const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream);
+
+/* dW_e = x[src_e] * g[tgt_e]  materialised (E,F)  (second-order path and the unfused comparison). */
+int geossl_cfconv_bwd_w(const float* x, const float* grad_out, const int32_t* rowptr, const int32_t* src,
+                        int64_t n_atoms, int F, float* grad_filt, void* stream);
+
+/* Backward of the filter network fused with dW_e = x[src_e]*g[tgt_e] (never materialised):
+ * recomputes rbf / Lin1 / ssp from d_e and accumulates gw1 (F,G), gb1 (F), gw2 (F,F), gb2 (F).
+ * If grad_filt != NULL it is used as dW_e instead of x/g (then x, grad_out, src, edge_tgt may be NULL).
+ * workspace: geossl_filter_bwd_workspace floats.  The gradient outputs are OVERWRITTEN (not accumulated).
+ * (Force training, finetune_md17.py:46, differentiates through the geometry and uses the composable
+ * primitives geossl_filter_fwd / geossl_cfconv_* from the host-side double-backward path instead.) */
+int64_t geossl_filter_bwd_workspace(int G, int F);
+int geossl_filter_bwd(const float* edge_dist, const int32_t* n_edges_dev, int64_t capacity,
+                      const float* offset, float coeff, float cutoff, int G, int F,
+                      const float* w1, const float* b1, const float* w2, const float* b2,
+                      const float* x, const float* grad_out, const int32_t* src, const int32_t* edge_tgt,
+                      const float* grad_filt, float* workspace,
+                      float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DDM head.  Replaces the distance block of do_DDM (examples/pretrain_GeoSSL.py:197-205) and
+ * NCSN_version_03.forward (examples/NCSN.py:183-212) + MultiLayerPerceptron (NCSN.py:9-43) and their
+ * autograd.  H = emb_dim in {32,64,128}.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* d_p = sqrt(sum((pos[u_p]-pos[v_p])^2))  (P,) ; sei = super_edge_index (2,P) int64. */
+int geossl_pair_distance(const float* pos, const int64_t* sei, int64_t n_pairs, float* dist, void* stream);
+
+typedef struct {
+    const float* in_w0;  /* input_distance_mlp.layers.0.weight (H,1) */
+    const float* in_b0;  /* (H) */
+    const float* in_w1;  /* input_distance_mlp.layers.1.weight (1,H) */
+    const float* in_b1;  /* (1) */
+    const float* out_w0; /* output_mlp.layers.0.weight (H,H+1) */
+    const float* out_b0; /* (H) */
+    const float* out_w1; /* output_mlp.layers.1.weight (H/2,H) */
+    const float* out_b1; /* (H/2) */
+    const float* out_w2; /* output_mlp.layers.2.weight (1,H/2) */
+    const float* out_b2; /* (1) */
+} geossl_ddm_params;
+
+typedef struct {
+    float* in_w0; float* in_b0; float* in_w1; float* in_b1;
+    float* out_w0; float* out_b0; float* out_w1; float* out_b1; float* out_w2; float* out_b2;
+} geossl_ddm_grads;
+
+/* loss (1,) = mean over graphs of sum_p 0.5*(score_p - target_p)^2 * sigma_p^anneal_power with the
+ * noise level (per graph) and the N(0,1) draw (per pair) supplied by the caller (RNG contract,
+ * NCSN.py:190,194).  The mean is over max_p(batch[u_p])+1 graphs (torch_scatter dim_size).
+ * workspace: geossl_ddm_workspace(H) floats. */
+int64_t geossl_ddm_workspace(int H);
+int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+                        const float* dist, const float* noise, const int64_t* noise_level,
+                        const float* sigmas, int n_levels, float anneal_power, int H,
+                        const geossl_ddm_params* params /*host*/, float* workspace, float* loss /*(2,): loss, #graphs*/,
+                        void* stream);
+
+/* Backward: grad_h (n_atoms,H) is ZEROED then accumulated; parameter gradients are overwritten.
+ * grad_loss is the (1,) upstream gradient on the device. */
+int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, int64_t n_atoms,
+                        const float* dist, const float* noise, const int64_t* noise_level,
+                        const float* sigmas, int n_levels, float anneal_power, int H,
+                        const geossl_ddm_params* params /*host*/, const float* loss_aux /*(2,) from fwd*/,
+                        const float* grad_loss, float* workspace,
+                        float* grad_h, const geossl_ddm_grads* grads /*host*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PaiNN message block.  Replaces the per-edge part of PaiNN.forward (Geom3D/models/painn.py:232-245:
+ * r_ij, d_ij, dir_ij, GaussianRBF painn_utils.py:99-103, CosineCutoff painn_utils.py:152-155,
+ * filter_net * fcut) and PaiNNInteraction.forward's gather / Wij*xj / split / index_add (painn.py:53-64).
+ * F = n_atom_basis in {32,64,128}; n_rbf <= 32.  The (E,3F) filter is rebuilt per edge, never stored.
+ * Edge order: radius_edge_index (2,E) = [idx_i; idx_j] sorted by idx_j (row 1), idx_i ascending inside.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dist (E), dir (E,3) = (pos[idx_i]-pos[idx_j])/d, fcut (E) = 0.5(cos(d*pi/rc)+1)*[d<rc]. */
+int geossl_painn_edge_geometry(const float* pos, const int64_t* radius_edge_index, int64_t n_edges, float cutoff,
+                               float* dist, float* dir, float* fcut, void* stream);
+
+/* q_out = q + sum_{e: idx_i=n} W_e[0:F]*ctx[j][0:F];
+ * mu_out = mu + sum_e ( W_e[F:2F]*ctx[j][F:2F] * dir_e + W_e[2F:3F]*ctx[j][2F:3F] * mu[j] ),
+ * W_e = (rbf(d_e) filter_w^T + filter_b) * fcut_e with filter_w (3F,n_rbf) the interaction's slice of
+ * filter_net.weight.  ctx (N,3F) = interatomic_context_net(q); mu (N,3,F).
+ * (i_rowptr, i_eid, i_nbr): edges grouped by idx_i -- edge id and idx_j of each. */
+int geossl_painn_message_fwd(const float* q, const float* mu, const float* ctx, const float* filter_w, const float* filter_b,
+                             const float* offsets, const float* widths, int n_rbf, int F,
+                             const float* dist, const float* dir, const float* fcut,
+                             const int32_t* i_rowptr, const int32_t* i_eid, const int32_t* i_nbr, int64_t n_atoms,
+                             float* q_out, float* mu_out, void* stream);
+
+/* Backward.  (j_rowptr, j_ctr): rowptr over the idx_j-sorted edge list and idx_i of each edge (int32).
+ * Outputs: grad_ctx (N,3F), grad_mu_in (N,3,F) (includes the identity path), grad_filter_w (3F,n_rbf),
+ * grad_filter_b (3F); dL/dq_in is grad_q_out itself.  edge_scratch: (E,3F) floats; workspace:
+ * geossl_painn_workspace floats.  Positions receive no gradient (DDM pretraining does not need it). */
+int64_t geossl_painn_workspace(int n_rbf, int F);
+int geossl_painn_message_bwd(const float* grad_q_out, const float* grad_mu_out, const float* mu, const float* ctx,
+                             const float* filter_w, const float* filter_b, const float* offsets, const float* widths,
+                             int n_rbf, int F, const float* dist, const float* dir, const float* fcut,
+                             const int32_t* j_rowptr, const int32_t* j_ctr, int64_t n_atoms, int64_t n_edges,
+                             float* grad_ctx, float* grad_mu_in, float* edge_scratch, float* workspace,
+                             float* grad_filter_w, float* grad_filter_b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOSSL_B200_H */

@@ -1,0 +1,121 @@
+"""CPU: host-side logic -- drop-in module surface (state_dict keys, seeded init bit-identical to the
+reference's), the AtomTuple batch contract, and the data-parallel gradient exchange on gloo (world size 2)."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from _build import full_sd
+from _golden import Golden
+from geossl_b200.data import pair_count, super_edges_host, synthetic_batch
+
+
+def _same(sd_a, sd_b):
+    assert sorted(sd_a) == sorted(sd_b)
+    for k in sd_a:
+        assert sd_a[k].dtype == sd_b[k].dtype and sd_a[k].shape == sd_b[k].shape, k
+        if k != "atomic_mass":
+            assert torch.equal(sd_a[k], sd_b[k]), k
+
+
+@pytest.mark.parametrize("name", ["schnet_small", "schnet_trunc"])
+def test_schnet_seeded_init_matches_reference(name):
+    from geossl_b200.Geom3D.models import SchNet
+    g = Golden(name)
+    c = g.cfg
+    torch.manual_seed(c["seed"])
+    m = SchNet(hidden_channels=c["hidden"], num_filters=c["filters"], num_interactions=c["layers"],
+               num_gaussians=c["gaussians"], cutoff=c["cutoff"], node_class=9, readout=c["readout"])
+    _same(m.state_dict(), full_sd(g.sd()))
+    assert m.state_dict()["atomic_mass"].dtype == torch.float64 and m.state_dict()["atomic_mass"].numel() == 119
+    # quirk kept: mlp[2].bias is NOT zeroed (schnet.py:155-158)
+    assert m.interactions[0].mlp[2].bias.abs().max() > 0 and m.interactions[0].mlp[0].bias.abs().max() == 0
+    assert m.interactions[0].conv.nn[0].weight is m.interactions[0].mlp[0].weight
+
+
+@pytest.mark.parametrize("name", ["painn_small", "painn_full"])
+def test_painn_seeded_init_matches_reference(name):
+    from geossl_b200.Geom3D.models import PaiNN
+    g = Golden(name)
+    c = g.cfg
+    torch.manual_seed(c["seed"])
+    m = PaiNN(n_atom_basis=c["feat"], n_interactions=c["layers"], n_rbf=c["rbf"], cutoff=c["cutoff"], max_z=9, n_out=1,
+              readout=c["readout"])
+    _same(m.state_dict(), g.sd())
+    assert m.embedding.weight[0].abs().max() == 0       # padding_idx=0 (painn.py:174)
+
+
+def test_ncsn_seeded_init_and_sigma_schedule():
+    from geossl_b200.NCSN import NCSN_version_03
+    g = Golden("ncsn_h128")
+    c = g.cfg
+    torch.manual_seed(c["seed"])
+    m = NCSN_version_03(c["emb"], sigma_begin=10, sigma_end=0.01, num_noise_level=c["levels"], noise_type="symmetry",
+                        anneal_power=c["anneal_power"])
+    _same(m.state_dict(), g.sd())
+    assert not m.sigmas.requires_grad and "sigmas" in dict(m.named_parameters())   # frozen nn.Parameter (NCSN.py:179)
+
+
+def test_super_edges_match_itertools():
+    counts = [1, 2, 5, 0, 7, 3]
+    for option, gen in (("combination", itertools.combinations), ("permutation", itertools.permutations)):
+        sei = super_edges_host(counts, option)
+        ref, off = [], 0
+        for n in counts:
+            if n >= 2:
+                ref.append(np.array(list(gen(np.arange(n), 2))).T + off)
+            off += n
+        assert torch.equal(sei, torch.from_numpy(np.concatenate(ref, axis=1)))
+        assert sei.shape[1] == int(pair_count(counts, option).sum())
+
+
+def test_synthetic_batch_contract():
+    b = synthetic_batch(8, 10, 20, seed=3)
+    n = b.positions.shape[0]
+    assert b.x.shape == (n, 2) and b.x.dtype == torch.int64 and b.positions.dtype == torch.float32
+    assert b.batch.dtype == torch.int64 and bool((b.batch[1:] >= b.batch[:-1]).all())
+    assert b.num_graphs == 8 and int(b.x[:, 0].max()) <= 8
+    assert bool((b.batch[b.super_edge_index[0]] == b.batch[b.super_edge_index[1]]).all())
+    assert int(b.graph_ptr[-1]) == n
+
+
+def _dp_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    from geossl_b200.pretrain import FlatGradAllReduce, broadcast_parameters
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # different init per rank ...
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    broadcast_parameters([model])                       # ... made identical by the broadcast
+    sync = FlatGradAllReduce(model.parameters())
+    torch.manual_seed(7)
+    x = torch.randn(8, 6)
+    shard = x[rank * 4:(rank + 1) * 4]                  # equal shards => mean of means == global mean
+    model(shard).pow(2).mean().backward()
+    sync()
+    torch.save({"grads": [p.grad.clone() for p in model.parameters()],
+                "params": [p.detach().clone() for p in model.parameters()]}, os.path.join(tmp, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_gloo_world2(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    for a, b in zip(r0["params"], r1["params"]):
+        assert torch.equal(a, b)
+    for a, b in zip(r0["grads"], r1["grads"]):
+        assert torch.equal(a, b)
+    # single-process reference on the full batch
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    with torch.no_grad():
+        for p, v in zip(model.parameters(), r0["params"]):
+            p.copy_(v)
+    torch.manual_seed(7)
+    x = torch.randn(8, 6)
+    model(x).pow(2).mean().backward()
+    for p, gsync in zip(model.parameters(), r0["grads"]):
+        assert torch.allclose(p.grad, gsync, rtol=1e-5, atol=1e-7)
