@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- GeoSSL-DDM SchNet pretraining throughput (molecules/s) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # product arm (CUDA kernels via the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+A "step" is one full pretraining iteration of BASELINE.json configs[1] on one synthetic batch per GPU:
+perturb -> SchNet encoder x2 (radius graph, 6 interactions) -> two DDM heads -> backward -> gradient
+all-reduce (N>1) -> Adam.  Prints ONE JSON line (contract in the task statement / DESIGN.md section 6).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+METRIC = "GeoSSL-DDM SchNet train molecules/s at 1/2/4/8 B200; cfconv % HBM roofline"
+CFG = dict(batch_per_gpu=256, atoms=30, cutoff=10.0, num_gaussians=50, hidden=128, filters=128, interactions=6,
+           sigma_levels=50, anneal_power=2.0, pos_sigma=0.3, lr=5e-4)
+WORKLOAD = ("configs[1]: SchNet GeoSSL-DDM pretraining step, synthetic Molecule3D-shaped conformers, "
+            "batch 256 per GPU x 30 atoms, cutoff 10 A, 50 RBF, hidden 128, 6 interactions, data-parallel")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="geossl_b200", choices=["geossl_b200", "reference"])
+    ap.add_argument("--pool", type=int, default=8, help="distinct synthetic batches cycled through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timers", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(steps, warmup, sample_graphs=32, threads=None):
+    """The reference's CPU path (oracle port of schnet.py / NCSN.py / do_DDM, same torch ops) on a bounded sample."""
+    from oracle import models as O
+    from geossl_b200.data import synthetic_batch
+    from geossl_b200.Geom3D.models import SchNet
+    from geossl_b200.NCSN import NCSN_version_03
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    model = SchNet(hidden_channels=CFG["hidden"], num_filters=CFG["filters"], num_interactions=CFG["interactions"],
+                   num_gaussians=CFG["num_gaussians"], cutoff=CFG["cutoff"], node_class=9)
+    heads = [NCSN_version_03(CFG["hidden"], 10, 0.01, CFG["sigma_levels"], "symmetry", CFG["anneal_power"]) for _ in range(2)]
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and v.dtype == torch.float32) for k, v in model.state_dict().items()}
+    sdh = [{k: v.clone().requires_grad_(k != "sigmas") for k, v in h.state_dict().items()} for h in heads]
+    leaves = [v for v in sd.values() if v.requires_grad] + [v for d in sdh for v in d.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=CFG["lr"])
+    times = []
+    for it in range(warmup + steps):
+        b = synthetic_batch(sample_graphs, CFG["atoms"], seed=1000 + it)
+        t0 = time.perf_counter()
+        _, pos2 = O.perturb(None, b.positions, 0.0, CFG["pos_sigma"])
+        enc = lambda z, p: O.schnet_forward(sd, z, p, b.batch, cutoff=CFG["cutoff"])[1]
+        n_pairs = b.super_edge_index.shape[1]
+        draws = [(torch.randint(0, CFG["sigma_levels"], (sample_graphs,)), torch.randn(n_pairs, 1)) for _ in range(2)]
+        loss, _ = O.ddm_loss(enc, sdh[0], sdh[1], b.x[:, 0], b.positions, pos2, b.batch, b.super_edge_index, draws[0], draws[1],
+                             CFG["anneal_power"])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        float(loss.detach())
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": sample_graphs * len(times) / total, "unit": "molecules/s", "cores": threads, "kind": "port",
+            "sample": f"{len(times)} steps x {sample_graphs} molecules x {CFG['atoms']} atoms of the same workload "
+                      f"(oracle/models.py, torch CPU fp32, {warmup} warm-up)",
+            "ms_per_step": 1e3 * total / len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 8), min(args.warmup, 1)
+    cb = cpu_reference(steps, max(warmup, 1))
+    line = {"metric": METRIC, "value": cb["value"], "unit": "molecules/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(warmup, 1),
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, **CFG, "device": "host CPU"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- product arm
+def run_product(args):
+    import torch.distributed as dist
+    from geossl_b200 import _lib, ops
+    from geossl_b200.Geom3D.models import SchNet
+    from geossl_b200.NCSN import NCSN_version_03
+    from geossl_b200.data import synthetic_batch
+    from geossl_b200.pretrain import FlatGradAllReduce, broadcast_parameters, default_args, train_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- geossl_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    torch.manual_seed(42)
+    model = SchNet(hidden_channels=CFG["hidden"], num_filters=CFG["filters"], num_interactions=CFG["interactions"],
+                   num_gaussians=CFG["num_gaussians"], cutoff=CFG["cutoff"], node_class=9).to(dev)
+    heads = [NCSN_version_03(CFG["hidden"], 10, 0.01, CFG["sigma_levels"], "symmetry", CFG["anneal_power"]).to(dev) for _ in range(2)]
+    broadcast_parameters([model] + heads)
+    groups = [{"params": model.parameters()}] + [{"params": [p for p in h.parameters() if p.requires_grad]} for h in heads]
+    opt = torch.optim.Adam(groups, lr=CFG["lr"], fused=True)
+    sync = FlatGradAllReduce([p for g in groups for p in g["params"]]) if world > 1 else None
+    targs = default_args("schnet")
+    torch.manual_seed(1234 + rank)
+
+    B = CFG["batch_per_gpu"]
+    host_pool = [synthetic_batch(B, CFG["atoms"], seed=10_000 * rank + i).pin_memory() for i in range(args.pool)]
+    dev_pool = [b.to(dev) for b in host_pool]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (host_pool[0].x, host_pool[0].positions, host_pool[0].batch,
+                                                           host_pool[0].super_edge_index))
+
+    def step(batch):
+        return train_step(targs, batch, model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync, device_noise=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(n):
+            fn(i)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up (allocator, cuBLAS handles, kernel attribute setup)
+    for i in range(max(args.warmup, 3)):
+        step(dev_pool[i % args.pool])
+    barrier()
+
+    # ---- (1) device-resident throughput + clocks + per-kernel timers
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if not args.no_kernel_timers:
+        ops.KERNEL_TIMERS.enable(("cfconv_fwd", "filter_fwd", "filter_bwd", "cfconv_bwd_x", "ddm_head_fwd", "ddm_head_bwd"))
+    _lib.launch_count(reset=True)
+    ms = timed(lambda i: step(dev_pool[i % args.pool]), args.steps)
+    launches = _lib.launch_count()
+    ktimes = ops.KERNEL_TIMERS.collect() if not args.no_kernel_timers else {}
+    ops.KERNEL_TIMERS.disable()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- (2) end to end: host (pinned) batches -> H2D every step -> step -> D2H loss every step
+    sink = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        b = host_pool[i % args.pool].to(dev, non_blocking=True)
+        loss = step(b)
+        sink.copy_(loss.view(1), non_blocking=False)
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the cfconv forward kernel (BASELINE metric) + the other hot kernels
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    pk = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = {**json.load(open(pk)), "src": "measured"}
+    b0 = dev_pool[0]
+    g = ops.radius_csr(b0.positions, b0.batch, CFG["cutoff"], num_graphs=B)
+    n_atoms, n_edges, F_, G = b0.positions.shape[0], g.num_edges, CFG["filters"], CFG["num_gaussians"]
+    n_pairs = b0.super_edge_index.shape[1]
+    cf_bytes = 4 * F_ * n_edges + 2 * 4 * F_ * n_atoms + 4 * n_edges + 4 * (n_atoms + 1)
+    roof = None
+    others = {}
+    if "cfconv_fwd" in ktimes:
+        t = ktimes["cfconv_fwd"]["mean_ms"] / 1e3
+        ach = cf_bytes / t / 1e9
+        roof = {"kernel": "cfconv_fwd_kernel<128,4>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"],
+                "algorithmic_bytes_per_launch": cf_bytes, "mean_ms": 1e3 * t, "launches_timed": ktimes["cfconv_fwd"]["n"]}
+        flops = {"filter_fwd": n_edges * (2 * G * F_ + 2 * F_ * F_),
+                 "filter_bwd": n_edges * (2 * G * F_ + 2 * (2 * F_ * F_) + 2 * G * F_ + 2 * F_ * F_),
+                 "ddm_head_fwd": n_pairs * 50_048, "ddm_head_bwd": n_pairs * 3 * 50_048}
+        for k, fl in flops.items():
+            if k in ktimes:
+                tt = ktimes[k]["mean_ms"] / 1e3
+                others[k] = {"bound": "tensor", "achieved": fl / tt / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": fl / tt / 1e12 / peaks["bf16_tflops_sustained"], "mean_ms": 1e3 * tt,
+                             "share_of_step": ktimes[k]["total_ms"] / ms, "note": "fp32 SIMT kernel against the bf16 tensor peak"}
+        if "cfconv_bwd_x" in ktimes:
+            tt = ktimes["cfconv_bwd_x"]["mean_ms"] / 1e3
+            bb = 4 * F_ * n_edges + 2 * 4 * F_ * n_atoms + 8 * n_edges + 4 * (n_atoms + 1)
+            others["cfconv_bwd_x"] = {"bound": "hbm", "achieved": bb / tt / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                      "frac": bb / tt / 1e9 / peaks["hbm_gbs"], "mean_ms": 1e3 * tt,
+                                      "share_of_step": ktimes["cfconv_bwd_x"]["total_ms"] / ms}
+        roof["share_of_step"] = ktimes["cfconv_fwd"]["total_ms"] / ms
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cb = cpu_reference(4, 1)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, **CFG, "global_batch": world * B, "atoms_per_batch": n_atoms, "edges_per_view": n_edges,
+                       "pairs": n_pairs, "parallelism": f"dp{world}", "optimizer": "torch.optim.Adam(fused)",
+                       "l2": f"{args.pool} distinct batches cycled; per-step working set (12 x {4 * F_ * n_edges / 1e6:.0f} MB filter "
+                             "tensors) exceeds the 126 MB L2", "position_noise": "device generator"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roof, "roofline_other_kernels": others, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_product(a)

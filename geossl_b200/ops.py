@@ -15,6 +15,48 @@ from ._lib import DdmPtrs, check
 MAX_NEIGHBORS_DEFAULT = 32      # torch_cluster.radius_graph default, never overridden (schnet.py:91)
 
 
+class _KernelTimers:
+    """Optional CUDA-event brackets around named C-ABI calls (bench.py's live per-kernel durations).
+    Events are recorded on torch's current stream, which is the stream every kernel here is launched on."""
+
+    def __init__(self):
+        self.names, self.events = frozenset(), {}
+
+    def enable(self, names):
+        self.names, self.events = frozenset(names), {}
+
+    def disable(self):
+        self.names = frozenset()
+
+    def start(self, name):
+        if name not in self.names:
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        self.events.setdefault(name, []).append((a, b))
+        return b
+
+    def collect(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, pairs in self.events.items():
+            ts = [a.elapsed_time(b) for a, b in pairs]
+            out[name] = {"n": len(ts), "total_ms": sum(ts), "mean_ms": sum(ts) / max(len(ts), 1)}
+        return out
+
+
+KERNEL_TIMERS = _KernelTimers()
+
+
+def _timed(name, rc_fn):
+    """Run ``rc_fn()`` (a C-ABI call returning rc) between two events if ``name`` is being timed."""
+    end = KERNEL_TIMERS.start(name) if KERNEL_TIMERS.names else None
+    rc = rc_fn()
+    if end is not None:
+        end.record()
+    check(rc, name)
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -169,16 +211,16 @@ def csr_from_edge_index(edge_index, n_atoms, batch, graph_ptr=None, num_graphs=N
 # =====================================================================================================
 def _cfconv_fwd(x, filt, g):
     out = torch.empty((g.n_atoms, x.size(1)), dtype=torch.float32, device=x.device)
-    check(_lib.load().geossl_cfconv_fwd(_p(x), _p(filt), _p(g.rowptr), _p(g.src), g.n_atoms, x.size(1), _p(out), _stream()),
-          "cfconv_fwd")
+    _timed("cfconv_fwd", lambda: _lib.load().geossl_cfconv_fwd(_p(x), _p(filt), _p(g.rowptr), _p(g.src), g.n_atoms, x.size(1),
+                                                               _p(out), _stream()))
     return out
 
 
 def _cfconv_bwd_x(filt, grad_out, g):
     g.ensure_transpose()
     dx = torch.empty((g.n_atoms, grad_out.size(1)), dtype=torch.float32, device=grad_out.device)
-    check(_lib.load().geossl_cfconv_bwd_x(_p(filt), _p(grad_out), _p(g.t_rowptr), _p(g.t_eid), _p(g.t_tgt), g.n_atoms,
-                                          grad_out.size(1), _p(dx), _stream()), "cfconv_bwd_x")
+    _timed("cfconv_bwd_x", lambda: _lib.load().geossl_cfconv_bwd_x(_p(filt), _p(grad_out), _p(g.t_rowptr), _p(g.t_eid),
+                                                                   _p(g.t_tgt), g.n_atoms, grad_out.size(1), _p(dx), _stream()))
     return dx
 
 
@@ -250,9 +292,9 @@ def filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2):
     """W_e (capacity,F) from the edge distances held by ``graph`` (fused rbf + filter MLP + cutoff)."""
     F_, G = w1.size(0), w1.size(1)
     filt = torch.empty((graph.capacity, F_), dtype=torch.float32, device=w1.device)
-    check(_lib.load().geossl_filter_fwd(_p(graph.dist), _p(graph.n_edges_dev), graph.capacity, _p(offset), float(coeff),
-                                        float(cutoff), G, F_, _p(w1), _p(b1), _p(w2), _p(b2), _p(filt), _stream()),
-          "filter_fwd")
+    _timed("filter_fwd", lambda: _lib.load().geossl_filter_fwd(_p(graph.dist), _p(graph.n_edges_dev), graph.capacity, _p(offset),
+                                                               float(coeff), float(cutoff), G, F_, _p(w1), _p(b1), _p(w2), _p(b2),
+                                                               _p(filt), _stream()))
     return filt
 
 
@@ -286,10 +328,9 @@ class CFConvLayer(torch.autograd.Function):
         gx = _cfconv_bwd_x(filt, grad_out, g) if ctx.needs_input_grad[0] else None
         gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
         ws = torch.empty(lib.geossl_filter_bwd_workspace(G, F_), dtype=torch.float32, device=x.device)
-        check(lib.geossl_filter_bwd(_p(g.dist), _p(g.n_edges_dev), g.capacity, _p(offset), float(ctx.coeff),
-                                    float(ctx.cutoff), G, F_, _p(w1), _p(b1), _p(w2), _p(b2), _p(x), _p(grad_out),
-                                    _p(g.src), _p(g.tgt), None, _p(ws), _p(gw1), _p(gb1), _p(gw2), _p(gb2), _stream()),
-              "filter_bwd")
+        _timed("filter_bwd", lambda: lib.geossl_filter_bwd(
+            _p(g.dist), _p(g.n_edges_dev), g.capacity, _p(offset), float(ctx.coeff), float(ctx.cutoff), G, F_, _p(w1), _p(b1),
+            _p(w2), _p(b2), _p(x), _p(grad_out), _p(g.src), _p(g.tgt), None, _p(ws), _p(gw1), _p(gb1), _p(gw2), _p(gb2), _stream()))
         return gx, gw1, gb1, gw2, gb2, None, None, None, None
 
 
@@ -333,9 +374,9 @@ class DDMHead(torch.autograd.Function):
         ws = torch.empty(max(lib.geossl_ddm_workspace(H), 1), dtype=torch.float32, device=h.device)
         loss = torch.empty(2, dtype=torch.float32, device=h.device)
         pp = _ddm_ptrs(params)
-        check(lib.geossl_ddm_head_fwd(_p(h), _p(sei), _p(batch), n_pairs, _p(dist), _p(noise), _p(noise_level), _p(sigmas),
-                                      sigmas.numel(), float(anneal_power), H, ctypes.byref(pp), _p(ws), _p(loss), _stream()),
-              "ddm_head_fwd")
+        _timed("ddm_head_fwd", lambda: lib.geossl_ddm_head_fwd(
+            _p(h), _p(sei), _p(batch), n_pairs, _p(dist), _p(noise), _p(noise_level), _p(sigmas), sigmas.numel(),
+            float(anneal_power), H, ctypes.byref(pp), _p(ws), _p(loss), _stream()))
         ctx.anneal_power = float(anneal_power)
         ctx.save_for_backward(h, sei, batch, dist, noise, noise_level, sigmas, loss, *params)
         return loss[0]
@@ -353,9 +394,9 @@ class DDMHead(torch.autograd.Function):
         ws = torch.empty(lib.geossl_ddm_workspace(H), dtype=torch.float32, device=h.device)
         gl = grad_loss.contiguous().view(1).to(torch.float32)
         pp, gp = _ddm_ptrs(params), _ddm_ptrs(grads)
-        check(lib.geossl_ddm_head_bwd(_p(h), _p(sei), _p(batch), n_pairs, h.size(0), _p(dist), _p(noise), _p(noise_level),
-                                      _p(sigmas), sigmas.numel(), ctx.anneal_power, H, ctypes.byref(pp), _p(loss), _p(gl),
-                                      _p(ws), _p(grad_h), ctypes.byref(gp), _stream()), "ddm_head_bwd")
+        _timed("ddm_head_bwd", lambda: lib.geossl_ddm_head_bwd(
+            _p(h), _p(sei), _p(batch), n_pairs, h.size(0), _p(dist), _p(noise), _p(noise_level), _p(sigmas), sigmas.numel(),
+            ctx.anneal_power, H, ctypes.byref(pp), _p(loss), _p(gl), _p(ws), _p(grad_h), ctypes.byref(gp), _stream()))
         return (grad_h, None, None, None, None, None, None, None, *grads)
 
 

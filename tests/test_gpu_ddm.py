@@ -1,0 +1,119 @@
+"""GPU: DDM head, the full do_DDM step and PaiNN against the golden fixtures (reference modules on CPU)."""
+import pytest
+import torch
+
+from _build import grads_of, head_from, painn_from, schnet_from
+from _golden import Golden, rel_err
+from geossl_b200 import ops
+from geossl_b200.data import AtomTupleBatch, synthetic_batch
+from geossl_b200.pretrain import default_args, do_DDM
+from oracle import models as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_OUT, TOL_GRAD = 1e-5, 1e-4
+
+
+def test_pair_distance():
+    b = synthetic_batch(9, 2, 25, seed=1)
+    d = ops.pair_distance(b.positions.to(DEV), b.super_edge_index.to(DEV))
+    assert d.shape == (b.super_edge_index.shape[1], 1)
+    assert rel_err(d, O.pair_distance(b.positions, b.super_edge_index)) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["ncsn_h128", "ncsn_perm"])
+def test_ddm_head_vs_golden(name):
+    g = Golden(name)
+    head = head_from(g, device=DEV)
+    i = g["in"]
+    data = AtomTupleBatch(None, None, i["batch"].to(DEV), i["super_edge_index"].to(DEV))
+    nf = i["node_feature"].to(DEV).requires_grad_()
+    loss = head(data, nf, i["distance"].to(DEV), noise_level=i["noise_level"].to(DEV),
+                distance_noise=i["distance_noise"].to(DEV))
+    assert rel_err(loss, g["out"]["loss"]) <= TOL_OUT
+    loss.backward()
+    assert rel_err(nf.grad, g["grad"]["node_feature"]) <= TOL_GRAD
+    got = grads_of(head)
+    for k, ref in g["grad"].items():
+        if k != "node_feature":
+            assert rel_err(got[k], ref) <= TOL_GRAD, (k, rel_err(got[k], ref))
+
+
+def test_ddm_head_rng_contract():
+    """Without injected draws the head consumes the device generator exactly like NCSN.py:190,194."""
+    g = Golden("ncsn_h128")
+    head = head_from(g, device=DEV)
+    i = g["in"]
+    data = AtomTupleBatch(None, None, i["batch"].to(DEV), i["super_edge_index"].to(DEV))
+    nf, dist = i["node_feature"].to(DEV), i["distance"].to(DEV)
+    torch.manual_seed(5)
+    l1 = head(data, nf, dist)
+    torch.manual_seed(5)
+    lvl = torch.randint(0, head.sigmas.size(0), (data.num_graphs,), device=DEV)
+    eps = torch.randn_like(dist)
+    l2 = head(data, nf, dist, noise_level=lvl, distance_noise=eps)
+    assert torch.equal(l1, l2)
+
+
+@pytest.mark.parametrize("name", ["ddm_schnet_small", "ddm_schnet_cfg1", "ddm_painn_small"])
+def test_do_ddm_vs_golden(name):
+    g = Golden(name)
+    c, i = g.cfg, g["in"]
+    model = schnet_from(g, DEV) if c["model_3d"] == "schnet" else painn_from(g, DEV)
+    heads = (head_from(g, "sd1", DEV), head_from(g, "sd2", DEV))
+    batch = AtomTupleBatch(i["x"].to(DEV), i["pos"].to(DEV), i["batch"].to(DEV), i["super_edge_index"].to(DEV),
+                           i["radius_edge_index"].to(DEV) if "radius_edge_index" in i else None)
+    draws = ((i["noise_level_1"].to(DEV), i["distance_noise_1"].to(DEV)),
+             (i["noise_level_2"].to(DEV), i["distance_noise_2"].to(DEV)))
+    loss, acc = do_DDM(default_args(c["model_3d"]), batch, model, None, 0.0, c["sigma"], heads=heads, draws=draws,
+                       positions_02=(i["pos"] + i["pos_noise"]).to(DEV))
+    assert acc == 0 and rel_err(loss, g["out"]["loss"]) <= TOL_OUT, rel_err(loss, g["out"]["loss"])
+    loss.backward()
+    for mod, grp in ((model, "grad"), (heads[0], "grad1"), (heads[1], "grad2")):
+        got = grads_of(mod)
+        for k, ref in g[grp].items():
+            assert rel_err(got[k], ref) <= TOL_GRAD, (grp, k, rel_err(got[k], ref))
+
+
+@pytest.mark.parametrize("name", ["painn_small", "painn_full"])
+def test_painn_module_vs_golden(name):
+    g = Golden(name)
+    m = painn_from(g, DEV)
+    i = g["in"]
+    h, q = m(i["x"].to(DEV), i["pos"].to(DEV), i["radius_edge_index"].to(DEV), i["batch"].to(DEV), return_latent=True)
+    assert rel_err(q, g["out"]["q"]) <= TOL_OUT and rel_err(h, g["out"]["h"]) <= TOL_OUT
+    ((q * i["w_q"].to(DEV)).sum() + (h * i["w_h"].to(DEV)).sum()).backward()
+    got = grads_of(m)
+    for k, ref in g["grad"].items():
+        assert rel_err(got[k], ref) <= TOL_GRAD, (k, rel_err(got[k], ref))
+    assert got["embedding.weight"][0].abs().max() == 0
+
+
+def test_painn_unsorted_edge_list_is_handled():
+    g = Golden("painn_small")
+    m = painn_from(g, DEV)
+    i = g["in"]
+    rei = i["radius_edge_index"]
+    perm = torch.randperm(rei.shape[1], generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        _, q = m(i["x"].to(DEV), i["pos"].to(DEV), rei[:, perm].contiguous().to(DEV), i["batch"].to(DEV), return_latent=True)
+    assert rel_err(q, g["out"]["q"]) <= TOL_OUT
+
+
+def test_train_step_decreases_loss_config1():
+    """A few Adam steps of the whole path at config-1 size run, stay finite and reduce the loss."""
+    from geossl_b200.Geom3D.models import SchNet
+    from geossl_b200.NCSN import NCSN_version_03
+    from geossl_b200.pretrain import train_step
+    torch.manual_seed(0)
+    model = SchNet(node_class=9).to(DEV)
+    heads = [NCSN_version_03(128, 10, 0.01, 50, "symmetry", 2.0).to(DEV) for _ in range(2)]
+    params = [{"params": model.parameters()}] + [{"params": h.parameters()} for h in heads]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    batch = synthetic_batch(32, 30, seed=0).to(DEV)
+    pos2 = batch.positions + 0.3 * torch.randn_like(batch.positions)
+    lvl = torch.randint(0, 50, (32,), device=DEV)
+    eps = torch.randn((batch.super_edge_index.shape[1], 1), device=DEV)
+    draws = ((lvl, eps), (lvl, eps))
+    losses = [float(train_step(default_args(), batch, model, heads, opt, draws=draws, positions_02=pos2)) for _ in range(8)]
+    assert all(map(lambda v: v == v and v < 1e30, losses)) and losses[-1] < losses[0]

@@ -1,0 +1,108 @@
+"""GPU: neighbour search / CSR kernels against oracle/radius.py -- bit-exact (integer work)."""
+import numpy as np
+import pytest
+import torch
+
+from _golden import Golden
+from geossl_b200 import ops
+from geossl_b200.data import synthetic_batch
+from oracle.radius import radius_graph as oracle_radius_graph, radius_neighbors, transpose_csr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def check_graph(pos, batch, r, num_graphs=None, max_nb=32):
+    g = ops.radius_csr(pos.to(DEV), batch.to(DEV), r, max_nb, num_graphs=num_graphs)
+    rowptr, src = radius_neighbors(pos, r, batch, max_nb)
+    e = int(rowptr[-1])
+    assert g.num_edges == e
+    assert np.array_equal(g.rowptr.cpu().numpy(), rowptr.astype(np.int32))
+    assert np.array_equal(g.src[:e].cpu().numpy(), src.astype(np.int32))
+    ei = g.edge_index.cpu()
+    assert torch.equal(ei, oracle_radius_graph(pos, r, batch, max_num_neighbors=max_nb))
+    t_rowptr, t_eid, t_tgt = transpose_csr(rowptr, src)
+    assert np.array_equal(g.t_rowptr.cpu().numpy(), t_rowptr.astype(np.int32))
+    assert np.array_equal(g.t_eid[:e].cpu().numpy(), t_eid.astype(np.int32))
+    assert np.array_equal(g.t_tgt[:e].cpu().numpy(), t_tgt.astype(np.int32))
+    if e:
+        d = (pos[ei[0]] - pos[ei[1]]).norm(dim=-1)
+        assert torch.allclose(g.dist[:e].cpu(), d, rtol=1e-6, atol=1e-7)
+    return g
+
+
+@pytest.mark.parametrize("name", ["schnet_small", "schnet_trunc"])
+def test_radius_graph_matches_golden_edge_index(name):
+    g = Golden(name)
+    ei = ops.radius_graph(g["in"]["pos"].to(DEV), g.cfg["cutoff"], g["in"]["batch"].to(DEV))
+    assert ei.dtype == torch.int64 and torch.equal(ei.cpu(), g["out"]["edge_index"])
+
+
+@pytest.mark.parametrize("seed,ng,lo,hi,r,density", [
+    (0, 7, 1, 9, 10.0, 0.05), (1, 16, 10, 60, 10.0, 0.05), (2, 5, 40, 90, 10.0, 0.08), (3, 6, 25, 70, 3.0, 0.05),
+    (4, 3, 200, 600, 6.0, 0.05), (5, 64, 30, 30, 10.0, 0.05), (6, 4, 33, 35, 50.0, 0.05)])
+def test_radius_csr_random(seed, ng, lo, hi, r, density):
+    b = synthetic_batch(ng, lo, hi, seed=seed, density=density, with_pairs=False)
+    g = check_graph(b.positions, b.batch, r, num_graphs=ng)
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).cpu()
+    assert int(deg.max()) <= 33
+
+
+def test_truncation_rows_of_32_and_33():
+    b = synthetic_batch(3, 50, 64, seed=11, density=0.1, with_pairs=False)
+    g = check_graph(b.positions, b.batch, 10.0)
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).cpu()
+    assert int(deg.max()) == 33 and bool((deg == 32).any())     # asymmetric truncation
+
+
+def test_boundary_ties_duplicates_and_tiny_graphs():
+    # atoms exactly at distance r (strict <), duplicated positions (d = 0 kept, self dropped), 1-atom and empty graphs
+    pos = torch.tensor([[0, 0, 0], [3, 4, 0], [0, 0, 0], [0, 0, 5], [0, 5.0000005, 0],
+                        [1, 1, 1],
+                        [2, 2, 2], [2, 2, 2]], dtype=torch.float32)
+    batch = torch.tensor([0, 0, 0, 0, 0, 1, 3, 3])          # graph 2 is empty
+    g = check_graph(pos, batch, 5.0, num_graphs=4)
+    ei = g.edge_index.cpu()
+    pairs = set(map(tuple, ei.t().tolist()))
+    assert (2, 0) in pairs and (0, 2) in pairs and (1, 0) not in pairs and (3, 0) not in pairs
+    assert (7, 6) in pairs and (6, 7) in pairs and not any(5 in p for p in pairs)
+
+
+def test_small_max_num_neighbors_and_single_graph_default_batch():
+    b = synthetic_batch(1, 40, seed=5, with_pairs=False)
+    check_graph(b.positions, b.batch, 10.0, max_nb=4)
+    ei = ops.radius_graph(b.positions.to(DEV), 4.0)             # batch=None
+    assert torch.equal(ei.cpu(), oracle_radius_graph(b.positions, 4.0))
+
+
+def test_empty_input():
+    g = ops.radius_csr(torch.zeros((0, 3), device=DEV), torch.zeros(0, dtype=torch.long, device=DEV), 5.0, num_graphs=0)
+    assert g.num_edges == 0 and g.edge_index.shape == (2, 0)
+
+
+def test_full_size_properties_config2():
+    """Config-2 sized batch (256 x U{10..60}) : size-independent invariants instead of the O(n^2) oracle."""
+    b = synthetic_batch(256, 10, 60, seed=21, with_pairs=False)
+    g = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), 10.0, num_graphs=256)
+    e = g.num_edges
+    rowptr, src, tgt = g.rowptr.cpu().long(), g.src[:e].cpu().long(), g.tgt[:e].cpu().long()
+    deg = rowptr[1:] - rowptr[:-1]
+    assert int(deg.max()) <= 33 and int(rowptr[-1]) == e
+    assert bool((tgt[1:] >= tgt[:-1]).all())                                        # target-major
+    same = tgt[1:] == tgt[:-1]
+    assert bool((src[1:][same] > src[:-1][same]).all())                             # sources ascending, no duplicates
+    assert bool((b.batch[src] == b.batch[tgt]).all()) and bool((src != tgt).all())  # intra-graph, no self loops
+    d2 = ((b.positions[src] - b.positions[tgt]) ** 2).sum(-1)
+    assert bool((d2 < 100.0 + 1e-3).all())
+    untrunc = deg < 32                                                              # untruncated rows are complete
+    n_in = torch.zeros(len(deg), dtype=torch.long)
+    for gi in range(256):
+        lo, hi = int(b.graph_ptr[gi]), int(b.graph_ptr[gi + 1])
+        p = b.positions[lo:hi]
+        dd = ((p[:, None] - p[None]) ** 2).sum(-1)
+        n_in[lo:hi] = (dd < 100.0).sum(1) - 1
+    assert bool((deg[untrunc] == n_in[untrunc]).all())
+    # the transpose is a permutation of the edge ids grouped by source
+    t_eid = g.t_eid[:e].cpu().long()
+    assert torch.equal(torch.sort(t_eid).values, torch.arange(e))
+    assert bool((src[t_eid][1:] >= src[t_eid][:-1]).all()) and torch.equal(g.t_tgt[:e].cpu().long(), tgt[t_eid])

@@ -1,0 +1,151 @@
+"""GPU: SchNet kernels and module against the oracle and the golden fixtures.
+Tolerances are BASELINE.json's: representations rel 1e-5, parameter gradients rel 1e-4 (fp32 SIMT path),
+rel = max|a-b| / max|b| on the tensor."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _build import grads_of, schnet_from
+from _golden import Golden, rel_err
+from geossl_b200 import ops
+from geossl_b200.data import synthetic_batch
+from oracle import models as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_OUT, TOL_GRAD = 1e-5, 1e-4
+
+
+def _layer_params(Fd, G, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(Fd, G, generator=g) * 0.3, torch.randn(Fd, generator=g) * 0.1,
+            torch.randn(Fd, Fd, generator=g) * 0.15, torch.randn(Fd, generator=g) * 0.1)
+
+
+@pytest.mark.parametrize("Fd,G,ng,lo,hi", [(128, 50, 6, 20, 40), (64, 51, 5, 5, 30), (32, 20, 4, 3, 12), (128, 64, 2, 70, 90)])
+def test_filter_and_cfconv_kernels_vs_oracle(Fd, G, ng, lo, hi):
+    b = synthetic_batch(ng, lo, hi, seed=Fd + G, with_pairs=False)
+    cutoff = 10.0
+    w1, b1, w2, b2 = _layer_params(Fd, G, 1)
+    offset = torch.linspace(0.0, cutoff, G)
+    coeff = O.smearing_coeff(offset)
+    n = b.positions.shape[0]
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(n, Fd, generator=gen)
+    gout = torch.randn(n, Fd, generator=gen)
+    # oracle
+    ei = O.radius_graph(b.positions, cutoff, b.batch)
+    d = (b.positions[ei[0]] - b.positions[ei[1]]).norm(dim=-1)
+    sd = {"interactions.0.mlp.0.weight": w1.clone().requires_grad_(), "interactions.0.mlp.0.bias": b1.clone().requires_grad_(),
+          "interactions.0.mlp.2.weight": w2.clone().requires_grad_(), "interactions.0.mlp.2.bias": b2.clone().requires_grad_()}
+    xr = x.clone().requires_grad_()
+    W = O.schnet_filter(sd, 0, d, O.gaussian_smearing(d, offset), cutoff)
+    m = O.cfconv_aggregate(xr, W, ei)
+    (m * gout).sum().backward()
+    # product
+    graph = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), cutoff, num_graphs=ng)
+    e = graph.num_edges
+    assert e == ei.shape[1]
+    cw = [t.to(DEV).requires_grad_() for t in (w1, b1, w2, b2)]
+    filt = ops.filter_forward(graph, offset.to(DEV), coeff, cutoff, *[t.detach() for t in cw])
+    assert rel_err(filt[:e], W) <= TOL_OUT
+    xc = x.to(DEV).requires_grad_()
+    out = ops.CFConvLayer.apply(xc, *cw, offset.to(DEV), graph, coeff, cutoff)
+    assert rel_err(out, m) <= TOL_OUT
+    out.backward(gout.to(DEV))
+    assert rel_err(xc.grad, xr.grad) <= TOL_GRAD
+    for got, key in zip(cw, sd):
+        assert rel_err(got.grad, sd[key].grad) <= TOL_GRAD, key
+    # the three composable primitives, including the materialised edge product
+    ge = graph.exact()
+    dW = ops.CFConvEdgeProduct.apply(x.to(DEV), gout.to(DEV), ge)
+    assert rel_err(dW, x[ei[0]] * gout[ei[1]]) <= 1e-6
+    assert rel_err(ops.CFConvAggregateT.apply(filt[:e].contiguous(), gout.to(DEV), ge), xr.grad) <= TOL_GRAD
+
+
+def test_cfconv_is_deterministic_and_linear():
+    b = synthetic_batch(64, 10, 60, seed=9, with_pairs=False)
+    graph = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), 10.0, num_graphs=64)
+    n, e = b.positions.shape[0], graph.num_edges
+    x1, x2 = torch.randn(n, 128, device=DEV), torch.randn(n, 128, device=DEV)
+    W = torch.randn(graph.capacity, 128, device=DEV)
+    a = ops.CFConvAggregate.apply(x1, W, graph)
+    assert torch.equal(a, ops.CFConvAggregate.apply(x1, W, graph))            # atomic free => bitwise repeatable
+    lin = ops.CFConvAggregate.apply(x1 + 2 * x2, W, graph)
+    assert rel_err(lin, a + 2 * ops.CFConvAggregate.apply(x2, W, graph)) <= 1e-5
+    # adjoint identity <A x, g> = <x, A^T g>
+    gq = torch.randn(n, 128, device=DEV)
+    lhs = (a.double() * gq.double()).sum()
+    rhs = (x1.double() * ops.CFConvAggregateT.apply(W, gq, graph).double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["schnet_small", "schnet_trunc"])
+def test_schnet_module_vs_golden(name):
+    g = Golden(name)
+    m = schnet_from(g, DEV)
+    i = g["in"]
+    out, h = m(i["z"].to(DEV), i["pos"].to(DEV), i["batch"].to(DEV), return_latent=True)
+    assert rel_err(h, g["out"]["h"]) <= TOL_OUT and rel_err(out, g["out"]["out"]) <= TOL_OUT
+    ((h * i["w_h"].to(DEV)).sum() + (out * i["w_o"].to(DEV)).sum()).backward()
+    got = grads_of(m)
+    for k, ref in g["grad"].items():
+        assert rel_err(got[k], ref) <= TOL_GRAD, (k, rel_err(got[k], ref))
+
+
+def test_schnet_standalone_block_api():
+    """InteractionBlock / CFConv keep the reference signature (x, edge_index, edge_weight, edge_attr)."""
+    g = Golden("schnet_small")
+    m = schnet_from(g, DEV)
+    i = g["in"]
+    pos, batch = i["pos"].to(DEV), i["batch"].to(DEV)
+    ei = ops.radius_graph(pos, g.cfg["cutoff"], batch)
+    ew = (pos[ei[0]] - pos[ei[1]]).norm(dim=-1)
+    ea = m.distance_expansion(ew)
+    h = m.embedding(i["z"].to(DEV))
+    y = m.interactions[0](h, ei, ew, ea, batch)
+    sd = g.sd()
+    W = O.schnet_filter(sd, 0, ew.cpu(), ea.cpu(), g.cfg["cutoff"])
+    x = F.linear(h.cpu(), sd["interactions.0.conv.lin1.weight"])
+    x = O.cfconv_aggregate(x, W, ei.cpu())
+    x = F.linear(x, sd["interactions.0.conv.lin2.weight"], sd["interactions.0.conv.lin2.bias"])
+    x = F.linear(O.shifted_softplus(x), sd["interactions.0.lin.weight"], sd["interactions.0.lin.bias"])
+    assert rel_err(y, x.detach()) <= TOL_OUT
+
+
+def test_md17_double_backward_vs_golden():
+    """Energy + autograd force + backward through the force (finetune_md17.py:32-54)."""
+    g = Golden("md17_small")
+    m = schnet_from(g, DEV)
+    lin = torch.nn.Linear(g.cfg["hidden"], 1).to(DEV)
+    lin.load_state_dict(g.sd("sdlin", DEV))
+    i = g["in"]
+    pos = i["pos"].to(DEV).requires_grad_()
+    rep = m(i["z"].to(DEV), pos, i["batch"].to(DEV))
+    energy = lin(rep).squeeze(1)
+    force = -torch.autograd.grad(energy, pos, grad_outputs=torch.ones_like(energy), create_graph=True, retain_graph=True)[0]
+    loss = 0.05 * F.l1_loss(energy, i["y"].to(DEV)) + 0.95 * F.l1_loss(force, i["force_target"].to(DEV))
+    loss.backward()
+    assert rel_err(energy, g["out"]["energy"]) <= TOL_OUT and rel_err(force, g["out"]["force"]) <= TOL_GRAD
+    assert rel_err(loss, g["out"]["loss"]) <= TOL_OUT
+    got = grads_of(m)
+    for k, ref in g["grad"].items():
+        assert rel_err(got[k], ref) <= 2e-4, (k, rel_err(got[k], ref))
+    for k, ref in g["gradlin"].items():
+        assert rel_err(dict(lin.named_parameters())[k].grad, ref) <= 2e-4
+
+
+def test_full_size_forward_properties_config2():
+    """Config 2 (256 x 30 atoms, H=F=128, G=50, L=6): permuting whole molecules permutes the result."""
+    torch.manual_seed(0)
+    from geossl_b200.Geom3D.models import SchNet
+    m = SchNet(node_class=9).to(DEV)
+    b = synthetic_batch(256, 30, seed=4, with_pairs=False).to(DEV)
+    z = b.x[:, 0].contiguous()
+    with torch.no_grad():
+        out, h = m(z, b.positions, b.batch, return_latent=True, num_graphs=256)
+        perm = torch.arange(256, device=DEV).flip(0)
+        idx = (perm[:, None] * 30 + torch.arange(30, device=DEV)[None]).reshape(-1)
+        out2, h2 = m(z[idx], b.positions[idx], b.batch, return_latent=True, num_graphs=256)
+    assert torch.isfinite(h).all()
+    assert rel_err(h2, h[idx]) <= 1e-6 and rel_err(out2, out[perm]) <= 1e-6
