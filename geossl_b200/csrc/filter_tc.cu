@@ -1,0 +1,344 @@
+// SchNet filter network on the sm_100a tensor cores (tcgen05 + TMEM), forward.
+//
+//   d_e -> rbf (64-wide, zero padded) --MMA1--> a = rbf W1^T  --epilogue--> s = ssp(a + b1)
+//       --MMA2--> u = s W2^T --epilogue--> W_e = (u + b2) * cutoff(d_e)  -> filt (E,128) in HBM
+//
+// Replaces GaussianSmearing.forward (Geom3D/models/schnet.py:205-207), InteractionBlock.mlp
+// (schnet.py:141-145) and the cutoff product of CFConv.forward (schnet.py:186-187).  F = 128, G <= 64.
+//
+// One persistent CTA per SM, 128-edge tiles, 13 warps:
+//   warps 0-7   epilogue: TMEM lane = edge row; warps 0-3 own accumulator columns 0-63, warps 4-7 64-127
+//   warps 8-11  producer: rbf tile (hi/lo, K-major SW128) for the next tile, double buffered
+//   warp 12     TMEM allocation + the single MMA-issuing thread
+// Operands never come from HBM (they are computed on chip), so tiles are written with st.shared in the
+// swizzled layout and published to the async proxy with fence.proxy.async; the two weight matrices are
+// split once per CTA into shared memory.  Accumulators D1/D2 are double buffered in TMEM (4 x 128 columns).
+// fp32 operands are split into two 16-bit parts and every product is three MMAs (see tc.cuh).
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace geossl {
+namespace tc {
+
+constexpr int kF = 128;            // filters
+constexpr int kTile = 128;         // edges per tile (UMMA M)
+constexpr int kBlk = kTile * 128;  // bytes of one [128 rows x 64 k] 16-bit block
+constexpr int kEpiThreads = 256, kProdThreads = 128, kThreads = kEpiThreads + kProdThreads + 32;
+
+struct FwdLayout {                 // byte offsets from the 1024-aligned dynamic smem base
+    static constexpr int W1_hi = 0, W1_lo = W1_hi + kBlk;                 // [128 f][64 g]
+    static constexpr int W2_hi = W1_lo + kBlk, W2_lo = W2_hi + 2 * kBlk;  // [128 o][128 i] = 2 k-blocks
+    static constexpr int PHI = W2_lo + 2 * kBlk;                          // 2 buffers x (hi, lo)
+    static constexpr int S = PHI + 4 * kBlk;                              // (hi: 2 k-blocks, lo: 2 k-blocks)
+    static constexpr int B1 = S + 4 * kBlk;                               // 128 floats
+    static constexpr int B2 = B1 + 512;
+    static constexpr int OFF = B2 + 512;                                  // 64 floats
+    static constexpr int BAR = OFF + 256;                                 // 16 mbarriers
+    static constexpr int TMEM_PTR = BAR + 16 * 8;
+    static constexpr int kBytes = TMEM_PTR + 16;
+};
+static_assert(FwdLayout::kBytes + 1024 <= 227 * 1024, "shared memory budget");
+
+enum Bar { PHI_FULL = 0, PHI_EMPTY = 2, D1_FULL = 4, D1_EMPTY = 6, S_FULL = 8, S_EMPTY = 9, D2_FULL = 10, D2_EMPTY = 12 };
+
+template <bool FP16>
+__global__ void __launch_bounds__(kThreads, 1)
+filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restrict__ n_edges_dev, int64_t capacity,
+                     const float* __restrict__ offset, float coeff, float cutoff, int G,
+                     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                     const float* __restrict__ b2, float* __restrict__ filt) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    using L = FwdLayout;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + L::BAR;
+    auto bar = [&](int i) { return bar0 + 8u * i; };
+    float* sB1 = reinterpret_cast<float*>(smem + L::B1);
+    float* sB2 = reinterpret_cast<float*>(smem + L::B2);
+    float* sOff = reinterpret_cast<float*>(smem + L::OFF);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    int64_t n_edges = (int64_t)(*n_edges_dev);
+    if (n_edges > capacity) n_edges = capacity;
+    const int64_t n_tiles = (n_edges + kTile - 1) / kTile;
+    const int my_tiles = (blockIdx.x < n_tiles) ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+
+    // ---- one-time setup: weights (split, swizzled), biases, barriers, TMEM
+    for (int idx = tid; idx < kF * 8; idx += kThreads) {             // W1: row f, chunk c (8 g each), zero padded to 64
+        const int f = idx >> 3, c = idx & 7;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int g = c * 8 + j; x[j] = (g < G) ? __ldg(w1 + f * G + g) : 0.f; }
+        store_chunk8<FP16>(smem + L::W1_hi, smem + L::W1_lo, f, c * 8, x);
+    }
+    for (int idx = tid; idx < kF * 16; idx += kThreads) {            // W2: row o, 16 chunks over i
+        const int o = idx >> 4, c = idx & 15;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __ldg(w2 + o * kF + c * 8 + j);
+        const int blk = c >> 3;
+        store_chunk8<FP16>(smem + L::W2_hi + blk * kBlk, smem + L::W2_lo + blk * kBlk, o, (c & 7) * 8, x);
+    }
+    if (tid < kF) { sB1[tid] = __ldg(b1 + tid); sB2[tid] = __ldg(b2 + tid); }
+    if (tid < 64) sOff[tid] = (tid < G) ? __ldg(offset + tid) : 0.f;
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(PHI_FULL + b), kProdThreads);
+            mbar_init(bar(PHI_EMPTY + b), 1);
+            mbar_init(bar(D1_FULL + b), 1);
+            mbar_init(bar(D1_EMPTY + b), kEpiThreads);
+            mbar_init(bar(D2_FULL + b), 1);
+            mbar_init(bar(D2_EMPTY + b), kEpiThreads);
+        }
+        mbar_init(bar(S_FULL), kEpiThreads);
+        mbar_init(bar(S_EMPTY), 1);
+        fence_barrier_init();
+    }
+    if (warp == 12) tmem_alloc(sbase + L::TMEM_PTR, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR);
+    const uint32_t tD1[2] = {tmem, tmem + 128}, tD2[2] = {tmem + 256, tmem + 384};
+
+    if (warp >= 8 && warp < 12) {
+        // ===================== producer: rbf tile of local tile i into PHI[i & 1]
+        const int r = tid - kEpiThreads;                              // edge row 0..127
+        for (int i = 0; i < my_tiles; ++i) {
+            const int64_t e = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTile + r;
+            const int b = i & 1;
+            mbar_wait(bar(PHI_EMPTY + b), ((i >> 1) & 1) ^ 1);
+            const float d = (e < n_edges) ? __ldg(edge_dist + e) : 0.f;
+            uint8_t* hi = smem + L::PHI + b * 2 * kBlk;
+            uint8_t* lo = hi + kBlk;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = c * 8 + j;
+                    const float diff = d - sOff[g];
+                    x[j] = (g < G) ? __expf(__fmul_rn(coeff, __fmul_rn(diff, diff))) : 0.f;
+                }
+                store_chunk8<FP16>(hi, lo, r, c * 8, x);
+            }
+            fence_proxy_async();
+            mbar_arrive(bar(PHI_FULL + b));
+        }
+    } else if (warp == 12) {
+        // ===================== MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, kTile, kF);
+            const uint64_t dW1h = desc_k_sw128(sbase + L::W1_hi), dW1l = desc_k_sw128(sbase + L::W1_lo);
+            const uint64_t dW2h = desc_k_sw128(sbase + L::W2_hi), dW2l = desc_k_sw128(sbase + L::W2_lo);
+            const uint64_t dSh = desc_k_sw128(sbase + L::S), dSl = desc_k_sw128(sbase + L::S + 2 * kBlk);
+            auto issue_mma1 = [&](int i) {
+                const int b = i & 1;
+                mbar_wait(bar(PHI_FULL + b), (i >> 1) & 1);
+                mbar_wait(bar(D1_EMPTY + b), ((i >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint64_t dPh = desc_k_sw128(sbase + L::PHI + b * 2 * kBlk), dPl = desc_k_sw128(sbase + L::PHI + b * 2 * kBlk + kBlk);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)                         // K = 64 = 4 x 16 (+32 bytes = +2 encoded)
+                    mma3(tD1[b], dPh + 2 * kk, dPl + 2 * kk, dW1h + 2 * kk, dW1l + 2 * kk, idesc, kk > 0);
+                tc_commit(bar(PHI_EMPTY + b));
+                tc_commit(bar(D1_FULL + b));
+            };
+            if (my_tiles > 0) issue_mma1(0);
+            for (int i = 0; i < my_tiles; ++i) {
+                if (i + 1 < my_tiles) issue_mma1(i + 1);
+                const int b = i & 1;
+                mbar_wait(bar(S_FULL), i & 1);
+                mbar_wait(bar(D2_EMPTY + b), ((i >> 1) & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)                         // K = 128 = 2 blocks x 4 x 16
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t o = kb * (kBlk >> 4) + 2 * kk;
+                        mma3(tD2[b], dSh + o, dSl + o, dW2h + o, dW2l + o, idesc, (kb | kk) > 0);
+                    }
+                tc_commit(bar(S_EMPTY));
+                tc_commit(bar(D2_FULL + b));
+            }
+        }
+    } else {
+        // ===================== epilogue warps: E1(i) then E2(i-1)
+        const int q = warp & 3, half = warp >> 2;                     // lane quadrant, column half
+        const int r = q * 32 + lane;                                  // edge row in the tile = TMEM lane
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        for (int i = 0; i <= my_tiles; ++i) {
+            if (i < my_tiles) {
+                const int b = i & 1;
+                mbar_wait(bar(D1_FULL + b), (i >> 1) & 1);
+                tc_fence_after();
+                float v[2][32];
+                tmem_ld32(tD1[b] + lane_base + half * 64, v[0]);
+                tmem_ld32(tD1[b] + lane_base + half * 64 + 32, v[1]);
+                tc_fence_before();
+                mbar_arrive(bar(D1_EMPTY + b));
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[h][j] = ssp_fast(v[h][j] + sB1[half * 64 + h * 32 + j]);
+                mbar_wait(bar(S_EMPTY), (i & 1) ^ 1);                  // MMA2 of the previous tile released S
+                uint8_t* hi = smem + L::S + half * kBlk;               // k-block `half` holds columns 64*half..+63
+                uint8_t* lo = hi + 2 * kBlk;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) store_chunk8<FP16>(hi, lo, r, c * 8, &v[c >> 2][(c & 3) * 8]);
+                fence_proxy_async();
+                mbar_arrive(bar(S_FULL));
+            }
+            if (i > 0) {
+                const int t = i - 1, b = t & 1;
+                const int64_t e = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile + r;
+                mbar_wait(bar(D2_FULL + b), (t >> 1) & 1);
+                tc_fence_after();
+                float v[2][32];
+                tmem_ld32(tD2[b] + lane_base + half * 64, v[0]);
+                tmem_ld32(tD2[b] + lane_base + half * 64 + 32, v[1]);
+                tc_fence_before();
+                mbar_arrive(bar(D2_EMPTY + b));
+                if (e < n_edges) {
+                    const float c = cosine_cutoff(__ldg(edge_dist + e), cutoff);
+                    float* out = filt + e * kF + half * 64;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const int col = half * 64 + h * 32 + j;
+                            float4 o4 = make_float4((v[h][j] + sB2[col]) * c, (v[h][j + 1] + sB2[col + 1]) * c,
+                                                    (v[h][j + 2] + sB2[col + 2]) * c, (v[h][j + 3] + sB2[col + 3]) * c);
+                            *reinterpret_cast<float4*>(out + h * 32 + j) = o4;
+                        }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        __syncwarp();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ self test
+// mode 0: D[m][n] = sum_k A[m][k] B[n][k]        A (128,K), B (128,K) row-major fp32, K in {64,128}  (K-major operands)
+// mode 1: D[m][n] = sum_k X[k][m] Y[k][n]        X (128,128), Y (128,N) row-major fp32, N in {64,128} (MN-major operands)
+template <bool FP16>
+__global__ void __launch_bounds__(128, 1)
+tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restrict__ B, int K, int N, float* __restrict__ D) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    // A_hi | A_lo | B_hi | B_lo, each 2 blocks of 16 KB; barrier + tmem ptr after
+    uint8_t* Ah = smem; uint8_t* Al = smem + 2 * kBlk; uint8_t* Bh = smem + 4 * kBlk; uint8_t* Bl = smem + 6 * kBlk;
+    const uint32_t bar = sbase + 8 * kBlk, tptr = bar + 8;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (mode == 0) {
+        for (int c = 0; c < K / 8; ++c) {                            // thread = row
+            store_chunk8<FP16>(Ah + (c >> 3) * kBlk, Al + (c >> 3) * kBlk, tid, (c & 7) * 8, A + tid * K + c * 8);
+            store_chunk8<FP16>(Bh + (c >> 3) * kBlk, Bl + (c >> 3) * kBlk, tid, (c & 7) * 8, B + tid * K + c * 8);
+        }
+    } else {
+        for (int c = 0; c < 16; ++c)                                 // thread = k row; X has 128 m = 2 MN blocks
+            store_chunk8<FP16>(Ah + (c >> 3) * kBlk, Al + (c >> 3) * kBlk, tid, (c & 7) * 8, A + tid * 128 + c * 8);
+        for (int c = 0; c < N / 8; ++c)
+            store_chunk8<FP16>(Bh + (c >> 3) * kBlk, Bl + (c >> 3) * kBlk, tid, (c & 7) * 8, B + tid * N + c * 8);
+    }
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(tptr, 128);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 8 * kBlk + 8);
+    if (tid == 0) {
+        if (mode == 0) {
+            const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, 128);
+            const uint64_t ah = desc_k_sw128(sbase), al = desc_k_sw128(sbase + 2 * kBlk);
+            const uint64_t bh = desc_k_sw128(sbase + 4 * kBlk), bl = desc_k_sw128(sbase + 6 * kBlk);
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint32_t o = (ks >> 2) * (kBlk >> 4) + 2 * (ks & 3);
+                mma3(tmem, ah + o, al + o, bh + o, bl + o, idesc, ks > 0);
+            }
+        } else {
+            const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, N, 1, 1);
+            const uint64_t ah = desc_mn_sw128(sbase, kBlk), al = desc_mn_sw128(sbase + 2 * kBlk, kBlk);
+            const uint64_t bh = desc_mn_sw128(sbase + 4 * kBlk, kBlk), bl = desc_mn_sw128(sbase + 6 * kBlk, kBlk);
+            for (int ks = 0; ks < 8; ++ks) {                          // K = 128 rows = 8 x 16; +2048 bytes per step
+                const uint32_t o = ks * (2048 >> 4);
+                mma3(tmem, ah + o, al + o, bh + o, bl + o, idesc, ks > 0);
+            }
+        }
+        tc_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + lane_base + c0, v);
+        for (int j = 0; j < 32; ++j) D[tid * N + c0 + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem, 128);
+    }
+}
+
+}  // namespace tc
+}  // namespace geossl
+
+using namespace geossl;
+
+extern "C" {
+
+int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream) {
+    GEOSSL_REQUIRE(a && b && d, "null pointer");
+    GEOSSL_REQUIRE((mode == 0 && (K == 64 || K == 128) && N == 128) || (mode == 1 && K == 128 && (N == 64 || N == 128)),
+                   "unsupported shape");
+    const size_t smem = 8 * tc::kBlk + 64 + 1024;
+    if (fp16) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::tc_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::tc_selftest_kernel<true><<<1, 128, smem, as_stream(stream)>>>(mode, a, b, K, N, d);
+    } else {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::tc_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::tc_selftest_kernel<false><<<1, 128, smem, as_stream(stream)>>>(mode, a, b, K, N, d);
+    }
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_filter_fwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int64_t capacity,
+                         const float* offset, float coeff, float cutoff, int G, int F,
+                         const float* w1, const float* b1, const float* w2, const float* b2,
+                         float* filt, int bf16_parts, void* stream) {
+    if (capacity == 0) return 0;
+    GEOSSL_REQUIRE(edge_dist && n_edges_dev && offset && w1 && b1 && w2 && b2 && filt && capacity > 0, "null pointer");
+    GEOSSL_REQUIRE(F == 128, "the tensor-core filter kernel is built for num_filters = 128");
+    GEOSSL_REQUIRE(G >= 1 && G <= 64, "num_gaussians must be in [1,64]");
+    const size_t smem = tc::FwdLayout::kBytes + 1024;
+    int64_t tiles = (capacity + tc::kTile - 1) / tc::kTile;
+    const int grid = (int)(tiles < kNumSM ? tiles : kNumSM);
+    static bool configured = false;
+    if (!configured) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    if (bf16_parts)
+        tc::filter_fwd_tc_kernel<false><<<grid, tc::kThreads, smem, as_stream(stream)>>>(edge_dist, n_edges_dev, capacity, offset, coeff,
+                                                                                        cutoff, G, w1, b1, w2, b2, filt);
+    else
+        tc::filter_fwd_tc_kernel<true><<<grid, tc::kThreads, smem, as_stream(stream)>>>(edge_dist, n_edges_dev, capacity, offset, coeff,
+                                                                                       cutoff, G, w1, b1, w2, b2, filt);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

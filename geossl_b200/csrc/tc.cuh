@@ -1,0 +1,176 @@
+// sm_100a tensor-core plumbing written directly in PTX: tcgen05.mma (kind::f16) with shared-memory
+// operand descriptors, TMEM allocation / loads, mbarriers, and the 128-byte swizzled K-major operand
+// layout that st.shared producers fill by hand (operands here are computed on chip, so there is no TMA
+// load in front of the MMA -- the generic->async proxy fence below is what makes the stores visible).
+//
+// fp32-grade accuracy on 16-bit tensor cores: every fp32 operand x is split as x = hi + lo with
+// hi = rn16(x), lo = rn16(x - hi) and a product A.B is issued as three MMAs
+//     A_hi.B_hi + A_lo.B_hi + A_hi.B_lo            (the lo.lo term is below the kept precision)
+// accumulating in fp32 in TMEM.  With fp16 parts (11+11 significant bits) the result is fp32-grade
+// (~2^-22 per product) for operands of bounded range (rbf values, activations, weights); with bf16 parts
+// (8+8 bits, ~2^-17) the dynamic range is fp32's, which is what gradient operands need.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace geossl {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------ addresses
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// Spin on the phase parity.  Bounded: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------ tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {   // whole warp, cols = pow2 >= 32
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {    // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// all previously issued MMAs of this thread complete -> one arrive on the mbarrier
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T   (M x N x 16, 16-bit operands, fp32 accumulate)
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32*(warp%4) + laneid) -> registers
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows of 128 bytes (64 16-bit values of
+// K), 8-row groups 1024 bytes apart (SBO), tile base 1024-byte aligned.  Advancing K by 16 elements is
+// +32 bytes on the start address (the hardware applies the XOR swizzle to the final address bits).
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4)      // start address  [0,14)
+           | ((uint64_t)1 << 16)                        // leading byte offset (unused for swizzled K-major)
+           | ((uint64_t)(1024 >> 4) << 32)              // stride byte offset   [32,46)
+           | ((uint64_t)1 << 46)                        // descriptor version (Blackwell)
+           | ((uint64_t)2 << 61);                       // SWIZZLE_128B
+}
+// MN-major operand over the SAME memory image ([k-row][64 MN values = 128 bytes], 8-row groups at 1024 B):
+// LBO = byte distance between 64-wide MN blocks, SBO = 1024.  Advancing K by 16 rows is +2048 bytes.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t mn_block_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4)
+           | ((uint64_t)((mn_block_bytes >> 4) & 0x3FFFu) << 16)
+           | ((uint64_t)(1024 >> 4) << 32)
+           | ((uint64_t)1 << 46)
+           | ((uint64_t)2 << 61);
+}
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1;
+// Instruction descriptor for kind::f16: fp32 accumulate, both operands `fmt`, majors (0 = K, 1 = MN).
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t fmt, int M, int N, uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ operand tiles
+// Byte offset of element (row, k) inside one [rows x 64] 16-bit K-major SW128 block (rows*128 bytes).
+__device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {
+    return row * 128u + ((((k >> 3) ^ (row & 7u)) << 4) | ((k & 7u) << 1));
+}
+
+template <bool FP16>
+struct Split;   // x = hi + lo in 16-bit parts; packs two values per 32-bit word (low half = first value)
+template <>
+struct Split<true> {
+    static constexpr uint32_t kFmt = kFmtF16;
+    __device__ static __forceinline__ void pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        hi = *reinterpret_cast<const uint32_t*>(&h);
+        lo = *reinterpret_cast<const uint32_t*>(&l);
+    }
+};
+template <>
+struct Split<false> {
+    static constexpr uint32_t kFmt = kFmtBF16;
+    __device__ static __forceinline__ void pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+        const float2 hf = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+        hi = *reinterpret_cast<const uint32_t*>(&h);
+        lo = *reinterpret_cast<const uint32_t*>(&l);
+    }
+};
+
+// Store 8 consecutive K values (k0 % 8 == 0) of `row` into the hi and lo images of a SW128 block.
+template <bool FP16>
+__device__ __forceinline__ void store_chunk8(uint8_t* hi_block, uint8_t* lo_block, uint32_t row, uint32_t k0, const float* x) {
+    uint4 h, l;
+    Split<FP16>::pair(x[0], x[1], h.x, l.x);
+    Split<FP16>::pair(x[2], x[3], h.y, l.y);
+    Split<FP16>::pair(x[4], x[5], h.z, l.z);
+    Split<FP16>::pair(x[6], x[7], h.w, l.w);
+    const uint32_t off = sw128_offset(row, k0);
+    *reinterpret_cast<uint4*>(hi_block + off) = h;
+    *reinterpret_cast<uint4*>(lo_block + off) = l;
+}
+
+// The three-product MMA group for one 16-wide K step.
+__device__ __forceinline__ void mma3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                     uint32_t idesc, uint32_t accumulate) {
+    mma_f16_ss(d_tmem, a_hi, b_hi, idesc, accumulate);
+    mma_f16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
+    mma_f16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+}
+
+// Fast shifted softplus: max(x,0) + log1p(exp(-|x|)) - log 2 on the MUFU ex2/lg2 units.
+// Absolute error <= ~4e-7 (lg2.approx on [1,2]); torch's threshold-20 branch is reproduced.
+__device__ __forceinline__ float ssp_fast(float x) {
+    const float t = exp2f(-fabsf(x) * 1.4426950408889634f);
+    const float l = __log2f(1.0f + t) * 0.6931471805599453f;
+    return (x > 20.f ? x : fmaxf(x, 0.f) + l) - kLog2;
+}
+
+}  // namespace tc
+}  // namespace geossl

@@ -288,10 +288,22 @@ class CFConvEdgeProduct(torch.autograd.Function):
 # =====================================================================================================
 # fused interaction filter + aggregate (training fast path, first order)
 # =====================================================================================================
-def filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2):
+# Which kernel computes the filter network forward: "tc_fp16" / "tc_bf16" = tcgen05 tensor cores with fp32
+# operands split into two fp16 / bf16 parts (three MMAs per product, fp32 accumulate; needs F = 128),
+# "simt" = fp32 CUDA cores (any supported width; also what narrower models use).
+FILTER_MODE = "tc_fp16"
+
+
+def filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2, mode=None):
     """W_e (capacity,F) from the edge distances held by ``graph`` (fused rbf + filter MLP + cutoff)."""
     F_, G = w1.size(0), w1.size(1)
     filt = torch.empty((graph.capacity, F_), dtype=torch.float32, device=w1.device)
+    mode = mode or FILTER_MODE
+    if mode != "simt" and F_ == 128:
+        _timed("filter_fwd", lambda: _lib.load().geossl_filter_fwd_tc(
+            _p(graph.dist), _p(graph.n_edges_dev), graph.capacity, _p(offset), float(coeff), float(cutoff), G, F_, _p(w1),
+            _p(b1), _p(w2), _p(b2), _p(filt), 1 if mode == "tc_bf16" else 0, _stream()))
+        return filt
     _timed("filter_fwd", lambda: _lib.load().geossl_filter_fwd(_p(graph.dist), _p(graph.n_edges_dev), graph.capacity, _p(offset),
                                                                float(coeff), float(cutoff), G, F_, _p(w1), _p(b1), _p(w2), _p(b2),
                                                                _p(filt), _stream()))

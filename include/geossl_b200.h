@@ -83,6 +83,19 @@ int geossl_filter_fwd(const float* edge_dist, const int32_t* n_edges_dev, int64_
                       const float* w1, const float* b1, const float* w2, const float* b2,
                       float* filt, void* stream);
 
+/* Same contract as geossl_filter_fwd, on the tcgen05 tensor cores (F = 128 only).  fp32 operands are split
+ * into two 16-bit parts and each product is three MMAs with fp32 accumulation in TMEM: fp16 parts
+ * (bf16_parts = 0; ~2^-22 per product, fp32 grade) or bf16 parts (bf16_parts = 1; ~2^-17, fp32 range). */
+int geossl_filter_fwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int64_t capacity,
+                         const float* offset, float coeff, float cutoff, int G, int F,
+                         const float* w1, const float* b1, const float* w2, const float* b2,
+                         float* filt, int bf16_parts, void* stream);
+
+/* Self test of the tcgen05 plumbing (descriptors, swizzle, TMEM): one 128 x N x K split-precision GEMM.
+ * mode 0: d[m][n] = sum_k a[m][k] b[n][k]  (a (128,K), b (128,K), K in {64,128}, N = 128; K-major operands)
+ * mode 1: d[m][n] = sum_k a[k][m] b[k][n]  (a (128,128), b (128,N), N in {64,128}; MN-major operands) */
+int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream);
+
 /* m_i = sum_{e in row i} x[src_e] * W_e   (atomic-free segmented reduction, one warp per row). */
 int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* rowptr, const int32_t* src,
                       int64_t n_atoms, int F, float* out, void* stream);

@@ -1,0 +1,67 @@
+"""GPU: the tcgen05 / TMEM plumbing (split-precision GEMM self test) and the tensor-core filter kernel."""
+import ctypes
+
+import pytest
+import torch
+
+from _golden import rel_err
+from geossl_b200 import _lib, ops
+from geossl_b200.data import synthetic_batch
+from oracle import models as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _selftest(mode, fp16, a, b, K, N):
+    d = torch.full((128, N), float("nan"), device=DEV)
+    rc = _lib.load().geossl_tc_selftest(mode, fp16, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), K, N,
+                                        ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "tc_selftest")
+    torch.cuda.synchronize()
+    return d
+
+
+@pytest.mark.parametrize("fp16,tol", [(1, 2e-6), (0, 4e-5)])
+@pytest.mark.parametrize("K", [64, 128])
+def test_tc_selftest_k_major(fp16, tol, K):
+    g = torch.Generator().manual_seed(K + fp16)
+    a, b = torch.randn(128, K, generator=g), torch.randn(128, K, generator=g)
+    d = _selftest(0, fp16, a.to(DEV), b.to(DEV), K, 128)
+    ref = a.double() @ b.double().t()
+    assert rel_err(d, ref) <= tol, rel_err(d, ref)
+
+
+@pytest.mark.parametrize("fp16,tol", [(1, 2e-6), (0, 4e-5)])
+@pytest.mark.parametrize("N", [64, 128])
+def test_tc_selftest_mn_major(fp16, tol, N):
+    g = torch.Generator().manual_seed(N + fp16)
+    x, y = torch.randn(128, 128, generator=g), torch.randn(128, N, generator=g)
+    d = _selftest(1, fp16, x.to(DEV), y.to(DEV), 128, N)
+    ref = x.double().t() @ y.double()
+    assert rel_err(d, ref) <= tol, rel_err(d, ref)
+
+
+@pytest.mark.parametrize("mode,tol", [("tc_fp16", 3e-6), ("tc_bf16", 1e-4)])
+@pytest.mark.parametrize("G,ng,lo,hi", [(50, 8, 20, 40), (64, 3, 5, 9), (20, 40, 25, 35)])
+def test_filter_fwd_tc_vs_oracle(mode, tol, G, ng, lo, hi):
+    b = synthetic_batch(ng, lo, hi, seed=G, with_pairs=False)
+    cutoff = 10.0
+    gen = torch.Generator().manual_seed(1)
+    w1, b1 = torch.randn(128, G, generator=gen) * 0.3, torch.randn(128, generator=gen) * 0.1
+    w2, b2 = torch.randn(128, 128, generator=gen) * 0.15, torch.randn(128, generator=gen) * 0.1
+    offset = torch.linspace(0.0, cutoff, G)
+    coeff = O.smearing_coeff(offset)
+    ei = O.radius_graph(b.positions, cutoff, b.batch)
+    d = (b.positions[ei[0]] - b.positions[ei[1]]).norm(dim=-1)
+    sd = {"interactions.0.mlp.0.weight": w1, "interactions.0.mlp.0.bias": b1,
+          "interactions.0.mlp.2.weight": w2, "interactions.0.mlp.2.bias": b2}
+    W = O.schnet_filter(sd, 0, d, O.gaussian_smearing(d, offset), cutoff)
+    graph = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), cutoff, num_graphs=ng)
+    e = graph.num_edges
+    dev = [t.to(DEV) for t in (w1, b1, w2, b2)]
+    filt = ops.filter_forward(graph, offset.to(DEV), coeff, cutoff, *dev, mode=mode)
+    torch.cuda.synchronize()
+    assert rel_err(filt[:e], W) <= tol, rel_err(filt[:e], W)
+    simt = ops.filter_forward(graph, offset.to(DEV), coeff, cutoff, *dev, mode="simt")
+    assert rel_err(filt[:e], simt[:e]) <= tol
