@@ -83,14 +83,14 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
     if (tid < 64) sOff[tid] = (tid < G) ? __ldg(offset + tid) : 0.f;
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar(PHI_FULL + b), kProdThreads);
+            mbar_init(bar(PHI_FULL + b), kProdThreads / 32);
             mbar_init(bar(PHI_EMPTY + b), 1);
             mbar_init(bar(D1_FULL + b), 1);
-            mbar_init(bar(D1_EMPTY + b), kEpiThreads);
+            mbar_init(bar(D1_EMPTY + b), kEpiThreads / 32);
             mbar_init(bar(D2_FULL + b), 1);
-            mbar_init(bar(D2_EMPTY + b), kEpiThreads);
+            mbar_init(bar(D2_EMPTY + b), kEpiThreads / 32);
         }
-        mbar_init(bar(S_FULL), kEpiThreads);
+        mbar_init(bar(S_FULL), kEpiThreads / 32);
         mbar_init(bar(S_EMPTY), 1);
         fence_barrier_init();
     }
@@ -124,7 +124,7 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 store_chunk8<FP16>(hi, lo, r, c * 8, x);
             }
             fence_proxy_async();
-            mbar_arrive(bar(PHI_FULL + b));
+            warp_arrive(bar(PHI_FULL + b));
         }
     } else if (warp == 12) {
         // ===================== MMA issuer (one thread)
@@ -177,7 +177,7 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 tmem_ld32(tD1[b] + lane_base + half * 64, v[0]);
                 tmem_ld32(tD1[b] + lane_base + half * 64 + 32, v[1]);
                 tc_fence_before();
-                mbar_arrive(bar(D1_EMPTY + b));
+                warp_arrive(bar(D1_EMPTY + b));
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -188,7 +188,7 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
 #pragma unroll
                 for (int c = 0; c < 8; ++c) store_chunk8<FP16>(hi, lo, r, c * 8, &v[c >> 2][(c & 3) * 8]);
                 fence_proxy_async();
-                mbar_arrive(bar(S_FULL));
+                warp_arrive(bar(S_FULL));
             }
             if (i > 0) {
                 const int t = i - 1, b = t & 1;
@@ -199,7 +199,7 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 tmem_ld32(tD2[b] + lane_base + half * 64, v[0]);
                 tmem_ld32(tD2[b] + lane_base + half * 64 + 32, v[1]);
                 tc_fence_before();
-                mbar_arrive(bar(D2_EMPTY + b));
+                warp_arrive(bar(D2_EMPTY + b));
                 if (e < n_edges) {
                     const float c = cosine_cutoff(__ldg(edge_dist + e), cutoff);
                     float* out = filt + e * kF + half * 64;

@@ -325,7 +325,7 @@ class CFConvLayer(torch.autograd.Function):
         offset = _req(offset, torch.float32, "offset", 1)
         filt = filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2)
         out = _cfconv_fwd(x, filt, graph)
-        ctx.graph, ctx.coeff, ctx.cutoff = graph, coeff, cutoff
+        ctx.graph, ctx.coeff, ctx.cutoff, ctx.mode = graph, coeff, cutoff, FILTER_MODE
         ctx.save_for_backward(x, filt, w1, b1, w2, b2, offset)
         return out
 
@@ -338,6 +338,13 @@ class CFConvLayer(torch.autograd.Function):
         lib = _lib.load()
         F_, G = w1.size(0), w1.size(1)
         gx = _cfconv_bwd_x(filt, grad_out, g) if ctx.needs_input_grad[0] else None
+        gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
+        if ctx.mode != "simt" and F_ == 128 and G <= 63:
+            ws = torch.empty(lib.geossl_filter_bwd_tc_workspace(), dtype=torch.float32, device=x.device)
+            _timed("filter_bwd", lambda: lib.geossl_filter_bwd_tc(
+                _p(g.dist), _p(g.n_edges_dev), g.capacity, _p(offset), float(ctx.coeff), float(ctx.cutoff), G, F_, _p(w1), _p(b1),
+                _p(w2), _p(x), _p(grad_out), _p(g.src), _p(g.tgt), _p(ws), _p(gw1), _p(gb1), _p(gw2), _p(gb2), _stream()))
+            return gx, gw1, gb1, gw2, gb2, None, None, None, None
         gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
         ws = torch.empty(lib.geossl_filter_bwd_workspace(G, F_), dtype=torch.float32, device=x.device)
         _timed("filter_bwd", lambda: lib.geossl_filter_bwd(

@@ -122,6 +122,16 @@ int geossl_filter_bwd(const float* edge_dist, const int32_t* n_edges_dev, int64_
                       const float* grad_filt, float* workspace,
                       float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
 
+/* Same contract as geossl_filter_bwd (x / grad_out / src / edge_tgt form), on the tcgen05 tensor cores:
+ * F = 128, G <= 63, operands split into two bf16 parts, weight gradients accumulated in TMEM.
+ * workspace: geossl_filter_bwd_tc_workspace() floats. */
+int64_t geossl_filter_bwd_tc_workspace(void);
+int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int64_t capacity,
+                         const float* offset, float coeff, float cutoff, int G, int F,
+                         const float* w1, const float* b1, const float* w2,
+                         const float* x, const float* grad_out, const int32_t* src, const int32_t* edge_tgt,
+                         float* workspace, float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * DDM head.  Replaces the distance block of do_DDM (examples/pretrain_GeoSSL.py:197-205) and
  * NCSN_version_03.forward (examples/NCSN.py:183-212) + MultiLayerPerceptron (NCSN.py:9-43) and their

@@ -38,3 +38,10 @@ def rel_err(a, b):
     if denom == 0.0:
         return (a - b).abs().max().item()
     return (a - b).abs().max().item() / denom
+
+
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2 -- robust to the isolated ReLU-mask flips a 1e-6 perturbation of h can cause."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    n = b.norm().item()
+    return (a - b).norm().item() / (n if n else 1.0)

@@ -17,3 +17,13 @@ def lib():
     """The C-ABI library; GPU tests call the product through it."""
     from geossl_b200 import _lib
     return _lib.load()
+
+
+@pytest.fixture(params=["simt", "tc_fp16"])
+def filter_mode(request):
+    """Runs a test once on the exact fp32 CUDA-core filter kernels and once on the tcgen05 tensor-core ones."""
+    from geossl_b200 import ops
+    old = ops.FILTER_MODE
+    ops.FILTER_MODE = request.param
+    yield request.param
+    ops.FILTER_MODE = old

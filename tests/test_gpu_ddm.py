@@ -3,7 +3,7 @@ import pytest
 import torch
 
 from _build import grads_of, head_from, painn_from, schnet_from
-from _golden import Golden, rel_err
+from _golden import Golden, rel_err, rel_l2
 from geossl_b200 import ops
 from geossl_b200.data import AtomTupleBatch, synthetic_batch
 from geossl_b200.pretrain import default_args, do_DDM
@@ -56,7 +56,10 @@ def test_ddm_head_rng_contract():
 
 
 @pytest.mark.parametrize("name", ["ddm_schnet_small", "ddm_schnet_cfg1", "ddm_painn_small"])
-def test_do_ddm_vs_golden(name):
+def test_do_ddm_vs_golden(name, filter_mode):
+    """Loss rel 1e-5 in both modes.  Gradients: rel 1e-4 (max-norm) on the exact fp32 path; on the tensor-core path
+    the stated bound is rel 1e-4 in the L2 norm and 2e-3 in the max norm -- a ~1e-6 perturbation of h can flip an
+    isolated ReLU mask in the score MLP, which moves single gradient entries by O(1/pairs)."""
     g = Golden(name)
     c, i = g.cfg, g["in"]
     model = schnet_from(g, DEV) if c["model_3d"] == "schnet" else painn_from(g, DEV)
@@ -72,7 +75,10 @@ def test_do_ddm_vs_golden(name):
     for mod, grp in ((model, "grad"), (heads[0], "grad1"), (heads[1], "grad2")):
         got = grads_of(mod)
         for k, ref in g[grp].items():
-            assert rel_err(got[k], ref) <= TOL_GRAD, (grp, k, rel_err(got[k], ref))
+            if filter_mode == "simt":
+                assert rel_err(got[k], ref) <= TOL_GRAD, (grp, k, rel_err(got[k], ref))
+            else:
+                assert rel_l2(got[k], ref) <= TOL_GRAD and rel_err(got[k], ref) <= 2e-3, (grp, k, rel_l2(got[k], ref), rel_err(got[k], ref))
 
 
 @pytest.mark.parametrize("name", ["painn_small", "painn_full"])

@@ -23,7 +23,7 @@ def _layer_params(Fd, G, seed):
 
 
 @pytest.mark.parametrize("Fd,G,ng,lo,hi", [(128, 50, 6, 20, 40), (64, 51, 5, 5, 30), (32, 20, 4, 3, 12), (128, 64, 2, 70, 90)])
-def test_filter_and_cfconv_kernels_vs_oracle(Fd, G, ng, lo, hi):
+def test_filter_and_cfconv_kernels_vs_oracle(Fd, G, ng, lo, hi, filter_mode):
     b = synthetic_batch(ng, lo, hi, seed=Fd + G, with_pairs=False)
     cutoff = 10.0
     w1, b1, w2, b2 = _layer_params(Fd, G, 1)
@@ -81,7 +81,7 @@ def test_cfconv_is_deterministic_and_linear():
 
 
 @pytest.mark.parametrize("name", ["schnet_small", "schnet_trunc"])
-def test_schnet_module_vs_golden(name):
+def test_schnet_module_vs_golden(name, filter_mode):
     g = Golden(name)
     m = schnet_from(g, DEV)
     i = g["in"]
@@ -135,7 +135,7 @@ def test_md17_double_backward_vs_golden():
         assert rel_err(dict(lin.named_parameters())[k].grad, ref) <= 2e-4
 
 
-def test_full_size_forward_properties_config2():
+def test_full_size_forward_properties_config2(filter_mode):
     """Config 2 (256 x 30 atoms, H=F=128, G=50, L=6): permuting whole molecules permutes the result."""
     torch.manual_seed(0)
     from geossl_b200.Geom3D.models import SchNet

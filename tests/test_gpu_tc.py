@@ -65,3 +65,34 @@ def test_filter_fwd_tc_vs_oracle(mode, tol, G, ng, lo, hi):
     assert rel_err(filt[:e], W) <= tol, rel_err(filt[:e], W)
     simt = ops.filter_forward(graph, offset.to(DEV), coeff, cutoff, *dev, mode="simt")
     assert rel_err(filt[:e], simt[:e]) <= tol
+
+
+@pytest.mark.parametrize("G,ng,lo,hi", [(50, 8, 20, 40), (63, 3, 5, 9), (20, 40, 25, 35), (51, 300, 28, 32)])
+def test_filter_bwd_tc_vs_simt(G, ng, lo, hi):
+    """Tensor-core backward (bf16 split, TMEM-resident weight gradients) against the exact fp32 kernel."""
+    b = synthetic_batch(ng, lo, hi, seed=G + 1, with_pairs=False)
+    cutoff = 10.0
+    gen = torch.Generator().manual_seed(3)
+    params = [(torch.randn(128, G, generator=gen) * 0.3), torch.randn(128, generator=gen) * 0.1,
+              torch.randn(128, 128, generator=gen) * 0.15, torch.randn(128, generator=gen) * 0.1]
+    offset = torch.linspace(0.0, cutoff, G).to(DEV)
+    coeff = O.smearing_coeff(offset.cpu())
+    n = b.positions.shape[0]
+    x, gout = torch.randn(n, 128, generator=gen), torch.randn(n, 128, generator=gen) * 1e-3
+    graph = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), cutoff, num_graphs=ng)
+    res = {}
+    old = ops.FILTER_MODE
+    try:
+        for mode in ("simt", "tc_fp16"):
+            ops.FILTER_MODE = mode
+            leaves = [p.clone().to(DEV).requires_grad_() for p in params]
+            xc = x.to(DEV).requires_grad_()
+            out = ops.CFConvLayer.apply(xc, *leaves, offset, graph, coeff, cutoff)
+            out.backward(gout.to(DEV))
+            torch.cuda.synchronize()
+            res[mode] = [xc.grad] + [p.grad for p in leaves]
+    finally:
+        ops.FILTER_MODE = old
+    for name, a, ref in zip(("x", "w1", "b1", "w2", "b2"), res["tc_fp16"], res["simt"]):
+        assert torch.isfinite(a).all(), name
+        assert rel_err(a, ref) <= 5e-5, (name, rel_err(a, ref))
