@@ -42,6 +42,8 @@ _SIGNATURES = {
     "geossl_rowptr_from_sorted": (c_int, [c_p, c_i64, c_i64, c_p, c_p]),
     "geossl_filter_fwd": (c_int, [c_p, c_p, c_i64, c_p, c_f, c_f, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
     "geossl_filter_fwd_tc": (c_int, [c_p, c_p, c_i64, c_p, c_f, c_f, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_p]),
+    "geossl_debug_set_trace": (c_int, [c_p]),
+    "geossl_debug_set_trace_bwd": (c_int, [c_p]),
     "geossl_tc_selftest": (c_int, [c_int, c_int, c_p, c_p, c_int, c_int, c_p, c_p]),
     "geossl_cfconv_fwd": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
     "geossl_cfconv_bwd_x": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),

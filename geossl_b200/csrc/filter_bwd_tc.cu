@@ -14,17 +14,24 @@
 // (fp32 range for the gradient operands) and every product is three MMAs with fp32 accumulation.
 //
 // Replaces the autograd of schnet.py:141-145,186-187,190,194-195 w.r.t. the filter-network parameters.
-// Warp roles as in filter_tc.cu: warps 0-7 epilogue (lane quadrant x edge half), 8-11 producers, 12 MMA.
+// Warp roles as in filter_tc.cu: warps 0-15 epilogue (lane quadrant x edge quarter), 16-19 producers, 20 MMA.
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace geossl {
 namespace tc {
 
+__device__ long long* g_trace_bwd = nullptr;   // optional clock64() trace of CTA 0 (geossl_debug_set_trace_bwd)
+__device__ __forceinline__ void trace_b(int tile, int event) {
+    long long* t = g_trace_bwd;
+    if (t != nullptr && blockIdx.x == 0 && tile < 32 && (threadIdx.x & 31) == 0) t[tile * 16 + event] = clock64();
+}
+
 constexpr int kBT = 64;                  // edges per tile
 constexpr int kBlkW = 128 * 128;         // bytes of a [128 rows x 64 k] weight block
 constexpr int kBlkT = kBT * 128;         // bytes of a [64 rows x 64 k] tile block
-constexpr int kBwdThreads = 256 + 128 + 32;
+constexpr int kBwdEpiWarps = 16, kBwdEpiThreads = kBwdEpiWarps * 32, kBwdThreads = kBwdEpiThreads + 128 + 32;
+constexpr int kBwdProdWarp0 = kBwdEpiWarps, kBwdMmaWarp = kBwdEpiWarps + 4;
 constexpr bool kBwdFP16 = false;         // bf16 parts
 
 struct BwdLayout {
@@ -64,7 +71,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                      const float* __restrict__ x, const float* __restrict__ grad_out,
                      const int32_t* __restrict__ src, const int32_t* __restrict__ edge_tgt, float* __restrict__ workspace) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align1024(smem_raw);
     using L = BwdLayout;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + L::BAR;
@@ -101,15 +108,15 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(PHI_FULL_ + b), 4); mbar_init(bar(PHI_FREE_ + b), 1);
             mbar_init(bar(DU_FULL_ + b), 4);  mbar_init(bar(DU_FREE_ + b), 1);
-            mbar_init(bar(D1_FULL_ + b), 1);  mbar_init(bar(D1_FREE_ + b), 8);
-            mbar_init(bar(D3_FULL_ + b), 1);  mbar_init(bar(D3_FREE_ + b), 8);
+            mbar_init(bar(D1_FULL_ + b), 1);  mbar_init(bar(D1_FREE_ + b), kBwdEpiWarps);
+            mbar_init(bar(D3_FULL_ + b), 1);  mbar_init(bar(D3_FREE_ + b), kBwdEpiWarps);
         }
-        mbar_init(bar(S_FULL_), 8);  mbar_init(bar(S_FREE_), 1);
-        mbar_init(bar(DA_FULL_), 8); mbar_init(bar(DA_FREE_), 1);
+        mbar_init(bar(S_FULL_), kBwdEpiWarps);  mbar_init(bar(S_FREE_), 1);
+        mbar_init(bar(DA_FULL_), kBwdEpiWarps); mbar_init(bar(DA_FREE_), 1);
         mbar_init(bar(DONE_), 1);
         fence_barrier_init();
     }
-    if (warp == 12) tmem_alloc(sbase + L::TMEM_PTR, 512);
+    if (warp == kBwdMmaWarp) tmem_alloc(sbase + L::TMEM_PTR, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -118,9 +125,9 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
     const uint32_t tDW2 = tmem, tDW1 = tmem + 128;
     const uint32_t tD1[2] = {tmem + 192, tmem + 256}, tD3[2] = {tmem + 320, tmem + 384};
 
-    if (warp >= 8 && warp < 12) {
+    if (warp >= kBwdProdWarp0 && warp < kBwdMmaWarp) {
         // ===================== producers: rbf tile and dU tile
-        const int tp = tid - 256;
+        const int tp = tid - kBwdEpiThreads;
         const int cg = tp & 15, ro = tp >> 4;                            // dU: 8 columns 8cg.., rows ro + 8 s
         float acc[8];
 #pragma unroll
@@ -130,6 +137,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             const int b = i & 1;
             {   // ---- rbf(i): thread = (row, half of the 8 chunks)
                 mbar_wait(bar(PHI_FREE_ + b), ((i >> 1) & 1) ^ 1);
+                if (warp == kBwdProdWarp0) trace_b(i, 0);
                 const int row = tp >> 1, c0 = (tp & 1) * 4;
                 const int64_t e = e_base + row;
                 const bool valid = e < n_edges;
@@ -149,9 +157,11 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 }
                 fence_proxy_async();
                 warp_arrive(bar(PHI_FULL_ + b));
+                if (warp == kBwdProdWarp0) trace_b(i, 1);
             }
             {   // ---- dU(i)
                 mbar_wait(bar(DU_FREE_ + b), ((i >> 1) & 1) ^ 1);
+                if (warp == kBwdProdWarp0) trace_b(i, 2);
                 uint8_t* hi = smem + L::DU + b * 4 * kBlkT + (cg >> 3) * kBlkT;
                 uint8_t* lo = hi + 2 * kBlkT;
 #pragma unroll
@@ -186,6 +196,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 }
                 fence_proxy_async();
                 warp_arrive(bar(DU_FULL_ + b));
+                if (warp == kBwdProdWarp0) trace_b(i, 3);
             }
         }
         // db2[o] = sum over the 8 row groups; scratch = dU buffer 0 once every MMA has retired
@@ -198,7 +209,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
 #pragma unroll
         for (int r = 0; r < 8; ++r) s += red[r * 128 + tp];
         ws[Part::kB2 + tp] = s;
-    } else if (warp == 12) {
+    } else if (warp == kBwdMmaWarp) {
         // ===================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t fmt = Split<kBwdFP16>::kFmt;
@@ -225,6 +236,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 mbar_wait(bar(DU_FULL_ + b), (i >> 1) & 1);
                 mbar_wait(bar(D3_FREE_ + b), ((i >> 1) & 1) ^ 1);
                 tc_fence_after();
+                trace_b(i, 4);
                 {
                     const uint64_t uh = desc_k_sw128(du), ul = desc_k_sw128(du + 2 * kBlkT);
 #pragma unroll
@@ -239,6 +251,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 // ---- WG2(i): DW2 += dU^T s
                 mbar_wait(bar(S_FULL_), i & 1);
                 tc_fence_after();
+                trace_b(i, 5);
                 {
                     const uint64_t uh = desc_mn_sw128(du, kBlkT), ul = desc_mn_sw128(du + 2 * kBlkT, kBlkT);
 #pragma unroll
@@ -250,10 +263,12 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 tc_commit(bar(S_FREE_));
                 tc_commit(bar(DU_FREE_ + b));
                 // ---- MMA1(i+1)
+                trace_b(i, 6);
                 if (i + 1 < my_tiles) mma1(i + 1);
                 // ---- WG1(i): DW1 += dA^T rbf
                 mbar_wait(bar(DA_FULL_), i & 1);
                 tc_fence_after();
+                trace_b(i, 7);
                 {
                     const uint32_t ph_addr = sbase + L::PHI + b * 2 * kBlkT;
                     const uint64_t ph = desc_mn_sw128(ph_addr, kBlkT), pl = desc_mn_sw128(ph_addr + kBlkT, kBlkT);
@@ -265,84 +280,89 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 }
                 tc_commit(bar(DA_FREE_));
                 tc_commit(bar(PHI_FREE_ + b));
+                trace_b(i, 8);
             }
             tc_commit(bar(DONE_));
         }
     } else {
-        // ===================== epilogue warps (TMEM lane = feature, columns = edges)
-        const int q = warp & 3, eh = warp >> 2;
+        // ===================== epilogue warps (TMEM lane = feature, columns = edges): warp = (quadrant q, edge quarter eq)
+        const int q = warp & 3, eq = warp >> 2;
         const int f = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const float b1f = sB1[f];
         uint8_t* sa_hi = smem + L::SA + (f >> 6) * kBlkT;
         uint8_t* sa_lo = sa_hi + 2 * kBlkT;
         const uint32_t kcol = f & 63;
-        float sig[32];
+        float sig[16];
         auto e1 = [&](int i) {
             const int b = i & 1;
             mbar_wait(bar(D1_FULL_ + b), (i >> 1) & 1);
             tc_fence_after();
-            float a[32];
-            tmem_ld32(tD1[b] + lane_base + eh * 32, a);
+            if (warp == 0) trace_b(i, 9);
+            float a[16];
+            tmem_ld16(tD1[b] + lane_base + eq * 16, a);
             tc_fence_before();
             warp_arrive(bar(D1_FREE_ + b));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float av = a[j] + b1f;
                 a[j] = ssp_fast(av);
-                sig[j] = av > 20.f ? 1.f : __frcp_rn(1.f + exp2f(-av * 1.4426950408889634f));
+                sig[j] = av > 20.f ? 1.f : sigmoid_fast(av);
             }
             if (i > 0) mbar_wait(bar(DA_FREE_), (i - 1) & 1);            // WG1(i-1) has consumed dA in the shared S/dA buffer
 #pragma unroll
-            for (int j = 0; j < 32; ++j) store_split_bf16(sa_hi, sa_lo, eh * 32 + j, kcol, a[j]);
+            for (int j = 0; j < 16; ++j) store_split_bf16(sa_hi, sa_lo, eq * 16 + j, kcol, a[j]);
             fence_proxy_async();
             warp_arrive(bar(S_FULL_));
+            if (warp == 0) trace_b(i, 10);
         };
         if (my_tiles > 0) e1(0);
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1;
             mbar_wait(bar(D3_FULL_ + b), (i >> 1) & 1);
             tc_fence_after();
-            float ds[32];
-            tmem_ld32(tD3[b] + lane_base + eh * 32, ds);
+            if (warp == 0) trace_b(i, 11);
+            float ds[16];
+            tmem_ld16(tD3[b] + lane_base + eq * 16, ds);
             tc_fence_before();
             warp_arrive(bar(D3_FREE_ + b));
             mbar_wait(bar(S_FREE_), i & 1);                              // WG2(i) has consumed S
+            if (warp == 0) trace_b(i, 12);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) store_split_bf16(sa_hi, sa_lo, eh * 32 + j, kcol, ds[j] * sig[j]);
+            for (int j = 0; j < 16; ++j) store_split_bf16(sa_hi, sa_lo, eq * 16 + j, kcol, ds[j] * sig[j]);
             fence_proxy_async();
             warp_arrive(bar(DA_FULL_));
+            if (warp == 0) trace_b(i, 13);
             if (i + 1 < my_tiles) e1(i + 1);
         }
         // ---- accumulators -> per-CTA partials
         mbar_wait(bar(DONE_), 0);
         tc_fence_after();
         if (my_tiles > 0) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            {
                 float v[32];
-                tmem_ld32(tDW2 + lane_base + eh * 64 + h * 32, v);
-                float* dst = ws + Part::kW2 + f * 128 + eh * 64 + h * 32;
+                tmem_ld32(tDW2 + lane_base + eq * 32, v);
+                float* dst = ws + Part::kW2 + f * 128 + eq * 32;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-            float v[32];
-            tmem_ld32(tDW1 + lane_base + eh * 32, v);
+            float v[16];
+            tmem_ld16(tDW1 + lane_base + eq * 16, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int g = eh * 32 + j;
+            for (int j = 0; j < 16; ++j) {
+                const int g = eq * 16 + j;
                 if (g < G) ws[Part::kW1 + g * 128 + f] = v[j];
                 if (g == 63) ws[Part::kB1 + f] = v[j];
             }
         } else {
-            for (int c = eh * 64; c < eh * 64 + 64; ++c) ws[Part::kW2 + f * 128 + c] = 0.f;
-            for (int g = eh * 32; g < eh * 32 + 32; ++g) ws[Part::kW1 + g * 128 + f] = 0.f;
-            if (eh == 1) ws[Part::kB1 + f] = 0.f;
+            for (int c = eq * 32; c < eq * 32 + 32; ++c) ws[Part::kW2 + f * 128 + c] = 0.f;
+            for (int g = eq * 16; g < eq * 16 + 16; ++g) ws[Part::kW1 + g * 128 + f] = 0.f;
+            if (eq == 3) ws[Part::kB1 + f] = 0.f;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == kBwdMmaWarp) {
         __syncwarp();
         tmem_dealloc(tmem, 512);
     }
@@ -370,6 +390,11 @@ __global__ void filter_bwd_tc_reduce_kernel(const float* __restrict__ workspace,
 using namespace geossl;
 
 extern "C" {
+
+int geossl_debug_set_trace_bwd(long long* device_buffer) {
+    GEOSSL_CUDA(cudaMemcpyToSymbol(tc::g_trace_bwd, &device_buffer, sizeof(device_buffer)));
+    return 0;
+}
 
 int64_t geossl_filter_bwd_tc_workspace(void) { return (int64_t)kNumSM * tc::Part::kFloats; }
 

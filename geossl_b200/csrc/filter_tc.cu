@@ -6,10 +6,15 @@
 // Replaces GaussianSmearing.forward (Geom3D/models/schnet.py:205-207), InteractionBlock.mlp
 // (schnet.py:141-145) and the cutoff product of CFConv.forward (schnet.py:186-187).  F = 128, G <= 64.
 //
-// One persistent CTA per SM, 128-edge tiles, 13 warps:
-//   warps 0-7   epilogue: TMEM lane = edge row; warps 0-3 own accumulator columns 0-63, warps 4-7 64-127
-//   warps 8-11  producer: rbf tile (hi/lo, K-major SW128) for the next tile, double buffered
-//   warp 12     TMEM allocation + the single MMA-issuing thread
+// One persistent CTA per SM, 128-edge tiles, 25 warps:
+//   warps 0-15  epilogue (quadrant = warp & 3, 32 accumulator columns per warp = warp >> 2):
+//               E1 reads D1 (lanes = edges) and writes the s tile with 16-byte row stores;
+//               E2 reads D2^T (lanes = FEATURES, columns = edges -- MMA2 is issued with the operands swapped),
+//               so every store instruction writes 128 contiguous bytes of one W_e row
+//   warps 16-23 producer: rbf tile (hi/lo, K-major SW128) for the next tile, double buffered
+//   warp 24     TMEM allocation + the single MMA-issuing thread
+// Measured structure (profiles/r01_v4_trace_fwd.txt -> v5): the epilogue is MUFU bound (2 MUFU per softplus),
+// the tensor pipe needs ~2.3 k cycles per tile, uncoalesced row-per-thread stores cost 4 k LSU cycles per tile.
 // Operands never come from HBM (they are computed on chip), so tiles are written with st.shared in the
 // swizzled layout and published to the async proxy with fence.proxy.async; the two weight matrices are
 // split once per CTA into shared memory.  Accumulators D1/D2 are double buffered in TMEM (4 x 128 columns).
@@ -20,10 +25,19 @@
 namespace geossl {
 namespace tc {
 
+// Optional per-phase clock64() trace of CTA 0 (set with geossl_debug_set_trace); slot = tile*16 + event.
+__device__ long long* g_trace = nullptr;
+__device__ __forceinline__ void trace(int tile, int event) {
+    long long* t = g_trace;
+    if (t != nullptr && blockIdx.x == 0 && tile < 32 && (threadIdx.x & 31) == 0) t[tile * 16 + event] = clock64();
+}
+
 constexpr int kF = 128;            // filters
 constexpr int kTile = 128;         // edges per tile (UMMA M)
 constexpr int kBlk = kTile * 128;  // bytes of one [128 rows x 64 k] 16-bit block
-constexpr int kEpiThreads = 256, kProdThreads = 128, kThreads = kEpiThreads + kProdThreads + 32;
+constexpr int kEpiWarps = 16, kEpiThreads = kEpiWarps * 32, kProdWarps = 8, kProdThreads = kProdWarps * 32;
+constexpr int kThreads = kEpiThreads + kProdThreads + 32;
+constexpr int kProdWarp0 = kEpiWarps, kMmaWarp = kEpiWarps + kProdWarps;
 
 struct FwdLayout {                 // byte offsets from the 1024-aligned dynamic smem base
     static constexpr int W1_hi = 0, W1_lo = W1_hi + kBlk;                 // [128 f][64 g]
@@ -48,7 +62,7 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                      const float* __restrict__ b2, float* __restrict__ filt) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align1024(smem_raw);
     using L = FwdLayout;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + L::BAR;
@@ -80,7 +94,7 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
         store_chunk8<FP16>(smem + L::W2_hi + blk * kBlk, smem + L::W2_lo + blk * kBlk, o, (c & 7) * 8, x);
     }
     if (tid < kF) { sB1[tid] = __ldg(b1 + tid); sB2[tid] = __ldg(b2 + tid); }
-    if (tid < 64) sOff[tid] = (tid < G) ? __ldg(offset + tid) : 0.f;
+    if (tid < 64) sOff[tid] = (tid < G) ? __ldg(offset + tid) : 1e18f;   // padded gaussians: exp(coeff * 1e36) == 0, no branch
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar(PHI_FULL + b), kProdThreads / 32);
@@ -94,7 +108,7 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
         mbar_init(bar(S_EMPTY), 1);
         fence_barrier_init();
     }
-    if (warp == 12) tmem_alloc(sbase + L::TMEM_PTR, 512);
+    if (warp == kMmaWarp) tmem_alloc(sbase + L::TMEM_PTR, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -102,31 +116,34 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR);
     const uint32_t tD1[2] = {tmem, tmem + 128}, tD2[2] = {tmem + 256, tmem + 384};
 
-    if (warp >= 8 && warp < 12) {
-        // ===================== producer: rbf tile of local tile i into PHI[i & 1]
-        const int r = tid - kEpiThreads;                              // edge row 0..127
+    if (warp >= kProdWarp0 && warp < kMmaWarp) {
+        // ===================== producer: rbf tile of local tile i into PHI[i & 1]; thread = (row, half of the 64 columns)
+        const int tp = tid - kEpiThreads;
+        const int r = tp & 127, c0 = (tp >> 7) * 4;
+        const float cl2 = coeff * 1.4426950408889634f;                // exp(coeff * x) = 2^(cl2 * x)
         for (int i = 0; i < my_tiles; ++i) {
             const int64_t e = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTile + r;
             const int b = i & 1;
             mbar_wait(bar(PHI_EMPTY + b), ((i >> 1) & 1) ^ 1);
+            if (warp == kProdWarp0) trace(i, 0);
             const float d = (e < n_edges) ? __ldg(edge_dist + e) : 0.f;
             uint8_t* hi = smem + L::PHI + b * 2 * kBlk;
             uint8_t* lo = hi + kBlk;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = c0; c < c0 + 4; ++c) {
                 float x[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int g = c * 8 + j;
-                    const float diff = d - sOff[g];
-                    x[j] = (g < G) ? __expf(__fmul_rn(coeff, __fmul_rn(diff, diff))) : 0.f;
+                    const float diff = d - sOff[c * 8 + j];
+                    x[j] = ex2_approx(cl2 * (diff * diff));
                 }
                 store_chunk8<FP16>(hi, lo, r, c * 8, x);
             }
             fence_proxy_async();
             warp_arrive(bar(PHI_FULL + b));
+            if (warp == kProdWarp0) trace(i, 1);
         }
-    } else if (warp == 12) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer (one thread)
         if (lane == 0) {
             const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, kTile, kF);
@@ -138,12 +155,14 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 mbar_wait(bar(PHI_FULL + b), (i >> 1) & 1);
                 mbar_wait(bar(D1_EMPTY + b), ((i >> 1) & 1) ^ 1);
                 tc_fence_after();
+                trace(i, 2);
                 const uint64_t dPh = desc_k_sw128(sbase + L::PHI + b * 2 * kBlk), dPl = desc_k_sw128(sbase + L::PHI + b * 2 * kBlk + kBlk);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)                         // K = 64 = 4 x 16 (+32 bytes = +2 encoded)
                     mma3(tD1[b], dPh + 2 * kk, dPl + 2 * kk, dW1h + 2 * kk, dW1l + 2 * kk, idesc, kk > 0);
                 tc_commit(bar(PHI_EMPTY + b));
                 tc_commit(bar(D1_FULL + b));
+                trace(i, 3);
             };
             if (my_tiles > 0) issue_mma1(0);
             for (int i = 0; i < my_tiles; ++i) {
@@ -152,73 +171,75 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 mbar_wait(bar(S_FULL), i & 1);
                 mbar_wait(bar(D2_EMPTY + b), ((i >> 1) & 1) ^ 1);
                 tc_fence_after();
+                trace(i, 4);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)                         // K = 128 = 2 blocks x 4 x 16
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint32_t o = kb * (kBlk >> 4) + 2 * kk;
-                        mma3(tD2[b], dSh + o, dSl + o, dW2h + o, dW2l + o, idesc, (kb | kk) > 0);
+                        mma3(tD2[b], dW2h + o, dW2l + o, dSh + o, dSl + o, idesc, (kb | kk) > 0);   // D2^T = W2 . S^T
                     }
                 tc_commit(bar(S_EMPTY));
                 tc_commit(bar(D2_FULL + b));
+                trace(i, 5);
             }
         }
     } else {
-        // ===================== epilogue warps: E1(i) then E2(i-1)
-        const int q = warp & 3, half = warp >> 2;                     // lane quadrant, column half
-        const int r = q * 32 + lane;                                  // edge row in the tile = TMEM lane
+        // ===================== epilogue warps: E1(i) then E2(i-1); warp = (lane quadrant q, column quarter cq)
+        const int q = warp & 3, cq = warp >> 2;
+        const int r = q * 32 + lane;                                  // TMEM lane: edge row in E1, FEATURE in E2
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int col0 = cq * 32;                                     // this warp's 32 accumulator columns
+        const float b2f = sB2[r];
         for (int i = 0; i <= my_tiles; ++i) {
             if (i < my_tiles) {
                 const int b = i & 1;
                 mbar_wait(bar(D1_FULL + b), (i >> 1) & 1);
                 tc_fence_after();
-                float v[2][32];
-                tmem_ld32(tD1[b] + lane_base + half * 64, v[0]);
-                tmem_ld32(tD1[b] + lane_base + half * 64 + 32, v[1]);
+                if (warp == 0) trace(i, 6);
+                float v[32];
+                tmem_ld32(tD1[b] + lane_base + col0, v);
                 tc_fence_before();
                 warp_arrive(bar(D1_EMPTY + b));
+                if (warp == 0) trace(i, 7);
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[h][j] = ssp_fast(v[h][j] + sB1[half * 64 + h * 32 + j]);
+                for (int j = 0; j < 32; ++j) v[j] = ssp_fast(v[j] + sB1[col0 + j]);
+                if (warp == 0) trace(i, 8);
                 mbar_wait(bar(S_EMPTY), (i & 1) ^ 1);                  // MMA2 of the previous tile released S
-                uint8_t* hi = smem + L::S + half * kBlk;               // k-block `half` holds columns 64*half..+63
+                if (warp == 0) trace(i, 9);
+                uint8_t* hi = smem + L::S + (cq >> 1) * kBlk;          // k-block holds columns 64*(cq>>1)..+63
                 uint8_t* lo = hi + 2 * kBlk;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) store_chunk8<FP16>(hi, lo, r, c * 8, &v[c >> 2][(c & 3) * 8]);
+                for (int c = 0; c < 4; ++c) store_chunk8<FP16>(hi, lo, r, (cq & 1) * 32 + c * 8, &v[c * 8]);
                 fence_proxy_async();
                 warp_arrive(bar(S_FULL));
+                if (warp == 0) trace(i, 10);
             }
             if (i > 0) {
                 const int t = i - 1, b = t & 1;
-                const int64_t e = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile + r;
+                const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile + col0;
+                // lane j holds the cutoff of edge column j of this warp; broadcast by shuffle in the store loop
+                const float myc = (e0 + lane < n_edges) ? cosine_cutoff(__ldg(edge_dist + e0 + lane), cutoff) : 0.f;
                 mbar_wait(bar(D2_FULL + b), (t >> 1) & 1);
                 tc_fence_after();
-                float v[2][32];
-                tmem_ld32(tD2[b] + lane_base + half * 64, v[0]);
-                tmem_ld32(tD2[b] + lane_base + half * 64 + 32, v[1]);
+                if (warp == 0) trace(t, 11);
+                float v[32];
+                tmem_ld32(tD2[b] + lane_base + col0, v);               // lane = feature r, columns = edges col0..col0+31
                 tc_fence_before();
                 warp_arrive(bar(D2_EMPTY + b));
-                if (e < n_edges) {
-                    const float c = cosine_cutoff(__ldg(edge_dist + e), cutoff);
-                    float* out = filt + e * kF + half * 64;
+                float* out = filt + e0 * kF + r;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const int col = half * 64 + h * 32 + j;
-                            float4 o4 = make_float4((v[h][j] + sB2[col]) * c, (v[h][j + 1] + sB2[col + 1]) * c,
-                                                    (v[h][j + 2] + sB2[col + 2]) * c, (v[h][j + 3] + sB2[col + 3]) * c);
-                            *reinterpret_cast<float4*>(out + h * 32 + j) = o4;
-                        }
+                for (int j = 0; j < 32; ++j) {
+                    const float c = __shfl_sync(0xffffffffu, myc, j);
+                    if (e0 + j < n_edges) out[(int64_t)j * kF] = (v[j] + b2f) * c;        // 32 lanes -> 128 contiguous bytes
                 }
+                if (warp == 0) trace(t, 12);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == kMmaWarp) {
         __syncwarp();
         tmem_dealloc(tmem, 512);
     }
@@ -231,13 +252,13 @@ template <bool FP16>
 __global__ void __launch_bounds__(128, 1)
 tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restrict__ B, int K, int N, float* __restrict__ D) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align1024(smem_raw);
     const uint32_t sbase = smem_u32(smem);
     // A_hi | A_lo | B_hi | B_lo, each 2 blocks of 16 KB; barrier + tmem ptr after
     uint8_t* Ah = smem; uint8_t* Al = smem + 2 * kBlk; uint8_t* Bh = smem + 4 * kBlk; uint8_t* Bl = smem + 6 * kBlk;
     const uint32_t bar = sbase + 8 * kBlk, tptr = bar + 8;
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2 || mode == 3) {
         for (int c = 0; c < K / 8; ++c) {                            // thread = row
             store_chunk8<FP16>(Ah + (c >> 3) * kBlk, Al + (c >> 3) * kBlk, tid, (c & 7) * 8, A + tid * K + c * 8);
             store_chunk8<FP16>(Bh + (c >> 3) * kBlk, Bl + (c >> 3) * kBlk, tid, (c & 7) * 8, B + tid * K + c * 8);
@@ -249,12 +270,20 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
             store_chunk8<FP16>(Bh + (c >> 3) * kBlk, Bl + (c >> 3) * kBlk, tid, (c & 7) * 8, B + tid * N + c * 8);
     }
     if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(tptr, 128);
+    if (warp == 0) tmem_alloc(tptr, 256);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 8 * kBlk + 8);
+    if (mode == 3) {                                                 // A (hi | lo) into TMEM columns [128,128+K/2) | [192,192+K/2)
+        const uint32_t lane_b = (uint32_t)(warp * 32) << 16;
+        for (int k0 = 0; k0 < K; k0 += 16) tmem_store_split16<FP16>(tmem + lane_b + 128 + k0 / 2, tmem + lane_b + 192 + k0 / 2, A + tid * K + k0);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     if (tid == 0) {
         if (mode == 0) {
             const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, 128);
@@ -264,6 +293,28 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
                 const uint32_t o = (ks >> 2) * (kBlk >> 4) + 2 * (ks & 3);
                 mma3(tmem, ah + o, al + o, bh + o, bl + o, idesc, ks > 0);
             }
+        } else if (mode == 3) {
+            const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, N);
+            const uint64_t bh = desc_k_sw128(sbase + 4 * kBlk), bl = desc_k_sw128(sbase + 6 * kBlk);
+            const long long t0 = clock64();
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint32_t o = (ks >> 2) * (kBlk >> 4) + 2 * (ks & 3);
+                mma3_ts(tmem, tmem + 128 + ks * 8, tmem + 192 + ks * 8, bh + o, bl + o, idesc, ks > 0);
+            }
+            (void)t0;
+        } else if (mode == 2) {
+            // throughput probe: 240 back-to-back MMAs (K = 64 reused), N in {64,128}; cycles -> D[0..1] as raw ints
+            const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, N);
+            const uint64_t ah = desc_k_sw128(sbase), bh = desc_k_sw128(sbase + 4 * kBlk);
+            const long long t0 = clock64();
+            for (int rep = 0; rep < 60; ++rep)
+                for (int ks = 0; ks < 4; ++ks) mma_f16_ss(tmem, ah + 2 * ks, bh + 2 * ks, idesc, 1u);
+            const long long t1 = clock64();
+            tc_commit(bar);
+            mbar_wait(bar, 0);
+            const long long t2 = clock64();
+            reinterpret_cast<long long*>(D)[0] = t1 - t0;
+            reinterpret_cast<long long*>(D)[1] = t2 - t0;
         } else {
             const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, N, 1, 1);
             const uint64_t ah = desc_mn_sw128(sbase, kBlk), al = desc_mn_sw128(sbase + 2 * kBlk, kBlk);
@@ -273,12 +324,12 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
                 mma3(tmem, ah + o, al + o, bh + o, bl + o, idesc, ks > 0);
             }
         }
-        tc_commit(bar);
+        if (mode != 2) tc_commit(bar);
     }
     mbar_wait(bar, 0);
     tc_fence_after();
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    for (int c0 = 0; c0 < N; c0 += 32) {
+    for (int c0 = 0; c0 < N && mode != 2; c0 += 32) {
         float v[32];
         tmem_ld32(tmem + lane_base + c0, v);
         for (int j = 0; j < 32; ++j) D[tid * N + c0 + j] = v[j];
@@ -287,7 +338,7 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
     __syncthreads();
     if (warp == 0) {
         __syncwarp();
-        tmem_dealloc(tmem, 128);
+        tmem_dealloc(tmem, 256);
     }
 }
 
@@ -298,9 +349,15 @@ using namespace geossl;
 
 extern "C" {
 
+int geossl_debug_set_trace(long long* device_buffer) {
+    GEOSSL_CUDA(cudaMemcpyToSymbol(tc::g_trace, &device_buffer, sizeof(device_buffer)));
+    return 0;
+}
+
 int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream) {
     GEOSSL_REQUIRE(a && b && d, "null pointer");
-    GEOSSL_REQUIRE((mode == 0 && (K == 64 || K == 128) && N == 128) || (mode == 1 && K == 128 && (N == 64 || N == 128)),
+    GEOSSL_REQUIRE((mode == 0 && (K == 64 || K == 128) && N == 128) || (mode == 1 && K == 128 && (N == 64 || N == 128)) ||
+                   (mode == 2 && K == 64 && (N == 64 || N == 128)) || (mode == 3 && (K == 64 || K == 128) && (N == 64 || N == 128)),
                    "unsupported shape");
     const size_t smem = 8 * tc::kBlk + 64 + 1024;
     if (fp16) {

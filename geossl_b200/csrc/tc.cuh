@@ -73,6 +73,22 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// D[tmem] (+)= A[tmem] . B[smem desc]^T : A (M = 128 lanes) lives in tensor memory, K-major, two 16-bit values per
+// 32-bit column (column c of the operand holds k = 2c in its low half and k = 2c+1 in its high half).
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32*(warp%4) + laneid) -> registers
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -161,6 +177,23 @@ __device__ __forceinline__ void store_chunk8(uint8_t* hi_block, uint8_t* lo_bloc
     *reinterpret_cast<uint4*>(lo_block + off) = l;
 }
 
+// 16 consecutive K values of this thread's row -> the hi and lo images of a TMEM-resident A operand (8 columns each).
+template <bool FP16>
+__device__ __forceinline__ void tmem_store_split16(uint32_t hi_taddr, uint32_t lo_taddr, const float* x) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Split<FP16>::pair(x[2 * j], x[2 * j + 1], h[j], l[j]);
+    tmem_st8(hi_taddr, h);
+    tmem_st8(lo_taddr, l);
+}
+// Three-product group with the A operand in tensor memory.
+__device__ __forceinline__ void mma3_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                        uint32_t idesc, uint32_t accumulate) {
+    mma_f16_ts(d_tmem, a_hi, b_hi, idesc, accumulate);
+    mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1u);
+    mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1u);
+}
+
 // The three-product MMA group for one 16-wide K step.
 __device__ __forceinline__ void mma3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                      uint32_t idesc, uint32_t accumulate) {
@@ -171,10 +204,40 @@ __device__ __forceinline__ void mma3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_
 
 // Fast shifted softplus: max(x,0) + log1p(exp(-|x|)) - log 2 on the MUFU ex2/lg2 units.
 // Absolute error <= ~4e-7 (lg2.approx on [1,2]); torch's threshold-20 branch is reproduced.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// (above torch's threshold of 20 the formula already returns x exactly in fp32: log1p(exp(-20)) < ulp(20)/2)
 __device__ __forceinline__ float ssp_fast(float x) {
-    const float t = exp2f(-fabsf(x) * 1.4426950408889634f);
-    const float l = __log2f(1.0f + t) * 0.6931471805599453f;
-    return (x > 20.f ? x : fmaxf(x, 0.f) + l) - kLog2;
+    const float t = ex2_approx(-fabsf(x) * 1.4426950408889634f);
+    return fmaf(lg2_approx(1.0f + t), 0.6931471805599453f, fmaxf(x, 0.f)) - kLog2;
+}
+// sigmoid(x) = d/dx softplus(x)
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    return __frcp_rn(1.0f + ex2_approx(-x * 1.4426950408889634f));
+}
+// 1024-byte aligned view of the dynamic shared memory that keeps the shared address space visible to the compiler
+__device__ __forceinline__ uint8_t* align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
+
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 }  // namespace tc

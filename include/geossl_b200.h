@@ -91,9 +91,15 @@ int geossl_filter_fwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
                          const float* w1, const float* b1, const float* w2, const float* b2,
                          float* filt, int bf16_parts, void* stream);
 
+/* Debug: per-phase clock64() trace of CTA 0 of the tensor-core filter kernels into a device buffer of 512
+ * int64 slots (slot = tile*16 + event); NULL disables.  Used by profiles/trace_tc.py. */
+int geossl_debug_set_trace(long long* device_buffer);       /* forward kernel */
+int geossl_debug_set_trace_bwd(long long* device_buffer);   /* backward kernel */
+
 /* Self test of the tcgen05 plumbing (descriptors, swizzle, TMEM): one 128 x N x K split-precision GEMM.
  * mode 0: d[m][n] = sum_k a[m][k] b[n][k]  (a (128,K), b (128,K), K in {64,128}, N = 128; K-major operands)
- * mode 1: d[m][n] = sum_k a[k][m] b[k][n]  (a (128,128), b (128,N), N in {64,128}; MN-major operands) */
+ * mode 1: d[m][n] = sum_k a[k][m] b[k][n]  (a (128,128), b (128,N), N in {64,128}; MN-major operands)
+ * mode 2: throughput probe (cycle counts in d[0..1]);  mode 3: as mode 0 with A resident in tensor memory, b (N,K) */
 int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream);
 
 /* m_i = sum_{e in row i} x[src_e] * W_e   (atomic-free segmented reduction, one warp per row). */

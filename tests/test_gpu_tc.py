@@ -42,6 +42,16 @@ def test_tc_selftest_mn_major(fp16, tol, N):
     assert rel_err(d, ref) <= tol, rel_err(d, ref)
 
 
+@pytest.mark.parametrize("fp16,tol", [(1, 2e-6), (0, 4e-5)])
+@pytest.mark.parametrize("K,N", [(64, 128), (128, 128), (128, 64)])
+def test_tc_selftest_a_in_tmem(fp16, tol, K, N):
+    g = torch.Generator().manual_seed(K + N + fp16)
+    a, b = torch.randn(128, K, generator=g), torch.randn(128, K, generator=g)     # only the first N rows of b are used
+    d = _selftest(3, fp16, a.to(DEV), b.to(DEV), K, N)
+    ref = a.double() @ b[:N].double().t()
+    assert rel_err(d, ref) <= tol, rel_err(d, ref)
+
+
 @pytest.mark.parametrize("mode,tol", [("tc_fp16", 3e-6), ("tc_bf16", 1e-4)])
 @pytest.mark.parametrize("G,ng,lo,hi", [(50, 8, 20, 40), (64, 3, 5, 9), (20, 40, 25, 35)])
 def test_filter_fwd_tc_vs_oracle(mode, tol, G, ng, lo, hi):
