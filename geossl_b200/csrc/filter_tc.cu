@@ -258,7 +258,7 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
     uint8_t* Ah = smem; uint8_t* Al = smem + 2 * kBlk; uint8_t* Bh = smem + 4 * kBlk; uint8_t* Bl = smem + 6 * kBlk;
     const uint32_t bar = sbase + 8 * kBlk, tptr = bar + 8;
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (mode == 0 || mode == 2 || mode == 3) {
+    if (mode != 1) {
         for (int c = 0; c < K / 8; ++c) {                            // thread = row
             store_chunk8<FP16>(Ah + (c >> 3) * kBlk, Al + (c >> 3) * kBlk, tid, (c & 7) * 8, A + tid * K + c * 8);
             store_chunk8<FP16>(Bh + (c >> 3) * kBlk, Bl + (c >> 3) * kBlk, tid, (c & 7) * 8, B + tid * K + c * 8);
@@ -302,6 +302,23 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
                 mma3_ts(tmem, tmem + 128 + ks * 8, tmem + 192 + ks * 8, bh + o, bl + o, idesc, ks > 0);
             }
             (void)t0;
+        } else if (mode == 4 || mode == 5) {
+            // throughput probes: mode 4 = A in TMEM (K-major B from smem), mode 5 = both operands MN-major from smem
+            const uint32_t idesc = mode == 4 ? idesc_f16(Split<FP16>::kFmt, 128, N) : idesc_f16(Split<FP16>::kFmt, 128, N, 1, 1);
+            const uint64_t bh = desc_k_sw128(sbase + 4 * kBlk);
+            const uint64_t am = desc_mn_sw128(sbase, kBlk), bm = desc_mn_sw128(sbase + 4 * kBlk, kBlk);
+            const long long t0 = clock64();
+            for (int rep = 0; rep < 60; ++rep)
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (mode == 4) mma_f16_ts(tmem, tmem + 128 + ks * 8, bh + 2 * ks, idesc, 1u);
+                    else mma_f16_ss(tmem, am + ks * 128, bm + ks * 128, idesc, 1u);
+                }
+            const long long t1 = clock64();
+            tc_commit(bar);
+            mbar_wait(bar, 0);
+            const long long t2 = clock64();
+            reinterpret_cast<long long*>(D)[0] = t1 - t0;
+            reinterpret_cast<long long*>(D)[1] = t2 - t0;
         } else if (mode == 2) {
             // throughput probe: 240 back-to-back MMAs (K = 64 reused), N in {64,128}; cycles -> D[0..1] as raw ints
             const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, N);
@@ -324,12 +341,12 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
                 mma3(tmem, ah + o, al + o, bh + o, bl + o, idesc, ks > 0);
             }
         }
-        if (mode != 2) tc_commit(bar);
+        if (mode != 2 && mode < 4) tc_commit(bar);
     }
     mbar_wait(bar, 0);
     tc_fence_after();
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    for (int c0 = 0; c0 < N && mode != 2; c0 += 32) {
+    for (int c0 = 0; c0 < N && mode != 2 && mode < 4; c0 += 32) {
         float v[32];
         tmem_ld32(tmem + lane_base + c0, v);
         for (int j = 0; j < 32; ++j) D[tid * N + c0 + j] = v[j];
@@ -357,7 +374,7 @@ int geossl_debug_set_trace(long long* device_buffer) {
 int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream) {
     GEOSSL_REQUIRE(a && b && d, "null pointer");
     GEOSSL_REQUIRE((mode == 0 && (K == 64 || K == 128) && N == 128) || (mode == 1 && K == 128 && (N == 64 || N == 128)) ||
-                   (mode == 2 && K == 64 && (N == 64 || N == 128)) || (mode == 3 && (K == 64 || K == 128) && (N == 64 || N == 128)),
+                   ((mode == 2 || mode == 4 || mode == 5) && K == 64 && (N == 64 || N == 128)) || (mode == 3 && (K == 64 || K == 128) && (N == 64 || N == 128)),
                    "unsupported shape");
     const size_t smem = 8 * tc::kBlk + 64 + 1024;
     if (fp16) {
