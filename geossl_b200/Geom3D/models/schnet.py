@@ -74,10 +74,10 @@ class CFConv(torch.nn.Module):
 
     # ---- training fast path: everything edge-wise happens inside two kernels
     def forward_graph(self, x, graph, smearing):
-        x = self.lin1(x)
+        x = ops.linear(x, self.lin1)
         x = ops.CFConvLayer.apply(x, self.nn[0].weight, self.nn[0].bias, self.nn[2].weight, self.nn[2].bias,
                                   smearing.offset, graph, smearing.coeff, self.cutoff)
-        return self.lin2(x)
+        return ops.linear(x, self.lin2)
 
     # ---- composable path (any derivative order): filter from torch ops, aggregate from the CUDA primitive
     def forward_composed(self, x, graph, edge_weight, edge_attr):
@@ -126,8 +126,9 @@ class InteractionBlock(torch.nn.Module):
         torch.nn.init.xavier_uniform_(self.lin.weight)
         self.lin.bias.data.fill_(0)
 
-    def forward_graph(self, x, graph, smearing):
-        return self.lin(self.act(self.conv.forward_graph(x, graph, smearing)))
+    def forward_graph(self, x, graph, smearing, residual=None):
+        # act + lin (+ the `h + interaction(...)` residual of schnet.py:97) are one fused kernel on the tensor-core path
+        return ops.linear(self.conv.forward_graph(x, graph, smearing), self.lin, pre_ssp=True, residual=residual)
 
     def forward_composed(self, x, graph, edge_weight, edge_attr):
         return self.lin(self.act(self.conv.forward_composed(x, graph, edge_weight, edge_attr)))
@@ -197,11 +198,12 @@ class SchNet(torch.nn.Module):
                 h = h + interaction.forward_composed(h, ge, edge_weight, edge_attr)
         else:
             for interaction in self.interactions:
-                h = h + interaction.forward_graph(h, graph, self.distance_expansion)
+                h = interaction.forward_graph(h, graph, self.distance_expansion, residual=h)
 
-        h = self.lin1(h)
-        h = self.act(h)
-        h = self.lin2(h)
+        if pos.requires_grad and torch.is_grad_enabled():
+            h = self.lin2(self.act(self.lin1(h)))
+        else:
+            h = ops.linear(ops.linear(h, self.lin1), self.lin2, pre_ssp=True)
 
         n_graphs = graph.graph_ptr.numel() - 1
         if self.dipole:

@@ -1,0 +1,334 @@
+// Node-level dense layers (128 -> 128) on the sm_100a tensor cores: forward / data-gradient and
+// weight-gradient kernels with split-precision operands (tc.cuh), fused bias, shifted-softplus
+// pre-activation, activation-gradient and residual epilogues.
+//
+// Replaces the atom-wise nn.Linear calls of the reference encoder (Geom3D/models/schnet.py:99-101 head,
+// :165-166 InteractionBlock act + lin, :189,191 CFConv lin1 / lin2, and the `h + interaction(...)` residual
+// of :97), which run as fp32 SIMT cuBLAS GEMMs + separate elementwise kernels in PyTorch.
+//
+//   linear_tc:        Y[r][n] = epi( sum_k pre(X[r][k]) * Wm[n][k] )
+//                       pre  in {identity, shifted softplus}
+//                       Wm   = W (nn.Linear layout, forward) or W^T (data gradient)
+//                       epi  : + bias[n], * sigmoid(Z[r][n]) (activation gradient), + R[r][n] (residual)
+//                     computed transposed (D^T = Wm . X^T: TMEM lanes = output features, columns = rows) so
+//                     that bias is a per-thread scalar and every store instruction writes 128 contiguous bytes.
+//   linear_wgrad_tc:  DW[o][i] = sum_r dY[r][o] * pre(X[r][i]),  db[o] = sum_r dY[r][o]
+//                     MN-major views of [row][feature] tiles, accumulator resident in TMEM, per-CTA partials
+//                     reduced in a fixed order (deterministic).
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace geossl {
+namespace tc {
+
+constexpr int kNR = 64;                   // rows per tile
+constexpr int kNBlkW = 128 * 128;         // [128 rows x 64 k] 16-bit weight block
+constexpr int kNBlkT = kNR * 128;         // [64 rows x 64 k] 16-bit tile block
+
+struct LinLayout {
+    static constexpr int W = 0;                       // hi (2 k-blocks) | lo (2 k-blocks)   64 KB
+    static constexpr int X = W + 4 * kNBlkW;          // hi (2 k-blocks) | lo (2 k-blocks)   32 KB
+    static constexpr int BAR = X + 4 * kNBlkT;
+    static constexpr int TMEM_PTR = BAR + 16;
+    static constexpr int kBytes = TMEM_PTR + 16;
+};
+
+// X tile (64 rows x 128 k, fp32, optional ssp) -> split K-major SW128 image.  256 threads: (row = tid/4, 32 k each).
+template <bool FP16>
+__device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, int64_t row0, int64_t n_rows, bool pre_ssp,
+                                                  uint8_t* hi, uint8_t* lo) {
+    const int tid = threadIdx.x, r = tid >> 2, kq = tid & 3;
+    const int64_t row = row0 + r;
+    float v[32];
+    if (row < n_rows) {
+        const float* p = X + row * 128 + kq * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = ldg4(p + 4 * j);
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+        if (pre_ssp) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ssp_fast(v[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    const int blk = kq >> 1;                          // k-block of 64
+#pragma unroll
+    for (int c = 0; c < 4; ++c) store_chunk8<FP16>(hi + blk * kNBlkT, lo + blk * kNBlkT, r, (kq & 1) * 32 + c * 8, &v[c * 8]);
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(256, 2)
+linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const float* __restrict__ Wt, int trans, const float* __restrict__ bias,
+                 int pre_ssp, const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    using L = LinLayout;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar = sbase + L::BAR;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // weights: A operand, rows n (M = 128), K-major.  forward: A[n][k] = W[n][k]; data gradient: A[n][k] = W[k][n]
+    for (int idx = tid; idx < 128 * 16; idx += 256) {
+        float v[8];
+        int n, c;
+        if (!trans) {
+            n = idx >> 4; c = idx & 15;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(Wt + n * 128 + c * 8 + j);
+        } else {
+            n = idx & 127; c = idx >> 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(Wt + (c * 8 + j) * 128 + n);
+        }
+        const int blk = c >> 3;
+        store_chunk8<FP16>(smem + L::W + blk * kNBlkW, smem + L::W + 2 * kNBlkW + blk * kNBlkW, n, (c & 7) * 8, v);
+    }
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR);
+    const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, kNR);
+    const int q = warp & 3, eh = warp >> 2, f = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float bf = bias ? __ldg(bias + f) : 0.f;
+
+    const int64_t n_tiles = (n_rows + kNR - 1) / kNR;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t row0 = t * kNR;
+        stage_rows_kmajor<FP16>(X, row0, n_rows, pre_ssp != 0, smem + L::X, smem + L::X + 2 * kNBlkT);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t wh = desc_k_sw128(sbase + L::W), wl = desc_k_sw128(sbase + L::W + 2 * kNBlkW);
+            const uint64_t xh = desc_k_sw128(sbase + L::X), xl = desc_k_sw128(sbase + L::X + 2 * kNBlkT);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kNBlkT >> 4) + 2 * (ks & 3);
+                mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, ks > 0);
+            }
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem + lane_base + eh * 32, v);          // lane = output feature f, columns = rows eh*32..+31
+        tc_fence_before();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int64_t row = row0 + eh * 32 + j;
+            if (row < n_rows) {
+                float y = v[j] + bf;
+                if (Z) y *= sigmoid_fast(__ldg(Z + row * 128 + f));
+                if (R) y += __ldg(R + row * 128 + f);
+                Y[row * 128 + f] = y;
+            }
+        }
+        __syncthreads();                                   // TMEM / X tile reuse by the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem, 64);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ weight gradient
+struct WgLayout {
+    static constexpr int DY = 0;                      // [64 r][128 o] hi (2 MN blocks) | lo                32 KB
+    static constexpr int XT = DY + 4 * kNBlkT;        // [64 r][128 i] hi | lo                              32 KB
+    static constexpr int RED = XT + 4 * kNBlkT;       // 16 x 128 floats (bias column sums)                  8 KB
+    static constexpr int BAR = RED + 16 * 128 * 4;
+    static constexpr int TMEM_PTR = BAR + 16;
+    static constexpr int kBytes = TMEM_PTR + 16;
+};
+constexpr int kWgPart = 128 * 128 + 128;              // per-CTA partial: DW [o][i] then db [o]
+
+// [row][feature] tile -> split image (same memory layout as K-major rows; read by the MMA as MN-major).
+// thread = (8 columns 8cg.., rows ro + 16 s); returns the per-thread column sums in acc when requested.
+template <bool FP16, bool SUM>
+__device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64_t row0, int64_t n_rows, bool pre_ssp,
+                                              uint8_t* hi, uint8_t* lo, float (&acc)[8]) {
+    const int tid = threadIdx.x, cg = tid & 15, ro = tid >> 4;
+    float4 a[4][2];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int64_t row = row0 + s * 16 + ro;
+        if (row < n_rows) {
+            const float* p = X + row * 128 + cg * 8;
+            a[s][0] = ldg4(p); a[s][1] = ldg4(p + 4);
+        } else {
+            a[s][0] = a[s][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float v[8] = {a[s][0].x, a[s][0].y, a[s][0].z, a[s][0].w, a[s][1].x, a[s][1].y, a[s][1].z, a[s][1].w};
+        const bool valid = row0 + s * 16 + ro < n_rows;
+        if (pre_ssp) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = valid ? ssp_fast(v[k]) : 0.f;
+        }
+        if (SUM) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v[k];
+        }
+        store_chunk8<FP16>(hi + (cg >> 3) * kNBlkT, lo + (cg >> 3) * kNBlkT, s * 16 + ro, (cg & 7) * 8, v);
+    }
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(256, 2)
+linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, int64_t n_rows, int pre_ssp,
+                       float* __restrict__ workspace) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    using L = WgLayout;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar = sbase + L::BAR;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR);
+    const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, 128, 1, 1);
+    float acc[8], dummy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+
+    const int64_t n_tiles = (n_rows + kNR - 1) / kNR;
+    uint32_t phase = 0;
+    int done = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++done) {
+        const int64_t row0 = t * kNR;
+        stage_rows_mn<FP16, true>(dY, row0, n_rows, false, smem + L::DY, smem + L::DY + 2 * kNBlkT, acc);
+        stage_rows_mn<FP16, false>(X, row0, n_rows, pre_ssp != 0, smem + L::XT, smem + L::XT + 2 * kNBlkT, dummy);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t ah = desc_mn_sw128(sbase + L::DY, kNBlkT), al = desc_mn_sw128(sbase + L::DY + 2 * kNBlkT, kNBlkT);
+            const uint64_t bh = desc_mn_sw128(sbase + L::XT, kNBlkT), bl = desc_mn_sw128(sbase + L::XT + 2 * kNBlkT, kNBlkT);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t o = ks * (2048 >> 4);
+                mma3(tmem, ah + o, al + o, bh + o, bl + o, idesc, (done | ks) > 0);
+            }
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase);                               // tiles are re-staged only after the MMAs have read them
+        phase ^= 1;
+    }
+    tc_fence_after();
+    // ---- partials: DW from TMEM (lane = o, columns = i), db from the staged column sums
+    float* ws = workspace + (int64_t)blockIdx.x * kWgPart;
+    const int q = warp & 3, eh = warp >> 2, o = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float v[32];
+        if (done > 0) {
+            tmem_ld32(tmem + lane_base + eh * 64 + h * 32, v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        float* dst = ws + o * 128 + eh * 64 + h * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    float* red = reinterpret_cast<float*>(smem + L::RED);
+    {
+        const int cg = tid & 15, ro = tid >> 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[ro * 128 + cg * 8 + k] = acc[k];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) s += red[r * 128 + tid];
+        ws[128 * 128 + tid] = s;
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem, 128);
+    }
+}
+
+__global__ void linear_wgrad_reduce_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ gw, float* __restrict__ gb) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kWgPart) return;
+    float s = 0.f;
+    for (int p = 0; p < n_parts; ++p) s += workspace[(int64_t)p * kWgPart + idx];
+    if (idx < 128 * 128) gw[idx] = s;
+    else if (gb) gb[idx - 128 * 128] = s;
+}
+
+static int node_grid(int64_t n_rows) {
+    int64_t tiles = (n_rows + kNR - 1) / kNR;
+    const int cap = 2 * kNumSM;                              // two CTAs per SM fit (96 KB / 72 KB of shared memory)
+    return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
+}  // namespace tc
+}  // namespace geossl
+
+using namespace geossl;
+
+extern "C" {
+
+int geossl_linear_tc(const float* x, int64_t n_rows, const float* weight, int transpose_weight, const float* bias, int pre_ssp,
+                     const float* act_grad_input, const float* residual, float* y, int bf16_parts, void* stream) {
+    if (n_rows == 0) return 0;
+    GEOSSL_REQUIRE(x && weight && y && n_rows > 0, "null pointer");
+    const size_t smem = tc::LinLayout::kBytes + 1024;
+    static bool configured = false;
+    if (!configured) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int grid = tc::node_grid(n_rows);
+    if (bf16_parts)
+        tc::linear_tc_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(x, n_rows, weight, transpose_weight, bias, pre_ssp,
+                                                                           act_grad_input, residual, y);
+    else
+        tc::linear_tc_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(x, n_rows, weight, transpose_weight, bias, pre_ssp,
+                                                                          act_grad_input, residual, y);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::node_grid(n_rows) * tc::kWgPart; }
+
+int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, int pre_ssp, float* workspace,
+                           float* grad_weight, float* grad_bias, void* stream) {
+    GEOSSL_REQUIRE(grad_y && x && workspace && grad_weight && n_rows > 0, "null pointer or empty input");
+    const size_t smem = tc::WgLayout::kBytes + 1024;
+    static bool configured = false;
+    if (!configured) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int grid = tc::node_grid(n_rows);
+    tc::linear_wgrad_tc_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(grad_y, x, n_rows, pre_ssp, workspace);
+    GEOSSL_LAUNCH_CHECK();
+    tc::linear_wgrad_reduce_kernel<<<(tc::kWgPart + 255) / 256, 256, 0, as_stream(stream)>>>(workspace, grid, grad_weight, grad_bias);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

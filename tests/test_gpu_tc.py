@@ -106,3 +106,32 @@ def test_filter_bwd_tc_vs_simt(G, ng, lo, hi):
     for name, a, ref in zip(("x", "w1", "b1", "w2", "b2"), res["tc_fp16"], res["simt"]):
         assert torch.isfinite(a).all(), name
         assert rel_err(a, ref) <= 5e-5, (name, rel_err(a, ref))
+
+
+@pytest.mark.parametrize("n,pre_ssp,use_bias,use_res", [(7680, False, False, False), (1000, True, True, True), (63, False, True, False),
+                                                         (129, True, True, False), (20000, True, True, True)])
+def test_linear_tc_vs_torch(n, pre_ssp, use_bias, use_res):
+    """128 -> 128 atom-wise layer on the tensor cores (fp16-split forward, bf16-split gradients) against fp64 torch."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(n)
+    x = (torch.randn(n, 128, generator=g) * 2).to(DEV).requires_grad_()
+    w = (torch.randn(128, 128, generator=g) * 0.1).to(DEV).requires_grad_()
+    b = (torch.randn(128, generator=g) * 0.1).to(DEV).requires_grad_() if use_bias else None
+    r = torch.randn(n, 128, generator=g).to(DEV).requires_grad_() if use_res else None
+    gy = (torch.randn(n, 128, generator=g) * 1e-3).to(DEV)
+    y = ops.LinearTC.apply(x, w, b, r, pre_ssp)
+    y.backward(gy)
+    xd, wd = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+    bd = b.detach().double().requires_grad_() if use_bias else None
+    rd = r.detach().double().requires_grad_() if use_res else None
+    inp = (F.softplus(xd) - 0.6931471805599453) if pre_ssp else xd
+    yd = F.linear(inp, wd, bd)
+    if use_res:
+        yd = yd + rd
+    yd.backward(gy.double())
+    assert rel_err(y, yd) <= 3e-6, rel_err(y, yd)
+    assert rel_err(x.grad, xd.grad) <= 5e-5 and rel_err(w.grad, wd.grad) <= 5e-5, (rel_err(x.grad, xd.grad), rel_err(w.grad, wd.grad))
+    if use_bias:
+        assert rel_err(b.grad, bd.grad) <= 1e-5
+    if use_res:
+        assert torch.equal(r.grad, gy)
