@@ -588,3 +588,459 @@ int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Tensor-core edition (H = 128): same math, 64-pair tiles, everything transposed so that TMEM lanes are
+// hidden units / features and columns are pairs (tc.cuh: split-precision operands, three MMAs per product).
+//   MMA1  D1^T[n][p]  = W0[:, :128] . feat^T          z1 = relu(D1^T + emb_p * W0[n][128] + b0[n])
+//   MMA2  D2^T[n2][p] = W1 . z1^T                      z2 = relu(D2^T + b1[n2]); score_p = sum_n2 z2 w2[n2] + b2
+//   (backward, recomputing the above)
+//   MMA3  D3^T[n][p]  = W1^T . dz2^T                   dz1 = D3^T * [z1 > 0]
+//   MMA4  D4^T[k][p]  = W0[:, :128]^T . dz1^T          -> RED into grad_h[u_p], grad_h[v_p] (128 contiguous bytes / warp)
+//   WG0   DW0[n][k]  += dz1^T feat                     WG1  DW1^T[n][n2] += z1^T dz2        (accumulated in TMEM)
+// Weight images live once in shared memory and serve both orientations (K-major for MMA1/2, MN-major for MMA3/4).
+// Synchronous per-tile pipeline (stage -> MMA -> epilogue, __syncthreads between): the head is ~8 % of the step's
+// FLOPs, so simplicity wins over overlap here.
+// =====================================================================================================
+#include "tc.cuh"
+
+namespace geossl {
+namespace tc {
+
+constexpr int kHP = 64;                        // pairs per tile
+constexpr int kHBlkW = 128 * 128;              // [128 rows x 64 k] weight block (bytes)
+constexpr int kHBlkT = kHP * 128;              // [64 rows x 64 k] tile block (bytes)
+constexpr int kHThreads = 512;
+
+struct HeadSmem {
+    static constexpr int W0 = 0;                               // hi (2 k-blocks) | lo                       64 KB
+    static constexpr int W1 = W0 + 4 * kHBlkW;                 // rows n2 < 64: hi (2 x 8 KB) | lo (2 x 8 KB)  32 KB
+    static constexpr int FEAT = W1 + 4 * kHBlkT;               // hi (2 blk) | lo (2 blk)                     32 KB
+    static constexpr int Z1 = FEAT + 4 * kHBlkT;               // 32 KB
+    static constexpr int DZ1 = Z1 + 4 * kHBlkT;                // 32 KB
+    static constexpr int DZ2 = DZ1 + 4 * kHBlkT;               // hi (1 blk) | lo (1 blk)                     16 KB
+    static constexpr int SC = DZ2 + 2 * kHBlkT;                // per-pair scalars: 10 arrays x 64 x 4 B
+    static constexpr int RED = SC + 10 * 64 * 4;               // [4][64] floats
+    static constexpr int BAR = RED + 4 * 64 * 4;
+    static constexpr int TMEM_PTR = BAR + 16;
+    static constexpr int kBytes = TMEM_PTR + 16;
+};
+static_assert(HeadSmem::kBytes + 1024 <= 227 * 1024, "shared memory budget");
+
+template <bool FP16, bool BWD>
+__global__ void __launch_bounds__(kHThreads, 1)
+ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* __restrict__ grad_loss,
+                   float* __restrict__ grad_h, float* __restrict__ workspace) {
+    using K = HeadCfg<128>;
+    using L = HeadSmem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar = sbase + L::BAR;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int* sU = reinterpret_cast<int*>(smem + L::SC);
+    int* sV = sU + 64;
+    float* sSig = reinterpret_cast<float*>(sV + 64);
+    float* sDt = sSig + 64; float* sTgt = sDt + 64; float* sSa = sTgt + 64; float* sEmb = sSa + 64;
+    float* sDsr = sEmb + 64; float* sDemb = sDsr + 64; float* sValid = sDemb + 64;
+    float* sRed = reinterpret_cast<float*>(smem + L::RED);
+
+    // ---- weights: W0[:, :128] rows n, W1 rows n2 (K-major images, split)
+    for (int idx = tid; idx < 128 * 16; idx += kHThreads) {
+        const int n = idx >> 4, c = idx & 15;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(in.p.out_w0 + n * 129 + c * 8 + j);
+        store_chunk8<FP16>(smem + L::W0 + (c >> 3) * kHBlkW, smem + L::W0 + 2 * kHBlkW + (c >> 3) * kHBlkW, n, (c & 7) * 8, v);
+    }
+    for (int idx = tid; idx < 64 * 16; idx += kHThreads) {
+        const int n2 = idx >> 4, c = idx & 15;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(in.p.out_w1 + n2 * 128 + c * 8 + j);
+        store_chunk8<FP16>(smem + L::W1 + (c >> 3) * kHBlkT, smem + L::W1 + 2 * kHBlkT + (c >> 3) * kHBlkT, n2, (c & 7) * 8, v);
+    }
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR);
+    const uint32_t tDW0 = tmem, tDW1 = tmem + 128, tD1 = tmem + 192, tD2 = tmem + 256, tD3 = tmem + 320, tD4 = tmem + 384;
+
+    const int q = warp & 3, cg4 = warp >> 2;                   // TMEM lane quadrant, column (pair) group of 16
+    const int Ln = q * 32 + lane;                              // this thread's TMEM lane: hidden unit n / n2 / feature k
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int col0 = cg4 * 16;
+    const float wl = __ldg(in.p.out_w0 + Ln * 129 + 128), b0n = __ldg(in.p.out_b0 + Ln);
+    const float b1n = Ln < 64 ? __ldg(in.p.out_b1 + Ln) : 0.f, w2n = Ln < 64 ? __ldg(in.p.out_w2 + Ln) : 0.f;
+    const float out_b2 = __ldg(in.p.out_b2), in_b1 = __ldg(in.p.in_b1);
+    const float iw0 = tid < 128 ? __ldg(in.p.in_w0 + tid) : 0.f, ib0 = tid < 128 ? __ldg(in.p.in_b0 + tid) : 0.f,
+                iw1 = tid < 128 ? __ldg(in.p.in_w1 + tid) : 0.f;
+    float gscale = 0.f;
+    if (BWD) {
+        const float ng = __ldg(loss_aux + 1);
+        gscale = ng > 0.f ? __ldg(grad_loss) / ng : 0.f;
+    }
+    constexpr uint32_t fmt = Split<FP16>::kFmt;
+    const uint32_t id_t = idesc_f16(fmt, 128, kHP);            // K-major A and B
+    const uint32_t id_a_mn = idesc_f16(fmt, 128, kHP, 1, 0);   // MN-major A (weight image), K-major B
+    const uint32_t id_wg0 = idesc_f16(fmt, 128, 128, 1, 1), id_wg1 = idesc_f16(fmt, 128, 64, 1, 1);
+
+    float loss_acc = 0.f;
+    int gmax = -1;
+    float a_db0 = 0.f, a_dwl = 0.f, a_db1 = 0.f, a_dw2 = 0.f, a_db2 = 0.f, a_iw0 = 0.f, a_ib0 = 0.f, a_iw1 = 0.f, a_ib1 = 0.f;
+    uint32_t phase = 0;
+    int done = 0;
+    const int64_t n_tiles = (in.n_pairs + kHP - 1) / kHP;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++done) {
+        const int64_t p0 = t * kHP;
+        // ---- 0. per-pair scalars
+        if (tid < kHP) {
+            const int64_t p = p0 + tid;
+            int u = 0, v = 0;
+            float sigma = 1.f, dt = 0.f, tgt = 0.f, sa = 0.f, valid = 0.f;
+            if (p < in.n_pairs) {
+                u = (int)in.sei[p];
+                v = (int)in.sei[in.n_pairs + p];
+                const int g = (int)in.batch[u];
+                gmax = max(gmax, g);
+                int lvl = (int)in.noise_level[g];
+                lvl = lvl < 0 ? 0 : (lvl >= in.n_levels ? in.n_levels - 1 : lvl);
+                sigma = __ldg(in.sigmas + lvl);
+                const float d = __ldg(in.dist + p);
+                dt = __fadd_rn(d, __fmul_rn(__ldg(in.noise + p), sigma));
+                tgt = __fmul_rn(-(1.f / __fmul_rn(sigma, sigma)), __fsub_rn(dt, d));
+                sa = (in.anneal_power == 2.f) ? sigma * sigma : powf(sigma, in.anneal_power);
+                valid = 1.f;
+            }
+            sU[tid] = u; sV[tid] = v; sSig[tid] = sigma; sDt[tid] = dt; sTgt[tid] = tgt; sSa[tid] = sa; sValid[tid] = valid;
+        }
+        __syncthreads();
+        // ---- 1. distance embedding (8 threads per pair) and the feat tile (lanes over columns: coalesced row gathers)
+        {
+            const int pl = tid >> 3, part = tid & 7;
+            const float dt = sDt[pl];
+            float s = 0.f;
+#pragma unroll 4
+            for (int k = part; k < 128; k += 8) {
+                const float pre = fmaf(__ldg(in.p.in_w0 + k), dt, __ldg(in.p.in_b0 + k));
+                s = fmaf(__ldg(in.p.in_w1 + k), fmaxf(pre, 0.f), s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (part == 0) sEmb[pl] = s + in_b1;
+        }
+        {
+            const int cg = tid & 15, ro = tid >> 4;             // 8 columns 8cg.., rows ro and ro + 32
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int row = ro + 32 * s2;
+                const float* hu = in.h + (int64_t)sU[row] * 128 + cg * 8;
+                const float* hv = in.h + (int64_t)sV[row] * 128 + cg * 8;
+                const float4 a0 = ldg4(hu), a1 = ldg4(hu + 4), c0 = ldg4(hv), c1 = ldg4(hv + 4);
+                const float m = sValid[row];
+                float v[8] = {(a0.x + c0.x) * m, (a0.y + c0.y) * m, (a0.z + c0.z) * m, (a0.w + c0.w) * m,
+                              (a1.x + c1.x) * m, (a1.y + c1.y) * m, (a1.z + c1.z) * m, (a1.w + c1.w) * m};
+                store_chunk8<FP16>(smem + L::FEAT + (cg >> 3) * kHBlkT, smem + L::FEAT + 2 * kHBlkT + (cg >> 3) * kHBlkT, row,
+                                   (cg & 7) * 8, v);
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // ---- 2. MMA1: D1^T = W0h . feat^T
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t ah = desc_k_sw128(sbase + L::W0), al = desc_k_sw128(sbase + L::W0 + 2 * kHBlkW);
+            const uint64_t bh = desc_k_sw128(sbase + L::FEAT), bl = desc_k_sw128(sbase + L::FEAT + 2 * kHBlkT);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t oa = (ks >> 2) * (kHBlkW >> 4) + 2 * (ks & 3), ob = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
+                mma3(tD1, ah + oa, al + oa, bh + ob, bl + ob, id_t, ks > 0);
+            }
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- 3. E1: z1 = relu(D1^T + emb_p * wl + b0) -> Z1 tile [p][n]
+        uint32_t mask1 = 0;
+        {
+            float v[16];
+            tmem_ld16(tD1 + lane_base + col0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float z = fmaxf(fmaf(sEmb[col0 + j], wl, v[j]) + b0n, 0.f);
+                if (z > 0.f) mask1 |= 1u << j;
+                store_split1<FP16>(smem + L::Z1 + (Ln >> 6) * kHBlkT, smem + L::Z1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0 + j, Ln & 63, z);
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        // ---- 4. MMA2: D2^T = W1 . z1^T   (rows n2 >= 64 of the A operand are garbage lanes that are never read)
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t ah = desc_k_sw128(sbase + L::W1), al = desc_k_sw128(sbase + L::W1 + 2 * kHBlkT);
+            const uint64_t bh = desc_k_sw128(sbase + L::Z1), bl = desc_k_sw128(sbase + L::Z1 + 2 * kHBlkT);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t o = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
+                mma3(tD2, ah + o, al + o, bh + o, bl + o, id_t, ks > 0);
+            }
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- 5. E2: z2, score (sum over the 64 lanes n2), loss / dsr, dz2
+        float z2[16];
+        {
+            float v[16];
+            tmem_ld16(tD2 + lane_base + col0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                z2[j] = Ln < 64 ? fmaxf(v[j] + b1n, 0.f) : 0.f;
+                float ps = z2[j] * w2n;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+                if (lane == 0 && q < 2) sRed[q * 64 + col0 + j] = ps;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (tid < kHP) {
+            const float inv = 1.f / sSig[tid];
+            const float s = (sRed[tid] + sRed[64 + tid] + out_b2) * inv;
+            const float diff = s - sTgt[tid];
+            loss_acc += 0.5f * (diff * diff) * sSa[tid];
+            sDsr[tid] = diff * sSa[tid] * gscale * inv;
+        }
+        if (!BWD) { __syncthreads(); continue; }
+        __syncthreads();
+        if (Ln < 64) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float dsr = sDsr[col0 + j];
+                const float dz = z2[j] > 0.f ? dsr * w2n : 0.f;
+                a_dw2 = fmaf(dsr, z2[j], a_dw2);
+                a_db1 += dz;
+                store_split1<FP16>(smem + L::DZ2, smem + L::DZ2 + kHBlkT, col0 + j, Ln, dz);
+            }
+        }
+        if (tid < kHP) a_db2 += sDsr[tid];
+        fence_proxy_async();
+        __syncthreads();
+        // ---- 6. MMA3: D3^T = W1^T . dz2^T (A = MN-major view of the W1 image, K = 64) ; WG1: DW1^T += z1^T dz2
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t ah = desc_mn_sw128(sbase + L::W1, kHBlkT), al = desc_mn_sw128(sbase + L::W1 + 2 * kHBlkT, kHBlkT);
+            const uint64_t bh = desc_k_sw128(sbase + L::DZ2), bl = desc_k_sw128(sbase + L::DZ2 + kHBlkT);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma3(tD3, ah + ks * 128, al + ks * 128, bh + 2 * ks, bl + 2 * ks, id_a_mn, ks > 0);
+            const uint64_t zh = desc_mn_sw128(sbase + L::Z1, kHBlkT), zl = desc_mn_sw128(sbase + L::Z1 + 2 * kHBlkT, kHBlkT);
+            const uint64_t dh = desc_mn_sw128(sbase + L::DZ2, kHBlkT), dl = desc_mn_sw128(sbase + L::DZ2 + kHBlkT, kHBlkT);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma3(tDW1, zh + ks * 128, zl + ks * 128, dh + ks * 128, dl + ks * 128, id_wg1, (done | ks) > 0);
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- 7. E3: dz1 = D3^T * [z1 > 0] -> dZ1 tile ; db0, dW0[:,128] in-thread ; demb_p = sum_n dz1 wl (over lanes)
+        {
+            float v[16];
+            tmem_ld16(tD3 + lane_base + col0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float dz = ((mask1 >> j) & 1u) ? v[j] : 0.f;
+                a_db0 += dz;
+                a_dwl = fmaf(dz, sEmb[col0 + j], a_dwl);
+                float pd = dz * wl;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) pd += __shfl_xor_sync(0xffffffffu, pd, o);
+                if (lane == 0) sRed[q * 64 + col0 + j] = pd;
+                store_split1<FP16>(smem + L::DZ1 + (Ln >> 6) * kHBlkT, smem + L::DZ1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0 + j, Ln & 63, dz);
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        // ---- 8. MMA4: D4^T = W0h^T . dz1^T (A = MN-major view of the W0 image, K = 128) ; WG0: DW0 += dz1^T feat
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t ah = desc_mn_sw128(sbase + L::W0, kHBlkW), al = desc_mn_sw128(sbase + L::W0 + 2 * kHBlkW, kHBlkW);
+            const uint64_t bh = desc_k_sw128(sbase + L::DZ1), bl = desc_k_sw128(sbase + L::DZ1 + 2 * kHBlkT);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t ob = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
+                mma3(tD4, ah + ks * 128, al + ks * 128, bh + ob, bl + ob, id_a_mn, ks > 0);
+            }
+            const uint64_t zh = desc_mn_sw128(sbase + L::DZ1, kHBlkT), zl = desc_mn_sw128(sbase + L::DZ1 + 2 * kHBlkT, kHBlkT);
+            const uint64_t fh = desc_mn_sw128(sbase + L::FEAT, kHBlkT), fl = desc_mn_sw128(sbase + L::FEAT + 2 * kHBlkT, kHBlkT);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma3(tDW0, zh + ks * 128, zl + ks * 128, fh + ks * 128, fl + ks * 128, id_wg0, (done | ks) > 0);
+            tc_commit(bar);
+        }
+        if (tid < kHP) sDemb[tid] = sRed[tid] + sRed[64 + tid] + sRed[128 + tid] + sRed[192 + tid];
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        __syncthreads();
+        // ---- 9. E4: scatter dfeat to both endpoints (lanes = features: 128 contiguous bytes per warp instruction)
+        {
+            float v[16];
+            tmem_ld16(tD4 + lane_base + col0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (sValid[col0 + j] != 0.f) {
+                    atomicAdd(grad_h + (int64_t)sU[col0 + j] * 128 + Ln, v[j]);
+                    atomicAdd(grad_h + (int64_t)sV[col0 + j] * 128 + Ln, v[j]);
+                }
+            }
+        }
+        if (tid < 128) {   // distance-embedding MLP gradients, thread per hidden unit
+            for (int p = 0; p < kHP; ++p) {
+                const float dt = sDt[p], de = sDemb[p];
+                const float pre = fmaf(iw0, dt, ib0);
+                if (pre > 0.f) {
+                    a_iw1 = fmaf(de, pre, a_iw1);
+                    const float dpre = de * iw1;
+                    a_iw0 = fmaf(dpre, dt, a_iw0);
+                    a_ib0 += dpre;
+                }
+                if (tid == 0) a_ib1 += de;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+
+    if (!BWD) {
+        __shared__ float red_l[16];
+        __shared__ int red_g[16];
+        loss_acc = warp_sum(loss_acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        if (lane == 0) { red_l[warp] = loss_acc; red_g[warp] = gmax; }
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            int g = -1;
+            for (int w = 0; w < 16; ++w) { s += red_l[w]; g = max(g, red_g[w]); }
+            workspace[2 * blockIdx.x] = s;
+            workspace[2 * blockIdx.x + 1] = (float)g;
+        }
+    } else {
+        // ---- per-CTA partial gradients in HeadCfg<128>'s layout (reduced by ddm_head_reduce_kernel<128>)
+        float* ws = workspace + (int64_t)blockIdx.x * K::kPartial;
+        tc_fence_after();
+        {   // DW0 [n][k]: lane n, this warp's column group covers k = cg4*32 .. +31
+            float v[32];
+            if (done > 0) tmem_ld32(tDW0 + lane_base + cg4 * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ws[K::pW0 + Ln * K::LD + cg4 * 32 + j] = done > 0 ? v[j] : 0.f;
+        }
+        {   // DW1^T [n][n2] -> pW1 [n2][n]
+            float v[16];
+            if (done > 0) tmem_ld16(tDW1 + lane_base + cg4 * 16, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ws[K::pW1 + (cg4 * 16 + j) * 128 + Ln] = done > 0 ? v[j] : 0.f;
+        }
+        tc_fence_before();
+        __syncthreads();
+        // column-group partials of the in-thread accumulators: reduce over the 4 warps that share a lane quadrant
+        float* red = reinterpret_cast<float*>(smem + L::FEAT);      // [4 cg][128] x 4 quantities
+        red[(0 * 4 + cg4) * 128 + Ln] = a_db0;
+        red[(1 * 4 + cg4) * 128 + Ln] = a_dwl;
+        red[(2 * 4 + cg4) * 128 + Ln] = a_db1;
+        red[(3 * 4 + cg4) * 128 + Ln] = a_dw2;
+        __syncthreads();
+        if (tid < 128) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int c = 0; c < 4; ++c) {
+                s0 += red[(0 * 4 + c) * 128 + tid]; s1 += red[(1 * 4 + c) * 128 + tid];
+                s2 += red[(2 * 4 + c) * 128 + tid]; s3 += red[(3 * 4 + c) * 128 + tid];
+            }
+            ws[K::pB0 + tid] = s0;
+            ws[K::pW0 + tid * K::LD + 128] = s1;
+            if (tid < 64) { ws[K::pB1 + tid] = s2; ws[K::pW2 + tid] = s3; }
+            ws[K::pIW0 + tid] = a_iw0; ws[K::pIB0 + tid] = a_ib0; ws[K::pIW1 + tid] = a_iw1;
+        }
+        if (tid == 0) ws[K::pIB1] = a_ib1;
+        // out_b2: sum over the 64 scalar threads
+        if (warp < 2) {
+            float s = warp_sum(a_db2);
+            if (lane == 0) sRed[warp] = s;
+        }
+        __syncthreads();
+        if (tid == 0) ws[K::pB2] = sRed[0] + sRed[1];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace tc
+}  // namespace geossl
+
+extern "C" {
+
+int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+                           const float* dist, const float* noise, const int64_t* noise_level,
+                           const float* sigmas, int n_levels, float anneal_power, int H,
+                           const geossl_ddm_params* params, float* workspace, float* loss, void* stream) {
+    GEOSSL_REQUIRE(workspace && loss && n_pairs >= 0, "null workspace/loss");
+    GEOSSL_REQUIRE(H == 128, "the tensor-core DDM head is built for emb_dim = 128");
+    if (n_pairs == 0) {
+        GEOSSL_CUDA(cudaMemsetAsync(loss, 0, 2 * sizeof(float), as_stream(stream)));
+        return 0;
+    }
+    HeadIn in;
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+                   "null input pointer");
+    const size_t smem = tc::HeadSmem::kBytes + 1024;
+    static bool configured = false;
+    if (!configured) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::ddm_head_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int grid = head_grid(n_pairs);
+    tc::ddm_head_tc_kernel<true, false><<<grid, tc::kHThreads, smem, as_stream(stream)>>>(in, nullptr, nullptr, nullptr, workspace);
+    GEOSSL_LAUNCH_CHECK();
+    ddm_loss_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(workspace, grid, loss);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, int64_t n_atoms,
+                           const float* dist, const float* noise, const int64_t* noise_level,
+                           const float* sigmas, int n_levels, float anneal_power, int H,
+                           const geossl_ddm_params* params, const float* loss_aux, const float* grad_loss, float* workspace,
+                           float* grad_h, const geossl_ddm_grads* grads, void* stream) {
+    GEOSSL_REQUIRE(workspace && grad_h && grads && loss_aux && grad_loss && n_pairs > 0 && n_atoms >= 0, "null pointer / empty input");
+    GEOSSL_REQUIRE(H == 128, "the tensor-core DDM head is built for emb_dim = 128");
+    const geossl_ddm_grads& g = *grads;
+    GEOSSL_REQUIRE(g.in_w0 && g.in_b0 && g.in_w1 && g.in_b1 && g.out_w0 && g.out_b0 && g.out_w1 && g.out_b1 && g.out_w2 && g.out_b2,
+                   "null gradient pointer");
+    HeadIn in;
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+                   "null input pointer");
+    const size_t smem = tc::HeadSmem::kBytes + 1024;
+    static bool configured = false;
+    if (!configured) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::ddm_head_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    GEOSSL_CUDA(cudaMemsetAsync(grad_h, 0, sizeof(float) * (size_t)n_atoms * 128, as_stream(stream)));
+    const int grid = head_grid(n_pairs);
+    tc::ddm_head_tc_kernel<false, true><<<grid, tc::kHThreads, smem, as_stream(stream)>>>(in, loss_aux, grad_loss, grad_h, workspace);
+    GEOSSL_LAUNCH_CHECK();
+    const int n = HeadCfg<128>::kPartial;
+    ddm_head_reduce_kernel<128><<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(workspace, grid, g);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

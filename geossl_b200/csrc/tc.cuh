@@ -164,6 +164,21 @@ struct Split<false> {
     }
 };
 
+// One value -> the hi and lo images (2-byte scattered stores; used by the transposed epilogues).
+template <bool FP16>
+__device__ __forceinline__ void store_split1(uint8_t* hi_block, uint8_t* lo_block, uint32_t row, uint32_t k, float x) {
+    const uint32_t off = sw128_offset(row, k);
+    if constexpr (FP16) {
+        const __half h = __float2half_rn(x);
+        *reinterpret_cast<__half*>(hi_block + off) = h;
+        *reinterpret_cast<__half*>(lo_block + off) = __float2half_rn(x - __half2float(h));
+    } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        *reinterpret_cast<__nv_bfloat16*>(hi_block + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(lo_block + off) = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+
 // Store 8 consecutive K values (k0 % 8 == 0) of `row` into the hi and lo images of a SW128 block.
 template <bool FP16>
 __device__ __forceinline__ void store_chunk8(uint8_t* hi_block, uint8_t* lo_block, uint32_t row, uint32_t k0, const float* x) {

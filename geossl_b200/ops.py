@@ -454,7 +454,9 @@ class DDMHead(torch.autograd.Function):
         ws = torch.empty(max(lib.geossl_ddm_workspace(H), 1), dtype=torch.float32, device=h.device)
         loss = torch.empty(2, dtype=torch.float32, device=h.device)
         pp = _ddm_ptrs(params)
-        _timed("ddm_head_fwd", lambda: lib.geossl_ddm_head_fwd(
+        ctx.tc = FILTER_MODE != "simt" and H == 128
+        fwd = lib.geossl_ddm_head_fwd_tc if ctx.tc else lib.geossl_ddm_head_fwd
+        _timed("ddm_head_fwd", lambda: fwd(
             _p(h), _p(sei), _p(batch), n_pairs, _p(dist), _p(noise), _p(noise_level), _p(sigmas), sigmas.numel(),
             float(anneal_power), H, ctypes.byref(pp), _p(ws), _p(loss), _stream()))
         ctx.anneal_power = float(anneal_power)
@@ -474,7 +476,8 @@ class DDMHead(torch.autograd.Function):
         ws = torch.empty(lib.geossl_ddm_workspace(H), dtype=torch.float32, device=h.device)
         gl = grad_loss.contiguous().view(1).to(torch.float32)
         pp, gp = _ddm_ptrs(params), _ddm_ptrs(grads)
-        _timed("ddm_head_bwd", lambda: lib.geossl_ddm_head_bwd(
+        bwd = lib.geossl_ddm_head_bwd_tc if ctx.tc else lib.geossl_ddm_head_bwd
+        _timed("ddm_head_bwd", lambda: bwd(
             _p(h), _p(sei), _p(batch), n_pairs, h.size(0), _p(dist), _p(noise), _p(noise_level), _p(sigmas), sigmas.numel(),
             ctx.anneal_power, H, ctypes.byref(pp), _p(loss), _p(gl), _p(ws), _p(grad_h), ctypes.byref(gp), _stream()))
         return (grad_h, None, None, None, None, None, None, None, *grads)

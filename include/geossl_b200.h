@@ -201,6 +201,17 @@ int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch
                         const float* grad_loss, float* workspace,
                         float* grad_h, const geossl_ddm_grads* grads /*host*/, void* stream);
 
+/* Same contracts on the tcgen05 tensor cores (H = 128; fp16-split forward, bf16-split backward operands). */
+int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+                           const float* dist, const float* noise, const int64_t* noise_level,
+                           const float* sigmas, int n_levels, float anneal_power, int H,
+                           const geossl_ddm_params* params /*host*/, float* workspace, float* loss /*(2,)*/, void* stream);
+int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, int64_t n_atoms,
+                           const float* dist, const float* noise, const int64_t* noise_level,
+                           const float* sigmas, int n_levels, float anneal_power, int H,
+                           const geossl_ddm_params* params /*host*/, const float* loss_aux, const float* grad_loss,
+                           float* workspace, float* grad_h, const geossl_ddm_grads* grads /*host*/, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * PaiNN message block.  Replaces the per-edge part of PaiNN.forward (Geom3D/models/painn.py:232-245:
  * r_ij, d_ij, dir_ij, GaussianRBF painn_utils.py:99-103, CosineCutoff painn_utils.py:152-155,

@@ -22,7 +22,7 @@ def test_pair_distance():
 
 
 @pytest.mark.parametrize("name", ["ncsn_h128", "ncsn_perm"])
-def test_ddm_head_vs_golden(name):
+def test_ddm_head_vs_golden(name, filter_mode):
     g = Golden(name)
     head = head_from(g, device=DEV)
     i = g["in"]
