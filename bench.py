@@ -249,8 +249,7 @@ def run_product(args):
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- roofline of the cfconv forward kernel (BASELINE metric) + the other hot kernels
@@ -310,8 +309,17 @@ def run_product(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof, "roofline_other_kernels": others, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank exit: the captured CUDA graph keeps references into the NCCL communicator, and tearing the process
+    group down under it can block; everything is flushed, so leave without the teardown."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
