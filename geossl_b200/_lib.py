@@ -54,7 +54,9 @@ _SIGNATURES = {
     "geossl_filter_bwd_tc_workspace": (c_i64, []),
     "geossl_filter_bwd_tc": (c_int, [c_p, c_p, c_i64, c_p, c_f, c_f, c_int, c_int, c_p, c_p, c_p,
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
-    "geossl_linear_tc": (c_int, [c_p, c_i64, c_p, c_int, c_p, c_int, c_p, c_p, c_p, c_int, c_p]),
+    "geossl_weight_image_bytes": (c_i64, []),
+    "geossl_pack_weight": (c_int, [c_p, c_int, c_int, c_p, c_p]),
+    "geossl_linear_tc": (c_int, [c_p, c_i64, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p]),
     "geossl_linear_wgrad_tc_workspace": (c_i64, [c_i64]),
     "geossl_linear_wgrad_tc": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
     "geossl_pair_distance": (c_int, [c_p, c_p, c_i64, c_p, c_p]),

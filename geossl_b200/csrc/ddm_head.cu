@@ -431,8 +431,17 @@ __global__ void ddm_head_reduce_kernel(const float* __restrict__ workspace, int 
     using K = HeadCfg<H>;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= K::kPartial) return;
-    float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += workspace[(int64_t)p * K::kPartial + idx];
+    // four independent chains (fixed association order => still deterministic) keep enough loads in flight
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 3 < n_parts; p += 4) {
+        s0 += workspace[(int64_t)p * K::kPartial + idx];
+        s1 += workspace[(int64_t)(p + 1) * K::kPartial + idx];
+        s2 += workspace[(int64_t)(p + 2) * K::kPartial + idx];
+        s3 += workspace[(int64_t)(p + 3) * K::kPartial + idx];
+    }
+    for (; p < n_parts; ++p) s0 += workspace[(int64_t)p * K::kPartial + idx];
+    const float s = (s0 + s1) + (s2 + s3);
     if (idx < K::pB0) g.out_w0[idx] = s;
     else if (idx < K::pW1) g.out_b0[idx - K::pB0] = s;
     else if (idx < K::pB1) g.out_w1[idx - K::pW1] = s;

@@ -392,8 +392,17 @@ __global__ void filter_bwd_tc_reduce_kernel(const float* __restrict__ workspace,
     const bool w1_slot = idx >= Part::kW1 && idx < Part::kB2;
     const int g = w1_slot ? (idx - Part::kW1) / 128 : 0;
     if (w1_slot && g >= G) return;                                      // padded gaussians are never written
-    float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += workspace[(int64_t)p * Part::kFloats + idx];
+    // four independent chains (fixed association order => still deterministic) keep enough loads in flight
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 3 < n_parts; p += 4) {
+        s0 += workspace[(int64_t)p * Part::kFloats + idx];
+        s1 += workspace[(int64_t)(p + 1) * Part::kFloats + idx];
+        s2 += workspace[(int64_t)(p + 2) * Part::kFloats + idx];
+        s3 += workspace[(int64_t)(p + 3) * Part::kFloats + idx];
+    }
+    for (; p < n_parts; ++p) s0 += workspace[(int64_t)p * Part::kFloats + idx];
+    const float s = (s0 + s1) + (s2 + s3);
     if (idx < Part::kW1) gw2[idx] = s;
     else if (w1_slot) gw1[((idx - Part::kW1) % 128) * G + g] = s;
     else if (idx < Part::kB1) gb2[idx - Part::kB2] = s;

@@ -309,8 +309,17 @@ __global__ void filter_bwd_reduce_kernel(const float* __restrict__ workspace, in
     using P = Partial<F>;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P::kFloats) return;
-    float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += workspace[(int64_t)p * P::kFloats + idx];
+    // four independent chains (fixed association order => still deterministic) keep enough loads in flight
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 3 < n_parts; p += 4) {
+        s0 += workspace[(int64_t)p * P::kFloats + idx];
+        s1 += workspace[(int64_t)(p + 1) * P::kFloats + idx];
+        s2 += workspace[(int64_t)(p + 2) * P::kFloats + idx];
+        s3 += workspace[(int64_t)(p + 3) * P::kFloats + idx];
+    }
+    for (; p < n_parts; ++p) s0 += workspace[(int64_t)p * P::kFloats + idx];
+    const float s = (s0 + s1) + (s2 + s3);
     if (idx < P::kW1) {
         gw2[idx] = s;
     } else if (idx < P::kB2) {

@@ -28,10 +28,33 @@ constexpr int kNBlkT = kNR * 128;         // [64 rows x 64 k] 16-bit tile block
 struct LinLayout {
     static constexpr int W = 0;                       // hi (2 k-blocks) | lo (2 k-blocks)   64 KB
     static constexpr int X = W + 4 * kNBlkW;          // hi (2 k-blocks) | lo (2 k-blocks)   32 KB
-    static constexpr int BAR = X + 4 * kNBlkT;
+    static constexpr int BAR = X + 4 * kNBlkT;            // [0] MMA done, [1] weight image landed
     static constexpr int TMEM_PTR = BAR + 16;
     static constexpr int kBytes = TMEM_PTR + 16;
 };
+constexpr int kWImage = 4 * kNBlkW;                   // bytes of a packed weight image: hi (2 k-blocks) | lo (2 k-blocks)
+
+// Weight (128,128) fp32 -> the exact shared-memory operand image (split, swizzled) in global memory, so that every CTA
+// of the layer kernels fetches it with one bulk async copy instead of re-splitting it.
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ Wt, int trans, uint8_t* __restrict__ image) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * 16; idx += gridDim.x * blockDim.x) {
+        float v[8];
+        int n, c;
+        if (!trans) {
+            n = idx >> 4; c = idx & 15;
+            const float4 a = ldg4(Wt + n * 128 + c * 8), b = ldg4(Wt + n * 128 + c * 8 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+            n = idx & 127; c = idx >> 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(Wt + (c * 8 + j) * 128 + n);
+        }
+        const int blk = c >> 3;
+        store_chunk8<FP16>(image + blk * kNBlkW, image + 2 * kNBlkW + blk * kNBlkW, n, (c & 7) * 8, v);
+    }
+}
 
 // X tile (64 rows x 128 k, fp32, optional ssp) -> split K-major SW128 image.  256 threads: (row = tid/4, 32 k each).
 template <bool FP16>
@@ -62,7 +85,7 @@ __device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, i
 
 template <bool FP16>
 __global__ void __launch_bounds__(256, 2)
-linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const float* __restrict__ Wt, int trans, const float* __restrict__ bias,
+linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __restrict__ w_image, const float* __restrict__ bias,
                  int pre_ssp, const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
@@ -71,23 +94,16 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const float* __res
     const uint32_t bar = sbase + L::BAR;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // weights: A operand, rows n (M = 128), K-major.  forward: A[n][k] = W[n][k]; data gradient: A[n][k] = W[k][n]
-    for (int idx = tid; idx < 128 * 16; idx += 256) {
-        float v[8];
-        int n, c;
-        if (!trans) {
-            n = idx >> 4; c = idx & 15;
+    // weights: the packed A-operand image (rows n, K-major, split) arrives by bulk async copy while the X tile is staged
+    const uint32_t wbar = bar + 8;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(wbar, kWImage);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(Wt + n * 128 + c * 8 + j);
-        } else {
-            n = idx & 127; c = idx >> 7;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(Wt + (c * 8 + j) * 128 + n);
-        }
-        const int blk = c >> 3;
-        store_chunk8<FP16>(smem + L::W + blk * kNBlkW, smem + L::W + 2 * kNBlkW + blk * kNBlkW, n, (c & 7) * 8, v);
+        for (int c = 0; c < 4; ++c) bulk_g2s(sbase + L::W + c * kNBlkW, w_image + c * kNBlkW, kNBlkW, wbar);
     }
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, 64);
     tc_fence_before();
     __syncthreads();
@@ -103,9 +119,20 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const float* __res
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t row0 = t * kNR;
         stage_rows_kmajor<FP16>(X, row0, n_rows, pre_ssp != 0, smem + L::X, smem + L::X + 2 * kNBlkT);
+        // epilogue operands do not depend on the MMA: fetch them now so their latency hides behind it
+        float zr[32], rr[32];
+        if (Z) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const int64_t row = row0 + eh * 32 + j; zr[j] = row < n_rows ? __ldg(Z + row * 128 + f) : 0.f; }
+        }
+        if (R) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const int64_t row = row0 + eh * 32 + j; rr[j] = row < n_rows ? __ldg(R + row * 128 + f) : 0.f; }
+        }
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
+            mbar_wait(wbar, 0);                                // (completes once; later tiles pass immediately)
             tc_fence_after();
             const uint64_t wh = desc_k_sw128(sbase + L::W), wl = desc_k_sw128(sbase + L::W + 2 * kNBlkW);
             const uint64_t xh = desc_k_sw128(sbase + L::X), xl = desc_k_sw128(sbase + L::X + 2 * kNBlkT);
@@ -127,8 +154,8 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const float* __res
             const int64_t row = row0 + eh * 32 + j;
             if (row < n_rows) {
                 float y = v[j] + bf;
-                if (Z) y *= sigmoid_fast(__ldg(Z + row * 128 + f));
-                if (R) y += __ldg(R + row * 128 + f);
+                if (Z) y *= sigmoid_fast(zr[j]);
+                if (R) y += rr[j];
                 Y[row * 128 + f] = y;
             }
         }
@@ -268,13 +295,30 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
     }
 }
 
-__global__ void linear_wgrad_reduce_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ gw, float* __restrict__ gb) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= kWgPart) return;
-    float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += workspace[(int64_t)p * kWgPart + idx];
-    if (idx < 128 * 128) gw[idx] = s;
-    else if (gb) gb[idx - 128 * 128] = s;
+// 256 threads = 32 outputs x 8 slices of the partial list; slices are combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+linear_wgrad_reduce_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ gw, float* __restrict__ gb) {
+    __shared__ float red[8][33];
+    const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 32 + o;
+    float s0 = 0.f, s1 = 0.f;
+    if (idx < kWgPart) {
+        int p = sl;
+        for (; p + 8 < n_parts; p += 16) {
+            s0 += workspace[(int64_t)p * kWgPart + idx];
+            s1 += workspace[(int64_t)(p + 8) * kWgPart + idx];
+        }
+        if (p < n_parts) s0 += workspace[(int64_t)p * kWgPart + idx];
+    }
+    red[sl][o] = s0 + s1;
+    __syncthreads();
+    if (sl == 0 && idx < kWgPart) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][o];
+        if (idx < 128 * 128) gw[idx] = s;
+        else if (gb) gb[idx - 128 * 128] = s;
+    }
 }
 
 static int node_grid(int64_t n_rows) {
@@ -290,9 +334,20 @@ using namespace geossl;
 
 extern "C" {
 
-int geossl_linear_tc(const float* x, int64_t n_rows, const float* weight, int transpose_weight, const float* bias, int pre_ssp,
+int64_t geossl_weight_image_bytes(void) { return tc::kWImage; }
+
+int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts, void* image, void* stream) {
+    GEOSSL_REQUIRE(weight && image, "null pointer");
+    if (bf16_parts) tc::pack_weight_kernel<false><<<8, 256, 0, as_stream(stream)>>>(weight, transpose_weight, (uint8_t*)image);
+    else tc::pack_weight_kernel<true><<<8, 256, 0, as_stream(stream)>>>(weight, transpose_weight, (uint8_t*)image);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, const float* bias, int pre_ssp,
                      const float* act_grad_input, const float* residual, float* y, int bf16_parts, void* stream) {
     if (n_rows == 0) return 0;
+    const uint8_t* weight = (const uint8_t*)weight_image;
     GEOSSL_REQUIRE(x && weight && y && n_rows > 0, "null pointer");
     const size_t smem = tc::LinLayout::kBytes + 1024;
     static bool configured = false;
@@ -303,11 +358,9 @@ int geossl_linear_tc(const float* x, int64_t n_rows, const float* weight, int tr
     }
     const int grid = tc::node_grid(n_rows);
     if (bf16_parts)
-        tc::linear_tc_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(x, n_rows, weight, transpose_weight, bias, pre_ssp,
-                                                                           act_grad_input, residual, y);
+        tc::linear_tc_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(x, n_rows, weight, bias, pre_ssp, act_grad_input, residual, y);
     else
-        tc::linear_tc_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(x, n_rows, weight, transpose_weight, bias, pre_ssp,
-                                                                          act_grad_input, residual, y);
+        tc::linear_tc_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(x, n_rows, weight, bias, pre_ssp, act_grad_input, residual, y);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
@@ -326,7 +379,7 @@ int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, 
     const int grid = tc::node_grid(n_rows);
     tc::linear_wgrad_tc_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(grad_y, x, n_rows, pre_ssp, workspace);
     GEOSSL_LAUNCH_CHECK();
-    tc::linear_wgrad_reduce_kernel<<<(tc::kWgPart + 255) / 256, 256, 0, as_stream(stream)>>>(workspace, grid, grad_weight, grad_bias);
+    tc::linear_wgrad_reduce_kernel<<<(tc::kWgPart + 31) / 32, 256, 0, as_stream(stream)>>>(workspace, grid, grad_weight, grad_bias);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -356,11 +356,18 @@ class CFConvLayer(torch.autograd.Function):
 # =====================================================================================================
 # atom-wise dense layers on the tensor cores
 # =====================================================================================================
+def _pack_weight(weight, transpose, bf16_parts):
+    lib = _lib.load()
+    image = torch.empty(lib.geossl_weight_image_bytes(), dtype=torch.uint8, device=weight.device)
+    check(lib.geossl_pack_weight(_p(weight), 1 if transpose else 0, 1 if bf16_parts else 0, _p(image), _stream()), "pack_weight")
+    return image
+
+
 def _linear_tc(x, weight, transpose, bias, pre_ssp, act_grad_input, residual, bf16_parts, name):
     y = torch.empty((x.size(0), 128), dtype=torch.float32, device=x.device)
-    _timed(name, lambda: _lib.load().geossl_linear_tc(_p(x), x.size(0), _p(weight), 1 if transpose else 0, _p(bias),
-                                                      1 if pre_ssp else 0, _p(act_grad_input), _p(residual), _p(y),
-                                                      1 if bf16_parts else 0, _stream()))
+    image = _pack_weight(weight, transpose, bf16_parts)
+    _timed(name, lambda: _lib.load().geossl_linear_tc(_p(x), x.size(0), _p(image), _p(bias), 1 if pre_ssp else 0,
+                                                      _p(act_grad_input), _p(residual), _p(y), 1 if bf16_parts else 0, _stream()))
     return y
 
 

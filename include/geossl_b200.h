@@ -143,10 +143,15 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
  * nn.Linear calls of schnet.py:99-101 (head), :165-166 (act + lin), :189,:191 (CFConv lin1 / lin2) and the
  * residual of :97.
  *   y[r][n] = epi( sum_k pre(x[r][k]) * Wm[n][k] ),  pre = identity | shifted softplus (pre_ssp),
- *   Wm = weight (out,in) or its transpose (transpose_weight: data gradient),
+ *   Wm = weight (out,in) or its transpose (data gradient) -- chosen when the weight is packed,
  *   epi: + bias[n] (may be NULL), * sigmoid(act_grad_input[r][n]) (may be NULL), + residual[r][n] (may be NULL).
  * ---------------------------------------------------------------------------------------------- */
-int geossl_linear_tc(const float* x, int64_t n_rows, const float* weight, int transpose_weight, const float* bias, int pre_ssp,
+/* `weight_image` = the weight packed by geossl_pack_weight (split + swizzled shared-memory operand image,
+ * geossl_weight_image_bytes() bytes, 16-byte aligned) with the same transpose / parts flags; every CTA fetches it with
+ * one bulk async copy (cp.async.bulk). */
+int64_t geossl_weight_image_bytes(void);
+int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts, void* image, void* stream);
+int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, const float* bias, int pre_ssp,
                      const float* act_grad_input, const float* residual, float* y, int bf16_parts, void* stream);
 
 /* grad_weight[o][i] = sum_r grad_y[r][o] * pre(x[r][i]);  grad_bias[o] = sum_r grad_y[r][o] (may be NULL). */
