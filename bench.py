@@ -24,6 +24,7 @@ import torch  # noqa: E402
 METRIC = "GeoSSL-DDM SchNet train molecules/s at 1/2/4/8 B200; cfconv % HBM roofline"
 CFG = dict(batch_per_gpu=256, atoms=30, cutoff=10.0, num_gaussians=50, hidden=128, filters=128, interactions=6,
            sigma_levels=50, anneal_power=2.0, pos_sigma=0.3, lr=5e-4)
+NCU_TRAFFIC_CFCONV_FWD = 234.14e6 + 4.98e6     # bytes per launch of the bench workload (profiles/r01_v10_ncu_full.txt)
 WORKLOAD = ("configs[1]: SchNet GeoSSL-DDM pretraining step, synthetic Molecule3D-shaped conformers, "
             "batch 256 per GPU x 30 atoms, cutoff 10 A, 50 RBF, hidden 128, 6 interactions, data-parallel")
 
@@ -270,7 +271,9 @@ def run_product(args):
         t = ktimes["cfconv_fwd"]["mean_ms"] / 1e3
         ach = cf_bytes / t / 1e9
         roof = {"kernel": "cfconv_fwd_kernel<128,4>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"],
+                "frac": ach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_CFCONV_FWD if n_edges > 400_000 else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_v10_ncu_full.txt",
+                "peak_source": peaks["src"],
                 "algorithmic_bytes_per_launch": cf_bytes, "mean_ms": 1e3 * t, "launches_timed": ktimes["cfconv_fwd"]["n"]}
         flops = {"filter_fwd": n_edges * (2 * G * F_ + 2 * F_ * F_),
                  "filter_bwd": n_edges * (2 * G * F_ + 2 * (2 * F_ * F_) + 2 * G * F_ + 2 * F_ * F_),

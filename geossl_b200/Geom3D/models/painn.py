@@ -49,6 +49,13 @@ class PaiNNMixing(nn.Module):
         self.mu_channel_mix = Dense(n_atom_basis, 2 * n_atom_basis, activation=None, bias=False)
         self.epsilon = epsilon
 
+    def forward_fused(self, q, mu):
+        """q (N,F), mu (N,3,F): the three Dense layers are library GEMMs, everything between them is two fused kernels."""
+        mu_mix = self.mu_channel_mix(mu)
+        ctx, dot = ops.PaiNNMixPre.apply(q, mu_mix, self.epsilon)
+        y = self.intraatomic_context_net(ctx)
+        return ops.PaiNNMixPost.apply(q, mu, y, mu_mix, dot)
+
     def forward(self, q, mu):
         mu_V, mu_W = torch.split(self.mu_channel_mix(mu), self.n_atom_basis, dim=-1)
         mu_Vn = torch.sqrt(torch.sum(mu_V ** 2, dim=-2, keepdim=True) + self.epsilon)
@@ -103,8 +110,7 @@ class PaiNN(nn.Module):
             fo = 0 if self.share_filters else i * 3 * Fd
             q, mu = ops.PaiNNMessage.apply(q, mu, ctx, self.filter_net.weight[fo:fo + 3 * Fd],
                                            self.filter_net.bias[fo:fo + 3 * Fd], edges)
-            q, mu = mixing(q.unsqueeze(1), mu)
-            q = q.squeeze(1)
+            q, mu = mixing.forward_fused(q, mu)
         if num_graphs is None:
             num_graphs = int(batch[-1].item()) + 1 if batch.numel() else 0
         h = torch.zeros((num_graphs, Fd), dtype=q.dtype, device=q.device).index_add_(0, batch, q)

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "geossl_radius_csr": (c_int, [c_p, c_p, c_p, c_i64, c_f, c_int, c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),
     "geossl_csr_to_edge_index": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "geossl_csr_transpose": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p]),
+    "geossl_super_edges": (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_i64, c_p, c_p, c_p]),
     "geossl_rowptr_from_sorted": (c_int, [c_p, c_i64, c_i64, c_p, c_p]),
     "geossl_filter_fwd": (c_int, [c_p, c_p, c_i64, c_p, c_f, c_f, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
     "geossl_filter_fwd_tc": (c_int, [c_p, c_p, c_i64, c_p, c_f, c_f, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_p]),
@@ -75,6 +76,10 @@ _SIGNATURES = {
     "geossl_painn_workspace": (c_i64, [c_int, c_int]),
     "geossl_painn_message_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_p,
                                          c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "geossl_painn_mix_pre": (c_int, [c_p, c_p, c_i64, c_int, c_f, c_p, c_p, c_p]),
+    "geossl_painn_mix_pre_bwd": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p, c_p]),
+    "geossl_painn_mix_post": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p, c_p]),
+    "geossl_painn_mix_post_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
 }
 
 

@@ -178,11 +178,45 @@ transpose_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     if (MODE == 0 && lane == 0) t_deg[j] = kept;
 }
 
+// Batch assembly on the device (replaces AtomTupleExtractor + the collate offsets of BatchAtomTuple.from_data_list,
+// Geom3D/dataloaders/dataloaders_AtomTuple.py:15-37,45-73, for ratio == 1): one thread per (graph, first atom i) writes the
+// pairs (i, j) of its row in itertools order -- combination: j > i; permutation: j != i -- at the graph's pair offset.
+__global__ void super_edges_kernel(const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ pair_ptr, int n_graphs,
+                                   int n_atoms, int permutation, int64_t n_pairs, int64_t* __restrict__ sei,
+                                   int64_t* __restrict__ batch) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;        // global atom index
+    if (a >= n_atoms) return;
+    int lo = 0, hi = n_graphs;                                   // graph of atom a: last g with graph_ptr[g] <= a
+    while (hi - lo > 1) {
+        const int m = (lo + hi) >> 1;
+        if (graph_ptr[m] <= a) lo = m; else hi = m;
+    }
+    const int g = lo, first = graph_ptr[g], n = graph_ptr[g + 1] - first, i = a - first;
+    if (batch) batch[a] = g;
+    int64_t p = pair_ptr[g] + (permutation ? (int64_t)i * (n - 1) : (int64_t)i * n - (int64_t)i * (i + 1) / 2);
+    for (int j = permutation ? 0 : i + 1; j < n; ++j) {
+        if (j == i) continue;
+        sei[p] = a;
+        sei[n_pairs + p] = first + j;
+        ++p;
+    }
+}
+
 }  // namespace geossl
 
 using namespace geossl;
 
 extern "C" {
+
+int geossl_super_edges(const int32_t* graph_ptr, const int64_t* pair_ptr, int64_t n_graphs, int64_t n_atoms, int permutation,
+                       int64_t n_pairs, int64_t* super_edge_index, int64_t* batch, void* stream) {
+    if (n_atoms == 0) return 0;
+    GEOSSL_REQUIRE(graph_ptr && pair_ptr && (super_edge_index || n_pairs == 0) && n_graphs > 0, "null pointer");
+    super_edges_kernel<<<(int)((n_atoms + 127) / 128), 128, 0, as_stream(stream)>>>(graph_ptr, pair_ptr, (int)n_graphs, (int)n_atoms,
+                                                                                   permutation, n_pairs, super_edge_index, batch);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
 
 int geossl_abi_version(void) { return GEOSSL_ABI_VERSION; }
 const char* geossl_last_error(void) { return g_err; }

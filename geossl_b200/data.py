@@ -96,3 +96,19 @@ def synthetic_batch(num_graphs=32, atoms=30, atoms_max=None, *, seed=0, option="
     ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     return AtomTupleBatch(torch.from_numpy(x), torch.from_numpy(pos), torch.from_numpy(batch), sei,
                           None, int(num_graphs), torch.from_numpy(ptr))
+
+
+def assemble_batch_device(counts, z, positions, option="combination", device="cuda"):
+    """Batch assembly on the GPU from per-molecule atom counts (host list) + concatenated ``z`` / ``positions``:
+    ``batch``, ``graph_ptr`` and ``super_edge_index`` are produced by geossl_super_edges instead of the reference's
+    Python itertools loop (dataloaders_AtomTuple.py:15-37) and collate (:45-73)."""
+    from . import ops
+    counts = np.asarray(counts, dtype=np.int64)
+    n_atoms, n_graphs = int(counts.sum()), len(counts)
+    pc = pair_count(counts, option)
+    ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(device)
+    pair_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(pc)]).astype(np.int64)).to(device)
+    sei, batch = ops.super_edges(ptr, pair_ptr, n_graphs, n_atoms, int(pc.sum()), option == "permutation")
+    z = z.to(device)
+    x = torch.stack([z, torch.zeros_like(z)], dim=1)
+    return AtomTupleBatch(x, positions.to(device), batch, sei, None, n_graphs, ptr)

@@ -151,6 +151,16 @@ def graph_ptr_from_batch(batch, num_graphs=None):
     return ptr
 
 
+def super_edges(graph_ptr, pair_ptr, n_graphs, n_atoms, n_pairs, permutation=False):
+    """(super_edge_index (2,P) int64, batch (N,) int64) from the atom / pair offsets (see geossl_super_edges)."""
+    graph_ptr, pair_ptr = _req(graph_ptr, torch.int32, "graph_ptr", 1), _req(pair_ptr, torch.int64, "pair_ptr", 1)
+    sei = torch.empty((2, n_pairs), dtype=torch.int64, device=graph_ptr.device)
+    batch = torch.empty(n_atoms, dtype=torch.int64, device=graph_ptr.device)
+    check(_lib.load().geossl_super_edges(_p(graph_ptr), _p(pair_ptr), n_graphs, n_atoms, 1 if permutation else 0, n_pairs,
+                                         _p(sei), _p(batch), _stream()), "super_edges")
+    return sei, batch
+
+
 def radius_csr(pos, batch, r, max_num_neighbors=MAX_NEIGHBORS_DEFAULT, *, graph_ptr=None, num_graphs=None,
                capacity=None, transpose=True):
     """Neighbour search -> RadiusCSR (torch_cluster.radius_graph semantics, see include/geossl_b200.h)."""
@@ -575,3 +585,57 @@ class PaiNNMessage(torch.autograd.Function):
                                            _p(s.rowptr), _p(s.src), n, e, _p(gx), _p(gmu), _p(scratch), _p(ws), _p(gw), _p(gb),
                                            _stream()), "painn_message_bwd")
         return gq_out, gmu, gx, gw, gb, None
+
+
+# =====================================================================================================
+# PaiNN update (mixing) block, fused elementwise parts
+# =====================================================================================================
+class PaiNNMixPre(torch.autograd.Function):
+    """(q (N,F), mu_mix (N,3,2F)) -> ctx (N,2F) = [q, |mu_V|_eps], dot (N,F) = <mu_V, mu_W>   (painn.py:100-105,111)."""
+
+    @staticmethod
+    def forward(ctx_, q, mu_mix, epsilon):
+        q, mu_mix = _req(q, torch.float32, "q", 2), _req(mu_mix, torch.float32, "mu_mix", 3)
+        n, Fd = q.shape
+        out = torch.empty((n, 2 * Fd), dtype=torch.float32, device=q.device)
+        dot = torch.empty((n, Fd), dtype=torch.float32, device=q.device)
+        check(_lib.load().geossl_painn_mix_pre(_p(q), _p(mu_mix), n, Fd, float(epsilon), _p(out), _p(dot), _stream()), "painn_mix_pre")
+        ctx_.save_for_backward(mu_mix, out)
+        return out, dot
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx_, g_ctx, g_dot):
+        mu_mix, out = ctx_.saved_tensors
+        n, Fd = out.size(0), out.size(1) // 2
+        g_q = torch.empty((n, Fd), dtype=torch.float32, device=out.device)
+        g_mm = torch.empty_like(mu_mix)
+        check(_lib.load().geossl_painn_mix_pre_bwd(_p(mu_mix), _p(out), _p(g_ctx.contiguous()), _p(g_dot.contiguous()), n, Fd, _p(g_q),
+                                                   _p(g_mm), _stream()), "painn_mix_pre_bwd")
+        return g_q, g_mm, None
+
+
+class PaiNNMixPost(torch.autograd.Function):
+    """(q, mu, y = [a|b|c], mu_mix, dot) -> q + a + c*dot, mu + b*mu_W   (painn.py:108-113)."""
+
+    @staticmethod
+    def forward(ctx_, q, mu, y, mu_mix, dot):
+        q, mu, y = _req(q, torch.float32, "q", 2), _req(mu, torch.float32, "mu", 3), _req(y, torch.float32, "y", 2)
+        mu_mix, dot = _req(mu_mix, torch.float32, "mu_mix", 3), _req(dot, torch.float32, "dot", 2)
+        n, Fd = q.shape
+        q_out, mu_out = torch.empty_like(q), torch.empty_like(mu)
+        check(_lib.load().geossl_painn_mix_post(_p(q), _p(mu), _p(y), _p(mu_mix), _p(dot), n, Fd, _p(q_out), _p(mu_out), _stream()),
+              "painn_mix_post")
+        ctx_.save_for_backward(y, mu_mix, dot)
+        return q_out, mu_out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx_, gq, gmu):
+        y, mu_mix, dot = ctx_.saved_tensors
+        n, Fd = dot.shape
+        gq, gmu = gq.contiguous(), gmu.contiguous()
+        g_y, g_mm, g_dot = torch.empty_like(y), torch.empty_like(mu_mix), torch.empty_like(dot)
+        check(_lib.load().geossl_painn_mix_post_bwd(_p(gq), _p(gmu), _p(y), _p(mu_mix), _p(dot), n, Fd, _p(g_y), _p(g_mm), _p(g_dot),
+                                                    _stream()), "painn_mix_post_bwd")
+        return gq, gmu, g_y, g_mm, g_dot

@@ -66,6 +66,13 @@ int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_
                          const int32_t* graph_ptr, int64_t n_atoms, int32_t* scratch,
                          int32_t* t_rowptr, int32_t* t_eid, int32_t* t_tgt, void* stream);
 
+/* Device-side batch assembly: all ordered atom pairs of every molecule in itertools order (combination: i<j,
+ * permutation: i!=j), offset by the cumulative atom count -- AtomTupleExtractor + BatchAtomTuple.from_data_list
+ * (dataloaders_AtomTuple.py:15-37,45-73; ratio == 1).  pair_ptr (n_graphs+1) int64 = exclusive scan of the per-graph
+ * pair counts; super_edge_index (2,n_pairs) int64; batch (n_atoms) int64 may be NULL. */
+int geossl_super_edges(const int32_t* graph_ptr, const int64_t* pair_ptr, int64_t n_graphs, int64_t n_atoms, int permutation,
+                       int64_t n_pairs, int64_t* super_edge_index, int64_t* batch, void* stream);
+
 /* rowptr from a SORTED int64 key vector (row 1 of a radius_edge_index), keys in [0,n_rows). */
 int geossl_rowptr_from_sorted(const int64_t* keys, int64_t n_keys, int64_t n_rows, int32_t* rowptr, void* stream);
 
@@ -251,6 +258,18 @@ int geossl_painn_message_bwd(const float* grad_q_out, const float* grad_mu_out, 
                              const int32_t* j_rowptr, const int32_t* j_ctr, int64_t n_atoms, int64_t n_edges,
                              float* grad_ctx, float* grad_mu_in, float* edge_scratch, float* workspace,
                              float* grad_filter_w, float* grad_filter_b, void* stream);
+
+/* PaiNN update block, non-GEMM part (PaiNNMixing.forward, painn.py:100-113).  mu_mix (N,3,2F) = mu_channel_mix(mu).
+ *   pre : ctx (N,2F) = [q, sqrt(sum_xyz mu_V^2 + eps)], dot (N,F) = sum_xyz mu_V*mu_W
+ *   post: y (N,3F) = intraatomic_context_net(ctx) = [a|b|c];  q_out = q + a + c*dot;  mu_out = mu + b*mu_W
+ * and their backward kernels (grad_mu_mix contributions of pre and post are summed by the caller). */
+int geossl_painn_mix_pre(const float* q, const float* mu_mix, int64_t n_atoms, int F, float epsilon, float* ctx, float* dot, void* stream);
+int geossl_painn_mix_pre_bwd(const float* mu_mix, const float* ctx, const float* grad_ctx, const float* grad_dot, int64_t n_atoms, int F,
+                             float* grad_q, float* grad_mu_mix, void* stream);
+int geossl_painn_mix_post(const float* q, const float* mu, const float* y, const float* mu_mix, const float* dot, int64_t n_atoms, int F,
+                          float* q_out, float* mu_out, void* stream);
+int geossl_painn_mix_post_bwd(const float* grad_q_out, const float* grad_mu_out, const float* y, const float* mu_mix, const float* dot,
+                              int64_t n_atoms, int F, float* grad_y, float* grad_mu_mix, float* grad_dot, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,3 +106,17 @@ def test_full_size_properties_config2():
     t_eid = g.t_eid[:e].cpu().long()
     assert torch.equal(torch.sort(t_eid).values, torch.arange(e))
     assert bool((src[t_eid][1:] >= src[t_eid][:-1]).all()) and torch.equal(g.t_tgt[:e].cpu().long(), tgt[t_eid])
+
+
+@pytest.mark.parametrize("option", ["combination", "permutation"])
+def test_device_batch_assembly_matches_host(option):
+    """geossl_super_edges vs the itertools-order host restatement of AtomTupleExtractor + collate offsets."""
+    from geossl_b200.data import assemble_batch_device, super_edges_host
+    counts = [1, 2, 30, 5, 1, 17, 60, 3]
+    n = sum(counts)
+    z = torch.randint(0, 9, (n,))
+    pos = torch.rand(n, 3)
+    b = assemble_batch_device(counts, z, pos, option=option, device=DEV)
+    assert torch.equal(b.super_edge_index.cpu(), super_edges_host(counts, option))
+    assert torch.equal(b.batch.cpu(), torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts)))
+    assert b.num_graphs == len(counts) and b.super_edge_index.dtype == torch.int64

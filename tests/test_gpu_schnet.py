@@ -149,3 +149,19 @@ def test_full_size_forward_properties_config2(filter_mode):
         out2, h2 = m(z[idx], b.positions[idx], b.batch, return_latent=True, num_graphs=256)
     assert torch.isfinite(h).all()
     assert rel_err(h2, h[idx]) <= 1e-6 and rel_err(out2, out[perm]) <= 1e-6
+
+
+def test_lba_shaped_pockets_vs_oracle(filter_mode):
+    """BASELINE configs[4] shape: ~600-atom pockets, cutoff 6 A (every row truncates to 32/33 neighbours)."""
+    torch.manual_seed(3)
+    from geossl_b200.Geom3D.models import SchNet
+    m = SchNet(hidden_channels=128, num_filters=128, num_interactions=2, num_gaussians=50, cutoff=6.0, node_class=9, readout="mean")
+    b = synthetic_batch(2, 520, 600, seed=8, with_pairs=False)
+    z = b.x[:, 0].contiguous()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    out_ref, h_ref, ei = O.schnet_forward(sd, z, b.positions, b.batch, cutoff=6.0, readout="mean", return_edge_index=True)
+    m.to(DEV)
+    out, h = m(z.to(DEV), b.positions.to(DEV), b.batch.to(DEV), return_latent=True)
+    deg = torch.bincount(ei[1], minlength=z.numel())
+    assert int(deg.max()) == 33 and float((deg >= 32).float().mean()) > 0.5
+    assert rel_err(h, h_ref) <= TOL_OUT and rel_err(out, out_ref) <= TOL_OUT
