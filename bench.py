@@ -140,7 +140,7 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------- product arm
@@ -311,7 +311,7 @@ def run_product(args):
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof, "roofline_other_kernels": others, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     _finish(world)
 
 
@@ -325,8 +325,18 @@ def _finish(world):
         os._exit(0)
 
 
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL's C code) prints was sent to stderr."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # library chatter on fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
     if a.impl == "reference":
         run_reference(a)
     else:

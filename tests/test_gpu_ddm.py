@@ -128,29 +128,24 @@ def test_train_step_decreases_loss_config1():
     assert all(map(lambda v: v == v and v < 1e30, losses)) and losses[-1] < losses[0]
 
 
-def test_graphed_train_step_matches_eager():
-    """The CUDA-graph replay of the whole step reproduces eager steps (same seeds => same draws and losses)."""
+def test_graphed_train_step_trains():
+    """The CUDA-graph replay of the whole step (no host sync anywhere on the path) runs on new batches of the captured
+    shape, refuses other shapes, and optimises: replaying on a fixed batch drives the loss down."""
     from geossl_b200.Geom3D.models import SchNet
     from geossl_b200.NCSN import NCSN_version_03
-    from geossl_b200.pretrain import GraphedTrainStep, train_step
+    from geossl_b200.pretrain import GraphedTrainStep
 
-    def build():
-        torch.manual_seed(0)
-        model = SchNet(node_class=9, num_interactions=2).to(DEV)
-        heads = [NCSN_version_03(128, 10, 0.01, 50, "symmetry", 2.0).to(DEV) for _ in range(2)]
-        groups = [{"params": model.parameters()}] + [{"params": [p for p in h.parameters() if p.requires_grad]} for h in heads]
-        return model, heads, torch.optim.Adam(groups, lr=5e-4, fused=True, capturable=True)
-
+    torch.manual_seed(0)
+    model = SchNet(node_class=9, num_interactions=2).to(DEV)
+    heads = [NCSN_version_03(128, 10, 0.01, 50, "symmetry", 2.0).to(DEV) for _ in range(2)]
+    groups = [{"params": model.parameters()}] + [{"params": [p for p in h.parameters() if p.requires_grad]} for h in heads]
+    opt = torch.optim.Adam(groups, lr=5e-4, fused=True, capturable=True)
     batches = [synthetic_batch(16, 12, seed=s).to(DEV) for s in range(3)]
-    model, heads, opt = build()
     step = GraphedTrainStep(default_args(), batches[0], model, heads, opt, warmup=2)
-    assert step.matches(batches[1])
+    assert step.matches(batches[1]) and not step.matches(synthetic_batch(16, 13, seed=9).to(DEV))
+    w0 = model.interactions[0].mlp[0].weight.detach().clone()
     losses = [float(step(b)) for b in batches]
     assert all(v == v and v < 1e30 for v in losses)
-    w_graph = model.interactions[0].mlp[0].weight.detach().clone()
-    # eager run with the same number of optimizer steps: parameters stay close (different random draws => not equal)
-    model2, heads2, opt2 = build()
-    for b in [batches[0]] * 2 + [batches[0]] + batches:      # warm-up (2) + capture (1 traced, not executed) ...
-        pass
-    assert torch.isfinite(w_graph).all()
-    assert not step.matches(synthetic_batch(16, 13, seed=9).to(DEV))
+    assert not torch.equal(w0, model.interactions[0].mlp[0].weight)          # Adam ran inside the graph
+    fixed = [float(step(batches[0])) for _ in range(40)]
+    assert sum(fixed[-10:]) < sum(fixed[:10])
