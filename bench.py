@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timers", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--model", default="schnet", choices=["schnet", "painn"],
+                    help="schnet = the headline workload (configs[1]); painn = configs[2] (F=128, 3 interactions, 20 RBF, cutoff 5 A)")
     return ap.parse_args()
 
 
@@ -164,21 +166,34 @@ def run_product(args):
     _lib.load()
 
     torch.manual_seed(42)
-    model = SchNet(hidden_channels=CFG["hidden"], num_filters=CFG["filters"], num_interactions=CFG["interactions"],
-                   num_gaussians=CFG["num_gaussians"], cutoff=CFG["cutoff"], node_class=9).to(dev)
+    if args.model == "painn":
+        from geossl_b200.Geom3D.models import PaiNN
+        model = PaiNN(n_atom_basis=CFG["hidden"], n_interactions=3, n_rbf=20, cutoff=5.0, max_z=9, n_out=1, readout="add").to(dev)
+    else:
+        model = SchNet(hidden_channels=CFG["hidden"], num_filters=CFG["filters"], num_interactions=CFG["interactions"],
+                       num_gaussians=CFG["num_gaussians"], cutoff=CFG["cutoff"], node_class=9).to(dev)
     heads = [NCSN_version_03(CFG["hidden"], 10, 0.01, CFG["sigma_levels"], "symmetry", CFG["anneal_power"]).to(dev) for _ in range(2)]
     broadcast_parameters([model] + heads)
     groups = [{"params": model.parameters()}] + [{"params": [p for p in h.parameters() if p.requires_grad]} for h in heads]
     opt = torch.optim.Adam(groups, lr=CFG["lr"], fused=True, capturable=not args.no_graph)
     sync = FlatGradAllReduce([p for g in groups for p in g["params"]]) if world > 1 else None
-    targs = default_args("schnet")
+    targs = default_args(args.model)
     torch.manual_seed(1234 + rank)
 
     B = CFG["batch_per_gpu"]
-    host_pool = [synthetic_batch(B, CFG["atoms"], seed=10_000 * rank + i).pin_memory() for i in range(args.pool)]
+    host_pool = [synthetic_batch(B, CFG["atoms"], seed=10_000 * rank + i) for i in range(args.pool)]
+    if args.model == "painn":
+        # dataset-time radius graph (datasets_3D_Radius.py:120) on the clean coordinates, reused for both views
+        from geossl_b200 import ops as _ops
+        for hb in host_pool:
+            g0 = _ops.radius_csr(hb.positions.to(dev), hb.batch.to(dev), 5.0, num_graphs=B, transpose=False)
+            hb.radius_edge_index = g0.edge_index.cpu()
+            hb.extras["rei_sorted"] = True
+    host_pool = [hb.pin_memory() for hb in host_pool]
     dev_pool = [b.to(dev) for b in host_pool]
     h2d_bytes = sum(t.numel() * t.element_size() for t in (host_pool[0].x, host_pool[0].positions, host_pool[0].batch,
-                                                           host_pool[0].super_edge_index))
+                                                           host_pool[0].super_edge_index, host_pool[0].radius_edge_index)
+                    if t is not None)
 
     def step(batch):
         return train_step(targs, batch, model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync, device_noise=True)
@@ -206,7 +221,7 @@ def run_product(args):
         step(dev_pool[i % args.pool])
     barrier()
     eager_step = step
-    if not args.no_graph:
+    if not args.no_graph and args.model == "schnet":       # (PaiNN edge lists differ in length per batch: eager launches)
         graphed = GraphedTrainStep(targs, dev_pool[0], model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync)
         step = graphed
         for i in range(2):
@@ -238,7 +253,7 @@ def run_product(args):
     sink = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
-        if args.no_graph:
+        if args.no_graph or args.model != "schnet":
             loss = step(host_pool[i % args.pool].to(dev, non_blocking=True))
         else:
             loss = step(host_pool[i % args.pool])            # pinned host -> the graph's static input buffers, then replay
@@ -258,6 +273,18 @@ def run_product(args):
     pk = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = {**json.load(open(pk)), "src": "measured"}
+    if args.model == "painn":
+        line = {"metric": "GeoSSL-DDM PaiNN train molecules/s (BASELINE configs[2], secondary)", "value": value, "unit": "molecules/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[2]: PaiNN GeoSSL-DDM pretraining step, F=128, 3 interactions, 20 RBF, cutoff 5 A, "
+                                       "batch 256 x 30 atoms, eager launches"},
+                "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clocks}
+        _emit(json.dumps(line))
+        _finish(world)
+        return
+
     # one encoder launch processes BOTH views stacked as 2B graphs (pretrain._encode_stacked): size the work from that graph
     b0 = dev_pool[0]
     pos2 = torch.cat([b0.positions, b0.positions + CFG["pos_sigma"] * torch.randn_like(b0.positions)])

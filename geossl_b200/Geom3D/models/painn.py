@@ -97,14 +97,16 @@ class PaiNN(nn.Module):
         return build_mlp(n_in=self.n_atom_basis, n_out=self.n_out, n_hidden=self.n_out_hidden,
                          n_layers=self.n_out_layers, activation=self.activation)
 
-    def forward(self, x, positions, radius_edge_index, batch, return_latent=False, num_graphs=None):
+    def forward(self, x, positions, radius_edge_index, batch, return_latent=False, num_graphs=None, assume_sorted=False):
+        """``num_graphs`` / ``assume_sorted`` are optional extensions that remove the two host syncs of this forward
+        (graph count, sortedness check of the edge list) so that a training step can be captured in a CUDA graph."""
         atomic_numbers = x[:, 0] if x.dim() == 2 else x
         n_atoms = atomic_numbers.size(0)
         Fd = self.n_atom_basis
         q = self.embedding(atomic_numbers)                      # (N,F)
         mu = torch.zeros((n_atoms, 3, Fd), dtype=q.dtype, device=q.device)
         edges = ops.painn_edges(positions, radius_edge_index, n_atoms, batch, self.radial_basis.offsets,
-                                self.radial_basis.widths, self.cutoff, num_graphs=num_graphs)
+                                self.radial_basis.widths, self.cutoff, num_graphs=num_graphs, assume_sorted=assume_sorted)
         for i, (interaction, mixing) in enumerate(zip(self.interactions, self.mixing)):
             ctx = interaction.interatomic_context_net(q)        # (N,3F)
             fo = 0 if self.share_filters else i * 3 * Fd

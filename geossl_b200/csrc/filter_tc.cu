@@ -16,8 +16,9 @@
 // Measured structure (profiles/r01_v4_trace_fwd.txt -> v5): the epilogue is MUFU bound (2 MUFU per softplus),
 // the tensor pipe needs ~2.3 k cycles per tile, uncoalesced row-per-thread stores cost 4 k LSU cycles per tile.
 // Operands never come from HBM (they are computed on chip), so tiles are written with st.shared in the
-// swizzled layout and published to the async proxy with fence.proxy.async; the two weight matrices are
-// split once per CTA into shared memory.  Accumulators D1/D2 are double buffered in TMEM (4 x 128 columns).
+// swizzled layout and published to the async proxy with fence.proxy.async; W1 is split once per CTA into shared
+// memory, W2 into TENSOR memory (A operand of MMA2, which frees 64 KB of shared memory for a second s buffer and halves
+// MMA2's shared-memory operand traffic).  TMEM: D1 x2 | D2^T | W2 hi | W2 lo = 512 columns.
 // fp32 operands are split into two 16-bit parts and every product is three MMAs (see tc.cuh).
 #include "common.cuh"
 #include "tc.cuh"
@@ -41,10 +42,9 @@ constexpr int kProdWarp0 = kEpiWarps, kMmaWarp = kEpiWarps + kProdWarps;
 
 struct FwdLayout {                 // byte offsets from the 1024-aligned dynamic smem base
     static constexpr int W1_hi = 0, W1_lo = W1_hi + kBlk;                 // [128 f][64 g]
-    static constexpr int W2_hi = W1_lo + kBlk, W2_lo = W2_hi + 2 * kBlk;  // [128 o][128 i] = 2 k-blocks
-    static constexpr int PHI = W2_lo + 2 * kBlk;                          // 2 buffers x (hi, lo)
-    static constexpr int S = PHI + 4 * kBlk;                              // (hi: 2 k-blocks, lo: 2 k-blocks)
-    static constexpr int B1 = S + 4 * kBlk;                               // 128 floats
+    static constexpr int PHI = W1_lo + kBlk;                              // 2 buffers x (hi, lo)
+    static constexpr int S = PHI + 4 * kBlk;                              // 2 buffers x (hi: 2 k-blocks, lo: 2 k-blocks)
+    static constexpr int B1 = S + 8 * kBlk;                               // 128 floats
     static constexpr int B2 = B1 + 512;
     static constexpr int OFF = B2 + 512;                                  // 64 floats
     static constexpr int BAR = OFF + 256;                                 // 16 mbarriers
@@ -53,7 +53,7 @@ struct FwdLayout {                 // byte offsets from the 1024-aligned dynamic
 };
 static_assert(FwdLayout::kBytes + 1024 <= 227 * 1024, "shared memory budget");
 
-enum Bar { PHI_FULL = 0, PHI_EMPTY = 2, D1_FULL = 4, D1_EMPTY = 6, S_FULL = 8, S_EMPTY = 9, D2_FULL = 10, D2_EMPTY = 12 };
+enum Bar { PHI_FULL = 0, PHI_EMPTY = 2, D1_FULL = 4, D1_EMPTY = 6, S_FULL = 8, S_EMPTY = 10, D2_FULL = 12, D2_EMPTY = 13 };
 
 template <bool FP16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -85,14 +85,6 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
         for (int j = 0; j < 8; ++j) { const int g = c * 8 + j; x[j] = (g < G) ? __ldg(w1 + f * G + g) : 0.f; }
         store_chunk8<FP16>(smem + L::W1_hi, smem + L::W1_lo, f, c * 8, x);
     }
-    for (int idx = tid; idx < kF * 16; idx += kThreads) {            // W2: row o, 16 chunks over i
-        const int o = idx >> 4, c = idx & 15;
-        float x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __ldg(w2 + o * kF + c * 8 + j);
-        const int blk = c >> 3;
-        store_chunk8<FP16>(smem + L::W2_hi + blk * kBlk, smem + L::W2_lo + blk * kBlk, o, (c & 7) * 8, x);
-    }
     if (tid < kF) { sB1[tid] = __ldg(b1 + tid); sB2[tid] = __ldg(b2 + tid); }
     if (tid < 64) sOff[tid] = (tid < G) ? __ldg(offset + tid) : 1e18f;   // padded gaussians: exp(coeff * 1e36) == 0, no branch
     if (tid == 0) {
@@ -101,11 +93,11 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             mbar_init(bar(PHI_EMPTY + b), 1);
             mbar_init(bar(D1_FULL + b), 1);
             mbar_init(bar(D1_EMPTY + b), kEpiThreads / 32);
-            mbar_init(bar(D2_FULL + b), 1);
-            mbar_init(bar(D2_EMPTY + b), kEpiThreads / 32);
+            mbar_init(bar(S_FULL + b), kEpiThreads / 32);
+            mbar_init(bar(S_EMPTY + b), 1);
         }
-        mbar_init(bar(S_FULL), kEpiThreads / 32);
-        mbar_init(bar(S_EMPTY), 1);
+        mbar_init(bar(D2_FULL), 1);
+        mbar_init(bar(D2_EMPTY), kEpiThreads / 32);
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(sbase + L::TMEM_PTR, 512);
@@ -114,7 +106,27 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR);
-    const uint32_t tD1[2] = {tmem, tmem + 128}, tD2[2] = {tmem + 256, tmem + 384};
+    // tensor memory: D1 x2 | D2^T | W2 hi | W2 lo   (W2 resident: MMA2 reads its A operand from TMEM, only the s tile from smem)
+    const uint32_t tD1[2] = {tmem, tmem + 128}, tD2 = tmem + 256, tW2h = tmem + 384, tW2l = tmem + 448;
+    if (warp < kEpiWarps) {
+        const int q = warp & 3, part = warp >> 2, o = q * 32 + lane;           // lane o owns row o of W2, 32 k per warp
+        const uint32_t lane_b = (uint32_t)(q * 32) << 16;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k0 = part * 32 + h * 16;
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 t = ldg4(w2 + o * kF + k0 + j);
+                x[j] = t.x; x[j + 1] = t.y; x[j + 2] = t.z; x[j + 3] = t.w;
+            }
+            tmem_store_split16<FP16>(tW2h + lane_b + k0 / 2, tW2l + lane_b + k0 / 2, x);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     if (warp >= kProdWarp0 && warp < kMmaWarp) {
         // ===================== producer: rbf tile of local tile i into PHI[i & 1]; thread = (row, half of the 64 columns)
@@ -148,8 +160,6 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
         if (lane == 0) {
             const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, kTile, kF);
             const uint64_t dW1h = desc_k_sw128(sbase + L::W1_hi), dW1l = desc_k_sw128(sbase + L::W1_lo);
-            const uint64_t dW2h = desc_k_sw128(sbase + L::W2_hi), dW2l = desc_k_sw128(sbase + L::W2_lo);
-            const uint64_t dSh = desc_k_sw128(sbase + L::S), dSl = desc_k_sw128(sbase + L::S + 2 * kBlk);
             auto issue_mma1 = [&](int i) {
                 const int b = i & 1;
                 mbar_wait(bar(PHI_FULL + b), (i >> 1) & 1);
@@ -168,19 +178,20 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             for (int i = 0; i < my_tiles; ++i) {
                 if (i + 1 < my_tiles) issue_mma1(i + 1);
                 const int b = i & 1;
-                mbar_wait(bar(S_FULL), i & 1);
-                mbar_wait(bar(D2_EMPTY + b), ((i >> 1) & 1) ^ 1);
+                mbar_wait(bar(S_FULL + b), (i >> 1) & 1);
+                mbar_wait(bar(D2_EMPTY), (i & 1) ^ 1);
+                const uint64_t dSh = desc_k_sw128(sbase + L::S + b * 4 * kBlk), dSl = desc_k_sw128(sbase + L::S + b * 4 * kBlk + 2 * kBlk);
                 tc_fence_after();
                 trace(i, 4);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)                         // K = 128 = 2 blocks x 4 x 16
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t o = kb * (kBlk >> 4) + 2 * kk;
-                        mma3(tD2[b], dW2h + o, dW2l + o, dSh + o, dSl + o, idesc, (kb | kk) > 0);   // D2^T = W2 . S^T
+                        const uint32_t o = kb * (kBlk >> 4) + 2 * kk, ka = (kb * 4 + kk) * 8;
+                        mma3_ts(tD2, tW2h + ka, tW2l + ka, dSh + o, dSl + o, idesc, (kb | kk) > 0);   // D2^T = W2 . S^T
                     }
-                tc_commit(bar(S_EMPTY));
-                tc_commit(bar(D2_FULL + b));
+                tc_commit(bar(S_EMPTY + b));
+                tc_commit(bar(D2_FULL));
                 trace(i, 5);
             }
         }
@@ -205,28 +216,28 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = ssp_fast(v[j] + sB1[col0 + j]);
                 if (warp == 0) trace(i, 8);
-                mbar_wait(bar(S_EMPTY), (i & 1) ^ 1);                  // MMA2 of the previous tile released S
+                mbar_wait(bar(S_EMPTY + b), ((i >> 1) & 1) ^ 1);       // MMA2 of tile i-2 released this S buffer
                 if (warp == 0) trace(i, 9);
-                uint8_t* hi = smem + L::S + (cq >> 1) * kBlk;          // k-block holds columns 64*(cq>>1)..+63
+                uint8_t* hi = smem + L::S + b * 4 * kBlk + (cq >> 1) * kBlk;   // k-block holds columns 64*(cq>>1)..+63
                 uint8_t* lo = hi + 2 * kBlk;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store_chunk8<FP16>(hi, lo, r, (cq & 1) * 32 + c * 8, &v[c * 8]);
                 fence_proxy_async();
-                warp_arrive(bar(S_FULL));
+                warp_arrive(bar(S_FULL + b));
                 if (warp == 0) trace(i, 10);
             }
             if (i > 0) {
-                const int t = i - 1, b = t & 1;
+                const int t = i - 1;
                 const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile + col0;
                 // lane j holds the cutoff of edge column j of this warp; broadcast by shuffle in the store loop
                 const float myc = (e0 + lane < n_edges) ? cosine_cutoff(__ldg(edge_dist + e0 + lane), cutoff) : 0.f;
-                mbar_wait(bar(D2_FULL + b), (t >> 1) & 1);
+                mbar_wait(bar(D2_FULL), t & 1);
                 tc_fence_after();
                 if (warp == 0) trace(t, 11);
                 float v[32];
-                tmem_ld32(tD2[b] + lane_base + col0, v);               // lane = feature r, columns = edges col0..col0+31
+                tmem_ld32(tD2 + lane_base + col0, v);                  // lane = feature r, columns = edges col0..col0+31
                 tc_fence_before();
-                warp_arrive(bar(D2_EMPTY + b));
+                warp_arrive(bar(D2_EMPTY));
                 float* out = filt + e0 * kF + r;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {

@@ -514,15 +514,17 @@ class PaiNNEdges:
 _structure_cache = {}
 
 
-def _painn_structure(radius_edge_index, n_atoms, batch, num_graphs):
+def _painn_structure(radius_edge_index, n_atoms, batch, num_graphs, assume_sorted=False):
     """CSR by idx_j (row 1) and its grouping by idx_i, cached per edge tensor (both DDM views share it,
-    pretrain_GeoSSL.py:190-191).  Falls back to a stable sort if the list is not (idx_j, idx_i)-sorted."""
+    pretrain_GeoSSL.py:190-191).  Falls back to a stable sort if the list is not (idx_j, idx_i)-sorted; the check
+    costs one host sync, ``assume_sorted=True`` (lists produced by radius_graph are sorted) skips it so that the step
+    can be captured in a CUDA graph."""
     key = (radius_edge_index.data_ptr(), radius_edge_index._version, tuple(radius_edge_index.shape), n_atoms)
     hit = _structure_cache.get(key)
-    if hit is not None:
+    if hit is not None and not torch.cuda.is_current_stream_capturing():
         return hit
     rei = _req(radius_edge_index, torch.int64, "radius_edge_index", 2)
-    if rei.size(1) > 1:
+    if rei.size(1) > 1 and not assume_sorted:
         k = rei[1] * n_atoms + rei[0]
         if not bool((k[1:] > k[:-1]).all().item()):
             perm = torch.sort(k, stable=True).indices
@@ -535,9 +537,9 @@ def _painn_structure(radius_edge_index, n_atoms, batch, num_graphs):
     return g
 
 
-def painn_edges(positions, radius_edge_index, n_atoms, batch, offsets, widths, cutoff, num_graphs=None):
+def painn_edges(positions, radius_edge_index, n_atoms, batch, offsets, widths, cutoff, num_graphs=None, assume_sorted=False):
     pos = _req(positions.detach(), torch.float32, "positions", 2)
-    s = _painn_structure(radius_edge_index, n_atoms, batch, num_graphs)
+    s = _painn_structure(radius_edge_index, n_atoms, batch, num_graphs, assume_sorted)
     e = s.rei.size(1)
     dev = pos.device
     dist = torch.empty(e, dtype=torch.float32, device=dev)

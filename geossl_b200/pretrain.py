@@ -34,7 +34,8 @@ def _encode(args, model, x, positions, batch):
     if args.model_3d == "schnet":
         _, rep = model(x, positions, batch.batch, return_latent=True, num_graphs=n_graphs)
     elif args.model_3d == "painn":
-        _, rep = model(x, positions, batch.radius_edge_index, batch.batch, return_latent=True, num_graphs=n_graphs)
+        _, rep = model(x, positions, batch.radius_edge_index, batch.batch, return_latent=True, num_graphs=n_graphs,
+                       assume_sorted=bool(getattr(batch, "extras", {}).get("rei_sorted", False)))
     else:
         raise Exception("3D model {} not included.".format(args.model_3d))
     return rep
@@ -51,7 +52,8 @@ def _encode_stacked(args, model, x_01, positions_01, x_02, positions_02, batch):
         _, rep = model(x, pos, bvec, return_latent=True, num_graphs=2 * b)
     else:
         rei = batch.radius_edge_index
-        _, rep = model(x, pos, torch.cat([rei, rei + n], dim=1), bvec, return_latent=True, num_graphs=2 * b)
+        _, rep = model(x, pos, torch.cat([rei, rei + n], dim=1), bvec, return_latent=True, num_graphs=2 * b,
+                       assume_sorted=bool(getattr(batch, "extras", {}).get("rei_sorted", False)))
     return rep[:n], rep[n:]
 
 
@@ -167,7 +169,7 @@ class GraphedTrainStep:
         dev = b.positions.device
         self.static = type(b)(b.x.clone(), b.positions.clone(), b.batch.clone(), b.super_edge_index.clone(),
                               None if b.radius_edge_index is None else b.radius_edge_index.clone(), b.num_graphs,
-                              None if b.graph_ptr is None else b.graph_ptr.clone())
+                              None if b.graph_ptr is None else b.graph_ptr.clone(), dict(getattr(b, "extras", {})))
 
         def run():
             loss, _ = do_DDM(args, self.static, model, None, mu, sigma, heads=heads, device_noise=True)
