@@ -119,9 +119,12 @@ def load():
         if _lib is not None:
             return _lib
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"{LIB_PATH} is missing: geossl_b200 has no CPU / eager fallback. Build it with "
-                "`python -c \"import __graft_entry__ as g; g.build()\"` (needs nvcc).")
+            try:                                   # fresh checkout: compile in-tree (nvcc, ~10 s); there is no other path
+                build()
+            except Exception as exc:
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing and could not be built ({exc}): geossl_b200 has no CPU / eager fallback. "
+                    "Build it with `python -c \"import __graft_entry__ as g; g.build()\"` (needs nvcc).") from exc
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)     # AttributeError if the symbol is not exported
