@@ -73,11 +73,11 @@ class CFConv(torch.nn.Module):
         self.lin2.bias.data.fill_(0)
 
     # ---- training fast path: everything edge-wise happens inside two kernels
-    def forward_graph(self, x, graph, smearing):
-        x = ops.linear(x, self.lin1)
+    def forward_graph(self, x, graph, smearing, images=None):
+        x = ops.linear(x, self.lin1, images=images)
         x = ops.CFConvLayer.apply(x, self.nn[0].weight, self.nn[0].bias, self.nn[2].weight, self.nn[2].bias,
                                   smearing.offset, graph, smearing.coeff, self.cutoff)
-        return ops.linear(x, self.lin2)
+        return ops.linear(x, self.lin2, images=images)
 
     # ---- composable path (any derivative order): filter from torch ops, aggregate from the CUDA primitive
     def forward_composed(self, x, graph, edge_weight, edge_attr):
@@ -126,9 +126,10 @@ class InteractionBlock(torch.nn.Module):
         torch.nn.init.xavier_uniform_(self.lin.weight)
         self.lin.bias.data.fill_(0)
 
-    def forward_graph(self, x, graph, smearing, residual=None):
+    def forward_graph(self, x, graph, smearing, residual=None, images=None):
         # act + lin (+ the `h + interaction(...)` residual of schnet.py:97) are one fused kernel on the tensor-core path
-        return ops.linear(self.conv.forward_graph(x, graph, smearing), self.lin, pre_ssp=True, residual=residual)
+        return ops.linear(self.conv.forward_graph(x, graph, smearing, images), self.lin, pre_ssp=True, residual=residual,
+                          images=images)
 
     def forward_composed(self, x, graph, edge_weight, edge_attr):
         return self.lin(self.act(self.conv.forward_composed(x, graph, edge_weight, edge_attr)))
@@ -197,13 +198,17 @@ class SchNet(torch.nn.Module):
             for interaction in self.interactions:
                 h = h + interaction.forward_composed(h, ge, edge_weight, edge_attr)
         else:
+            layers = [self.lin1, self.lin2]
             for interaction in self.interactions:
-                h = interaction.forward_graph(h, graph, self.distance_expansion, residual=h)
+                layers += [interaction.conv.lin1, interaction.conv.lin2, interaction.lin]
+            images = ops.prepack_linear_weights(layers)
+            for interaction in self.interactions:
+                h = interaction.forward_graph(h, graph, self.distance_expansion, residual=h, images=images)
 
         if pos.requires_grad and torch.is_grad_enabled():
             h = self.lin2(self.act(self.lin1(h)))
         else:
-            h = ops.linear(ops.linear(h, self.lin1), self.lin2, pre_ssp=True)
+            h = ops.linear(ops.linear(h, self.lin1, images=images), self.lin2, pre_ssp=True, images=images)
 
         n_graphs = graph.graph_ptr.numel() - 1
         if self.dipole:

@@ -373,12 +373,44 @@ def _pack_weight(weight, transpose, bf16_parts):
     return image
 
 
-def _linear_tc(x, weight, transpose, bias, pre_ssp, act_grad_input, residual, bf16_parts, name):
+def _linear_tc(x, weight, transpose, bias, pre_ssp, act_grad_input, residual, bf16_parts, name, image=None):
     y = torch.empty((x.size(0), 128), dtype=torch.float32, device=x.device)
-    image = _pack_weight(weight, transpose, bf16_parts)
+    if image is None:
+        image = _pack_weight(weight, transpose, bf16_parts)
     _timed(name, lambda: _lib.load().geossl_linear_tc(_p(x), x.size(0), _p(image), _p(bias), 1 if pre_ssp else 0,
                                                       _p(act_grad_input), _p(residual), _p(y), 1 if bf16_parts else 0, _stream()))
     return y
+
+
+# Weight-gradient kernels are off the critical path of the backward chain (nothing upstream consumes them), and they are
+# small, latency-bound launches.  Inside ``side_stream_wgrads()`` they are issued on a second stream so that they fill the
+# gaps of the main chain; ``join_side_stream()`` must run before anything reads the gradients (optimizer, all-reduce).
+# Off by default: a caller that runs loss.backward(); optimizer.step() itself never sees a second stream.
+_SIDE = {"on": False, "stream": {}, "dirty": False}
+
+
+class side_stream_wgrads:
+    def __enter__(self):
+        self.prev = _SIDE["on"]
+        _SIDE["on"] = True
+
+    def __exit__(self, *exc):
+        join_side_stream()
+        _SIDE["on"] = self.prev
+
+
+def _side_stream(device):
+    st = _SIDE["stream"].get(device)
+    if st is None:
+        st = _SIDE["stream"][device] = torch.cuda.Stream(device=device)
+    return st
+
+
+def join_side_stream():
+    if _SIDE["dirty"]:
+        for dev, st in _SIDE["stream"].items():
+            torch.cuda.current_stream(dev).wait_stream(st)
+        _SIDE["dirty"] = False
 
 
 class LinearTC(torch.autograd.Function):
@@ -386,17 +418,19 @@ class LinearTC(torch.autograd.Function):
     Forward operands are split into fp16 parts, gradient operands into bf16 parts (see tc.cuh)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, pre_ssp):
+    def forward(ctx, x, weight, bias, residual, pre_ssp, images=None):
         x, weight = _req(x, torch.float32, "x", 2), _req(weight, torch.float32, "weight", 2)
         if x.size(1) != 128 or tuple(weight.shape) != (128, 128):
             raise RuntimeError("geossl_b200: LinearTC is built for 128 -> 128 layers")
         bias = None if bias is None else _req(bias, torch.float32, "bias", 1)
         residual = None if residual is None else _req(residual, torch.float32, "residual", 2)
         ctx.pre_ssp, ctx.has_bias, ctx.has_res = bool(pre_ssp), bias is not None, residual is not None
+        ctx.image_t = None if images is None else images[1]
         ctx.save_for_backward(x, weight)
         if x.size(0) == 0:
             return x.new_zeros((0, 128))
-        return _linear_tc(x, weight, False, bias, pre_ssp, None, residual, False, "linear_fwd")
+        return _linear_tc(x, weight, False, bias, pre_ssp, None, residual, False, "linear_fwd",
+                          None if images is None else images[0])
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -409,22 +443,67 @@ class LinearTC(torch.autograd.Function):
             return (torch.zeros_like(x), torch.zeros_like(weight), torch.zeros(128, device=x.device) if ctx.has_bias else None,
                     gy if ctx.has_res else None, None)
         if ctx.needs_input_grad[0]:
-            gx = _linear_tc(gy, weight, True, None, False, x if ctx.pre_ssp else None, None, True, "linear_dgrad")
+            gx = _linear_tc(gy, weight, True, None, False, x if ctx.pre_ssp else None, None, True, "linear_dgrad", ctx.image_t)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             lib = _lib.load()
-            gw = torch.empty_like(weight)
-            gb = torch.empty(128, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-            ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
-            _timed("linear_wgrad", lambda: lib.geossl_linear_wgrad_tc(_p(gy), _p(x), n, 1 if ctx.pre_ssp else 0, _p(ws), _p(gw), _p(gb),
-                                                                      _stream()))
-        return gx, gw, gb, (gy if ctx.has_res else None), None
+
+            def wgrad():
+                gw_ = torch.empty_like(weight)
+                gb_ = torch.empty(128, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
+                _timed("linear_wgrad", lambda: lib.geossl_linear_wgrad_tc(_p(gy), _p(x), n, 1 if ctx.pre_ssp else 0, _p(ws), _p(gw_),
+                                                                          _p(gb_), _stream()))
+                return gw_, gb_
+
+            if _SIDE["on"]:
+                main, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    gw, gb = wgrad()
+                for t in (gy, x):
+                    t.record_stream(side)
+                for t in (gw, gb):
+                    if t is not None:
+                        t.record_stream(main)
+                _SIDE["dirty"] = True
+            else:
+                gw, gb = wgrad()
+        return gx, gw, gb, (gy if ctx.has_res else None), None, None
 
 
-def linear(x, layer, pre_ssp=False, residual=None):
+def linear_tc_applies(layer):
+    w = layer.weight
+    return FILTER_MODE != "simt" and w.is_cuda and tuple(w.shape) == (128, 128)
+
+
+def prepack_linear_weights(layers):
+    """Pack the operand images of several 128x128 layers (forward orientation in fp16 parts, transposed orientation in
+    bf16 parts for the data gradient) on the side stream, ahead of their first use: none of them depends on anything
+    computed in the step, so the ~3 us launches overlap the neighbour search.  Returns {layer: (image, image_t)}; valid
+    for the current forward/backward only (weights change at the next optimizer step)."""
+    layers = [l for l in layers if linear_tc_applies(l)]
+    if not layers:
+        return {}
+    dev = layers[0].weight.device
+    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+    side.wait_stream(main)
+    out = {}
+    with torch.cuda.stream(side):
+        for l in layers:
+            w = l.weight.detach()
+            out[l] = (_pack_weight(w, False, False), _pack_weight(w, True, True))
+    main.wait_stream(side)
+    for a, b in out.values():
+        a.record_stream(main)
+        b.record_stream(main)
+    return out
+
+
+def linear(x, layer, pre_ssp=False, residual=None, images=None):
     """nn.Linear on the tensor-core path when it applies (128 -> 128, tensor-core mode), else library GEMM."""
     w = layer.weight
-    if FILTER_MODE != "simt" and x.dim() == 2 and x.size(1) == 128 and tuple(w.shape) == (128, 128) and x.is_cuda:
-        return LinearTC.apply(x, w, layer.bias, residual, pre_ssp)
+    if x.dim() == 2 and x.size(1) == 128 and x.is_cuda and linear_tc_applies(layer):
+        return LinearTC.apply(x, w, layer.bias, residual, pre_ssp, None if images is None else images.get(layer))
     if pre_ssp:
         x = torch.nn.functional.softplus(x) - 0.6931471824645996
     y = torch.nn.functional.linear(x, w, layer.bias)

@@ -145,7 +145,8 @@ def train_step(args, batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_syn
     loss, _ = do_DDM(args, batch, model, None, mu, sigma, heads=heads, device_noise=device_noise, draws=draws,
                      positions_02=positions_02)
     optimizer.zero_grad(set_to_none=True)
-    loss.backward()
+    with ops.side_stream_wgrads():          # small weight-gradient kernels overlap the backward chain; joined on exit
+        loss.backward()
     if grad_sync is not None:
         grad_sync()
     optimizer.step()
@@ -173,7 +174,8 @@ class GraphedTrainStep:
 
         def run():
             loss, _ = do_DDM(args, self.static, model, None, mu, sigma, heads=heads, device_noise=True)
-            loss.backward()
+            with ops.side_stream_wgrads():
+                loss.backward()
             if grad_sync is not None:
                 grad_sync()
             optimizer.step()
