@@ -760,16 +760,19 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         fence_proxy_async();
         __syncthreads();
         // ---- 2. MMA1: D1^T = W0h . feat^T
-        if (tid == 0) {
+        if (warp == 0) {                                      // uniform operands; the elected lane issues
             tc_fence_after();
-            const uint64_t ah = desc_k_sw128(sbase + L::W0), al = desc_k_sw128(sbase + L::W0 + 2 * kHBlkW);
-            const uint64_t bh = desc_k_sw128(sbase + L::FEAT), bl = desc_k_sw128(sbase + L::FEAT + 2 * kHBlkT);
+            if (elect_one_sync()) {
+                const uint64_t ah = desc_k_sw128(sbase + L::W0), al = desc_k_sw128(sbase + L::W0 + 2 * kHBlkW);
+                const uint64_t bh = desc_k_sw128(sbase + L::FEAT), bl = desc_k_sw128(sbase + L::FEAT + 2 * kHBlkT);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const uint32_t oa = (ks >> 2) * (kHBlkW >> 4) + 2 * (ks & 3), ob = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
-                mma3(tD1, ah + oa, al + oa, bh + ob, bl + ob, id_t, ks > 0);
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t oa = (ks >> 2) * (kHBlkW >> 4) + 2 * (ks & 3), ob = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
+                    mma3(tD1, ah + oa, al + oa, bh + ob, bl + ob, id_t, ks > 0);
+                }
+                tc_commit(bar);
             }
-            tc_commit(bar);
+            __syncwarp();
         }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
@@ -789,16 +792,19 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         fence_proxy_async();
         __syncthreads();
         // ---- 4. MMA2: D2^T = W1 . z1^T   (rows n2 >= 64 of the A operand are garbage lanes that are never read)
-        if (tid == 0) {
+        if (warp == 0) {                                      // uniform operands; the elected lane issues
             tc_fence_after();
-            const uint64_t ah = desc_k_sw128(sbase + L::W1), al = desc_k_sw128(sbase + L::W1 + 2 * kHBlkT);
-            const uint64_t bh = desc_k_sw128(sbase + L::Z1), bl = desc_k_sw128(sbase + L::Z1 + 2 * kHBlkT);
+            if (elect_one_sync()) {
+                const uint64_t ah = desc_k_sw128(sbase + L::W1), al = desc_k_sw128(sbase + L::W1 + 2 * kHBlkT);
+                const uint64_t bh = desc_k_sw128(sbase + L::Z1), bl = desc_k_sw128(sbase + L::Z1 + 2 * kHBlkT);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const uint32_t o = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
-                mma3(tD2, ah + o, al + o, bh + o, bl + o, id_t, ks > 0);
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t o = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
+                    mma3(tD2, ah + o, al + o, bh + o, bl + o, id_t, ks > 0);
+                }
+                tc_commit(bar);
             }
-            tc_commit(bar);
+            __syncwarp();
         }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
@@ -841,17 +847,20 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         fence_proxy_async();
         __syncthreads();
         // ---- 6. MMA3: D3^T = W1^T . dz2^T (A = MN-major view of the W1 image, K = 64) ; WG1: DW1^T += z1^T dz2
-        if (tid == 0) {
+        if (warp == 0) {                                      // uniform operands; the elected lane issues
             tc_fence_after();
-            const uint64_t ah = desc_mn_sw128(sbase + L::W1, kHBlkT), al = desc_mn_sw128(sbase + L::W1 + 2 * kHBlkT, kHBlkT);
-            const uint64_t bh = desc_k_sw128(sbase + L::DZ2), bl = desc_k_sw128(sbase + L::DZ2 + kHBlkT);
+            if (elect_one_sync()) {
+                const uint64_t ah = desc_mn_sw128(sbase + L::W1, kHBlkT), al = desc_mn_sw128(sbase + L::W1 + 2 * kHBlkT, kHBlkT);
+                const uint64_t bh = desc_k_sw128(sbase + L::DZ2), bl = desc_k_sw128(sbase + L::DZ2 + kHBlkT);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma3(tD3, ah + ks * 128, al + ks * 128, bh + 2 * ks, bl + 2 * ks, id_a_mn, ks > 0);
-            const uint64_t zh = desc_mn_sw128(sbase + L::Z1, kHBlkT), zl = desc_mn_sw128(sbase + L::Z1 + 2 * kHBlkT, kHBlkT);
-            const uint64_t dh = desc_mn_sw128(sbase + L::DZ2, kHBlkT), dl = desc_mn_sw128(sbase + L::DZ2 + kHBlkT, kHBlkT);
+                for (int ks = 0; ks < 4; ++ks) mma3(tD3, ah + ks * 128, al + ks * 128, bh + 2 * ks, bl + 2 * ks, id_a_mn, ks > 0);
+                const uint64_t zh = desc_mn_sw128(sbase + L::Z1, kHBlkT), zl = desc_mn_sw128(sbase + L::Z1 + 2 * kHBlkT, kHBlkT);
+                const uint64_t dh = desc_mn_sw128(sbase + L::DZ2, kHBlkT), dl = desc_mn_sw128(sbase + L::DZ2 + kHBlkT, kHBlkT);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma3(tDW1, zh + ks * 128, zl + ks * 128, dh + ks * 128, dl + ks * 128, id_wg1, (done | ks) > 0);
-            tc_commit(bar);
+                for (int ks = 0; ks < 4; ++ks) mma3(tDW1, zh + ks * 128, zl + ks * 128, dh + ks * 128, dl + ks * 128, id_wg1, (done | ks) > 0);
+                tc_commit(bar);
+            }
+            __syncwarp();
         }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
@@ -875,20 +884,23 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         fence_proxy_async();
         __syncthreads();
         // ---- 8. MMA4: D4^T = W0h^T . dz1^T (A = MN-major view of the W0 image, K = 128) ; WG0: DW0 += dz1^T feat
-        if (tid == 0) {
+        if (warp == 0) {                                      // uniform operands; the elected lane issues
             tc_fence_after();
-            const uint64_t ah = desc_mn_sw128(sbase + L::W0, kHBlkW), al = desc_mn_sw128(sbase + L::W0 + 2 * kHBlkW, kHBlkW);
-            const uint64_t bh = desc_k_sw128(sbase + L::DZ1), bl = desc_k_sw128(sbase + L::DZ1 + 2 * kHBlkT);
+            if (elect_one_sync()) {
+                const uint64_t ah = desc_mn_sw128(sbase + L::W0, kHBlkW), al = desc_mn_sw128(sbase + L::W0 + 2 * kHBlkW, kHBlkW);
+                const uint64_t bh = desc_k_sw128(sbase + L::DZ1), bl = desc_k_sw128(sbase + L::DZ1 + 2 * kHBlkT);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const uint32_t ob = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
-                mma3(tD4, ah + ks * 128, al + ks * 128, bh + ob, bl + ob, id_a_mn, ks > 0);
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t ob = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
+                    mma3(tD4, ah + ks * 128, al + ks * 128, bh + ob, bl + ob, id_a_mn, ks > 0);
+                }
+                const uint64_t zh = desc_mn_sw128(sbase + L::DZ1, kHBlkT), zl = desc_mn_sw128(sbase + L::DZ1 + 2 * kHBlkT, kHBlkT);
+                const uint64_t fh = desc_mn_sw128(sbase + L::FEAT, kHBlkT), fl = desc_mn_sw128(sbase + L::FEAT + 2 * kHBlkT, kHBlkT);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma3(tDW0, zh + ks * 128, zl + ks * 128, fh + ks * 128, fl + ks * 128, id_wg0, (done | ks) > 0);
+                tc_commit(bar);
             }
-            const uint64_t zh = desc_mn_sw128(sbase + L::DZ1, kHBlkT), zl = desc_mn_sw128(sbase + L::DZ1 + 2 * kHBlkT, kHBlkT);
-            const uint64_t fh = desc_mn_sw128(sbase + L::FEAT, kHBlkT), fl = desc_mn_sw128(sbase + L::FEAT + 2 * kHBlkT, kHBlkT);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma3(tDW0, zh + ks * 128, zl + ks * 128, fh + ks * 128, fl + ks * 128, id_wg0, (done | ks) > 0);
-            tc_commit(bar);
+            __syncwarp();
         }
         if (tid < kHP) sDemb[tid] = sRed[tid] + sRed[64 + tid] + sRed[128 + tid] + sRed[192 + tid];
         mbar_wait(bar, phase); phase ^= 1;

@@ -225,7 +225,8 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
         }
     } else if (warp == kBwdMmaWarp) {
         // ===================== MMA issuer
-        if (lane == 0) {
+        {
+            const bool leader = elect_one_sync();
             constexpr uint32_t fmt = Split<kBwdFP16>::kFmt;
             const uint32_t id_t = idesc_f16(fmt, 128, kBT);                 // D^T tiles: M = features, N = 64 edges
             const uint32_t id_w2 = idesc_f16(fmt, 128, 128, 1, 1), id_w1 = idesc_f16(fmt, 128, 64, 1, 1);
@@ -236,9 +237,12 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 mbar_wait(bar(D1_FREE_), (i & 1) ^ 1);
                 tc_fence_after();
                 const uint64_t ph = desc_k_sw128(sbase + L::PHI + b * 2 * kBlkT), pl = desc_k_sw128(sbase + L::PHI + b * 2 * kBlkT + kBlkT);
+                if (leader) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) mma3_ts(tD1, tW1h + 8 * kk, tW1l + 8 * kk, ph + 2 * kk, pl + 2 * kk, id_t, kk > 0);
-                tc_commit(bar(D1_FULL_));
+                    for (int kk = 0; kk < 4; ++kk) mma3_ts(tD1, tW1h + 8 * kk, tW1l + 8 * kk, ph + 2 * kk, pl + 2 * kk, id_t, kk > 0);
+                    tc_commit(bar(D1_FULL_));
+                }
+                __syncwarp();
             };
             if (my_tiles > 0) mma1(0);
             for (int i = 0; i < my_tiles; ++i) {
@@ -252,13 +256,16 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 trace_b(i, 4);
                 {
                     const uint64_t uh = desc_k_sw128(du), ul = desc_k_sw128(du + 2 * kBlkT);
+                    if (leader) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t ot = (ks >> 2) * (kBlkT >> 4) + 2 * (ks & 3);
-                        mma3_ts(tD3, tW2h + 8 * ks, tW2l + 8 * ks, uh + ot, ul + ot, id_t, ks > 0);
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint32_t ot = (ks >> 2) * (kBlkT >> 4) + 2 * (ks & 3);
+                            mma3_ts(tD3, tW2h + 8 * ks, tW2l + 8 * ks, uh + ot, ul + ot, id_t, ks > 0);
+                        }
+                        tc_commit(bar(D3_FULL_));
                     }
+                    __syncwarp();
                 }
-                tc_commit(bar(D3_FULL_));
                 // ---- WG2(i): DW2 += dU^T s
                 mbar_wait(bar(S_FULL_ + b), (i >> 1) & 1);
                 tc_fence_after();
@@ -266,14 +273,17 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 {
                     const uint64_t uh = desc_mn_sw128(du, kBlkT), ul = desc_mn_sw128(du + 2 * kBlkT, kBlkT);
                     const uint64_t sh = desc_mn_sw128(sa, kBlkT), sl = desc_mn_sw128(sa + 2 * kBlkT, kBlkT);
+                    if (leader) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t o = ks * (2048 >> 4);
-                        mma3(tDW2, uh + o, ul + o, sh + o, sl + o, id_w2, (i | ks) > 0);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t o = ks * (2048 >> 4);
+                            mma3(tDW2, uh + o, ul + o, sh + o, sl + o, id_w2, (i | ks) > 0);
+                        }
+                        tc_commit(bar(S_FREE_ + b));
+                        tc_commit(bar(DU_FREE_ + b));
                     }
+                    __syncwarp();
                 }
-                tc_commit(bar(S_FREE_ + b));
-                tc_commit(bar(DU_FREE_ + b));
                 trace_b(i, 6);
                 // ---- MMA1(i+1)
                 if (i + 1 < my_tiles) mma1(i + 1);
@@ -284,17 +294,21 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 {
                     const uint32_t ph_addr = sbase + L::PHI + b * 2 * kBlkT;
                     const uint64_t ph = desc_mn_sw128(ph_addr, kBlkT), pl = desc_mn_sw128(ph_addr + kBlkT, kBlkT);
+                    if (leader) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t o = ks * (2048 >> 4);
-                        mma3(tDW1, dAh + o, dAl + o, ph + o, pl + o, id_w1, (i | ks) > 0);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t o = ks * (2048 >> 4);
+                            mma3(tDW1, dAh + o, dAl + o, ph + o, pl + o, id_w1, (i | ks) > 0);
+                        }
+                        tc_commit(bar(DA_FREE_));
+                        tc_commit(bar(PHI_FREE_ + b));
                     }
+                    __syncwarp();
                 }
-                tc_commit(bar(DA_FREE_));
-                tc_commit(bar(PHI_FREE_ + b));
                 trace_b(i, 8);
             }
-            tc_commit(bar(DONE_));
+            if (leader) tc_commit(bar(DONE_));
+            __syncwarp();
         }
     } else {
         // ===================== epilogue warps (TMEM lane = feature, columns = edges): warp = (quadrant q, edge quarter eq)

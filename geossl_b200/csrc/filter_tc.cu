@@ -156,8 +156,9 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             if (warp == kProdWarp0) trace(i, 1);
         }
     } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer (one thread)
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp runs the loop; the elected lane issues)
+        {
+            const bool leader = elect_one_sync();
             const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, kTile, kF);
             const uint64_t dW1h = desc_k_sw128(sbase + L::W1_hi), dW1l = desc_k_sw128(sbase + L::W1_lo);
             auto issue_mma1 = [&](int i) {
@@ -167,11 +168,14 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 tc_fence_after();
                 trace(i, 2);
                 const uint64_t dPh = desc_k_sw128(sbase + L::PHI + b * 2 * kBlk), dPl = desc_k_sw128(sbase + L::PHI + b * 2 * kBlk + kBlk);
+                if (leader) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)                         // K = 64 = 4 x 16 (+32 bytes = +2 encoded)
-                    mma3(tD1[b], dPh + 2 * kk, dPl + 2 * kk, dW1h + 2 * kk, dW1l + 2 * kk, idesc, kk > 0);
-                tc_commit(bar(PHI_EMPTY + b));
-                tc_commit(bar(D1_FULL + b));
+                    for (int kk = 0; kk < 4; ++kk)                     // K = 64 = 4 x 16 (+32 bytes = +2 encoded)
+                        mma3(tD1[b], dPh + 2 * kk, dPl + 2 * kk, dW1h + 2 * kk, dW1l + 2 * kk, idesc, kk > 0);
+                    tc_commit(bar(PHI_EMPTY + b));
+                    tc_commit(bar(D1_FULL + b));
+                }
+                __syncwarp();
                 trace(i, 3);
             };
             if (my_tiles > 0) issue_mma1(0);
@@ -183,15 +187,18 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 const uint64_t dSh = desc_k_sw128(sbase + L::S + b * 4 * kBlk), dSl = desc_k_sw128(sbase + L::S + b * 4 * kBlk + 2 * kBlk);
                 tc_fence_after();
                 trace(i, 4);
+                if (leader) {
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)                         // K = 128 = 2 blocks x 4 x 16
+                    for (int kb = 0; kb < 2; ++kb)                     // K = 128 = 2 blocks x 4 x 16
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t o = kb * (kBlk >> 4) + 2 * kk, ka = (kb * 4 + kk) * 8;
-                        mma3_ts(tD2, tW2h + ka, tW2l + ka, dSh + o, dSl + o, idesc, (kb | kk) > 0);   // D2^T = W2 . S^T
-                    }
-                tc_commit(bar(S_EMPTY + b));
-                tc_commit(bar(D2_FULL));
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t o = kb * (kBlk >> 4) + 2 * kk, ka = (kb * 4 + kk) * 8;
+                            mma3_ts(tD2, tW2h + ka, tW2l + ka, dSh + o, dSl + o, idesc, (kb | kk) > 0);   // D2^T = W2 . S^T
+                        }
+                    tc_commit(bar(S_EMPTY + b));
+                    tc_commit(bar(D2_FULL));
+                }
+                __syncwarp();
                 trace(i, 5);
             }
         }
@@ -295,7 +302,7 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
         __syncthreads();
         tc_fence_after();
     }
-    if (tid == 0) {
+    if (warp == 0 && elect_one_sync()) {                             // uniform operands; the elected lane issues
         if (mode == 0) {
             const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, 128);
             const uint64_t ah = desc_k_sw128(sbase), al = desc_k_sw128(sbase + 2 * kBlk);
@@ -313,17 +320,30 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
                 mma3_ts(tmem, tmem + 128 + ks * 8, tmem + 192 + ks * 8, bh + o, bl + o, idesc, ks > 0);
             }
             (void)t0;
-        } else if (mode == 4 || mode == 5) {
-            // throughput probes: mode 4 = A in TMEM (K-major B from smem), mode 5 = both operands MN-major from smem
-            const uint32_t idesc = mode == 4 ? idesc_f16(Split<FP16>::kFmt, 128, N) : idesc_f16(Split<FP16>::kFmt, 128, N, 1, 1);
-            const uint64_t bh = desc_k_sw128(sbase + 4 * kBlk);
-            const uint64_t am = desc_mn_sw128(sbase, kBlk), bm = desc_mn_sw128(sbase + 4 * kBlk, kBlk);
+        } else if (mode >= 4 && mode <= 7) {
+            // throughput probes with a LEAN issue loop (descriptors precomputed, no branches inside):
+            // 4 = A in TMEM (K-major B from smem), 5 = A,B MN-major, 6 = A MN-major / B K-major, 7 = A K-major / B MN-major
+            const uint32_t idesc = mode == 4 ? idesc_f16(Split<FP16>::kFmt, 128, N)
+                                             : idesc_f16(Split<FP16>::kFmt, 128, N, mode != 7 ? 1 : 0, mode != 6 ? 1 : 0);
+            uint64_t da[4], db[4];
+            uint32_t ta[4];
+            for (int ks = 0; ks < 4; ++ks) {
+                ta[ks] = tmem + 128 + ks * 8;
+                da[ks] = (mode == 7) ? desc_k_sw128(sbase) + 2 * ks : desc_mn_sw128(sbase, kBlk) + ks * 128;
+                db[ks] = (mode == 4 || mode == 6) ? desc_k_sw128(sbase + 4 * kBlk) + 2 * ks : desc_mn_sw128(sbase + 4 * kBlk, kBlk) + ks * 128;
+            }
             const long long t0 = clock64();
-            for (int rep = 0; rep < 60; ++rep)
-                for (int ks = 0; ks < 4; ++ks) {
-                    if (mode == 4) mma_f16_ts(tmem, tmem + 128 + ks * 8, bh + 2 * ks, idesc, 1u);
-                    else mma_f16_ss(tmem, am + ks * 128, bm + ks * 128, idesc, 1u);
+            if (mode == 4) {
+                for (int rep = 0; rep < 60; ++rep) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) mma_f16_ts(tmem, ta[ks], db[ks], idesc, 1u);
                 }
+            } else {
+                for (int rep = 0; rep < 60; ++rep) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) mma_f16_ss(tmem, da[ks], db[ks], idesc, 1u);
+                }
+            }
             const long long t1 = clock64();
             tc_commit(bar);
             mbar_wait(bar, 0);
@@ -385,7 +405,7 @@ int geossl_debug_set_trace(long long* device_buffer) {
 int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream) {
     GEOSSL_REQUIRE(a && b && d, "null pointer");
     GEOSSL_REQUIRE((mode == 0 && (K == 64 || K == 128) && N == 128) || (mode == 1 && K == 128 && (N == 64 || N == 128)) ||
-                   ((mode == 2 || mode == 4 || mode == 5) && K == 64 && (N == 64 || N == 128)) || (mode == 3 && (K == 64 || K == 128) && (N == 64 || N == 128)),
+                   ((mode == 2 || (mode >= 4 && mode <= 7)) && K == 64 && (N == 64 || N == 128)) || (mode == 3 && (K == 64 || K == 128) && (N == 64 || N == 128)),
                    "unsupported shape");
     const size_t smem = 8 * tc::kBlk + 64 + 1024;
     if (fp16) {

@@ -131,17 +131,20 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
         }
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {                                       // whole warp (uniform operands); the elected lane issues
             mbar_wait(wbar, 0);                                // (completes once; later tiles pass immediately)
             tc_fence_after();
             const uint64_t wh = desc_k_sw128(sbase + L::W), wl = desc_k_sw128(sbase + L::W + 2 * kNBlkW);
             const uint64_t xh = desc_k_sw128(sbase + L::X), xl = desc_k_sw128(sbase + L::X + 2 * kNBlkT);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kNBlkT >> 4) + 2 * (ks & 3);
-                mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, ks > 0);
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kNBlkT >> 4) + 2 * (ks & 3);
+                    mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, ks > 0);
+                }
+                tc_commit(bar);
             }
-            tc_commit(bar);
+            __syncwarp();
         }
         mbar_wait(bar, phase);
         phase ^= 1;
@@ -243,16 +246,19 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
         stage_rows_mn<FP16, false>(X, row0, n_rows, pre_ssp != 0, smem + L::XT, smem + L::XT + 2 * kNBlkT, dummy);
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             const uint64_t ah = desc_mn_sw128(sbase + L::DY, kNBlkT), al = desc_mn_sw128(sbase + L::DY + 2 * kNBlkT, kNBlkT);
             const uint64_t bh = desc_mn_sw128(sbase + L::XT, kNBlkT), bl = desc_mn_sw128(sbase + L::XT + 2 * kNBlkT, kNBlkT);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t o = ks * (2048 >> 4);
-                mma3(tmem, ah + o, al + o, bh + o, bl + o, idesc, (done | ks) > 0);
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t o = ks * (2048 >> 4);
+                    mma3(tmem, ah + o, al + o, bh + o, bl + o, idesc, (done | ks) > 0);
+                }
+                tc_commit(bar);
             }
-            tc_commit(bar);
+            __syncwarp();
         }
         mbar_wait(bar, phase);                               // tiles are re-staged only after the MMAs have read them
         phase ^= 1;

@@ -67,6 +67,13 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {  
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {    // whole warp
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// Warp-uniform leader election.  The MMA warp runs its loop with all 32 lanes (so every descriptor / address is
+// provably warp-uniform and lands in uniform registers) and only the elected lane issues tcgen05.mma / commit.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // all previously issued MMAs of this thread complete -> one arrive on the mbarrier

@@ -4,8 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from geossl_b200 import _lib
 lib = _lib.load()
-NAMES = {2: "SS  K-major A,B from smem", 4: "TS  A in TMEM, B K-major smem", 5: "SS  A,B MN-major from smem"}
-for mode, N in ((2, 128), (2, 64), (4, 128), (4, 64), (5, 128), (5, 64)):
+NAMES = {2: "SS  K-major A,B from smem", 4: "TS  A in TMEM, B K-major smem", 5: "SS  A,B MN-major from smem",
+         6: "SS  A MN-major, B K-major", 7: "SS  A K-major, B MN-major"}
+for mode, N in ((2, 128), (2, 64), (4, 128), (4, 64), (5, 128), (5, 64), (6, 128), (6, 64), (7, 128), (7, 64)):
     a, b = torch.randn(128, 64, device="cuda"), torch.randn(128, 64, device="cuda")
     d = torch.zeros(128, N, device="cuda")
     for _ in range(2):
