@@ -210,6 +210,10 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
         const int col0 = cq * 32;                                     // this warp's 32 accumulator columns
         const float b2f = sB2[r];
         for (int i = 0; i <= my_tiles; ++i) {
+            // E2(i-1)'s edge distance is fetched before E1(i) so its global-load latency hides behind the softplus phase
+            const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)(i - 1) * gridDim.x) * kTile + col0;
+            float dpre = 0.f;
+            if (i > 0 && e0 + lane < n_edges) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dpre) : "l"(edge_dist + e0 + lane));
             if (i < my_tiles) {
                 const int b = i & 1;
                 mbar_wait(bar(D1_FULL + b), (i >> 1) & 1);
@@ -235,9 +239,8 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             }
             if (i > 0) {
                 const int t = i - 1;
-                const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kTile + col0;
                 // lane j holds the cutoff of edge column j of this warp; broadcast by shuffle in the store loop
-                const float myc = (e0 + lane < n_edges) ? cosine_cutoff(__ldg(edge_dist + e0 + lane), cutoff) : 0.f;
+                const float myc = (e0 + lane < n_edges) ? 0.5f * (__cosf(dpre * (kPi / cutoff)) + 1.0f) : 0.f;
                 mbar_wait(bar(D2_FULL), t & 1);
                 tc_fence_after();
                 if (warp == 0) trace(t, 11);

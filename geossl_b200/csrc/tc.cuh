@@ -33,15 +33,16 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
+constexpr uint32_t kWaitHintNs = 20000;
 // Spin on the phase parity.  Bounded: a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"      // suspend-time hint: sleep in hardware,
+            "selp.u32 %0, 1, 0, p;\n\t}"                                        // not in an issue-slot-eating spin loop
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(kWaitHintNs) : "memory");
         if (spin > (1u << 28)) __trap();
     }
 }
