@@ -53,10 +53,33 @@ def pair_count(n, option="combination"):
     return full // 2 if option == "combination" else full
 
 
-def super_edges_host(counts, option="combination"):
+def sampled_pair_count(n, option="combination", ratio=1.0):
+    """``int(M * ratio)`` pairs kept per molecule (dataloaders_AtomTuple.py:25-27); M itself when ratio >= 1."""
+    m = pair_count(n, option)
+    if ratio >= 1:
+        return m
+    return np.asarray([int(v * ratio) for v in np.atleast_1d(m).tolist()], dtype=np.int64).reshape(np.shape(m))
+
+
+def sample_pairs_host(counts, option="combination", ratio=1.0, rng=np.random):
+    """The reference's sub-sampling draw (dataloaders_AtomTuple.py:25-29): per molecule, in molecule order,
+    ``rng.choice(M, int(M * ratio), replace=False)``.  With ``rng=np.random`` and the same ``np.random.seed`` this
+    consumes the global numpy stream exactly like ``AtomTupleExtractor.__call__``.  Returns one index array per
+    molecule (molecules with fewer than two atoms draw nothing, :17)."""
+    sel = []
+    for n in np.asarray(counts, dtype=np.int64).tolist():
+        m = int(pair_count(n, option))
+        sel.append(rng.choice(m, int(m * ratio), replace=False).astype(np.int64) if n >= 2 else np.empty(0, np.int64))
+    return sel
+
+
+def super_edges_host(counts, option="combination", ratio=1.0, selection=None, rng=np.random):
     """All ordered atom pairs per molecule in ``itertools`` order, offset by cumulative atom count.
-    Vectorised numpy restatement of AtomTupleExtractor + the collate offset (ratio == 1)."""
+    Vectorised numpy restatement of AtomTupleExtractor + the collate offset; ``ratio < 1`` keeps the sampled
+    columns in draw order (``selection`` = the per-molecule index arrays, default: drawn from ``rng``)."""
     counts = np.asarray(counts, dtype=np.int64)
+    if ratio < 1 and selection is None:
+        selection = sample_pairs_host(counts, option, ratio, rng)
     offs = np.concatenate([[0], np.cumsum(counts)])
     us, vs = [], []
     cache = {}
@@ -71,6 +94,8 @@ def super_edges_host(counts, option="combination"):
                 v = np.concatenate([np.delete(np.arange(n), i) for i in range(n)])
             cache[n] = (u.astype(np.int64), v.astype(np.int64))
         u, v = cache[n]
+        if selection is not None:
+            u, v = u[selection[g]], v[selection[g]]
         us.append(u + offs[g])
         vs.append(v + offs[g])
     if not us:
@@ -98,17 +123,41 @@ def synthetic_batch(num_graphs=32, atoms=30, atoms_max=None, *, seed=0, option="
                           None, int(num_graphs), torch.from_numpy(ptr))
 
 
-def assemble_batch_device(counts, z, positions, option="combination", device="cuda"):
+def assemble_batch_device(counts, z, positions, option="combination", device="cuda", ratio=1.0, selection=None,
+                          generator=None):
     """Batch assembly on the GPU from per-molecule atom counts (host list) + concatenated ``z`` / ``positions``:
     ``batch``, ``graph_ptr`` and ``super_edge_index`` are produced by geossl_super_edges instead of the reference's
-    Python itertools loop (dataloaders_AtomTuple.py:15-37) and collate (:45-73)."""
+    Python itertools loop (dataloaders_AtomTuple.py:15-37) and collate (:45-73).
+
+    ``ratio < 1`` (``--distance_sample_ratio``, :25-29) keeps ``int(M * ratio)`` distinct pairs per molecule.  The
+    draw happens on the device (random key per pair, one sort keyed by (molecule, key), first ``int(M * ratio)`` of
+    each segment): same distribution as ``np.random.choice(..., replace=False)``, a different random stream.  Pass
+    ``selection`` (per-molecule index arrays, e.g. from ``sample_pairs_host``) to reproduce the host draw exactly."""
     from . import ops
     counts = np.asarray(counts, dtype=np.int64)
     n_atoms, n_graphs = int(counts.sum()), len(counts)
     pc = pair_count(counts, option)
     ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(device)
-    pair_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(pc)]).astype(np.int64)).to(device)
+    pair_off = np.concatenate([[0], np.cumsum(pc)]).astype(np.int64)
+    pair_ptr = torch.from_numpy(pair_off).to(device)
     sei, batch = ops.super_edges(ptr, pair_ptr, n_graphs, n_atoms, int(pc.sum()), option == "permutation")
+    if ratio < 1:
+        if selection is not None:
+            cols = np.concatenate([np.asarray(s, dtype=np.int64) + pair_off[g] for g, s in enumerate(selection)]
+                                  + [np.empty(0, np.int64)])
+            cols = torch.from_numpy(cols).to(device)
+        else:
+            kept = sampled_pair_count(counts, option, ratio)                    # host-known => no device sync
+            kept_off = np.concatenate([[0], np.cumsum(kept)]).astype(np.int64)
+            seg = torch.repeat_interleave(torch.arange(n_graphs, device=device), torch.from_numpy(pc).to(device),
+                                          output_size=int(pc.sum()))
+            key = seg.double() + torch.rand(seg.numel(), device=device, dtype=torch.float64, generator=generator)
+            order = torch.argsort(key)                                          # molecule-major, random within
+            seg_k = torch.repeat_interleave(torch.arange(n_graphs, device=device), torch.from_numpy(kept).to(device),
+                                            output_size=int(kept.sum()))
+            rank = torch.arange(int(kept.sum()), device=device) - torch.from_numpy(kept_off).to(device)[seg_k]
+            cols = order[pair_ptr[seg_k] + rank]
+        sei = sei[:, cols].contiguous()
     z = z.to(device)
     x = torch.stack([z, torch.zeros_like(z)], dim=1)
     return AtomTupleBatch(x, positions.to(device), batch, sei, None, n_graphs, ptr)

@@ -92,8 +92,120 @@ def do_DDM(args, batch, model, criterion=None, mu=0.0, sigma=0.3, num_neg=1, hea
     return loss, 0
 
 
-def default_args(model_3d="schnet", normalize=False):
-    return SimpleNamespace(model_3d=model_3d, normalize=normalize)
+def default_args(model_3d="schnet", normalize=False, T=0.1):
+    return SimpleNamespace(model_3d=model_3d, normalize=normalize, T=T)
+
+
+# ------------------------------------------------------------------------------------------ sibling objectives
+# same two-view encoder pass as do_DDM, (B,H) molecule representations, tiny heads.
+def cycle_index(num, shift):
+    """examples/util.py:19-22."""
+    arr = torch.arange(num) + shift
+    arr[-shift:] = torch.arange(shift)
+    return arr
+
+
+def _two_view_molecule_repr(args, batch, model, mu, sigma, positions_02=None, device_noise=False, stack_views=True):
+    """The shared prologue of do_RR / do_EBM_NCE / do_InfoNCE (pretrain_GeoSSL.py:103-120,141-157): the readout of
+    the clean and the perturbed view, both through ONE stacked encoder launch sequence when the graph count is known."""
+    x_01 = batch.x[:, 0]
+    positions_01 = batch.positions
+    if positions_02 is None:
+        x_02, positions_02 = perturb(x_01, positions_01, mu, sigma, device_noise=device_noise)
+    else:
+        x_02 = x_01
+    b = getattr(batch, "n_graphs", None)
+    if stack_views and b is not None:
+        n = positions_01.size(0)
+        x, pos = torch.cat([x_01, x_02]), torch.cat([positions_01, positions_02])
+        bvec = torch.cat([batch.batch, batch.batch + b])
+        if args.model_3d == "schnet":
+            out = model(x, pos, bvec, num_graphs=2 * b)
+        elif args.model_3d == "painn":
+            rei = batch.radius_edge_index
+            out = model(x, pos, torch.cat([rei, rei + n], dim=1), bvec, num_graphs=2 * b)
+        else:
+            raise Exception("3D model {} not included.".format(args.model_3d))
+        repr_01, repr_02 = out[:b], out[b:]
+    elif args.model_3d == "schnet":
+        repr_01 = model(x_01, positions_01, batch.batch, num_graphs=b)
+        repr_02 = model(x_02, positions_02, batch.batch, num_graphs=b)
+    elif args.model_3d == "painn":
+        repr_01 = model(x_01, positions_01, batch.radius_edge_index, batch.batch, num_graphs=b)
+        repr_02 = model(x_02, positions_02, batch.radius_edge_index, batch.batch, num_graphs=b)
+    else:
+        raise Exception("3D model {} not included.".format(args.model_3d))
+    if getattr(args, "normalize", False):
+        repr_01 = F.normalize(repr_01, dim=-1)
+        repr_02 = F.normalize(repr_02, dim=-1)
+    return repr_01, repr_02
+
+
+def do_EBM_NCE(args, batch, model, criterion, mu, sigma, num_neg=1, positions_02=None, device_noise=False,
+               stack_views=True):
+    """pretrain_GeoSSL.py:103-138; ``criterion`` is the reference's ``nn.BCEWithLogitsLoss()`` (:344).
+    Returns ``(loss, acc)`` with ``acc`` a Python float like the reference (one host sync)."""
+    repr_01, repr_02 = _two_view_molecule_repr(args, batch, model, mu, sigma, positions_02, device_noise, stack_views)
+    B = len(repr_01)
+    dev = repr_01.device
+    neg_01 = repr_01.repeat((num_neg, 1))
+    neg_02 = torch.cat([repr_02[cycle_index(B, i + 1).to(dev)] for i in range(num_neg)], dim=0)
+    pred_pos = torch.sum(repr_01 * repr_02, dim=1)
+    pred_neg = torch.sum(neg_01 * neg_02, dim=1)
+    loss_pos = criterion(pred_pos.double(), torch.ones(B, device=dev).double())
+    loss_neg = criterion(pred_neg.double(), torch.zeros(B * num_neg, device=dev).double())
+    SSL_loss = (loss_pos + num_neg * loss_neg) / (1 + num_neg)
+    num_pred = len(pred_pos) + len(pred_neg)
+    SSL_acc = (torch.sum(pred_pos > 0).float() + torch.sum(pred_neg < 0).float()) / num_pred
+    return SSL_loss, SSL_acc.detach().item()
+
+
+def do_InfoNCE(args, batch, model, criterion=None, mu=0.0, sigma=0.3, num_neg=1, positions_02=None,
+               device_noise=False, stack_views=True):
+    """pretrain_GeoSSL.py:141-176 (temperature ``args.T``; the reference's global ``CE_criterion`` is
+    ``nn.CrossEntropyLoss()``, :345).  Returns ``(loss, acc)``."""
+    repr_01, repr_02 = _two_view_molecule_repr(args, batch, model, mu, sigma, positions_02, device_noise, stack_views)
+
+    def cal_loss(X, Y):
+        B = X.size()[0]
+        logits = torch.div(torch.mm(X, Y.transpose(1, 0)), args.T)
+        labels = torch.arange(B, device=logits.device)
+        CL_loss = F.cross_entropy(logits, labels)
+        CL_acc = logits.argmax(dim=1).eq(labels).sum().detach().cpu().item() * 1. / B
+        return CL_loss, CL_acc
+    loss_01, acc_01 = cal_loss(repr_01, repr_02)
+    loss_02, acc_02 = cal_loss(repr_02, repr_01)
+    return (loss_01 + loss_02) / 2, (acc_01 + acc_02) / 2
+
+
+class DistancePredictor(torch.nn.Module):
+    """pretrain_DistancePrediction.py:15-26, same parameters (``predictor.{weight,bias}``) and ``forward``.
+    ``forward_pairs`` is the fused edition of train():72-79: the (P,2H) pair features are never materialised --
+    ``Linear([h_u, h_v])`` splits into two per-atom dot products gathered per pair, and the distances come from
+    the pair-distance kernel."""
+
+    def __init__(self, emb_dim):
+        super().__init__()
+        self.predictor = torch.nn.Linear(emb_dim * 2, 1)
+        self.criterion = torch.nn.L1Loss()
+
+    def forward(self, u_node_repr, v_node_repr, distance_actual):
+        edge_repr = torch.cat([u_node_repr, v_node_repr], dim=1)
+        distance_pred = self.predictor(edge_repr).squeeze()
+        return self.criterion(distance_pred, distance_actual)
+
+    def forward_pairs(self, node_repr, super_edge_index, positions):
+        H = node_repr.size(1)
+        per_atom = node_repr @ self.predictor.weight.view(2, H).t()                  # (N,2): u-part, v-part
+        distance_pred = per_atom[super_edge_index[0], 0] + per_atom[super_edge_index[1], 1] + self.predictor.bias
+        distance_actual = ops.pair_distance(positions, super_edge_index).squeeze(1)
+        return self.criterion(distance_pred, distance_actual)
+
+
+def do_DistancePrediction(args, batch, model, distance_predictor):
+    """The loss of pretrain_DistancePrediction.py::train (:64-79)."""
+    return distance_predictor.forward_pairs(_encode(args, model, batch.x[:, 0], batch.positions, batch),
+                                            batch.super_edge_index, batch.positions)
 
 
 class FlatGradAllReduce:

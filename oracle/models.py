@@ -226,3 +226,55 @@ def ddm_loss(encoder, sd_head1, sd_head2, x, positions, positions_02, batch, sup
     l1 = ncsn_forward(sd_head1, batch, super_edge_index, repr_01, d02, draws1[0], draws1[1], anneal_power)
     l2 = ncsn_forward(sd_head2, batch, super_edge_index, repr_02, d01, draws2[0], draws2[1], anneal_power)
     return (l1 + l2) / 2, (repr_01, repr_02, l1, l2)
+
+
+# ------------------------------------------------------------------------------------------ sibling objectives
+# the objectives that share the two-view encoder pass with do_DDM.
+def cycle_index(num, shift):
+    """examples/util.py:19-22."""
+    arr = torch.arange(num) + shift
+    arr[-shift:] = torch.arange(shift)
+    return arr
+
+
+def info_nce_loss(repr_01, repr_02, T, normalize=False):
+    """do_InfoNCE (pretrain_GeoSSL.py:141-176) on the two (B,H) molecule representations: returns (loss, acc)."""
+    if normalize:
+        repr_01, repr_02 = F.normalize(repr_01, dim=-1), F.normalize(repr_02, dim=-1)
+
+    def cal_loss(X, Y):                                                               # :159-168
+        B = X.size(0)
+        logits = torch.div(torch.mm(X, Y.transpose(1, 0)), T)
+        labels = torch.arange(B, device=logits.device)
+        loss = F.cross_entropy(logits, labels)
+        acc = logits.argmax(dim=1).eq(labels).sum().item() * 1. / B
+        return loss, acc
+    l1, a1 = cal_loss(repr_01, repr_02)
+    l2, a2 = cal_loss(repr_02, repr_01)
+    return (l1 + l2) / 2, (a1 + a2) / 2                                               # :173-176
+
+
+def ebm_nce_loss(repr_01, repr_02, num_neg=1, normalize=False):
+    """do_EBM_NCE (pretrain_GeoSSL.py:103-138) with criterion = BCEWithLogitsLoss (:344), computed in float64."""
+    if normalize:
+        repr_01, repr_02 = F.normalize(repr_01, dim=-1), F.normalize(repr_02, dim=-1)
+    B = len(repr_01)
+    neg_01 = repr_01.repeat((num_neg, 1))                                             # :125
+    neg_02 = torch.cat([repr_02[cycle_index(B, i + 1)] for i in range(num_neg)], dim=0)  # :126
+    pred_pos = torch.sum(repr_01 * repr_02, dim=1)
+    pred_neg = torch.sum(neg_01 * neg_02, dim=1)
+    loss_pos = F.binary_cross_entropy_with_logits(pred_pos.double(), torch.ones(B, dtype=torch.float64, device=pred_pos.device))
+    loss_neg = F.binary_cross_entropy_with_logits(pred_neg.double(), torch.zeros(B * num_neg, dtype=torch.float64, device=pred_pos.device))
+    loss = (loss_pos + num_neg * loss_neg) / (1 + num_neg)                            # :134
+    acc = (torch.sum(pred_pos > 0).float() + torch.sum(pred_neg < 0).float()) / (len(pred_pos) + len(pred_neg))
+    return loss, acc.item()
+
+
+def distance_prediction_loss(sd, node_repr, positions, super_edge_index):
+    """DistancePredictor.forward + the pair block of train() (pretrain_DistancePrediction.py:15-26,72-79);
+    ``sd`` holds ``predictor.weight`` (1,2H) and ``predictor.bias`` (1,)."""
+    u = torch.index_select(node_repr, 0, super_edge_index[0])
+    v = torch.index_select(node_repr, 0, super_edge_index[1])
+    d = torch.sqrt(torch.sum((positions[super_edge_index[0]] - positions[super_edge_index[1]]) ** 2, dim=1))
+    pred = F.linear(torch.cat([u, v], dim=1), sd["predictor.weight"], sd["predictor.bias"]).squeeze()
+    return F.l1_loss(pred, d)

@@ -194,6 +194,81 @@ def md17_case(name, *, seed, hidden, filters, gaussians, layers, cutoff, num_gra
             "grad": grads_of(model), "gradlin": grads_of(lin)})
 
 
+def ssl_case(name, *, seed, hidden, filters, gaussians, layers, cutoff, num_graphs, atoms, atoms_max=None,
+             T=0.1, num_neg=1, sigma=0.3):
+    """The sibling objectives on the reference SchNet: do_InfoNCE (pretrain_GeoSSL.py:141-176), do_EBM_NCE (:103-138,
+    criterion = BCEWithLogitsLoss :344) and the DistancePredictor step (pretrain_DistancePrediction.py:15-26,64-79).
+    Each objective's loss is back-propagated separately into the same encoder."""
+    torch.manual_seed(seed)
+    model = SchNet(hidden_channels=hidden, num_filters=filters, num_interactions=layers,
+                   num_gaussians=gaussians, cutoff=cutoff, node_class=9, readout="mean")
+    predictor = torch.nn.Linear(hidden * 2, 1)                              # DistancePredictor.predictor, :18
+    b = synthetic_batch(num_graphs, atoms, atoms_max, seed=seed + 1)
+    torch.manual_seed(seed + 3)
+    pos_noise = torch.normal(0.0, sigma, size=b.positions.size())          # perturb(), :72
+    x_01 = b.x[:, 0]
+    positions_02 = b.positions + pos_noise
+    out, grads = {}, {}
+
+    def reprs():
+        return model(x_01, b.positions, b.batch), model(x_01, positions_02, b.batch)
+
+    # ---- InfoNCE, :159-176
+    r1, r2 = reprs()
+    CE = torch.nn.CrossEntropyLoss()
+
+    def cal_loss(X, Y):
+        B = X.size()[0]
+        logits = torch.div(torch.mm(X, Y.transpose(1, 0)), T)
+        labels = torch.arange(B).long()
+        return CE(logits, labels), logits.argmax(dim=1).eq(labels).sum().item() * 1. / B
+    l01, a01 = cal_loss(r1, r2)
+    l02, a02 = cal_loss(r2, r1)
+    loss = (l01 + l02) / 2
+    model.zero_grad(); loss.backward()
+    out.update(repr_01=r1, repr_02=r2, infonce_loss=loss, infonce_acc=torch.tensor((a01 + a02) / 2))
+    grads.update({"infonce/" + k: v.clone() for k, v in grads_of(model).items()})
+
+    # ---- EBM-NCE, :122-138
+    r1, r2 = reprs()
+    B = len(r1)
+    cyc = lambda num, shift: torch.cat([torch.arange(shift, num), torch.arange(shift)])   # == util.py:19-22
+    neg_01 = r1.repeat((num_neg, 1))
+    neg_02 = torch.cat([r2[cyc(B, i + 1)] for i in range(num_neg)], dim=0)
+    pred_pos = torch.sum(r1 * r2, dim=1)
+    pred_neg = torch.sum(neg_01 * neg_02, dim=1)
+    BCE = torch.nn.BCEWithLogitsLoss()
+    loss_pos = BCE(pred_pos.double(), torch.ones(B).double())
+    loss_neg = BCE(pred_neg.double(), torch.zeros(B * num_neg).double())
+    loss = (loss_pos + num_neg * loss_neg) / (1 + num_neg)
+    acc = (torch.sum(pred_pos > 0).float() + torch.sum(pred_neg < 0).float()) / (len(pred_pos) + len(pred_neg))
+    model.zero_grad(); loss.backward()
+    out.update(ebm_loss=loss, ebm_acc=acc)
+    grads.update({"ebm/" + k: v.clone() for k, v in grads_of(model).items()})
+
+    # ---- distance prediction, pretrain_DistancePrediction.py:64-79
+    _, node_repr = model(x_01, b.positions, b.batch, return_latent=True)
+    sei = b.super_edge_index
+    u_node_repr = torch.index_select(node_repr, dim=0, index=sei[0])
+    v_node_repr = torch.index_select(node_repr, dim=0, index=sei[1])
+    u_pos = torch.index_select(b.positions, dim=0, index=sei[0])
+    v_pos = torch.index_select(b.positions, dim=0, index=sei[1])
+    distance_actual = torch.sqrt(torch.sum((u_pos - v_pos) ** 2, dim=1))
+    distance_pred = predictor(torch.cat([u_node_repr, v_node_repr], dim=1)).squeeze()
+    loss = torch.nn.L1Loss()(distance_pred, distance_actual)
+    model.zero_grad(); predictor.zero_grad(); loss.backward()
+    out.update(distance_loss=loss)
+    grads.update({"distance/" + k: v.clone() for k, v in grads_of(model).items()})
+    grads.update({"distance_predictor/" + k: v.clone() for k, v in grads_of(predictor).items()})
+
+    cfg = dict(kind="ssl", hidden=hidden, filters=filters, gaussians=gaussians, layers=layers, cutoff=cutoff,
+               readout="mean", T=T, num_neg=num_neg, sigma=sigma, seed=seed)
+    save(name, cfg,
+         **{"in": dict(x=b.x, pos=b.positions, batch=b.batch, super_edge_index=sei, pos_noise=pos_noise),
+            "sd": dict(model.state_dict()), "sdpred": {"predictor." + k: v for k, v in predictor.state_dict().items()},
+            "out": out, "grad": grads})
+
+
 if __name__ == "__main__":
     schnet_case("schnet_small", seed=11, hidden=32, filters=32, gaussians=20, layers=2, cutoff=10.0,
                 readout="mean", num_graphs=5, atoms=4, atoms_max=12)
@@ -215,3 +290,5 @@ if __name__ == "__main__":
              layers=2, rbf=20, cutoff=5.0)
     md17_case("md17_small", seed=51, hidden=32, filters=32, gaussians=20, layers=2, cutoff=10.0,
               num_graphs=3, atoms=9)
+    ssl_case("ssl_schnet_small", seed=61, hidden=32, filters=32, gaussians=20, layers=2, cutoff=10.0,
+             num_graphs=7, atoms=4, atoms_max=12)

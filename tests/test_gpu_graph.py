@@ -120,3 +120,33 @@ def test_device_batch_assembly_matches_host(option):
     assert torch.equal(b.super_edge_index.cpu(), super_edges_host(counts, option))
     assert torch.equal(b.batch.cpu(), torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts)))
     assert b.num_graphs == len(counts) and b.super_edge_index.dtype == torch.int64
+
+
+@pytest.mark.parametrize("option", ["combination", "permutation"])
+def test_device_pair_subsampling(option):
+    """--distance_sample_ratio < 1 on the device: int(M * ratio) distinct intra-molecule pairs per molecule; with the
+    host draw injected the columns equal the host restatement (= the reference extractor, tests/test_host_logic.py)."""
+    import numpy as np
+    from geossl_b200.data import assemble_batch_device, pair_count, sample_pairs_host, sampled_pair_count, super_edges_host
+    counts, ratio = [1, 2, 30, 5, 1, 17, 60, 3], 0.3
+    n = sum(counts)
+    z, pos = torch.randint(0, 9, (n,)), torch.rand(n, 3)
+    full = super_edges_host(counts, option)
+    kept = sampled_pair_count(counts, option, ratio)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    b = assemble_batch_device(counts, z, pos, option=option, device=DEV, ratio=ratio, generator=gen)
+    sei = b.super_edge_index.cpu()
+    assert sei.shape == (2, int(kept.sum()))
+    gid = b.batch.cpu()[sei[0]]
+    assert torch.equal(gid, b.batch.cpu()[sei[1]])                                   # intra-molecule
+    assert torch.equal(torch.bincount(gid, minlength=len(counts)), torch.from_numpy(kept))
+    code = lambda e: e[0] * n + e[1]
+    assert torch.unique(code(sei)).numel() == sei.shape[1]                           # without replacement
+    assert bool(torch.isin(code(sei), code(full)).all())                             # valid pairs of the option
+    gen2 = torch.Generator(device=DEV).manual_seed(4)
+    b2 = assemble_batch_device(counts, z, pos, option=option, device=DEV, ratio=ratio, generator=gen2)
+    assert not torch.equal(b2.super_edge_index, b.super_edge_index)
+    np.random.seed(11)
+    sel = sample_pairs_host(counts, option, ratio)
+    b3 = assemble_batch_device(counts, z, pos, option=option, device=DEV, ratio=ratio, selection=sel)
+    assert torch.equal(b3.super_edge_index.cpu(), super_edges_host(counts, option, ratio=ratio, selection=sel))

@@ -72,6 +72,31 @@ def test_super_edges_match_itertools():
         assert sei.shape[1] == int(pair_count(counts, option).sum())
 
 
+def test_pair_subsampling_consumes_numpy_stream_like_the_extractor():
+    """--distance_sample_ratio < 1 (dataloaders_AtomTuple.py:15-37): literal replay of AtomTupleExtractor.__call__ per
+    molecule + the collate offset (:60-66) with the same np.random seed must give the same columns in the same order."""
+    from geossl_b200.data import sample_pairs_host, sampled_pair_count
+    counts, ratio = [1, 2, 5, 0, 7, 3, 12], 0.4
+    for option, gen in (("combination", itertools.combinations), ("permutation", itertools.permutations)):
+        np.random.seed(7)
+        ref, off = [], 0
+        for n in counts:
+            if n >= 2:
+                sei = np.array(list(gen(np.arange(n), 2))).T
+                M = sei.shape[1]
+                sampled = np.random.choice(M, int(M * ratio), replace=False)
+                ref.append(sei[:, sampled] + off)
+            off += n
+        ref = torch.from_numpy(np.concatenate(ref, axis=1))
+        np.random.seed(7)
+        got = super_edges_host(counts, option, ratio=ratio)
+        assert torch.equal(got, ref)
+        assert got.shape[1] == int(sampled_pair_count(counts, option, ratio).sum())
+        np.random.seed(7)
+        sel = sample_pairs_host(counts, option, ratio)
+        assert torch.equal(super_edges_host(counts, option, ratio=ratio, selection=sel), ref)
+
+
 def test_synthetic_batch_contract():
     b = synthetic_batch(8, 10, 20, seed=3)
     n = b.positions.shape[0]

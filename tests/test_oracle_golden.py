@@ -148,3 +148,43 @@ def test_head_gradient_is_discontinuous_at_1e_6():
         assert abs(l1 - l0) / abs(l0) < 2e-6
         worst = max(worst, max(rel_err(g1[k], g0[k]) for k in g0))
     assert 1e-4 < worst < 2e-3
+
+
+def test_sibling_objectives_oracle():
+    """InfoNCE / EBM-NCE / distance prediction restated vs the reference-driven fixture."""
+    g = Golden("ssl_schnet_small")
+    c, i = g.cfg, g["in"]
+    z, pos2 = i["x"][:, 0].contiguous(), i["pos"] + i["pos_noise"]
+
+    def grads(prefix):
+        return {k[len(prefix):]: v for k, v in g["grad"].items() if k.startswith(prefix)}
+
+    def enc(sd, p, latent=False):
+        out, h = O.schnet_forward(sd, z, p, i["batch"], cutoff=c["cutoff"], readout="mean")
+        return h if latent else out
+
+    sd = leaf_sd(g.sd())
+    r1, r2 = enc(sd, i["pos"]), enc(sd, pos2)
+    assert rel_err(r1, g["out"]["repr_01"]) <= TOL and rel_err(r2, g["out"]["repr_02"]) <= TOL
+    loss, acc = O.info_nce_loss(r1, r2, c["T"])
+    assert rel_err(loss, g["out"]["infonce_loss"]) <= TOL and abs(acc - float(g["out"]["infonce_acc"])) < 1e-6
+    loss.backward()
+    check_grads(sd, grads("infonce/"))
+
+    sd = leaf_sd(g.sd())
+    loss, acc = O.ebm_nce_loss(enc(sd, i["pos"]), enc(sd, pos2), c["num_neg"])
+    assert loss.dtype == torch.float64 and rel_err(loss, g["out"]["ebm_loss"]) <= TOL
+    assert abs(acc - float(g["out"]["ebm_acc"])) < 1e-7
+    loss.backward()
+    check_grads(sd, grads("ebm/"))
+
+    sd, sdp = leaf_sd(g.sd()), leaf_sd(g.sd("sdpred"))
+    loss = O.distance_prediction_loss(sdp, enc(sd, i["pos"], latent=True), i["pos"], i["super_edge_index"])
+    assert rel_err(loss, g["out"]["distance_loss"]) <= TOL
+    loss.backward()
+    check_grads(sd, grads("distance/"))
+    check_grads(sdp, {"predictor." + k: v for k, v in grads("distance_predictor/").items()})
+
+
+def test_cycle_index_matches_reference_definition():
+    assert O.cycle_index(5, 2).tolist() == [2, 3, 4, 0, 1] and O.cycle_index(4, 1).tolist() == [1, 2, 3, 0]
