@@ -18,8 +18,8 @@ __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w
 // LPR lanes cover one F-wide row with float4 each; a warp walks EPW = 32/LPR edges per step.
 template <int F, int UNROLL>
 __global__ void __launch_bounds__(256)
-cfconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ filt, const int32_t* __restrict__ rowptr,
-                  const int32_t* __restrict__ src, int n_atoms, float* __restrict__ out) {
+cfconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ filt, const int32_t* __restrict__ filt_row,
+                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, int n_atoms, float* __restrict__ out) {
     constexpr int LPR = F / 4, EPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
     const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -34,7 +34,8 @@ cfconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ filt, c
             const int e = e0 + u * EPW;
             if (e < end) {
                 const int j = __ldg(src + e);
-                w[u] = ld_stream4(filt + (int64_t)e * F + f);
+                const int r = filt_row ? __ldg(filt_row + e) : e;          // shared filter row of the undirected pair
+                w[u] = ld_stream4(filt + (int64_t)r * F + f);
                 xv[u] = ldg4(x + (int64_t)j * F + f);
             } else {
                 w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -56,7 +57,8 @@ cfconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ filt, c
 
 template <int F, int UNROLL>
 __global__ void __launch_bounds__(256)
-cfconv_bwd_x_kernel(const float* __restrict__ filt, const float* __restrict__ g, const int32_t* __restrict__ t_rowptr,
+cfconv_bwd_x_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ g,
+                    const int32_t* __restrict__ t_rowptr,
                     const int32_t* __restrict__ t_eid, const int32_t* __restrict__ t_tgt, int n_atoms,
                     float* __restrict__ dx) {
     constexpr int LPR = F / 4, EPW = 32 / LPR;
@@ -73,7 +75,8 @@ cfconv_bwd_x_kernel(const float* __restrict__ filt, const float* __restrict__ g,
             const int k = k0 + u * EPW;
             if (k < end) {
                 const int e = __ldg(t_eid + k), i = __ldg(t_tgt + k);
-                w[u] = ld_stream4(filt + (int64_t)e * F + f);
+                const int r = filt_row ? __ldg(filt_row + e) : e;
+                w[u] = ld_stream4(filt + (int64_t)r * F + f);
                 gv[u] = ldg4(g + (int64_t)i * F + f);
             } else {
                 w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -112,17 +115,19 @@ cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, co
 }
 
 template <int F>
-int launch_fwd(const float* x, const float* filt, const int32_t* rowptr, const int32_t* src, int64_t n, float* out, cudaStream_t st) {
+int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src, int64_t n,
+               float* out, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    cfconv_fwd_kernel<F, 4><<<blocks, threads, 0, st>>>(x, filt, rowptr, src, (int)n, out);
+    cfconv_fwd_kernel<F, 4><<<blocks, threads, 0, st>>>(x, filt, filt_row, rowptr, src, (int)n, out);
     return 0;
 }
 template <int F>
-int launch_bwd_x(const float* filt, const float* g, const int32_t* tr, const int32_t* te, const int32_t* tt, int64_t n, float* dx, cudaStream_t st) {
+int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, const int32_t* tr, const int32_t* te, const int32_t* tt,
+                 int64_t n, float* dx, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    cfconv_bwd_x_kernel<F, 4><<<blocks, threads, 0, st>>>(filt, g, tr, te, tt, (int)n, dx);
+    cfconv_bwd_x_kernel<F, 4><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx);
     return 0;
 }
 template <int F>
@@ -147,20 +152,20 @@ using namespace geossl;
 
 extern "C" {
 
-int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* rowptr, const int32_t* src,
+int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src,
                       int64_t n_atoms, int F, float* out, void* stream) {
     if (n_atoms == 0) return 0;
     GEOSSL_REQUIRE(x && filt && rowptr && src && out && n_atoms > 0, "null pointer");
-    DISPATCH_F(F, launch_fwd<kF>(x, filt, rowptr, src, n_atoms, out, as_stream(stream)));
+    DISPATCH_F(F, launch_fwd<kF>(x, filt, filt_row, rowptr, src, n_atoms, out, as_stream(stream)));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
 
-int geossl_cfconv_bwd_x(const float* filt, const float* grad_out, const int32_t* t_rowptr, const int32_t* t_eid,
+int geossl_cfconv_bwd_x(const float* filt, const int32_t* filt_row, const float* grad_out, const int32_t* t_rowptr, const int32_t* t_eid,
                         const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream) {
     if (n_atoms == 0) return 0;
     GEOSSL_REQUIRE(filt && grad_out && t_rowptr && t_eid && t_tgt && grad_x && n_atoms > 0, "null pointer");
-    DISPATCH_F(F, launch_bwd_x<kF>(filt, grad_out, t_rowptr, t_eid, t_tgt, n_atoms, grad_x, as_stream(stream)));
+    DISPATCH_F(F, launch_bwd_x<kF>(filt, filt_row, grad_out, t_rowptr, t_eid, t_tgt, n_atoms, grad_x, as_stream(stream)));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -65,12 +65,17 @@ __device__ __forceinline__ void store_split_bf16(uint8_t* hi_block, uint8_t* lo_
     *reinterpret_cast<__nv_bfloat16*>(lo_block + off) = l;
 }
 
+// PAIRS: the tile rows are undirected pairs (geossl_pair_index): edge_dist / n_edges_dev describe the pairs, and
+// dU_u = C(d_u) * (x[s] * g[t] + x[t] * g[s]) sums both directions of pair u = (s -> t) (second term only if the reverse
+// edge exists, pair_e2[u] >= 0).  Everything downstream of dU is linear in it, so the parameter gradients are unchanged.
+template <bool PAIRS>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restrict__ n_edges_dev, int64_t capacity,
                      const float* __restrict__ offset, float coeff, float cutoff, int G,
                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                      const float* __restrict__ x, const float* __restrict__ grad_out,
-                     const int32_t* __restrict__ src, const int32_t* __restrict__ edge_tgt, float* __restrict__ workspace) {
+                     const int32_t* __restrict__ src, const int32_t* __restrict__ edge_tgt,
+                     const int32_t* __restrict__ pair_e1, const int32_t* __restrict__ pair_e2, float* __restrict__ workspace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     using L = BwdLayout;
@@ -173,6 +178,38 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             const int b = i & 1;
             uint8_t* hi = smem + L::DU + b * 4 * kBlkT + (cg >> 3) * kBlkT;
             uint8_t* lo = hi + 2 * kBlkT;
+            if constexpr (PAIRS) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int row = rr * 16 + ro;
+                    const int64_t u = e_base + row;
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 xs0 = z4, xs1 = z4, gt0 = z4, gt1 = z4, xt0 = z4, xt1 = z4, gs0 = z4, gs1 = z4;
+                    float cs = 0.f;
+                    if (u < n_edges) {
+                        const int e1 = __ldg(pair_e1 + u), e2 = __ldg(pair_e2 + u);
+                        const int64_t sa = (int64_t)__ldg(src + e1) * 128 + cg * 8, ta = (int64_t)__ldg(edge_tgt + e1) * 128 + cg * 8;
+                        xs0 = ldg4(x + sa); xs1 = ldg4(x + sa + 4);
+                        gt0 = ldg4(grad_out + ta); gt1 = ldg4(grad_out + ta + 4);
+                        if (e2 >= 0) {
+                            xt0 = ldg4(x + ta); xt1 = ldg4(x + ta + 4);
+                            gs0 = ldg4(grad_out + sa); gs1 = ldg4(grad_out + sa + 4);
+                        }
+                        cs = 0.5f * (__cosf(__ldg(edge_dist + u) * pi_over_rc) + 1.0f);
+                    }
+                    if (rr == 0) {
+                        mbar_wait(bar(DU_FREE_ + b), ((i >> 1) & 1) ^ 1);   // gathers of the first row are already in flight
+                        if (warp == kBwdDuWarp0) trace_b(i, 2);
+                    }
+                    float v[8] = {fmaf(xs0.x, gt0.x, xt0.x * gs0.x) * cs, fmaf(xs0.y, gt0.y, xt0.y * gs0.y) * cs,
+                                  fmaf(xs0.z, gt0.z, xt0.z * gs0.z) * cs, fmaf(xs0.w, gt0.w, xt0.w * gs0.w) * cs,
+                                  fmaf(xs1.x, gt1.x, xt1.x * gs1.x) * cs, fmaf(xs1.y, gt1.y, xt1.y * gs1.y) * cs,
+                                  fmaf(xs1.z, gt1.z, xt1.z * gs1.z) * cs, fmaf(xs1.w, gt1.w, xt1.w * gs1.w) * cs};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+                    store_chunk8<kBwdFP16>(hi, lo, row, (cg & 7) * 8, v);
+                }
+            } else {
 #pragma unroll
             for (int sb = 0; sb < 2; ++sb) {
                 float4 xv[2][2], gv[2][2];
@@ -206,6 +243,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                     for (int k = 0; k < 8; ++k) acc[k] += v[k];
                     store_chunk8<kBwdFP16>(hi, lo, row, (cg & 7) * 8, v);
                 }
+            }
             }
             fence_proxy_async();
             warp_arrive(bar(DU_FULL_ + b));
@@ -441,20 +479,26 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
                          const float* offset, float coeff, float cutoff, int G, int F,
                          const float* w1, const float* b1, const float* w2,
                          const float* x, const float* grad_out, const int32_t* src, const int32_t* edge_tgt,
+                         const int32_t* pair_e1, const int32_t* pair_e2,
                          float* workspace, float* gw1, float* gb1, float* gw2, float* gb2, void* stream) {
     GEOSSL_REQUIRE(edge_dist && n_edges_dev && offset && w1 && b1 && w2 && x && grad_out && src && edge_tgt && workspace &&
                    gw1 && gb1 && gw2 && gb2, "null pointer");
     GEOSSL_REQUIRE(F == 128, "the tensor-core filter kernel is built for num_filters = 128");
     GEOSSL_REQUIRE(G >= 1 && G <= 63, "num_gaussians must be in [1,63] (column 63 of the rbf tile carries the bias sum)");
+    GEOSSL_REQUIRE((pair_e1 == nullptr) == (pair_e2 == nullptr), "pair_e1 and pair_e2 go together");
     const size_t smem = tc::BwdLayout::kBytes + 1024;
     static bool configured = false;
     if (!configured) {
-        GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    tc::filter_bwd_tc_kernel<<<kNumSM, tc::kBwdThreads, smem, as_stream(stream)>>>(edge_dist, n_edges_dev, capacity, offset, coeff,
-                                                                                  cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt,
-                                                                                  workspace);
+    if (pair_e1)
+        tc::filter_bwd_tc_kernel<true><<<kNumSM, tc::kBwdThreads, smem, as_stream(stream)>>>(
+            edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt, pair_e1, pair_e2, workspace);
+    else
+        tc::filter_bwd_tc_kernel<false><<<kNumSM, tc::kBwdThreads, smem, as_stream(stream)>>>(
+            edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt, nullptr, nullptr, workspace);
     GEOSSL_LAUNCH_CHECK();
     tc::filter_bwd_tc_reduce_kernel<<<(tc::Part::kFloats + 255) / 256, 256, 0, as_stream(stream)>>>(workspace, kNumSM, G, gw1, gb1,
                                                                                                    gw2, gb2);

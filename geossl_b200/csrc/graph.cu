@@ -178,6 +178,51 @@ transpose_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     if (MODE == 0 && lane == 0) t_deg[j] = kept;
 }
 
+// Undirected-pair index of a destination-sorted CSR with ascending sources per row.
+// The interaction filter W_e depends on the edge only through its length d_e (schnet.py:186-187), and
+// |pos_j - pos_i| == |pos_i - pos_j| bit for bit, so the two directions of a pair share ONE filter row.  A pair's
+// canonical edge is the direction with source < target; an edge whose reverse was cut by the neighbour limit (or is
+// absent) is its own pair ("orphan").  Row t's pairs are its canonical edges in row order: first the edges with
+// source < t (a prefix of the row, sources ascend), then the orphans with source > t.
+// MODE 0: pair_deg[t]; MODE 1: pair_of_edge / pair_e1 / pair_e2 / pair_dist at pair_rowptr[t] + rank.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+pair_index_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const float* __restrict__ edge_dist,
+                  int n_atoms, int32_t* __restrict__ pair_deg, const int32_t* __restrict__ pair_rowptr,
+                  int32_t* __restrict__ pair_of_edge, int32_t* __restrict__ pair_e1, int32_t* __restrict__ pair_e2,
+                  float* __restrict__ pair_dist) {
+    const int lane = threadIdx.x & 31;
+    const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (t >= n_atoms) return;
+    const int lo = __ldg(rowptr + t), hi = __ldg(rowptr + t + 1);
+    const int base = (MODE == 1) ? pair_rowptr[t] : 0;
+    int kept = 0;
+    for (int e0 = lo; e0 < hi; e0 += 32) {
+        const int e = e0 + lane;
+        int s = -1, rev = -1;
+        if (e < hi) {
+            s = __ldg(src + e);
+            rev = find_in_row(src, __ldg(rowptr + s), __ldg(rowptr + s + 1), t);      // edge t -> s, or -1
+        }
+        const bool canon = e < hi && (s < t || rev < 0);
+        const unsigned mask = __ballot_sync(0xffffffffu, canon);
+        if (MODE == 1 && e < hi) {
+            if (canon) {
+                const int u = base + kept + __popc(mask & ((1u << lane) - 1u));
+                pair_of_edge[e] = u;
+                pair_e1[u] = e;
+                pair_e2[u] = (s < t) ? rev : -1;
+                pair_dist[u] = edge_dist[e];
+            } else {
+                // reverse edge (t -> s) sits in row s among the prefix of sources < s, every one of which is canonical
+                pair_of_edge[e] = pair_rowptr[s] + (rev - __ldg(rowptr + s));
+            }
+        }
+        kept += __popc(mask);
+    }
+    if (MODE == 0 && lane == 0) pair_deg[t] = kept;
+}
+
 // Batch assembly on the device (replaces AtomTupleExtractor + the collate offsets of BatchAtomTuple.from_data_list,
 // Geom3D/dataloaders/dataloaders_AtomTuple.py:15-37,45-73, for ratio == 1): one thread per (graph, first atom i) writes the
 // pairs (i, j) of its row in itertools order -- combination: j > i; permutation: j != i -- at the graph's pair offset.
@@ -294,6 +339,29 @@ int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(t_deg, (int)n_atoms, t_rowptr);
     GEOSSL_LAUNCH_CHECK();
     transpose_kernel<1><<<blocks, threads, 0, st>>>(rowptr, src, batch, graph_ptr, (int)n_atoms, nullptr, t_rowptr, t_eid, t_tgt);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_pair_index(const int32_t* rowptr, const int32_t* src, const float* edge_dist, int64_t n_atoms, int32_t* scratch,
+                      int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2, float* pair_dist,
+                      void* stream) {
+    GEOSSL_REQUIRE(pair_rowptr && scratch, "null pair_rowptr/scratch");
+    cudaStream_t st = as_stream(stream);
+    if (n_atoms == 0) {
+        GEOSSL_CUDA(cudaMemsetAsync(pair_rowptr, 0, sizeof(int32_t), st));
+        return 0;
+    }
+    GEOSSL_REQUIRE(rowptr && src && edge_dist && pair_of_edge && pair_e1 && pair_e2 && pair_dist, "null input");
+    const int threads = 256;
+    const int blocks = (int)((n_atoms * 32 + threads - 1) / threads);
+    pair_index_kernel<0><<<blocks, threads, 0, st>>>(rowptr, src, edge_dist, (int)n_atoms, scratch, nullptr, nullptr, nullptr,
+                                                     nullptr, nullptr);
+    GEOSSL_LAUNCH_CHECK();
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(scratch, (int)n_atoms, pair_rowptr);
+    GEOSSL_LAUNCH_CHECK();
+    pair_index_kernel<1><<<blocks, threads, 0, st>>>(rowptr, src, edge_dist, (int)n_atoms, nullptr, pair_rowptr, pair_of_edge,
+                                                     pair_e1, pair_e2, pair_dist);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

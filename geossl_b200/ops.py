@@ -91,6 +91,7 @@ class RadiusCSR:
         self.rowptr, self.src, self.tgt, self.dist = rowptr, src, tgt, dist
         self.batch, self.graph_ptr = batch, graph_ptr
         self.t_rowptr = self.t_eid = self.t_tgt = None
+        self.pair_rowptr = self.pair_of_edge = self.pair_e1 = self.pair_e2 = self.pair_dist = None
         self._n_edges = None
         self._exact = None
 
@@ -125,6 +126,26 @@ class RadiusCSR:
             check(_lib.load().geossl_csr_transpose(_p(self.rowptr), _p(self.src), _p(self.batch), _p(self.graph_ptr), n,
                                                    _p(scratch), _p(self.t_rowptr), _p(self.t_eid), _p(self.t_tgt),
                                                    _stream()), "csr_transpose")
+        return self
+
+    @property
+    def n_pairs_dev(self):
+        return self.pair_rowptr[self.n_atoms:]
+
+    def ensure_pairs(self):
+        """Undirected-pair index (geossl_pair_index): both directions of a pair share one filter row."""
+        if self.pair_rowptr is None:
+            dev = self.rowptr.device
+            n = self.n_atoms
+            self.pair_rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            self.pair_of_edge = torch.empty(self.capacity, dtype=torch.int32, device=dev)
+            self.pair_e1 = torch.empty(self.capacity, dtype=torch.int32, device=dev)
+            self.pair_e2 = torch.empty(self.capacity, dtype=torch.int32, device=dev)
+            self.pair_dist = torch.empty(self.capacity, dtype=torch.float32, device=dev)
+            scratch = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            check(_lib.load().geossl_pair_index(_p(self.rowptr), _p(self.src), _p(self.dist), n, _p(scratch), _p(self.pair_rowptr),
+                                                _p(self.pair_of_edge), _p(self.pair_e1), _p(self.pair_e2), _p(self.pair_dist),
+                                                _stream()), "pair_index")
         return self
 
     def exact(self):
@@ -219,18 +240,19 @@ def csr_from_edge_index(edge_index, n_atoms, batch, graph_ptr=None, num_graphs=N
 # =====================================================================================================
 # cfconv primitives (closed under differentiation: A, A^T and the edge product)
 # =====================================================================================================
-def _cfconv_fwd(x, filt, g):
+def _cfconv_fwd(x, filt, g, filt_row=None):
     out = torch.empty((g.n_atoms, x.size(1)), dtype=torch.float32, device=x.device)
-    _timed("cfconv_fwd", lambda: _lib.load().geossl_cfconv_fwd(_p(x), _p(filt), _p(g.rowptr), _p(g.src), g.n_atoms, x.size(1),
-                                                               _p(out), _stream()))
+    _timed("cfconv_fwd", lambda: _lib.load().geossl_cfconv_fwd(_p(x), _p(filt), _p(filt_row), _p(g.rowptr), _p(g.src), g.n_atoms,
+                                                               x.size(1), _p(out), _stream()))
     return out
 
 
-def _cfconv_bwd_x(filt, grad_out, g):
+def _cfconv_bwd_x(filt, grad_out, g, filt_row=None):
     g.ensure_transpose()
     dx = torch.empty((g.n_atoms, grad_out.size(1)), dtype=torch.float32, device=grad_out.device)
-    _timed("cfconv_bwd_x", lambda: _lib.load().geossl_cfconv_bwd_x(_p(filt), _p(grad_out), _p(g.t_rowptr), _p(g.t_eid),
-                                                                   _p(g.t_tgt), g.n_atoms, grad_out.size(1), _p(dx), _stream()))
+    _timed("cfconv_bwd_x", lambda: _lib.load().geossl_cfconv_bwd_x(_p(filt), _p(filt_row), _p(grad_out), _p(g.t_rowptr),
+                                                                   _p(g.t_eid), _p(g.t_tgt), g.n_atoms, grad_out.size(1), _p(dx),
+                                                                   _stream()))
     return dx
 
 
@@ -302,19 +324,26 @@ class CFConvEdgeProduct(torch.autograd.Function):
 # operands split into two fp16 / bf16 parts (three MMAs per product, fp32 accumulate; needs F = 128),
 # "simt" = fp32 CUDA cores (any supported width; also what narrower models use).
 FILTER_MODE = "tc_fp16"
+# The filter of an edge depends only on its length, so the two directions of an atom pair share one filter row
+# (geossl_pair_index): the tensor-core filter kernels then run over U <= E undirected pairs -- E/2 when no neighbour row
+# is truncated.  Forward results are bit-identical to the per-edge form; parameter gradients differ by summation order.
+# Applies to the tensor-core modes; "simt" stays per edge (the exact fp32 cross-check).
+SHARE_PAIR_FILTERS = True
 
 
-def filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2, mode=None):
-    """W_e (capacity,F) from the edge distances held by ``graph`` (fused rbf + filter MLP + cutoff)."""
+def filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2, mode=None, pairs=False):
+    """W (capacity,F) from the edge distances held by ``graph`` (fused rbf + filter MLP + cutoff); one row per directed
+    edge, or per undirected pair with ``pairs=True`` (index rows through ``graph.pair_of_edge``)."""
     F_, G = w1.size(0), w1.size(1)
     filt = torch.empty((graph.capacity, F_), dtype=torch.float32, device=w1.device)
     mode = mode or FILTER_MODE
+    dist, count = (graph.ensure_pairs().pair_dist, graph.n_pairs_dev) if pairs else (graph.dist, graph.n_edges_dev)
     if mode != "simt" and F_ == 128:
         _timed("filter_fwd", lambda: _lib.load().geossl_filter_fwd_tc(
-            _p(graph.dist), _p(graph.n_edges_dev), graph.capacity, _p(offset), float(coeff), float(cutoff), G, F_, _p(w1),
+            _p(dist), _p(count), graph.capacity, _p(offset), float(coeff), float(cutoff), G, F_, _p(w1),
             _p(b1), _p(w2), _p(b2), _p(filt), 1 if mode == "tc_bf16" else 0, _stream()))
         return filt
-    _timed("filter_fwd", lambda: _lib.load().geossl_filter_fwd(_p(graph.dist), _p(graph.n_edges_dev), graph.capacity, _p(offset),
+    _timed("filter_fwd", lambda: _lib.load().geossl_filter_fwd(_p(dist), _p(count), graph.capacity, _p(offset),
                                                                float(coeff), float(cutoff), G, F_, _p(w1), _p(b1), _p(w2), _p(b2),
                                                                _p(filt), _stream()))
     return filt
@@ -333,9 +362,11 @@ class CFConvLayer(torch.autograd.Function):
         x = _req(x, torch.float32, "x", 2)
         w1, b1, w2, b2 = (_req(t, torch.float32, n) for t, n in ((w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")))
         offset = _req(offset, torch.float32, "offset", 1)
-        filt = filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2)
-        out = _cfconv_fwd(x, filt, graph)
-        ctx.graph, ctx.coeff, ctx.cutoff, ctx.mode = graph, coeff, cutoff, FILTER_MODE
+        pairs = (SHARE_PAIR_FILTERS and FILTER_MODE != "simt" and w1.size(0) == 128 and w1.size(1) <= 63
+                 and graph.dist is not None)
+        filt = filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2, pairs=pairs)
+        out = _cfconv_fwd(x, filt, graph, graph.pair_of_edge if pairs else None)
+        ctx.graph, ctx.coeff, ctx.cutoff, ctx.mode, ctx.pairs = graph, coeff, cutoff, FILTER_MODE, pairs
         ctx.save_for_backward(x, filt, w1, b1, w2, b2, offset)
         return out
 
@@ -347,13 +378,16 @@ class CFConvLayer(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         lib = _lib.load()
         F_, G = w1.size(0), w1.size(1)
-        gx = _cfconv_bwd_x(filt, grad_out, g) if ctx.needs_input_grad[0] else None
+        gx = _cfconv_bwd_x(filt, grad_out, g, g.pair_of_edge if ctx.pairs else None) if ctx.needs_input_grad[0] else None
         gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
         if ctx.mode != "simt" and F_ == 128 and G <= 63:
             ws = torch.empty(lib.geossl_filter_bwd_tc_workspace(), dtype=torch.float32, device=x.device)
+            dist, count = (g.pair_dist, g.n_pairs_dev) if ctx.pairs else (g.dist, g.n_edges_dev)
+            e1, e2 = (g.pair_e1, g.pair_e2) if ctx.pairs else (None, None)
             _timed("filter_bwd", lambda: lib.geossl_filter_bwd_tc(
-                _p(g.dist), _p(g.n_edges_dev), g.capacity, _p(offset), float(ctx.coeff), float(ctx.cutoff), G, F_, _p(w1), _p(b1),
-                _p(w2), _p(x), _p(grad_out), _p(g.src), _p(g.tgt), _p(ws), _p(gw1), _p(gb1), _p(gw2), _p(gb2), _stream()))
+                _p(dist), _p(count), g.capacity, _p(offset), float(ctx.coeff), float(ctx.cutoff), G, F_, _p(w1), _p(b1),
+                _p(w2), _p(x), _p(grad_out), _p(g.src), _p(g.tgt), _p(e1), _p(e2), _p(ws), _p(gw1), _p(gb1), _p(gw2), _p(gb2),
+                _stream()))
             return gx, gw1, gb1, gw2, gb2, None, None, None, None
         gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
         ws = torch.empty(lib.geossl_filter_bwd_workspace(G, F_), dtype=torch.float32, device=x.device)

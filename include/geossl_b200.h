@@ -66,6 +66,20 @@ int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_
                          const int32_t* graph_ptr, int64_t n_atoms, int32_t* scratch,
                          int32_t* t_rowptr, int32_t* t_eid, int32_t* t_tgt, void* stream);
 
+/* Undirected-pair index of a destination-sorted CSR with ascending sources per row.  The interaction filter depends on an
+ * edge only through its length (schnet.py:186-187) and |pos_j - pos_i| == |pos_i - pos_j| bit for bit, so both directions
+ * of a pair can share one filter row: the filter network runs over U <= E pairs instead of E edges (U = E/2 when no row
+ * is truncated).  Pair u of row t: first the edges with source < t in row order, then the "orphans" (source > t whose
+ * reverse edge was cut by max_num_neighbors or is absent).
+ *   pair_rowptr  (n_atoms+1)  pairs owned by each target row; pair_rowptr[n_atoms] = U stays on the device
+ *   pair_of_edge (capacity)   pair id of every directed edge (the filt_row map of geossl_cfconv_*)
+ *   pair_e1, pair_e2 (capacity) canonical edge id of pair u and its reverse edge id (or -1)
+ *   pair_dist    (capacity)   edge length of pair u
+ * scratch: n_atoms int32.  Deterministic, atomic free, no host sync. */
+int geossl_pair_index(const int32_t* rowptr, const int32_t* src, const float* edge_dist, int64_t n_atoms, int32_t* scratch,
+                      int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2, float* pair_dist,
+                      void* stream);
+
 /* Device-side batch assembly: all ordered atom pairs of every molecule in itertools order (combination: i<j,
  * permutation: i!=j), offset by the cumulative atom count -- AtomTupleExtractor + BatchAtomTuple.from_data_list
  * (dataloaders_AtomTuple.py:15-37,45-73; ratio == 1).  pair_ptr (n_graphs+1) int64 = exclusive scan of the per-graph
@@ -109,13 +123,15 @@ int geossl_debug_set_trace_bwd(long long* device_buffer);   /* backward kernel *
  * mode 2: throughput probe (cycle counts in d[0..1]);  mode 3: as mode 0 with A resident in tensor memory, b (N,K) */
 int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream);
 
-/* m_i = sum_{e in row i} x[src_e] * W_e   (atomic-free segmented reduction, one warp per row). */
-int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* rowptr, const int32_t* src,
+/* m_i = sum_{e in row i} x[src_e] * W_row(e)   (atomic-free segmented reduction, one warp per row).
+ * filt_row: NULL => row(e) = e (one filter row per directed edge); else row(e) = filt_row[e] (the pair_of_edge map of
+ * geossl_pair_index: both directions of an undirected pair read ONE shared filter row). */
+int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src,
                       int64_t n_atoms, int F, float* out, void* stream);
 
 /* dx_j = sum_{e: src_e = j} W_e * g[tgt_e]   over the source-sorted view. */
-int geossl_cfconv_bwd_x(const float* filt, const float* grad_out, const int32_t* t_rowptr, const int32_t* t_eid,
-                        const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream);
+int geossl_cfconv_bwd_x(const float* filt, const int32_t* filt_row, const float* grad_out, const int32_t* t_rowptr,
+                        const int32_t* t_eid, const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream);
 
 /* dW_e = x[src_e] * g[tgt_e]  materialised (E,F)  (second-order path and the unfused comparison). */
 int geossl_cfconv_bwd_w(const float* x, const float* grad_out, const int32_t* rowptr, const int32_t* src,
@@ -137,12 +153,16 @@ int geossl_filter_bwd(const float* edge_dist, const int32_t* n_edges_dev, int64_
 
 /* Same contract as geossl_filter_bwd (x / grad_out / src / edge_tgt form), on the tcgen05 tensor cores:
  * F = 128, G <= 63, operands split into two bf16 parts, weight gradients accumulated in TMEM.
- * workspace: geossl_filter_bwd_tc_workspace() floats. */
+ * workspace: geossl_filter_bwd_tc_workspace() floats.
+ * Pair form (pair_e1 / pair_e2 non-NULL, from geossl_pair_index): edge_dist / n_edges_dev / capacity describe the
+ * undirected PAIRS, and the filter-output gradient of pair u is formed as the sum over its one or two directions,
+ * x[s]*g[t] + x[t]*g[s]; the parameter gradients equal the per-edge form up to fp32 summation order. */
 int64_t geossl_filter_bwd_tc_workspace(void);
 int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int64_t capacity,
                          const float* offset, float coeff, float cutoff, int G, int F,
                          const float* w1, const float* b1, const float* w2,
                          const float* x, const float* grad_out, const int32_t* src, const int32_t* edge_tgt,
+                         const int32_t* pair_e1, const int32_t* pair_e2,
                          float* workspace, float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

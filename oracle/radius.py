@@ -81,3 +81,28 @@ def transpose_csr(rowptr, src):
     order = np.argsort(src, kind="stable")
     t_rowptr = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=n))]).astype(np.int64)
     return t_rowptr, order.astype(np.int64), tgt[order]
+
+
+def pair_index(rowptr, src):
+    """Undirected-pair index of a destination-sorted CSR with ascending sources per row (the contract of
+    geossl_pair_index, include/geossl_b200.h): pair ids are assigned row by row to the canonical edges -- source <
+    target, or an edge whose reverse is absent -- in row order.  Returns (pair_rowptr, pair_of_edge, pair_e1, pair_e2)."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    src = np.asarray(src, dtype=np.int64)
+    n = rowptr.size - 1
+    tgt = np.repeat(np.arange(n, dtype=np.int64), np.diff(rowptr))
+    eid = {(int(s), int(t)): e for e, (s, t) in enumerate(zip(src, tgt))}
+    pair_of_edge = np.full(src.size, -1, dtype=np.int64)
+    pair_rowptr = np.zeros(n + 1, dtype=np.int64)
+    e1, e2 = [], []
+    for e, (s, t) in enumerate(zip(src.tolist(), tgt.tolist())):
+        rev = eid.get((t, s), -1)
+        if s < t or rev < 0:
+            pair_of_edge[e] = len(e1)
+            e1.append(e)
+            e2.append(rev if s < t else -1)
+            pair_rowptr[t + 1] += 1
+    for e, (s, t) in enumerate(zip(src.tolist(), tgt.tolist())):
+        if pair_of_edge[e] < 0:
+            pair_of_edge[e] = pair_of_edge[eid[(t, s)]]
+    return np.cumsum(pair_rowptr), pair_of_edge, np.asarray(e1, dtype=np.int64), np.asarray(e2, dtype=np.int64)

@@ -150,3 +150,27 @@ def test_device_pair_subsampling(option):
     sel = sample_pairs_host(counts, option, ratio)
     b3 = assemble_batch_device(counts, z, pos, option=option, device=DEV, ratio=ratio, selection=sel)
     assert torch.equal(b3.super_edge_index.cpu(), super_edges_host(counts, option, ratio=ratio, selection=sel))
+
+
+
+@pytest.mark.parametrize("ng,lo,hi,density", [(7, 3, 30, 0.05), (4, 40, 70, 0.1), (6, 1, 2, 0.05)])
+def test_pair_index_matches_oracle(ng, lo, hi, density):
+    """geossl_pair_index vs oracle/radius.py::pair_index, including truncated rows (edges without a reverse)."""
+    from oracle.radius import pair_index, radius_neighbors
+    b = synthetic_batch(ng, lo, hi, seed=ng, with_pairs=False, density=density)
+    g = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), 10.0, num_graphs=ng).ensure_pairs()
+    rp, src = radius_neighbors(b.positions, 10.0, b.batch)
+    prp, poe, e1, e2 = pair_index(rp, src)
+    e, u = src.size, len(e1)
+    assert g.num_edges == e and int(g.n_pairs_dev.item()) == u
+    assert torch.equal(g.pair_rowptr.cpu().long(), torch.from_numpy(prp))
+    assert torch.equal(g.pair_of_edge[:e].cpu().long(), torch.from_numpy(poe))
+    assert torch.equal(g.pair_e1[:u].cpu().long(), torch.from_numpy(e1))
+    assert torch.equal(g.pair_e2[:u].cpu().long(), torch.from_numpy(e2))
+    assert torch.equal(g.pair_dist[:u], g.dist[:e][g.pair_e1[:u].long()])
+    if e:
+        rev = g.pair_e2[:u].long()
+        has = rev >= 0
+        assert torch.equal(g.dist[:e][rev[has]], g.pair_dist[:u][has])          # both directions: the same length, bitwise
+    if hi >= 40:
+        assert (e2 < 0).any() and u > e // 2                                     # truncation produced orphans

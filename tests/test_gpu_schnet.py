@@ -165,3 +165,27 @@ def test_lba_shaped_pockets_vs_oracle(filter_mode):
     deg = torch.bincount(ei[1], minlength=z.numel())
     assert int(deg.max()) == 33 and float((deg >= 32).float().mean()) > 0.5
     assert rel_err(h, h_ref) <= TOL_OUT and rel_err(out, out_ref) <= TOL_OUT
+
+
+def test_md17_train_step_through_finetune_module():
+    """The fine-tune caller (finetune_md17.py::train) via geossl_b200.finetune: same losses as the golden, and one Adam
+    step changes the weights."""
+    from geossl_b200.data import AtomTupleBatch
+    from geossl_b200.finetune import md17_losses, md17_train_step
+    from geossl_b200.pretrain import default_args
+    g = Golden("md17_small")
+    m = schnet_from(g, DEV)
+    lin = torch.nn.Linear(g.cfg["hidden"], 1).to(DEV)
+    lin.load_state_dict(g.sd("sdlin", DEV))
+    i = g["in"]
+    z = i["z"].to(DEV)
+    batch = AtomTupleBatch(torch.stack([z, torch.zeros_like(z)], 1), i["pos"].to(DEV), i["batch"].to(DEV), None,
+                           n_graphs=int(i["batch"][-1]) + 1, extras=dict(y=i["y"].to(DEV), force=i["force_target"].to(DEV)))
+    crit = torch.nn.L1Loss()
+    loss, energy, force = md17_losses(default_args("schnet"), batch, m, lin, crit)
+    assert rel_err(loss, g["out"]["loss"]) <= TOL_OUT and rel_err(force, g["out"]["force"]) <= TOL_GRAD
+    opt = torch.optim.Adam(list(m.parameters()) + list(lin.parameters()), lr=1e-3)
+    before = m.lin1.weight.detach().clone()
+    batch.positions = i["pos"].to(DEV)
+    l2 = md17_train_step(default_args("schnet"), batch, m, lin, crit, opt)
+    assert rel_err(l2, g["out"]["loss"]) <= TOL_OUT and not torch.equal(before, m.lin1.weight)

@@ -77,10 +77,14 @@ def test_filter_fwd_tc_vs_oracle(mode, tol, G, ng, lo, hi):
     assert rel_err(filt[:e], simt[:e]) <= tol
 
 
-@pytest.mark.parametrize("G,ng,lo,hi", [(50, 8, 20, 40), (63, 3, 5, 9), (20, 40, 25, 35), (51, 300, 28, 32)])
-def test_filter_bwd_tc_vs_simt(G, ng, lo, hi):
-    """Tensor-core backward (bf16 split, TMEM-resident weight gradients) against the exact fp32 kernel."""
-    b = synthetic_batch(ng, lo, hi, seed=G + 1, with_pairs=False)
+@pytest.mark.parametrize("share", [True, False])
+@pytest.mark.parametrize("G,ng,lo,hi,density", [(50, 8, 20, 40, 0.05), (63, 3, 5, 9, 0.05), (20, 40, 25, 35, 0.05),
+                                                (51, 300, 28, 32, 0.05), (50, 6, 40, 70, 0.1)])
+def test_filter_bwd_tc_vs_simt(G, ng, lo, hi, density, share, monkeypatch):
+    """Tensor-core backward (bf16 split, TMEM-resident weight gradients) against the exact fp32 per-edge kernel; with
+    ``share`` the tensor-core path runs over undirected pairs (the last case has truncated rows => orphan edges)."""
+    monkeypatch.setattr(ops, "SHARE_PAIR_FILTERS", share)
+    b = synthetic_batch(ng, lo, hi, seed=G + 1, with_pairs=False, density=density)
     cutoff = 10.0
     gen = torch.Generator().manual_seed(3)
     params = [(torch.randn(128, G, generator=gen) * 0.3), torch.randn(128, generator=gen) * 0.1,
@@ -135,3 +139,27 @@ def test_linear_tc_vs_torch(n, pre_ssp, use_bias, use_res):
         assert rel_err(b.grad, bd.grad) <= 1e-5
     if use_res:
         assert torch.equal(r.grad, gy)
+
+
+
+@pytest.mark.parametrize("ng,lo,hi,density", [(8, 20, 40, 0.05), (6, 40, 70, 0.1), (5, 1, 3, 0.05)])
+def test_pair_sharing_forward_is_bit_identical(ng, lo, hi, density, monkeypatch):
+    """|pos_j - pos_i| == |pos_i - pos_j| bit for bit, so sharing one filter row per atom pair must not change a single
+    bit of the aggregate m_i = sum_e x[src_e] * W_e (same kernel arithmetic, same summation order)."""
+    b = synthetic_batch(ng, lo, hi, seed=7, with_pairs=False, density=density)
+    gen = torch.Generator().manual_seed(5)
+    G, cutoff = 50, 10.0
+    params = [(torch.randn(128, G, generator=gen) * 0.3).to(DEV), (torch.randn(128, generator=gen) * 0.1).to(DEV),
+              (torch.randn(128, 128, generator=gen) * 0.15).to(DEV), (torch.randn(128, generator=gen) * 0.1).to(DEV)]
+    offset = torch.linspace(0.0, cutoff, G).to(DEV)
+    coeff = O.smearing_coeff(offset.cpu())
+    x = torch.randn(b.positions.shape[0], 128, generator=gen).to(DEV)
+    out = {}
+    for share in (False, True):
+        monkeypatch.setattr(ops, "SHARE_PAIR_FILTERS", share)
+        graph = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), cutoff, num_graphs=ng)
+        out[share] = ops.CFConvLayer.apply(x, *params, offset, graph, coeff, cutoff)
+        if share:
+            e, u = graph.num_edges, int(graph.n_pairs_dev.item())
+            assert e // 2 <= u <= e
+    assert torch.equal(out[True], out[False])
