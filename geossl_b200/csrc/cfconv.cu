@@ -16,34 +16,49 @@ __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w
 }
 
 // LPR lanes cover one F-wide row with float4 each; a warp walks EPW = 32/LPR edges per step.
-template <int F, int UNROLL>
-__global__ void __launch_bounds__(256)
-cfconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ filt, const int32_t* __restrict__ filt_row,
-                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, int n_atoms, float* __restrict__ out) {
+// One kernel serves both adjoint directions (row = target over the CSR, or row = source over the transposed view):
+//   out[row] = sum_{k in [ptr[row], ptr[row+1])} filt[frow(k)] * v[idx_b[k]],   frow(k) = filt_row[e(k)] or e(k),
+//   e(k) = k (CSR) or idx_a[k] (transposed view: t_eid).
+// The edge ids / gather indices of up to 32 edges are fetched with ONE coalesced load per lane and broadcast by shuffle,
+// so the 128-bit row loads of an unrolled step do not wait on per-edge index loads (the kernel is latency bound).
+template <int F, int UNROLL, bool TRANSPOSED, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+cfconv_gather_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ v,
+                     const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx_a, const int32_t* __restrict__ idx_b,
+                     int n_atoms, float* __restrict__ out) {
     constexpr int LPR = F / 4, EPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
     const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (row >= n_atoms) return;
     const int f = (lane % LPR) * 4, sub = lane / LPR;
-    const int b = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const int b = __ldg(ptr + row), end = __ldg(ptr + row + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e0 = b + sub; e0 < end; e0 += EPW * UNROLL) {
-        float4 w[UNROLL], xv[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int e = e0 + u * EPW;
-            if (e < end) {
-                const int j = __ldg(src + e);
-                const int r = filt_row ? __ldg(filt_row + e) : e;          // shared filter row of the undirected pair
-                w[u] = ld_stream4(filt + (int64_t)r * F + f);
-                xv[u] = ldg4(x + (int64_t)j * F + f);
-            } else {
-                w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                xv[u] = w[u];
-            }
+    for (int base = b; base < end; base += 32) {
+        const int mine = base + lane;
+        int my_a = 0, my_b = 0;
+        if (mine < end) {
+            const int e = TRANSPOSED ? __ldg(idx_a + mine) : mine;
+            my_a = filt_row ? __ldg(filt_row + e) : e;               // shared filter row of the undirected pair
+            my_b = __ldg(idx_b + mine);
         }
+        const int cnt = min(32, end - base);
+        for (int k0 = 0; k0 < cnt; k0 += EPW * UNROLL) {             // warp-uniform trip count (shuffles inside)
+            float4 w[UNROLL], xv[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) fma4(acc, xv[u], w[u]);
+            for (int u = 0; u < UNROLL; ++u) {
+                const int k = k0 + sub + u * EPW;
+                const int ra = __shfl_sync(0xffffffffu, my_a, k & 31), rb = __shfl_sync(0xffffffffu, my_b, k & 31);
+                if (k < cnt) {
+                    w[u] = ld_stream4(filt + (int64_t)ra * F + f);
+                    xv[u] = ldg4(v + (int64_t)rb * F + f);
+                } else {
+                    w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[u] = w[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) fma4(acc, xv[u], w[u]);
+        }
     }
 #pragma unroll
     for (int o = LPR; o < 32; o <<= 1) {
@@ -53,47 +68,6 @@ cfconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ filt, c
         acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
     if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
-}
-
-template <int F, int UNROLL>
-__global__ void __launch_bounds__(256)
-cfconv_bwd_x_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ g,
-                    const int32_t* __restrict__ t_rowptr,
-                    const int32_t* __restrict__ t_eid, const int32_t* __restrict__ t_tgt, int n_atoms,
-                    float* __restrict__ dx) {
-    constexpr int LPR = F / 4, EPW = 32 / LPR;
-    const int lane = threadIdx.x & 31;
-    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (row >= n_atoms) return;
-    const int f = (lane % LPR) * 4, sub = lane / LPR;
-    const int b = __ldg(t_rowptr + row), end = __ldg(t_rowptr + row + 1);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k0 = b + sub; k0 < end; k0 += EPW * UNROLL) {
-        float4 w[UNROLL], gv[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int k = k0 + u * EPW;
-            if (k < end) {
-                const int e = __ldg(t_eid + k), i = __ldg(t_tgt + k);
-                const int r = filt_row ? __ldg(filt_row + e) : e;
-                w[u] = ld_stream4(filt + (int64_t)r * F + f);
-                gv[u] = ldg4(g + (int64_t)i * F + f);
-            } else {
-                w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                gv[u] = w[u];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) fma4(acc, gv[u], w[u]);
-    }
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if (sub == 0) *reinterpret_cast<float4*>(dx + (int64_t)row * F + f) = acc;
 }
 
 template <int F>
@@ -114,12 +88,19 @@ cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, co
     }
 }
 
+static int g_variant = 0;   // tuning switch (geossl_debug_set_cfconv_variant)
+
 template <int F>
 int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src, int64_t n,
                float* out, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    cfconv_fwd_kernel<F, 4><<<blocks, threads, 0, st>>>(x, filt, filt_row, rowptr, src, (int)n, out);
+    switch (g_variant & 3) {
+        case 1: cfconv_gather_kernel<F, 8, false, 3><<<blocks, threads, 0, st>>>(filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        case 2: cfconv_gather_kernel<F, 8, false, 2><<<blocks, threads, 0, st>>>(filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        case 3: cfconv_gather_kernel<F, 4, false, 6><<<blocks, threads, 0, st>>>(filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        default: cfconv_gather_kernel<F, 4, false, 4><<<blocks, threads, 0, st>>>(filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
+    }
     return 0;
 }
 template <int F>
@@ -127,7 +108,12 @@ int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, con
                  int64_t n, float* dx, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    cfconv_bwd_x_kernel<F, 4><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx);
+    switch ((g_variant >> 2) & 3) {
+        case 1: cfconv_gather_kernel<F, 4, true, 4><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        case 2: cfconv_gather_kernel<F, 8, true, 2><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        case 3: cfconv_gather_kernel<F, 4, true, 6><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        default: cfconv_gather_kernel<F, 8, true, 3><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx);
+    }
     return 0;
 }
 template <int F>
@@ -151,6 +137,8 @@ using namespace geossl;
     }
 
 extern "C" {
+
+int geossl_debug_set_cfconv_variant(int v) { g_variant = v; return 0; }
 
 int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src,
                       int64_t n_atoms, int F, float* out, void* stream) {

@@ -123,6 +123,9 @@ int geossl_debug_set_trace_bwd(long long* device_buffer);   /* backward kernel *
  * mode 2: throughput probe (cycle counts in d[0..1]);  mode 3: as mode 0 with A resident in tensor memory, b (N,K) */
 int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream);
 
+/* Tuning switch for the cfconv gather kernels (0 = default; 1-3 = other unroll / occupancy points; profiles/tune_cfconv.py). */
+int geossl_debug_set_cfconv_variant(int variant);
+
 /* m_i = sum_{e in row i} x[src_e] * W_row(e)   (atomic-free segmented reduction, one warp per row).
  * filt_row: NULL => row(e) = e (one filter row per directed edge); else row(e) = filt_row[e] (the pair_of_edge map of
  * geossl_pair_index: both directions of an undirected pair read ONE shared filter row). */
