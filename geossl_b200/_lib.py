@@ -45,6 +45,7 @@ _SIGNATURES = {
     "geossl_filter_fwd_tc": (c_int, [c_p, c_p, c_i64, c_p, c_f, c_f, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_p]),
     "geossl_debug_set_trace": (c_int, [c_p]),
     "geossl_debug_set_trace_bwd": (c_int, [c_p]),
+    "geossl_debug_set_trace_head": (c_int, [c_p]),
     "geossl_tc_selftest": (c_int, [c_int, c_int, c_p, c_p, c_int, c_int, c_p, c_p]),
     "geossl_cfconv_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
     "geossl_cfconv_bwd_x": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
@@ -64,6 +65,7 @@ _SIGNATURES = {
     "geossl_linear_wgrad_tc": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
     "geossl_pair_distance": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "geossl_ddm_workspace": (c_i64, [c_int]),
+    "geossl_ddm_workspace_tc": (c_i64, [c_i64]),
     "geossl_ddm_head_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
                                     ctypes.POINTER(DdmPtrs), c_p, c_p, c_p]),
     "geossl_ddm_head_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,

@@ -535,6 +535,11 @@ int geossl_pair_distance(const float* pos, const int64_t* sei, int64_t n_pairs, 
 
 int64_t geossl_ddm_workspace(int H) { return head_workspace(H); }
 
+static int64_t head_pad(int64_t n_pairs) { return (n_pairs + 63) / 64 * 64; }
+static int64_t head_prep_offset() { return (head_workspace(128) + 63) / 64 * 64; }
+// partial sums | per-pair scalars (8 rows of n_pairs rounded up to the tile size)
+int64_t geossl_ddm_workspace_tc(int64_t n_pairs) { return head_prep_offset() + 8 * head_pad(n_pairs > 0 ? n_pairs : 0) + 64; }
+
 static int fill_head_in(HeadIn& in, const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
                         const float* dist, const float* noise, const int64_t* noise_level, const float* sigmas,
                         int n_levels, float anneal_power, const geossl_ddm_params* params) {
@@ -616,6 +621,89 @@ int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch
 namespace geossl {
 namespace tc {
 
+__device__ long long* g_trace_head = nullptr;  // optional clock64() trace of CTA 0 (geossl_debug_set_trace_head)
+__device__ __forceinline__ void trace_h(int tile, int event) {
+    long long* t = g_trace_head;
+    if (t != nullptr && blockIdx.x == 0 && tile < 32 && threadIdx.x == 0) t[tile * 16 + event] = clock64();
+}
+
+// Per-pair scalars of the DDM objective, one thread per pair, computed ONCE per launch instead of per tile inside
+// the MMA pipeline (where the index -> graph id -> noise level -> sigma chain was four dependent global loads):
+//   prep[0][p] = u, prep[1][p] = v, prep[2][p] = graph id   (int32 bit patterns)
+//   prep[3][p] = sigma, [4] = perturbed distance d~, [5] = target, [6] = sigma^anneal, [7] = distance embedding(d~)
+// Row stride = n_pad (pairs rounded up to the tile size); rows past n_pairs are zero / sigma = 1.
+constexpr int kPrepRows = 8;
+__global__ void __launch_bounds__(256)
+ddm_pair_prep_kernel(HeadIn in, int64_t n_pad, float* __restrict__ prep) {
+    __shared__ float sw0[128], sb0[128], sw1[128];
+    if (threadIdx.x < 128) {
+        sw0[threadIdx.x] = __ldg(in.p.in_w0 + threadIdx.x);
+        sb0[threadIdx.x] = __ldg(in.p.in_b0 + threadIdx.x);
+        sw1[threadIdx.x] = __ldg(in.p.in_w1 + threadIdx.x);
+    }
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pad) return;
+    int u = 0, v = 0, g = -1;
+    float sigma = 1.f, dt = 0.f, tgt = 0.f, sa = 0.f, emb = 0.f;
+    if (p < in.n_pairs) {
+        u = (int)in.sei[p];
+        v = (int)in.sei[in.n_pairs + p];
+        g = (int)in.batch[u];
+        int lvl = (int)in.noise_level[g];
+        lvl = lvl < 0 ? 0 : (lvl >= in.n_levels ? in.n_levels - 1 : lvl);
+        sigma = __ldg(in.sigmas + lvl);
+        const float d = __ldg(in.dist + p);
+        dt = __fadd_rn(d, __fmul_rn(__ldg(in.noise + p), sigma));                    // NCSN.py:194-195
+        tgt = __fmul_rn(-(1.f / __fmul_rn(sigma, sigma)), __fsub_rn(dt, d));         // :196
+        sa = (in.anneal_power == 2.f) ? sigma * sigma : powf(sigma, in.anneal_power);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                                // input_distance_mlp, 1 -> 128 -> 1
+#pragma unroll 4
+        for (int k = 0; k < 128; k += 4) {
+            s0 = fmaf(sw1[k], fmaxf(fmaf(sw0[k], dt, sb0[k]), 0.f), s0);
+            s1 = fmaf(sw1[k + 1], fmaxf(fmaf(sw0[k + 1], dt, sb0[k + 1]), 0.f), s1);
+            s2 = fmaf(sw1[k + 2], fmaxf(fmaf(sw0[k + 2], dt, sb0[k + 2]), 0.f), s2);
+            s3 = fmaf(sw1[k + 3], fmaxf(fmaf(sw0[k + 3], dt, sb0[k + 3]), 0.f), s3);
+        }
+        emb = ((s0 + s1) + (s2 + s3)) + __ldg(in.p.in_b1);
+    }
+    prep[0 * n_pad + p] = __int_as_float(u);
+    prep[1 * n_pad + p] = __int_as_float(v);
+    prep[2 * n_pad + p] = __int_as_float(g);
+    prep[3 * n_pad + p] = sigma;
+    prep[4 * n_pad + p] = dt;
+    prep[5 * n_pad + p] = tgt;
+    prep[6 * n_pad + p] = sa;
+    prep[7 * n_pad + p] = emb;
+}
+
+// Sum over the 32 lanes of each of 16 per-lane values with 16 shuffles (instead of 16 x 5): after the four halving
+// exchanges lane l holds the total of element e(l) = (l >> 1) & 15 ... returned; both lanes of a pair (l, l^1) agree.
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float send = h16 ? v[j] : v[j + 8], keep = h16 ? v[j + 8] : v[j];
+        a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float send = h8 ? a[j] : a[j + 4], keep = h8 ? a[j + 4] : a[j];
+        b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float send = h4 ? b[j] : b[j + 2], keep = h4 ? b[j + 2] : b[j];
+        c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float send = h2 ? c[0] : c[1], keep = h2 ? c[1] : c[0];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;                                                   // element index = 8*bit4 + 4*bit3 + 2*bit2 + bit1 of the lane
+}
+__device__ __forceinline__ int reduce16_index(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
 constexpr int kHP = 64;                        // pairs per tile
 constexpr int kHBlkW = 128 * 128;              // [128 rows x 64 k] weight block (bytes)
 constexpr int kHBlkT = kHP * 128;              // [64 rows x 64 k] tile block (bytes)
@@ -638,8 +726,8 @@ static_assert(HeadSmem::kBytes + 1024 <= 227 * 1024, "shared memory budget");
 
 template <bool FP16, bool BWD>
 __global__ void __launch_bounds__(kHThreads, 1)
-ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* __restrict__ grad_loss,
-                   float* __restrict__ grad_h, float* __restrict__ workspace) {
+ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, const float* __restrict__ loss_aux,
+                   const float* __restrict__ grad_loss, float* __restrict__ grad_h, float* __restrict__ workspace) {
     using K = HeadCfg<128>;
     using L = HeadSmem;
     extern __shared__ uint8_t smem_raw[];
@@ -669,7 +757,8 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         for (int j = 0; j < 8; ++j) v[j] = __ldg(in.p.out_w1 + n2 * 128 + c * 8 + j);
         store_chunk8<FP16>(smem + L::W1 + (c >> 3) * kHBlkT, smem + L::W1 + 2 * kHBlkT + (c >> 3) * kHBlkT, n2, (c & 7) * 8, v);
     }
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    const uint32_t bar_wg = bar + 8;                           // weight-gradient MMAs retire off the critical path
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar_wg, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, 512);
     fence_proxy_async();
     tc_fence_before();
@@ -685,8 +774,8 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
     const float wl = __ldg(in.p.out_w0 + Ln * 129 + 128), b0n = __ldg(in.p.out_b0 + Ln);
     const float b1n = Ln < 64 ? __ldg(in.p.out_b1 + Ln) : 0.f, w2n = Ln < 64 ? __ldg(in.p.out_w2 + Ln) : 0.f;
     const float out_b2 = __ldg(in.p.out_b2), in_b1 = __ldg(in.p.in_b1);
-    const float iw0 = tid < 128 ? __ldg(in.p.in_w0 + tid) : 0.f, ib0 = tid < 128 ? __ldg(in.p.in_b0 + tid) : 0.f,
-                iw1 = tid < 128 ? __ldg(in.p.in_w1 + tid) : 0.f;
+    const int unit = tid & 127, pgrp = tid >> 7;               // emb-gradient mapping: hidden unit x quarter of the tile's pairs
+    const float iw0 = __ldg(in.p.in_w0 + unit), ib0 = __ldg(in.p.in_b0 + unit), iw1 = __ldg(in.p.in_w1 + unit);
     float gscale = 0.f;
     if (BWD) {
         const float ng = __ldg(loss_aux + 1);
@@ -700,47 +789,36 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
     float loss_acc = 0.f;
     int gmax = -1;
     float a_db0 = 0.f, a_dwl = 0.f, a_db1 = 0.f, a_dw2 = 0.f, a_db2 = 0.f, a_iw0 = 0.f, a_ib0 = 0.f, a_iw1 = 0.f, a_ib1 = 0.f;
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase_wg = 0;
     int done = 0;
     const int64_t n_tiles = (in.n_pairs + kHP - 1) / kHP;
+    float pre[kPrepRows];
+    if (tid < kHP && blockIdx.x < n_tiles) {
+#pragma unroll
+        for (int r = 0; r < kPrepRows; ++r) pre[r] = __ldg(prep + r * n_pad + (int64_t)blockIdx.x * kHP + tid);
+    }
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++done) {
-        const int64_t p0 = t * kHP;
-        // ---- 0. per-pair scalars
+        trace_h(done, 0);
+        // ---- 0. per-pair scalars: precomputed by ddm_pair_prep_kernel, the next tile's are prefetched into registers
         if (tid < kHP) {
-            const int64_t p = p0 + tid;
-            int u = 0, v = 0;
-            float sigma = 1.f, dt = 0.f, tgt = 0.f, sa = 0.f, valid = 0.f;
-            if (p < in.n_pairs) {
-                u = (int)in.sei[p];
-                v = (int)in.sei[in.n_pairs + p];
-                const int g = (int)in.batch[u];
-                gmax = max(gmax, g);
-                int lvl = (int)in.noise_level[g];
-                lvl = lvl < 0 ? 0 : (lvl >= in.n_levels ? in.n_levels - 1 : lvl);
-                sigma = __ldg(in.sigmas + lvl);
-                const float d = __ldg(in.dist + p);
-                dt = __fadd_rn(d, __fmul_rn(__ldg(in.noise + p), sigma));
-                tgt = __fmul_rn(-(1.f / __fmul_rn(sigma, sigma)), __fsub_rn(dt, d));
-                sa = (in.anneal_power == 2.f) ? sigma * sigma : powf(sigma, in.anneal_power);
-                valid = 1.f;
-            }
-            sU[tid] = u; sV[tid] = v; sSig[tid] = sigma; sDt[tid] = dt; sTgt[tid] = tgt; sSa[tid] = sa; sValid[tid] = valid;
+            sU[tid] = __float_as_int(pre[0]); sV[tid] = __float_as_int(pre[1]);
+            const int g = __float_as_int(pre[2]);
+            gmax = max(gmax, g);
+            sSig[tid] = pre[3]; sDt[tid] = pre[4]; sTgt[tid] = pre[5]; sSa[tid] = pre[6]; sEmb[tid] = pre[7];
+            sValid[tid] = g >= 0 ? 1.f : 0.f;
         }
         __syncthreads();
-        // ---- 1. distance embedding (8 threads per pair) and the feat tile (lanes over columns: coalesced row gathers)
-        {
-            const int pl = tid >> 3, part = tid & 7;
-            const float dt = sDt[pl];
-            float s = 0.f;
-#pragma unroll 4
-            for (int k = part; k < 128; k += 8) {
-                const float pre = fmaf(__ldg(in.p.in_w0 + k), dt, __ldg(in.p.in_b0 + k));
-                s = fmaf(__ldg(in.p.in_w1 + k), fmaxf(pre, 0.f), s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (part == 0) sEmb[pl] = s + in_b1;
+        trace_h(done, 1);
+        if (tid < kHP && t + gridDim.x < n_tiles) {
+            const int64_t pn = (t + gridDim.x) * kHP + tid;
+#pragma unroll
+            for (int r = 0; r < kPrepRows; ++r) pre[r] = __ldg(prep + r * n_pad + pn);
+        }
+        trace_h(done, 2);
+        // ---- 1. the feat tile (lanes over columns: coalesced row gathers)
+        if (BWD && done > 0) {                                 // WG0/WG1 of the previous tile still read FEAT / Z1 / dZ1 / dZ2
+            mbar_wait(bar_wg, phase_wg); phase_wg ^= 1;
+            tc_fence_after();
         }
         {
             const int cg = tid & 15, ro = tid >> 4;             // 8 columns 8cg.., rows ro and ro + 32
@@ -759,6 +837,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         }
         fence_proxy_async();
         __syncthreads();
+        trace_h(done, 3);
         // ---- 2. MMA1: D1^T = W0h . feat^T
         if (warp == 0) {                                      // uniform operands; the elected lane issues
             tc_fence_after();
@@ -776,6 +855,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
+        trace_h(done, 4);
         // ---- 3. E1: z1 = relu(D1^T + emb_p * wl + b0) -> Z1 tile [p][n]
         uint32_t mask1 = 0;
         {
@@ -791,6 +871,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
+        trace_h(done, 5);
         // ---- 4. MMA2: D2^T = W1 . z1^T   (rows n2 >= 64 of the A operand are garbage lanes that are never read)
         if (warp == 0) {                                      // uniform operands; the elected lane issues
             tc_fence_after();
@@ -808,19 +889,20 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
+        trace_h(done, 6);
         // ---- 5. E2: z2, score (sum over the 64 lanes n2), loss / dsr, dz2
         float z2[16];
         {
             float v[16];
             tmem_ld16(tD2 + lane_base + col0, v);
+            float ps[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 z2[j] = Ln < 64 ? fmaxf(v[j] + b1n, 0.f) : 0.f;
-                float ps = z2[j] * w2n;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-                if (lane == 0 && q < 2) sRed[q * 64 + col0 + j] = ps;
+                ps[j] = z2[j] * w2n;
             }
+            const float tot = warp_reduce16(ps, lane);
+            if ((lane & 1) == 0 && q < 2) sRed[q * 64 + col0 + reduce16_index(lane)] = tot;
         }
         tc_fence_before();
         __syncthreads();
@@ -831,8 +913,9 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
             loss_acc += 0.5f * (diff * diff) * sSa[tid];
             sDsr[tid] = diff * sSa[tid] * gscale * inv;
         }
-        if (!BWD) { __syncthreads(); continue; }
+        if (!BWD) { __syncthreads(); trace_h(done, 7); continue; }
         __syncthreads();
+        trace_h(done, 7);
         if (Ln < 64) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -846,6 +929,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         if (tid < kHP) a_db2 += sDsr[tid];
         fence_proxy_async();
         __syncthreads();
+        trace_h(done, 8);
         // ---- 6. MMA3: D3^T = W1^T . dz2^T (A = MN-major view of the W1 image, K = 64) ; WG1: DW1^T += z1^T dz2
         if (warp == 0) {                                      // uniform operands; the elected lane issues
             tc_fence_after();
@@ -854,35 +938,37 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
                 const uint64_t bh = desc_k_sw128(sbase + L::DZ2), bl = desc_k_sw128(sbase + L::DZ2 + kHBlkT);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) mma3(tD3, ah + ks * 128, al + ks * 128, bh + 2 * ks, bl + 2 * ks, id_a_mn, ks > 0);
+                tc_commit(bar);                                // E3 waits for MMA3 only; WG1 runs behind it
                 const uint64_t zh = desc_mn_sw128(sbase + L::Z1, kHBlkT), zl = desc_mn_sw128(sbase + L::Z1 + 2 * kHBlkT, kHBlkT);
                 const uint64_t dh = desc_mn_sw128(sbase + L::DZ2, kHBlkT), dl = desc_mn_sw128(sbase + L::DZ2 + kHBlkT, kHBlkT);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) mma3(tDW1, zh + ks * 128, zl + ks * 128, dh + ks * 128, dl + ks * 128, id_wg1, (done | ks) > 0);
-                tc_commit(bar);
             }
             __syncwarp();
         }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
+        trace_h(done, 9);
         // ---- 7. E3: dz1 = D3^T * [z1 > 0] -> dZ1 tile ; db0, dW0[:,128] in-thread ; demb_p = sum_n dz1 wl (over lanes)
         {
             float v[16];
             tmem_ld16(tD3 + lane_base + col0, v);
+            float pd[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float dz = ((mask1 >> j) & 1u) ? v[j] : 0.f;
                 a_db0 += dz;
                 a_dwl = fmaf(dz, sEmb[col0 + j], a_dwl);
-                float pd = dz * wl;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) pd += __shfl_xor_sync(0xffffffffu, pd, o);
-                if (lane == 0) sRed[q * 64 + col0 + j] = pd;
+                pd[j] = dz * wl;
                 store_split1<FP16>(smem + L::DZ1 + (Ln >> 6) * kHBlkT, smem + L::DZ1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0 + j, Ln & 63, dz);
             }
+            const float tot = warp_reduce16(pd, lane);
+            if ((lane & 1) == 0) sRed[q * 64 + col0 + reduce16_index(lane)] = tot;
         }
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
+        trace_h(done, 10);
         // ---- 8. MMA4: D4^T = W0h^T . dz1^T (A = MN-major view of the W0 image, K = 128) ; WG0: DW0 += dz1^T feat
         if (warp == 0) {                                      // uniform operands; the elected lane issues
             tc_fence_after();
@@ -894,11 +980,12 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
                     const uint32_t ob = (ks >> 2) * (kHBlkT >> 4) + 2 * (ks & 3);
                     mma3(tD4, ah + ks * 128, al + ks * 128, bh + ob, bl + ob, id_a_mn, ks > 0);
                 }
+                tc_commit(bar);                                // E4 waits for MMA4 only
                 const uint64_t zh = desc_mn_sw128(sbase + L::DZ1, kHBlkT), zl = desc_mn_sw128(sbase + L::DZ1 + 2 * kHBlkT, kHBlkT);
                 const uint64_t fh = desc_mn_sw128(sbase + L::FEAT, kHBlkT), fl = desc_mn_sw128(sbase + L::FEAT + 2 * kHBlkT, kHBlkT);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) mma3(tDW0, zh + ks * 128, zl + ks * 128, fh + ks * 128, fl + ks * 128, id_wg0, (done | ks) > 0);
-                tc_commit(bar);
+                tc_commit(bar_wg);                             // covers WG1 and WG0 of this tile
             }
             __syncwarp();
         }
@@ -906,33 +993,48 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
         __syncthreads();
+        trace_h(done, 11);
         // ---- 9. E4: scatter dfeat to both endpoints (lanes = features: 128 contiguous bytes per warp instruction)
         {
             float v[16];
             tmem_ld16(tD4 + lane_base + col0, v);
+            // consecutive pairs of a molecule share their first atom (itertools order): one RED per run of equal u
+            int cur_u = -1;
+            float run = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 if (sValid[col0 + j] != 0.f) {
-                    atomicAdd(grad_h + (int64_t)sU[col0 + j] * 128 + Ln, v[j]);
+                    const int uj = sU[col0 + j];
                     atomicAdd(grad_h + (int64_t)sV[col0 + j] * 128 + Ln, v[j]);
+                    if (uj != cur_u) {
+                        if (cur_u >= 0) atomicAdd(grad_h + (int64_t)cur_u * 128 + Ln, run);
+                        cur_u = uj;
+                        run = v[j];
+                    } else {
+                        run += v[j];
+                    }
                 }
             }
+            if (cur_u >= 0) atomicAdd(grad_h + (int64_t)cur_u * 128 + Ln, run);
         }
-        if (tid < 128) {   // distance-embedding MLP gradients, thread per hidden unit
-            for (int p = 0; p < kHP; ++p) {
+        trace_h(done, 12);
+        {   // distance-embedding MLP gradients: thread = (hidden unit, quarter of the tile's pairs)
+#pragma unroll 4
+            for (int p = pgrp * 16; p < pgrp * 16 + 16; ++p) {
                 const float dt = sDt[p], de = sDemb[p];
-                const float pre = fmaf(iw0, dt, ib0);
-                if (pre > 0.f) {
-                    a_iw1 = fmaf(de, pre, a_iw1);
+                const float pa = fmaf(iw0, dt, ib0);
+                if (pa > 0.f) {
+                    a_iw1 = fmaf(de, pa, a_iw1);
                     const float dpre = de * iw1;
                     a_iw0 = fmaf(dpre, dt, a_iw0);
                     a_ib0 += dpre;
                 }
-                if (tid == 0) a_ib1 += de;
+                if (unit == 0) a_ib1 += de;
             }
         }
         tc_fence_before();
         __syncthreads();
+        trace_h(done, 13);
     }
 
     if (!BWD) {
@@ -953,6 +1055,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
     } else {
         // ---- per-CTA partial gradients in HeadCfg<128>'s layout (reduced by ddm_head_reduce_kernel<128>)
         float* ws = workspace + (int64_t)blockIdx.x * K::kPartial;
+        if (done > 0) mbar_wait(bar_wg, phase_wg);             // the last tile's weight-gradient MMAs
         tc_fence_after();
         {   // DW0 [n][k]: lane n, this warp's column group covers k = cg4*32 .. +31
             float v[32];
@@ -984,9 +1087,21 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
             ws[K::pB0 + tid] = s0;
             ws[K::pW0 + tid * K::LD + 128] = s1;
             if (tid < 64) { ws[K::pB1 + tid] = s2; ws[K::pW2 + tid] = s3; }
-            ws[K::pIW0 + tid] = a_iw0; ws[K::pIB0 + tid] = a_ib0; ws[K::pIW1 + tid] = a_iw1;
         }
-        if (tid == 0) ws[K::pIB1] = a_ib1;
+        __syncthreads();
+        red[(0 * 4 + pgrp) * 128 + unit] = a_iw0;                    // the four pair-quarters of every hidden unit
+        red[(1 * 4 + pgrp) * 128 + unit] = a_ib0;
+        red[(2 * 4 + pgrp) * 128 + unit] = a_iw1;
+        if (unit == 0) red[3 * 4 * 128 + pgrp] = a_ib1;
+        __syncthreads();
+        if (tid < 128) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            for (int c = 0; c < 4; ++c) {
+                s0 += red[(0 * 4 + c) * 128 + tid]; s1 += red[(1 * 4 + c) * 128 + tid]; s2 += red[(2 * 4 + c) * 128 + tid];
+            }
+            ws[K::pIW0 + tid] = s0; ws[K::pIB0 + tid] = s1; ws[K::pIW1 + tid] = s2;
+        }
+        if (tid == 0) ws[K::pIB1] = (red[3 * 4 * 128] + red[3 * 4 * 128 + 1]) + (red[3 * 4 * 128 + 2] + red[3 * 4 * 128 + 3]);
         // out_b2: sum over the 64 scalar threads
         if (warp < 2) {
             float s = warp_sum(a_db2);
@@ -1008,6 +1123,12 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* _
 
 extern "C" {
 
+int geossl_debug_set_trace_head(long long* device_buffer) {
+    GEOSSL_CUDA(cudaMemcpyToSymbol(tc::g_trace_head, &device_buffer, sizeof(device_buffer)));
+    return 0;
+}
+
+
 int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
                            const float* dist, const float* noise, const int64_t* noise_level,
                            const float* sigmas, int n_levels, float anneal_power, int H,
@@ -1028,7 +1149,12 @@ int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* ba
         configured = true;
     }
     const int grid = head_grid(n_pairs);
-    tc::ddm_head_tc_kernel<true, false><<<grid, tc::kHThreads, smem, as_stream(stream)>>>(in, nullptr, nullptr, nullptr, workspace);
+    const int64_t n_pad = head_pad(n_pairs);
+    float* prep = workspace + head_prep_offset();
+    tc::ddm_pair_prep_kernel<<<(int)((n_pad + 255) / 256), 256, 0, as_stream(stream)>>>(in, n_pad, prep);
+    GEOSSL_LAUNCH_CHECK();
+    tc::ddm_head_tc_kernel<true, false><<<grid, tc::kHThreads, smem, as_stream(stream)>>>(in, prep, n_pad, nullptr, nullptr, nullptr,
+                                                                                         workspace);
     GEOSSL_LAUNCH_CHECK();
     ddm_loss_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(workspace, grid, loss);
     GEOSSL_LAUNCH_CHECK();
@@ -1056,7 +1182,12 @@ int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     }
     GEOSSL_CUDA(cudaMemsetAsync(grad_h, 0, sizeof(float) * (size_t)n_atoms * 128, as_stream(stream)));
     const int grid = head_grid(n_pairs);
-    tc::ddm_head_tc_kernel<false, true><<<grid, tc::kHThreads, smem, as_stream(stream)>>>(in, loss_aux, grad_loss, grad_h, workspace);
+    const int64_t n_pad = head_pad(n_pairs);
+    float* prep = workspace + head_prep_offset();
+    tc::ddm_pair_prep_kernel<<<(int)((n_pad + 255) / 256), 256, 0, as_stream(stream)>>>(in, n_pad, prep);
+    GEOSSL_LAUNCH_CHECK();
+    tc::ddm_head_tc_kernel<false, true><<<grid, tc::kHThreads, smem, as_stream(stream)>>>(in, prep, n_pad, loss_aux, grad_loss, grad_h,
+                                                                                         workspace);
     GEOSSL_LAUNCH_CHECK();
     const int n = HeadCfg<128>::kPartial;
     ddm_head_reduce_kernel<128><<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(workspace, grid, g);

@@ -581,10 +581,11 @@ class DDMHead(torch.autograd.Function):
         lib = _lib.load()
         H = h.size(1)
         n_pairs = sei.size(1)
-        ws = torch.empty(max(lib.geossl_ddm_workspace(H), 1), dtype=torch.float32, device=h.device)
+        ctx.tc = FILTER_MODE != "simt" and H == 128
+        ws = torch.empty(max(lib.geossl_ddm_workspace_tc(n_pairs) if ctx.tc else lib.geossl_ddm_workspace(H), 1),
+                         dtype=torch.float32, device=h.device)
         loss = torch.empty(2, dtype=torch.float32, device=h.device)
         pp = _ddm_ptrs(params)
-        ctx.tc = FILTER_MODE != "simt" and H == 128
         fwd = lib.geossl_ddm_head_fwd_tc if ctx.tc else lib.geossl_ddm_head_fwd
         _timed("ddm_head_fwd", lambda: fwd(
             _p(h), _p(sei), _p(batch), n_pairs, _p(dist), _p(noise), _p(noise_level), _p(sigmas), sigmas.numel(),
@@ -603,7 +604,8 @@ class DDMHead(torch.autograd.Function):
         grads = [torch.empty_like(p) for p in params]
         if n_pairs == 0:
             return (torch.zeros_like(h), None, None, None, None, None, None, None, *[torch.zeros_like(p) for p in params])
-        ws = torch.empty(lib.geossl_ddm_workspace(H), dtype=torch.float32, device=h.device)
+        ws = torch.empty(lib.geossl_ddm_workspace_tc(n_pairs) if ctx.tc else lib.geossl_ddm_workspace(H),
+                         dtype=torch.float32, device=h.device)
         gl = grad_loss.contiguous().view(1).to(torch.float32)
         pp, gp = _ddm_ptrs(params), _ddm_ptrs(grads)
         bwd = lib.geossl_ddm_head_bwd_tc if ctx.tc else lib.geossl_ddm_head_bwd

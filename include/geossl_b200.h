@@ -116,6 +116,7 @@ int geossl_filter_fwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
  * int64 slots (slot = tile*16 + event); NULL disables.  Used by profiles/trace_tc.py. */
 int geossl_debug_set_trace(long long* device_buffer);       /* forward kernel */
 int geossl_debug_set_trace_bwd(long long* device_buffer);   /* backward kernel */
+int geossl_debug_set_trace_head(long long* device_buffer);  /* tensor-core DDM head kernels */
 
 /* Self test of the tcgen05 plumbing (descriptors, swizzle, TMEM): one 128 x N x K split-precision GEMM.
  * mode 0: d[m][n] = sum_k a[m][k] b[n][k]  (a (128,K), b (128,K), K in {64,128}, N = 128; K-major operands)
@@ -221,6 +222,10 @@ typedef struct {
  * NCSN.py:190,194).  The mean is over max_p(batch[u_p])+1 graphs (torch_scatter dim_size).
  * workspace: geossl_ddm_workspace(H) floats. */
 int64_t geossl_ddm_workspace(int H);
+/* workspace of the tensor-core editions (geossl_ddm_head_{fwd,bwd}_tc): the partial sums plus 8 per-pair scalars
+ * (endpoints, graph id, sigma, perturbed distance, target, sigma^anneal, distance embedding) that a one-thread-per-pair
+ * prologue kernel writes before the MMA pipeline starts. */
+int64_t geossl_ddm_workspace_tc(int64_t n_pairs);
 int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
                         const float* dist, const float* noise, const int64_t* noise_level,
                         const float* sigmas, int n_levels, float anneal_power, int H,
