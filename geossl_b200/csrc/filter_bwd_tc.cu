@@ -67,7 +67,7 @@ __device__ __forceinline__ void store_split_bf16(uint8_t* hi_block, uint8_t* lo_
 
 // PAIRS: the tile rows are undirected pairs (geossl_pair_index): edge_dist / n_edges_dev describe the pairs, and
 // dU_u = C(d_u) * (x[s] * g[t] + x[t] * g[s]) sums both directions of pair u = (s -> t) (second term only if the reverse
-// edge exists, pair_e2[u] >= 0).  Everything downstream of dU is linear in it, so the parameter gradients are unchanged.
+// edge exists: pair_atoms[u] = (s, t) or (s, ~t)).  Everything downstream of dU is linear in it, so the parameter gradients are unchanged.
 template <bool PAIRS>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restrict__ n_edges_dev, int64_t capacity,
@@ -75,7 +75,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                      const float* __restrict__ x, const float* __restrict__ grad_out,
                      const int32_t* __restrict__ src, const int32_t* __restrict__ edge_tgt,
-                     const int32_t* __restrict__ pair_e1, const int32_t* __restrict__ pair_e2, float* __restrict__ workspace) {
+                     const int2* __restrict__ pair_atoms, float* __restrict__ workspace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     using L = BwdLayout;
@@ -179,23 +179,32 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             uint8_t* hi = smem + L::DU + b * 4 * kBlkT + (cg >> 3) * kBlkT;
             uint8_t* lo = hi + 2 * kBlkT;
             if constexpr (PAIRS) {
+                // the four rows' atom ids and lengths first (one latency), so that the row gathers below start back to back
+                int2 st[4];
+                float dd[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int64_t u = e_base + rr * 16 + ro;
+                    st[rr] = make_int2(-1, 0);
+                    dd[rr] = 0.f;
+                    if (u < n_edges) { st[rr] = __ldg(pair_atoms + u); dd[rr] = __ldg(edge_dist + u); }
+                }
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                     const int row = rr * 16 + ro;
-                    const int64_t u = e_base + row;
                     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 xs0 = z4, xs1 = z4, gt0 = z4, gt1 = z4, xt0 = z4, xt1 = z4, gs0 = z4, gs1 = z4;
                     float cs = 0.f;
-                    if (u < n_edges) {
-                        const int e1 = __ldg(pair_e1 + u), e2 = __ldg(pair_e2 + u);
-                        const int64_t sa = (int64_t)__ldg(src + e1) * 128 + cg * 8, ta = (int64_t)__ldg(edge_tgt + e1) * 128 + cg * 8;
+                    if (st[rr].x >= 0) {
+                        const bool both = st[rr].y >= 0;
+                        const int64_t sa = (int64_t)st[rr].x * 128 + cg * 8, ta = (int64_t)(both ? st[rr].y : ~st[rr].y) * 128 + cg * 8;
                         xs0 = ldg4(x + sa); xs1 = ldg4(x + sa + 4);
                         gt0 = ldg4(grad_out + ta); gt1 = ldg4(grad_out + ta + 4);
-                        if (e2 >= 0) {
+                        if (both) {
                             xt0 = ldg4(x + ta); xt1 = ldg4(x + ta + 4);
                             gs0 = ldg4(grad_out + sa); gs1 = ldg4(grad_out + sa + 4);
                         }
-                        cs = 0.5f * (__cosf(__ldg(edge_dist + u) * pi_over_rc) + 1.0f);
+                        cs = 0.5f * (__cosf(dd[rr] * pi_over_rc) + 1.0f);
                     }
                     if (rr == 0) {
                         mbar_wait(bar(DU_FREE_ + b), ((i >> 1) & 1) ^ 1);   // gathers of the first row are already in flight
@@ -479,13 +488,12 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
                          const float* offset, float coeff, float cutoff, int G, int F,
                          const float* w1, const float* b1, const float* w2,
                          const float* x, const float* grad_out, const int32_t* src, const int32_t* edge_tgt,
-                         const int32_t* pair_e1, const int32_t* pair_e2,
+                         const int32_t* pair_atoms,
                          float* workspace, float* gw1, float* gb1, float* gw2, float* gb2, void* stream) {
-    GEOSSL_REQUIRE(edge_dist && n_edges_dev && offset && w1 && b1 && w2 && x && grad_out && src && edge_tgt && workspace &&
-                   gw1 && gb1 && gw2 && gb2, "null pointer");
+    GEOSSL_REQUIRE(edge_dist && n_edges_dev && offset && w1 && b1 && w2 && x && grad_out && workspace &&
+                   gw1 && gb1 && gw2 && gb2 && (pair_atoms || (src && edge_tgt)), "null pointer");
     GEOSSL_REQUIRE(F == 128, "the tensor-core filter kernel is built for num_filters = 128");
     GEOSSL_REQUIRE(G >= 1 && G <= 63, "num_gaussians must be in [1,63] (column 63 of the rbf tile carries the bias sum)");
-    GEOSSL_REQUIRE((pair_e1 == nullptr) == (pair_e2 == nullptr), "pair_e1 and pair_e2 go together");
     const size_t smem = tc::BwdLayout::kBytes + 1024;
     static bool configured = false;
     if (!configured) {
@@ -493,12 +501,13 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    if (pair_e1)
+    if (pair_atoms)
         tc::filter_bwd_tc_kernel<true><<<kNumSM, tc::kBwdThreads, smem, as_stream(stream)>>>(
-            edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt, pair_e1, pair_e2, workspace);
+            edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt,
+            reinterpret_cast<const int2*>(pair_atoms), workspace);
     else
         tc::filter_bwd_tc_kernel<false><<<kNumSM, tc::kBwdThreads, smem, as_stream(stream)>>>(
-            edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt, nullptr, nullptr, workspace);
+            edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt, nullptr, workspace);
     GEOSSL_LAUNCH_CHECK();
     tc::filter_bwd_tc_reduce_kernel<<<(tc::Part::kFloats + 255) / 256, 256, 0, as_stream(stream)>>>(workspace, kNumSM, G, gw1, gb1,
                                                                                                    gw2, gb2);

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256)
 pair_index_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const float* __restrict__ edge_dist,
                   int n_atoms, int32_t* __restrict__ pair_deg, const int32_t* __restrict__ pair_rowptr,
                   int32_t* __restrict__ pair_of_edge, int32_t* __restrict__ pair_e1, int32_t* __restrict__ pair_e2,
-                  float* __restrict__ pair_dist) {
+                  int2* __restrict__ pair_atoms, float* __restrict__ pair_dist) {
     const int lane = threadIdx.x & 31;
     const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (t >= n_atoms) return;
@@ -212,6 +212,7 @@ pair_index_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                 pair_of_edge[e] = u;
                 pair_e1[u] = e;
                 pair_e2[u] = (s < t) ? rev : -1;
+                pair_atoms[u] = make_int2(s, (s < t && rev >= 0) ? t : ~t);       // ~t: no reverse direction
                 pair_dist[u] = edge_dist[e];
             } else {
                 // reverse edge (t -> s) sits in row s among the prefix of sources < s, every one of which is canonical
@@ -344,24 +345,25 @@ int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_
 }
 
 int geossl_pair_index(const int32_t* rowptr, const int32_t* src, const float* edge_dist, int64_t n_atoms, int32_t* scratch,
-                      int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2, float* pair_dist,
-                      void* stream) {
+                      int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2, int32_t* pair_atoms,
+                      float* pair_dist, void* stream) {
     GEOSSL_REQUIRE(pair_rowptr && scratch, "null pair_rowptr/scratch");
     cudaStream_t st = as_stream(stream);
     if (n_atoms == 0) {
         GEOSSL_CUDA(cudaMemsetAsync(pair_rowptr, 0, sizeof(int32_t), st));
         return 0;
     }
-    GEOSSL_REQUIRE(rowptr && src && edge_dist && pair_of_edge && pair_e1 && pair_e2 && pair_dist, "null input");
+    GEOSSL_REQUIRE(rowptr && src && edge_dist && pair_of_edge && pair_e1 && pair_e2 && pair_atoms && pair_dist, "null input");
+    GEOSSL_REQUIRE((reinterpret_cast<uintptr_t>(pair_atoms) & 7) == 0, "pair_atoms must be 8-byte aligned");
     const int threads = 256;
     const int blocks = (int)((n_atoms * 32 + threads - 1) / threads);
     pair_index_kernel<0><<<blocks, threads, 0, st>>>(rowptr, src, edge_dist, (int)n_atoms, scratch, nullptr, nullptr, nullptr,
-                                                     nullptr, nullptr);
+                                                     nullptr, nullptr, nullptr);
     GEOSSL_LAUNCH_CHECK();
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(scratch, (int)n_atoms, pair_rowptr);
     GEOSSL_LAUNCH_CHECK();
     pair_index_kernel<1><<<blocks, threads, 0, st>>>(rowptr, src, edge_dist, (int)n_atoms, nullptr, pair_rowptr, pair_of_edge,
-                                                     pair_e1, pair_e2, pair_dist);
+                                                     pair_e1, pair_e2, reinterpret_cast<int2*>(pair_atoms), pair_dist);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

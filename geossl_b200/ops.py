@@ -91,7 +91,7 @@ class RadiusCSR:
         self.rowptr, self.src, self.tgt, self.dist = rowptr, src, tgt, dist
         self.batch, self.graph_ptr = batch, graph_ptr
         self.t_rowptr = self.t_eid = self.t_tgt = None
-        self.pair_rowptr = self.pair_of_edge = self.pair_e1 = self.pair_e2 = self.pair_dist = None
+        self.pair_rowptr = self.pair_of_edge = self.pair_e1 = self.pair_e2 = self.pair_atoms = self.pair_dist = None
         self._n_edges = None
         self._exact = None
 
@@ -142,10 +142,11 @@ class RadiusCSR:
             self.pair_e1 = torch.empty(self.capacity, dtype=torch.int32, device=dev)
             self.pair_e2 = torch.empty(self.capacity, dtype=torch.int32, device=dev)
             self.pair_dist = torch.empty(self.capacity, dtype=torch.float32, device=dev)
+            self.pair_atoms = torch.empty((self.capacity, 2), dtype=torch.int32, device=dev)
             scratch = torch.empty(n + 1, dtype=torch.int32, device=dev)
             check(_lib.load().geossl_pair_index(_p(self.rowptr), _p(self.src), _p(self.dist), n, _p(scratch), _p(self.pair_rowptr),
-                                                _p(self.pair_of_edge), _p(self.pair_e1), _p(self.pair_e2), _p(self.pair_dist),
-                                                _stream()), "pair_index")
+                                                _p(self.pair_of_edge), _p(self.pair_e1), _p(self.pair_e2), _p(self.pair_atoms),
+                                                _p(self.pair_dist), _stream()), "pair_index")
         return self
 
     def exact(self):
@@ -383,10 +384,10 @@ class CFConvLayer(torch.autograd.Function):
         if ctx.mode != "simt" and F_ == 128 and G <= 63:
             ws = torch.empty(lib.geossl_filter_bwd_tc_workspace(), dtype=torch.float32, device=x.device)
             dist, count = (g.pair_dist, g.n_pairs_dev) if ctx.pairs else (g.dist, g.n_edges_dev)
-            e1, e2 = (g.pair_e1, g.pair_e2) if ctx.pairs else (None, None)
+            pa = g.pair_atoms if ctx.pairs else None
             _timed("filter_bwd", lambda: lib.geossl_filter_bwd_tc(
                 _p(dist), _p(count), g.capacity, _p(offset), float(ctx.coeff), float(ctx.cutoff), G, F_, _p(w1), _p(b1),
-                _p(w2), _p(x), _p(grad_out), _p(g.src), _p(g.tgt), _p(e1), _p(e2), _p(ws), _p(gw1), _p(gb1), _p(gw2), _p(gb2),
+                _p(w2), _p(x), _p(grad_out), _p(g.src), _p(g.tgt), _p(pa), _p(ws), _p(gw1), _p(gb1), _p(gw2), _p(gb2),
                 _stream()))
             return gx, gw1, gb1, gw2, gb2, None, None, None, None
         gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)

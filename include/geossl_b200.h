@@ -74,11 +74,13 @@ int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_
  *   pair_rowptr  (n_atoms+1)  pairs owned by each target row; pair_rowptr[n_atoms] = U stays on the device
  *   pair_of_edge (capacity)   pair id of every directed edge (the filt_row map of geossl_cfconv_*)
  *   pair_e1, pair_e2 (capacity) canonical edge id of pair u and its reverse edge id (or -1)
+ *   pair_atoms   (2*capacity, 8-byte aligned) (s, t) of pair u's canonical edge s -> t; t is stored as ~t (negative)
+ *                             when the reverse direction t -> s does not exist
  *   pair_dist    (capacity)   edge length of pair u
  * scratch: n_atoms int32.  Deterministic, atomic free, no host sync. */
 int geossl_pair_index(const int32_t* rowptr, const int32_t* src, const float* edge_dist, int64_t n_atoms, int32_t* scratch,
-                      int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2, float* pair_dist,
-                      void* stream);
+                      int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2, int32_t* pair_atoms,
+                      float* pair_dist, void* stream);
 
 /* Device-side batch assembly: all ordered atom pairs of every molecule in itertools order (combination: i<j,
  * permutation: i!=j), offset by the cumulative atom count -- AtomTupleExtractor + BatchAtomTuple.from_data_list
@@ -158,15 +160,16 @@ int geossl_filter_bwd(const float* edge_dist, const int32_t* n_edges_dev, int64_
 /* Same contract as geossl_filter_bwd (x / grad_out / src / edge_tgt form), on the tcgen05 tensor cores:
  * F = 128, G <= 63, operands split into two bf16 parts, weight gradients accumulated in TMEM.
  * workspace: geossl_filter_bwd_tc_workspace() floats.
- * Pair form (pair_e1 / pair_e2 non-NULL, from geossl_pair_index): edge_dist / n_edges_dev / capacity describe the
- * undirected PAIRS, and the filter-output gradient of pair u is formed as the sum over its one or two directions,
- * x[s]*g[t] + x[t]*g[s]; the parameter gradients equal the per-edge form up to fp32 summation order. */
+ * Pair form (pair_atoms non-NULL, from geossl_pair_index; src / edge_tgt are then unused and may be NULL):
+ * edge_dist / n_edges_dev / capacity describe the undirected PAIRS, and the filter-output gradient of pair u is formed
+ * as the sum over its one or two directions, x[s]*g[t] + x[t]*g[s]; the parameter gradients equal the per-edge form up
+ * to fp32 summation order. */
 int64_t geossl_filter_bwd_tc_workspace(void);
 int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int64_t capacity,
                          const float* offset, float coeff, float cutoff, int G, int F,
                          const float* w1, const float* b1, const float* w2,
                          const float* x, const float* grad_out, const int32_t* src, const int32_t* edge_tgt,
-                         const int32_t* pair_e1, const int32_t* pair_e2,
+                         const int32_t* pair_atoms,
                          float* workspace, float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

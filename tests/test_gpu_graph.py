@@ -168,6 +168,12 @@ def test_pair_index_matches_oracle(ng, lo, hi, density):
     assert torch.equal(g.pair_e1[:u].cpu().long(), torch.from_numpy(e1))
     assert torch.equal(g.pair_e2[:u].cpu().long(), torch.from_numpy(e2))
     assert torch.equal(g.pair_dist[:u], g.dist[:e][g.pair_e1[:u].long()])
+    pa = g.pair_atoms[:u].cpu().long()                                            # (s, t) or (s, ~t) of the canonical edge
+    tgt = torch.repeat_interleave(torch.arange(rp.size - 1), torch.from_numpy(np.diff(rp)))
+    s_ref, t_ref = torch.from_numpy(src)[e1], tgt[e1]
+    both = torch.from_numpy(e2) >= 0
+    assert torch.equal(pa[:, 0], s_ref) and torch.equal(torch.where(both, pa[:, 1], ~pa[:, 1]), t_ref)
+    assert torch.equal(pa[:, 1] >= 0, both)
     if e:
         rev = g.pair_e2[:u].long()
         has = rev >= 0
