@@ -177,6 +177,9 @@ def run_product(args):
     groups = [{"params": model.parameters()}] + [{"params": [p for p in h.parameters() if p.requires_grad]} for h in heads]
     opt = torch.optim.Adam(groups, lr=CFG["lr"], fused=True, capturable=not args.no_graph)
     sync = FlatGradAllReduce([p for g in groups for p in g["params"]]) if world > 1 else None
+    if os.environ.get("GEOSSL_PAIR_OWNER_SMALL"):         # tuning only
+        from geossl_b200 import ops as _o
+        _o.PAIR_OWNER_SMALL = os.environ["GEOSSL_PAIR_OWNER_SMALL"] != "0"
     if os.environ.get("GEOSSL_CFCONV_VARIANT"):          # tuning only (profiles/tune_cfconv.py)
         from geossl_b200 import _lib as _l
         _l.load().geossl_debug_set_cfconv_variant(int(os.environ["GEOSSL_CFCONV_VARIANT"]))

@@ -181,16 +181,18 @@ transpose_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
 // Undirected-pair index of a destination-sorted CSR with ascending sources per row.
 // The interaction filter W_e depends on the edge only through its length d_e (schnet.py:186-187), and
 // |pos_j - pos_i| == |pos_i - pos_j| bit for bit, so the two directions of a pair share ONE filter row.  A pair's
-// canonical edge is the direction with source < target; an edge whose reverse was cut by the neighbour limit (or is
-// absent) is its own pair ("orphan").  Row t's pairs are its canonical edges in row order: first the edges with
-// source < t (a prefix of the row, sources ascend), then the orphans with source > t.
-// MODE 0: pair_deg[t]; MODE 1: pair_of_edge / pair_e1 / pair_e2 / pair_dist at pair_rowptr[t] + rank.
+// canonical edge is the direction with source > target (owner_small: the pair lives in the row of its SMALLER atom, so
+// that rows processed in ascending order touch their own block first, as one sequential stream, and later rows find
+// the shared rows in L2) or source < target (owner_small = 0); an edge whose reverse was cut by the neighbour limit (or
+// is absent) is its own pair ("orphan").  Row t's pairs are its canonical edges in row order.
+// MODE 0: pair_deg[t]; MODE 1: canonical edges: pair_of_edge / pair_e1 / pair_e2 / pair_atoms / pair_dist at
+// pair_rowptr[t] + rank; MODE 2: the other direction copies the pair id of its reverse edge.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 pair_index_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const float* __restrict__ edge_dist,
                   int n_atoms, int32_t* __restrict__ pair_deg, const int32_t* __restrict__ pair_rowptr,
                   int32_t* __restrict__ pair_of_edge, int32_t* __restrict__ pair_e1, int32_t* __restrict__ pair_e2,
-                  int2* __restrict__ pair_atoms, float* __restrict__ pair_dist) {
+                  int2* __restrict__ pair_atoms, float* __restrict__ pair_dist, int owner_small) {
     const int lane = threadIdx.x & 31;
     const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (t >= n_atoms) return;
@@ -204,21 +206,18 @@ pair_index_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
             s = __ldg(src + e);
             rev = find_in_row(src, __ldg(rowptr + s), __ldg(rowptr + s + 1), t);      // edge t -> s, or -1
         }
-        const bool canon = e < hi && (s < t || rev < 0);
+        const bool first = owner_small ? (s > t) : (s < t);
+        const bool canon = e < hi && (first || rev < 0);
         const unsigned mask = __ballot_sync(0xffffffffu, canon);
-        if (MODE == 1 && e < hi) {
-            if (canon) {
-                const int u = base + kept + __popc(mask & ((1u << lane) - 1u));
-                pair_of_edge[e] = u;
-                pair_e1[u] = e;
-                pair_e2[u] = (s < t) ? rev : -1;
-                pair_atoms[u] = make_int2(s, (s < t && rev >= 0) ? t : ~t);       // ~t: no reverse direction
-                pair_dist[u] = edge_dist[e];
-            } else {
-                // reverse edge (t -> s) sits in row s among the prefix of sources < s, every one of which is canonical
-                pair_of_edge[e] = pair_rowptr[s] + (rev - __ldg(rowptr + s));
-            }
+        if (MODE == 1 && canon) {
+            const int u = base + kept + __popc(mask & ((1u << lane) - 1u));
+            pair_of_edge[e] = u;
+            pair_e1[u] = e;
+            pair_e2[u] = rev;                                                  // -1: no reverse direction
+            pair_atoms[u] = make_int2(s, rev >= 0 ? t : ~t);
+            pair_dist[u] = edge_dist[e];
         }
+        if (MODE == 2 && e < hi && !canon) pair_of_edge[e] = pair_of_edge[rev];
         kept += __popc(mask);
     }
     if (MODE == 0 && lane == 0) pair_deg[t] = kept;
@@ -345,8 +344,8 @@ int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_
 }
 
 int geossl_pair_index(const int32_t* rowptr, const int32_t* src, const float* edge_dist, int64_t n_atoms, int32_t* scratch,
-                      int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2, int32_t* pair_atoms,
-                      float* pair_dist, void* stream) {
+                      int owner_small, int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2,
+                      int32_t* pair_atoms, float* pair_dist, void* stream) {
     GEOSSL_REQUIRE(pair_rowptr && scratch, "null pair_rowptr/scratch");
     cudaStream_t st = as_stream(stream);
     if (n_atoms == 0) {
@@ -358,12 +357,15 @@ int geossl_pair_index(const int32_t* rowptr, const int32_t* src, const float* ed
     const int threads = 256;
     const int blocks = (int)((n_atoms * 32 + threads - 1) / threads);
     pair_index_kernel<0><<<blocks, threads, 0, st>>>(rowptr, src, edge_dist, (int)n_atoms, scratch, nullptr, nullptr, nullptr,
-                                                     nullptr, nullptr, nullptr);
+                                                     nullptr, nullptr, nullptr, owner_small);
     GEOSSL_LAUNCH_CHECK();
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(scratch, (int)n_atoms, pair_rowptr);
     GEOSSL_LAUNCH_CHECK();
     pair_index_kernel<1><<<blocks, threads, 0, st>>>(rowptr, src, edge_dist, (int)n_atoms, nullptr, pair_rowptr, pair_of_edge,
-                                                     pair_e1, pair_e2, reinterpret_cast<int2*>(pair_atoms), pair_dist);
+                                                     pair_e1, pair_e2, reinterpret_cast<int2*>(pair_atoms), pair_dist, owner_small);
+    GEOSSL_LAUNCH_CHECK();
+    pair_index_kernel<2><<<blocks, threads, 0, st>>>(rowptr, src, edge_dist, (int)n_atoms, nullptr, pair_rowptr, pair_of_edge,
+                                                     nullptr, nullptr, nullptr, nullptr, owner_small);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -21,6 +21,12 @@
 namespace geossl {
 namespace tc {
 
+__device__ long long* g_trace_lin = nullptr;   // optional clock64() trace of CTA 0 (geossl_debug_set_trace_linear)
+__device__ __forceinline__ void trace_l(int event) {
+    long long* t = g_trace_lin;
+    if (t != nullptr && blockIdx.x == 0 && threadIdx.x == 0) t[event] = clock64();
+}
+
 constexpr int kNR = 64;                   // rows per tile
 constexpr int kNBlkW = 128 * 128;         // [128 rows x 64 k] 16-bit weight block
 constexpr int kNBlkT = kNR * 128;         // [64 rows x 64 k] 16-bit tile block
@@ -88,6 +94,7 @@ __global__ void __launch_bounds__(256, 2)
 linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __restrict__ w_image, const float* __restrict__ bias,
                  int pre_ssp, const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y) {
     extern __shared__ uint8_t smem_raw[];
+    trace_l(0);
     uint8_t* smem = align1024(smem_raw);
     using L = LinLayout;
     const uint32_t sbase = smem_u32(smem);
@@ -116,9 +123,11 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
 
     const int64_t n_tiles = (n_rows + kNR - 1) / kNR;
     uint32_t phase = 0;
+    trace_l(1);
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t row0 = t * kNR;
         stage_rows_kmajor<FP16>(X, row0, n_rows, pre_ssp != 0, smem + L::X, smem + L::X + 2 * kNBlkT);
+        trace_l(2);
         // epilogue operands do not depend on the MMA: fetch them now so their latency hides behind it
         float zr[32], rr[32];
         if (Z) {
@@ -131,8 +140,10 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
         }
         fence_proxy_async();
         __syncthreads();
+        trace_l(3);
         if (warp == 0) {                                       // whole warp (uniform operands); the elected lane issues
-            mbar_wait(wbar, 0);                                // (completes once; later tiles pass immediately)
+            mbar_wait(wbar, 0);
+            trace_l(4);                                // (completes once; later tiles pass immediately)
             tc_fence_after();
             const uint64_t wh = desc_k_sw128(sbase + L::W), wl = desc_k_sw128(sbase + L::W + 2 * kNBlkW);
             const uint64_t xh = desc_k_sw128(sbase + L::X), xl = desc_k_sw128(sbase + L::X + 2 * kNBlkT);
@@ -149,6 +160,7 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        trace_l(5);
         float v[32];
         tmem_ld32(tmem + lane_base + eh * 32, v);          // lane = output feature f, columns = rows eh*32..+31
         tc_fence_before();
@@ -163,6 +175,7 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
             }
         }
         __syncthreads();                                   // TMEM / X tile reuse by the next tile
+        trace_l(6);
     }
     tc_fence_before();
     __syncthreads();
@@ -170,6 +183,7 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
         __syncwarp();
         tmem_dealloc(tmem, 64);
     }
+    trace_l(7);
 }
 
 // ------------------------------------------------------------------------------------------ weight gradient
@@ -347,6 +361,11 @@ int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts
     if (bf16_parts) tc::pack_weight_kernel<false><<<8, 256, 0, as_stream(stream)>>>(weight, transpose_weight, (uint8_t*)image);
     else tc::pack_weight_kernel<true><<<8, 256, 0, as_stream(stream)>>>(weight, transpose_weight, (uint8_t*)image);
     GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_debug_set_trace_linear(long long* device_buffer) {
+    GEOSSL_CUDA(cudaMemcpyToSymbol(tc::g_trace_lin, &device_buffer, sizeof(device_buffer)));
     return 0;
 }
 

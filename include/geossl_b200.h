@@ -69,8 +69,10 @@ int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_
 /* Undirected-pair index of a destination-sorted CSR with ascending sources per row.  The interaction filter depends on an
  * edge only through its length (schnet.py:186-187) and |pos_j - pos_i| == |pos_i - pos_j| bit for bit, so both directions
  * of a pair can share one filter row: the filter network runs over U <= E pairs instead of E edges (U = E/2 when no row
- * is truncated).  Pair u of row t: first the edges with source < t in row order, then the "orphans" (source > t whose
- * reverse edge was cut by max_num_neighbors or is absent).
+ * is truncated).  A pair lives in the row of its smaller atom (owner_small = 1: canonical direction source > target; rows
+ * walked in ascending order then stream their own block first and find shared rows in L2) or of its larger atom
+ * (owner_small = 0); an edge whose reverse was cut by max_num_neighbors or is absent is its own pair ("orphan").  Row t's
+ * pairs are its canonical edges in row order.
  *   pair_rowptr  (n_atoms+1)  pairs owned by each target row; pair_rowptr[n_atoms] = U stays on the device
  *   pair_of_edge (capacity)   pair id of every directed edge (the filt_row map of geossl_cfconv_*)
  *   pair_e1, pair_e2 (capacity) canonical edge id of pair u and its reverse edge id (or -1)
@@ -79,8 +81,8 @@ int geossl_csr_transpose(const int32_t* rowptr, const int32_t* src, const int64_
  *   pair_dist    (capacity)   edge length of pair u
  * scratch: n_atoms int32.  Deterministic, atomic free, no host sync. */
 int geossl_pair_index(const int32_t* rowptr, const int32_t* src, const float* edge_dist, int64_t n_atoms, int32_t* scratch,
-                      int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2, int32_t* pair_atoms,
-                      float* pair_dist, void* stream);
+                      int owner_small, int32_t* pair_rowptr, int32_t* pair_of_edge, int32_t* pair_e1, int32_t* pair_e2,
+                      int32_t* pair_atoms, float* pair_dist, void* stream);
 
 /* Device-side batch assembly: all ordered atom pairs of every molecule in itertools order (combination: i<j,
  * permutation: i!=j), offset by the cumulative atom count -- AtomTupleExtractor + BatchAtomTuple.from_data_list
@@ -119,6 +121,7 @@ int geossl_filter_fwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
 int geossl_debug_set_trace(long long* device_buffer);       /* forward kernel */
 int geossl_debug_set_trace_bwd(long long* device_buffer);   /* backward kernel */
 int geossl_debug_set_trace_head(long long* device_buffer);  /* tensor-core DDM head kernels */
+int geossl_debug_set_trace_linear(long long* device_buffer); /* atom-wise dense layer kernel (8 events) */
 
 /* Self test of the tcgen05 plumbing (descriptors, swizzle, TMEM): one 128 x N x K split-precision GEMM.
  * mode 0: d[m][n] = sum_k a[m][k] b[n][k]  (a (128,K), b (128,K), K in {64,128}, N = 128; K-major operands)

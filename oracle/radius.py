@@ -83,10 +83,10 @@ def transpose_csr(rowptr, src):
     return t_rowptr, order.astype(np.int64), tgt[order]
 
 
-def pair_index(rowptr, src):
+def pair_index(rowptr, src, owner_small=True):
     """Undirected-pair index of a destination-sorted CSR with ascending sources per row (the contract of
-    geossl_pair_index, include/geossl_b200.h): pair ids are assigned row by row to the canonical edges -- source <
-    target, or an edge whose reverse is absent -- in row order.  Returns (pair_rowptr, pair_of_edge, pair_e1, pair_e2)."""
+    geossl_pair_index, include/geossl_b200.h): pair ids are assigned row by row to the canonical edges -- source >
+    target (``owner_small``) or source < target, or an edge whose reverse is absent -- in row order.  Returns (pair_rowptr, pair_of_edge, pair_e1, pair_e2)."""
     rowptr = np.asarray(rowptr, dtype=np.int64)
     src = np.asarray(src, dtype=np.int64)
     n = rowptr.size - 1
@@ -97,10 +97,10 @@ def pair_index(rowptr, src):
     e1, e2 = [], []
     for e, (s, t) in enumerate(zip(src.tolist(), tgt.tolist())):
         rev = eid.get((t, s), -1)
-        if s < t or rev < 0:
+        if (s > t if owner_small else s < t) or rev < 0:
             pair_of_edge[e] = len(e1)
             e1.append(e)
-            e2.append(rev if s < t else -1)
+            e2.append(rev)
             pair_rowptr[t + 1] += 1
     for e, (s, t) in enumerate(zip(src.tolist(), tgt.tolist())):
         if pair_of_edge[e] < 0:

@@ -153,14 +153,16 @@ def test_device_pair_subsampling(option):
 
 
 
+@pytest.mark.parametrize("owner_small", [True, False])
 @pytest.mark.parametrize("ng,lo,hi,density", [(7, 3, 30, 0.05), (4, 40, 70, 0.1), (6, 1, 2, 0.05)])
-def test_pair_index_matches_oracle(ng, lo, hi, density):
+def test_pair_index_matches_oracle(ng, lo, hi, density, owner_small, monkeypatch):
     """geossl_pair_index vs oracle/radius.py::pair_index, including truncated rows (edges without a reverse)."""
     from oracle.radius import pair_index, radius_neighbors
+    monkeypatch.setattr(ops, "PAIR_OWNER_SMALL", owner_small)
     b = synthetic_batch(ng, lo, hi, seed=ng, with_pairs=False, density=density)
     g = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), 10.0, num_graphs=ng).ensure_pairs()
     rp, src = radius_neighbors(b.positions, 10.0, b.batch)
-    prp, poe, e1, e2 = pair_index(rp, src)
+    prp, poe, e1, e2 = pair_index(rp, src, owner_small)
     e, u = src.size, len(e1)
     assert g.num_edges == e and int(g.n_pairs_dev.item()) == u
     assert torch.equal(g.pair_rowptr.cpu().long(), torch.from_numpy(prp))
