@@ -379,7 +379,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             for (int j = 0; j < 16; ++j) {
                 const float av = a[j] + b1f;
                 const float t = ex2_approx(-fabsf(av) * 1.4426950408889634f);       // exp(-|a|)
-                const float r = __frcp_rn(1.0f + t);
+                const float r = rcp_approx(1.0f + t);
                 a[j] = fmaf(lg2_approx(1.0f + t), 0.6931471805599453f, fmaxf(av, 0.f)) - kLog2;
                 sig[j] = av >= 0.f ? r : t * r;                                      // sigmoid(a): three MUFU per element in all
             }

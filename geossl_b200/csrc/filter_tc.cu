@@ -249,10 +249,16 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                 tc_fence_before();
                 warp_arrive(bar(D2_EMPTY));
                 float* out = filt + e0 * kF + r;
+                if (e0 + 32 <= n_edges) {                              // full column group: no per-edge bounds checks
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float c = __shfl_sync(0xffffffffu, myc, j);
-                    if (e0 + j < n_edges) out[(int64_t)j * kF] = (v[j] + b2f) * c;        // 32 lanes -> 128 contiguous bytes
+                    for (int j = 0; j < 32; ++j)
+                        out[j * kF] = (v[j] + b2f) * __shfl_sync(0xffffffffu, myc, j);   // 32 lanes -> 128 contiguous bytes
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float c = __shfl_sync(0xffffffffu, myc, j);
+                        if (e0 + j < n_edges) out[(int64_t)j * kF] = (v[j] + b2f) * c;
+                    }
                 }
                 if (warp == 0) trace(t, 12);
             }

@@ -89,10 +89,10 @@ __device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, i
     for (int c = 0; c < 4; ++c) store_chunk8<FP16>(hi + blk * kNBlkT, lo + blk * kNBlkT, r, (kq & 1) * 32 + c * 8, &v[c * 8]);
 }
 
-template <bool FP16>
+template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R>
 __global__ void __launch_bounds__(256, 2)
 linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __restrict__ w_image, const float* __restrict__ bias,
-                 int pre_ssp, const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y) {
+                 const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y) {
     extern __shared__ uint8_t smem_raw[];
     trace_l(0);
     uint8_t* smem = align1024(smem_raw);
@@ -126,17 +126,19 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
     trace_l(1);
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t row0 = t * kNR;
-        stage_rows_kmajor<FP16>(X, row0, n_rows, pre_ssp != 0, smem + L::X, smem + L::X + 2 * kNBlkT);
+        stage_rows_kmajor<FP16>(X, row0, n_rows, PRE_SSP, smem + L::X, smem + L::X + 2 * kNBlkT);
         trace_l(2);
         // epilogue operands do not depend on the MMA: fetch them now so their latency hides behind it
-        float zr[32], rr[32];
-        if (Z) {
+        const bool full = row0 + kNR <= n_rows;                // warp-uniform: no per-row bounds checks on full tiles
+        const int64_t ebase = (row0 + eh * 32) * 128 + f;
+        float zr[HAS_Z ? 32 : 1], rr[HAS_R ? 32 : 1];
+        if constexpr (HAS_Z) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { const int64_t row = row0 + eh * 32 + j; zr[j] = row < n_rows ? __ldg(Z + row * 128 + f) : 0.f; }
+            for (int j = 0; j < 32; ++j) zr[j] = (full || row0 + eh * 32 + j < n_rows) ? __ldg(Z + ebase + j * 128) : 0.f;
         }
-        if (R) {
+        if constexpr (HAS_R) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { const int64_t row = row0 + eh * 32 + j; rr[j] = row < n_rows ? __ldg(R + row * 128 + f) : 0.f; }
+            for (int j = 0; j < 32; ++j) rr[j] = (full || row0 + eh * 32 + j < n_rows) ? __ldg(R + ebase + j * 128) : 0.f;
         }
         fence_proxy_async();
         __syncthreads();
@@ -166,13 +168,18 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
         tc_fence_before();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const int64_t row = row0 + eh * 32 + j;
-            if (row < n_rows) {
-                float y = v[j] + bf;
-                if (Z) y *= sigmoid_fast(zr[j]);
-                if (R) y += rr[j];
-                Y[row * 128 + f] = y;
-            }
+            float y = v[j] + bf;
+            if constexpr (HAS_Z) y *= sigmoid_fast(zr[j]);
+            if constexpr (HAS_R) y += rr[j];
+            v[j] = y;
+        }
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) Y[ebase + j * 128] = v[j];                // 128 contiguous bytes per warp store
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (row0 + eh * 32 + j < n_rows) Y[ebase + j * 128] = v[j];
         }
         __syncthreads();                                   // TMEM / X tile reuse by the next tile
         trace_l(6);
@@ -352,6 +359,21 @@ static int node_grid(int64_t n_rows) {
 
 using namespace geossl;
 
+template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R>
+static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weight, const float* bias, const float* z, const float* r,
+                            float* y, cudaStream_t st) {
+    const size_t smem = tc::LinLayout::kBytes + 1024;
+    static bool configured = false;                            // one flag per instantiation
+    if (!configured) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        configured = true;
+    }
+    tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R><<<tc::node_grid(n_rows), 256, smem, st>>>(x, n_rows, weight, bias, z, r, y);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" {
 
 int64_t geossl_weight_image_bytes(void) { return tc::kWImage; }
@@ -374,20 +396,21 @@ int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, c
     if (n_rows == 0) return 0;
     const uint8_t* weight = (const uint8_t*)weight_image;
     GEOSSL_REQUIRE(x && weight && y && n_rows > 0, "null pointer");
-    const size_t smem = tc::LinLayout::kBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
-        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    cudaStream_t st = as_stream(stream);
+    const int key = (bf16_parts ? 0 : 8) | (pre_ssp ? 4 : 0) | (act_grad_input ? 2 : 0) | (residual ? 1 : 0);
+#define GEOSSL_LIN_CASE(K, A, B, C, D) case K: return launch_linear_tc<A, B, C, D>(x, n_rows, weight, bias, act_grad_input, residual, y, st);
+    switch (key) {
+        GEOSSL_LIN_CASE(0, false, false, false, false) GEOSSL_LIN_CASE(1, false, false, false, true)
+        GEOSSL_LIN_CASE(2, false, false, true, false)  GEOSSL_LIN_CASE(3, false, false, true, true)
+        GEOSSL_LIN_CASE(4, false, true, false, false)  GEOSSL_LIN_CASE(5, false, true, false, true)
+        GEOSSL_LIN_CASE(6, false, true, true, false)   GEOSSL_LIN_CASE(7, false, true, true, true)
+        GEOSSL_LIN_CASE(8, true, false, false, false)  GEOSSL_LIN_CASE(9, true, false, false, true)
+        GEOSSL_LIN_CASE(10, true, false, true, false)  GEOSSL_LIN_CASE(11, true, false, true, true)
+        GEOSSL_LIN_CASE(12, true, true, false, false)  GEOSSL_LIN_CASE(13, true, true, false, true)
+        GEOSSL_LIN_CASE(14, true, true, true, false)   GEOSSL_LIN_CASE(15, true, true, true, true)
     }
-    const int grid = tc::node_grid(n_rows);
-    if (bf16_parts)
-        tc::linear_tc_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(x, n_rows, weight, bias, pre_ssp, act_grad_input, residual, y);
-    else
-        tc::linear_tc_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(x, n_rows, weight, bias, pre_ssp, act_grad_input, residual, y);
-    GEOSSL_LAUNCH_CHECK();
-    return 0;
+#undef GEOSSL_LIN_CASE
+    return GEOSSL_EINVAL;
 }
 
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::node_grid(n_rows) * tc::kWgPart; }

@@ -252,9 +252,15 @@ __device__ __forceinline__ float ssp_fast(float x) {
     const float t = ex2_approx(-fabsf(x) * 1.4426950408889634f);
     return fmaf(lg2_approx(1.0f + t), 0.6931471805599453f, fmaxf(x, 0.f)) - kLog2;
 }
+// 1 / x on the MUFU unit (1 ulp); __frcp_rn compiles to a range check + slow-path call around the same instruction
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // sigmoid(x) = d/dx softplus(x)
 __device__ __forceinline__ float sigmoid_fast(float x) {
-    return __frcp_rn(1.0f + ex2_approx(-x * 1.4426950408889634f));
+    return rcp_approx(1.0f + ex2_approx(-x * 1.4426950408889634f));
 }
 // 1024-byte aligned view of the dynamic shared memory that keeps the shared address space visible to the compiler
 __device__ __forceinline__ uint8_t* align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }

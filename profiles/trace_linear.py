@@ -19,10 +19,9 @@ for pre_ssp, r in ((False, None), (True, res)):
     a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     image = ops._pack_weight(lin.weight, False, False)
     y = torch.empty_like(x)
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     call = lambda: lib.geossl_linear_tc(ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(image.data_ptr()), ctypes.c_void_p(lin.bias.data_ptr()),
                                         1 if pre_ssp else 0, None, None if r is None else ctypes.c_void_p(r.data_ptr()),
-                                        ctypes.c_void_p(y.data_ptr()), 0, st)
+                                        ctypes.c_void_p(y.data_ptr()), 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(20):
