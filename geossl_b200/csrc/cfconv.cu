@@ -27,6 +27,8 @@ cfconv_gather_kernel(const float* __restrict__ filt, const int32_t* __restrict__
                      const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx_a, const int32_t* __restrict__ idx_b,
                      int n_atoms, float* __restrict__ out) {
     constexpr int LPR = F / 4, EPW = 32 / LPR;
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (row >= n_atoms) return;
@@ -96,10 +98,10 @@ int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
     switch (g_variant & 3) {
-        case 1: cfconv_gather_kernel<F, 8, false, 3><<<blocks, threads, 0, st>>>(filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        case 2: cfconv_gather_kernel<F, 8, false, 2><<<blocks, threads, 0, st>>>(filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        case 3: cfconv_gather_kernel<F, 4, false, 6><<<blocks, threads, 0, st>>>(filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        default: cfconv_gather_kernel<F, 4, false, 4><<<blocks, threads, 0, st>>>(filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
+        case 1: launch_pdl(cfconv_gather_kernel<F, 8, false, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        case 2: launch_pdl(cfconv_gather_kernel<F, 8, false, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        case 3: launch_pdl(cfconv_gather_kernel<F, 4, false, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        default: launch_pdl(cfconv_gather_kernel<F, 4, false, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
     }
     return 0;
 }
@@ -109,10 +111,10 @@ int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, con
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
     switch ((g_variant >> 2) & 3) {
-        case 1: cfconv_gather_kernel<F, 4, true, 4><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        case 2: cfconv_gather_kernel<F, 8, true, 2><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        case 3: cfconv_gather_kernel<F, 4, true, 6><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        default: cfconv_gather_kernel<F, 8, true, 3><<<blocks, threads, 0, st>>>(filt, filt_row, g, tr, te, tt, (int)n, dx);
+        case 1: launch_pdl(cfconv_gather_kernel<F, 4, true, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        case 2: launch_pdl(cfconv_gather_kernel<F, 8, true, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        case 3: launch_pdl(cfconv_gather_kernel<F, 4, true, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        default: launch_pdl(cfconv_gather_kernel<F, 8, true, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
     }
     return 0;
 }

@@ -250,6 +250,8 @@ __global__ void __launch_bounds__(256, 1) ddm_head_fwd_kernel(HeadIn in, float* 
 }
 
 __global__ void ddm_loss_finalize_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ loss) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         float s = 0.f, g = -1.f;
         for (int p = 0; p < n_parts; ++p) { s += workspace[2 * p]; g = fmaxf(g, workspace[2 * p + 1]); }
@@ -429,6 +431,9 @@ ddm_head_bwd_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* 
 template <int H>
 __global__ void ddm_head_reduce_kernel(const float* __restrict__ workspace, int n_parts, geossl_ddm_grads g) {
     using K = HeadCfg<H>;
+    pdl_launch_dependents();
+    pdl_wait();
+
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= K::kPartial) return;
     // four independent chains (fixed association order => still deterministic) keep enough loads in flight
@@ -636,6 +641,9 @@ constexpr int kPrepRows = 8;
 __global__ void __launch_bounds__(256)
 ddm_pair_prep_kernel(HeadIn in, int64_t n_pad, float* __restrict__ prep) {
     __shared__ float sw0[128], sb0[128], sw1[128];
+    pdl_launch_dependents();
+    pdl_wait();
+
     if (threadIdx.x < 128) {
         sw0[threadIdx.x] = __ldg(in.p.in_w0 + threadIdx.x);
         sb0[threadIdx.x] = __ldg(in.p.in_b0 + threadIdx.x);
@@ -735,6 +743,8 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar = sbase + L::BAR;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     int* sU = reinterpret_cast<int*>(smem + L::SC);
     int* sV = sU + 64;
     float* sSig = reinterpret_cast<float*>(sV + 64);
@@ -1151,12 +1161,12 @@ int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     const int grid = head_grid(n_pairs);
     const int64_t n_pad = head_pad(n_pairs);
     float* prep = workspace + head_prep_offset();
-    tc::ddm_pair_prep_kernel<<<(int)((n_pad + 255) / 256), 256, 0, as_stream(stream)>>>(in, n_pad, prep);
+    GEOSSL_CUDA(launch_pdl(tc::ddm_pair_prep_kernel, dim3((unsigned)((n_pad + 255) / 256)), dim3(256), 0, as_stream(stream), in, n_pad, prep));
     GEOSSL_LAUNCH_CHECK();
-    tc::ddm_head_tc_kernel<true, false><<<grid, tc::kHThreads, smem, as_stream(stream)>>>(in, prep, n_pad, nullptr, nullptr, nullptr,
-                                                                                         workspace);
+    GEOSSL_CUDA(launch_pdl(tc::ddm_head_tc_kernel<true, false>, dim3(grid), dim3(tc::kHThreads), smem, as_stream(stream), in,
+                           (const float*)prep, n_pad, (const float*)nullptr, (const float*)nullptr, (float*)nullptr, workspace));
     GEOSSL_LAUNCH_CHECK();
-    ddm_loss_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(workspace, grid, loss);
+    GEOSSL_CUDA(launch_pdl(ddm_loss_finalize_kernel, dim3(1), dim3(32), 0, as_stream(stream), (const float*)workspace, grid, loss));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
@@ -1184,13 +1194,13 @@ int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     const int grid = head_grid(n_pairs);
     const int64_t n_pad = head_pad(n_pairs);
     float* prep = workspace + head_prep_offset();
-    tc::ddm_pair_prep_kernel<<<(int)((n_pad + 255) / 256), 256, 0, as_stream(stream)>>>(in, n_pad, prep);
+    GEOSSL_CUDA(launch_pdl(tc::ddm_pair_prep_kernel, dim3((unsigned)((n_pad + 255) / 256)), dim3(256), 0, as_stream(stream), in, n_pad, prep));
     GEOSSL_LAUNCH_CHECK();
-    tc::ddm_head_tc_kernel<false, true><<<grid, tc::kHThreads, smem, as_stream(stream)>>>(in, prep, n_pad, loss_aux, grad_loss, grad_h,
-                                                                                         workspace);
+    GEOSSL_CUDA(launch_pdl(tc::ddm_head_tc_kernel<false, true>, dim3(grid), dim3(tc::kHThreads), smem, as_stream(stream), in,
+                           (const float*)prep, n_pad, loss_aux, grad_loss, grad_h, workspace));
     GEOSSL_LAUNCH_CHECK();
     const int n = HeadCfg<128>::kPartial;
-    ddm_head_reduce_kernel<128><<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(workspace, grid, g);
+    GEOSSL_CUDA(launch_pdl(ddm_head_reduce_kernel<128>, dim3((n + 255) / 256), dim3(256), 0, as_stream(stream), (const float*)workspace, grid, g));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -84,6 +84,8 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
     auto bar = [&](int i) { return bar0 + 8u * i; };
     float* sOff = reinterpret_cast<float*>(smem + L::OFF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
+    pdl_wait();
 
     int64_t n_edges = (int64_t)(*n_edges_dev);
     if (n_edges > capacity) n_edges = capacity;
@@ -448,6 +450,8 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
 __global__ void filter_bwd_tc_reduce_kernel(const float* __restrict__ workspace, int n_parts, int G,
                                             float* __restrict__ gw1, float* __restrict__ gb1,
                                             float* __restrict__ gw2, float* __restrict__ gb2) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Part::kFloats) return;
     const bool w1_slot = idx >= Part::kW1 && idx < Part::kB2;
@@ -501,16 +505,18 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    if (pair_atoms)
-        tc::filter_bwd_tc_kernel<true><<<kNumSM, tc::kBwdThreads, smem, as_stream(stream)>>>(
-            edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt,
-            reinterpret_cast<const int2*>(pair_atoms), workspace);
-    else
-        tc::filter_bwd_tc_kernel<false><<<kNumSM, tc::kBwdThreads, smem, as_stream(stream)>>>(
-            edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt, nullptr, workspace);
+    if (pair_atoms) {
+        GEOSSL_CUDA(launch_pdl(tc::filter_bwd_tc_kernel<true>, dim3(kNumSM), dim3(tc::kBwdThreads), smem, as_stream(stream),
+                               edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt,
+                               reinterpret_cast<const int2*>(pair_atoms), workspace));
+    } else {
+        GEOSSL_CUDA(launch_pdl(tc::filter_bwd_tc_kernel<false>, dim3(kNumSM), dim3(tc::kBwdThreads), smem, as_stream(stream),
+                               edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, x, grad_out, src, edge_tgt,
+                               (const int2*)nullptr, workspace));
+    }
     GEOSSL_LAUNCH_CHECK();
-    tc::filter_bwd_tc_reduce_kernel<<<(tc::Part::kFloats + 255) / 256, 256, 0, as_stream(stream)>>>(workspace, kNumSM, G, gw1, gb1,
-                                                                                                   gw2, gb2);
+    GEOSSL_CUDA(launch_pdl(tc::filter_bwd_tc_reduce_kernel, dim3((tc::Part::kFloats + 255) / 256), dim3(256), 0, as_stream(stream),
+                           workspace, (int)kNumSM, G, gw1, gb1, gw2, gb2));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -71,6 +71,8 @@ filter_fwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
     float* sB2 = reinterpret_cast<float*>(smem + L::B2);
     float* sOff = reinterpret_cast<float*>(smem + L::OFF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
+    pdl_wait();
 
     int64_t n_edges = (int64_t)(*n_edges_dev);
     if (n_edges > capacity) n_edges = capacity;
@@ -445,12 +447,13 @@ int geossl_filter_fwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    if (bf16_parts)
-        tc::filter_fwd_tc_kernel<false><<<grid, tc::kThreads, smem, as_stream(stream)>>>(edge_dist, n_edges_dev, capacity, offset, coeff,
-                                                                                        cutoff, G, w1, b1, w2, b2, filt);
-    else
-        tc::filter_fwd_tc_kernel<true><<<grid, tc::kThreads, smem, as_stream(stream)>>>(edge_dist, n_edges_dev, capacity, offset, coeff,
-                                                                                       cutoff, G, w1, b1, w2, b2, filt);
+    if (bf16_parts) {
+        GEOSSL_CUDA(launch_pdl(tc::filter_fwd_tc_kernel<false>, dim3(grid), dim3(tc::kThreads), smem, as_stream(stream), edge_dist,
+                               n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, b2, filt));
+    } else {
+        GEOSSL_CUDA(launch_pdl(tc::filter_fwd_tc_kernel<true>, dim3(grid), dim3(tc::kThreads), smem, as_stream(stream), edge_dist,
+                               n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2, b2, filt));
+    }
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -45,6 +45,8 @@ constexpr int kWImage = 4 * kNBlkW;                   // bytes of a packed weigh
 template <bool FP16>
 __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ Wt, int trans, uint8_t* __restrict__ image) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * 16; idx += gridDim.x * blockDim.x) {
         float v[8];
         int n, c;
@@ -103,15 +105,19 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
 
     // weights: the packed A-operand image (rows n, K-major, split) arrives by bulk async copy while the X tile is staged
     const uint32_t wbar = bar + 8;
+    pdl_launch_dependents();
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_init(wbar, 1);
         fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, 64);
+    pdl_wait();                                                // everything above overlaps the previous kernel's tail
+    if (tid == 0) {
         mbar_expect_tx(wbar, kWImage);
 #pragma unroll
         for (int c = 0; c < 4; ++c) bulk_g2s(sbase + L::W + c * kNBlkW, w_image + c * kNBlkW, kNBlkW, wbar);
     }
-    if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, 64);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -242,6 +248,8 @@ __global__ void __launch_bounds__(256, 2)
 linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, int64_t n_rows, int pre_ssp,
                        float* __restrict__ workspace) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_launch_dependents();
+    pdl_wait();
     uint8_t* smem = align1024(smem_raw);
     using L = WgLayout;
     const uint32_t sbase = smem_u32(smem);
@@ -326,6 +334,9 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
 __global__ void __launch_bounds__(256)
 linear_wgrad_reduce_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ gw, float* __restrict__ gb) {
     __shared__ float red[8][33];
+    pdl_launch_dependents();
+    pdl_wait();
+
     const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int idx = blockIdx.x * 32 + o;
     float s0 = 0.f, s1 = 0.f;
@@ -369,7 +380,8 @@ static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weigh
                                          (int)smem));
         configured = true;
     }
-    tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R><<<tc::node_grid(n_rows), 256, smem, st>>>(x, n_rows, weight, bias, z, r, y);
+    GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R>, dim3(tc::node_grid(n_rows)), dim3(256), smem, st,
+                           x, n_rows, weight, bias, z, r, y));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
@@ -380,8 +392,11 @@ int64_t geossl_weight_image_bytes(void) { return tc::kWImage; }
 
 int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts, void* image, void* stream) {
     GEOSSL_REQUIRE(weight && image, "null pointer");
-    if (bf16_parts) tc::pack_weight_kernel<false><<<8, 256, 0, as_stream(stream)>>>(weight, transpose_weight, (uint8_t*)image);
-    else tc::pack_weight_kernel<true><<<8, 256, 0, as_stream(stream)>>>(weight, transpose_weight, (uint8_t*)image);
+    if (bf16_parts) {
+        GEOSSL_CUDA(launch_pdl(tc::pack_weight_kernel<false>, dim3(8), dim3(256), 0, as_stream(stream), weight, transpose_weight, (uint8_t*)image));
+    } else {
+        GEOSSL_CUDA(launch_pdl(tc::pack_weight_kernel<true>, dim3(8), dim3(256), 0, as_stream(stream), weight, transpose_weight, (uint8_t*)image));
+    }
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
@@ -425,9 +440,9 @@ int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, 
         configured = true;
     }
     const int grid = tc::node_grid(n_rows);
-    tc::linear_wgrad_tc_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(grad_y, x, n_rows, pre_ssp, workspace);
+    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid), dim3(256), smem, as_stream(stream), grad_y, x, n_rows, pre_ssp, workspace));
     GEOSSL_LAUNCH_CHECK();
-    tc::linear_wgrad_reduce_kernel<<<(tc::kWgPart + 31) / 32, 256, 0, as_stream(stream)>>>(workspace, grid, grad_weight, grad_bias);
+    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_reduce_kernel, dim3((tc::kWgPart + 31) / 32), dim3(256), 0, as_stream(stream), workspace, grid, grad_weight, grad_bias));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
