@@ -30,8 +30,11 @@ cfconv_gather_kernel(const float* __restrict__ filt, const int32_t* __restrict__
     pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31;
-    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (row >= n_atoms) return;
+    const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (wid >= n_atoms) return;
+    // Forward walks the rows LAST to first: the filter tensor was just written front to back by the filter kernel, so its
+    // tail is what the L2 still holds; reading in write order would evict exactly the lines about to be needed.
+    const int row = TRANSPOSED ? wid : n_atoms - 1 - wid;
     const int f = (lane % LPR) * 4, sub = lane / LPR;
     const int b = __ldg(ptr + row), end = __ldg(ptr + row + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
