@@ -24,7 +24,7 @@ import torch  # noqa: E402
 METRIC = "GeoSSL-DDM SchNet train molecules/s at 1/2/4/8 B200; cfconv % HBM roofline"
 CFG = dict(batch_per_gpu=256, atoms=30, cutoff=10.0, num_gaussians=50, hidden=128, filters=128, interactions=6,
            sigma_levels=50, anneal_power=2.0, pos_sigma=0.3, lr=5e-4)
-NCU_TRAFFIC_CFCONV_FWD = 234.14e6 + 4.98e6     # bytes per launch of the bench workload (profiles/r01_v10_ncu_full.txt)
+NCU_TRAFFIC_CFCONV_FWD = 123.68e6 + 4.48e6     # bytes per launch of the bench workload (profiles/r01_v26_ncu_full.txt)
 WORKLOAD = ("configs[1]: SchNet GeoSSL-DDM pretraining step, synthetic Molecule3D-shaped conformers, "
             "batch 256 per GPU x 30 atoms, cutoff 10 A, 50 RBF, hidden 128, 6 interactions, data-parallel")
 
@@ -297,19 +297,29 @@ def run_product(args):
     g = ops.radius_csr(pos2, torch.cat([b0.batch, b0.batch + B]), CFG["cutoff"], num_graphs=2 * B)
     n_atoms, n_edges, F_, G = pos2.shape[0], g.num_edges, CFG["filters"], CFG["num_gaussians"]
     n_pairs = b0.super_edge_index.shape[1]
-    cf_bytes = 4 * F_ * n_edges + 2 * 4 * F_ * n_atoms + 4 * n_edges + 4 * (n_atoms + 1)
+    # filter rows: one per undirected atom pair when the two directions share it (ops.SHARE_PAIR_FILTERS), else one per edge
+    shared = ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE != "simt"
+    n_rows_w = int(g.ensure_pairs().n_pairs_dev.item()) if shared else n_edges
+    # algorithmic bytes of cfconv forward: every filter row once + x in + m out + src ids (+ the pair map) + rowptr
+    cf_bytes = 4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + 4 * n_edges * (2 if shared else 1) + 4 * (n_atoms + 1)
+    cf_bytes_per_edge_form = 4 * F_ * n_edges + 2 * 4 * F_ * n_atoms + 4 * n_edges + 4 * (n_atoms + 1)   # 551 B/edge
     roof = None
     others = {}
     if "cfconv_fwd" in ktimes:
         t = ktimes["cfconv_fwd"]["mean_ms"] / 1e3
         ach = cf_bytes / t / 1e9
-        roof = {"kernel": "cfconv_fwd_kernel<128,4>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_CFCONV_FWD if n_edges > 400_000 else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_v10_ncu_full.txt",
+        roof = {"kernel": "cfconv_gather_kernel<128,4,false,4> (cfconv forward)", "bound": "hbm", "achieved": ach,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_CFCONV_FWD if (shared and n_edges > 400_000) else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_v26_ncu_full.txt",
                 "peak_source": peaks["src"],
-                "algorithmic_bytes_per_launch": cf_bytes, "mean_ms": 1e3 * t, "launches_timed": ktimes["cfconv_fwd"]["n"]}
-        flops = {"filter_fwd": n_edges * (2 * G * F_ + 2 * F_ * F_),
-                 "filter_bwd": n_edges * (2 * G * F_ + 2 * (2 * F_ * F_) + 2 * G * F_ + 2 * F_ * F_),
+                "algorithmic_bytes_per_launch": cf_bytes, "filter_rows_per_launch": n_rows_w, "mean_ms": 1e3 * t,
+                "launches_timed": ktimes["cfconv_fwd"]["n"],
+                "per_edge_form": {"bytes_per_launch": cf_bytes_per_edge_form, "achieved": cf_bytes_per_edge_form / t / 1e9,
+                                  "note": "SURVEY 8d figure (551 B/edge, one filter row per DIRECTED edge) over the same duration: "
+                                          "the rate a per-edge kernel would need to match this one; not a DRAM rate"}}
+        flops = {"filter_fwd": n_rows_w * (2 * G * F_ + 2 * F_ * F_),
+                 "filter_bwd": n_rows_w * (2 * G * F_ + 2 * (2 * F_ * F_) + 2 * G * F_ + 2 * F_ * F_),
                  "ddm_head_fwd": n_pairs * 50_048, "ddm_head_bwd": n_pairs * 3 * 50_048}
         for k, fl in flops.items():
             if k in ktimes:
@@ -317,11 +327,12 @@ def run_product(args):
                 others[k] = {"bound": "tensor", "achieved": fl / tt / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                              "frac": fl / tt / 1e12 / peaks["bf16_tflops_sustained"], "mean_ms": 1e3 * tt,
                              "share_of_step": ktimes[k]["total_ms"] / n_k / (ms / args.steps),
-                             "note": "3 split-precision MMAs per product (fp32-grade); useful FLOPs against the bf16 tensor peak"
-                             if k.startswith("filter") else "fp32 SIMT kernel against the bf16 tensor peak"}
+                             "note": ("3 split-precision MMAs per product (fp32-grade); FLOPs of the rows actually processed "
+                                      f"({n_rows_w} filter rows for {n_edges} edges) against the bf16 tensor peak")
+                             if k.startswith("filter") else "3 split-precision MMAs per product; useful FLOPs against the bf16 tensor peak"}
         if "cfconv_bwd_x" in ktimes:
             tt = ktimes["cfconv_bwd_x"]["mean_ms"] / 1e3
-            bb = 4 * F_ * n_edges + 2 * 4 * F_ * n_atoms + 8 * n_edges + 4 * (n_atoms + 1)
+            bb = 4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + 4 * n_edges * (3 if shared else 2) + 4 * (n_atoms + 1)
             others["cfconv_bwd_x"] = {"bound": "hbm", "achieved": bb / tt / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                       "frac": bb / tt / 1e9 / peaks["hbm_gbs"], "mean_ms": 1e3 * tt,
                                       "share_of_step": ktimes["cfconv_bwd_x"]["total_ms"] / n_k / (ms / args.steps)}
@@ -338,7 +349,8 @@ def run_product(args):
             "config": {"workload": WORKLOAD, **CFG, "global_batch": world * B, "atoms_per_launch": n_atoms, "edges_per_launch": n_edges, "views_stacked": 2,
                        "pairs": n_pairs, "parallelism": f"dp{world}", "optimizer": "torch.optim.Adam(fused)", "launch": "eager" if args.no_graph else "whole step captured in one CUDA graph",
                        "kernel_timing": f"CUDA-event brackets over {n_k} eager steps of the same workload ({ms_eager / n_k:.2f} ms/step eager)",
-                       "l2": f"{args.pool} distinct batches cycled; per-step working set (6 x {4 * F_ * n_edges / 1e6:.0f} MB filter "
+                       "filter_rows_per_launch": n_rows_w,
+                       "l2": f"{args.pool} distinct batches cycled; per-step working set (6 x {4 * F_ * n_rows_w / 1e6:.0f} MB filter "
                              "tensors) exceeds the 126 MB L2", "position_noise": "device generator"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -75,6 +75,86 @@ cfconv_gather_kernel(const float* __restrict__ filt, const int32_t* __restrict__
     if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
 }
 
+// Windowed edition: the ROWS consecutive rows of a CTA belong to one or two molecules, so the atoms they gather from sit
+// in a short contiguous index range.  That window of `v` (x or grad_out rows) is staged in shared memory once per CTA and
+// the per-edge gathers read it from there; the L2 -> SM traffic of the gather operand drops by ~ROWS x and only the filter
+// rows remain as long-latency loads.  Atoms outside the window (large graphs) fall back to the global gather.
+template <int F, int UNROLL, bool TRANSPOSED, int ROWS, int WIN, int MINB>
+__global__ void __launch_bounds__(ROWS * 32, MINB)
+cfconv_gather_win_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ v,
+                         const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx_a, const int32_t* __restrict__ idx_b,
+                         int n_atoms, float* __restrict__ out) {
+    constexpr int LPR = F / 4, EPW = 32 / LPR;
+    __shared__ __align__(16) float sv[WIN * F];
+    __shared__ int s_first[ROWS], s_last[ROWS];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n_blocks = gridDim.x;
+    // forward walks the CTAs last to first (the tail of the freshly written filter tensor is what L2 still holds)
+    const int blk = TRANSPOSED ? blockIdx.x : n_blocks - 1 - blockIdx.x;
+    const int row = blk * ROWS + w;
+    const bool live = row < n_atoms;
+    int b = 0, end = 0;
+    if (live) { b = __ldg(ptr + row); end = __ldg(ptr + row + 1); }
+    if (lane == 0) {                                               // gather indices ascend within a row
+        s_first[w] = (end > b) ? __ldg(idx_b + b) : 0x7fffffff;
+        s_last[w] = (end > b) ? __ldg(idx_b + end - 1) : -1;
+    }
+    __syncthreads();
+    int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) { lo = min(lo, s_first[r]); hi = max(hi, s_last[r]); }
+    const int cnt = (hi >= lo) ? min(hi - lo + 1, WIN) : 0;
+    for (int i = threadIdx.x; i < cnt * LPR; i += ROWS * 32)
+        *reinterpret_cast<float4*>(sv + i * 4) = ldg4(v + (int64_t)lo * F + i * 4);
+    __syncthreads();
+    if (!live) return;
+    const int f = (lane % LPR) * 4, sub = lane / LPR;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = b; base < end; base += 32) {
+        const int mine = base + lane;
+        int my_a = 0, my_b = 0;
+        if (mine < end) {
+            const int e = TRANSPOSED ? __ldg(idx_a + mine) : mine;
+            my_a = filt_row ? __ldg(filt_row + e) : e;               // shared filter row of the undirected pair
+            my_b = __ldg(idx_b + mine);
+        }
+        const int n_here = min(32, end - base);
+        for (int k0 = 0; k0 < n_here; k0 += EPW * UNROLL) {          // warp-uniform trip count (shuffles inside)
+            float4 wv[UNROLL];
+            int rb[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int k = k0 + sub + u * EPW;
+                const int ra = __shfl_sync(0xffffffffu, my_a, k & 31);
+                rb[u] = __shfl_sync(0xffffffffu, my_b, k & 31);
+                if (k < n_here) {
+                    wv[u] = ld_stream4(filt + (int64_t)ra * F + f);
+                } else {
+                    wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    rb[u] = lo;                                      // any staged row: multiplied by zero
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int o = rb[u] - lo;
+                const float4 xv = (o >= 0 && o < cnt) ? *reinterpret_cast<const float4*>(sv + o * F + f)
+                                                      : ldg4(v + (int64_t)rb[u] * F + f);
+                fma4(acc, xv, wv[u]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
+}
+
 template <int F>
 __global__ void __launch_bounds__(256)
 cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, const int32_t* __restrict__ rowptr,
@@ -93,18 +173,25 @@ cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, co
     }
 }
 
-static int g_variant = 0;   // tuning switch (geossl_debug_set_cfconv_variant)
+// Tuning switch (geossl_debug_set_cfconv_variant): bits 0-2 forward, 3-5 backward.  0 = plain gather (default);
+// 4-6 = windowed edition.  Measured on the bench workload the windowed kernels are not faster (forward 41 vs 46 us alone,
+// backward 43 vs 33 us; whole step 84.2 k vs 86.1 k molecules/s), i.e. the gather operand's L2 traffic is not the limiter.
+static int g_variant = 0;
 
 template <int F>
 int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src, int64_t n,
                float* out, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    switch (g_variant & 3) {
+    constexpr int kWin = 8192 / F;                                  // 32 KB of staged rows: 64 atoms at F = 128
+    switch (g_variant & 7) {
         case 1: launch_pdl(cfconv_gather_kernel<F, 8, false, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 2: launch_pdl(cfconv_gather_kernel<F, 8, false, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 3: launch_pdl(cfconv_gather_kernel<F, 4, false, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        default: launch_pdl(cfconv_gather_kernel<F, 4, false, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
+        case 0: launch_pdl(cfconv_gather_kernel<F, 4, false, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        case 5: launch_pdl(cfconv_gather_win_kernel<F, 4, false, 8, kWin, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        case 6: launch_pdl(cfconv_gather_win_kernel<F, 4, false, 8, kWin, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        default: launch_pdl(cfconv_gather_win_kernel<F, 8, false, 8, kWin, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
     }
     return 0;
 }
@@ -113,11 +200,15 @@ int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, con
                  int64_t n, float* dx, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    switch ((g_variant >> 2) & 3) {
+    constexpr int kWin = 8192 / F;
+    switch ((g_variant >> 3) & 7) {
         case 1: launch_pdl(cfconv_gather_kernel<F, 4, true, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 2: launch_pdl(cfconv_gather_kernel<F, 8, true, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 3: launch_pdl(cfconv_gather_kernel<F, 4, true, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        default: launch_pdl(cfconv_gather_kernel<F, 8, true, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
+        case 0: launch_pdl(cfconv_gather_kernel<F, 8, true, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        case 5: launch_pdl(cfconv_gather_win_kernel<F, 4, true, 8, kWin, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        case 6: launch_pdl(cfconv_gather_win_kernel<F, 4, true, 8, kWin, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        default: launch_pdl(cfconv_gather_win_kernel<F, 8, true, 8, kWin, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
     }
     return 0;
 }

@@ -29,8 +29,8 @@ def timeit(fn, reps=40):
 
 
 print(f"atoms {n}, edges {g.num_edges}, pairs {int(g.n_pairs_dev.item())}")
-for variant in (0, 1, 2, 3):
-    lib.geossl_debug_set_cfconv_variant(variant)
+for variant in (0, 4, 5, 6):
+    lib.geossl_debug_set_cfconv_variant(variant | (variant << 3))
     for shared in (True, False):
         row = g.pair_of_edge if shared else None
         f = timeit(lambda i: ops._cfconv_fwd(xs[i % 4], filts[i % 4], g, row))
