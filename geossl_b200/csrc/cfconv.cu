@@ -75,6 +75,64 @@ cfconv_gather_kernel(const float* __restrict__ filt, const int32_t* __restrict__
     if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
 }
 
+// Deep edition: the kernel is latency bound (DRAM 33 %, L2 25 % busy; 72 % of issue slots have no eligible warp), so what
+// matters is how many filter-row loads are in flight per SM.  Eight filter rows are requested per step, but the gather
+// operand (an L1/L2 hit) is fetched in two halves so that the register budget still allows four CTAs per SM.
+template <int F, bool TRANSPOSED>
+__global__ void __launch_bounds__(256, 4)
+cfconv_gather_deep_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ v,
+                          const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx_a, const int32_t* __restrict__ idx_b,
+                          int n_atoms, float* __restrict__ out) {
+    constexpr int LPR = F / 4, EPW = 32 / LPR, U = 8;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (wid >= n_atoms) return;
+    const int row = TRANSPOSED ? wid : n_atoms - 1 - wid;
+    const int f = (lane % LPR) * 4, sub = lane / LPR;
+    const int b = __ldg(ptr + row), end = __ldg(ptr + row + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = b; base < end; base += 32) {
+        const int mine = base + lane;
+        int my_a = 0, my_b = 0;
+        if (mine < end) {
+            const int e = TRANSPOSED ? __ldg(idx_a + mine) : mine;
+            my_a = filt_row ? __ldg(filt_row + e) : e;
+            my_b = __ldg(idx_b + mine);
+        }
+        const int cnt = min(32, end - base);
+        for (int k0 = 0; k0 < cnt; k0 += EPW * U) {
+            float4 w[U];
+            int rb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 + sub + u * EPW;
+                const int ra = __shfl_sync(0xffffffffu, my_a, k & 31);
+                rb[u] = __shfl_sync(0xffffffffu, my_b, k & 31);
+                if (k < cnt) w[u] = ld_stream4(filt + (int64_t)ra * F + f);
+                else { w[u] = make_float4(0.f, 0.f, 0.f, 0.f); rb[u] = __shfl_sync(0xffffffffu, my_b, 0); }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xv[u] = ldg4(v + (int64_t)rb[h * 4 + u] * F + f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) fma4(acc, xv[u], w[h * 4 + u]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
+}
+
 // Windowed edition: the ROWS consecutive rows of a CTA belong to one or two molecules, so the atoms they gather from sit
 // in a short contiguous index range.  That window of `v` (x or grad_out rows) is staged in shared memory once per CTA and
 // the per-edge gathers read it from there; the L2 -> SM traffic of the gather operand drops by ~ROWS x and only the filter
@@ -173,10 +231,11 @@ cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, co
     }
 }
 
-// Tuning switch (geossl_debug_set_cfconv_variant): bits 0-2 forward, 3-5 backward.  0 = plain gather (default);
-// 4-6 = windowed edition.  Measured on the bench workload the windowed kernels are not faster (forward 41 vs 46 us alone,
-// backward 43 vs 33 us; whole step 84.2 k vs 86.1 k molecules/s), i.e. the gather operand's L2 traffic is not the limiter.
-static int g_variant = 0;
+// Tuning switch (geossl_debug_set_cfconv_variant): bits 0-2 forward, 3-5 backward.  7 = deep edition (default), 0-3 = plain
+// gather at other unroll / occupancy points, 4-6 = windowed edition.  Measured alone on the bench workload (us, forward /
+// backward): plain 45.9 / 33.4, windowed 41.4 / 43.5, deep 31.1 / 31.3 -- the kernel is latency bound, what pays is filter
+// rows in flight, not less L2 traffic for the gather operand (profiles/tune_cfconv.py).
+static int g_variant = 7 | (7 << 3);
 
 template <int F>
 int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src, int64_t n,
@@ -189,6 +248,7 @@ int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const
         case 2: launch_pdl(cfconv_gather_kernel<F, 8, false, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 3: launch_pdl(cfconv_gather_kernel<F, 4, false, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 0: launch_pdl(cfconv_gather_kernel<F, 4, false, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        case 7: launch_pdl(cfconv_gather_deep_kernel<F, false>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 5: launch_pdl(cfconv_gather_win_kernel<F, 4, false, 8, kWin, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 6: launch_pdl(cfconv_gather_win_kernel<F, 4, false, 8, kWin, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         default: launch_pdl(cfconv_gather_win_kernel<F, 8, false, 8, kWin, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
@@ -206,6 +266,7 @@ int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, con
         case 2: launch_pdl(cfconv_gather_kernel<F, 8, true, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 3: launch_pdl(cfconv_gather_kernel<F, 4, true, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 0: launch_pdl(cfconv_gather_kernel<F, 8, true, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        case 7: launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 5: launch_pdl(cfconv_gather_win_kernel<F, 4, true, 8, kWin, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 6: launch_pdl(cfconv_gather_win_kernel<F, 4, true, 8, kWin, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         default: launch_pdl(cfconv_gather_win_kernel<F, 8, true, 8, kWin, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);

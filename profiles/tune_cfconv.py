@@ -29,11 +29,11 @@ def timeit(fn, reps=40):
 
 
 print(f"atoms {n}, edges {g.num_edges}, pairs {int(g.n_pairs_dev.item())}")
-for variant in (0, 4, 5, 6):
+for variant in (0, 4, 7):
     lib.geossl_debug_set_cfconv_variant(variant | (variant << 3))
     for shared in (True, False):
         row = g.pair_of_edge if shared else None
         f = timeit(lambda i: ops._cfconv_fwd(xs[i % 4], filts[i % 4], g, row))
         bx = timeit(lambda i: ops._cfconv_bwd_x(filts[i % 4], xs[i % 4], g, row))
         print(f"variant {variant} shared={shared}: fwd {f:.1f} us, bwd_x {bx:.1f} us")
-lib.geossl_debug_set_cfconv_variant(0)
+lib.geossl_debug_set_cfconv_variant(7 | (7 << 3))
