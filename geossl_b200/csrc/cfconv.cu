@@ -102,16 +102,17 @@ cfconv_gather_deep_kernel(const float* __restrict__ filt, const int32_t* __restr
             my_b = __ldg(idx_b + mine);
         }
         const int cnt = min(32, end - base);
+        const int rb_any = __shfl_sync(0xffffffffu, my_b, 0);         // a valid row for the padded slots (multiplied by zero)
         for (int k0 = 0; k0 < cnt; k0 += EPW * U) {
             float4 w[U];
             int rb[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int k = k0 + sub + u * EPW;
-                const int ra = __shfl_sync(0xffffffffu, my_a, k & 31);
-                rb[u] = __shfl_sync(0xffffffffu, my_b, k & 31);
-                if (k < cnt) w[u] = ld_stream4(filt + (int64_t)ra * F + f);
-                else { w[u] = make_float4(0.f, 0.f, 0.f, 0.f); rb[u] = __shfl_sync(0xffffffffu, my_b, 0); }
+                const int k = k0 + sub + u * EPW;                     // lanes of different sub-groups diverge on k < cnt:
+                const int ra = __shfl_sync(0xffffffffu, my_a, k & 31);   // every shuffle stays outside the branch
+                const int rbk = __shfl_sync(0xffffffffu, my_b, k & 31);
+                if (k < cnt) { w[u] = ld_stream4(filt + (int64_t)ra * F + f); rb[u] = rbk; }
+                else { w[u] = make_float4(0.f, 0.f, 0.f, 0.f); rb[u] = rb_any; }
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
