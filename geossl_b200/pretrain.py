@@ -230,15 +230,14 @@ class FlatGradAllReduce:
     def __call__(self):
         if self.world == 1:
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        torch._foreach_copy_(self.views, grads)
+        for p in self.params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in self.params]
+        torch._foreach_copy_(self.views, grads)              # a handful of multi-tensor kernels, not one launch per parameter
         self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
         self.flat.mul_(1.0 / self.world)
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+        torch._foreach_copy_(grads, self.views)
 
 
 def broadcast_parameters(modules, src=0):
