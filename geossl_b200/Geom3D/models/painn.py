@@ -103,7 +103,7 @@ class PaiNN(nn.Module):
         atomic_numbers = x[:, 0] if x.dim() == 2 else x
         n_atoms = atomic_numbers.size(0)
         Fd = self.n_atom_basis
-        q = self.embedding(atomic_numbers)                      # (N,F)
+        q = ops.embedding(self.embedding, atomic_numbers)       # (N,F)
         mu = torch.zeros((n_atoms, 3, Fd), dtype=q.dtype, device=q.device)
         edges = ops.painn_edges(positions, radius_edge_index, n_atoms, batch, self.radial_basis.offsets,
                                 self.radial_basis.widths, self.cutoff, num_graphs=num_graphs, assume_sorted=assume_sorted)

@@ -187,7 +187,7 @@ class SchNet(torch.nn.Module):
         on ``batch[-1]``; ``graph`` reuses a prebuilt RadiusCSR."""
         assert z.dim() == 1 and z.dtype == torch.long
         batch = torch.zeros_like(z) if batch is None else batch
-        h = self.embedding(z)
+        h = ops.embedding(self.embedding, z)
         if graph is None:
             graph = ops.radius_csr(pos, batch, self.cutoff, num_graphs=num_graphs)
         if pos.requires_grad and torch.is_grad_enabled():

@@ -61,6 +61,7 @@ _SIGNATURES = {
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "geossl_weight_image_bytes": (c_i64, []),
     "geossl_pack_weight": (c_int, [c_p, c_int, c_int, c_p, c_p]),
+    "geossl_pack_weights_batched": (c_int, [c_p, c_int, c_p, c_p]),
     "geossl_linear_tc": (c_int, [c_p, c_i64, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p]),
     "geossl_linear_wgrad_tc_workspace": (c_i64, [c_i64]),
     "geossl_linear_wgrad_tc": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),

@@ -98,6 +98,35 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (n <= 1024 * 64) {
+        // batch-sized inputs: every thread owns c consecutive elements -> one block scan of the 1024 partial sums
+        // (two barriers in all instead of four per 1024 elements)
+        const int c = (n + 1023) / 1024, lo = min(tid * c, n), hi = min(lo + c, n);
+        int sum = 0;
+        for (int i = lo; i < hi; ++i) sum += deg[i];
+        int v = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) warp_tot[w] = v;
+        __syncthreads();
+        if (w == 0) {
+            int t = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += u;
+            }
+            warp_tot[lane] = t;   // inclusive totals
+        }
+        __syncthreads();
+        int run = (w == 0 ? 0 : warp_tot[w - 1]) + v - sum;       // exclusive prefix of this thread's first element
+        if (tid == 0) out[0] = 0;
+        for (int i = lo; i < hi; ++i) { run += deg[i]; out[i + 1] = run; }
+        return;
+    }
     if (tid == 0) { carry_s = 0; out[0] = 0; }
     __syncthreads();
     for (int base = 0; base < n; base += 1024) {

@@ -43,10 +43,7 @@ constexpr int kWImage = 4 * kNBlkW;                   // bytes of a packed weigh
 // Weight (128,128) fp32 -> the exact shared-memory operand image (split, swizzled) in global memory, so that every CTA
 // of the layer kernels fetches it with one bulk async copy instead of re-splitting it.
 template <bool FP16>
-__global__ void __launch_bounds__(256)
-pack_weight_kernel(const float* __restrict__ Wt, int trans, uint8_t* __restrict__ image) {
-    pdl_launch_dependents();
-    pdl_wait();
+__device__ __forceinline__ void pack_weight_body(const float* __restrict__ Wt, int trans, uint8_t* __restrict__ image) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * 16; idx += gridDim.x * blockDim.x) {
         float v[8];
         int n, c;
@@ -62,6 +59,24 @@ pack_weight_kernel(const float* __restrict__ Wt, int trans, uint8_t* __restrict_
         const int blk = c >> 3;
         store_chunk8<FP16>(image + blk * kNBlkW, image + 2 * kNBlkW + blk * kNBlkW, n, (c & 7) * 8, v);
     }
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ Wt, int trans, uint8_t* __restrict__ image) {
+    pdl_launch_dependents();
+    pdl_wait();
+    pack_weight_body<FP16>(Wt, trans, image);
+}
+
+// All layers of a model in ONE launch: blockIdx.y = layer, blockIdx.z = 0: forward image (fp16 parts, nn.Linear
+// orientation) / 1: data-gradient image (bf16 parts, transposed).  images = [layer][2][kWImage] bytes.
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const float* const* __restrict__ weights, uint8_t* __restrict__ images) {
+    const float* Wt = weights[blockIdx.y];
+    uint8_t* image = images + ((size_t)blockIdx.y * 2 + blockIdx.z) * kWImage;
+    if (blockIdx.z == 0) pack_weight_body<true>(Wt, 0, image);
+    else pack_weight_body<false>(Wt, 1, image);
 }
 
 // X tile (64 rows x 128 k, fp32, optional ssp) -> split K-major SW128 image.  256 threads: (row = tid/4, 32 k each).
@@ -397,6 +412,14 @@ int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts
     } else {
         GEOSSL_CUDA(launch_pdl(tc::pack_weight_kernel<true>, dim3(8), dim3(256), 0, as_stream(stream), weight, transpose_weight, (uint8_t*)image));
     }
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_pack_weights_batched(const float* const* weights, int n_weights, void* images, void* stream) {
+    if (n_weights == 0) return 0;
+    GEOSSL_REQUIRE(weights && images && n_weights > 0, "null pointer");
+    tc::pack_weights_batched_kernel<<<dim3(8, n_weights, 2), 256, 0, as_stream(stream)>>>(weights, (uint8_t*)images);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -516,27 +516,34 @@ def linear_tc_applies(layer):
     return FILTER_MODE != "simt" and w.is_cuda and tuple(w.shape) == (128, 128)
 
 
+_ptr_tables = {}
+
+
 def prepack_linear_weights(layers):
     """Pack the operand images of several 128x128 layers (forward orientation in fp16 parts, transposed orientation in
-    bf16 parts for the data gradient) on the side stream, ahead of their first use: none of them depends on anything
-    computed in the step, so the ~3 us launches overlap the neighbour search.  Returns {layer: (image, image_t)}; valid
-    for the current forward/backward only (weights change at the next optimizer step)."""
+    bf16 parts for the data gradient) with ONE launch (geossl_pack_weights_batched).  The device table of weight
+    addresses is built once per set of layers (parameter storage does not move).  Returns {layer: (image, image_t)};
+    valid for the current forward/backward only (weights change at the next optimizer step)."""
     layers = [l for l in layers if linear_tc_applies(l)]
     if not layers:
         return {}
     dev = layers[0].weight.device
-    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-    side.wait_stream(main)
-    out = {}
-    with torch.cuda.stream(side):
-        for l in layers:
-            w = l.weight.detach()
-            out[l] = (_pack_weight(w, False, False), _pack_weight(w, True, True))
-    main.wait_stream(side)
-    for a, b in out.values():
-        a.record_stream(main)
-        b.record_stream(main)
-    return out
+    ws = [l.weight.detach() for l in layers]
+    for w in ws:
+        _req(w, torch.float32, "weight", 2)
+    key = (dev, tuple(w.data_ptr() for w in ws))
+    table = _ptr_tables.get(key)
+    if table is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("geossl_b200: run the model once before capturing it in a CUDA graph (weight pointer table)")
+        if len(_ptr_tables) > 16:
+            _ptr_tables.clear()
+        table = _ptr_tables[key] = torch.tensor(key[1], dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    nbytes = lib.geossl_weight_image_bytes()
+    images = torch.empty((len(ws), 2, nbytes), dtype=torch.uint8, device=dev)
+    check(lib.geossl_pack_weights_batched(_p(table), len(ws), _p(images), _stream()), "pack_weights_batched")
+    return {l: (images[i, 0], images[i, 1]) for i, l in enumerate(layers)}
 
 
 def linear(x, layer, pre_ssp=False, residual=None, images=None):
@@ -548,6 +555,39 @@ def linear(x, layer, pre_ssp=False, residual=None, images=None):
         x = torch.nn.functional.softplus(x) - 0.6931471824645996
     y = torch.nn.functional.linear(x, w, layer.bias)
     return y if residual is None else residual + y
+
+
+# =====================================================================================================
+# embedding lookup with a short, deterministic backward
+# =====================================================================================================
+class EmbeddingLookup(torch.autograd.Function):
+    """``weight[z]`` for a small vocabulary (atom classes).  torch's embedding backward sorts the indices and runs a
+    segmented reduction (about twenty small launches); with a 9..100-row table the gradient is one GEMM
+    ``one_hot(z)^T @ grad`` -- four launches, no atomics, fixed summation order."""
+
+    @staticmethod
+    def forward(ctx, weight, z, padding_idx):
+        ctx.save_for_backward(z)
+        ctx.rows, ctx.padding_idx = weight.size(0), padding_idx
+        return weight.index_select(0, z)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        (z,) = ctx.saved_tensors
+        onehot = torch.nn.functional.one_hot(z, ctx.rows).to(grad.dtype)
+        gw = onehot.t() @ grad
+        if ctx.padding_idx is not None:
+            gw[ctx.padding_idx] = 0                     # nn.Embedding(padding_idx=...) never updates that row (painn.py:174)
+        return gw, None, None
+
+
+def embedding(module, z):
+    """``module(z)`` for an nn.Embedding, through EmbeddingLookup when the table is small and on the GPU."""
+    w = module.weight
+    if w.is_cuda and w.size(0) <= 128 and z.dim() == 1 and module.max_norm is None and not module.sparse:
+        return EmbeddingLookup.apply(w, z, module.padding_idx)
+    return module(z)
 
 
 # =====================================================================================================

@@ -188,6 +188,10 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
  * one bulk async copy (cp.async.bulk). */
 int64_t geossl_weight_image_bytes(void);
 int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts, void* image, void* stream);
+/* Every 128 x 128 layer of a model in one launch: `weights` = DEVICE array of n_weights device pointers; images =
+ * n_weights x 2 x geossl_weight_image_bytes(): [layer][0] forward image (fp16 parts), [layer][1] data-gradient image
+ * (transposed, bf16 parts). */
+int geossl_pack_weights_batched(const float* const* weights, int n_weights, void* images, void* stream);
 int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, const float* bias, int pre_ssp,
                      const float* act_grad_input, const float* residual, float* y, int bf16_parts, void* stream);
 
