@@ -380,6 +380,14 @@ static int node_grid(int64_t n_rows) {
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
+// Weight-gradient kernels run on the side stream next to the main backward chain and every CTA dumps a 66 KB partial:
+// a smaller grid (several row tiles per CTA, accumulated in TMEM) cuts the partial traffic and leaves SMs to the main chain.
+static int wgrad_grid(int64_t n_rows) {
+    int64_t tiles = (n_rows + kNR - 1) / kNR;
+    static const int cap = [] { const char* e = getenv("GEOSSL_WGRAD_CTAS"); return e ? atoi(e) : 80; }();
+    return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
 }  // namespace tc
 }  // namespace geossl
 
@@ -451,7 +459,7 @@ int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, c
     return GEOSSL_EINVAL;
 }
 
-int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::node_grid(n_rows) * tc::kWgPart; }
+int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::wgrad_grid(n_rows) * tc::kWgPart; }
 
 int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, int pre_ssp, float* workspace,
                            float* grad_weight, float* grad_bias, void* stream) {
@@ -462,7 +470,7 @@ int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, 
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const int grid = tc::node_grid(n_rows);
+    const int grid = tc::wgrad_grid(n_rows);
     GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid), dim3(256), smem, as_stream(stream), grad_y, x, n_rows, pre_ssp, workspace));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_reduce_kernel, dim3((tc::kWgPart + 31) / 32), dim3(256), 0, as_stream(stream), workspace, grid, grad_weight, grad_bias));
