@@ -89,7 +89,7 @@ cfconv_gather_deep_kernel(const float* __restrict__ filt, const int32_t* __restr
     const int lane = threadIdx.x & 31;
     const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (wid >= n_atoms) return;
-    const int row = TRANSPOSED ? wid : n_atoms - 1 - wid;
+    const int row = n_atoms - 1 - wid;      // rows last to first: own (contiguous) block first, shared rows then hit L2
     const int f = (lane % LPR) * 4, sub = lane / LPR;
     const int b = __ldg(ptr + row), end = __ldg(ptr + row + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
