@@ -31,10 +31,11 @@ constexpr int kNR = 64;                   // rows per tile
 constexpr int kNBlkW = 128 * 128;         // [128 rows x 64 k] 16-bit weight block
 constexpr int kNBlkT = kNR * 128;         // [64 rows x 64 k] 16-bit tile block
 
-struct LinLayout {
+template <int NR>                                     // NR rows per tile (64: two CTAs per SM; 128: one wave of 1-CTA SMs)
+struct LinLayoutT {
     static constexpr int W = 0;                       // hi (2 k-blocks) | lo (2 k-blocks)   64 KB
-    static constexpr int X = W + 4 * kNBlkW;          // hi (2 k-blocks) | lo (2 k-blocks)   32 KB
-    static constexpr int BAR = X + 4 * kNBlkT;            // [0] MMA done, [1] weight image landed
+    static constexpr int X = W + 4 * kNBlkW;          // hi (2 k-blocks) | lo (2 k-blocks)   32 / 64 KB
+    static constexpr int BAR = X + 4 * NR * 128;          // [0] MMA done, [1] weight image landed
     static constexpr int TMEM_PTR = BAR + 16;
     static constexpr int kBytes = TMEM_PTR + 16;
 };
@@ -79,41 +80,47 @@ pack_weights_batched_kernel(const float* const* __restrict__ weights, uint8_t* _
     else pack_weight_body<false>(Wt, 1, image);
 }
 
-// X tile (64 rows x 128 k, fp32, optional ssp) -> split K-major SW128 image.  256 threads: (row = tid/4, 32 k each).
-template <bool FP16>
+// X tile (NR rows x 128 k, fp32, optional ssp) -> split K-major SW128 image.  4 NR threads, four (row, 8-column chunk)
+// items each: 16 lanes cover one 512-byte row, so every load instruction of a warp reads 1 KB of contiguous memory
+// (full 32-byte sectors) and all eight loads of a thread are in flight before the first conversion.
+template <bool FP16, int NR>
 __device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, int64_t row0, int64_t n_rows, bool pre_ssp,
                                                   uint8_t* hi, uint8_t* lo) {
-    const int tid = threadIdx.x, r = tid >> 2, kq = tid & 3;
-    const int64_t row = row0 + r;
-    float v[32];
-    if (row < n_rows) {
-        const float* p = X + row * 128 + kq * 32;
+    constexpr int kBlkT = NR * 128, kRowsPerPass = NR / 4;
+    const int tid = threadIdx.x, c = tid & 15, r0 = tid >> 4;
+    float4 a[4][2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 t = ldg4(p + 4 * j);
-            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    for (int it = 0; it < 4; ++it) {
+        const int64_t row = row0 + r0 + it * kRowsPerPass;
+        if (row < n_rows) {
+            const float* p = X + row * 128 + c * 8;
+            a[it][0] = ldg4(p);
+            a[it][1] = ldg4(p + 4);
+        } else {
+            a[it][0] = a[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (pre_ssp) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ssp_fast(v[j]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    const int blk = kq >> 1;                          // k-block of 64
 #pragma unroll
-    for (int c = 0; c < 4; ++c) store_chunk8<FP16>(hi + blk * kNBlkT, lo + blk * kNBlkT, r, (kq & 1) * 32 + c * 8, &v[c * 8]);
+    for (int it = 0; it < 4; ++it) {
+        float v[8] = {a[it][0].x, a[it][0].y, a[it][0].z, a[it][0].w, a[it][1].x, a[it][1].y, a[it][1].z, a[it][1].w};
+        if (pre_ssp && row0 + r0 + it * kRowsPerPass < n_rows) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = ssp_fast(v[k]);
+        }
+        const int blk = c >> 3;                       // k-block of 64
+        store_chunk8<FP16>(hi + blk * kBlkT, lo + blk * kBlkT, r0 + it * kRowsPerPass, (c & 7) * 8, v);
+    }
 }
 
-template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R>
-__global__ void __launch_bounds__(256, 2)
+template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R, int NR>
+__global__ void __launch_bounds__(4 * NR, NR == 64 ? 2 : 1)
 linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __restrict__ w_image, const float* __restrict__ bias,
                  const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y) {
     extern __shared__ uint8_t smem_raw[];
     trace_l(0);
     uint8_t* smem = align1024(smem_raw);
-    using L = LinLayout;
+    using L = LinLayoutT<NR>;
+    constexpr int kBlkT = NR * 128;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar = sbase + L::BAR;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -126,7 +133,7 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, 64);
+    if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, NR);
     pdl_wait();                                                // everything above overlaps the previous kernel's tail
     if (tid == 0) {
         mbar_expect_tx(wbar, kWImage);
@@ -137,20 +144,20 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR);
-    const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, kNR);
+    const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, NR);
     const int q = warp & 3, eh = warp >> 2, f = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float bf = bias ? __ldg(bias + f) : 0.f;
 
-    const int64_t n_tiles = (n_rows + kNR - 1) / kNR;
+    const int64_t n_tiles = (n_rows + NR - 1) / NR;
     uint32_t phase = 0;
     trace_l(1);
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t row0 = t * kNR;
-        stage_rows_kmajor<FP16>(X, row0, n_rows, PRE_SSP, smem + L::X, smem + L::X + 2 * kNBlkT);
+        const int64_t row0 = t * NR;
+        stage_rows_kmajor<FP16, NR>(X, row0, n_rows, PRE_SSP, smem + L::X, smem + L::X + 2 * kBlkT);
         trace_l(2);
         // epilogue operands do not depend on the MMA: fetch them now so their latency hides behind it
-        const bool full = row0 + kNR <= n_rows;                // warp-uniform: no per-row bounds checks on full tiles
+        const bool full = row0 + NR <= n_rows;                 // warp-uniform: no per-row bounds checks on full tiles
         const int64_t ebase = (row0 + eh * 32) * 128 + f;
         float zr[HAS_Z ? 32 : 1], rr[HAS_R ? 32 : 1];
         if constexpr (HAS_Z) {
@@ -169,11 +176,11 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
             trace_l(4);                                // (completes once; later tiles pass immediately)
             tc_fence_after();
             const uint64_t wh = desc_k_sw128(sbase + L::W), wl = desc_k_sw128(sbase + L::W + 2 * kNBlkW);
-            const uint64_t xh = desc_k_sw128(sbase + L::X), xl = desc_k_sw128(sbase + L::X + 2 * kNBlkT);
+            const uint64_t xh = desc_k_sw128(sbase + L::X), xl = desc_k_sw128(sbase + L::X + 2 * kBlkT);
             if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kNBlkT >> 4) + 2 * (ks & 3);
+                    const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kBlkT >> 4) + 2 * (ks & 3);
                     mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, ks > 0);
                 }
                 tc_commit(bar);
@@ -209,7 +216,7 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
     __syncthreads();
     if (warp == 0) {
         __syncwarp();
-        tmem_dealloc(tmem, 64);
+        tmem_dealloc(tmem, NR);
     }
     trace_l(7);
 }
@@ -396,14 +403,33 @@ using namespace geossl;
 template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R>
 static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weight, const float* bias, const float* z, const float* r,
                             float* y, cudaStream_t st) {
-    const size_t smem = tc::LinLayout::kBytes + 1024;
-    static bool configured = false;                            // one flag per instantiation
+    static const int wide_min = [] { const char* e = getenv("GEOSSL_LINEAR_WIDE_MIN"); return e ? atoi(e) : 64 * kNumSM; }();
+    if (n_rows >= wide_min) {
+        // enough rows for every SM: 128-row tiles, one 512-thread CTA per SM (no co-resident CTA competing for the
+        // tensor pipe / shared memory during the same phases), half as many weight-image fetches
+        constexpr int NR = 128;
+        const size_t smem = tc::LinLayoutT<NR>::kBytes + 1024;
+        static bool configured = false;                        // one flag per instantiation
+        if (!configured) {
+            GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        const int64_t tiles = (n_rows + NR - 1) / NR;
+        GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, dim3((unsigned)(tiles < kNumSM ? tiles : kNumSM)),
+                               dim3(4 * NR), smem, st, x, n_rows, weight, bias, z, r, y));
+        GEOSSL_LAUNCH_CHECK();
+        return 0;
+    }
+    constexpr int NR = 64;
+    const size_t smem = tc::LinLayoutT<NR>::kBytes + 1024;
+    static bool configured = false;
     if (!configured) {
-        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
         configured = true;
     }
-    GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R>, dim3(tc::node_grid(n_rows)), dim3(256), smem, st,
+    GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, dim3(tc::node_grid(n_rows)), dim3(4 * NR), smem, st,
                            x, n_rows, weight, bias, z, r, y));
     GEOSSL_LAUNCH_CHECK();
     return 0;
