@@ -315,6 +315,9 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                     }
                     __syncwarp();
                 }
+                // ---- MMA1(i+1) ahead of the weight-gradient MMAs: it only needs the next rbf tile and a drained D1, and the
+                // epilogue warps -- the bottleneck -- can then start E1(i+1) the moment they finish E3(i)
+                if (i + 1 < my_tiles) mma1(i + 1);
                 // ---- WG2(i): DW2 += dU^T s
                 mbar_wait(bar(S_FULL_ + b), (i >> 1) & 1);
                 tc_fence_after();
@@ -334,8 +337,6 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
                     __syncwarp();
                 }
                 trace_b(i, 6);
-                // ---- MMA1(i+1)
-                if (i + 1 < my_tiles) mma1(i + 1);
                 // ---- WG1(i): DW1 += dA^T rbf
                 mbar_wait(bar(DA_FULL_), i & 1);
                 tc_fence_after();
