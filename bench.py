@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timers", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--atoms-max", type=int, default=0,
+                    help="secondary variant of configs[1]: n ~ U{atoms..atoms_max} atoms per molecule (rows beyond 32 neighbours "
+                         "are truncated, shapes differ per batch => eager launches)")
     ap.add_argument("--model", default="schnet", choices=["schnet", "painn"],
                     help="schnet = the headline workload (configs[1]); painn = configs[2] (F=128, 3 interactions, 20 RBF, cutoff 5 A)")
     return ap.parse_args()
@@ -187,7 +190,10 @@ def run_product(args):
     torch.manual_seed(1234 + rank)
 
     B = CFG["batch_per_gpu"]
-    host_pool = [synthetic_batch(B, CFG["atoms"], seed=10_000 * rank + i) for i in range(args.pool)]
+    if args.atoms_max:
+        args.no_graph = True
+    host_pool = [synthetic_batch(B, CFG["atoms"] if not args.atoms_max else 10, args.atoms_max or None, seed=10_000 * rank + i)
+                 for i in range(args.pool)]
     if args.model == "painn":
         # dataset-time radius graph (datasets_3D_Radius.py:120) on the clean coordinates, reused for both views
         from geossl_b200 import ops as _ops
@@ -346,7 +352,8 @@ def run_product(args):
     line = {"metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, **CFG, "global_batch": world * B, "atoms_per_launch": n_atoms, "edges_per_launch": n_edges, "views_stacked": 2,
+            "config": {"workload": WORKLOAD if not args.atoms_max else
+                       WORKLOAD + f" -- VARIABLE-SIZE VARIANT: 10..{args.atoms_max} atoms per molecule, eager launches", **CFG, "global_batch": world * B, "atoms_per_launch": n_atoms, "edges_per_launch": n_edges, "views_stacked": 2,
                        "pairs": n_pairs, "parallelism": f"dp{world}", "optimizer": "torch.optim.Adam(fused)", "launch": "eager" if args.no_graph else "whole step captured in one CUDA graph",
                        "kernel_timing": f"CUDA-event brackets over {n_k} eager steps of the same workload ({ms_eager / n_k:.2f} ms/step eager)",
                        "filter_rows_per_launch": n_rows_w,
