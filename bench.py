@@ -314,7 +314,7 @@ def run_product(args):
     if "cfconv_fwd" in ktimes:
         t = ktimes["cfconv_fwd"]["mean_ms"] / 1e3
         ach = cf_bytes / t / 1e9
-        roof = {"kernel": "cfconv_gather_deep_kernel<128,false> (cfconv forward)", "bound": "hbm", "achieved": ach,
+        roof = {"kernel": "cfconv_gather_async_kernel<false> (cfconv forward, F = 128)", "bound": "hbm", "achieved": ach,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_CFCONV_FWD if (shared and n_edges > 400_000) else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_v29_ncu_full.txt",

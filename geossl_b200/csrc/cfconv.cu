@@ -134,6 +134,84 @@ cfconv_gather_deep_kernel(const float* __restrict__ filt, const int32_t* __restr
     if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
 }
 
+// Async edition (F = 128): the filter rows of a step go global -> shared with cp.async (no registers held while they are
+// in flight), double buffered, so the NEXT step's eight rows are already requested while the current step is consumed and
+// filter-row loads stay in flight continuously; each lane reads back exactly the 16 bytes it copied (no cross-lane sync).
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256, 3)
+cfconv_gather_async_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ v,
+                           const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx_a, const int32_t* __restrict__ idx_b,
+                           int n_atoms, float* __restrict__ out) {
+    constexpr int F = 128, U = 8;
+    extern __shared__ float4 sW_raw[];                                // 64 KB: [warp][stage][row of the step][lane]
+    float4 (*sW)[2][U][32] = reinterpret_cast<float4 (*)[2][U][32]>(sW_raw);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (wid >= n_atoms) return;
+    const int row = n_atoms - 1 - wid;
+    const int f = lane * 4;
+    const int b = __ldg(ptr + row), end = __ldg(ptr + row + 1);
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(&sW[w][0][0][lane]);
+    constexpr uint32_t kRowB = 32 * 16, kStageB = U * kRowB;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = b; base < end; base += 32) {
+        const int mine = base + lane;
+        int my_a = 0, my_b = 0;
+        if (mine < end) {
+            const int e = TRANSPOSED ? __ldg(idx_a + mine) : mine;
+            my_a = filt_row ? __ldg(filt_row + e) : e;
+            my_b = __ldg(idx_b + mine);
+        }
+        const int cnt = min(32, end - base);
+        const int n_steps = (cnt + U - 1) / U;
+        auto issue = [&](int step) {                                  // rows step*U .. +U-1 of this chunk -> stage step & 1
+            const uint32_t dst = s0 + (step & 1) * kStageB;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = step * U + u;
+                const int ra = __shfl_sync(0xffffffffu, my_a, k & 31);
+                if (k < cnt) cp_async16(dst + u * kRowB, filt + (int64_t)ra * F + f);
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        for (int step = 0; step < n_steps; ++step) {
+            if (step + 1 < n_steps) issue(step + 1);
+            else cp_async_commit();                                   // empty group keeps the wait count uniform
+            int rb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = step * U + u;
+                rb[u] = __shfl_sync(0xffffffffu, my_b, (k < cnt ? k : 0) & 31);
+            }
+            float4 xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = ldg4(v + (int64_t)rb[u] * F + f);
+            cp_async_wait<1>();                                       // this step's rows have landed (next step's may not)
+            const float4* st = &sW[w][step & 1][0][lane];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (step * U + u < cnt) fma4(acc, xv[u], st[u * 32]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = ldg4(v + (int64_t)rb[4 + u] * F + f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (step * U + 4 + u < cnt) fma4(acc, xv[u], st[(4 + u) * 32]);
+        }
+        cp_async_wait<0>();
+    }
+    *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
+}
+
 // Windowed edition: the ROWS consecutive rows of a CTA belong to one or two molecules, so the atoms they gather from sit
 // in a short contiguous index range.  That window of `v` (x or grad_out rows) is staged in shared memory once per CTA and
 // the per-edge gathers read it from there; the L2 -> SM traffic of the gather operand drops by ~ROWS x and only the filter
@@ -232,11 +310,25 @@ cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, co
     }
 }
 
-// Tuning switch (geossl_debug_set_cfconv_variant): bits 0-2 forward, 3-5 backward.  7 = deep edition (default), 0-3 = plain
-// gather at other unroll / occupancy points, 4-6 = windowed edition.  Measured alone on the bench workload (us, forward /
-// backward): plain 45.9 / 33.4, windowed 41.4 / 43.5, deep 31.1 / 31.3 -- the kernel is latency bound, what pays is filter
-// rows in flight, not less L2 traffic for the gather operand (profiles/tune_cfconv.py).
-static int g_variant = 7 | (7 << 3);
+template <bool TRANSPOSED>
+static void launch_async(int blocks, cudaStream_t st, const float* filt, const int32_t* filt_row, const float* v, const int32_t* ptr,
+                         const int32_t* idx_a, const int32_t* idx_b, int n, float* out) {
+    constexpr int kSmem = 8 * 2 * 8 * 32 * 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(cfconv_gather_async_kernel<TRANSPOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        configured = true;
+    }
+    launch_pdl(cfconv_gather_async_kernel<TRANSPOSED>, dim3(blocks), dim3(256), (size_t)kSmem, st, filt, filt_row, v, ptr, idx_a, idx_b, n, out);
+}
+
+// Tuning switch (geossl_debug_set_cfconv_variant): bits 0-2 forward, 3-5 backward.  3 = async edition (default; F = 128,
+// other widths take the deep edition), 7 = deep edition, 0-2 = plain gather at other unroll / occupancy points, 4-6 =
+// windowed edition.  Measured alone on the bench workload (us, forward / backward): plain 45.9 / 33.4, windowed 41.4 /
+// 43.5, deep 31.1 / 31.3; on a slower box of the pool deep 40.7 / 41.3, async 36.7 / 37.7 -- the kernel is latency bound,
+// what pays is filter rows in flight, not less L2 traffic for the gather operand (profiles/tune_cfconv.py).  All editions
+// accumulate in edge order and agree bit for bit.
+static int g_variant = 3 | (3 << 3);
 
 template <int F>
 int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src, int64_t n,
@@ -247,7 +339,10 @@ int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const
     switch (g_variant & 7) {
         case 1: launch_pdl(cfconv_gather_kernel<F, 8, false, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 2: launch_pdl(cfconv_gather_kernel<F, 8, false, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        case 3: launch_pdl(cfconv_gather_kernel<F, 4, false, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
+        case 3:
+            if constexpr (F == 128) launch_async<false>(blocks, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
+            else launch_pdl(cfconv_gather_deep_kernel<F, false>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
+            break;
         case 0: launch_pdl(cfconv_gather_kernel<F, 4, false, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 7: launch_pdl(cfconv_gather_deep_kernel<F, false>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
         case 5: launch_pdl(cfconv_gather_win_kernel<F, 4, false, 8, kWin, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
@@ -265,7 +360,10 @@ int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, con
     switch ((g_variant >> 3) & 7) {
         case 1: launch_pdl(cfconv_gather_kernel<F, 4, true, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 2: launch_pdl(cfconv_gather_kernel<F, 8, true, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        case 3: launch_pdl(cfconv_gather_kernel<F, 4, true, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
+        case 3:
+            if constexpr (F == 128) launch_async<true>(blocks, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
+            else launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
+            break;
         case 0: launch_pdl(cfconv_gather_kernel<F, 8, true, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 7: launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
         case 5: launch_pdl(cfconv_gather_win_kernel<F, 4, true, 8, kWin, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;

@@ -29,11 +29,21 @@ def timeit(fn, reps=40):
 
 
 print(f"atoms {n}, edges {g.num_edges}, pairs {int(g.n_pairs_dev.item())}")
-for variant in (0, 4, 7):
+ref = {}
+for variant in (7, 3, 0):                                   # every variant must give bit-identical results (same edge order)
+    lib.geossl_debug_set_cfconv_variant(variant | (variant << 3))
+    o1, o2 = ops._cfconv_fwd(xs[0], filts[0], g, g.pair_of_edge), ops._cfconv_bwd_x(filts[0], xs[0], g, g.pair_of_edge)
+    torch.cuda.synchronize()
+    if not ref:
+        ref = {"f": o1, "b": o2}
+    else:
+        assert torch.equal(o1, ref["f"]) and torch.equal(o2, ref["b"]), variant
+print("variants 7 / 3 / 0 agree bit for bit")
+for variant in (7, 3):
     lib.geossl_debug_set_cfconv_variant(variant | (variant << 3))
     for shared in (True, False):
         row = g.pair_of_edge if shared else None
         f = timeit(lambda i: ops._cfconv_fwd(xs[i % 4], filts[i % 4], g, row))
         bx = timeit(lambda i: ops._cfconv_bwd_x(filts[i % 4], xs[i % 4], g, row))
         print(f"variant {variant} shared={shared}: fwd {f:.1f} us, bwd_x {bx:.1f} us")
-lib.geossl_debug_set_cfconv_variant(7 | (7 << 3))
+lib.geossl_debug_set_cfconv_variant(3 | (3 << 3))
