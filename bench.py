@@ -24,7 +24,7 @@ import torch  # noqa: E402
 METRIC = "GeoSSL-DDM SchNet train molecules/s at 1/2/4/8 B200; cfconv % HBM roofline"
 CFG = dict(batch_per_gpu=256, atoms=30, cutoff=10.0, num_gaussians=50, hidden=128, filters=128, interactions=6,
            sigma_levels=50, anneal_power=2.0, pos_sigma=0.3, lr=5e-4)
-NCU_TRAFFIC_CFCONV_FWD = 123.92e6 + 4.49e6     # bytes per launch of the bench workload (profiles/r01_v29_ncu_full.txt)
+NCU_TRAFFIC_CFCONV_FWD = 123.69e6 + 6.86e6     # bytes per launch of the bench workload (profiles/r01_v32_ncu_full.txt)
 WORKLOAD = ("configs[1]: SchNet GeoSSL-DDM pretraining step, synthetic Molecule3D-shaped conformers, "
             "batch 256 per GPU x 30 atoms, cutoff 10 A, 50 RBF, hidden 128, 6 interactions, data-parallel")
 
@@ -317,7 +317,7 @@ def run_product(args):
         roof = {"kernel": "cfconv_gather_async_kernel<false> (cfconv forward, F = 128)", "bound": "hbm", "achieved": ach,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_CFCONV_FWD if (shared and n_edges > 400_000) else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_v29_ncu_full.txt",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_v32_ncu_full.txt",
                 "peak_source": peaks["src"],
                 "algorithmic_bytes_per_launch": cf_bytes, "filter_rows_per_launch": n_rows_w, "mean_ms": 1e3 * t,
                 "launches_timed": ktimes["cfconv_fwd"]["n"],
