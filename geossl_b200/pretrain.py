@@ -235,8 +235,11 @@ class FlatGradAllReduce:
                 p.grad = torch.zeros_like(p)
         grads = [p.grad for p in self.params]
         torch._foreach_copy_(self.views, grads)              # a handful of multi-tensor kernels, not one launch per parameter
-        self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
-        self.flat.mul_(1.0 / self.world)
+        if self.flat.is_cuda and self.dist.get_backend(self.group) == "nccl":
+            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.AVG, group=self.group)     # 1/R folded into the collective
+        else:
+            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)
         torch._foreach_copy_(grads, self.views)
 
 
