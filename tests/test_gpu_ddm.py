@@ -149,3 +149,14 @@ def test_graphed_train_step_trains():
     assert not torch.equal(w0, model.interactions[0].mlp[0].weight)          # Adam ran inside the graph
     fixed = [float(step(batches[0])) for _ in range(40)]
     assert sum(fixed[-10:]) < sum(fixed[:10])
+    # input pipeline: pinned host batches staged on a copy stream one step ahead of the replay that consumes them
+    host = [synthetic_batch(16, 12, seed=20 + s).pin_memory() for s in range(4)]
+    step.prefetch(host[0], 0)
+    for i in range(4):
+        loss = step.run_prefetched(i & 1)
+        if i + 1 < 4:
+            step.prefetch(host[i + 1], (i + 1) & 1)
+        torch.cuda.synchronize()
+        assert torch.equal(step.static.positions.cpu(), host[i].positions)
+        assert torch.equal(step.static.super_edge_index.cpu(), host[i].super_edge_index)
+        assert float(loss) == float(loss)
