@@ -2,11 +2,15 @@
 //
 // Replaces PyG MessagePassing.propagate + CFConv.message (Geom3D/models/schnet.py:190,194-195):
 //   x_j = x[edge_index[0]] (materialised (E,F)), msg = x_j * W, torch_scatter atomicAdd by edge_index[1].
-// Here: one warp per destination row, W_e streamed once with 128-bit loads that bypass L1, x rows
-// gathered through L1/L2 (x is (N,F) = a few MB, L2 resident), fp32 accumulation in registers in
-// edge order, one coalesced store per row: atomic free and run-to-run deterministic.
+// Here: one warp per destination row, filter rows streamed with 128-bit loads that bypass L1 (through the
+// `filt_row` map when the two directions of an atom pair share one row, geossl_pair_index), x rows gathered
+// through L1/L2 (x is (N,F) = a few MB, L2 resident), fp32 accumulation in registers in edge order, one
+// coalesced store per row: atomic free and run-to-run deterministic.
 //
-// HBM roofline: bytes = 4F*E (W) + 2*4F*N (x, out) + 4E (src) + 4(N+1) (rowptr).
+// HBM roofline: bytes = 4F*U (every filter row once) + 2*4F*N (x, out) + 8E (src, filt_row) + 4(N+1) (rowptr);
+// U = E without pair sharing (551 B/edge), U = E/2 for untruncated graphs (300 B/edge).
+// Four editions of the gather kernel are kept behind a tuning switch (all bit-identical, see g_variant below);
+// the default is the cp.async double-buffered one.
 #include "common.cuh"
 
 namespace geossl {
