@@ -144,3 +144,27 @@ def test_flat_grad_allreduce_gloo_world2(tmp_path):
     model(x).pow(2).mean().backward()
     for p, gsync in zip(model.parameters(), r0["grads"]):
         assert torch.allclose(p.grad, gsync, rtol=1e-5, atol=1e-7)
+
+
+def test_embedding_lookup_backward_matches_torch_embedding():
+    """ops.EmbeddingLookup (one-hot GEMM backward) vs nn.Embedding's own backward, with and without padding_idx
+    (pure torch ops, so the check runs on the CPU; the CUDA path uses the same function)."""
+    from geossl_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for rows, pad in ((9, None), (100, 0)):
+        emb = torch.nn.Embedding(rows, 16, padding_idx=pad)
+        z = torch.randint(0, rows, (257,), generator=g)
+        w_out = torch.randn(257, 16, generator=g)
+        ref = emb(z)
+        (ref * w_out).sum().backward()
+        gref = emb.weight.grad.clone()
+        emb.weight.grad = None
+        out = ops.EmbeddingLookup.apply(emb.weight, z, pad)
+        assert torch.equal(out, ref)
+        (out * w_out).sum().backward()
+        assert torch.allclose(emb.weight.grad, gref, rtol=1e-5, atol=1e-6)
+        if pad is not None:
+            assert emb.weight.grad[pad].abs().max() == 0
+    # the lookup is a torch op either way (not one of the CUDA kernels); off the GPU the dispatcher leaves nn.Embedding alone
+    # -- the model itself still refuses CPU tensors at the first kernel (tests/test_abi.py::test_no_cpu_fallback)
+    assert torch.equal(ops.embedding(emb, z), emb(z))
