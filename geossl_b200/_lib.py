@@ -31,6 +31,8 @@ class DdmPtrs(ctypes.Structure):
                                    "out_w2", "out_b2")]
 
 
+ABI_VERSION = 2          # must equal GEOSSL_ABI_VERSION in include/geossl_b200.h
+
 _SIGNATURES = {
     "geossl_abi_version": (c_int, []),
     "geossl_last_error": (ctypes.c_char_p, []),
@@ -136,8 +138,9 @@ def load():
             fn = getattr(lib, name)     # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.geossl_abi_version() != 1:
-            raise RuntimeError("libgeossl_b200.so ABI version mismatch")
+        if lib.geossl_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} has ABI version {lib.geossl_abi_version()}, this package binds version {ABI_VERSION}: "
+                               "rebuild it with `python -c \"import __graft_entry__ as g; g.build()\"`")
         _lib = lib
         return _lib
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GEOSSL_ABI_VERSION 1
+#define GEOSSL_ABI_VERSION 2   /* 2: filt_row / pair-index / batched-pack entry points */
 #define GEOSSL_EINVAL (-1)   /* bad argument (null pointer, unsupported width, ...) */
 #define GEOSSL_ECAP   (-2)   /* capacity too small */
 
