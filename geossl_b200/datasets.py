@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .data import AtomTupleBatch, assemble_batch_device
+from .data import assemble_batch_device
 
 # keys concatenated along the LAST dimension and holding molecule-local atom indices
 # (torch_geometric Data.__cat_dim__ / dataloaders_AtomTuple.py:62-63)

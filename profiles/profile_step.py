@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from geossl_b200.Geom3D.models import SchNet, PaiNN  # noqa: E402
+from geossl_b200.Geom3D.models import SchNet  # noqa: E402
 from geossl_b200.NCSN import NCSN_version_03  # noqa: E402
 from geossl_b200.data import synthetic_batch  # noqa: E402
 from geossl_b200.pretrain import default_args, train_step  # noqa: E402
