@@ -25,6 +25,9 @@ METRIC = "GeoSSL-DDM SchNet train molecules/s at 1/2/4/8 B200; cfconv % HBM roof
 CFG = dict(batch_per_gpu=256, atoms=30, cutoff=10.0, num_gaussians=50, hidden=128, filters=128, interactions=6,
            sigma_levels=50, anneal_power=2.0, pos_sigma=0.3, lr=5e-4)
 NCU_TRAFFIC_CFCONV_FWD = 123.69e6 + 6.86e6     # bytes per launch of the bench workload (profiles/r01_v32_ncu_full.txt)
+PAINN_METRIC = "GeoSSL-DDM PaiNN train molecules/s (BASELINE configs[2], secondary)"
+PAINN_WORKLOAD = ("configs[2]: PaiNN GeoSSL-DDM pretraining step, F=128, 3 interactions, 20 RBF, cutoff 5 A, synthetic Molecule3D-shaped "
+                  "conformers, batch 256 per GPU x 30 atoms, data-parallel")
 WORKLOAD = ("configs[1]: SchNet GeoSSL-DDM pretraining step, synthetic Molecule3D-shaped conformers, "
             "batch 256 per GPU x 30 atoms, cutoff 10 A, 50 RBF, hidden 128, 6 interactions, data-parallel")
 
@@ -94,54 +97,91 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(steps, warmup, sample_graphs=32, threads=None):
-    """The reference's CPU path (oracle port of schnet.py / NCSN.py / do_DDM, same torch ops) on a bounded sample."""
-    from oracle import models as O
+def cpu_reference(steps, warmup, sample_graphs=None, threads=None, budget_s=None, model_3d="schnet"):
+    """The reference's own CPU implementation of the step on this box's host cores.
+
+    kind "reference": the UNMODIFIED reference modules (Geom3D/models/schnet.py | painn.py, examples/NCSN.py; placed in
+    the git-ignored oracle/_ref by oracle/make_ref.py, imported under oracle/shims) driven with do_DDM's call sequence
+    (oracle/reference_loader.ddm_step) + loss.backward() + torch.optim.Adam, as train() does (pretrain_GeoSSL.py:249-260).
+    kind "port": the functional restatement oracle/models.py -- only when oracle/_ref is absent.
+    Each step is one full batch of the bench workload (``sample_graphs`` molecules, default the whole 256-molecule batch);
+    ``budget_s`` stops early (after >= 2 timed steps) if the host is too slow, and the line says how many steps ran."""
+    from oracle import reference_loader
     from geossl_b200.data import synthetic_batch
-    from geossl_b200.Geom3D.models import SchNet
-    from geossl_b200.NCSN import NCSN_version_03
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
+    sample_graphs = sample_graphs or CFG["batch_per_gpu"]
     torch.manual_seed(42)
-    model = SchNet(hidden_channels=CFG["hidden"], num_filters=CFG["filters"], num_interactions=CFG["interactions"],
-                   num_gaussians=CFG["num_gaussians"], cutoff=CFG["cutoff"], node_class=9)
-    heads = [NCSN_version_03(CFG["hidden"], 10, 0.01, CFG["sigma_levels"], "symmetry", CFG["anneal_power"]) for _ in range(2)]
-    sd = {k: v.clone().requires_grad_(v.is_floating_point() and v.dtype == torch.float32) for k, v in model.state_dict().items()}
-    sdh = [{k: v.clone().requires_grad_(k != "sigmas") for k, v in h.state_dict().items()} for h in heads]
-    leaves = [v for v in sd.values() if v.requires_grad] + [v for d in sdh for v in d.values() if v.requires_grad]
+    painn = model_3d == "painn"
+    kind = "reference" if reference_loader.available() else "port"
+    if kind == "reference":
+        SchNet, PaiNN, NCSN = reference_loader.load()
+    else:
+        from geossl_b200.Geom3D.models import PaiNN, SchNet
+        from geossl_b200.NCSN import NCSN_version_03 as NCSN
+        from oracle import models as O
+    if painn:
+        model = PaiNN(n_atom_basis=CFG["hidden"], n_interactions=3, n_rbf=20, cutoff=5.0, max_z=9, n_out=1, readout="add")
+    else:
+        model = SchNet(hidden_channels=CFG["hidden"], num_filters=CFG["filters"], num_interactions=CFG["interactions"],
+                       num_gaussians=CFG["num_gaussians"], cutoff=CFG["cutoff"], node_class=9)
+    heads = [NCSN(CFG["hidden"], 10, 0.01, CFG["sigma_levels"], "symmetry", CFG["anneal_power"]) for _ in range(2)]
+    if kind == "reference":
+        leaves = [p for m in [model] + heads for p in m.parameters() if p.requires_grad]
+    else:
+        sd = {k: v.clone().requires_grad_(v.is_floating_point() and v.dtype == torch.float32) for k, v in model.state_dict().items()}
+        sdh = [{k: v.clone().requires_grad_(k != "sigmas") for k, v in h.state_dict().items()} for h in heads]
+        leaves = [v for v in sd.values() if v.requires_grad] + [v for d in sdh for v in d.values() if v.requires_grad]
     opt = torch.optim.Adam(leaves, lr=CFG["lr"])
+    from oracle.radius import radius_graph
     times = []
+    t_start = time.perf_counter()
     for it in range(warmup + steps):
         b = synthetic_batch(sample_graphs, CFG["atoms"], seed=1000 + it)
+        if painn:                      # dataset-time radius graph (datasets_3D_Radius.py:120): outside the timed step
+            b.radius_edge_index = radius_graph(b.positions, 5.0, b.batch)
         t0 = time.perf_counter()
-        _, pos2 = O.perturb(None, b.positions, 0.0, CFG["pos_sigma"])
-        enc = lambda z, p: O.schnet_forward(sd, z, p, b.batch, cutoff=CFG["cutoff"])[1]
-        n_pairs = b.super_edge_index.shape[1]
-        draws = [(torch.randint(0, CFG["sigma_levels"], (sample_graphs,)), torch.randn(n_pairs, 1)) for _ in range(2)]
-        loss, _ = O.ddm_loss(enc, sdh[0], sdh[1], b.x[:, 0], b.positions, pos2, b.batch, b.super_edge_index, draws[0], draws[1],
-                             CFG["anneal_power"])
+        if kind == "reference":
+            loss = reference_loader.ddm_step(model_3d, model, heads, b, 0.0, CFG["pos_sigma"])
+        else:
+            _, pos2 = O.perturb(None, b.positions, 0.0, CFG["pos_sigma"])
+            if painn:
+                enc = lambda z, p: O.painn_forward(sd, z, p, b.radius_edge_index, b.batch, readout="add")[1]
+            else:
+                enc = lambda z, p: O.schnet_forward(sd, z, p, b.batch, cutoff=CFG["cutoff"])[1]
+            n_pairs = b.super_edge_index.shape[1]
+            draws = [(torch.randint(0, CFG["sigma_levels"], (sample_graphs,)), torch.randn(n_pairs, 1)) for _ in range(2)]
+            loss, _ = O.ddm_loss(enc, sdh[0], sdh[1], b.x[:, 0], b.positions, pos2, b.batch, b.super_edge_index, draws[0], draws[1],
+                                 CFG["anneal_power"])
         opt.zero_grad()
         loss.backward()
         opt.step()
         float(loss.detach())
         if it >= warmup:
             times.append(time.perf_counter() - t0)
+            if budget_s and len(times) >= 2 and time.perf_counter() - t_start > budget_s:
+                break
     total = sum(times)
-    return {"value": sample_graphs * len(times) / total, "unit": "molecules/s", "cores": threads, "kind": "port",
-            "sample": f"{len(times)} steps x {sample_graphs} molecules x {CFG['atoms']} atoms of the same workload "
-                      f"(oracle/models.py, torch CPU fp32, {warmup} warm-up)",
-            "ms_per_step": 1e3 * total / len(times)}
+    what = ("unmodified reference modules (oracle/_ref) under oracle/shims" if kind == "reference"
+            else "oracle/models.py port (oracle/_ref absent)")
+    return {"value": sample_graphs * len(times) / total, "unit": "molecules/s", "cores": threads, "kind": kind,
+            "sample": f"{len(times)} steps x {sample_graphs} molecules x {CFG['atoms']} atoms = the bench batch "
+                      f"({what}, torch CPU fp32, {warmup} warm-up, fwd+bwd+Adam)",
+            "ms_per_step": 1e3 * total / len(times), "steps": len(times)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 8), min(args.warmup, 1)
-    cb = cpu_reference(steps, max(warmup, 1))
-    line = {"metric": METRIC, "value": cb["value"], "unit": "molecules/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(warmup, 1),
+    painn = args.model == "painn"
+    cb = cpu_reference(args.steps, args.warmup, budget_s=240.0, model_3d=args.model)
+    line = {"metric": PAINN_METRIC if painn else METRIC, "value": cb["value"], "unit": "molecules/s", "n_gpus": args.gpus,
+            "steps": cb["steps"], "warmup": args.warmup,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, **CFG, "device": "host CPU"},
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": PAINN_WORKLOAD if painn else WORKLOAD, **CFG, "device": "host CPU",
+                       "reference_step": "one 256-molecule batch per step on rank 0's host cores"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -183,9 +223,6 @@ def run_product(args):
     if os.environ.get("GEOSSL_PAIR_OWNER_SMALL"):         # tuning only
         from geossl_b200 import ops as _o
         _o.PAIR_OWNER_SMALL = os.environ["GEOSSL_PAIR_OWNER_SMALL"] != "0"
-    if os.environ.get("GEOSSL_CFCONV_VARIANT"):          # tuning only (profiles/tune_cfconv.py)
-        from geossl_b200 import _lib as _l
-        _l.load().geossl_debug_set_cfconv_variant(int(os.environ["GEOSSL_CFCONV_VARIANT"]))
     targs = default_args(args.model)
     torch.manual_seed(1234 + rank)
 
@@ -246,19 +283,38 @@ def run_product(args):
         sampler.start()
     ms = timed(lambda i: step(dev_pool[i % args.pool]), args.steps)
     value = world * B * args.steps / (ms / 1e3)
-    # per-kernel durations: CUDA events cannot bracket nodes inside a replayed graph, so the same steps run once more
-    # with eager launches and event brackets; the launch counter runs there too (a replay launches the same kernels)
+    # per-kernel durations, measured INSIDE a replayed graph: the step is captured a second time with external event-record
+    # nodes around the named kernels (ops.KERNEL_TIMERS in-graph mode) and replayed n_k times; the launch counter runs
+    # during that capture (a replay launches exactly the captured kernels).  Eager runs (--no-graph, variable shapes) fall
+    # back to eager event brackets.
     ktimes = {}
-    _lib.launch_count(reset=True)
     n_k = min(args.steps, 10)
-    if not args.no_kernel_timers:
-        ops.KERNEL_TIMERS.enable(("cfconv_fwd", "filter_fwd", "filter_bwd", "cfconv_bwd_x", "ddm_head_fwd", "ddm_head_bwd",
-                                  "linear_fwd", "linear_dgrad", "linear_wgrad"))
-    ms_eager = timed(lambda i: eager_step(dev_pool[i % args.pool]), n_k)
-    launches = _lib.launch_count() * args.steps // n_k
-    if not args.no_kernel_timers:
-        ktimes = ops.KERNEL_TIMERS.collect()
-        ops.KERNEL_TIMERS.disable()
+    timer_names = ("cfconv_fwd", "filter_fwd", "filter_bwd", "cfconv_bwd_x", "ddm_head_fwd", "ddm_head_bwd",
+                   "linear_fwd", "linear_dgrad", "linear_wgrad")
+    if step is not eager_step:
+        _lib.launch_count(reset=True)
+        probe = GraphedTrainStep(targs, dev_pool[0], model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync, warmup=0,
+                                 kernel_timers=None if args.no_kernel_timers else timer_names)
+        launches = _lib.launch_count() * args.steps
+        acc = None
+        for i in range(n_k):
+            probe(dev_pool[i % args.pool])
+            if not args.no_kernel_timers:
+                acc = ops.KERNEL_TIMERS.collect_replay(acc)
+        barrier()
+        if acc:
+            ktimes = ops.KERNEL_TIMERS.stats(acc)
+        kernel_timing = f"event-record nodes inside a replayed CUDA graph of the step, {n_k} replays"
+    else:
+        _lib.launch_count(reset=True)
+        if not args.no_kernel_timers:
+            ops.KERNEL_TIMERS.enable(timer_names)
+        ms_eager = timed(lambda i: eager_step(dev_pool[i % args.pool]), n_k)
+        launches = _lib.launch_count() * args.steps // n_k
+        if not args.no_kernel_timers:
+            ktimes = ops.KERNEL_TIMERS.collect()
+            ops.KERNEL_TIMERS.disable()
+        kernel_timing = f"CUDA-event brackets over {n_k} eager steps ({ms_eager / n_k:.2f} ms/step eager)"
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- (2) end to end: host (pinned) batches -> H2D every step -> step -> D2H loss every step
@@ -353,7 +409,7 @@ def run_product(args):
                                   "note": "SURVEY 8d figure (551 B/edge, one filter row per DIRECTED edge) over the same duration: "
                                           "the rate a per-edge kernel would need to match this one; not a DRAM rate"}}
         flops = {"filter_fwd": n_rows_w * (2 * G * F_ + 2 * F_ * F_),
-                 "filter_bwd": n_rows_w * (2 * G * F_ + 2 * (2 * F_ * F_) + 2 * G * F_ + 2 * F_ * F_),
+                 "filter_bwd": n_rows_w * (2 * (2 * F_ * F_) + 2 * G * F_),      # 78,336 FLOP/row (no recompute counted)
                  "ddm_head_fwd": n_pairs * 50_048, "ddm_head_bwd": n_pairs * 3 * 50_048}
         for k, fl in flops.items():
             if k in ktimes:
@@ -371,10 +427,33 @@ def run_product(args):
                                       "frac": bb / tt / 1e9 / peaks["hbm_gbs"], "mean_ms": 1e3 * tt,
                                       "share_of_step": ktimes["cfconv_bwd_x"]["total_ms"] / n_k / (ms / args.steps)}
         roof["share_of_step"] = ktimes["cfconv_fwd"]["total_ms"] / n_k / (ms / args.steps)
+        for k in ("linear_fwd", "linear_dgrad", "linear_wgrad"):
+            if k in ktimes:
+                tt = ktimes[k]["mean_ms"] / 1e3
+                others[k] = {"bound": "latency", "mean_ms": 1e3 * tt, "launches_per_step": ktimes[k]["n"] // n_k,
+                             "share_of_step": ktimes[k]["total_ms"] / n_k / (ms / args.steps),
+                             "note": "128->128 atom-wise layer on tcgen05 (0.5 GFLOP per launch); linear_wgrad runs on the side stream"}
+
+    # whole-step floor: every kernel at its own roofline, back to back (the kernels are serial on the critical path).
+    # Tensor work is counted with the 3 split-precision MMAs per product the fp32-grade path issues.
+    L = CFG["interactions"]
+    fl_filter = n_rows_w * (2 * G * F_ + 2 * F_ * F_ + 2 * (2 * F_ * F_) + 2 * G * F_) * L            # fwd + bwd, per step
+    fl_dense = n_atoms * 2 * F_ * F_ * 3 * (3 * L + 2)                                                # fwd + dgrad + wgrad
+    fl_head = n_pairs * 50_048 * 3 * 2                                                                # two heads, fwd + bwd
+    bytes_hbm = L * (cf_bytes + (4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + 4 * n_edges * (3 if shared else 2))   # cfconv fwd + dx
+                     + 4 * F_ * n_rows_w)                                                             # filter rows written once
+    t_tensor = 3 * (fl_filter + fl_dense + fl_head) / (peaks["bf16_tflops_sustained"] * 1e12)
+    t_hbm = bytes_hbm / (peaks["hbm_gbs"] * 1e9)
+    floor = {"floor_ms": 1e3 * (t_tensor + t_hbm), "tensor_ms": 1e3 * t_tensor, "hbm_ms": 1e3 * t_hbm,
+             "frac_of_step": (t_tensor + t_hbm) / (ms / args.steps / 1e3),
+             "flops_per_step": {"filter_mlp": fl_filter, "atomwise_dense": fl_dense, "ddm_heads": fl_head, "mma_per_product": 3},
+             "hbm_bytes_per_step": bytes_hbm,
+             "note": "sum of per-kernel roofline times: split-precision tensor work at the sustained bf16 peak + the materialised-"
+                     "filter traffic (written once, read by cfconv forward and by dx) at the measured HBM peak"}
 
     cpu = None
     if not args.no_cpu_baseline:
-        cb = cpu_reference(4, 1)
+        cb = cpu_reference(3, 1, budget_s=40.0)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -383,14 +462,14 @@ def run_product(args):
             "config": {"workload": WORKLOAD if not args.atoms_max else
                        WORKLOAD + f" -- VARIABLE-SIZE VARIANT: 10..{args.atoms_max} atoms per molecule, eager launches", **CFG, "global_batch": world * B, "atoms_per_launch": n_atoms, "edges_per_launch": n_edges, "views_stacked": 2,
                        "pairs": n_pairs, "parallelism": f"dp{world}", "optimizer": "torch.optim.Adam(fused)", "launch": "eager" if args.no_graph else "whole step captured in one CUDA graph",
-                       "kernel_timing": f"CUDA-event brackets over {n_k} eager steps of the same workload ({ms_eager / n_k:.2f} ms/step eager)",
+                       "kernel_timing": kernel_timing,
                        "filter_rows_per_launch": n_rows_w,
                        "l2": f"{args.pool} distinct batches cycled; per-step working set (6 x {4 * F_ * n_rows_w / 1e6:.0f} MB filter "
                              "tensors) exceeds the 126 MB L2", "position_noise": "device generator"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "roofline": roof, "roofline_other_kernels": others, "cpu_baseline": cpu}
+            "gpu_launches": launches, "roofline": roof, "roofline_other_kernels": others, "step_floor": floor, "cpu_baseline": cpu}
     _emit(json.dumps(line))
     _finish(world)
 

@@ -31,7 +31,7 @@ class DdmPtrs(ctypes.Structure):
                                    "out_w2", "out_b2")]
 
 
-ABI_VERSION = 2          # must equal GEOSSL_ABI_VERSION in include/geossl_b200.h
+ABI_VERSION = 3          # must equal GEOSSL_ABI_VERSION in include/geossl_b200.h
 
 _SIGNATURES = {
     "geossl_abi_version": (c_int, []),
@@ -52,7 +52,6 @@ _SIGNATURES = {
     "geossl_tc_selftest": (c_int, [c_int, c_int, c_p, c_p, c_int, c_int, c_p, c_p]),
     "geossl_cfconv_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
     "geossl_cfconv_bwd_x": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
-    "geossl_debug_set_cfconv_variant": (c_int, [c_int]),
     "geossl_pair_index": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "geossl_cfconv_bwd_w": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
     "geossl_filter_bwd_workspace": (c_i64, [c_int, c_int]),

@@ -9,8 +9,6 @@
 //
 // HBM roofline: bytes = 4F*U (every filter row once) + 2*4F*N (x, out) + 8E (src, filt_row) + 4(N+1) (rowptr);
 // U = E without pair sharing (551 B/edge), U = E/2 for untruncated graphs (300 B/edge).
-// Four editions of the gather kernel are kept behind a tuning switch (all bit-identical, see g_variant below);
-// the default is the cp.async double-buffered one.
 #include "common.cuh"
 
 namespace geossl {
@@ -25,60 +23,7 @@ __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w
 //   e(k) = k (CSR) or idx_a[k] (transposed view: t_eid).
 // The edge ids / gather indices of up to 32 edges are fetched with ONE coalesced load per lane and broadcast by shuffle,
 // so the 128-bit row loads of an unrolled step do not wait on per-edge index loads (the kernel is latency bound).
-template <int F, int UNROLL, bool TRANSPOSED, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-cfconv_gather_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ v,
-                     const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx_a, const int32_t* __restrict__ idx_b,
-                     int n_atoms, float* __restrict__ out) {
-    constexpr int LPR = F / 4, EPW = 32 / LPR;
-    pdl_launch_dependents();
-    pdl_wait();
-    const int lane = threadIdx.x & 31;
-    const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (wid >= n_atoms) return;
-    // Forward walks the rows LAST to first: the filter tensor was just written front to back by the filter kernel, so its
-    // tail is what the L2 still holds; reading in write order would evict exactly the lines about to be needed.
-    const int row = TRANSPOSED ? wid : n_atoms - 1 - wid;
-    const int f = (lane % LPR) * 4, sub = lane / LPR;
-    const int b = __ldg(ptr + row), end = __ldg(ptr + row + 1);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = b; base < end; base += 32) {
-        const int mine = base + lane;
-        int my_a = 0, my_b = 0;
-        if (mine < end) {
-            const int e = TRANSPOSED ? __ldg(idx_a + mine) : mine;
-            my_a = filt_row ? __ldg(filt_row + e) : e;               // shared filter row of the undirected pair
-            my_b = __ldg(idx_b + mine);
-        }
-        const int cnt = min(32, end - base);
-        for (int k0 = 0; k0 < cnt; k0 += EPW * UNROLL) {             // warp-uniform trip count (shuffles inside)
-            float4 w[UNROLL], xv[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int k = k0 + sub + u * EPW;
-                const int ra = __shfl_sync(0xffffffffu, my_a, k & 31), rb = __shfl_sync(0xffffffffu, my_b, k & 31);
-                if (k < cnt) {
-                    w[u] = ld_stream4(filt + (int64_t)ra * F + f);
-                    xv[u] = ldg4(v + (int64_t)rb * F + f);
-                } else {
-                    w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    xv[u] = w[u];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) fma4(acc, xv[u], w[u]);
-        }
-    }
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
-}
-
+//
 // Deep edition: the kernel is latency bound (DRAM 33 %, L2 25 % busy; 72 % of issue slots have no eligible warp), so what
 // matters is how many filter-row loads are in flight per SM.  Eight filter rows are requested per step, but the gather
 // operand (an L1/L2 hit) is fetched in two halves so that the register budget still allows four CTAs per SM.
@@ -93,7 +38,9 @@ cfconv_gather_deep_kernel(const float* __restrict__ filt, const int32_t* __restr
     const int lane = threadIdx.x & 31;
     const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (wid >= n_atoms) return;
-    const int row = n_atoms - 1 - wid;      // rows last to first: own (contiguous) block first, shared rows then hit L2
+    // Rows are walked LAST to first: a row's own (contiguous) block of filter rows is touched first and the rows it shares
+    // were touched just before; in the forward the tail of the freshly written filter tensor is also what L2 still holds.
+    const int row = n_atoms - 1 - wid;
     const int f = (lane % LPR) * 4, sub = lane / LPR;
     const int b = __ldg(ptr + row), end = __ldg(ptr + row + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -216,86 +163,6 @@ cfconv_gather_async_kernel(const float* __restrict__ filt, const int32_t* __rest
     *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
 }
 
-// Windowed edition: the ROWS consecutive rows of a CTA belong to one or two molecules, so the atoms they gather from sit
-// in a short contiguous index range.  That window of `v` (x or grad_out rows) is staged in shared memory once per CTA and
-// the per-edge gathers read it from there; the L2 -> SM traffic of the gather operand drops by ~ROWS x and only the filter
-// rows remain as long-latency loads.  Atoms outside the window (large graphs) fall back to the global gather.
-template <int F, int UNROLL, bool TRANSPOSED, int ROWS, int WIN, int MINB>
-__global__ void __launch_bounds__(ROWS * 32, MINB)
-cfconv_gather_win_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ v,
-                         const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx_a, const int32_t* __restrict__ idx_b,
-                         int n_atoms, float* __restrict__ out) {
-    constexpr int LPR = F / 4, EPW = 32 / LPR;
-    __shared__ __align__(16) float sv[WIN * F];
-    __shared__ int s_first[ROWS], s_last[ROWS];
-    pdl_launch_dependents();
-    pdl_wait();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int n_blocks = gridDim.x;
-    // forward walks the CTAs last to first (the tail of the freshly written filter tensor is what L2 still holds)
-    const int blk = TRANSPOSED ? blockIdx.x : n_blocks - 1 - blockIdx.x;
-    const int row = blk * ROWS + w;
-    const bool live = row < n_atoms;
-    int b = 0, end = 0;
-    if (live) { b = __ldg(ptr + row); end = __ldg(ptr + row + 1); }
-    if (lane == 0) {                                               // gather indices ascend within a row
-        s_first[w] = (end > b) ? __ldg(idx_b + b) : 0x7fffffff;
-        s_last[w] = (end > b) ? __ldg(idx_b + end - 1) : -1;
-    }
-    __syncthreads();
-    int lo = 0x7fffffff, hi = -1;
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) { lo = min(lo, s_first[r]); hi = max(hi, s_last[r]); }
-    const int cnt = (hi >= lo) ? min(hi - lo + 1, WIN) : 0;
-    for (int i = threadIdx.x; i < cnt * LPR; i += ROWS * 32)
-        *reinterpret_cast<float4*>(sv + i * 4) = ldg4(v + (int64_t)lo * F + i * 4);
-    __syncthreads();
-    if (!live) return;
-    const int f = (lane % LPR) * 4, sub = lane / LPR;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = b; base < end; base += 32) {
-        const int mine = base + lane;
-        int my_a = 0, my_b = 0;
-        if (mine < end) {
-            const int e = TRANSPOSED ? __ldg(idx_a + mine) : mine;
-            my_a = filt_row ? __ldg(filt_row + e) : e;               // shared filter row of the undirected pair
-            my_b = __ldg(idx_b + mine);
-        }
-        const int n_here = min(32, end - base);
-        for (int k0 = 0; k0 < n_here; k0 += EPW * UNROLL) {          // warp-uniform trip count (shuffles inside)
-            float4 wv[UNROLL];
-            int rb[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int k = k0 + sub + u * EPW;
-                const int ra = __shfl_sync(0xffffffffu, my_a, k & 31);
-                rb[u] = __shfl_sync(0xffffffffu, my_b, k & 31);
-                if (k < n_here) {
-                    wv[u] = ld_stream4(filt + (int64_t)ra * F + f);
-                } else {
-                    wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    rb[u] = lo;                                      // any staged row: multiplied by zero
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int o = rb[u] - lo;
-                const float4 xv = (o >= 0 && o < cnt) ? *reinterpret_cast<const float4*>(sv + o * F + f)
-                                                      : ldg4(v + (int64_t)rb[u] * F + f);
-                fma4(acc, xv, wv[u]);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if (sub == 0) *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
-}
-
 template <int F>
 __global__ void __launch_bounds__(256)
 cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, const int32_t* __restrict__ rowptr,
@@ -318,41 +185,24 @@ template <bool TRANSPOSED>
 static void launch_async(int blocks, cudaStream_t st, const float* filt, const int32_t* filt_row, const float* v, const int32_t* ptr,
                          const int32_t* idx_a, const int32_t* idx_b, int n, float* out) {
     constexpr int kSmem = 8 * 2 * 8 * 32 * 16;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaFuncSetAttribute(cfconv_gather_async_kernel<TRANSPOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        configured = true;
+        configured.set();
     }
     launch_pdl(cfconv_gather_async_kernel<TRANSPOSED>, dim3(blocks), dim3(256), (size_t)kSmem, st, filt, filt_row, v, ptr, idx_a, idx_b, n, out);
 }
 
-// Tuning switch (geossl_debug_set_cfconv_variant): bits 0-2 forward, 3-5 backward.  3 = async edition (default; F = 128,
-// other widths take the deep edition), 7 = deep edition, 0-2 = plain gather at other unroll / occupancy points, 4-6 =
-// windowed edition.  Measured alone on the bench workload (us, forward / backward): plain 45.9 / 33.4, windowed 41.4 /
-// 43.5, deep 31.1 / 31.3; on a slower box of the pool deep 40.7 / 41.3, async 36.7 / 37.7 -- the kernel is latency bound,
-// what pays is filter rows in flight, not less L2 traffic for the gather operand (profiles/tune_cfconv.py).  All editions
-// accumulate in edge order and agree bit for bit.
-static int g_variant = 3 | (3 << 3);
-
+// F = 128 takes the cp.async edition, narrower models the deep register edition; both accumulate in edge order and agree
+// bit for bit.  (Round-1 A/B of four editions: profiles/r01_v26_tune_cfconv.txt, r01_v32_tune_cfconv.txt -- the kernel is
+// latency bound, what pays is filter rows in flight, not less L2 traffic for the gather operand.)
 template <int F>
 int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src, int64_t n,
                float* out, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    constexpr int kWin = 8192 / F;                                  // 32 KB of staged rows: 64 atoms at F = 128
-    switch (g_variant & 7) {
-        case 1: launch_pdl(cfconv_gather_kernel<F, 8, false, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        case 2: launch_pdl(cfconv_gather_kernel<F, 8, false, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        case 3:
-            if constexpr (F == 128) launch_async<false>(blocks, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
-            else launch_pdl(cfconv_gather_deep_kernel<F, false>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
-            break;
-        case 0: launch_pdl(cfconv_gather_kernel<F, 4, false, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        case 7: launch_pdl(cfconv_gather_deep_kernel<F, false>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        case 5: launch_pdl(cfconv_gather_win_kernel<F, 4, false, 8, kWin, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        case 6: launch_pdl(cfconv_gather_win_kernel<F, 4, false, 8, kWin, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out); break;
-        default: launch_pdl(cfconv_gather_win_kernel<F, 8, false, 8, kWin, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
-    }
+    if constexpr (F == 128) launch_async<false>(blocks, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
+    else launch_pdl(cfconv_gather_deep_kernel<F, false>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
     return 0;
 }
 template <int F>
@@ -360,20 +210,8 @@ int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, con
                  int64_t n, float* dx, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    constexpr int kWin = 8192 / F;
-    switch ((g_variant >> 3) & 7) {
-        case 1: launch_pdl(cfconv_gather_kernel<F, 4, true, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        case 2: launch_pdl(cfconv_gather_kernel<F, 8, true, 2>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        case 3:
-            if constexpr (F == 128) launch_async<true>(blocks, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
-            else launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
-            break;
-        case 0: launch_pdl(cfconv_gather_kernel<F, 8, true, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        case 7: launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        case 5: launch_pdl(cfconv_gather_win_kernel<F, 4, true, 8, kWin, 4>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        case 6: launch_pdl(cfconv_gather_win_kernel<F, 4, true, 8, kWin, 6>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx); break;
-        default: launch_pdl(cfconv_gather_win_kernel<F, 8, true, 8, kWin, 3>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
-    }
+    if constexpr (F == 128) launch_async<true>(blocks, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
+    else launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
     return 0;
 }
 template <int F>
@@ -397,8 +235,6 @@ using namespace geossl;
     }
 
 extern "C" {
-
-int geossl_debug_set_cfconv_variant(int v) { g_variant = v; return 0; }
 
 int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src,
                       int64_t n_atoms, int F, float* out, void* stream) {

@@ -20,6 +20,15 @@ void count_launch(int n = 1);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: every launcher remembers per
+// (call site, device) whether it has opted in, so a process that touches several GPUs configures each of them.
+struct PerDeviceFlag {
+    bool done[64] = {};
+    static int device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < 64) ? d : 0; }
+    bool get() const { return done[device()]; }
+    void set() { done[device()] = true; }
+};
+
 #define GEOSSL_REQUIRE(cond, msg)                                            \
     do {                                                                     \
         if (!(cond)) {                                                       \

@@ -478,11 +478,11 @@ static int head_grid(int64_t n_pairs) {
 template <int H>
 int launch_head_fwd(const HeadIn& in, float* workspace, float* loss, cudaStream_t st) {
     const size_t smem = HeadCfg<H>::kFloats * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(ddm_head_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.set();
     }
     const int grid = head_grid(in.n_pairs);
     ddm_head_fwd_kernel<H><<<grid, 256, smem, st>>>(in, workspace);
@@ -497,11 +497,11 @@ template <int H>
 int launch_head_bwd(const HeadIn& in, int64_t n_atoms, const float* loss_aux, const float* grad_loss, float* workspace,
                     float* grad_h, const geossl_ddm_grads& g, cudaStream_t st) {
     const size_t smem = HeadCfg<H>::kFloats * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(ddm_head_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.set();
     }
     cudaError_t e = cudaMemsetAsync(grad_h, 0, sizeof(float) * (size_t)n_atoms * H, st);
     if (e != cudaSuccess) return (int)e;
@@ -1153,10 +1153,10 @@ int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
                    "null input pointer");
     const size_t smem = tc::HeadSmem::kBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::ddm_head_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.set();
     }
     const int grid = head_grid(n_pairs);
     const int64_t n_pad = head_pad(n_pairs);
@@ -1185,10 +1185,10 @@ int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
                    "null input pointer");
     const size_t smem = tc::HeadSmem::kBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::ddm_head_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.set();
     }
     GEOSSL_CUDA(cudaMemsetAsync(grad_h, 0, sizeof(float) * (size_t)n_atoms * 128, as_stream(stream)));
     const int grid = head_grid(n_pairs);

@@ -500,11 +500,11 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
     GEOSSL_REQUIRE(F == 128, "the tensor-core filter kernel is built for num_filters = 128");
     GEOSSL_REQUIRE(G >= 1 && G <= 63, "num_gaussians must be in [1,63] (column 63 of the rbf tile carries the bias sum)");
     const size_t smem = tc::BwdLayout::kBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.set();
     }
     if (pair_atoms) {
         GEOSSL_CUDA(launch_pdl(tc::filter_bwd_tc_kernel<true>, dim3(kNumSM), dim3(tc::kBwdThreads), smem, as_stream(stream),

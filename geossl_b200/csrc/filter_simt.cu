@@ -342,11 +342,11 @@ int launch_filter_fwd(const float* edge_dist, const int32_t* n_edges_dev, int64_
                       float coeff, float cutoff, int G, const float* w1, const float* b1, const float* w2,
                       const float* b2, float* filt, cudaStream_t st) {
     const size_t smem = FwdSmem<F>::kFloats * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(filter_fwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.set();
     }
     filter_fwd_kernel<F><<<filter_grid(capacity), 256, smem, st>>>(edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G,
                                                                     w1, b1, w2, b2, filt);
@@ -360,11 +360,11 @@ int launch_filter_bwd(const float* edge_dist, const int32_t* n_edges_dev, int64_
                       const float* grad_filt, float* workspace, float* gw1, float* gb1, float* gw2, float* gb2,
                       cudaStream_t st) {
     const size_t smem = BwdSmem<F>::kFloats * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(filter_bwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.set();
     }
     filter_bwd_kernel<F><<<kNumSM, 256, smem, st>>>(edge_dist, n_edges_dev, capacity, offset, coeff, cutoff, G, w1, b1, w2,
                                                     x, grad_out, src, edge_tgt, grad_filt, workspace);

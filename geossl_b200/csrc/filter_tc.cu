@@ -441,11 +441,11 @@ int geossl_filter_fwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
     const size_t smem = tc::FwdLayout::kBytes + 1024;
     int64_t tiles = (capacity + tc::kTile - 1) / tc::kTile;
     const int grid = (int)(tiles < kNumSM ? tiles : kNumSM);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::filter_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.set();
     }
     if (bf16_parts) {
         GEOSSL_CUDA(launch_pdl(tc::filter_fwd_tc_kernel<false>, dim3(grid), dim3(tc::kThreads), smem, as_stream(stream), edge_dist,

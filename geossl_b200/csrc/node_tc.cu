@@ -409,11 +409,11 @@ static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weigh
         // tensor pipe / shared memory during the same phases), half as many weight-image fetches
         constexpr int NR = 128;
         const size_t smem = tc::LinLayoutT<NR>::kBytes + 1024;
-        static bool configured = false;                        // one flag per instantiation
-        if (!configured) {
+        static PerDeviceFlag configured;                        // one flag per instantiation
+        if (!configured.get()) {
             GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
+            configured.set();
         }
         const int64_t tiles = (n_rows + NR - 1) / NR;
         GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, dim3((unsigned)(tiles < kNumSM ? tiles : kNumSM)),
@@ -423,11 +423,11 @@ static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weigh
     }
     constexpr int NR = 64;
     const size_t smem = tc::LinLayoutT<NR>::kBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-        configured = true;
+        configured.set();
     }
     GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, dim3(tc::node_grid(n_rows)), dim3(4 * NR), smem, st,
                            x, n_rows, weight, bias, z, r, y));
@@ -491,10 +491,10 @@ int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, 
                            float* grad_weight, float* grad_bias, void* stream) {
     GEOSSL_REQUIRE(grad_y && x && workspace && grad_weight && n_rows > 0, "null pointer or empty input");
     const size_t smem = tc::WgLayout::kBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.set();
     }
     const int grid = tc::wgrad_grid(n_rows);
     GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid), dim3(256), smem, as_stream(stream), grad_y, x, n_rows, pre_ssp, workspace));

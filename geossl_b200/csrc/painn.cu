@@ -280,11 +280,11 @@ int launch_msg_fwd(const float* q, const float* mu, const float* x, const float*
                    const int32_t* i_rowptr, const int32_t* i_eid, const int32_t* i_nbr, int64_t n_atoms,
                    float* q_out, float* mu_out, cudaStream_t st) {
     const size_t smem = (size_t)(3 * F * R + 3 * F) * sizeof(float);
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
+    static PerDeviceFlag configured;
+    if (!configured.get() && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(painn_message_fwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.set();
     }
     int64_t blocks = (n_atoms + 7) / 8;
     if (blocks > kNumSM * 4) blocks = kNumSM * 4;
@@ -299,11 +299,11 @@ int launch_msg_bwd(const float* gq_out, const float* gmu_out, const float* mu, c
                    const float* fcut, const int32_t* j_rowptr, const int32_t* j_ctr, int64_t n_atoms, int64_t n_edges,
                    float* gx, float* gmu_in, float* gfilt, float* workspace, float* gw, float* gb, cudaStream_t st) {
     const size_t smem = (size_t)(3 * F * R + 3 * F) * sizeof(float);
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
+    static PerDeviceFlag configured;
+    if (!configured.get() && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(painn_message_bwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.set();
     }
     int64_t blocks = (n_atoms + 7) / 8;
     if (blocks > kNumSM * 4) blocks = kNumSM * 4;

@@ -35,6 +35,10 @@ class CollatedStore:
     def __init__(self, data, slices):
         self.data = dict(data)
         self.slices = {k: torch.as_tensor(v, dtype=torch.long) for k, v in slices.items()}
+        # keys whose per-molecule edge lists are known to be (target, source)-sorted because THIS package's neighbour
+        # kernel wrote them (add_radius_edges).  Lists read from a reference file come from torch_cluster's CPU KD-tree
+        # search, whose order inside a target row is not guaranteed: they take the one-time check + stable sort.
+        self.sorted_edge_keys = set()
 
     def __len__(self):
         return int(next(iter(self.slices.values())).numel()) - 1
@@ -152,6 +156,7 @@ def add_radius_edges(store, radius, device="cuda", max_num_neighbors=32, chunk_a
         per_mol.append(rp[atom_off[lo + 1:hi + 1] - a0] - rp[atom_off[lo:hi] - a0])
         lo = hi
     store.data[key] = torch.cat(pieces, dim=1) if pieces else torch.empty((2, 0), dtype=torch.long)
+    store.sorted_edge_keys.add(key)
     store.slices[key] = torch.from_numpy(np.concatenate([[0], np.cumsum(np.concatenate(per_mol))]) if per_mol
                                          else np.zeros(1, np.int64)).long()
     return store
@@ -169,5 +174,6 @@ def batch_from_store(store, indices, device="cuda", option="combination", ratio=
     if "radius_edge_index" in store.data:
         off = np.concatenate([[0], np.cumsum(counts)])
         b.radius_edge_index = torch.cat([d["radius_edge_index"] + int(off[i]) for i, d in enumerate(mols)], dim=1).to(device)
-        b.extras["rei_sorted"] = True                              # per-molecule target-sorted lists, molecule-major
+        # only lists written by add_radius_edges are known to be sorted (per-molecule target-sorted, molecule-major)
+        b.extras["rei_sorted"] = "radius_edge_index" in store.sorted_edge_keys
     return b

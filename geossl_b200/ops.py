@@ -17,13 +17,18 @@ MAX_NEIGHBORS_DEFAULT = 32      # torch_cluster.radius_graph default, never over
 
 class _KernelTimers:
     """Optional CUDA-event brackets around named C-ABI calls (bench.py's live per-kernel durations).
-    Events are recorded on torch's current stream, which is the stream every kernel here is launched on."""
+    Events are recorded on torch's current stream, which is the stream every kernel here is launched on.
+
+    ``enable(names, in_graph=True)``: the events are created ``external=True`` so that, recorded while a stream is being
+    captured, they become event-record NODES of the CUDA graph; every replay re-records them and ``collect_replay()``
+    reads the durations of the kernels as they ran inside the replayed step (back to back, warm instruction cache, no
+    host enqueue gap between the opening record and the launch -- the eager brackets of round 1 included that gap)."""
 
     def __init__(self):
-        self.names, self.events = frozenset(), {}
+        self.names, self.events, self.in_graph = frozenset(), {}, False
 
-    def enable(self, names):
-        self.names, self.events = frozenset(names), {}
+    def enable(self, names, in_graph=False):
+        self.names, self.events, self.in_graph = frozenset(names), {}, in_graph
 
     def disable(self):
         self.names = frozenset()
@@ -31,18 +36,29 @@ class _KernelTimers:
     def start(self, name):
         if name not in self.names:
             return None
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kw = {"external": True} if self.in_graph else {}
+        a, b = torch.cuda.Event(enable_timing=True, **kw), torch.cuda.Event(enable_timing=True, **kw)
         a.record()
         self.events.setdefault(name, []).append((a, b))
         return b
 
+    def _stats(self, per_name):
+        return {name: {"n": len(ts), "total_ms": sum(ts), "mean_ms": sum(ts) / max(len(ts), 1)} for name, ts in per_name.items()}
+
     def collect(self):
         torch.cuda.synchronize()
-        out = {}
+        return self._stats({name: [a.elapsed_time(b) for a, b in pairs] for name, pairs in self.events.items()})
+
+    def collect_replay(self, acc=None):
+        """After one replay of the instrumented graph (+ synchronize): append this replay's durations to ``acc``."""
+        torch.cuda.synchronize()
+        acc = {} if acc is None else acc
         for name, pairs in self.events.items():
-            ts = [a.elapsed_time(b) for a, b in pairs]
-            out[name] = {"n": len(ts), "total_ms": sum(ts), "mean_ms": sum(ts) / max(len(ts), 1)}
-        return out
+            acc.setdefault(name, []).extend(a.elapsed_time(b) for a, b in pairs)
+        return acc
+
+    def stats(self, acc):
+        return self._stats(acc)
 
 
 KERNEL_TIMERS = _KernelTimers()
@@ -57,8 +73,10 @@ def _timed(name, rc_fn):
     check(rc, name)
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """torch's current stream on ``device`` (default: the current device).  Callers run under
+    ``torch.cuda.device_of(tensor)`` semantics: one process drives one GPU."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -425,8 +443,12 @@ def _linear_tc(x, weight, transpose, bias, pre_ssp, act_grad_input, residual, bf
 # Weight-gradient kernels are off the critical path of the backward chain (nothing upstream consumes them), and they are
 # small, latency-bound launches.  Inside ``side_stream_wgrads()`` they are issued on a second stream so that they fill the
 # gaps of the main chain; ``join_side_stream()`` must run before anything reads the gradients (optimizer, all-reduce).
+# Autograd knows nothing about that second stream (it would sum two uses of a weight, or add into an existing
+# ``p.grad``, on the main stream while the side-stream kernel is still writing), so these gradients never pass through
+# autograd: backward returns None for them, the kernels write into private buffers, and ``join_side_stream()`` -- after
+# the main stream has waited for the side stream -- assigns / accumulates them into ``p.grad`` in launch order.
 # Off by default: a caller that runs loss.backward(); optimizer.step() itself never sees a second stream.
-_SIDE = {"on": False, "stream": {}, "dirty": False}
+_SIDE = {"on": False, "stream": {}, "dirty": False, "pending": []}
 
 
 class side_stream_wgrads:
@@ -451,6 +473,12 @@ def join_side_stream():
         for dev, st in _SIDE["stream"].items():
             torch.cuda.current_stream(dev).wait_stream(st)
         _SIDE["dirty"] = False
+    pending, _SIDE["pending"] = _SIDE["pending"], []
+    for param, buf in pending:                      # main stream, after the wait: plain stream-ordered accumulation
+        if param.grad is None:
+            param.grad = buf
+        else:
+            param.grad.add_(buf)
 
 
 class LinearTC(torch.autograd.Function):
@@ -466,6 +494,7 @@ class LinearTC(torch.autograd.Function):
         residual = None if residual is None else _req(residual, torch.float32, "residual", 2)
         ctx.pre_ssp, ctx.has_bias, ctx.has_res = bool(pre_ssp), bias is not None, residual is not None
         ctx.image_t = None if images is None else images[1]
+        ctx.params = (weight, bias)             # the leaf objects themselves (deferred side-stream accumulation)
         ctx.save_for_backward(x, weight)
         if x.size(0) == 0:
             return x.new_zeros((0, 128))
@@ -481,7 +510,7 @@ class LinearTC(torch.autograd.Function):
         gx = gw = gb = None
         if n == 0:
             return (torch.zeros_like(x), torch.zeros_like(weight), torch.zeros(128, device=x.device) if ctx.has_bias else None,
-                    gy if ctx.has_res else None, None)
+                    gy if ctx.has_res else None, None, None)
         if ctx.needs_input_grad[0]:
             gx = _linear_tc(gy, weight, True, None, False, x if ctx.pre_ssp else None, None, True, "linear_dgrad", ctx.image_t)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
@@ -495,7 +524,9 @@ class LinearTC(torch.autograd.Function):
                                                                           _p(gb_), _stream()))
                 return gw_, gb_
 
-            if _SIDE["on"]:
+            wp, bp = ctx.params
+            deferrable = wp.is_leaf and wp.requires_grad and (bp is None or (bp.is_leaf and bp.requires_grad))
+            if _SIDE["on"] and deferrable:
                 main, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
@@ -506,6 +537,10 @@ class LinearTC(torch.autograd.Function):
                     if t is not None:
                         t.record_stream(main)
                 _SIDE["dirty"] = True
+                _SIDE["pending"].append((wp, gw))
+                if gb is not None:
+                    _SIDE["pending"].append((bp, gb))
+                gw = gb = None                  # handed to join_side_stream(), not to autograd
             else:
                 gw, gb = wgrad()
         return gx, gw, gb, (gy if ctx.has_res else None), None, None
@@ -680,9 +715,12 @@ def _painn_structure(radius_edge_index, n_atoms, batch, num_graphs, assume_sorte
     pretrain_GeoSSL.py:190-191).  Falls back to a stable sort if the list is not (idx_j, idx_i)-sorted; the check
     costs one host sync, ``assume_sorted=True`` (lists produced by radius_graph are sorted) skips it so that the step
     can be captured in a CUDA graph."""
-    key = (radius_edge_index.data_ptr(), radius_edge_index._version, tuple(radius_edge_index.shape), n_atoms)
+    key = (radius_edge_index.data_ptr(), radius_edge_index._version, tuple(radius_edge_index.shape), n_atoms,
+           batch.data_ptr(), num_graphs)
     hit = _structure_cache.get(key)
-    if hit is not None and not torch.cuda.is_current_stream_capturing():
+    # the entry keeps its source tensors alive, so a recycled address can only hit with the very same objects
+    if hit is not None and hit.key_rei is radius_edge_index and hit.key_batch is batch \
+            and not torch.cuda.is_current_stream_capturing():
         return hit
     rei = _req(radius_edge_index, torch.int64, "radius_edge_index", 2)
     if rei.size(1) > 1 and not assume_sorted:
@@ -692,6 +730,7 @@ def _painn_structure(radius_edge_index, n_atoms, batch, num_graphs, assume_sorte
             rei = rei[:, perm].contiguous()
     g = csr_from_edge_index(rei, n_atoms, batch, num_graphs=num_graphs).ensure_transpose()
     g.rei = rei
+    g.key_rei, g.key_batch = radius_edge_index, batch
     if len(_structure_cache) > 8:
         _structure_cache.clear()
     _structure_cache[key] = g

@@ -278,7 +278,11 @@ class GraphedTrainStep:
     The optimizer must be capturable (``torch.optim.Adam(..., capturable=True)``).
     """
 
-    def __init__(self, args, example_batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_sync=None, warmup=3):
+    def __init__(self, args, example_batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_sync=None, warmup=3,
+                 kernel_timers=None):
+        """``kernel_timers``: names of C-ABI calls to bracket with event-record NODES inside the captured graph
+        (ops.KERNEL_TIMERS, in-graph mode): after each replay ``ops.KERNEL_TIMERS.collect_replay()`` returns the
+        durations of those kernels as they ran inside the step.  Used by bench.py on a second, instrumented capture."""
         self.args, self.model, self.heads, self.optimizer = args, model, heads, optimizer
         b = example_batch
         dev = b.positions.device
@@ -305,8 +309,14 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
-            self.loss = run()
+        if kernel_timers:
+            ops.KERNEL_TIMERS.enable(kernel_timers, in_graph=True)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = run()
+        finally:
+            if kernel_timers:
+                ops.KERNEL_TIMERS.disable()
 
     def matches(self, batch):
         s = self.static

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GEOSSL_ABI_VERSION 2   /* 2: filt_row / pair-index / batched-pack entry points */
+#define GEOSSL_ABI_VERSION 3   /* 2: filt_row / pair-index / batched-pack entry points; 3: round-2 entry points */
 #define GEOSSL_EINVAL (-1)   /* bad argument (null pointer, unsupported width, ...) */
 #define GEOSSL_ECAP   (-2)   /* capacity too small */
 
@@ -128,9 +128,6 @@ int geossl_debug_set_trace_linear(long long* device_buffer); /* atom-wise dense 
  * mode 1: d[m][n] = sum_k a[k][m] b[k][n]  (a (128,128), b (128,N), N in {64,128}; MN-major operands)
  * mode 2: throughput probe (cycle counts in d[0..1]);  mode 3: as mode 0 with A resident in tensor memory, b (N,K) */
 int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K, int N, float* d, void* stream);
-
-/* Tuning switch for the cfconv gather kernels (0 = default; 1-3 = other unroll / occupancy points; profiles/tune_cfconv.py). */
-int geossl_debug_set_cfconv_variant(int variant);
 
 /* m_i = sum_{e in row i} x[src_e] * W_row(e)   (atomic-free segmented reduction, one warp per row).
  * filt_row: NULL => row(e) = e (one filter row per directed edge); else row(e) = filt_row[e] (the pair_of_edge map of

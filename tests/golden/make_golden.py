@@ -118,8 +118,10 @@ def ncsn_case(name, *, seed, emb, levels, anneal_power, num_graphs, atoms, atoms
 
 
 def ddm_case(name, *, seed, model_3d, emb, num_graphs, atoms, atoms_max=None, levels=50, anneal_power=2.0,
-             sigma=0.3, **enc):
-    """The DDM step of pretrain_GeoSSL.py:179-212 driven on the reference modules."""
+             sigma=0.3, store_reprs=True, **enc):
+    """The DDM step of pretrain_GeoSSL.py:179-212 driven on the reference modules.  ``store_reprs=False`` drops the two
+    (N,H) representations from the file (the bench-sized fixture would otherwise be 8 MB larger); loss, both head losses
+    and every parameter gradient are always stored."""
     torch.manual_seed(seed)
     if model_3d == "schnet":
         model = SchNet(hidden_channels=emb, num_filters=enc["filters"], num_interactions=enc["layers"],
@@ -163,7 +165,8 @@ def ddm_case(name, *, seed, model_3d, emb, num_graphs, atoms, atoms_max=None, le
     save(name, cfg,
          **{"in": ins, "sd": dict(model.state_dict()), "sd1": dict(heads[0].state_dict()),
             "sd2": dict(heads[1].state_dict()),
-            "out": dict(loss=loss, loss_01=loss_01, loss_02=loss_02, repr_01=repr_01, repr_02=repr_02),
+            "out": dict(loss=loss, loss_01=loss_01, loss_02=loss_02,
+                        **(dict(repr_01=repr_01, repr_02=repr_02) if store_reprs else {})),
             "grad": grads_of(model), "grad1": grads_of(heads[0]), "grad2": grads_of(heads[1])})
 
 
@@ -270,11 +273,17 @@ def ssl_case(name, *, seed, hidden, filters, gaussians, layers, cutoff, num_grap
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])            # optional: names of the fixtures to (re)generate
+
+    def _wrap(fn):
+        return lambda name, **kw: fn(name, **kw) if (not only or name in only) else None
+    schnet_case, painn_case, ncsn_case, ddm_case, md17_case, ssl_case = map(
+        _wrap, (schnet_case, painn_case, ncsn_case, ddm_case, md17_case, ssl_case))
     schnet_case("schnet_small", seed=11, hidden=32, filters=32, gaussians=20, layers=2, cutoff=10.0,
                 readout="mean", num_graphs=5, atoms=4, atoms_max=12)
     schnet_case("schnet_trunc", seed=12, hidden=32, filters=64, gaussians=51, layers=2, cutoff=10.0,
                 readout="add", num_graphs=3, atoms=36, atoms_max=60, density=0.08)
-    # (full-size SchNet, H=F=128 / G=50 / L=6, is pinned by ddm_schnet_cfg1 below)
+    # (full-size SchNet, H=F=128 / G=50 / L=6, is pinned by ddm_schnet_full4 / _cfg1 / _cfg2 below)
     painn_case("painn_small", seed=21, feat=32, layers=2, rbf=20, cutoff=5.0, readout="add",
                num_graphs=5, atoms=4, atoms_max=14)
     painn_case("painn_full", seed=22, feat=128, layers=3, rbf=20, cutoff=5.0, readout="add",
@@ -284,7 +293,12 @@ if __name__ == "__main__":
               option="permutation")
     ddm_case("ddm_schnet_small", seed=41, model_3d="schnet", emb=32, num_graphs=6, atoms=5, atoms_max=14,
              filters=32, gaussians=20, layers=2, cutoff=10.0)
-    ddm_case("ddm_schnet_cfg1", seed=42, model_3d="schnet", emb=128, num_graphs=4, atoms=30,
+    ddm_case("ddm_schnet_full4", seed=42, model_3d="schnet", emb=128, num_graphs=4, atoms=30,
+             filters=128, gaussians=50, layers=6, cutoff=10.0)
+    # BASELINE.json configs[0] and configs[1] at their real batch sizes (32 x 30 and 256 x 30 atoms, full model)
+    ddm_case("ddm_schnet_cfg1", seed=44, model_3d="schnet", emb=128, num_graphs=32, atoms=30,
+             filters=128, gaussians=50, layers=6, cutoff=10.0)
+    ddm_case("ddm_schnet_cfg2", seed=45, model_3d="schnet", emb=128, num_graphs=256, atoms=30, store_reprs=False,
              filters=128, gaussians=50, layers=6, cutoff=10.0)
     ddm_case("ddm_painn_small", seed=43, model_3d="painn", emb=32, num_graphs=6, atoms=5, atoms_max=14,
              layers=2, rbf=20, cutoff=5.0)

@@ -73,7 +73,8 @@ def test_ncsn_oracle(name):
     check_grads(sd, {k: v for k, v in g["grad"].items() if k != "node_feature"})
 
 
-@pytest.mark.parametrize("name", ["ddm_schnet_small", "ddm_schnet_cfg1", "ddm_painn_small"])
+@pytest.mark.parametrize("name", ["ddm_schnet_small", "ddm_schnet_full4", "ddm_schnet_cfg1", "ddm_schnet_cfg2",
+                                  "ddm_painn_small"])
 def test_ddm_oracle(name):
     g = Golden(name)
     c, i = g.cfg, g["in"]
@@ -87,7 +88,8 @@ def test_ddm_oracle(name):
                                         i["super_edge_index"], (i["noise_level_1"], i["distance_noise_1"]),
                                         (i["noise_level_2"], i["distance_noise_2"]), c["anneal_power"])
     o = g["out"]
-    assert rel_err(r1, o["repr_01"]) <= TOL and rel_err(r2, o["repr_02"]) <= TOL
+    if "repr_01" in o:                           # (the 256-molecule fixture stores losses and gradients only)
+        assert rel_err(r1, o["repr_01"]) <= TOL and rel_err(r2, o["repr_02"]) <= TOL
     assert rel_err(l1, o["loss_01"]) <= TOL and rel_err(l2, o["loss_02"]) <= TOL and rel_err(loss, o["loss"]) <= TOL
     loss.backward()
     check_grads(sd, g["grad"]); check_grads(sd1, g["grad1"]); check_grads(sd2, g["grad2"])
@@ -124,10 +126,10 @@ def test_reference_crosscheck_when_available():
 
 
 def test_head_gradient_is_discontinuous_at_1e_6():
-    """Why the tensor-core path states a 2e-3 bound on the DDM-head gradients of ddm_schnet_cfg1: perturbing the node
+    """Why the tensor-core path states a looser bound on the DDM-head gradients of the small full-model fixture: perturbing the node
     representation by 1e-6 (relative to max|h|) on the CPU oracle itself flips ReLU masks of the score MLP and moves
     parameter gradients by ~7e-4, while the loss moves by < 1e-6."""
-    g = Golden("ddm_schnet_cfg1")
+    g = Golden("ddm_schnet_full4")
     c, i = g.cfg, g["in"]
     d02 = O.pair_distance(i["pos"] + i["pos_noise"], i["super_edge_index"])
 
