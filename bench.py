@@ -227,17 +227,28 @@ def run_product(args):
     torch.manual_seed(1234 + rank)
 
     B = CFG["batch_per_gpu"]
-    if args.atoms_max:
-        args.no_graph = True
     host_pool = [synthetic_batch(B, CFG["atoms"] if not args.atoms_max else 10, args.atoms_max or None, seed=10_000 * rank + i)
                  for i in range(args.pool)]
+    if args.atoms_max:
+        # variable-size molecules: every batch is padded to ONE capacity (data.pad_batch) so that a single captured graph
+        # serves the stream; capacity = the largest batch of the pool + 2 %, rounded up
+        from geossl_b200.data import pad_batch
+        n_cap = -(-int(1.02 * max(hb.positions.size(0) for hb in host_pool)) // 128) * 128
+        p_cap = -(-int(1.02 * max(hb.super_edge_index.size(1) for hb in host_pool)) // 1024) * 1024
+        live_atoms = [hb.positions.size(0) for hb in host_pool]
+        host_pool = [pad_batch(hb, n_cap, p_cap) for hb in host_pool]
     if args.model == "painn":
         # dataset-time radius graph (datasets_3D_Radius.py:120) on the clean coordinates, reused for both views
         from geossl_b200 import ops as _ops
+        from geossl_b200.data import pad_batch
         for hb in host_pool:
             g0 = _ops.radius_csr(hb.positions.to(dev), hb.batch.to(dev), 5.0, num_graphs=B, transpose=False)
             hb.radius_edge_index = g0.edge_index.cpu()
             hb.extras["rei_sorted"] = True
+        # edge lists differ in length per batch: pad every batch to one edge capacity so that ONE captured graph serves all
+        live_edges = [hb.radius_edge_index.size(1) for hb in host_pool]
+        e_cap = -(-int(1.03 * max(live_edges)) // 1024) * 1024
+        host_pool = [pad_batch(hb, hb.positions.size(0), hb.super_edge_index.size(1), e_cap) for hb in host_pool]
     host_pool = [hb.pin_memory() for hb in host_pool]
     dev_pool = [b.to(dev) for b in host_pool]
     h2d_bytes = sum(t.numel() * t.element_size() for t in (host_pool[0].x, host_pool[0].positions, host_pool[0].batch,
@@ -270,7 +281,7 @@ def run_product(args):
         step(dev_pool[i % args.pool])
     barrier()
     eager_step = step
-    if not args.no_graph and args.model == "schnet":       # (PaiNN edge lists differ in length per batch: eager launches)
+    if not args.no_graph:
         graphed = GraphedTrainStep(targs, dev_pool[0], model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync)
         step = graphed
         for i in range(2):
@@ -289,8 +300,8 @@ def run_product(args):
     # back to eager event brackets.
     ktimes = {}
     n_k = min(args.steps, 10)
-    timer_names = ("cfconv_fwd", "filter_fwd", "filter_bwd", "cfconv_bwd_x", "ddm_head_fwd", "ddm_head_bwd",
-                   "linear_fwd", "linear_dgrad", "linear_wgrad")
+    timer_names = ("cfconv_fwd", "filter_fwd", "filter_bwd", "cfconv_bwd_x", "ddm_head_fwd", "ddm_head_bwd", "ddm_head_fused",
+                   "linear_fwd", "linear_dgrad", "linear_wgrad", "painn_message_fwd", "painn_message_bwd")
     if step is not eager_step:
         _lib.launch_count(reset=True)
         probe = GraphedTrainStep(targs, dev_pool[0], model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync, warmup=0,
@@ -324,7 +335,7 @@ def run_product(args):
     landed = [torch.cuda.Event(), torch.cuda.Event()]
     losses_seen = []
 
-    piped = not (args.no_graph or args.model != "schnet")
+    piped = not args.no_graph
     staged = [-1, -1]                                        # which step's batch sits in each staging slot
 
     def e2e_step(i):
@@ -370,13 +381,41 @@ def run_product(args):
     if os.path.exists(pk):
         peaks = {**json.load(open(pk)), "src": "measured"}
     if args.model == "painn":
-        line = {"metric": "GeoSSL-DDM PaiNN train molecules/s (BASELINE configs[2], secondary)", "value": value, "unit": "molecules/s",
+        # roofline of the message kernel (north_star (3)): algorithmic HBM bytes = every per-atom row once (ctx 3F, mu in/out
+        # 3F + 3F, q in/out) + the per-edge scalars and indices; the kernel is in fact fp32-FMA bound (the 3F filter values of
+        # an edge are rebuilt from 20 rbf values: 2*20*3F + 10F FLOP per edge), so the FMA fraction is reported beside it.
+        F_, R = CFG["hidden"], 20
+        n_atoms2, n_edges2 = 2 * dev_pool[0].positions.size(0), 2 * live_edges[0]
+        msg_bytes = 4 * F_ * n_atoms2 * (3 + 3 + 3 + 1 + 1) + n_edges2 * (4 * 5 + 8)
+        msg_flops = n_edges2 * (2 * R * 3 * F_ + 2 * 5 * F_)
+        roof, others = None, {}
+        if "painn_message_fwd" in ktimes:
+            t = ktimes["painn_message_fwd"]["mean_ms"] / 1e3
+            roof = {"kernel": "painn_message_fwd_kernel<128> (PaiNN scalar/vector message, filter rebuilt per edge)", "bound": "hbm",
+                    "achieved": msg_bytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": msg_bytes / t / 1e9 / peaks["hbm_gbs"],
+                    "traffic": None, "peak_source": peaks["src"], "algorithmic_bytes_per_launch": msg_bytes, "mean_ms": 1e3 * t,
+                    "fp32_fma": {"achieved_tflops": msg_flops / t / 1e12, "flops_per_launch": msg_flops,
+                                 "note": "the kernel is bound by the fp32 FMA pipe / shared-memory reads of the filter slice, not by HBM"},
+                    "share_of_step": ktimes["painn_message_fwd"]["total_ms"] / n_k / (ms / args.steps)}
+        for k in ("painn_message_bwd", "ddm_head_fused", "ddm_head_fwd", "ddm_head_bwd", "linear_fwd", "linear_dgrad", "linear_wgrad"):
+            if k in ktimes:
+                others[k] = {"mean_ms": ktimes[k]["mean_ms"], "launches_per_step": ktimes[k]["n"] // n_k,
+                             "share_of_step": ktimes[k]["total_ms"] / n_k / (ms / args.steps)}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cb = cpu_reference(3, 1, budget_s=40.0, model_3d="painn")
+            cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": PAINN_METRIC, "value": value, "unit": "molecules/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[2]: PaiNN GeoSSL-DDM pretraining step, F=128, 3 interactions, 20 RBF, cutoff 5 A, "
-                                       "batch 256 x 30 atoms, eager launches"},
-                "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "clocks": clocks}
+                "config": {"workload": PAINN_WORKLOAD, **CFG, "global_batch": world * B, "parallelism": f"dp{world}",
+                           "launch": "eager" if args.no_graph else "whole step captured in one CUDA graph (edge lists padded to "
+                                     f"{e_cap} columns, {min(live_edges)}..{max(live_edges)} live)",
+                           "kernel_timing": kernel_timing, "edges_per_view": live_edges[0],
+                           "l2": f"{args.pool} distinct batches cycled"},
+                "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_other_kernels": others, "cpu_baseline": cpu}
         _emit(json.dumps(line))
         _finish(world)
         return
@@ -386,7 +425,7 @@ def run_product(args):
     pos2 = torch.cat([b0.positions, b0.positions + CFG["pos_sigma"] * torch.randn_like(b0.positions)])
     g = ops.radius_csr(pos2, torch.cat([b0.batch, b0.batch + B]), CFG["cutoff"], num_graphs=2 * B)
     n_atoms, n_edges, F_, G = pos2.shape[0], g.num_edges, CFG["filters"], CFG["num_gaussians"]
-    n_pairs = b0.super_edge_index.shape[1]
+    n_pairs = int(b0.extras["n_pairs_live"]) if args.atoms_max else b0.super_edge_index.shape[1]
     # filter rows: one per undirected atom pair when the two directions share it (ops.SHARE_PAIR_FILTERS), else one per edge
     shared = ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE != "simt"
     n_rows_w = int(g.ensure_pairs().n_pairs_dev.item()) if shared else n_edges
@@ -410,7 +449,8 @@ def run_product(args):
                                           "the rate a per-edge kernel would need to match this one; not a DRAM rate"}}
         flops = {"filter_fwd": n_rows_w * (2 * G * F_ + 2 * F_ * F_),
                  "filter_bwd": n_rows_w * (2 * (2 * F_ * F_) + 2 * G * F_),      # 78,336 FLOP/row (no recompute counted)
-                 "ddm_head_fwd": n_pairs * 50_048, "ddm_head_bwd": n_pairs * 3 * 50_048}
+                 "ddm_head_fwd": n_pairs * 50_048, "ddm_head_bwd": n_pairs * 3 * 50_048,
+                 "ddm_head_fused": n_pairs * 3 * 50_048}       # one pass = forward + backward (2x forward FLOPs) of one head
         for k, fl in flops.items():
             if k in ktimes:
                 tt = ktimes[k]["mean_ms"] / 1e3
@@ -460,7 +500,8 @@ def run_product(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD if not args.atoms_max else
-                       WORKLOAD + f" -- VARIABLE-SIZE VARIANT: 10..{args.atoms_max} atoms per molecule, eager launches", **CFG, "global_batch": world * B, "atoms_per_launch": n_atoms, "edges_per_launch": n_edges, "views_stacked": 2,
+                       WORKLOAD + f" -- VARIABLE-SIZE VARIANT: 10..{args.atoms_max} atoms per molecule, batches padded to the capacity "
+                       f"({n_cap} atoms, {p_cap} pairs; {min(live_atoms)}..{max(live_atoms)} live atoms) of one captured graph", **CFG, "global_batch": world * B, "atoms_per_launch": n_atoms, "edges_per_launch": n_edges, "views_stacked": 2,
                        "pairs": n_pairs, "parallelism": f"dp{world}", "optimizer": "torch.optim.Adam(fused)", "launch": "eager" if args.no_graph else "whole step captured in one CUDA graph",
                        "kernel_timing": kernel_timing,
                        "filter_rows_per_launch": n_rows_w,

@@ -69,15 +69,17 @@ _SIGNATURES = {
     "geossl_pair_distance": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "geossl_ddm_workspace": (c_i64, [c_int]),
     "geossl_ddm_workspace_tc": (c_i64, [c_i64]),
-    "geossl_ddm_head_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
+    "geossl_ddm_head_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
                                     ctypes.POINTER(DdmPtrs), c_p, c_p, c_p]),
-    "geossl_ddm_head_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
+    "geossl_ddm_head_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
                                     ctypes.POINTER(DdmPtrs), c_p, c_p, c_p, c_p, ctypes.POINTER(DdmPtrs), c_p]),
-    "geossl_ddm_head_fwd_tc": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
+    "geossl_ddm_head_fwd_tc": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
                                        ctypes.POINTER(DdmPtrs), c_p, c_p, c_p]),
-    "geossl_ddm_head_bwd_tc": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
+    "geossl_ddm_head_bwd_tc": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
                                        ctypes.POINTER(DdmPtrs), c_p, c_p, c_p, c_p, ctypes.POINTER(DdmPtrs), c_p]),
-    "geossl_painn_edge_geometry": (c_int, [c_p, c_p, c_i64, c_f, c_p, c_p, c_p, c_p]),
+    "geossl_ddm_head_fwd_bwd_tc": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_int, c_f, c_int,
+                                           ctypes.POINTER(DdmPtrs), c_p, c_p, c_p, ctypes.POINTER(DdmPtrs), c_p]),
+    "geossl_painn_edge_geometry": (c_int, [c_p, c_p, c_i64, c_i64, c_f, c_p, c_p, c_p, c_p]),
     "geossl_painn_message_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_p,
                                          c_p, c_p, c_p, c_i64, c_p, c_p, c_p]),
     "geossl_painn_workspace": (c_i64, [c_int, c_int]),

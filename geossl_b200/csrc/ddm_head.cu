@@ -70,6 +70,14 @@ struct HeadIn {
     const float* dist; const float* noise; const int64_t* noise_level; const float* sigmas; int n_levels;
     float anneal_power;
     geossl_ddm_params p;
+    // Capacity-padded batches (CUDA-graph replay over variable-size batches): n_pairs is the CAPACITY (row stride of
+    // sei, length of dist / noise); the number of live pairs is read from device memory.  NULL => all n_pairs are live.
+    const int32_t* n_live;
+    __device__ __forceinline__ int64_t live() const {
+        if (n_live == nullptr) return n_pairs;
+        const int64_t l = (int64_t)__ldg(n_live);
+        return l < 0 ? 0 : (l < n_pairs ? l : n_pairs);
+    }
 };
 
 template <int H>
@@ -104,7 +112,7 @@ __device__ __forceinline__ int head_build_tile(const HeadIn& in, int64_t p0, flo
         const int64_t p = p0 + tid;
         int u = 0, v = 0;
         float sigma = 1.f, dt = 0.f, tgt = 0.f, sa = 0.f;
-        if (p < in.n_pairs) {
+        if (p < in.live()) {
             u = (int)in.sei[p];
             v = (int)in.sei[in.n_pairs + p];
             const int g = (int)in.batch[u];
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(256, 1) ddm_head_fwd_kernel(HeadIn in, float* 
     const float out_b2 = __ldg(in.p.out_b2);
     float loss_acc = 0.f;
     int gmax = -1;
-    const int64_t n_tiles = (in.n_pairs + K::TP - 1) / K::TP;
+    const int64_t n_tiles = (in.live() + K::TP - 1) / K::TP;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         gmax = max(gmax, head_build_tile<H>(in, t * K::TP, smem));
         head_layer0<H>(smem);
@@ -286,7 +294,7 @@ ddm_head_bwd_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* 
     for (int j = 0; j < 4; ++j) aW2[j] = 0.f;
     float aB2 = 0.f, aW0last = 0.f, aB0 = 0.f, aB1 = 0.f, aIW0 = 0.f, aIB0 = 0.f, aIW1 = 0.f, aIB1 = 0.f;
 
-    const int64_t n_tiles = (in.n_pairs + K::TP - 1) / K::TP;
+    const int64_t n_tiles = (in.live() + K::TP - 1) / K::TP;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         head_build_tile<H>(in, t * K::TP, smem);
         head_layer0<H>(smem);
@@ -349,7 +357,7 @@ ddm_head_bwd_kernel(HeadIn in, const float* __restrict__ loss_aux, const float* 
 #pragma unroll
         for (int i = 0; i < C1::ME; ++i) {
             const int pl = r01 + i;
-            if (t * K::TP + pl < in.n_pairs) {
+            if (t * K::TP + pl < in.live()) {
                 float* gu = grad_h + (int64_t)sU[pl] * H;
                 float* gv = grad_h + (int64_t)sV[pl] * H;
 #pragma unroll
@@ -541,12 +549,13 @@ int geossl_pair_distance(const float* pos, const int64_t* sei, int64_t n_pairs, 
 int64_t geossl_ddm_workspace(int H) { return head_workspace(H); }
 
 static int64_t head_pad(int64_t n_pairs) { return (n_pairs + 63) / 64 * 64; }
-static int64_t head_prep_offset() { return (head_workspace(128) + 63) / 64 * 64; }
-// partial sums | per-pair scalars (8 rows of n_pairs rounded up to the tile size)
+static int64_t head_loss_offset() { return (head_workspace(128) + 63) / 64 * 64; }            // fused mode: 2 floats per CTA
+static int64_t head_prep_offset() { return head_loss_offset() + (2 * kNumSM + 63) / 64 * 64; }
+// parameter partial sums | loss partials (fused mode) | per-pair scalars (8 rows of n_pairs rounded up to the tile size)
 int64_t geossl_ddm_workspace_tc(int64_t n_pairs) { return head_prep_offset() + 8 * head_pad(n_pairs > 0 ? n_pairs : 0) + 64; }
 
 static int fill_head_in(HeadIn& in, const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
-                        const float* dist, const float* noise, const int64_t* noise_level, const float* sigmas,
+                        const int32_t* n_pairs_live, const float* dist, const float* noise, const int64_t* noise_level, const float* sigmas,
                         int n_levels, float anneal_power, const geossl_ddm_params* params) {
     if (!(h && sei && batch && dist && noise && noise_level && sigmas && params) || n_levels < 1) return GEOSSL_EINVAL;
     const geossl_ddm_params& p = *params;
@@ -554,10 +563,11 @@ static int fill_head_in(HeadIn& in, const float* h, const int64_t* sei, const in
         return GEOSSL_EINVAL;
     in.h = h; in.sei = sei; in.batch = batch; in.n_pairs = n_pairs; in.dist = dist; in.noise = noise;
     in.noise_level = noise_level; in.sigmas = sigmas; in.n_levels = n_levels; in.anneal_power = anneal_power; in.p = p;
+    in.n_live = n_pairs_live;
     return 0;
 }
 
-int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
                         const float* dist, const float* noise, const int64_t* noise_level,
                         const float* sigmas, int n_levels, float anneal_power, int H,
                         const geossl_ddm_params* params, float* workspace, float* loss, void* stream) {
@@ -567,7 +577,7 @@ int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch
         GEOSSL_CUDA(cudaMemsetAsync(loss, 0, 2 * sizeof(float), as_stream(stream)));
         return 0;
     }
-    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, n_pairs_live, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
                    "null input pointer");
     int rc;
     switch (H) {
@@ -581,7 +591,8 @@ int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch
     return 0;
 }
 
-int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, int64_t n_atoms,
+int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
+                        int64_t n_atoms,
                         const float* dist, const float* noise, const int64_t* noise_level,
                         const float* sigmas, int n_levels, float anneal_power, int H,
                         const geossl_ddm_params* params, const float* loss_aux, const float* grad_loss, float* workspace,
@@ -592,7 +603,7 @@ int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch
                    "null gradient pointer");
     HeadIn in;
     GEOSSL_REQUIRE(n_pairs > 0, "n_pairs must be > 0 (caller handles the empty case)");
-    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, n_pairs_live, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
                    "null input pointer");
     int rc;
     switch (H) {
@@ -654,7 +665,7 @@ ddm_pair_prep_kernel(HeadIn in, int64_t n_pad, float* __restrict__ prep) {
     if (p >= n_pad) return;
     int u = 0, v = 0, g = -1;
     float sigma = 1.f, dt = 0.f, tgt = 0.f, sa = 0.f, emb = 0.f;
-    if (p < in.n_pairs) {
+    if (p < in.live()) {
         u = (int)in.sei[p];
         v = (int)in.sei[in.n_pairs + p];
         g = (int)in.batch[u];
@@ -735,7 +746,8 @@ static_assert(HeadSmem::kBytes + 1024 <= 227 * 1024, "shared memory budget");
 template <bool FP16, bool BWD>
 __global__ void __launch_bounds__(kHThreads, 1)
 ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, const float* __restrict__ loss_aux,
-                   const float* __restrict__ grad_loss, float* __restrict__ grad_h, float* __restrict__ workspace) {
+                   const float* __restrict__ grad_loss, float* __restrict__ grad_h, float* __restrict__ workspace,
+                   float* __restrict__ loss_part) {
     using K = HeadCfg<128>;
     using L = HeadSmem;
     extern __shared__ uint8_t smem_raw[];
@@ -788,8 +800,15 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
     const float iw0 = __ldg(in.p.in_w0 + unit), ib0 = __ldg(in.p.in_b0 + unit), iw1 = __ldg(in.p.in_w1 + unit);
     float gscale = 0.f;
     if (BWD) {
-        const float ng = __ldg(loss_aux + 1);
-        gscale = ng > 0.f ? __ldg(grad_loss) / ng : 0.f;
+        if (loss_aux != nullptr) {
+            const float ng = __ldg(loss_aux + 1);
+            gscale = ng > 0.f ? __ldg(grad_loss) / ng : 0.f;
+        } else {
+            // fused forward + backward (geossl_ddm_head_fwd_bwd_tc): the number of graphs is not known until every CTA has
+            // finished, so the gradients are accumulated UNSCALED (dL/d. of the plain sum over pairs); the caller multiplies
+            // them by grad_loss / n_graphs.  The loss partials go to loss_part as in the forward kernel.
+            gscale = 1.f;
+        }
     }
     constexpr uint32_t fmt = Split<FP16>::kFmt;
     const uint32_t id_t = idesc_f16(fmt, 128, kHP);            // K-major A and B
@@ -801,7 +820,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
     float a_db0 = 0.f, a_dwl = 0.f, a_db1 = 0.f, a_dw2 = 0.f, a_db2 = 0.f, a_iw0 = 0.f, a_ib0 = 0.f, a_iw1 = 0.f, a_ib1 = 0.f;
     uint32_t phase = 0, phase_wg = 0;
     int done = 0;
-    const int64_t n_tiles = (in.n_pairs + kHP - 1) / kHP;
+    const int64_t n_tiles = (in.live() + kHP - 1) / kHP;
     float pre[kPrepRows];
     if (tid < kHP && blockIdx.x < n_tiles) {
 #pragma unroll
@@ -1047,9 +1066,10 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
         trace_h(done, 13);
     }
 
-    if (!BWD) {
+    if (!BWD || loss_part != nullptr) {
         __shared__ float red_l[16];
         __shared__ int red_g[16];
+        float* lp = BWD ? loss_part : workspace;
         loss_acc = warp_sum(loss_acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
@@ -1059,10 +1079,11 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
             float s = 0.f;
             int g = -1;
             for (int w = 0; w < 16; ++w) { s += red_l[w]; g = max(g, red_g[w]); }
-            workspace[2 * blockIdx.x] = s;
-            workspace[2 * blockIdx.x + 1] = (float)g;
+            lp[2 * blockIdx.x] = s;
+            lp[2 * blockIdx.x + 1] = (float)g;
         }
-    } else {
+    }
+    if (BWD) {
         // ---- per-CTA partial gradients in HeadCfg<128>'s layout (reduced by ddm_head_reduce_kernel<128>)
         float* ws = workspace + (int64_t)blockIdx.x * K::kPartial;
         if (done > 0) mbar_wait(bar_wg, phase_wg);             // the last tile's weight-gradient MMAs
@@ -1139,7 +1160,7 @@ int geossl_debug_set_trace_head(long long* device_buffer) {
 }
 
 
-int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
                            const float* dist, const float* noise, const int64_t* noise_level,
                            const float* sigmas, int n_levels, float anneal_power, int H,
                            const geossl_ddm_params* params, float* workspace, float* loss, void* stream) {
@@ -1150,7 +1171,7 @@ int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* ba
         return 0;
     }
     HeadIn in;
-    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, n_pairs_live, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
                    "null input pointer");
     const size_t smem = tc::HeadSmem::kBytes + 1024;
     static PerDeviceFlag configured;
@@ -1164,14 +1185,16 @@ int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     GEOSSL_CUDA(launch_pdl(tc::ddm_pair_prep_kernel, dim3((unsigned)((n_pad + 255) / 256)), dim3(256), 0, as_stream(stream), in, n_pad, prep));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(tc::ddm_head_tc_kernel<true, false>, dim3(grid), dim3(tc::kHThreads), smem, as_stream(stream), in,
-                           (const float*)prep, n_pad, (const float*)nullptr, (const float*)nullptr, (float*)nullptr, workspace));
+                           (const float*)prep, n_pad, (const float*)nullptr, (const float*)nullptr, (float*)nullptr, workspace,
+                           (float*)nullptr));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(ddm_loss_finalize_kernel, dim3(1), dim3(32), 0, as_stream(stream), (const float*)workspace, grid, loss));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
 
-int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, int64_t n_atoms,
+int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
+                        int64_t n_atoms,
                            const float* dist, const float* noise, const int64_t* noise_level,
                            const float* sigmas, int n_levels, float anneal_power, int H,
                            const geossl_ddm_params* params, const float* loss_aux, const float* grad_loss, float* workspace,
@@ -1182,7 +1205,7 @@ int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     GEOSSL_REQUIRE(g.in_w0 && g.in_b0 && g.in_w1 && g.in_b1 && g.out_w0 && g.out_b0 && g.out_w1 && g.out_b1 && g.out_w2 && g.out_b2,
                    "null gradient pointer");
     HeadIn in;
-    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, n_pairs_live, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
                    "null input pointer");
     const size_t smem = tc::HeadSmem::kBytes + 1024;
     static PerDeviceFlag configured;
@@ -1197,10 +1220,48 @@ int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     GEOSSL_CUDA(launch_pdl(tc::ddm_pair_prep_kernel, dim3((unsigned)((n_pad + 255) / 256)), dim3(256), 0, as_stream(stream), in, n_pad, prep));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(tc::ddm_head_tc_kernel<false, true>, dim3(grid), dim3(tc::kHThreads), smem, as_stream(stream), in,
-                           (const float*)prep, n_pad, loss_aux, grad_loss, grad_h, workspace));
+                           (const float*)prep, n_pad, loss_aux, grad_loss, grad_h, workspace, (float*)nullptr));
     GEOSSL_LAUNCH_CHECK();
     const int n = HeadCfg<128>::kPartial;
     GEOSSL_CUDA(launch_pdl(ddm_head_reduce_kernel<128>, dim3((n + 255) / 256), dim3(256), 0, as_stream(stream), (const float*)workspace, grid, g));
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_ddm_head_fwd_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
+                               int64_t n_atoms, const float* dist, const float* noise, const int64_t* noise_level,
+                               const float* sigmas, int n_levels, float anneal_power, int H,
+                               const geossl_ddm_params* params, float* workspace, float* loss, float* grad_h,
+                               const geossl_ddm_grads* grads, void* stream) {
+    GEOSSL_REQUIRE(workspace && loss && grad_h && grads && n_pairs > 0 && n_atoms >= 0, "null pointer / empty input");
+    GEOSSL_REQUIRE(H == 128, "the tensor-core DDM head is built for emb_dim = 128");
+    const geossl_ddm_grads& g = *grads;
+    GEOSSL_REQUIRE(g.in_w0 && g.in_b0 && g.in_w1 && g.in_b1 && g.out_w0 && g.out_b0 && g.out_w1 && g.out_b1 && g.out_w2 && g.out_b2,
+                   "null gradient pointer");
+    HeadIn in;
+    GEOSSL_REQUIRE(fill_head_in(in, h, sei, batch, n_pairs, n_pairs_live, dist, noise, noise_level, sigmas, n_levels, anneal_power, params) == 0,
+                   "null input pointer");
+    const size_t smem = tc::HeadSmem::kBytes + 1024;
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::ddm_head_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.set();
+    }
+    cudaStream_t st = as_stream(stream);
+    GEOSSL_CUDA(cudaMemsetAsync(grad_h, 0, sizeof(float) * (size_t)n_atoms * 128, st));
+    const int grid = head_grid(n_pairs);
+    const int64_t n_pad = head_pad(n_pairs);
+    float* prep = workspace + head_prep_offset();
+    float* loss_part = workspace + head_loss_offset();
+    GEOSSL_CUDA(launch_pdl(tc::ddm_pair_prep_kernel, dim3((unsigned)((n_pad + 255) / 256)), dim3(256), 0, st, in, n_pad, prep));
+    GEOSSL_LAUNCH_CHECK();
+    GEOSSL_CUDA(launch_pdl(tc::ddm_head_tc_kernel<false, true>, dim3(grid), dim3(tc::kHThreads), smem, st, in,
+                           (const float*)prep, n_pad, (const float*)nullptr, (const float*)nullptr, grad_h, workspace, loss_part));
+    GEOSSL_LAUNCH_CHECK();
+    GEOSSL_CUDA(launch_pdl(ddm_loss_finalize_kernel, dim3(1), dim3(32), 0, st, (const float*)loss_part, grid, loss));
+    GEOSSL_LAUNCH_CHECK();
+    const int n = HeadCfg<128>::kPartial;
+    GEOSSL_CUDA(launch_pdl(ddm_head_reduce_kernel<128>, dim3((n + 255) / 256), dim3(256), 0, st, (const float*)workspace, grid, g));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

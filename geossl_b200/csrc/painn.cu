@@ -18,10 +18,15 @@ namespace geossl {
 constexpr int kMaxRbf = 32;
 
 __global__ void painn_edge_geom_kernel(const float* __restrict__ pos, const int64_t* __restrict__ rei, int64_t n_edges,
-                                       float cutoff, float* __restrict__ dist, float* __restrict__ dir, float* __restrict__ fcut) {
+                                       int64_t n_atoms, float cutoff, float* __restrict__ dist, float* __restrict__ dir,
+                                       float* __restrict__ fcut) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     const int64_t i = rei[e], j = rei[n_edges + e];
+    if (i < 0 || j < 0 || i >= n_atoms || j >= n_atoms) {        // padding column of a capacity-padded list (idx_j = n_atoms)
+        dist[e] = 1.f; dir[3 * e] = 0.f; dir[3 * e + 1] = 0.f; dir[3 * e + 2] = 0.f; fcut[e] = 0.f;
+        return;
+    }
     const float rx = __fsub_rn(pos[3 * i], pos[3 * j]), ry = __fsub_rn(pos[3 * i + 1], pos[3 * j + 1]),
                 rz = __fsub_rn(pos[3 * i + 2], pos[3 * j + 2]);                              // painn.py:232
     const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
@@ -193,9 +198,11 @@ painn_message_bwd_kernel(const float* __restrict__ gq_out, const float* __restri
 // layout [c][R+1] (column R = bias).  256 threads: thread owns channels {tid % 128 + 128 b} x half of the rbf range.
 template <int F>
 __global__ void __launch_bounds__(256)
-painn_filter_wgrad_kernel(const float* __restrict__ gfilt, const float* __restrict__ dist, int64_t n_edges,
-                          const float* __restrict__ offsets, const float* __restrict__ widths, int R,
-                          float* __restrict__ workspace) {
+painn_filter_wgrad_kernel(const float* __restrict__ gfilt, const float* __restrict__ dist, int64_t n_edges_cap,
+                          const int32_t* __restrict__ n_edges_live, const float* __restrict__ offsets,
+                          const float* __restrict__ widths, int R, float* __restrict__ workspace) {
+    // live edge count on the device (= rowptr[n_atoms] of the idx_j-sorted CSR): rows past it are padding / never written
+    const int64_t n_edges = min((int64_t)__ldg(n_edges_live), n_edges_cap);
     constexpr int C3 = 3 * F;
     constexpr int NC = (C3 + 127) / 128;            // channels per thread (3 for F=128, 2 for F=64, 1 for F=32)
     constexpr int TE = 16;
@@ -312,7 +319,7 @@ int launch_msg_bwd(const float* gq_out, const float* gmu_out, const float* mu, c
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     count_launch();
-    painn_filter_wgrad_kernel<F><<<kNumSM, 256, 0, st>>>(gfilt, dist, n_edges, offsets, widths, R, workspace);
+    painn_filter_wgrad_kernel<F><<<kNumSM, 256, 0, st>>>(gfilt, dist, n_edges, j_rowptr + n_atoms, offsets, widths, R, workspace);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     count_launch();
@@ -327,12 +334,12 @@ using namespace geossl;
 
 extern "C" {
 
-int geossl_painn_edge_geometry(const float* pos, const int64_t* radius_edge_index, int64_t n_edges, float cutoff,
+int geossl_painn_edge_geometry(const float* pos, const int64_t* radius_edge_index, int64_t n_edges, int64_t n_atoms, float cutoff,
                                float* dist, float* dir, float* fcut, void* stream) {
     if (n_edges == 0) return 0;
     GEOSSL_REQUIRE(pos && radius_edge_index && dist && dir && fcut && n_edges > 0, "null pointer");
-    painn_edge_geom_kernel<<<(int)((n_edges + 255) / 256), 256, 0, as_stream(stream)>>>(pos, radius_edge_index, n_edges, cutoff,
-                                                                                        dist, dir, fcut);
+    painn_edge_geom_kernel<<<(int)((n_edges + 255) / 256), 256, 0, as_stream(stream)>>>(pos, radius_edge_index, n_edges, n_atoms,
+                                                                                        cutoff, dist, dir, fcut);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

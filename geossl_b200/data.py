@@ -37,14 +37,16 @@ class AtomTupleBatch:
     def to(self, device, non_blocking=False):
         def mv(t):
             return None if t is None else t.to(device, non_blocking=non_blocking)
+        extras = {k: (mv(v) if torch.is_tensor(v) else v) for k, v in self.extras.items()}
         return AtomTupleBatch(mv(self.x), mv(self.positions), mv(self.batch), mv(self.super_edge_index),
-                              mv(self.radius_edge_index), self.n_graphs, mv(self.graph_ptr), dict(self.extras))
+                              mv(self.radius_edge_index), self.n_graphs, mv(self.graph_ptr), extras)
 
     def pin_memory(self):
         def pm(t):
             return None if t is None else t.pin_memory()
+        extras = {k: (pm(v) if torch.is_tensor(v) else v) for k, v in self.extras.items()}
         return AtomTupleBatch(pm(self.x), pm(self.positions), pm(self.batch), pm(self.super_edge_index),
-                              pm(self.radius_edge_index), self.n_graphs, pm(self.graph_ptr), dict(self.extras))
+                              pm(self.radius_edge_index), self.n_graphs, pm(self.graph_ptr), extras)
 
 
 def pair_count(n, option="combination"):
@@ -161,3 +163,62 @@ def assemble_batch_device(counts, z, positions, option="combination", device="cu
     z = z.to(device)
     x = torch.stack([z, torch.zeros_like(z)], dim=1)
     return AtomTupleBatch(x, positions.to(device), batch, sei, None, n_graphs, ptr)
+
+
+# ------------------------------------------------------------------------------------------ capacity padding
+PAD_SPACING = 128.0      # Angstrom between padding atoms: larger than any cutoff, so they never gain an edge
+
+
+def pad_batch(batch, n_atoms_cap, n_pairs_cap, n_edges_cap=None):
+    """Capacity-padded copy of ``batch`` (same device): fixed tensor shapes for every batch of a stream, which is what
+    lets ONE captured CUDA graph serve variable-size Molecule3D batches (10-60 atoms per molecule,
+    datasets_utils.py:112-176; the collate is dataloaders_AtomTuple.py:45-78).
+
+    * atoms ``[N, n_atoms_cap)`` are padding: class 0, graph id ``B`` (ONE extra, trailing graph -- ``num_graphs``
+      becomes ``B + 1`` for every batch), placed ``PAD_SPACING`` apart on a line far from the molecules, so the
+      neighbour search gives them no edge; nothing downstream reads their rows, their gradients are exact zeros.
+    * pairs ``[P, n_pairs_cap)`` are padding (index 0/0); ``extras['n_pairs_live']`` = (1,) int32 ``P`` travels with
+      the batch and the DDM head kernels read it on the device (geossl_ddm_head_*: n_pairs_live).  The loss is a mean
+      over ``max(graph id of a LIVE pair) + 1`` graphs, so the padding graph does not enter it (NCSN.py:210-212).
+    * ``radius_edge_index`` (PaiNN), if present, is padded to ``n_edges_cap`` columns ``[idx_i = 0; idx_j = N_cap]``:
+      the sentinel ``idx_j`` (one past the last atom) keeps the list sorted and makes ``rowptr[N_cap]`` the live edge
+      count on the device (geossl_painn_edge_geometry).  Because two stacked views cannot simply be concatenated any
+      more (the sentinel of view 1 is a real atom of view 2), ``extras['rei_stacked']`` (2, 2 n_edges_cap) holds the
+      stacked list ready made: live edges of view 1, live edges of view 2 (+ N_cap), padding ``[0; 2 N_cap]``.
+    """
+    n, p, b = batch.positions.size(0), batch.super_edge_index.size(1), batch.num_graphs
+    if n > n_atoms_cap or p > n_pairs_cap:
+        raise ValueError(f"batch ({n} atoms, {p} pairs) exceeds the capacity ({n_atoms_cap}, {n_pairs_cap})")
+    dev = batch.positions.device
+    k = n_atoms_cap - n
+    x = torch.zeros((n_atoms_cap, batch.x.size(1)), dtype=batch.x.dtype, device=dev)
+    x[:n] = batch.x
+    pos = torch.zeros((n_atoms_cap, 3), dtype=batch.positions.dtype, device=dev)
+    pos[:n] = batch.positions
+    if k:
+        pos[n:, 0] = 1.0e4 + PAD_SPACING * torch.arange(k, dtype=pos.dtype, device=dev)
+    bvec = torch.full((n_atoms_cap,), b, dtype=batch.batch.dtype, device=dev)
+    bvec[:n] = batch.batch
+    sei = torch.zeros((2, n_pairs_cap), dtype=batch.super_edge_index.dtype, device=dev)
+    sei[:, :p] = batch.super_edge_index
+    extras = dict(batch.extras)
+    extras["n_pairs_live"] = torch.tensor([p], dtype=torch.int32, device=dev)
+    extras["n_atoms_live"] = n
+    rei = batch.radius_edge_index
+    if rei is not None and n_edges_cap is not None:
+        e = rei.size(1)
+        if e > n_edges_cap:
+            raise ValueError(f"batch has {e} radius edges, capacity is {n_edges_cap}")
+        rei_p = torch.zeros((2, n_edges_cap), dtype=rei.dtype, device=dev)
+        rei_p[1] = n_atoms_cap
+        rei_p[:, :e] = rei
+        st = torch.zeros((2, 2 * n_edges_cap), dtype=rei.dtype, device=dev)
+        st[1] = 2 * n_atoms_cap
+        st[:, :e] = rei
+        st[:, e:2 * e] = rei + n_atoms_cap
+        extras["rei_stacked"] = st
+        rei = rei_p
+    ptr = None
+    if batch.graph_ptr is not None:
+        ptr = torch.cat([batch.graph_ptr.to(torch.int32), torch.tensor([n_atoms_cap], dtype=torch.int32, device=dev)])
+    return AtomTupleBatch(x, pos, bvec, sei, rei, b + 1, ptr, extras)

@@ -162,11 +162,15 @@ def add_radius_edges(store, radius, device="cuda", max_num_neighbors=32, chunk_a
     return store
 
 
-def batch_from_store(store, indices, device="cuda", option="combination", ratio=1.0, generator=None):
+def batch_from_store(store, indices, device="cuda", option="combination", ratio=1.0, generator=None, mask_ratio=0.0,
+                     rng=np.random):
     """One training batch (``DataLoaderAtomTuple`` + ``AtomTupleExtractor``, dataloaders_AtomTuple.py:15-73,81-90) for
     the molecules ``indices`` of a store, assembled on the device: ``batch``, ``super_edge_index`` by kernel,
-    ``radius_edge_index`` (if the store has it) offset by the cumulative atom count."""
+    ``radius_edge_index`` (if the store has it) offset by the cumulative atom count.  ``mask_ratio > 0`` applies the
+    atom-masking augmentation to every molecule first, like ``Molecule3DDataset.get`` (datasets_3D.py:77-78)."""
     mols = [store.get(int(i)) for i in indices]
+    if mask_ratio > 0:
+        mols = [mask_subgraph(d, mask_ratio, rng) for d in mols]
     counts = [int(d["positions"].size(0)) for d in mols]
     z = torch.cat([d["x"][:, 0] if d["x"].dim() == 2 else d["x"] for d in mols]).long()
     pos = torch.cat([d["positions"] for d in mols]).to(torch.float32)
@@ -177,3 +181,54 @@ def batch_from_store(store, indices, device="cuda", option="combination", ratio=
         # only lists written by add_radius_edges are known to be sorted (per-molecule target-sorted, molecule-major)
         b.extras["rei_sorted"] = "radius_edge_index" in store.sorted_edge_keys
     return b
+
+
+def mask_subgraph(mol, mask_ratio, rng=np.random):
+    """The atom-masking augmentation of ``Molecule3DDataset.subgraph`` (datasets_3D.py:24-67,77-78) on one molecule
+    ``mol`` = the dict ``CollatedStore.get`` returns: a random connected-ish sub-molecule is grown over the bond graph
+    (``edge_index``) and everything else is dropped.
+
+    Host logic, faithful to the reference including its draws and quirks, so that with ``rng=np.random`` and the same
+    ``np.random.seed`` the kept atoms are the reference's: the start atom is ``randint(node_num, size=1)[0]`` (:29); each
+    step draws ``choice(list(frontier))`` from a Python *set* of not-yet-kept successors (:37-42, set iteration order
+    included), re-seeding the frontier with ``choice`` over the sorted unvisited atoms when it runs dry (:34-36); the loop
+    runs ``while len(kept) <= int(n * (1 - mask_ratio))`` and therefore keeps one atom more than that count (:27,33).
+    ``edge_index`` / ``edge_attr`` / ``radius_edge_index`` keep the edges with both endpoints kept, in their original
+    order, relabelled to the compacted atom numbering (PyG ``subgraph(..., relabel_nodes=True)``, :47-65); ``x`` and
+    ``positions`` are sliced.  Returns a new dict (other keys are passed through)."""
+    x = mol["x"]
+    node_num = int(x.size(0))
+    sub_num = int(node_num * (1 - mask_ratio))
+    ei = mol["edge_index"]
+    succ = [[] for _ in range(node_num)]
+    for u, v in ei.t().tolist():                                  # successor lists of the directed bond graph (:25)
+        succ[u].append(v)
+    idx_sub = [rng.randint(node_num, size=1)[0]]
+    idx_neigh = set([n for n in succ[idx_sub[-1]]])
+    while len(idx_sub) <= sub_num:
+        if len(idx_neigh) == 0:
+            idx_unsub = list(set([n for n in range(node_num)]).difference(set(idx_sub)))
+            idx_neigh = set([rng.choice(idx_unsub)])
+        sample_node = rng.choice(list(idx_neigh))
+        idx_sub.append(sample_node)
+        idx_neigh = idx_neigh.union(set([n for n in succ[idx_sub[-1]]])).difference(set(idx_sub))
+    keep = sorted(int(i) for i in idx_sub)
+    keep_t = torch.tensor(keep, dtype=torch.long)
+    n_mask = torch.zeros(node_num, dtype=torch.bool)
+    n_mask[keep_t] = True
+    n_idx = torch.zeros(node_num, dtype=torch.long)
+    n_idx[keep_t] = torch.arange(len(keep))
+
+    def sub_edges(edge_index, edge_attr=None):
+        m = n_mask[edge_index[0]] & n_mask[edge_index[1]]
+        return n_idx[edge_index[:, m]], (None if edge_attr is None else edge_attr[m])
+
+    out = dict(mol)
+    out["edge_index"], ea = sub_edges(ei, mol.get("edge_attr"))
+    if ea is not None:
+        out["edge_attr"] = ea
+    out["x"] = x[keep_t]
+    out["positions"] = mol["positions"][keep_t]
+    if "radius_edge_index" in mol:
+        out["radius_edge_index"], _ = sub_edges(mol["radius_edge_index"])
+    return out

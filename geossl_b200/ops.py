@@ -645,12 +645,19 @@ def _ddm_ptrs(tensors):
     return s
 
 
+# Training fast path of the tensor-core head: ONE pass computes the loss and (unscaled) gradients (geossl_ddm_head_fwd_bwd_tc),
+# the backward is a multi-tensor scale by grad_loss / n_graphs.  False restores separate forward / backward kernels.
+FUSE_DDM_HEAD = True
+
+
 class DDMHead(torch.autograd.Function):
     """NCSN_version_03.forward with the random draws supplied (NCSN.py:183-212).  Returns the scalar loss.
-    Gradients: node_feature and the ten MLP parameters (distance carries none, as in the reference)."""
+    Gradients: node_feature and the ten MLP parameters (distance carries none, as in the reference).
+    ``n_pairs_live``: optional (1,) int32 device tensor -- the batch is capacity padded and only that many pairs at the
+    front are live (CUDA-graph replay over variable-size batches)."""
 
     @staticmethod
-    def forward(ctx, node_feature, sei, batch, dist, noise, noise_level, sigmas, anneal_power, *params):
+    def forward(ctx, node_feature, sei, batch, dist, noise, noise_level, sigmas, anneal_power, n_pairs_live, *params):
         h = _req(node_feature, torch.float32, "node_feature", 2)
         sei = _req(sei, torch.int64, "super_edge_index", 2)
         batch = _req(batch, torch.int64, "batch", 1)
@@ -658,42 +665,63 @@ class DDMHead(torch.autograd.Function):
         noise = _req(noise, torch.float32, "distance_noise").view(-1)
         noise_level = _req(noise_level, torch.int64, "noise_level", 1)
         sigmas = _req(sigmas.detach(), torch.float32, "sigmas", 1)
+        live = None if n_pairs_live is None else _req(n_pairs_live, torch.int32, "n_pairs_live", 1)
         params = tuple(_req(p, torch.float32, "mlp parameter") for p in params)
         lib = _lib.load()
         H = h.size(1)
         n_pairs = sei.size(1)
         ctx.tc = FILTER_MODE != "simt" and H == 128
+        # (needs_input_grad is all False under torch.no_grad(): evaluation takes the forward-only kernel)
+        ctx.fused = bool(ctx.tc and FUSE_DDM_HEAD and n_pairs > 0
+                         and any(ctx.needs_input_grad[i] for i in (0, *range(9, 9 + len(params)))))
         ws = torch.empty(max(lib.geossl_ddm_workspace_tc(n_pairs) if ctx.tc else lib.geossl_ddm_workspace(H), 1),
                          dtype=torch.float32, device=h.device)
         loss = torch.empty(2, dtype=torch.float32, device=h.device)
         pp = _ddm_ptrs(params)
+        ctx.anneal_power = float(anneal_power)
+        if ctx.fused:
+            grad_h = torch.empty_like(h)
+            grads = [torch.empty_like(p) for p in params]
+            gp = _ddm_ptrs(grads)
+            _timed("ddm_head_fused", lambda: lib.geossl_ddm_head_fwd_bwd_tc(
+                _p(h), _p(sei), _p(batch), n_pairs, _p(live), h.size(0), _p(dist), _p(noise), _p(noise_level), _p(sigmas),
+                sigmas.numel(), float(anneal_power), H, ctypes.byref(pp), _p(ws), _p(loss), _p(grad_h), ctypes.byref(gp), _stream()))
+            ctx.save_for_backward(loss, grad_h, *grads)
+            return loss[0]
         fwd = lib.geossl_ddm_head_fwd_tc if ctx.tc else lib.geossl_ddm_head_fwd
         _timed("ddm_head_fwd", lambda: fwd(
-            _p(h), _p(sei), _p(batch), n_pairs, _p(dist), _p(noise), _p(noise_level), _p(sigmas), sigmas.numel(),
+            _p(h), _p(sei), _p(batch), n_pairs, _p(live), _p(dist), _p(noise), _p(noise_level), _p(sigmas), sigmas.numel(),
             float(anneal_power), H, ctypes.byref(pp), _p(ws), _p(loss), _stream()))
-        ctx.anneal_power = float(anneal_power)
+        ctx.live = live
         ctx.save_for_backward(h, sei, batch, dist, noise, noise_level, sigmas, loss, *params)
         return loss[0]
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss):
+        if ctx.fused:
+            loss, grad_h, *grads = ctx.saved_tensors
+            ng = loss[1]
+            scale = torch.where(ng > 0, grad_loss.to(torch.float32) / ng, torch.zeros_like(ng))
+            scaled = torch._foreach_mul([grad_h, *grads], scale)              # out of place: a retained graph may run again
+            return (scaled[0], None, None, None, None, None, None, None, None, *scaled[1:])
         h, sei, batch, dist, noise, noise_level, sigmas, loss, *params = ctx.saved_tensors
         lib = _lib.load()
         H, n_pairs = h.size(1), sei.size(1)
         grad_h = torch.empty_like(h)
         grads = [torch.empty_like(p) for p in params]
         if n_pairs == 0:
-            return (torch.zeros_like(h), None, None, None, None, None, None, None, *[torch.zeros_like(p) for p in params])
+            return (torch.zeros_like(h), None, None, None, None, None, None, None, None, *[torch.zeros_like(p) for p in params])
         ws = torch.empty(lib.geossl_ddm_workspace_tc(n_pairs) if ctx.tc else lib.geossl_ddm_workspace(H),
                          dtype=torch.float32, device=h.device)
         gl = grad_loss.contiguous().view(1).to(torch.float32)
         pp, gp = _ddm_ptrs(params), _ddm_ptrs(grads)
         bwd = lib.geossl_ddm_head_bwd_tc if ctx.tc else lib.geossl_ddm_head_bwd
         _timed("ddm_head_bwd", lambda: bwd(
-            _p(h), _p(sei), _p(batch), n_pairs, h.size(0), _p(dist), _p(noise), _p(noise_level), _p(sigmas), sigmas.numel(),
-            ctx.anneal_power, H, ctypes.byref(pp), _p(loss), _p(gl), _p(ws), _p(grad_h), ctypes.byref(gp), _stream()))
-        return (grad_h, None, None, None, None, None, None, None, *grads)
+            _p(h), _p(sei), _p(batch), n_pairs, _p(ctx.live), h.size(0), _p(dist), _p(noise), _p(noise_level), _p(sigmas),
+            sigmas.numel(), ctx.anneal_power, H, ctypes.byref(pp), _p(loss), _p(gl), _p(ws), _p(grad_h), ctypes.byref(gp),
+            _stream()))
+        return (grad_h, None, None, None, None, None, None, None, None, *grads)
 
 
 # =====================================================================================================
@@ -745,8 +773,8 @@ def painn_edges(positions, radius_edge_index, n_atoms, batch, offsets, widths, c
     dist = torch.empty(e, dtype=torch.float32, device=dev)
     dir_ = torch.empty((e, 3), dtype=torch.float32, device=dev)
     fcut = torch.empty(e, dtype=torch.float32, device=dev)
-    check(_lib.load().geossl_painn_edge_geometry(_p(pos), _p(s.rei), e, float(cutoff), _p(dist), _p(dir_), _p(fcut), _stream()),
-          "painn_edge_geometry")
+    check(_lib.load().geossl_painn_edge_geometry(_p(pos), _p(s.rei), e, n_atoms, float(cutoff), _p(dist), _p(dir_), _p(fcut),
+                                                 _stream()), "painn_edge_geometry")
     return PaiNNEdges(s, dist, dir_, fcut, _req(offsets, torch.float32, "offsets", 1), _req(widths, torch.float32, "widths", 1))
 
 
@@ -760,10 +788,9 @@ class PaiNNMessage(torch.autograd.Function):
         n, Fd = q.shape
         s = edges.s
         q_out, mu_out = torch.empty_like(q), torch.empty_like(mu)
-        check(_lib.load().geossl_painn_message_fwd(_p(q), _p(mu), _p(x), _p(fw), _p(fb), _p(edges.offsets), _p(edges.widths),
-                                                   edges.offsets.numel(), Fd, _p(edges.dist), _p(edges.dir), _p(edges.fcut),
-                                                   _p(s.t_rowptr), _p(s.t_eid), _p(s.t_tgt), n, _p(q_out), _p(mu_out),
-                                                   _stream()), "painn_message_fwd")
+        _timed("painn_message_fwd", lambda: _lib.load().geossl_painn_message_fwd(
+            _p(q), _p(mu), _p(x), _p(fw), _p(fb), _p(edges.offsets), _p(edges.widths), edges.offsets.numel(), Fd, _p(edges.dist),
+            _p(edges.dir), _p(edges.fcut), _p(s.t_rowptr), _p(s.t_eid), _p(s.t_tgt), n, _p(q_out), _p(mu_out), _stream()))
         ctx.edges = edges
         ctx.save_for_backward(mu, x, fw, fb)
         return q_out, mu_out
@@ -782,10 +809,10 @@ class PaiNNMessage(torch.autograd.Function):
         gw, gb = torch.empty_like(fw), torch.empty_like(fb)
         scratch = torch.empty((max(e, 1), 3 * Fd), dtype=torch.float32, device=x.device)
         ws = torch.empty(lib.geossl_painn_workspace(R, Fd), dtype=torch.float32, device=x.device)
-        check(lib.geossl_painn_message_bwd(_p(gq_out), _p(gmu_out), _p(mu), _p(x), _p(fw), _p(fb), _p(edges.offsets),
-                                           _p(edges.widths), R, Fd, _p(edges.dist), _p(edges.dir), _p(edges.fcut),
-                                           _p(s.rowptr), _p(s.src), n, e, _p(gx), _p(gmu), _p(scratch), _p(ws), _p(gw), _p(gb),
-                                           _stream()), "painn_message_bwd")
+        _timed("painn_message_bwd", lambda: lib.geossl_painn_message_bwd(
+            _p(gq_out), _p(gmu_out), _p(mu), _p(x), _p(fw), _p(fb), _p(edges.offsets), _p(edges.widths), R, Fd, _p(edges.dist),
+            _p(edges.dir), _p(edges.fcut), _p(s.rowptr), _p(s.src), n, e, _p(gx), _p(gmu), _p(scratch), _p(ws), _p(gw), _p(gb),
+            _stream()))
         return gq_out, gmu, gx, gw, gb, None
 
 

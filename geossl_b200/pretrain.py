@@ -52,7 +52,9 @@ def _encode_stacked(args, model, x_01, positions_01, x_02, positions_02, batch):
         _, rep = model(x, pos, bvec, return_latent=True, num_graphs=2 * b)
     else:
         rei = batch.radius_edge_index
-        _, rep = model(x, pos, torch.cat([rei, rei + n], dim=1), bvec, return_latent=True, num_graphs=2 * b,
+        stacked = getattr(batch, "extras", {}).get("rei_stacked")         # capacity-padded batches carry it ready made
+        _, rep = model(x, pos, torch.cat([rei, rei + n], dim=1) if stacked is None else stacked, bvec,
+                       return_latent=True, num_graphs=2 * b,
                        assume_sorted=bool(getattr(batch, "extras", {}).get("rei_sorted", False)))
     return rep[:n], rep[n:]
 
@@ -267,28 +269,48 @@ def train_step(args, batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_syn
     return loss.detach()
 
 
+def _batch_tensors(b):
+    """The tensors of a batch that a captured step reads, in a fixed order (static inputs / staging slots)."""
+    out = [b.x, b.positions, b.batch, b.super_edge_index]
+    if b.radius_edge_index is not None:
+        out.append(b.radius_edge_index)
+    for k in ("n_pairs_live", "rei_stacked"):
+        if torch.is_tensor(getattr(b, "extras", {}).get(k)):
+            out.append(b.extras[k])
+    return out
+
+
 class GraphedTrainStep:
     """The whole training iteration (perturb, two encoder passes, two DDM heads, backward, gradient all-reduce,
     Adam) captured once in a CUDA graph and replayed per batch.
 
     Possible because nothing on the path synchronises with the host: the data-dependent edge count lives in device
     memory (``rowptr[N]``), every buffer is sized at a host-known capacity, ``num_graphs`` is carried by the batch,
-    and the random draws use the graph-safe device generator.  Batches must have the captured shapes (same atom
-    and pair counts, e.g. fixed-size molecules); ``matches(batch)`` tells, and callers fall back to ``train_step``.
+    and the random draws use the graph-safe device generator.
+
+    Fixed-size molecules: batches must have the captured shapes.  Variable-size molecules (real Molecule3D: 10-60 atoms):
+    pass ``capacity=(n_atoms_cap, n_pairs_cap)``; the example batch and every later batch are padded to that capacity
+    (``data.pad_batch``: padding atoms form one edge-less extra graph, the live pair count is read on the device), so ONE
+    captured graph serves every batch with the same graph count that fits.  ``matches(batch)`` tells, and callers fall
+    back to ``train_step`` (or capture a larger step) otherwise.
     The optimizer must be capturable (``torch.optim.Adam(..., capturable=True)``).
     """
 
     def __init__(self, args, example_batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_sync=None, warmup=3,
-                 kernel_timers=None):
+                 kernel_timers=None, capacity=None):
         """``kernel_timers``: names of C-ABI calls to bracket with event-record NODES inside the captured graph
         (ops.KERNEL_TIMERS, in-graph mode): after each replay ``ops.KERNEL_TIMERS.collect_replay()`` returns the
         durations of those kernels as they ran inside the step.  Used by bench.py on a second, instrumented capture."""
+        from .data import pad_batch
         self.args, self.model, self.heads, self.optimizer = args, model, heads, optimizer
-        b = example_batch
-        dev = b.positions.device
+        self.capacity = capacity
+        self.n_graphs_in = example_batch.num_graphs
+        b = pad_batch(example_batch, *capacity) if capacity is not None else example_batch
+        extras = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in getattr(b, "extras", {}).items()}
         self.static = type(b)(b.x.clone(), b.positions.clone(), b.batch.clone(), b.super_edge_index.clone(),
                               None if b.radius_edge_index is None else b.radius_edge_index.clone(), b.num_graphs,
-                              None if b.graph_ptr is None else b.graph_ptr.clone(), dict(getattr(b, "extras", {})))
+                              None if b.graph_ptr is None else b.graph_ptr.clone(), extras)
+        dev = b.positions.device
 
         def run():
             loss, _ = do_DDM(args, self.static, model, None, mu, sigma, heads=heads, device_noise=True)
@@ -320,20 +342,31 @@ class GraphedTrainStep:
 
     def matches(self, batch):
         s = self.static
+        if self.capacity is not None:
+            if getattr(batch, "extras", {}).get("n_pairs_live") is not None:            # already padded
+                return batch.positions.shape == s.positions.shape and batch.super_edge_index.shape == s.super_edge_index.shape \
+                    and batch.num_graphs == s.num_graphs
+            rei = batch.radius_edge_index
+            return (batch.num_graphs == self.n_graphs_in and batch.positions.size(0) <= self.capacity[0]
+                    and batch.super_edge_index.size(1) <= self.capacity[1]
+                    and ((rei is None) == (s.radius_edge_index is None))
+                    and (rei is None or (len(self.capacity) > 2 and rei.size(1) <= self.capacity[2])))
         return (batch.positions.shape == s.positions.shape and batch.super_edge_index.shape == s.super_edge_index.shape
                 and batch.num_graphs == s.num_graphs
                 and (batch.radius_edge_index is None) == (s.radius_edge_index is None)
                 and (s.radius_edge_index is None or batch.radius_edge_index.shape == s.radius_edge_index.shape))
 
+    def pad(self, batch):
+        """``batch`` at the captured capacity (no-op for fixed-shape steps or already padded batches)."""
+        if self.capacity is None or getattr(batch, "extras", {}).get("n_pairs_live") is not None:
+            return batch
+        from .data import pad_batch
+        return pad_batch(batch, *self.capacity)
+
     def load(self, batch, non_blocking=True):
         """Copy a batch (device or pinned host) into the graph's static input buffers."""
-        s = self.static
-        s.x.copy_(batch.x, non_blocking=non_blocking)
-        s.positions.copy_(batch.positions, non_blocking=non_blocking)
-        s.batch.copy_(batch.batch, non_blocking=non_blocking)
-        s.super_edge_index.copy_(batch.super_edge_index, non_blocking=non_blocking)
-        if s.radius_edge_index is not None:
-            s.radius_edge_index.copy_(batch.radius_edge_index, non_blocking=non_blocking)
+        for d, t in zip(_batch_tensors(self.static), _batch_tensors(self.pad(batch))):
+            d.copy_(t, non_blocking=non_blocking)
 
     def __call__(self, batch=None):
         if batch is not None:
@@ -348,8 +381,7 @@ class GraphedTrainStep:
             dev = s.positions.device
 
             def clone():
-                return [t.clone() for t in (s.x, s.positions, s.batch, s.super_edge_index)] + \
-                       ([s.radius_edge_index.clone()] if s.radius_edge_index is not None else [])
+                return [t.clone() for t in _batch_tensors(s)]
             self._pipe = {"stream": torch.cuda.Stream(device=dev), "staging": [clone(), clone()],
                           "ready": [torch.cuda.Event(), torch.cuda.Event()], "consumed": [torch.cuda.Event(), torch.cuda.Event()],
                           "used": [False, False]}
@@ -358,8 +390,7 @@ class GraphedTrainStep:
     def prefetch(self, batch, slot):
         """Start copying ``batch`` (pinned host memory) into staging slot ``slot`` (0/1) on a copy stream; returns at once."""
         p = self._pipeline()
-        src = [batch.x, batch.positions, batch.batch, batch.super_edge_index] + \
-              ([batch.radius_edge_index] if self.static.radius_edge_index is not None else [])
+        src = _batch_tensors(self.pad(batch))       # (variable-size streams: pad on the host, in the loader, and pin)
         if p["used"][slot]:
             p["stream"].wait_event(p["consumed"][slot])          # the step that read this slot has taken its copy
         with torch.cuda.stream(p["stream"]):
@@ -373,9 +404,7 @@ class GraphedTrainStep:
         p = self._pipeline()
         main = torch.cuda.current_stream(self.static.positions.device)
         main.wait_event(p["ready"][slot])
-        s = self.static
-        dst = [s.x, s.positions, s.batch, s.super_edge_index] + ([s.radius_edge_index] if s.radius_edge_index is not None else [])
-        torch._foreach_copy_(dst, p["staging"][slot])
+        torch._foreach_copy_(_batch_tensors(self.static), p["staging"][slot])
         p["consumed"][slot].record(main)
         p["used"][slot] = True
         self.graph.replay()

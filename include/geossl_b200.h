@@ -227,13 +227,17 @@ typedef struct {
 /* loss (1,) = mean over graphs of sum_p 0.5*(score_p - target_p)^2 * sigma_p^anneal_power with the
  * noise level (per graph) and the N(0,1) draw (per pair) supplied by the caller (RNG contract,
  * NCSN.py:190,194).  The mean is over max_p(batch[u_p])+1 graphs (torch_scatter dim_size).
- * workspace: geossl_ddm_workspace(H) floats. */
+ * workspace: geossl_ddm_workspace(H) floats.
+ * n_pairs_live (all four entry points): NULL => every one of the n_pairs pairs is live.  Otherwise n_pairs is the
+ * CAPACITY of a padded batch (row stride of sei, length of dist / noise) and *n_pairs_live, read on the device, is the
+ * number of live pairs at the front: no host sync, so a CUDA graph captured once serves batches of any pair count up
+ * to the capacity (variable-size Molecule3D batches, dataloaders_AtomTuple.py:45-78). */
 int64_t geossl_ddm_workspace(int H);
 /* workspace of the tensor-core editions (geossl_ddm_head_{fwd,bwd}_tc): the partial sums plus 8 per-pair scalars
  * (endpoints, graph id, sigma, perturbed distance, target, sigma^anneal, distance embedding) that a one-thread-per-pair
  * prologue kernel writes before the MMA pipeline starts. */
 int64_t geossl_ddm_workspace_tc(int64_t n_pairs);
-int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
                         const float* dist, const float* noise, const int64_t* noise_level,
                         const float* sigmas, int n_levels, float anneal_power, int H,
                         const geossl_ddm_params* params /*host*/, float* workspace, float* loss /*(2,): loss, #graphs*/,
@@ -241,23 +245,32 @@ int geossl_ddm_head_fwd(const float* h, const int64_t* sei, const int64_t* batch
 
 /* Backward: grad_h (n_atoms,H) is ZEROED then accumulated; parameter gradients are overwritten.
  * grad_loss is the (1,) upstream gradient on the device. */
-int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, int64_t n_atoms,
-                        const float* dist, const float* noise, const int64_t* noise_level,
+int geossl_ddm_head_bwd(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
+                        int64_t n_atoms, const float* dist, const float* noise, const int64_t* noise_level,
                         const float* sigmas, int n_levels, float anneal_power, int H,
                         const geossl_ddm_params* params /*host*/, const float* loss_aux /*(2,) from fwd*/,
                         const float* grad_loss, float* workspace,
                         float* grad_h, const geossl_ddm_grads* grads /*host*/, void* stream);
 
 /* Same contracts on the tcgen05 tensor cores (H = 128; fp16-split forward, bf16-split backward operands). */
-int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs,
+int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
                            const float* dist, const float* noise, const int64_t* noise_level,
                            const float* sigmas, int n_levels, float anneal_power, int H,
                            const geossl_ddm_params* params /*host*/, float* workspace, float* loss /*(2,)*/, void* stream);
-int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, int64_t n_atoms,
-                           const float* dist, const float* noise, const int64_t* noise_level,
+int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
+                           int64_t n_atoms, const float* dist, const float* noise, const int64_t* noise_level,
                            const float* sigmas, int n_levels, float anneal_power, int H,
                            const geossl_ddm_params* params /*host*/, const float* loss_aux, const float* grad_loss,
                            float* workspace, float* grad_h, const geossl_ddm_grads* grads /*host*/, void* stream);
+/* Forward AND backward of the head in ONE pass over the pairs (training: the backward kernel recomputes the forward per
+ * tile anyway, so a separate forward launch is redundant work).  loss (2,) as geossl_ddm_head_fwd_tc.  grad_h and the
+ * parameter gradients are the gradients of the UNSCALED sum over pairs (the number of graphs is only known once every
+ * CTA has finished): the caller multiplies them by grad_loss / loss[1] (ops.DDMHead.backward: one multi-tensor scale). */
+int geossl_ddm_head_fwd_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
+                               int64_t n_atoms, const float* dist, const float* noise, const int64_t* noise_level,
+                               const float* sigmas, int n_levels, float anneal_power, int H,
+                               const geossl_ddm_params* params /*host*/, float* workspace, float* loss /*(2,)*/, float* grad_h,
+                               const geossl_ddm_grads* grads /*host*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PaiNN message block.  Replaces the per-edge part of PaiNN.forward (Geom3D/models/painn.py:232-245:
@@ -267,8 +280,11 @@ int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* ba
  * Edge order: radius_edge_index (2,E) = [idx_i; idx_j] sorted by idx_j (row 1), idx_i ascending inside.
  * ---------------------------------------------------------------------------------------------- */
 
-/* dist (E), dir (E,3) = (pos[idx_i]-pos[idx_j])/d, fcut (E) = 0.5(cos(d*pi/rc)+1)*[d<rc]. */
-int geossl_painn_edge_geometry(const float* pos, const int64_t* radius_edge_index, int64_t n_edges, float cutoff,
+/* dist (E), dir (E,3) = (pos[idx_i]-pos[idx_j])/d, fcut (E) = 0.5(cos(d*pi/rc)+1)*[d<rc].
+ * Capacity-padded lists (CUDA-graph replay): padding columns carry idx_j = n_atoms (one past the last atom, which keeps
+ * the list idx_j-sorted and makes rowptr[n_atoms] of geossl_rowptr_from_sorted the LIVE edge count on the device); they
+ * get fcut = 0 / dir = 0 here and are never visited by the message kernels (which walk the CSR rows). */
+int geossl_painn_edge_geometry(const float* pos, const int64_t* radius_edge_index, int64_t n_edges, int64_t n_atoms, float cutoff,
                                float* dist, float* dir, float* fcut, void* stream);
 
 /* q_out = q + sum_{e: idx_i=n} W_e[0:F]*ctx[j][0:F];

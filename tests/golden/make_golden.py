@@ -272,13 +272,52 @@ def ssl_case(name, *, seed, hidden, filters, gaussians, layers, cutoff, num_grap
             "out": out, "grad": grads})
 
 
+def masking_case(name, *, seed, mask_ratio, sizes):
+    """``Molecule3DDataset.subgraph`` (datasets_3D.py:24-67) of the UNMODIFIED reference file (imported under the
+    torch_geometric.utils / .data shims) on synthetic molecules: a random spanning tree + a few ring bonds as the
+    (bidirectional) bond graph, bond attributes, and a dataset-time radius graph.  Stores inputs, the numpy seed and the
+    masked molecules."""
+    import importlib.util
+    from torch_geometric.data import Data
+    spec = importlib.util.spec_from_file_location("ref_datasets_3D", os.path.join(reference_loader.reference_root(),
+                                                                                  "Geom3D", "datasets", "datasets_3D.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    ds = ref.Molecule3DDataset.__new__(ref.Molecule3DDataset)
+    ds.mask_ratio = mask_ratio
+    rng = np.random.default_rng(seed)
+    ins, outs = {}, {}
+    np.random.seed(seed)
+    for m, n in enumerate(sizes):
+        parents = [int(rng.integers(0, i)) for i in range(1, n)]
+        und = [(i + 1, p) for i, p in enumerate(parents)]
+        for _ in range(max(1, n // 6)):                                     # ring closures
+            a, b = (int(v) for v in rng.choice(n, 2, replace=False))
+            if (a, b) not in und and (b, a) not in und:
+                und.append((a, b))
+        if m == 1:                                                          # one molecule with a disconnected fragment
+            und = [e for e in und if n - 1 not in e and n - 2 not in e] + [(n - 1, n - 2)]
+        ei = torch.tensor([[a, b] for a, b in und] + [[b, a] for a, b in und], dtype=torch.long).t().contiguous()
+        ei = ei[:, torch.argsort(ei[0] * n + ei[1])]
+        ea = torch.from_numpy(rng.integers(0, 4, size=(ei.size(1), 2)))
+        x = torch.from_numpy(np.stack([rng.integers(0, 9, n), np.zeros(n, np.int64)], 1))
+        pos = torch.from_numpy(rng.random((n, 3)).astype(np.float32) * 6.0)
+        rei = radius_graph(pos, 3.0, torch.zeros(n, dtype=torch.long))
+        ins.update({f"x{m}": x, f"positions{m}": pos, f"edge_index{m}": ei, f"edge_attr{m}": ea, f"radius_edge_index{m}": rei})
+        d = ds.subgraph(Data(x=x.clone(), positions=pos.clone(), edge_index=ei.clone(), edge_attr=ea.clone(),
+                             radius_edge_index=rei.clone()))
+        outs.update({f"x{m}": d.x, f"positions{m}": d.positions, f"edge_index{m}": d.edge_index, f"edge_attr{m}": d.edge_attr,
+                     f"radius_edge_index{m}": d.radius_edge_index})
+    save(name, dict(kind="masking", seed=seed, mask_ratio=mask_ratio, n_mol=len(sizes)), **{"in": ins, "out": outs})
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])            # optional: names of the fixtures to (re)generate
 
     def _wrap(fn):
         return lambda name, **kw: fn(name, **kw) if (not only or name in only) else None
-    schnet_case, painn_case, ncsn_case, ddm_case, md17_case, ssl_case = map(
-        _wrap, (schnet_case, painn_case, ncsn_case, ddm_case, md17_case, ssl_case))
+    schnet_case, painn_case, ncsn_case, ddm_case, md17_case, ssl_case, masking_case = map(
+        _wrap, (schnet_case, painn_case, ncsn_case, ddm_case, md17_case, ssl_case, masking_case))
     schnet_case("schnet_small", seed=11, hidden=32, filters=32, gaussians=20, layers=2, cutoff=10.0,
                 readout="mean", num_graphs=5, atoms=4, atoms_max=12)
     schnet_case("schnet_trunc", seed=12, hidden=32, filters=64, gaussians=51, layers=2, cutoff=10.0,
@@ -306,3 +345,4 @@ if __name__ == "__main__":
               num_graphs=3, atoms=9)
     ssl_case("ssl_schnet_small", seed=61, hidden=32, filters=32, gaussians=20, layers=2, cutoff=10.0,
              num_graphs=7, atoms=4, atoms_max=12)
+    masking_case("masking_small", seed=71, mask_ratio=0.3, sizes=[12, 17, 9, 30, 5, 23])

@@ -87,3 +87,32 @@ def test_dataset_time_radius_edges_match_per_molecule_oracle():
     want = radius_graph(b.positions.cpu(), 3.0, b.batch.cpu())
     assert torch.equal(b.radius_edge_index.cpu(), want)
     assert bool((b.batch[b.super_edge_index[0]] == b.batch[b.super_edge_index[1]]).all())
+
+
+def test_mask_subgraph_matches_reference_fixture():
+    """The atom-masking augmentation (datasets_3D.py:24-67) replays the reference's numpy draws: same kept atoms, same
+    relabelled bond / radius edges, for every molecule of the fixture written by the UNMODIFIED reference function
+    (tests/golden/make_golden.py::masking_case), including a molecule with a disconnected fragment."""
+    from _golden import Golden
+    from geossl_b200.datasets import mask_subgraph
+    g = Golden("masking_small")
+    c, i, o = g.cfg, g["in"], g["out"]
+    np.random.seed(c["seed"])
+    for m in range(c["n_mol"]):
+        mol = {k: i[f"{k}{m}"] for k in ("x", "positions", "edge_index", "edge_attr", "radius_edge_index")}
+        got = mask_subgraph(mol, c["mask_ratio"])
+        n = mol["x"].size(0)
+        assert got["x"].size(0) == int(n * (1 - c["mask_ratio"])) + 1           # the reference's off-by-one (:33)
+        for k in ("x", "positions", "edge_index", "edge_attr", "radius_edge_index"):
+            assert torch.equal(got[k], o[f"{k}{m}"]), (m, k)
+        assert torch.equal(mol["x"], i[f"x{m}"])                                # input left untouched
+
+
+def test_mask_subgraph_keeps_edges_consistent():
+    from geossl_b200.datasets import mask_subgraph
+    rng = np.random.RandomState(3)
+    mol = _molecules([20], seed=5)[0]
+    out = mask_subgraph(mol, 0.5, rng)
+    k = out["x"].size(0)
+    assert k == 11 and out["positions"].shape == (k, 3)
+    assert out["edge_index"].numel() == 0 or int(out["edge_index"].max()) < k

@@ -160,7 +160,7 @@ def test_side_stream_wgrads_two_pass_matches_single_stream():
         a, b = run(False, pre), run(True, pre)
         assert a.keys() == b.keys()
         for k in a:
-            assert rel_err(a[k], b[k]) <= 2e-6, (pre, k, rel_err(a[k], b[k]))
+            assert rel_err(a[k], b[k]) <= 1e-5, (pre, k, rel_err(a[k], b[k]))
     _check_ddm_grads(g, *_ddm_backward("ddm_schnet_full4"), "tc_fp16")
 
 
@@ -247,3 +247,158 @@ def test_graphed_train_step_trains():
         assert torch.equal(step.static.positions.cpu(), host[i].positions)
         assert torch.equal(step.static.super_edge_index.cpu(), host[i].super_edge_index)
         assert float(loss) == float(loss)
+
+
+def _pad_draws(draws, n_graphs_cap, n_pairs_cap):
+    out = []
+    for lvl, eps in draws:
+        l2 = torch.zeros(n_graphs_cap, dtype=lvl.dtype, device=lvl.device)
+        l2[:lvl.numel()] = lvl
+        e2 = torch.zeros((n_pairs_cap, 1), dtype=eps.dtype, device=eps.device)
+        e2[:eps.size(0)] = eps
+        out.append((l2, e2))
+    return out
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_capacity_padded_batch_equals_unpadded(filter_mode, fused):
+    """data.pad_batch: padding atoms (one edge-less extra graph) and padding pairs (beyond the device-side live count)
+    change neither the loss nor any gradient -- the contract that lets one captured graph serve variable-size batches."""
+    from geossl_b200.Geom3D.models import SchNet
+    from geossl_b200.NCSN import NCSN_version_03
+    from geossl_b200.data import pad_batch
+    old = ops.FUSE_DDM_HEAD
+    ops.FUSE_DDM_HEAD = fused
+    try:
+        torch.manual_seed(0)
+        model = SchNet(node_class=9, num_interactions=2).to(DEV)
+        heads = [NCSN_version_03(128, 10, 0.01, 50, "symmetry", 2.0).to(DEV) for _ in range(2)]
+        b = synthetic_batch(6, 10, 40, seed=3).to(DEV)
+        n, p = b.positions.size(0), b.super_edge_index.size(1)
+        g = torch.Generator(device=DEV).manual_seed(1)
+        noise = 0.3 * torch.randn(b.positions.shape, device=DEV, generator=g)
+        draws = [(torch.randint(0, 50, (6,), device=DEV, generator=g), torch.randn((p, 1), device=DEV, generator=g)) for _ in range(2)]
+
+        def run(batch, pos2, dr):
+            for m in [model] + heads:
+                m.zero_grad(set_to_none=True)
+            loss, _ = do_DDM(default_args(), batch, model, None, heads=heads, draws=dr, positions_02=pos2)
+            loss.backward()
+            return loss.detach().clone(), {k: v.clone() for m in [model] + heads for k, v in grads_of(m).items()}
+
+        l0, g0 = run(b, b.positions + noise, draws)
+        n_cap, p_cap = n + 37, p + 300
+        bp = pad_batch(b, n_cap, p_cap)
+        assert bp.num_graphs == 7 and int(bp.extras["n_pairs_live"]) == p and bp.positions.shape == (n_cap, 3)
+        noise_p = torch.zeros((n_cap, 3), device=DEV)
+        noise_p[:n] = noise
+        noise_p[n:] = 0.3 * torch.randn((n_cap - n, 3), device=DEV, generator=g)       # padding atoms are perturbed too
+        l1, g1 = run(bp, bp.positions + noise_p, _pad_draws(draws, 7, p_cap))
+        assert rel_err(l1, l0) <= 1e-6, rel_err(l1, l0)
+        for k in g0:
+            assert rel_err(g1[k], g0[k]) <= 2e-5, (k, rel_err(g1[k], g0[k]))
+    finally:
+        ops.FUSE_DDM_HEAD = old
+
+
+def test_fused_head_equals_two_kernel_head():
+    """geossl_ddm_head_fwd_bwd_tc (one pass, gradients scaled afterwards) against the forward + backward kernel pair."""
+    g = Golden("ncsn_h128")
+    i = g["in"]
+    data = AtomTupleBatch(None, None, i["batch"].to(DEV), i["super_edge_index"].to(DEV))
+    res = {}
+    old = ops.FUSE_DDM_HEAD
+    try:
+        for fused in (True, False):
+            ops.FUSE_DDM_HEAD = fused
+            head = head_from(g, device=DEV)
+            nf = i["node_feature"].to(DEV).requires_grad_()
+            loss = head(data, nf, i["distance"].to(DEV), noise_level=i["noise_level"].to(DEV),
+                        distance_noise=i["distance_noise"].to(DEV))
+            (3.0 * loss).backward()
+            res[fused] = (loss.detach(), nf.grad, grads_of(head))
+            assert rel_err(loss, g["out"]["loss"]) <= TOL_OUT
+            assert rel_err(nf.grad / 3.0, g["grad"]["node_feature"]) <= TOL_GRAD
+        assert torch.equal(res[True][0], res[False][0])
+        assert rel_err(res[True][1], res[False][1]) <= 1e-5
+        for k in res[True][2]:
+            assert rel_err(res[True][2][k], res[False][2][k]) <= 1e-5, k
+        with torch.no_grad():                                   # evaluation: forward-only kernel, same value
+            ops.FUSE_DDM_HEAD = True
+            head = head_from(g, device=DEV)
+            l2 = head(data, i["node_feature"].to(DEV), i["distance"].to(DEV), noise_level=i["noise_level"].to(DEV),
+                      distance_noise=i["distance_noise"].to(DEV))
+        assert torch.equal(l2, res[True][0])
+    finally:
+        ops.FUSE_DDM_HEAD = old
+
+
+def test_graphed_step_serves_variable_size_batches():
+    """One captured graph (capacity padded) replays 10..40-atom batches of different atom / pair counts, including the
+    host->device input pipeline; a batch over the capacity is refused."""
+    from geossl_b200.Geom3D.models import SchNet
+    from geossl_b200.NCSN import NCSN_version_03
+    from geossl_b200.pretrain import GraphedTrainStep
+
+    torch.manual_seed(0)
+    model = SchNet(node_class=9, num_interactions=2).to(DEV)
+    heads = [NCSN_version_03(128, 10, 0.01, 50, "symmetry", 2.0).to(DEV) for _ in range(2)]
+    groups = [{"params": model.parameters()}] + [{"params": [p for p in h.parameters() if p.requires_grad]} for h in heads]
+    opt = torch.optim.Adam(groups, lr=5e-4, fused=True, capturable=True)
+    host = [synthetic_batch(12, 10, 40, seed=s) for s in range(6)]
+    n_cap = max(b.positions.size(0) for b in host) + 16
+    p_cap = max(b.super_edge_index.size(1) for b in host) + 256
+    step = GraphedTrainStep(default_args(), host[0].to(DEV), model, heads, opt, warmup=2, capacity=(n_cap, p_cap))
+    assert len({b.positions.size(0) for b in host}) > 1
+    losses = []
+    for b in host:
+        assert step.matches(b)
+        losses.append(float(step(b.to(DEV))))
+        assert int(step.static.extras["n_pairs_live"]) == b.super_edge_index.size(1)
+        assert torch.equal(step.static.positions[:b.positions.size(0)].cpu(), b.positions)
+    assert all(v == v and v < 1e30 for v in losses)
+    assert not step.matches(synthetic_batch(12, 60, 70, seed=9)) and not step.matches(synthetic_batch(13, 10, 12, seed=9))
+    fixed = [float(step(host[1].to(DEV))) for _ in range(40)]
+    assert sum(fixed[-10:]) < sum(fixed[:10])
+    # pipeline: padded + pinned on the host, staged one step ahead
+    pinned = [step.pad(b).pin_memory() for b in host[:4]]
+    step.prefetch(pinned[0], 0)
+    for i in range(4):
+        loss = step.run_prefetched(i & 1)
+        if i + 1 < 4:
+            step.prefetch(pinned[i + 1], (i + 1) & 1)
+        torch.cuda.synchronize()
+        assert torch.equal(step.static.positions.cpu(), pinned[i].positions) and float(loss) == float(loss)
+
+
+def test_painn_capacity_padded_edge_list_equals_unpadded():
+    """PaiNN on a capacity-padded batch (padding atoms, pairs AND radius edges with the idx_j = N_cap sentinel, stacked
+    list ready made) gives the loss and gradients of the unpadded batch -- what lets the PaiNN step be graph captured."""
+    from geossl_b200.data import pad_batch
+    g = Golden("ddm_painn_small")
+    c, i = g.cfg, g["in"]
+    n, p, e = i["pos"].size(0), i["super_edge_index"].size(1), i["radius_edge_index"].size(1)
+    nb = int(i["batch"][-1]) + 1
+    draws = [(i["noise_level_1"].to(DEV), i["distance_noise_1"].to(DEV)), (i["noise_level_2"].to(DEV), i["distance_noise_2"].to(DEV))]
+    for stack in (True, False):
+        res = []
+        for padded in (False, True):
+            model = painn_from(g, DEV)
+            heads = (head_from(g, "sd1", DEV), head_from(g, "sd2", DEV))
+            batch = AtomTupleBatch(i["x"].to(DEV), i["pos"].to(DEV), i["batch"].to(DEV), i["super_edge_index"].to(DEV),
+                                   i["radius_edge_index"].to(DEV), n_graphs=nb, extras={"rei_sorted": True})
+            pos2 = (i["pos"] + i["pos_noise"]).to(DEV)
+            dr = draws
+            if padded:
+                batch = pad_batch(batch, n + 5, p + 70, e + 33)
+                assert batch.radius_edge_index.shape == (2, e + 33) and int(batch.radius_edge_index[1, -1]) == n + 5
+                pos2 = torch.cat([pos2, batch.positions[n:] + 0.1])
+                dr = _pad_draws(draws, nb + 1, p + 70)
+            loss, _ = do_DDM(default_args("painn"), batch, model, None, 0.0, c["sigma"], heads=heads, draws=dr, positions_02=pos2,
+                             stack_views=stack)
+            loss.backward()
+            res.append((loss.detach(), grads_of(model)))
+        assert rel_err(res[0][0], g["out"]["loss"]) <= TOL_OUT
+        assert rel_err(res[1][0], res[0][0]) <= 1e-6
+        for k in res[0][1]:
+            assert rel_err(res[1][1][k], res[0][1][k]) <= 2e-5, (stack, k)
