@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--atoms-max", type=int, default=0,
                     help="secondary variant of configs[1]: n ~ U{atoms..atoms_max} atoms per molecule (rows beyond 32 neighbours "
                          "are truncated, shapes differ per batch => eager launches)")
+    ap.add_argument("--workload", default="ddm", choices=["ddm", "md17", "lba"],
+                    help="ddm = the DDM pretraining step (headline); md17 = configs[3]: SchNet energy + autograd-force fine-tune step "
+                         "(double backward) on aspirin-size conformers; lba = configs[4]: SchNet fine-tune step on ~600-atom pockets, "
+                         "cutoff 6 A, batch 32")
     ap.add_argument("--model", default="schnet", choices=["schnet", "painn"],
                     help="schnet = the headline workload (configs[1]); painn = configs[2] (F=128, 3 interactions, 20 RBF, cutoff 5 A)")
     return ap.parse_args()
@@ -515,6 +519,207 @@ def run_product(args):
     _finish(world)
 
 
+# ------------------------------------------------------------------------------------------- fine-tune workloads (configs[3], [4])
+FT = {"md17": dict(batch=256, atoms=21, density=0.08, cutoff=10.0, unit="conformers/s",
+                   metric="SchNet MD17-shaped force fine-tune conformers/s (BASELINE configs[3], secondary)",
+                   workload="configs[3]: SchNet MD17-shaped force fine-tune step (energy + autograd forces, double backward through cfconv, "
+                            "L1 losses 0.05/0.95, Adam), synthetic aspirin-size conformers (21 atoms), batch 256 per GPU"),
+      "lba": dict(batch=32, atoms=600, density=0.05, cutoff=6.0, unit="pockets/s",
+                  metric="SchNet LBA-shaped pocket fine-tune pockets/s (BASELINE configs[4], secondary)",
+                  workload="configs[4]: SchNet LBA-shaped fine-tune step (readout -> Linear -> MSE, Adam) on synthetic protein-ligand "
+                           "pockets (~600 atoms, cutoff 6 A: every neighbour row truncates at 32/33), batch 32 per GPU")}
+
+
+def _ft_batch(kind, seed):
+    from geossl_b200.data import synthetic_batch
+    f = FT[kind]
+    lo, hi = (f["atoms"], None) if kind == "md17" else (560, 640)
+    b = synthetic_batch(f["batch"], lo, hi, seed=seed, density=f["density"], with_pairs=False)
+    g = torch.Generator().manual_seed(seed + 7)
+    b.extras["y"] = torch.randn(f["batch"], generator=g)
+    if kind == "md17":
+        b.extras["force"] = torch.randn(b.positions.shape, generator=g)
+    return b
+
+
+def ft_cpu_reference(kind, steps, warmup, budget_s=None):
+    """The reference's CPU path of the fine-tune step: unmodified reference SchNet (oracle/_ref) + nn.Linear(128,1), loss
+    as finetune_md17.py:30-51 / finetune_lba.py:33-47 (oracle/reference_loader.{md17,lba}_step), backward, Adam."""
+    from oracle import reference_loader
+    f = FT[kind]
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(42)
+    if reference_loader.available():
+        SchNet, _, _ = reference_loader.load()
+        how = "reference"
+    else:
+        raise SystemExit("bench.py: the fine-tune reference arm needs oracle/_ref (run oracle/make_ref.py in the build container)")
+    model = SchNet(hidden_channels=128, num_filters=128, num_interactions=6, num_gaussians=50, cutoff=f["cutoff"], node_class=9)
+    lin = torch.nn.Linear(128, 1)
+    opt = torch.optim.Adam(list(model.parameters()) + list(lin.parameters()), lr=5e-4)
+    times, t_start = [], time.perf_counter()
+    for it in range(warmup + steps):
+        b = _ft_batch(kind, 2000 + it)
+        t0 = time.perf_counter()
+        loss = (reference_loader.md17_step(model, lin, b, b.extras["y"], b.extras["force"]) if kind == "md17"
+                else reference_loader.lba_step(model, lin, b, b.extras["y"]))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        float(loss.detach())
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+            if budget_s and len(times) >= 2 and time.perf_counter() - t_start > budget_s:
+                break
+    total = sum(times)
+    return {"value": f["batch"] * len(times) / total, "unit": f["unit"], "cores": os.cpu_count(), "kind": how,
+            "sample": f"{len(times)} steps x the bench batch ({f['batch']} x ~{f['atoms']} atoms; unmodified reference SchNet under "
+                      f"oracle/shims, torch CPU fp32, {warmup} warm-up, fwd+bwd+Adam)",
+            "ms_per_step": 1e3 * total / len(times), "steps": len(times)}
+
+
+def run_finetune(args):
+    """configs[3] / configs[4]: same JSON contract as the headline line, on the fine-tune callers of the encoder."""
+    kind, f = args.workload, FT[args.workload]
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    base = {"metric": f["metric"], "unit": f["unit"], "n_gpus": args.gpus, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    cfg = {"workload": f["workload"], "batch_per_gpu": f["batch"], "atoms": f["atoms"], "cutoff": f["cutoff"], "num_gaussians": 50,
+           "hidden": 128, "interactions": 6, "lr": 5e-4}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = ft_cpu_reference(kind, args.steps, args.warmup, budget_s=240.0)
+        _emit(json.dumps({**base, "value": cb["value"], "steps": cb["steps"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+                          "impl": "reference", "config": {**cfg, "device": "host CPU"},
+                          "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": cb["value"], "unit": f["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+    import torch.distributed as dist
+    from geossl_b200 import _lib, ops
+    from geossl_b200.Geom3D.models import SchNet
+    from geossl_b200.finetune import GraphedFinetuneStep, lba_train_step, md17_train_step
+    from geossl_b200.pretrain import FlatGradAllReduce, broadcast_parameters, default_args
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- geossl_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    torch.manual_seed(42)
+    model = SchNet(hidden_channels=128, num_filters=128, num_interactions=6, num_gaussians=50, cutoff=f["cutoff"], node_class=9).to(dev)
+    lin = torch.nn.Linear(128, 1).to(dev)
+    broadcast_parameters([model, lin])
+    params = list(model.parameters()) + list(lin.parameters())
+    opt = torch.optim.Adam(params, lr=5e-4, fused=True, capturable=not args.no_graph)
+    sync = FlatGradAllReduce(params) if world > 1 else None
+    targs = default_args("schnet")
+    crit = torch.nn.L1Loss() if kind == "md17" else torch.nn.MSELoss()
+    host_pool = [_ft_batch(kind, 10_000 * rank + i).pin_memory() for i in range(args.pool)]
+    dev_pool = [b.to(dev) for b in host_pool]
+    step_fn = md17_train_step if kind == "md17" else lba_train_step
+
+    def eager(batch):
+        return step_fn(targs, batch, model, lin, crit, opt, grad_sync=sync)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(n):
+            fn(i)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(max(args.warmup, 3)):
+        eager(dev_pool[i % args.pool])
+    barrier()
+    step, launch = eager, "eager launches"
+    same_shape = len({tuple(b.positions.shape) for b in dev_pool}) == 1
+    if not args.no_graph:
+        try:
+            step = GraphedFinetuneStep(lambda b: step_fn(targs, b, model, lin, crit, opt, grad_sync=sync, zero_grad=False), dev_pool, opt)
+            launch = "whole step captured in one CUDA graph (batches padded to one atom capacity)"
+        except Exception as exc:                              # noqa: BLE001 -- report, never hide
+            launch = f"eager launches (graph capture refused: {type(exc).__name__}: {str(exc)[:120]})"
+            step = eager
+    for i in range(2):
+        step(dev_pool[i % args.pool])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda i: step(dev_pool[i % args.pool]), args.steps)
+    value = world * f["batch"] * args.steps / (ms / 1e3)
+    # per-kernel durations (eager event brackets) + launch count
+    names = ("cfconv_fwd", "cfconv_bwd_x", "cfconv_bwd_w", "filter_fwd", "filter_bwd", "linear_fwd", "linear_dgrad", "linear_wgrad", "radius_csr")
+    _lib.launch_count(reset=True)
+    ops.KERNEL_TIMERS.enable(names)
+    n_k = min(args.steps, 5)
+    timed(lambda i: eager(dev_pool[i % args.pool]), n_k)
+    launches = _lib.launch_count() * args.steps // n_k
+    ktimes = ops.KERNEL_TIMERS.collect()
+    ops.KERNEL_TIMERS.disable()
+    clocks = sampler.stop() if rank == 0 else None
+    # end to end: pinned host batch -> H2D -> step -> loss D2H, every step
+    sink = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e(i):
+        loss = step(host_pool[i % args.pool].to(dev, non_blocking=True))
+        sink.copy_(loss.view(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        assert float(sink[0]) == float(sink[0])
+    e2e(0)
+    ms_e2e = timed(e2e, args.steps)
+    if rank != 0:
+        _finish(world)
+        return
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    pk = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = {**json.load(open(pk)), "src": "measured"}
+    b0 = dev_pool[0]
+    g = ops.radius_csr(b0.positions, b0.batch, f["cutoff"], num_graphs=f["batch"])
+    n_atoms, n_edges = b0.positions.size(0), g.num_edges
+    shared = kind == "lba" and ops.SHARE_PAIR_FILTERS
+    n_rows_w = int(g.ensure_pairs().n_pairs_dev.item()) if shared else n_edges
+    cf_bytes = 4 * 128 * n_rows_w + 2 * 4 * 128 * n_atoms + 4 * n_edges * (2 if shared else 1) + 4 * (n_atoms + 1)
+    roof = None
+    if "cfconv_fwd" in ktimes:
+        t = ktimes["cfconv_fwd"]["mean_ms"] / 1e3
+        roof = {"kernel": "cfconv_gather_async_kernel<false> (cfconv forward, F = 128)", "bound": "hbm", "achieved": cf_bytes / t / 1e9,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cf_bytes / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peaks["src"], "algorithmic_bytes_per_launch": cf_bytes, "mean_ms": 1e3 * t,
+                "note": "eager event brackets (include the host enqueue gap); the working set of this workload "
+                        + ("fits the 126 MB L2, so this is not a DRAM-bound launch" if kind == "md17" else "exceeds the L2")}
+    others = {k: {"mean_ms": v["mean_ms"], "launches_per_step": v["n"] // n_k} for k, v in ktimes.items() if k != "cfconv_fwd"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        cb = ft_cpu_reference(kind, 2, 1, budget_s=45.0)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    h2d = sum(t.numel() * t.element_size() for t in (host_pool[0].x, host_pool[0].positions, host_pool[0].batch)) + \
+        sum(v.numel() * v.element_size() for v in host_pool[0].extras.values() if torch.is_tensor(v))
+    _emit(json.dumps({**base, "value": value, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                      "config": {**cfg, "global_batch": world * f["batch"], "atoms_per_launch": n_atoms, "edges_per_launch": n_edges,
+                                 "filter_rows_per_launch": n_rows_w, "launch": launch, "parallelism": f"dp{world}",
+                                 "l2": f"{args.pool} distinct batches cycled"},
+                      "clocks": clocks, "e2e": {"value": world * f["batch"] * args.steps / (ms_e2e / 1e3), "unit": f["unit"],
+                                                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                      "gpu_launches": launches, "roofline": roof, "roofline_other_kernels": others, "cpu_baseline": cpu}))
+    _finish(world)
+
+
 def _finish(world):
     """Multi-rank exit: the captured CUDA graph keeps references into the NCCL communicator, and tearing the process
     group down under it can block; everything is flushed, so leave without the teardown."""
@@ -537,7 +742,9 @@ if __name__ == "__main__":
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)                       # library chatter on fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
-    if a.impl == "reference":
+    if a.workload != "ddm":
+        run_finetune(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_product(a)

@@ -186,7 +186,8 @@ def pad_batch(batch, n_atoms_cap, n_pairs_cap, n_edges_cap=None):
       more (the sentinel of view 1 is a real atom of view 2), ``extras['rei_stacked']`` (2, 2 n_edges_cap) holds the
       stacked list ready made: live edges of view 1, live edges of view 2 (+ N_cap), padding ``[0; 2 N_cap]``.
     """
-    n, p, b = batch.positions.size(0), batch.super_edge_index.size(1), batch.num_graphs
+    has_pairs = batch.super_edge_index is not None
+    n, p, b = batch.positions.size(0), (batch.super_edge_index.size(1) if has_pairs else 0), batch.num_graphs
     if n > n_atoms_cap or p > n_pairs_cap:
         raise ValueError(f"batch ({n} atoms, {p} pairs) exceeds the capacity ({n_atoms_cap}, {n_pairs_cap})")
     dev = batch.positions.device
@@ -199,11 +200,14 @@ def pad_batch(batch, n_atoms_cap, n_pairs_cap, n_edges_cap=None):
         pos[n:, 0] = 1.0e4 + PAD_SPACING * torch.arange(k, dtype=pos.dtype, device=dev)
     bvec = torch.full((n_atoms_cap,), b, dtype=batch.batch.dtype, device=dev)
     bvec[:n] = batch.batch
-    sei = torch.zeros((2, n_pairs_cap), dtype=batch.super_edge_index.dtype, device=dev)
-    sei[:, :p] = batch.super_edge_index
     extras = dict(batch.extras)
-    extras["n_pairs_live"] = torch.tensor([p], dtype=torch.int32, device=dev)
+    sei = None
+    if has_pairs:
+        sei = torch.zeros((2, n_pairs_cap), dtype=batch.super_edge_index.dtype, device=dev)
+        sei[:, :p] = batch.super_edge_index
+        extras["n_pairs_live"] = torch.tensor([p], dtype=torch.int32, device=dev)
     extras["n_atoms_live"] = n
+    extras["n_graphs_live"] = b                     # fine-tune readouts drop the padding graph's row (finetune._readout)
     rei = batch.radius_edge_index
     if rei is not None and n_edges_cap is not None:
         e = rei.size(1)

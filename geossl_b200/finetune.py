@@ -8,15 +8,20 @@ through the force (double backward; served by the closed-under-differentiation c
 import torch
 from torch.autograd import grad
 
+from . import ops
+
 
 def _readout(args, model, batch_data, positions):
     x = batch_data.x[:, 0] if batch_data.x.dim() == 2 else batch_data.x
     if args.model_3d == "schnet":
-        return model(x, positions, batch_data.batch, num_graphs=getattr(batch_data, "n_graphs", None))
-    if args.model_3d == "painn":
-        return model(x, positions, batch_data.radius_edge_index, batch_data.batch,
-                     num_graphs=getattr(batch_data, "n_graphs", None))
-    raise Exception("3D model {} not included.".format(args.model_3d))
+        out = model(x, positions, batch_data.batch, num_graphs=getattr(batch_data, "n_graphs", None))
+    elif args.model_3d == "painn":
+        out = model(x, positions, batch_data.radius_edge_index, batch_data.batch,
+                    num_graphs=getattr(batch_data, "n_graphs", None))
+    else:
+        raise Exception("3D model {} not included.".format(args.model_3d))
+    live = getattr(batch_data, "extras", {}).get("n_graphs_live")       # capacity-padded batch: drop the padding graph
+    return out if live is None else out[:live]
 
 
 def md17_losses(args, batch_data, model, graph_pred_linear, criterion, energy_coeff=0.05, force_coeff=0.95):
@@ -36,10 +41,14 @@ def md17_losses(args, batch_data, model, graph_pred_linear, criterion, energy_co
     return loss, pred_energy, pred_force
 
 
-def md17_train_step(args, batch_data, model, graph_pred_linear, criterion, optimizer, **coeffs):
+def md17_train_step(args, batch_data, model, graph_pred_linear, criterion, optimizer, grad_sync=None, zero_grad=True, **coeffs):
+    """One iteration of finetune_md17.py::train (:30-56); ``grad_sync`` = the data-parallel gradient exchange."""
     loss, _, _ = md17_losses(args, batch_data, model, graph_pred_linear, criterion, **coeffs)
-    optimizer.zero_grad()
+    if zero_grad:
+        optimizer.zero_grad()
     loss.backward()
+    if grad_sync is not None:
+        grad_sync()
     optimizer.step()
     return loss.detach()
 
@@ -51,9 +60,60 @@ def lba_loss(args, batch, model, graph_pred_linear, criterion):
     return criterion(pred, batch.extras["y"] if y is None else y)
 
 
-def lba_train_step(args, batch, model, graph_pred_linear, criterion, optimizer):
+def lba_train_step(args, batch, model, graph_pred_linear, criterion, optimizer, grad_sync=None, zero_grad=True):
+    """One iteration of finetune_lba.py::train (:33-51)."""
     loss = lba_loss(args, batch, model, graph_pred_linear, criterion)
-    optimizer.zero_grad()
-    loss.backward()
+    if zero_grad:
+        optimizer.zero_grad(set_to_none=True)
+    with ops.side_stream_wgrads():          # first-order path: the small weight-gradient kernels overlap the backward chain
+        loss.backward()
+    if grad_sync is not None:
+        grad_sync()
     optimizer.step()
     return loss.detach()
+
+
+class GraphedFinetuneStep:
+    """A fine-tune iteration (``step_fn(batch) -> loss``: forward, loss, backward, optimizer) captured in one CUDA graph.
+
+    Pockets differ in size, so every batch is padded to one atom capacity (``data.pad_batch``: the padding atoms form an
+    extra, edge-less graph whose readout row ``_readout`` drops); targets ride along in ``batch.extras``.  Works for any
+    step without host synchronisation -- the first-order SchNet path has none (edge counts stay on the device).  The MD17
+    force step (second order) trims its edge list on the host (``RadiusCSR.exact``) and is refused by the capture."""
+
+    def __init__(self, step_fn, example_batches, optimizer, warmup=2, margin=1.02):
+        from .data import pad_batch
+        from .pretrain import _batch_tensors
+        self._tensors, self._pad = _batch_tensors, pad_batch
+        n_max = max(b.positions.size(0) for b in example_batches)
+        same = len({b.positions.size(0) for b in example_batches}) == 1
+        self.n_cap = n_max if same else -(-int(margin * n_max) // 128) * 128
+        self.padded = not same
+        b = self.pad(example_batches[0])
+        extras = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.extras.items()}
+        self.static = type(b)(b.x.clone(), b.positions.clone(), b.batch.clone(), None, None, b.num_graphs,
+                              None if b.graph_ptr is None else b.graph_ptr.clone(), extras)
+        dev = b.positions.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                optimizer.zero_grad(set_to_none=True)
+                step_fn(self.static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = step_fn(self.static)
+
+    def pad(self, batch):
+        if not self.padded or batch.extras.get("n_graphs_live") is not None:
+            return batch
+        return self._pad(batch, self.n_cap, 0)
+
+    def __call__(self, batch):
+        for d, t in zip(self._tensors(self.static), self._tensors(self.pad(batch))):
+            d.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.loss

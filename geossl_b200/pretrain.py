@@ -271,12 +271,15 @@ def train_step(args, batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_syn
 
 def _batch_tensors(b):
     """The tensors of a batch that a captured step reads, in a fixed order (static inputs / staging slots)."""
-    out = [b.x, b.positions, b.batch, b.super_edge_index]
+    out = [b.x, b.positions, b.batch]
+    if b.super_edge_index is not None:
+        out.append(b.super_edge_index)
     if b.radius_edge_index is not None:
         out.append(b.radius_edge_index)
-    for k in ("n_pairs_live", "rei_stacked"):
-        if torch.is_tensor(getattr(b, "extras", {}).get(k)):
-            out.append(b.extras[k])
+    extras = getattr(b, "extras", {})
+    for k in sorted(extras):                        # live counts, the ready-made stacked edge list, fine-tune targets
+        if torch.is_tensor(extras[k]):
+            out.append(extras[k])
     return out
 
 

@@ -74,3 +74,26 @@ def ddm_step(model_3d, model, heads, batch, mu=0.0, sigma=0.3):
     loss_01 = heads[0](batch, repr_01, distance_02)                                       # :207
     loss_02 = heads[1](batch, repr_02, distance_01)                                       # :208
     return (loss_01 + loss_02) / 2                                                        # :210
+
+
+def md17_step(model, graph_pred_linear, batch, y, force, energy_coeff=0.05, force_coeff=0.95):
+    """The loss of finetune_md17.py::train (:30-51) on the reference SchNet: energy from the readout, force by
+    ``autograd.grad(..., create_graph=True)``, weighted L1 (coefficients of submit_finetune_md17_schnet.sh)."""
+    import torch
+    positions = batch.positions.clone().requires_grad_()                                  # :32-33
+    x = batch.x[:, 0] if batch.x.dim() == 2 else batch.x
+    molecule_3D_repr = model(x, positions, batch.batch)                                   # :37
+    pred_energy = graph_pred_linear(molecule_3D_repr).squeeze(1)                          # :42
+    pred_force = -torch.autograd.grad(outputs=pred_energy, inputs=positions, grad_outputs=torch.ones_like(pred_energy),
+                                      create_graph=True, retain_graph=True)[0]            # :46
+    crit = torch.nn.L1Loss()
+    return energy_coeff * crit(pred_energy, y) + force_coeff * crit(pred_force, force)    # :51
+
+
+def lba_step(model, graph_pred_linear, batch, y):
+    """The loss of finetune_lba.py::train (:33-47): SchNet readout -> Linear -> MSE (criterion, :244)."""
+    import torch
+    x = batch.x[:, 0] if batch.x.dim() == 2 else batch.x
+    molecule_3D_repr = model(x, batch.positions, batch.batch)                             # :37
+    pred = graph_pred_linear(molecule_3D_repr).squeeze()                                  # :42
+    return torch.nn.MSELoss()(pred, y)                                                    # :47

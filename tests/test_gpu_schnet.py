@@ -189,3 +189,65 @@ def test_md17_train_step_through_finetune_module():
     batch.positions = i["pos"].to(DEV)
     l2 = md17_train_step(default_args("schnet"), batch, m, lin, crit, opt)
     assert rel_err(l2, g["out"]["loss"]) <= TOL_OUT and not torch.equal(before, m.lin1.weight)
+
+
+def _lba_case(n_graphs, layers, seed):
+    from geossl_b200.Geom3D.models import SchNet
+    torch.manual_seed(seed)
+    m = SchNet(hidden_channels=128, num_filters=128, num_interactions=layers, num_gaussians=50, cutoff=6.0, node_class=9, readout="mean")
+    lin = torch.nn.Linear(128, 1)
+    b = synthetic_batch(n_graphs, 560, 640, seed=seed + 1, with_pairs=False)
+    b.extras["y"] = torch.randn(n_graphs, generator=torch.Generator().manual_seed(seed + 2))
+    return m, lin, b
+
+
+def _oracle_lba(m, lin, b):
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and v.dtype == torch.float32) for k, v in m.state_dict().items()}
+    sdl = {k: v.clone().requires_grad_() for k, v in lin.state_dict().items()}
+    out, _ = O.schnet_forward(sd, b.x[:, 0].contiguous(), b.positions, b.batch, cutoff=6.0, readout="mean")
+    loss = F.mse_loss(F.linear(out, sdl["weight"], sdl["bias"]).squeeze(), b.extras["y"])      # finetune_lba.py:42-47,244
+    loss.backward()
+    return loss, sd, sdl
+
+
+def test_lba_loss_and_backward_at_pocket_shape(filter_mode):
+    """BASELINE configs[4] shape (600-atom pockets, cutoff 6 A, full 6-layer model): ``finetune.lba_loss`` (the body of
+    finetune_lba.py::train :33-47) and EVERY parameter gradient against the CPU oracle.  Rows truncate at 32/33
+    neighbours, so the graph is asymmetric and most filter rows are 'orphan' pairs."""
+    from geossl_b200.finetune import lba_loss
+    from geossl_b200.pretrain import default_args
+    m, lin, b = _lba_case(4, 6, 11)
+    ref, sd, sdl = _oracle_lba(m, lin, b)
+    m.to(DEV), lin.to(DEV)
+    loss = lba_loss(default_args("schnet"), b.to(DEV), m, lin, torch.nn.MSELoss())
+    assert rel_err(loss, ref) <= TOL_OUT, rel_err(loss, ref)
+    loss.backward()
+    tol = TOL_GRAD if filter_mode == "simt" else 2e-4            # stated tensor-core bound (tests/test_gpu_ddm.py)
+    for k, g in grads_of(m).items():
+        if ".conv.nn." not in k:
+            assert rel_err(g, sd[k].grad) <= tol, (k, rel_err(g, sd[k].grad))
+    for k, g in grads_of(lin).items():
+        assert rel_err(g, sdl[k].grad) <= tol, (k, rel_err(g, sdl[k].grad))
+
+
+def test_graphed_finetune_step_pads_pockets_of_different_size():
+    """finetune.GraphedFinetuneStep: one captured graph serves pockets of different atom counts (padding atoms form an
+    extra graph whose readout row is dropped); the replayed loss equals the eager loss of the same batch."""
+    from geossl_b200.finetune import GraphedFinetuneStep, lba_loss, lba_train_step
+    from geossl_b200.pretrain import default_args
+    m, lin, _ = _lba_case(3, 2, 21)
+    m.to(DEV), lin.to(DEV)
+    pool = []
+    for s in range(4):
+        b = synthetic_batch(3, 100, 160, seed=40 + s, with_pairs=False)
+        b.extras["y"] = torch.randn(3, generator=torch.Generator().manual_seed(s))
+        pool.append(b.to(DEV))
+    assert len({b.positions.size(0) for b in pool}) > 1
+    crit = torch.nn.MSELoss()
+    opt = torch.optim.Adam(list(m.parameters()) + list(lin.parameters()), lr=0.0, fused=True, capturable=True)   # lr 0: weights stay put
+    targs = default_args("schnet")
+    step = GraphedFinetuneStep(lambda b: lba_train_step(targs, b, m, lin, crit, opt, zero_grad=False), pool, opt)
+    for b in pool:
+        with torch.no_grad():
+            ref = lba_loss(targs, b, m, lin, crit)
+        assert rel_err(step(b), ref) <= 1e-6
