@@ -305,7 +305,8 @@ def run_product(args):
     ktimes = {}
     n_k = min(args.steps, 10)
     timer_names = ("cfconv_fwd", "filter_fwd", "filter_bwd", "cfconv_bwd_x", "ddm_head_fwd", "ddm_head_bwd", "ddm_head_fused",
-                   "linear_fwd", "linear_dgrad", "linear_wgrad", "painn_message_fwd", "painn_message_bwd")
+                   "linear_fwd", "linear_dgrad", "linear_wgrad", "painn_message_fwd", "painn_message_bwd", "dense_fwd", "dense_dgrad",
+                   "dense_wgrad")
     if step is not eager_step:
         _lib.launch_count(reset=True)
         probe = GraphedTrainStep(targs, dev_pool[0], model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync, warmup=0,
@@ -401,7 +402,7 @@ def run_product(args):
                     "fp32_fma": {"achieved_tflops": msg_flops / t / 1e12, "flops_per_launch": msg_flops,
                                  "note": "the kernel is bound by the fp32 FMA pipe / shared-memory reads of the filter slice, not by HBM"},
                     "share_of_step": ktimes["painn_message_fwd"]["total_ms"] / n_k / (ms / args.steps)}
-        for k in ("painn_message_bwd", "ddm_head_fused", "ddm_head_fwd", "ddm_head_bwd", "linear_fwd", "linear_dgrad", "linear_wgrad"):
+        for k in ("painn_message_bwd", "ddm_head_fused", "ddm_head_fwd", "ddm_head_bwd", "dense_fwd", "dense_dgrad", "dense_wgrad"):
             if k in ktimes:
                 others[k] = {"mean_ms": ktimes[k]["mean_ms"], "launches_per_step": ktimes[k]["n"] // n_k,
                              "share_of_step": ktimes[k]["total_ms"] / n_k / (ms / args.steps)}

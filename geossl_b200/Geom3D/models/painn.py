@@ -49,11 +49,20 @@ class PaiNNMixing(nn.Module):
         self.mu_channel_mix = Dense(n_atom_basis, 2 * n_atom_basis, activation=None, bias=False)
         self.epsilon = epsilon
 
-    def forward_fused(self, q, mu):
-        """q (N,F), mu (N,3,F): the three Dense layers are library GEMMs, everything between them is two fused kernels."""
-        mu_mix = self.mu_channel_mix(mu)
-        ctx, dot = ops.PaiNNMixPre.apply(q, mu_mix, self.epsilon)
-        y = self.intraatomic_context_net(ctx)
+    def forward_fused(self, q, mu, images=None):
+        """q (N,F), mu (N,3,F): the three Dense layers (128->256 without bias on the 3N vector rows, 256->128 + SiLU,
+        128->384) run as 128 x 128 tensor-core blocks (ops.DenseTC) when ``images`` holds their packed weights, else as
+        library GEMMs; everything between them is two fused kernels."""
+        n, _, Fd = mu.shape
+        net = self.intraatomic_context_net
+        if images and id(self.mu_channel_mix.weight) in images:
+            mu_mix = ops.dense(mu.reshape(3 * n, Fd), self.mu_channel_mix, images).view(n, 3, 2 * Fd)
+            ctx, dot = ops.PaiNNMixPre.apply(q, mu_mix, self.epsilon)
+            y = ops.dense(ops.dense(ctx, net[0], images), net[1], images, pre_act=ops.ACT_SILU)
+        else:
+            mu_mix = self.mu_channel_mix(mu)
+            ctx, dot = ops.PaiNNMixPre.apply(q, mu_mix, self.epsilon)
+            y = net(ctx)
         return ops.PaiNNMixPost.apply(q, mu, y, mu_mix, dot)
 
     def forward(self, q, mu):
@@ -107,12 +116,39 @@ class PaiNN(nn.Module):
         mu = torch.zeros((n_atoms, 3, Fd), dtype=q.dtype, device=q.device)
         edges = ops.painn_edges(positions, radius_edge_index, n_atoms, batch, self.radial_basis.offsets,
                                 self.radial_basis.widths, self.cutoff, num_graphs=num_graphs, assume_sorted=assume_sorted)
+        # tensor-core path (F = 128, silu): every Dense layer as 128 x 128 blocks, and the filter Dense(n_rbf -> 3F) of
+        # painn.py:241 as a GEMM over the K-padded rbf matrix [phi, 1, 0...] against [W_f | b_f | 0] (bias folded into
+        # column n_rbf), materialising the pre-cutoff filter rows per interaction; the slicing / padding below is plain
+        # torch so that autograd carries the GEMM's weight gradient back to filter_net.{weight,bias}
+        tc = (ops.FILTER_MODE != "simt" and q.is_cuda and Fd == 128 and self.activation is F.silu
+              and self.radial_basis.n_rbf < 128 and not self.share_filters)
+        images, wf_pad = None, None
+        if tc:
+            R = self.radial_basis.n_rbf
+            buf = self.__dict__.get("_wf_pad_buf")
+            if buf is None or buf.device != q.device or buf.size(0) != self.filter_net.weight.size(0):
+                buf = self.__dict__["_wf_pad_buf"] = torch.zeros((self.filter_net.weight.size(0), 128), dtype=torch.float32,
+                                                                 device=q.device)
+            wf_pad = ops.FilterPad.apply(self.filter_net.weight, self.filter_net.bias, buf.detach())
+            mats = [wf_pad]
+            for interaction, mixing in zip(self.interactions, self.mixing):
+                mats += [interaction.interatomic_context_net[0].weight, interaction.interatomic_context_net[1].weight,
+                         mixing.mu_channel_mix.weight, mixing.intraatomic_context_net[0].weight,
+                         mixing.intraatomic_context_net[1].weight]
+            images = ops.prepack_dense_blocks(mats)
         for i, (interaction, mixing) in enumerate(zip(self.interactions, self.mixing)):
-            ctx = interaction.interatomic_context_net(q)        # (N,3F)
             fo = 0 if self.share_filters else i * 3 * Fd
-            q, mu = ops.PaiNNMessage.apply(q, mu, ctx, self.filter_net.weight[fo:fo + 3 * Fd],
-                                           self.filter_net.bias[fo:fo + 3 * Fd], edges)
-            q, mu = mixing.forward_fused(q, mu)
+            if tc:
+                net = interaction.interatomic_context_net
+                ctx = ops.dense(ops.dense(q, net[0], images), net[1], images, pre_act=ops.ACT_SILU)          # (N,3F)
+                wpre = ops.DenseTC.apply(edges.phi_pad(), wf_pad[fo:fo + 3 * Fd], None, ops.ACT_NONE,
+                                         images[id(wf_pad)][3 * i:3 * i + 3])                                   # (E,3F)
+                q, mu = ops.PaiNNMessage.apply(q, mu, ctx, None, None, edges, wpre)
+            else:
+                ctx = interaction.interatomic_context_net(q)        # (N,3F)
+                q, mu = ops.PaiNNMessage.apply(q, mu, ctx, self.filter_net.weight[fo:fo + 3 * Fd],
+                                               self.filter_net.bias[fo:fo + 3 * Fd], edges)
+            q, mu = mixing.forward_fused(q, mu, images)
         if num_graphs is None:
             num_graphs = int(batch[-1].item()) + 1 if batch.numel() else 0
         h = torch.zeros((num_graphs, Fd), dtype=q.dtype, device=q.device).index_add_(0, batch, q)

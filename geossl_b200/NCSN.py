@@ -68,7 +68,8 @@ class NCSN_version_03(torch.nn.Module):
         # capacity-padded batches (pretrain.pad_batch) carry the live pair count on the device
         n_pairs_live = getattr(data, "extras", {}).get("n_pairs_live") if hasattr(data, "extras") else None
         loss = ops.DDMHead.apply(node_feature, data.super_edge_index, data.batch, distance, distance_noise,
-                                 noise_level, self.sigmas, self.anneal_power, n_pairs_live, *self._mlp_parameters())
+                                 noise_level, self.sigmas, self.anneal_power, n_pairs_live, torch.is_grad_enabled(),
+                                 *self._mlp_parameters())
         if debug:
             print("distance", distance[:10].squeeze())
             print("loss", loss)

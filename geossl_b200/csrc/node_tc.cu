@@ -27,6 +27,17 @@ __device__ __forceinline__ void trace_l(int event) {
     if (t != nullptr && blockIdx.x == 0 && threadIdx.x == 0) t[event] = clock64();
 }
 
+// Pre-activation applied to X while it is staged (and its derivative in the data-gradient epilogue):
+// 1 = shifted softplus (SchNet, schnet.py:210-216), 2 = SiLU (PaiNN's Dense layers, painn.py:21-24 / painn_utils.py:9-35).
+constexpr int kActSsp = 1, kActSilu = 2;
+__device__ __forceinline__ float act_fwd(float x, int kind) {
+    return kind == kActSilu ? x * sigmoid_fast(x) : ssp_fast(x);
+}
+__device__ __forceinline__ float act_grad(float z, int kind) {
+    const float sg = sigmoid_fast(z);
+    return kind == kActSilu ? sg * fmaf(z, 1.f - sg, 1.f) : sg;
+}
+
 constexpr int kNR = 64;                   // rows per tile
 constexpr int kNBlkW = 128 * 128;         // [128 rows x 64 k] 16-bit weight block
 constexpr int kNBlkT = kNR * 128;         // [64 rows x 64 k] 16-bit tile block
@@ -44,18 +55,18 @@ constexpr int kWImage = 4 * kNBlkW;                   // bytes of a packed weigh
 // Weight (128,128) fp32 -> the exact shared-memory operand image (split, swizzled) in global memory, so that every CTA
 // of the layer kernels fetches it with one bulk async copy instead of re-splitting it.
 template <bool FP16>
-__device__ __forceinline__ void pack_weight_body(const float* __restrict__ Wt, int trans, uint8_t* __restrict__ image) {
+__device__ __forceinline__ void pack_weight_body(const float* __restrict__ Wt, int ldw, int trans, uint8_t* __restrict__ image) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * 16; idx += gridDim.x * blockDim.x) {
         float v[8];
         int n, c;
         if (!trans) {
             n = idx >> 4; c = idx & 15;
-            const float4 a = ldg4(Wt + n * 128 + c * 8), b = ldg4(Wt + n * 128 + c * 8 + 4);
+            const float4 a = ldg4(Wt + (size_t)n * ldw + c * 8), b = ldg4(Wt + (size_t)n * ldw + c * 8 + 4);
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         } else {
             n = idx & 127; c = idx >> 7;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(Wt + (c * 8 + j) * 128 + n);
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(Wt + (size_t)(c * 8 + j) * ldw + n);
         }
         const int blk = c >> 3;
         store_chunk8<FP16>(image + blk * kNBlkW, image + 2 * kNBlkW + blk * kNBlkW, n, (c & 7) * 8, v);
@@ -67,24 +78,26 @@ __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ Wt, int trans, uint8_t* __restrict__ image) {
     pdl_launch_dependents();
     pdl_wait();
-    pack_weight_body<FP16>(Wt, trans, image);
+    pack_weight_body<FP16>(Wt, 128, trans, image);
 }
 
 // All layers of a model in ONE launch: blockIdx.y = layer, blockIdx.z = 0: forward image (fp16 parts, nn.Linear
 // orientation) / 1: data-gradient image (bf16 parts, transposed).  images = [layer][2][kWImage] bytes.
 __global__ void __launch_bounds__(256)
-pack_weights_batched_kernel(const float* const* __restrict__ weights, uint8_t* __restrict__ images) {
+pack_weights_batched_kernel(const float* const* __restrict__ weights, const int32_t* __restrict__ lds, uint8_t* __restrict__ images) {
+    // weights[b] = first element of a 128 x 128 block of a row-major matrix with leading dimension lds[b] (NULL => 128)
     const float* Wt = weights[blockIdx.y];
+    const int ldw = lds ? lds[blockIdx.y] : 128;
     uint8_t* image = images + ((size_t)blockIdx.y * 2 + blockIdx.z) * kWImage;
-    if (blockIdx.z == 0) pack_weight_body<true>(Wt, 0, image);
-    else pack_weight_body<false>(Wt, 1, image);
+    if (blockIdx.z == 0) pack_weight_body<true>(Wt, ldw, 0, image);
+    else pack_weight_body<false>(Wt, ldw, 1, image);
 }
 
 // X tile (NR rows x 128 k, fp32, optional ssp) -> split K-major SW128 image.  4 NR threads, four (row, 8-column chunk)
 // items each: 16 lanes cover one 512-byte row, so every load instruction of a warp reads 1 KB of contiguous memory
 // (full 32-byte sectors) and all eight loads of a thread are in flight before the first conversion.
 template <bool FP16, int NR>
-__device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, int64_t row0, int64_t n_rows, bool pre_ssp,
+__device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, int64_t ldx, int64_t row0, int64_t n_rows, int pre_act,
                                                   uint8_t* hi, uint8_t* lo) {
     constexpr int kBlkT = NR * 128, kRowsPerPass = NR / 4;
     const int tid = threadIdx.x, c = tid & 15, r0 = tid >> 4;
@@ -93,7 +106,7 @@ __device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, i
     for (int it = 0; it < 4; ++it) {
         const int64_t row = row0 + r0 + it * kRowsPerPass;
         if (row < n_rows) {
-            const float* p = X + row * 128 + c * 8;
+            const float* p = X + row * ldx + c * 8;
             a[it][0] = ldg4(p);
             a[it][1] = ldg4(p + 4);
         } else {
@@ -103,9 +116,9 @@ __device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, i
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         float v[8] = {a[it][0].x, a[it][0].y, a[it][0].z, a[it][0].w, a[it][1].x, a[it][1].y, a[it][1].z, a[it][1].w};
-        if (pre_ssp && row0 + r0 + it * kRowsPerPass < n_rows) {
+        if (pre_act && row0 + r0 + it * kRowsPerPass < n_rows) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = ssp_fast(v[k]);
+            for (int k = 0; k < 8; ++k) v[k] = act_fwd(v[k], pre_act);
         }
         const int blk = c >> 3;                       // k-block of 64
         store_chunk8<FP16>(hi + blk * kBlkT, lo + blk * kBlkT, r0 + it * kRowsPerPass, (c & 7) * 8, v);
@@ -115,7 +128,10 @@ __device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, i
 template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R, int NR>
 __global__ void __launch_bounds__(4 * NR, NR == 64 ? 2 : 1)
 linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __restrict__ w_image, const float* __restrict__ bias,
-                 const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y) {
+                 const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y,
+                 int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act) {
+    // ld*: row strides in floats (128 for the plain 128 -> 128 layer; wider layers are tiled into 128 x 128 blocks by the
+    // host, each block one launch over a column window of the wider tensors).  act: kActSsp / kActSilu where PRE_SSP / HAS_Z apply.
     extern __shared__ uint8_t smem_raw[];
     trace_l(0);
     uint8_t* smem = align1024(smem_raw);
@@ -154,19 +170,20 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
     trace_l(1);
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t row0 = t * NR;
-        stage_rows_kmajor<FP16, NR>(X, row0, n_rows, PRE_SSP, smem + L::X, smem + L::X + 2 * kBlkT);
+        stage_rows_kmajor<FP16, NR>(X, ldx, row0, n_rows, PRE_SSP ? act : 0, smem + L::X, smem + L::X + 2 * kBlkT);
         trace_l(2);
         // epilogue operands do not depend on the MMA: fetch them now so their latency hides behind it
         const bool full = row0 + NR <= n_rows;                 // warp-uniform: no per-row bounds checks on full tiles
-        const int64_t ebase = (row0 + eh * 32) * 128 + f;
+        const int64_t erow = row0 + eh * 32;
+        const int64_t ebase = erow * ldy + f;
         float zr[HAS_Z ? 32 : 1], rr[HAS_R ? 32 : 1];
         if constexpr (HAS_Z) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) zr[j] = (full || row0 + eh * 32 + j < n_rows) ? __ldg(Z + ebase + j * 128) : 0.f;
+            for (int j = 0; j < 32; ++j) zr[j] = (full || erow + j < n_rows) ? __ldg(Z + (erow + j) * ldz + f) : 0.f;
         }
         if constexpr (HAS_R) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rr[j] = (full || row0 + eh * 32 + j < n_rows) ? __ldg(R + ebase + j * 128) : 0.f;
+            for (int j = 0; j < 32; ++j) rr[j] = (full || erow + j < n_rows) ? __ldg(R + (erow + j) * ldr + f) : 0.f;
         }
         fence_proxy_async();
         __syncthreads();
@@ -197,17 +214,17 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float y = v[j] + bf;
-            if constexpr (HAS_Z) y *= sigmoid_fast(zr[j]);
+            if constexpr (HAS_Z) y *= act_grad(zr[j], act);
             if constexpr (HAS_R) y += rr[j];
             v[j] = y;
         }
         if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) Y[ebase + j * 128] = v[j];                // 128 contiguous bytes per warp store
+            for (int j = 0; j < 32; ++j) Y[ebase + j * ldy] = v[j];                // 128 contiguous bytes per warp store
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (row0 + eh * 32 + j < n_rows) Y[ebase + j * 128] = v[j];
+                if (row0 + eh * 32 + j < n_rows) Y[ebase + j * ldy] = v[j];
         }
         __syncthreads();                                   // TMEM / X tile reuse by the next tile
         trace_l(6);
@@ -235,7 +252,7 @@ constexpr int kWgPart = 128 * 128 + 128;              // per-CTA partial: DW [o]
 // [row][feature] tile -> split image (same memory layout as K-major rows; read by the MMA as MN-major).
 // thread = (8 columns 8cg.., rows ro + 16 s); returns the per-thread column sums in acc when requested.
 template <bool FP16, bool SUM>
-__device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64_t row0, int64_t n_rows, bool pre_ssp,
+__device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64_t ldx, int64_t row0, int64_t n_rows, int pre_act,
                                               uint8_t* hi, uint8_t* lo, float (&acc)[8]) {
     const int tid = threadIdx.x, cg = tid & 15, ro = tid >> 4;
     float4 a[4][2];
@@ -243,7 +260,7 @@ __device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64
     for (int s = 0; s < 4; ++s) {
         const int64_t row = row0 + s * 16 + ro;
         if (row < n_rows) {
-            const float* p = X + row * 128 + cg * 8;
+            const float* p = X + row * ldx + cg * 8;
             a[s][0] = ldg4(p); a[s][1] = ldg4(p + 4);
         } else {
             a[s][0] = a[s][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -253,9 +270,9 @@ __device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64
     for (int s = 0; s < 4; ++s) {
         float v[8] = {a[s][0].x, a[s][0].y, a[s][0].z, a[s][0].w, a[s][1].x, a[s][1].y, a[s][1].z, a[s][1].w};
         const bool valid = row0 + s * 16 + ro < n_rows;
-        if (pre_ssp) {
+        if (pre_act) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = valid ? ssp_fast(v[k]) : 0.f;
+            for (int k = 0; k < 8; ++k) v[k] = valid ? act_fwd(v[k], pre_act) : 0.f;
         }
         if (SUM) {
 #pragma unroll
@@ -267,8 +284,8 @@ __device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64
 
 template <bool FP16>
 __global__ void __launch_bounds__(256, 2)
-linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, int64_t n_rows, int pre_ssp,
-                       float* __restrict__ workspace) {
+linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, int64_t n_rows, int pre_act,
+                       float* __restrict__ workspace, int64_t ld_dy, int64_t ld_x) {
     extern __shared__ uint8_t smem_raw[];
     pdl_launch_dependents();
     pdl_wait();
@@ -293,8 +310,8 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
     int done = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++done) {
         const int64_t row0 = t * kNR;
-        stage_rows_mn<FP16, true>(dY, row0, n_rows, false, smem + L::DY, smem + L::DY + 2 * kNBlkT, acc);
-        stage_rows_mn<FP16, false>(X, row0, n_rows, pre_ssp != 0, smem + L::XT, smem + L::XT + 2 * kNBlkT, dummy);
+        stage_rows_mn<FP16, true>(dY, ld_dy, row0, n_rows, 0, smem + L::DY, smem + L::DY + 2 * kNBlkT, acc);
+        stage_rows_mn<FP16, false>(X, ld_x, row0, n_rows, pre_act, smem + L::XT, smem + L::XT + 2 * kNBlkT, dummy);
         fence_proxy_async();
         __syncthreads();
         if (warp == 0) {
@@ -354,7 +371,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
 
 // 256 threads = 32 outputs x 8 slices of the partial list; slices are combined in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
-linear_wgrad_reduce_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ gw, float* __restrict__ gb) {
+linear_wgrad_reduce_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ gw, float* __restrict__ gb, int ld_gw) {
     __shared__ float red[8][33];
     pdl_launch_dependents();
     pdl_wait();
@@ -376,7 +393,7 @@ linear_wgrad_reduce_kernel(const float* __restrict__ workspace, int n_parts, flo
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += red[k][o];
-        if (idx < 128 * 128) gw[idx] = s;
+        if (idx < 128 * 128) gw[(size_t)(idx >> 7) * ld_gw + (idx & 127)] = s;
         else if (gb) gb[idx - 128 * 128] = s;
     }
 }
@@ -402,7 +419,7 @@ using namespace geossl;
 
 template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R>
 static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weight, const float* bias, const float* z, const float* r,
-                            float* y, cudaStream_t st) {
+                            float* y, int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act, cudaStream_t st) {
     static const int wide_min = [] { const char* e = getenv("GEOSSL_LINEAR_WIDE_MIN"); return e ? atoi(e) : 64 * kNumSM; }();
     if (n_rows >= wide_min) {
         // enough rows for every SM: 128-row tiles, one 512-thread CTA per SM (no co-resident CTA competing for the
@@ -417,7 +434,7 @@ static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weigh
         }
         const int64_t tiles = (n_rows + NR - 1) / NR;
         GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, dim3((unsigned)(tiles < kNumSM ? tiles : kNumSM)),
-                               dim3(4 * NR), smem, st, x, n_rows, weight, bias, z, r, y));
+                               dim3(4 * NR), smem, st, x, n_rows, weight, bias, z, r, y, ldx, ldz, ldr, ldy, act));
         GEOSSL_LAUNCH_CHECK();
         return 0;
     }
@@ -430,7 +447,7 @@ static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weigh
         configured.set();
     }
     GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, dim3(tc::node_grid(n_rows)), dim3(4 * NR), smem, st,
-                           x, n_rows, weight, bias, z, r, y));
+                           x, n_rows, weight, bias, z, r, y, ldx, ldz, ldr, ldy, act));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
@@ -450,10 +467,10 @@ int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts
     return 0;
 }
 
-int geossl_pack_weights_batched(const float* const* weights, int n_weights, void* images, void* stream) {
+int geossl_pack_weights_batched(const float* const* weights, const int32_t* lds, int n_weights, void* images, void* stream) {
     if (n_weights == 0) return 0;
     GEOSSL_REQUIRE(weights && images && n_weights > 0, "null pointer");
-    tc::pack_weights_batched_kernel<<<dim3(8, n_weights, 2), 256, 0, as_stream(stream)>>>(weights, (uint8_t*)images);
+    tc::pack_weights_batched_kernel<<<dim3(8, n_weights, 2), 256, 0, as_stream(stream)>>>(weights, lds, (uint8_t*)images);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
@@ -463,14 +480,11 @@ int geossl_debug_set_trace_linear(long long* device_buffer) {
     return 0;
 }
 
-int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, const float* bias, int pre_ssp,
-                     const float* act_grad_input, const float* residual, float* y, int bf16_parts, void* stream) {
-    if (n_rows == 0) return 0;
-    const uint8_t* weight = (const uint8_t*)weight_image;
-    GEOSSL_REQUIRE(x && weight && y && n_rows > 0, "null pointer");
-    cudaStream_t st = as_stream(stream);
-    const int key = (bf16_parts ? 0 : 8) | (pre_ssp ? 4 : 0) | (act_grad_input ? 2 : 0) | (residual ? 1 : 0);
-#define GEOSSL_LIN_CASE(K, A, B, C, D) case K: return launch_linear_tc<A, B, C, D>(x, n_rows, weight, bias, act_grad_input, residual, y, st);
+static int linear_tc_dispatch(const float* x, int64_t n_rows, const uint8_t* weight, const float* bias, int pre_act,
+                              const float* act_grad_input, const float* residual, float* y, int bf16_parts,
+                              int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act, cudaStream_t st) {
+    const int key = (bf16_parts ? 0 : 8) | (pre_act ? 4 : 0) | (act_grad_input ? 2 : 0) | (residual ? 1 : 0);
+#define GEOSSL_LIN_CASE(K, A, B, C, D) case K: return launch_linear_tc<A, B, C, D>(x, n_rows, weight, bias, act_grad_input, residual, y, ldx, ldz, ldr, ldy, act, st);
     switch (key) {
         GEOSSL_LIN_CASE(0, false, false, false, false) GEOSSL_LIN_CASE(1, false, false, false, true)
         GEOSSL_LIN_CASE(2, false, false, true, false)  GEOSSL_LIN_CASE(3, false, false, true, true)
@@ -485,10 +499,44 @@ int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, c
     return GEOSSL_EINVAL;
 }
 
+int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, const float* bias, int pre_ssp,
+                     const float* act_grad_input, const float* residual, float* y, int bf16_parts, void* stream) {
+    if (n_rows == 0) return 0;
+    GEOSSL_REQUIRE(x && weight_image && y && n_rows > 0, "null pointer");
+    return linear_tc_dispatch(x, n_rows, (const uint8_t*)weight_image, bias, pre_ssp, act_grad_input, residual, y, bf16_parts,
+                              128, 128, 128, 128, tc::kActSsp, as_stream(stream));
+}
+
+int geossl_linear_tc_block(const float* x, int64_t ldx, int64_t n_rows, const void* weight_image, const float* bias, int act,
+                           int pre_act, const float* act_grad_input, int64_t ldz, const float* residual, int64_t ldr,
+                           float* y, int64_t ldy, int bf16_parts, void* stream) {
+    if (n_rows == 0) return 0;
+    GEOSSL_REQUIRE(x && weight_image && y && n_rows > 0, "null pointer");
+    GEOSSL_REQUIRE(ldx >= 128 && ldy >= 128 && ldx % 4 == 0 && (!act_grad_input || ldz >= 128) && (!residual || ldr >= 128), "bad leading dimension");
+    GEOSSL_REQUIRE(act == tc::kActSsp || act == tc::kActSilu || !(pre_act || act_grad_input), "act must be 1 (ssp) or 2 (silu)");
+    return linear_tc_dispatch(x, n_rows, (const uint8_t*)weight_image, bias, pre_act, act_grad_input, residual, y, bf16_parts,
+                              ldx, ldz, ldr, ldy, act, as_stream(stream));
+}
+
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::wgrad_grid(n_rows) * tc::kWgPart; }
+
+static int wgrad_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act, float* workspace,
+                       float* grad_weight, int ld_gw, float* grad_bias, void* stream);
 
 int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, int pre_ssp, float* workspace,
                            float* grad_weight, float* grad_bias, void* stream) {
+    return wgrad_block(grad_y, 128, x, 128, n_rows, pre_ssp ? tc::kActSsp : 0, workspace, grad_weight, 128, grad_bias, stream);
+}
+
+int geossl_linear_wgrad_tc_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act,
+                                 float* workspace, float* grad_weight, int ld_gw, float* grad_bias, void* stream) {
+    GEOSSL_REQUIRE(ld_dy >= 128 && ld_x >= 128 && ld_gw >= 128 && ld_dy % 4 == 0 && ld_x % 4 == 0, "bad leading dimension");
+    GEOSSL_REQUIRE(pre_act >= 0 && pre_act <= 2, "pre_act must be 0, 1 (ssp) or 2 (silu)");
+    return wgrad_block(grad_y, ld_dy, x, ld_x, n_rows, pre_act, workspace, grad_weight, ld_gw, grad_bias, stream);
+}
+
+static int wgrad_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act, float* workspace,
+                       float* grad_weight, int ld_gw, float* grad_bias, void* stream) {
     GEOSSL_REQUIRE(grad_y && x && workspace && grad_weight && n_rows > 0, "null pointer or empty input");
     const size_t smem = tc::WgLayout::kBytes + 1024;
     static PerDeviceFlag configured;
@@ -497,9 +545,9 @@ int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, 
         configured.set();
     }
     const int grid = tc::wgrad_grid(n_rows);
-    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid), dim3(256), smem, as_stream(stream), grad_y, x, n_rows, pre_ssp, workspace));
+    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid), dim3(256), smem, as_stream(stream), grad_y, x, n_rows, pre_act, workspace, ld_dy, ld_x));
     GEOSSL_LAUNCH_CHECK();
-    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_reduce_kernel, dim3((tc::kWgPart + 31) / 32), dim3(256), 0, as_stream(stream), workspace, grid, grad_weight, grad_bias));
+    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_reduce_kernel, dim3((tc::kWgPart + 31) / 32), dim3(256), 0, as_stream(stream), workspace, grid, grad_weight, grad_bias, ld_gw));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -17,6 +17,27 @@ namespace geossl {
 
 constexpr int kMaxRbf = 32;
 
+// phi_pad (E,128), optional: [rbf_0 .. rbf_{R-1}, 1, 0 ...] -- the K-padded operand of the tensor-core filter GEMM
+// (column R carries the bias of filter_net); one warp-coalesced 512-byte row per edge.
+__global__ void painn_rbf_pad_kernel(const float* __restrict__ dist, const float* __restrict__ fcut, int64_t n_edges,
+                                     const float* __restrict__ offsets, const float* __restrict__ widths, int R,
+                                     float* __restrict__ phi_pad) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = idx >> 7;
+    const int c = (int)(idx & 127);
+    if (e >= n_edges) return;
+    float v = 0.f;
+    if (c < R) {
+        const float wdt = __ldg(widths + c);
+        const float coeff = -0.5f / __fmul_rn(wdt, wdt);                     // painn_utils.py:100
+        const float diff = __ldg(dist + e) - __ldg(offsets + c);
+        v = expf(__fmul_rn(coeff, __fmul_rn(diff, diff)));
+    } else if (c == R) {
+        v = 1.f;
+    }
+    phi_pad[idx] = v;
+}
+
 __global__ void painn_edge_geom_kernel(const float* __restrict__ pos, const int64_t* __restrict__ rei, int64_t n_edges,
                                        int64_t n_atoms, float cutoff, float* __restrict__ dist, float* __restrict__ dir,
                                        float* __restrict__ fcut) {
@@ -83,13 +104,17 @@ painn_message_fwd_kernel(const float* __restrict__ q, const float* __restrict__ 
                          const float* __restrict__ widths, int R,
                          const float* __restrict__ dist, const float* __restrict__ dir, const float* __restrict__ fcut,
                          const int32_t* __restrict__ i_rowptr, const int32_t* __restrict__ i_eid, const int32_t* __restrict__ i_nbr,
-                         int n_atoms, float* __restrict__ q_out, float* __restrict__ mu_out) {
+                         int n_atoms, float* __restrict__ q_out, float* __restrict__ mu_out, const float* __restrict__ wpre) {
+    // wpre != NULL: the pre-cutoff filter rows (E,3F) were materialised by the tensor-core filter GEMM; each warp streams
+    // its edge's 3F values (coalesced 128-byte segments) instead of rebuilding them from 20 rbf values against shared memory
     constexpr int CPL = F / 32;
     extern __shared__ __align__(16) float smem[];
     float* sW = smem;
     float* sB = smem + 3 * F * R;
-    load_filter_slice<F>(wf, bf, R, sW, sB);
-    __syncthreads();
+    if (wpre == nullptr) {
+        load_filter_slice<F>(wf, bf, R, sW, sB);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_atoms; i += warps_per_grid) {
@@ -102,7 +127,15 @@ painn_message_fwd_kernel(const float* __restrict__ q, const float* __restrict__ 
             const float d = __ldg(dist + e), fc = __ldg(fcut + e);
             const float dx = __ldg(dir + 3 * (int64_t)e), dy = __ldg(dir + 3 * (int64_t)e + 1), dz = __ldg(dir + 3 * (int64_t)e + 2);
             float w[3][CPL];
-            edge_filter<CPL, F>(w, sW, sB, rbf_lane(d, offsets, widths, R, lane), R, fc, lane);
+            if (wpre != nullptr) {
+                const float* wr = wpre + (int64_t)e * 3 * F;
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) w[b][j] = __ldg(wr + b * F + lane + 32 * j) * fc;
+            } else {
+                edge_filter<CPL, F>(w, sW, sB, rbf_lane(d, offsets, widths, R, lane), R, fc, lane);
+            }
             const float* xj = x + (int64_t)nb * 3 * F;
             const float* mj = mu + (int64_t)nb * 3 * F;
 #pragma unroll
@@ -135,13 +168,16 @@ painn_message_bwd_kernel(const float* __restrict__ gq_out, const float* __restri
                          const float* __restrict__ widths, int R,
                          const float* __restrict__ dist, const float* __restrict__ dir, const float* __restrict__ fcut,
                          const int32_t* __restrict__ j_rowptr, const int32_t* __restrict__ j_ctr,
-                         int n_atoms, float* __restrict__ gx, float* __restrict__ gmu_in, float* __restrict__ gfilt) {
+                         int n_atoms, float* __restrict__ gx, float* __restrict__ gmu_in, float* __restrict__ gfilt,
+                         const float* __restrict__ wpre) {
     constexpr int CPL = F / 32;
     extern __shared__ __align__(16) float smem[];
     float* sW = smem;
     float* sB = smem + 3 * F * R;
-    load_filter_slice<F>(wf, bf, R, sW, sB);
-    __syncthreads();
+    if (wpre == nullptr) {
+        load_filter_slice<F>(wf, bf, R, sW, sB);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int jn = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jn < n_atoms; jn += warps_per_grid) {
@@ -161,7 +197,15 @@ painn_message_bwd_kernel(const float* __restrict__ gq_out, const float* __restri
             const float d = __ldg(dist + e), fc = __ldg(fcut + e);
             const float dx = __ldg(dir + 3 * (int64_t)e), dy = __ldg(dir + 3 * (int64_t)e + 1), dz = __ldg(dir + 3 * (int64_t)e + 2);
             float w[3][CPL];
-            edge_filter<CPL, F>(w, sW, sB, rbf_lane(d, offsets, widths, R, lane), R, fc, lane);
+            if (wpre != nullptr) {
+                const float* wr = wpre + (int64_t)e * 3 * F;
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) w[b][j] = __ldg(wr + b * F + lane + 32 * j) * fc;
+            } else {
+                edge_filter<CPL, F>(w, sW, sB, rbf_lane(d, offsets, widths, R, lane), R, fc, lane);
+            }
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 const int f = lane + 32 * j;
@@ -285,8 +329,8 @@ template <int F>
 int launch_msg_fwd(const float* q, const float* mu, const float* x, const float* wf, const float* bf, const float* offsets,
                    const float* widths, int R, const float* dist, const float* dir, const float* fcut,
                    const int32_t* i_rowptr, const int32_t* i_eid, const int32_t* i_nbr, int64_t n_atoms,
-                   float* q_out, float* mu_out, cudaStream_t st) {
-    const size_t smem = (size_t)(3 * F * R + 3 * F) * sizeof(float);
+                   float* q_out, float* mu_out, const float* wpre, cudaStream_t st) {
+    const size_t smem = wpre ? 0 : (size_t)(3 * F * R + 3 * F) * sizeof(float);
     static PerDeviceFlag configured;
     if (!configured.get() && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(painn_message_fwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -296,7 +340,7 @@ int launch_msg_fwd(const float* q, const float* mu, const float* x, const float*
     int64_t blocks = (n_atoms + 7) / 8;
     if (blocks > kNumSM * 4) blocks = kNumSM * 4;
     painn_message_fwd_kernel<F><<<(int)blocks, 256, smem, st>>>(q, mu, x, wf, bf, offsets, widths, R, dist, dir, fcut,
-                                                                 i_rowptr, i_eid, i_nbr, (int)n_atoms, q_out, mu_out);
+                                                                 i_rowptr, i_eid, i_nbr, (int)n_atoms, q_out, mu_out, wpre);
     return 0;
 }
 
@@ -304,8 +348,8 @@ template <int F>
 int launch_msg_bwd(const float* gq_out, const float* gmu_out, const float* mu, const float* x, const float* wf,
                    const float* bf, const float* offsets, const float* widths, int R, const float* dist, const float* dir,
                    const float* fcut, const int32_t* j_rowptr, const int32_t* j_ctr, int64_t n_atoms, int64_t n_edges,
-                   float* gx, float* gmu_in, float* gfilt, float* workspace, float* gw, float* gb, cudaStream_t st) {
-    const size_t smem = (size_t)(3 * F * R + 3 * F) * sizeof(float);
+                   float* gx, float* gmu_in, float* gfilt, float* workspace, float* gw, float* gb, const float* wpre, cudaStream_t st) {
+    const size_t smem = wpre ? 0 : (size_t)(3 * F * R + 3 * F) * sizeof(float);
     static PerDeviceFlag configured;
     if (!configured.get() && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(painn_message_bwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -315,9 +359,10 @@ int launch_msg_bwd(const float* gq_out, const float* gmu_out, const float* mu, c
     int64_t blocks = (n_atoms + 7) / 8;
     if (blocks > kNumSM * 4) blocks = kNumSM * 4;
     painn_message_bwd_kernel<F><<<(int)blocks, 256, smem, st>>>(gq_out, gmu_out, mu, x, wf, bf, offsets, widths, R, dist, dir,
-                                                                 fcut, j_rowptr, j_ctr, (int)n_atoms, gx, gmu_in, gfilt);
+                                                                 fcut, j_rowptr, j_ctr, (int)n_atoms, gx, gmu_in, gfilt, wpre);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
+    if (wpre != nullptr) return 0;     // gfilt IS the gradient of the materialised filter: its GEMM's weight-gradient kernel takes over
     count_launch();
     painn_filter_wgrad_kernel<F><<<kNumSM, 256, 0, st>>>(gfilt, dist, n_edges, j_rowptr + n_atoms, offsets, widths, R, workspace);
     e = cudaGetLastError();
@@ -344,19 +389,31 @@ int geossl_painn_edge_geometry(const float* pos, const int64_t* radius_edge_inde
     return 0;
 }
 
+int geossl_painn_rbf_pad(const float* dist, const float* fcut, int64_t n_edges, const float* offsets, const float* widths, int n_rbf,
+                         float* phi_pad, void* stream) {
+    if (n_edges == 0) return 0;
+    GEOSSL_REQUIRE(dist && fcut && offsets && widths && phi_pad, "null pointer");
+    GEOSSL_REQUIRE(n_rbf >= 1 && n_rbf < 128, "n_rbf must be in [1,127]");
+    const int64_t n = n_edges * 128;
+    painn_rbf_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(dist, fcut, n_edges, offsets, widths, n_rbf, phi_pad);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
 int geossl_painn_message_fwd(const float* q, const float* mu, const float* ctx, const float* filter_w, const float* filter_b,
                              const float* offsets, const float* widths, int n_rbf, int F,
                              const float* dist, const float* dir, const float* fcut,
                              const int32_t* i_rowptr, const int32_t* i_eid, const int32_t* i_nbr, int64_t n_atoms,
-                             float* q_out, float* mu_out, void* stream) {
+                             float* q_out, float* mu_out, const float* filter_pre, void* stream) {
     if (n_atoms == 0) return 0;
-    GEOSSL_REQUIRE(q && mu && ctx && filter_w && filter_b && offsets && widths && i_rowptr && q_out && mu_out, "null pointer");
+    GEOSSL_REQUIRE(q && mu && ctx && offsets && widths && i_rowptr && q_out && mu_out, "null pointer");
+    GEOSSL_REQUIRE(filter_pre || (filter_w && filter_b), "either the materialised filter or the filter_net slice is required");
     GEOSSL_REQUIRE(n_rbf >= 1 && n_rbf <= kMaxRbf, "n_rbf must be in [1,32]");
     int rc;
     switch (F) {
-        case 32: rc = launch_msg_fwd<32>(q, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, i_rowptr, i_eid, i_nbr, n_atoms, q_out, mu_out, as_stream(stream)); break;
-        case 64: rc = launch_msg_fwd<64>(q, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, i_rowptr, i_eid, i_nbr, n_atoms, q_out, mu_out, as_stream(stream)); break;
-        case 128: rc = launch_msg_fwd<128>(q, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, i_rowptr, i_eid, i_nbr, n_atoms, q_out, mu_out, as_stream(stream)); break;
+        case 32: rc = launch_msg_fwd<32>(q, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, i_rowptr, i_eid, i_nbr, n_atoms, q_out, mu_out, filter_pre, as_stream(stream)); break;
+        case 64: rc = launch_msg_fwd<64>(q, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, i_rowptr, i_eid, i_nbr, n_atoms, q_out, mu_out, filter_pre, as_stream(stream)); break;
+        case 128: rc = launch_msg_fwd<128>(q, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, i_rowptr, i_eid, i_nbr, n_atoms, q_out, mu_out, filter_pre, as_stream(stream)); break;
         default: set_error("%s: unsupported width F=%d (32/64/128)", __func__, F); return GEOSSL_EINVAL;
     }
     if (rc) { set_error("%s: %s", __func__, cudaGetErrorString((cudaError_t)rc)); return rc; }
@@ -371,17 +428,18 @@ int geossl_painn_message_bwd(const float* grad_q_out, const float* grad_mu_out, 
                              int n_rbf, int F, const float* dist, const float* dir, const float* fcut,
                              const int32_t* j_rowptr, const int32_t* j_ctr, int64_t n_atoms, int64_t n_edges,
                              float* grad_ctx, float* grad_mu_in, float* edge_scratch, float* workspace,
-                             float* grad_filter_w, float* grad_filter_b, void* stream) {
-    GEOSSL_REQUIRE(grad_q_out && grad_mu_out && mu && ctx && filter_w && filter_b && offsets && widths && j_rowptr &&
-                   grad_ctx && grad_mu_in && workspace && grad_filter_w && grad_filter_b, "null pointer");
+                             float* grad_filter_w, float* grad_filter_b, const float* filter_pre, void* stream) {
+    GEOSSL_REQUIRE(grad_q_out && grad_mu_out && mu && ctx && offsets && widths && j_rowptr && grad_ctx && grad_mu_in, "null pointer");
+    GEOSSL_REQUIRE(filter_pre || (filter_w && filter_b && workspace && grad_filter_w && grad_filter_b),
+                   "either the materialised filter or the filter_net slice (+ its gradient buffers) is required");
     GEOSSL_REQUIRE(n_edges == 0 || (edge_scratch && dist && dir && fcut && j_ctr), "null edge pointer");
     GEOSSL_REQUIRE(n_rbf >= 1 && n_rbf <= kMaxRbf, "n_rbf must be in [1,32]");
     GEOSSL_REQUIRE(n_atoms > 0, "n_atoms must be > 0");
     int rc;
     switch (F) {
-        case 32: rc = launch_msg_bwd<32>(grad_q_out, grad_mu_out, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, j_rowptr, j_ctr, n_atoms, n_edges, grad_ctx, grad_mu_in, edge_scratch, workspace, grad_filter_w, grad_filter_b, as_stream(stream)); break;
-        case 64: rc = launch_msg_bwd<64>(grad_q_out, grad_mu_out, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, j_rowptr, j_ctr, n_atoms, n_edges, grad_ctx, grad_mu_in, edge_scratch, workspace, grad_filter_w, grad_filter_b, as_stream(stream)); break;
-        case 128: rc = launch_msg_bwd<128>(grad_q_out, grad_mu_out, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, j_rowptr, j_ctr, n_atoms, n_edges, grad_ctx, grad_mu_in, edge_scratch, workspace, grad_filter_w, grad_filter_b, as_stream(stream)); break;
+        case 32: rc = launch_msg_bwd<32>(grad_q_out, grad_mu_out, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, j_rowptr, j_ctr, n_atoms, n_edges, grad_ctx, grad_mu_in, edge_scratch, workspace, grad_filter_w, grad_filter_b, filter_pre, as_stream(stream)); break;
+        case 64: rc = launch_msg_bwd<64>(grad_q_out, grad_mu_out, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, j_rowptr, j_ctr, n_atoms, n_edges, grad_ctx, grad_mu_in, edge_scratch, workspace, grad_filter_w, grad_filter_b, filter_pre, as_stream(stream)); break;
+        case 128: rc = launch_msg_bwd<128>(grad_q_out, grad_mu_out, mu, ctx, filter_w, filter_b, offsets, widths, n_rbf, dist, dir, fcut, j_rowptr, j_ctr, n_atoms, n_edges, grad_ctx, grad_mu_in, edge_scratch, workspace, grad_filter_w, grad_filter_b, filter_pre, as_stream(stream)); break;
         default: set_error("%s: unsupported width F=%d (32/64/128)", __func__, F); return GEOSSL_EINVAL;
     }
     if (rc) { set_error("%s: %s", __func__, cudaGetErrorString((cudaError_t)rc)); return rc; }

@@ -83,8 +83,7 @@ class GraphedFinetuneStep:
 
     def __init__(self, step_fn, example_batches, optimizer, warmup=2, margin=1.02):
         from .data import pad_batch
-        from .pretrain import _batch_tensors
-        self._tensors, self._pad = _batch_tensors, pad_batch
+        self._pad = pad_batch
         n_max = max(b.positions.size(0) for b in example_batches)
         same = len({b.positions.size(0) for b in example_batches}) == 1
         self.n_cap = n_max if same else -(-int(margin * n_max) // 128) * 128
@@ -107,10 +106,16 @@ class GraphedFinetuneStep:
         with torch.cuda.graph(self.graph):
             self.loss = step_fn(self.static)
 
+    @staticmethod
+    def _tensors(b):
+        """x, positions, batch + the tensor extras (targets); fine-tune batches carry no atom pairs."""
+        return [b.x, b.positions, b.batch] + [b.extras[k] for k in sorted(b.extras) if torch.is_tensor(b.extras[k])]
+
     def pad(self, batch):
         if not self.padded or batch.extras.get("n_graphs_live") is not None:
             return batch
-        return self._pad(batch, self.n_cap, 0)
+        return self._pad(type(batch)(batch.x, batch.positions, batch.batch, None, None, batch.n_graphs, batch.graph_ptr,
+                                     dict(batch.extras)), self.n_cap, 0)
 
     def __call__(self, batch):
         for d, t in zip(self._tensors(self.static), self._tensors(self.pad(batch))):

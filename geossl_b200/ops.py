@@ -577,7 +577,7 @@ def prepack_linear_weights(layers):
     lib = _lib.load()
     nbytes = lib.geossl_weight_image_bytes()
     images = torch.empty((len(ws), 2, nbytes), dtype=torch.uint8, device=dev)
-    check(lib.geossl_pack_weights_batched(_p(table), len(ws), _p(images), _stream()), "pack_weights_batched")
+    check(lib.geossl_pack_weights_batched(_p(table), None, len(ws), _p(images), _stream()), "pack_weights_batched")
     return {l: (images[i, 0], images[i, 1]) for i, l in enumerate(layers)}
 
 
@@ -590,6 +590,174 @@ def linear(x, layer, pre_ssp=False, residual=None, images=None):
         x = torch.nn.functional.softplus(x) - 0.6931471824645996
     y = torch.nn.functional.linear(x, w, layer.bias)
     return y if residual is None else residual + y
+
+
+# =====================================================================================================
+# wider atom-wise dense layers (PaiNN: 128->384, 256->128, 128->256) as 128 x 128 blocks of the same kernels
+# =====================================================================================================
+ACT_NONE, ACT_SSP, ACT_SILU = 0, 1, 2
+
+
+def dense_tc_applies(layer):
+    w = layer.weight
+    return FILTER_MODE != "simt" and w.is_cuda and w.size(0) % 128 == 0 and w.size(1) % 128 == 0
+
+
+def prepack_dense_blocks(weights):
+    """Operand images of every 128 x 128 block of the given weight matrices (out, in multiples of 128) with ONE launch:
+    returns {id(weight): images (out/128, in/128, 2, nbytes) uint8} -- [..., 0] forward (fp16 parts), [..., 1] transposed
+    (bf16 parts, data gradient).  Valid for the current forward/backward only."""
+    weights = [w for w in weights if w.is_cuda and w.size(0) % 128 == 0 and w.size(1) % 128 == 0]
+    if not weights or FILTER_MODE == "simt":
+        return {}
+    dev = weights[0].device
+    ptrs, lds, shapes = [], [], []
+    for w in weights:
+        wd = _req(w.detach(), torch.float32, "weight", 2)
+        no, ni = wd.size(0) // 128, wd.size(1) // 128
+        shapes.append((no, ni))
+        for ob in range(no):
+            for ib in range(ni):
+                ptrs.append(wd.data_ptr() + 4 * (ob * 128 * wd.size(1) + ib * 128))
+                lds.append(wd.size(1))
+    key = (dev, "blocks", tuple(ptrs))
+    table = _ptr_tables.get(key)
+    if table is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("geossl_b200: run the model once before capturing it in a CUDA graph (weight pointer table)")
+        if len(_ptr_tables) > 16:
+            _ptr_tables.clear()
+        table = _ptr_tables[key] = (torch.tensor(ptrs, dtype=torch.int64, device=dev), torch.tensor(lds, dtype=torch.int32, device=dev))
+    lib = _lib.load()
+    nbytes = lib.geossl_weight_image_bytes()
+    images = torch.empty((len(ptrs), 2, nbytes), dtype=torch.uint8, device=dev)
+    check(lib.geossl_pack_weights_batched(_p(table[0]), _p(table[1]), len(ptrs), _p(images), _stream()), "pack_weights_batched")
+    out, off = {}, 0
+    for w, (no, ni) in zip(weights, shapes):
+        out[id(w)] = images[off:off + no * ni].view(no, ni, 2, nbytes)
+        off += no * ni
+    return out
+
+
+def _off(t, cols):
+    """Device pointer of column ``cols`` of row 0 of a row-major fp32 matrix."""
+    return ctypes.c_void_p(t.data_ptr() + 4 * cols)
+
+
+class DenseTC(torch.autograd.Function):
+    """y (n,N) = act(x (n,K)) @ W (N,K)^T + b, K and N multiples of 128, as N/128 x K/128 launches of the 128 x 128 tensor-core
+    layer kernel over column windows (geossl_linear_tc_block); K-blocks accumulate through the residual input.
+    ``pre_act``: ACT_NONE / ACT_SSP / ACT_SILU applied to x as it is staged -- PaiNN's ``Dense(activation=silu)`` followed by a
+    ``Dense`` is ``DenseTC(DenseTC(x, W1, b1), W2, b2, pre_act=ACT_SILU)`` (painn.py:21-24, painn_utils.py:9-35).
+    Backward: data gradient through the transposed images (x act'(x) in the epilogue), weight gradients by
+    geossl_linear_wgrad_tc_block per block (side stream inside ``side_stream_wgrads()``)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pre_act, images):
+        x, weight = _req(x, torch.float32, "x", 2), _req(weight, torch.float32, "weight", 2)
+        N, K = weight.shape
+        if x.size(1) != K or N % 128 or K % 128:
+            raise RuntimeError(f"geossl_b200: DenseTC needs in/out features in multiples of 128, got {tuple(weight.shape)}")
+        bias = None if bias is None else _req(bias, torch.float32, "bias", 1)
+        n = x.size(0)
+        ctx.pre_act, ctx.images, ctx.params = int(pre_act), images, (weight, bias)
+        ctx.save_for_backward(x, weight)
+        y = torch.empty((n, N), dtype=torch.float32, device=x.device)
+        if n == 0:
+            return y
+        lib = _lib.load()
+        act = ctx.pre_act or ACT_SSP
+        for ob in range(N // 128):
+            for ib in range(K // 128):
+                _timed("dense_fwd", lambda: lib.geossl_linear_tc_block(
+                    _off(x, ib * 128), K, n, _p(images[ob, ib, 0]), None if (bias is None or ib) else _off(bias, ob * 128), act,
+                    1 if ctx.pre_act else 0, None, 128, _off(y, ob * 128) if ib else None, N, _off(y, ob * 128), N, 0, _stream()))
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, K = weight.shape
+        n = x.size(0)
+        lib = _lib.load()
+        images, act = ctx.images, ctx.pre_act or ACT_SSP
+        gx = None
+        if n == 0:
+            return torch.zeros_like(x), torch.zeros_like(weight), None if ctx.params[1] is None else torch.zeros(N, device=x.device), None, None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            for ib in range(K // 128):
+                for ob in range(N // 128):
+                    _timed("dense_dgrad", lambda: lib.geossl_linear_tc_block(
+                        _off(gy, ob * 128), N, n, _p(images[ob, ib, 1]), None, act, 0,
+                        _off(x, ib * 128) if ctx.pre_act else None, K, _off(gx, ib * 128) if ob else None, K, _off(gx, ib * 128), K, 1,
+                        _stream()))
+        gw = gb = None
+        wp, bp = ctx.params
+        if ctx.needs_input_grad[1] or (bp is not None and ctx.needs_input_grad[2]):
+            def wgrad():
+                gw_ = torch.empty_like(weight)
+                gb_ = torch.empty(N, dtype=torch.float32, device=x.device) if bp is not None else None
+                ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
+                for ob in range(N // 128):
+                    for ib in range(K // 128):
+                        _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
+                            _off(gy, ob * 128), N, _off(x, ib * 128), K, n, ctx.pre_act, _p(ws), _off(gw_, ob * 128 * K + ib * 128), K,
+                            None if (gb_ is None or ib) else _off(gb_, ob * 128), _stream()))
+                return gw_, gb_
+
+            deferrable = wp.is_leaf and wp.requires_grad and (bp is None or (bp.is_leaf and bp.requires_grad))
+            if _SIDE["on"] and deferrable:
+                main, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    gw, gb = wgrad()
+                for t in (gy, x):
+                    t.record_stream(side)
+                for t in (gw, gb):
+                    if t is not None:
+                        t.record_stream(main)
+                _SIDE["dirty"] = True
+                _SIDE["pending"].append((wp, gw))
+                if gb is not None:
+                    _SIDE["pending"].append((bp, gb))
+                gw = gb = None
+            else:
+                gw, gb = wgrad()
+        return gx, gw, gb, None, None
+
+
+class FilterPad(torch.autograd.Function):
+    """[W_f | b_f | 0] (C,128) written into a PERSISTENT buffer (its address must not change between forwards: the packed
+    block pointer table is cached, and a captured CUDA graph replays fixed addresses).  Backward slices the gradient."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, buf):
+        R = weight.size(1)
+        buf[:, :R].copy_(weight)
+        buf[:, R].copy_(bias)
+        ctx.R = R
+        ctx.mark_dirty(buf)
+        return buf
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, :ctx.R], g[:, ctx.R], None
+
+
+def dense(x, layer, images=None, pre_act=ACT_NONE):
+    """``layer(act(x))`` for an nn.Linear-like layer with in/out features in multiples of 128: tensor-core blocks when
+    ``images`` (from prepack_dense_blocks) has the layer, library GEMM otherwise."""
+    w = layer.weight
+    if images and id(w) in images and x.is_cuda and x.dim() == 2:
+        return DenseTC.apply(x, w, layer.bias, pre_act, images[id(w)])
+    if pre_act == ACT_SILU:
+        x = torch.nn.functional.silu(x)
+    elif pre_act == ACT_SSP:
+        x = torch.nn.functional.softplus(x) - 0.6931471824645996
+    return torch.nn.functional.linear(x, w, layer.bias)
 
 
 # =====================================================================================================
@@ -657,7 +825,7 @@ class DDMHead(torch.autograd.Function):
     front are live (CUDA-graph replay over variable-size batches)."""
 
     @staticmethod
-    def forward(ctx, node_feature, sei, batch, dist, noise, noise_level, sigmas, anneal_power, n_pairs_live, *params):
+    def forward(ctx, node_feature, sei, batch, dist, noise, noise_level, sigmas, anneal_power, n_pairs_live, train_pass, *params):
         h = _req(node_feature, torch.float32, "node_feature", 2)
         sei = _req(sei, torch.int64, "super_edge_index", 2)
         batch = _req(batch, torch.int64, "batch", 1)
@@ -671,9 +839,10 @@ class DDMHead(torch.autograd.Function):
         H = h.size(1)
         n_pairs = sei.size(1)
         ctx.tc = FILTER_MODE != "simt" and H == 128
-        # (needs_input_grad is all False under torch.no_grad(): evaluation takes the forward-only kernel)
-        ctx.fused = bool(ctx.tc and FUSE_DDM_HEAD and n_pairs > 0
-                         and any(ctx.needs_input_grad[i] for i in (0, *range(9, 9 + len(params)))))
+        # ``train_pass`` = torch.is_grad_enabled() at the call site (inside forward() grad mode is always off, and
+        # needs_input_grad ignores torch.no_grad()): evaluation takes the forward-only kernel
+        ctx.fused = bool(ctx.tc and FUSE_DDM_HEAD and n_pairs > 0 and train_pass
+                         and any(ctx.needs_input_grad[i] for i in (0, *range(10, 10 + len(params)))))
         ws = torch.empty(max(lib.geossl_ddm_workspace_tc(n_pairs) if ctx.tc else lib.geossl_ddm_workspace(H), 1),
                          dtype=torch.float32, device=h.device)
         loss = torch.empty(2, dtype=torch.float32, device=h.device)
@@ -704,14 +873,14 @@ class DDMHead(torch.autograd.Function):
             ng = loss[1]
             scale = torch.where(ng > 0, grad_loss.to(torch.float32) / ng, torch.zeros_like(ng))
             scaled = torch._foreach_mul([grad_h, *grads], scale)              # out of place: a retained graph may run again
-            return (scaled[0], None, None, None, None, None, None, None, None, *scaled[1:])
+            return (scaled[0], None, None, None, None, None, None, None, None, None, *scaled[1:])
         h, sei, batch, dist, noise, noise_level, sigmas, loss, *params = ctx.saved_tensors
         lib = _lib.load()
         H, n_pairs = h.size(1), sei.size(1)
         grad_h = torch.empty_like(h)
         grads = [torch.empty_like(p) for p in params]
         if n_pairs == 0:
-            return (torch.zeros_like(h), None, None, None, None, None, None, None, None, *[torch.zeros_like(p) for p in params])
+            return (torch.zeros_like(h), None, None, None, None, None, None, None, None, None, *[torch.zeros_like(p) for p in params])
         ws = torch.empty(lib.geossl_ddm_workspace_tc(n_pairs) if ctx.tc else lib.geossl_ddm_workspace(H),
                          dtype=torch.float32, device=h.device)
         gl = grad_loss.contiguous().view(1).to(torch.float32)
@@ -721,7 +890,7 @@ class DDMHead(torch.autograd.Function):
             _p(h), _p(sei), _p(batch), n_pairs, _p(ctx.live), h.size(0), _p(dist), _p(noise), _p(noise_level), _p(sigmas),
             sigmas.numel(), ctx.anneal_power, H, ctypes.byref(pp), _p(loss), _p(gl), _p(ws), _p(grad_h), ctypes.byref(gp),
             _stream()))
-        return (grad_h, None, None, None, None, None, None, None, None, *grads)
+        return (grad_h, None, None, None, None, None, None, None, None, None, *grads)
 
 
 # =====================================================================================================
@@ -733,6 +902,16 @@ class PaiNNEdges:
     def __init__(self, structure, dist, dir_, fcut, offsets, widths):
         self.s, self.dist, self.dir, self.fcut = structure, dist, dir_, fcut
         self.offsets, self.widths = offsets, widths
+        self._phi_pad = None
+
+    def phi_pad(self):
+        """(E,128) = [rbf values, 1, 0...]: K-padded operand of the tensor-core filter GEMM (built once per forward)."""
+        if self._phi_pad is None:
+            e = self.dist.numel()
+            self._phi_pad = torch.empty((e, 128), dtype=torch.float32, device=self.dist.device)
+            check(_lib.load().geossl_painn_rbf_pad(_p(self.dist), _p(self.fcut), e, _p(self.offsets), _p(self.widths),
+                                                   self.offsets.numel(), _p(self._phi_pad), _stream()), "painn_rbf_pad")
+        return self._phi_pad
 
 
 _structure_cache = {}
@@ -779,32 +958,53 @@ def painn_edges(positions, radius_edge_index, n_atoms, batch, offsets, widths, c
 
 
 class PaiNNMessage(torch.autograd.Function):
-    """(q, mu, ctx, filter slice) -> (q + dq, mu + dmu)   (painn.py:53-64 with the filter of :241 fused in)."""
+    """(q, mu, ctx, filter) -> (q + dq, mu + dmu)   (painn.py:53-64).  The filter of painn.py:241 is either rebuilt per edge
+    from the ``filter_net`` slice ``(fw, fb)`` inside the kernels (``wpre`` None) or streamed from the materialised
+    pre-cutoff rows ``wpre`` (E,3F) of the tensor-core filter GEMM -- then ``wpre`` receives the per-edge gradient and the
+    ``filter_net`` gradients flow through that GEMM."""
 
     @staticmethod
-    def forward(ctx, q, mu, x, fw, fb, edges):
+    def forward(ctx, q, mu, x, fw, fb, edges, wpre=None):
         q, mu, x = _req(q, torch.float32, "q", 2), _req(mu, torch.float32, "mu", 3), _req(x, torch.float32, "ctx", 2)
-        fw, fb = _req(fw, torch.float32, "filter_w", 2), _req(fb, torch.float32, "filter_b", 1)
+        if wpre is None:
+            fw, fb = _req(fw, torch.float32, "filter_w", 2), _req(fb, torch.float32, "filter_b", 1)
+        else:
+            wpre = _req(wpre, torch.float32, "filter_pre", 2)
+            fw = fb = None
         n, Fd = q.shape
         s = edges.s
         q_out, mu_out = torch.empty_like(q), torch.empty_like(mu)
         _timed("painn_message_fwd", lambda: _lib.load().geossl_painn_message_fwd(
             _p(q), _p(mu), _p(x), _p(fw), _p(fb), _p(edges.offsets), _p(edges.widths), edges.offsets.numel(), Fd, _p(edges.dist),
-            _p(edges.dir), _p(edges.fcut), _p(s.t_rowptr), _p(s.t_eid), _p(s.t_tgt), n, _p(q_out), _p(mu_out), _stream()))
-        ctx.edges = edges
-        ctx.save_for_backward(mu, x, fw, fb)
+            _p(edges.dir), _p(edges.fcut), _p(s.t_rowptr), _p(s.t_eid), _p(s.t_tgt), n, _p(q_out), _p(mu_out), _p(wpre), _stream()))
+        ctx.edges, ctx.has_pre = edges, wpre is not None
+        if wpre is None:
+            ctx.save_for_backward(mu, x, fw, fb)
+        else:
+            ctx.save_for_backward(mu, x, wpre)
         return q_out, mu_out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gq_out, gmu_out):
-        mu, x, fw, fb = ctx.saved_tensors
         edges, s = ctx.edges, ctx.edges.s
         lib = _lib.load()
         n, Fd = gq_out.shape
         e = s.rei.size(1)
         R = edges.offsets.numel()
         gq_out, gmu_out = gq_out.contiguous(), gmu_out.contiguous()
+        if ctx.has_pre:
+            mu, x, wpre = ctx.saved_tensors
+            gx, gmu = torch.empty_like(x), torch.empty_like(mu)
+            # rows past the live edge count (capacity-padded lists) are never written by the kernel: they must be zeros,
+            # because the filter GEMM's weight-gradient kernel contracts over ALL rows
+            gpre = (torch.zeros if e > 0 else torch.empty)((max(e, 1), 3 * Fd), dtype=torch.float32, device=x.device)
+            _timed("painn_message_bwd", lambda: lib.geossl_painn_message_bwd(
+                _p(gq_out), _p(gmu_out), _p(mu), _p(x), None, None, _p(edges.offsets), _p(edges.widths), R, Fd, _p(edges.dist),
+                _p(edges.dir), _p(edges.fcut), _p(s.rowptr), _p(s.src), n, e, _p(gx), _p(gmu), _p(gpre), None, None, None,
+                _p(wpre), _stream()))
+            return gq_out, gmu, gx, None, None, None, gpre[:e] if e > 0 else torch.zeros_like(wpre)
+        mu, x, fw, fb = ctx.saved_tensors
         gx, gmu = torch.empty_like(x), torch.empty_like(mu)
         gw, gb = torch.empty_like(fw), torch.empty_like(fb)
         scratch = torch.empty((max(e, 1), 3 * Fd), dtype=torch.float32, device=x.device)
@@ -812,8 +1012,8 @@ class PaiNNMessage(torch.autograd.Function):
         _timed("painn_message_bwd", lambda: lib.geossl_painn_message_bwd(
             _p(gq_out), _p(gmu_out), _p(mu), _p(x), _p(fw), _p(fb), _p(edges.offsets), _p(edges.widths), R, Fd, _p(edges.dist),
             _p(edges.dir), _p(edges.fcut), _p(s.rowptr), _p(s.src), n, e, _p(gx), _p(gmu), _p(scratch), _p(ws), _p(gw), _p(gb),
-            _stream()))
-        return gq_out, gmu, gx, gw, gb, None
+            None, _stream()))
+        return gq_out, gmu, gx, gw, gb, None, None
 
 
 # =====================================================================================================

@@ -185,12 +185,25 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
  * one bulk async copy (cp.async.bulk). */
 int64_t geossl_weight_image_bytes(void);
 int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts, void* image, void* stream);
-/* Every 128 x 128 layer of a model in one launch: `weights` = DEVICE array of n_weights device pointers; images =
- * n_weights x 2 x geossl_weight_image_bytes(): [layer][0] forward image (fp16 parts), [layer][1] data-gradient image
- * (transposed, bf16 parts). */
-int geossl_pack_weights_batched(const float* const* weights, int n_weights, void* images, void* stream);
+/* Every 128 x 128 weight BLOCK of a model in one launch: `weights` = DEVICE array of n_weights device pointers to the first
+ * element of a block, `lds` = DEVICE array of the leading dimensions (in_features) of the matrices the blocks live in
+ * (NULL => 128: plain 128 x 128 layers); images = n_weights x 2 x geossl_weight_image_bytes(): [b][0] forward image
+ * (fp16 parts), [b][1] data-gradient image (transposed, bf16 parts). */
+int geossl_pack_weights_batched(const float* const* weights, const int32_t* lds, int n_weights, void* images, void* stream);
 int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, const float* bias, int pre_ssp,
                      const float* act_grad_input, const float* residual, float* y, int bf16_parts, void* stream);
+
+/* One 128 x 128 BLOCK of a wider dense layer (PaiNN's Dense 128->384, 256->128, 128->256: painn.py:21-24,76-83,
+ * painn_utils.py:9-35): the same kernel over column windows of wider row-major tensors.  x / act_grad_input / residual / y
+ * point at the first element of their 128-column window; ld* are the row strides in floats.  act selects the
+ * pre-activation (pre_act != 0) and its derivative (act_grad_input != NULL): 1 = shifted softplus, 2 = SiLU.  A K > 128
+ * layer is the sum of its K-blocks: pass the partial result as `residual` (it may alias y). */
+int geossl_linear_tc_block(const float* x, int64_t ldx, int64_t n_rows, const void* weight_image, const float* bias, int act,
+                           int pre_act, const float* act_grad_input, int64_t ldz, const float* residual, int64_t ldr,
+                           float* y, int64_t ldy, int bf16_parts, void* stream);
+/* grad_weight block [o][i] (row stride ld_gw) = sum_r grad_y[r][o] * pre(x[r][i]), pre_act in {0, 1 = ssp, 2 = SiLU}. */
+int geossl_linear_wgrad_tc_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act,
+                                 float* workspace, float* grad_weight, int ld_gw, float* grad_bias, void* stream);
 
 /* grad_weight[o][i] = sum_r grad_y[r][o] * pre(x[r][i]);  grad_bias[o] = sum_r grad_y[r][o] (may be NULL). */
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows);
@@ -296,7 +309,16 @@ int geossl_painn_message_fwd(const float* q, const float* mu, const float* ctx, 
                              const float* offsets, const float* widths, int n_rbf, int F,
                              const float* dist, const float* dir, const float* fcut,
                              const int32_t* i_rowptr, const int32_t* i_eid, const int32_t* i_nbr, int64_t n_atoms,
-                             float* q_out, float* mu_out, void* stream);
+                             float* q_out, float* mu_out, const float* filter_pre, void* stream);
+/* filter_pre (fwd and bwd): NULL => the 3F filter values of an edge are rebuilt from the rbf values against the
+ * filter_net slice (any F).  Otherwise (E,3F): the PRE-cutoff filter rows phi_e W_f^T + b_f materialised by the tensor-core
+ * filter GEMM (geossl_painn_rbf_pad + geossl_linear_tc_block over the K-padded rbf matrix); the kernels stream them and
+ * multiply by fcut.  In the backward, edge_scratch then IS the gradient w.r.t. filter_pre and the filter_net gradients come
+ * from that GEMM's weight-gradient kernel (geossl_linear_wgrad_tc_block); filter_w/b, workspace, grad_filter_* may be NULL. */
+/* phi_pad (E,128) = [rbf_0(d_e) .. rbf_{R-1}(d_e), 1, 0, ...]: the K-padded A operand of the filter GEMM (column R carries
+ * the bias of filter_net).  GaussianRBF, painn_utils.py:99-103. */
+int geossl_painn_rbf_pad(const float* dist, const float* fcut, int64_t n_edges, const float* offsets, const float* widths, int n_rbf,
+                         float* phi_pad, void* stream);
 
 /* Backward.  (j_rowptr, j_ctr): rowptr over the idx_j-sorted edge list and idx_i of each edge (int32).
  * Outputs: grad_ctx (N,3F), grad_mu_in (N,3,F) (includes the identity path), grad_filter_w (3F,n_rbf),
@@ -308,7 +330,7 @@ int geossl_painn_message_bwd(const float* grad_q_out, const float* grad_mu_out, 
                              int n_rbf, int F, const float* dist, const float* dir, const float* fcut,
                              const int32_t* j_rowptr, const int32_t* j_ctr, int64_t n_atoms, int64_t n_edges,
                              float* grad_ctx, float* grad_mu_in, float* edge_scratch, float* workspace,
-                             float* grad_filter_w, float* grad_filter_b, void* stream);
+                             float* grad_filter_w, float* grad_filter_b, const float* filter_pre, void* stream);
 
 /* PaiNN update block, non-GEMM part (PaiNNMixing.forward, painn.py:100-113).  mu_mix (N,3,2F) = mu_channel_mix(mu).
  *   pre : ctx (N,2F) = [q, sqrt(sum_xyz mu_V^2 + eps)], dot (N,F) = sum_xyz mu_V*mu_W

@@ -172,7 +172,9 @@ def _ddm_backward(name):
 
 
 @pytest.mark.parametrize("name", ["painn_small", "painn_full"])
-def test_painn_module_vs_golden(name):
+def test_painn_module_vs_golden(name, filter_mode):
+    """painn_full (F = 128) runs its Dense layers and the filter GEMM as tensor-core blocks in tc mode (ops.DenseTC);
+    painn_small (F = 32) always takes the fp32 kernels."""
     g = Golden(name)
     m = painn_from(g, DEV)
     i = g["in"]
@@ -180,8 +182,9 @@ def test_painn_module_vs_golden(name):
     assert rel_err(q, g["out"]["q"]) <= TOL_OUT and rel_err(h, g["out"]["h"]) <= TOL_OUT
     ((q * i["w_q"].to(DEV)).sum() + (h * i["w_h"].to(DEV)).sum()).backward()
     got = grads_of(m)
+    tol = TOL_GRAD if filter_mode == "simt" else TC_TOL_ENCODER
     for k, ref in g["grad"].items():
-        assert rel_err(got[k], ref) <= TOL_GRAD, (k, rel_err(got[k], ref))
+        assert rel_err(got[k], ref) <= tol, (k, rel_err(got[k], ref))
     assert got["embedding.weight"][0].abs().max() == 0
 
 
