@@ -38,7 +38,8 @@ _SIGNATURES = {
     "geossl_last_error": (ctypes.c_char_p, []),
     "geossl_launch_count": (c_i64, [c_int]),
     "geossl_graph_ptr": (c_int, [c_p, c_i64, c_i64, c_p, c_p]),
-    "geossl_radius_csr": (c_int, [c_p, c_p, c_p, c_i64, c_f, c_int, c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "geossl_radius_csr": (c_int, [c_p, c_p, c_p, c_i64, c_f, c_int, c_i64, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p]),
+    "geossl_radius_cell_keys": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_f, c_p, c_p, c_p]),
     "geossl_csr_to_edge_index": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "geossl_csr_transpose": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "geossl_super_edges": (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_i64, c_p, c_p, c_p]),
@@ -50,8 +51,8 @@ _SIGNATURES = {
     "geossl_debug_set_trace_head": (c_int, [c_p]),
     "geossl_debug_set_trace_linear": (c_int, [c_p]),
     "geossl_tc_selftest": (c_int, [c_int, c_int, c_p, c_p, c_int, c_int, c_p, c_p]),
-    "geossl_cfconv_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
-    "geossl_cfconv_bwd_x": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
+    "geossl_cfconv_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p, c_p]),
+    "geossl_cfconv_bwd_x": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p, c_p]),
     "geossl_pair_index": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "geossl_cfconv_bwd_w": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
     "geossl_filter_bwd_workspace": (c_i64, [c_int, c_int]),

@@ -36,34 +36,30 @@ __global__ void graph_ptr_kernel(const int64_t* __restrict__ keys, int64_t n, in
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float dist2_rn(float ax, float ay, float az, float bx, float by, float bz) {
-    // ((dx*dx) + dy*dy) + dz*dz, every op rounded separately (no FMA contraction)
+__device__ __forceinline__ float dist2_rn(float ax, float ay, float az, float bx, float by, float bz, int fma = 0) {
     float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    // GEOSSL_RADIUS_FMA: `dist += (x - y) * (x - y)` contracted by the compiler (nvcc -fmad=true, the default torch_cluster
+    // is built with): dist = fma(dz, dz, fma(dy, dy, dx * dx)) -- one rounding fewer per term
+    if (fma) return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    // default: ((dx*dx) + dy*dy) + dz*dz, every op rounded separately (no FMA contraction)
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// MODE 0: count (deg) ; MODE 1: fill (src / edge_tgt / edge_dist at rowptr[y] + rank)
+// Index-order scan of one query atom y by one warp (torch_cluster's radius_kernel semantics, 32 candidates per ballot).
+// MODE 0: count (deg) ; MODE 1: fill (src / edge_tgt / edge_dist at rowptr[y] + rank).  Returns the number of edges kept.
 template <int MODE>
-__global__ void __launch_bounds__(256)
-radius_scan_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch,
-                   const int32_t* __restrict__ graph_ptr, int n_atoms, float r2, int limit,
-                   int32_t* __restrict__ deg, const int32_t* __restrict__ rowptr, int64_t capacity,
-                   int32_t* __restrict__ src, int32_t* __restrict__ edge_tgt, float* __restrict__ edge_dist) {
-    const int lane = threadIdx.x & 31;
-    const int y = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (y >= n_atoms) return;
-    const int g = (int)batch[y];
-    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+__device__ __forceinline__ int scan_atom(const float* __restrict__ pos, int y, int lo, int hi, float r2, int limit, int fma,
+                                         int64_t base, int64_t capacity, int32_t* __restrict__ src,
+                                         int32_t* __restrict__ edge_tgt, float* __restrict__ edge_dist, int lane) {
     const float yx = __ldg(pos + 3 * (int64_t)y), yy = __ldg(pos + 3 * (int64_t)y + 1), yz = __ldg(pos + 3 * (int64_t)y + 2);
     int hits = 0;      // hits so far, self included (torch_cluster counts self against the limit)
     int kept = 0;      // edges kept so far (self excluded)
-    const int64_t base = (MODE == 1) ? (int64_t)rowptr[y] : 0;
     for (int c0 = lo; c0 < hi && hits < limit; c0 += 32) {
         const int c = c0 + lane;
         float d2 = 0.f;
         bool in = false;
         if (c < hi) {
-            d2 = dist2_rn(__ldg(pos + 3 * (int64_t)c), __ldg(pos + 3 * (int64_t)c + 1), __ldg(pos + 3 * (int64_t)c + 2), yx, yy, yz);
+            d2 = dist2_rn(__ldg(pos + 3 * (int64_t)c), __ldg(pos + 3 * (int64_t)c + 1), __ldg(pos + 3 * (int64_t)c + 2), yx, yy, yz, fma);
             in = d2 < r2;
         }
         unsigned mask = __ballot_sync(0xffffffffu, in);
@@ -90,7 +86,197 @@ radius_scan_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ba
         }
         kept += __popc(emask);
     }
+    return kept;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+radius_scan_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch,
+                   const int32_t* __restrict__ graph_ptr, int n_atoms, float r2, int limit, int fma,
+                   int32_t* __restrict__ deg, const int32_t* __restrict__ rowptr, int64_t capacity,
+                   int32_t* __restrict__ src, int32_t* __restrict__ edge_tgt, float* __restrict__ edge_dist) {
+    const int lane = threadIdx.x & 31;
+    const int y = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (y >= n_atoms) return;
+    const int g = (int)batch[y];
+    const int kept = scan_atom<MODE>(pos, y, graph_ptr[g], graph_ptr[g + 1], r2, limit, fma, (MODE == 1) ? (int64_t)rowptr[y] : 0,
+                                     capacity, src, edge_tgt, edge_dist, lane);
     if (MODE == 0 && lane == 0) deg[y] = kept;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cell list (north_star (1)) for LARGE graphs.  The index-order scan above visits every atom of a graph until 33 hits are
+// found -- optimal for molecules and pockets (<= ~600 atoms: <= 19 ballots per atom) -- but O(n) per atom.  Above
+// `cell_min_atoms` atoms per graph a uniform grid over the graph's bounding box (cell edge >= 1.001 r) restricts the
+// candidates to the 27 cells around the query.  Cells are NOT visited in index order, so the torch_cluster truncation
+// ("the first 33 hits in ascending atom index") is restored by an index-order select: all in-range candidates are
+// gathered, ranked by atom index, and the 33 smallest are kept -- the edge set and its order are bit-identical to the
+// scan's (same fp32 distance expression, same strict comparison).
+//   geossl_radius_cell_keys : per-graph bounding box -> key = graph << 30 | (cx << 20 | cy << 10 | cz) per atom
+//   (host layer: ONE stable sort of the keys -- atoms of a cell stay in ascending index)
+//   radius_cell_kernel      : warp per query atom; 27 binary searches (one per lane) find the cells' ranges in the sorted
+//                             keys; hits go to a per-warp shared-memory list; rank-by-counting selects the 33 smallest.
+// Graphs below the threshold, or atoms with more than kCellMaxHits hits, take the index-order scan inside the same kernel.
+constexpr int kCellDim = 1023;          // cells per dimension (10 bits each)
+constexpr int kCellMaxHits = 256;
+constexpr float kCellMargin = 1.001f;   // cell edge = margin * r: two atoms within r are always in adjacent cells, fp32 rounding included
+
+__global__ void __launch_bounds__(256)
+cell_bbox_kernel(const float* __restrict__ pos, const int32_t* __restrict__ graph_ptr, int n_graphs, float r, float* __restrict__ box) {
+    // one warp per graph: box[g] = {min x, min y, min z, cell edge x, y, z, (int) nx | ny << 10 | nz << 20, unused}
+    const int lane = threadIdx.x & 31;
+    const int g = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g >= n_graphs) return;
+    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = lo + lane; i < hi; i += 32)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float v = __ldg(pos + 3 * (int64_t)i + d);
+            mn[d] = fminf(mn[d], v);
+            mx[d] = fmaxf(mx[d], v);
+        }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if (lane == 0) {
+        int dims = 0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float ext = hi > lo ? fmaxf(mx[d] - mn[d], 0.f) : 0.f;
+            float h = kCellMargin * r;
+            if (ext / h >= (float)kCellDim) h = ext / (float)(kCellDim - 1);      // huge boxes: coarser cells (still >= margin * r)
+            const int n = min((int)(ext / h) + 1, kCellDim);
+            box[8 * g + d] = hi > lo ? mn[d] : 0.f;
+            box[8 * g + 3 + d] = h;
+            dims |= n << (10 * d);
+        }
+        box[8 * g + 6] = __int_as_float(dims);
+        box[8 * g + 7] = 0.f;
+    }
+}
+
+__device__ __forceinline__ void cell_of(const float* __restrict__ box, int g, float x, float y, float z, int (&c)[3], int (&n)[3]) {
+    const int dims = __float_as_int(box[8 * g + 6]);
+    const float p[3] = {x, y, z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        n[d] = (dims >> (10 * d)) & 1023;
+        const int v = (int)((p[d] - box[8 * g + d]) / box[8 * g + 3 + d]);
+        c[d] = min(max(v, 0), n[d] - 1);
+    }
+}
+__device__ __forceinline__ int64_t cell_key(int g, int cx, int cy, int cz) {
+    return ((int64_t)g << 30) | ((int64_t)cx << 20) | ((int64_t)cy << 10) | (int64_t)cz;
+}
+
+__global__ void __launch_bounds__(256)
+cell_key_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, int n_atoms, const float* __restrict__ box,
+                int64_t* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    const int g = (int)batch[i];
+    int c[3], n[3];
+    cell_of(box, g, pos[3 * (int64_t)i], pos[3 * (int64_t)i + 1], pos[3 * (int64_t)i + 2], c, n);
+    keys[i] = cell_key(g, c[0], c[1], c[2]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+radius_cell_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, const int32_t* __restrict__ graph_ptr,
+                   int n_atoms, float r2, int limit, int fma, int cell_min_atoms, const float* __restrict__ box,
+                   const int64_t* __restrict__ sorted_keys, const int64_t* __restrict__ sorted_atoms,
+                   int32_t* __restrict__ deg, const int32_t* __restrict__ rowptr, int64_t capacity,
+                   int32_t* __restrict__ src, int32_t* __restrict__ edge_tgt, float* __restrict__ edge_dist) {
+    __shared__ int s_idx[8][kCellMaxHits];
+    __shared__ float s_d2[8][kCellMaxHits];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int y = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (y >= n_atoms) return;
+    const int g = (int)batch[y];
+    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    const int64_t base = (MODE == 1) ? (int64_t)rowptr[y] : 0;
+    bool scan = hi - lo < cell_min_atoms;
+    int n_hits = 0;
+    const float yx = __ldg(pos + 3 * (int64_t)y), yy = __ldg(pos + 3 * (int64_t)y + 1), yz = __ldg(pos + 3 * (int64_t)y + 2);
+    if (!scan) {
+        // ---- ranges of the 27 neighbour cells: lane l < 27 searches cell (dx,dy,dz) = (l/9-1, l/3%3-1, l%3-1)
+        int c[3], n[3];
+        cell_of(box, g, yx, yy, yz, c, n);
+        int start = 0, count = 0;
+        if (lane < 27) {
+            const int cx = c[0] + lane / 9 - 1, cy = c[1] + (lane / 3) % 3 - 1, cz = c[2] + lane % 3 - 1;
+            if (cx >= 0 && cy >= 0 && cz >= 0 && cx < n[0] && cy < n[1] && cz < n[2]) {
+                const int64_t key = cell_key(g, cx, cy, cz);
+                int a = 0, b = n_atoms;                         // lower_bound(key)
+                while (a < b) { const int m = (a + b) >> 1; if (__ldg(sorted_keys + m) < key) a = m + 1; else b = m; }
+                start = a;
+                b = n_atoms;                                    // upper_bound(key)
+                while (a < b) { const int m = (a + b) >> 1; if (__ldg(sorted_keys + m) <= key) a = m + 1; else b = m; }
+                count = a - start;
+            }
+        }
+        // ---- gather every in-range candidate (any order) into the warp's list
+        for (int cell = 0; cell < 27 && !scan; ++cell) {
+            const int cs = __shfl_sync(0xffffffffu, start, cell), cc = __shfl_sync(0xffffffffu, count, cell);
+            for (int k0 = 0; k0 < cc; k0 += 32) {
+                const int k = k0 + lane;
+                int a = -1;
+                float d2 = 0.f;
+                bool in = false;
+                if (k < cc) {
+                    a = (int)__ldg(sorted_atoms + cs + k);
+                    d2 = dist2_rn(__ldg(pos + 3 * (int64_t)a), __ldg(pos + 3 * (int64_t)a + 1), __ldg(pos + 3 * (int64_t)a + 2), yx, yy, yz, fma);
+                    in = d2 < r2;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, in);
+                const int cnt = __popc(mask);
+                if (n_hits + cnt > kCellMaxHits) { scan = true; break; }      // (warp-uniform) too dense for the list: index scan
+                if (in) {
+                    const int p = n_hits + __popc(mask & ((1u << lane) - 1u));
+                    s_idx[w][p] = a;
+                    s_d2[w][p] = d2;
+                }
+                n_hits += cnt;
+            }
+        }
+        __syncwarp();
+    }
+    if (scan) {
+        const int kept = scan_atom<MODE>(pos, y, lo, hi, r2, limit, fma, base, capacity, src, edge_tgt, edge_dist, lane);
+        if (MODE == 0 && lane == 0) deg[y] = kept;
+        return;
+    }
+    // ---- index-order select: rank every hit by atom index; keep ranks < limit; self (always a hit) is dropped
+    int self_rank = 0;
+    for (int j = lane; j < n_hits; j += 32) self_rank += (s_idx[w][j] < y) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) self_rank += __shfl_xor_sync(0xffffffffu, self_rank, o);
+    const int kept_total = min(n_hits, limit) - (self_rank < limit ? 1 : 0);
+    if (MODE == 0) {
+        if (lane == 0) deg[y] = kept_total;
+        return;
+    }
+    for (int i0 = 0; i0 < n_hits; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < n_hits) {
+            const int a = s_idx[w][i];
+            int rank = 0;
+            for (int j = 0; j < n_hits; ++j) rank += (s_idx[w][j] < a) ? 1 : 0;
+            if (rank < limit && a != y) {
+                const int64_t e = base + rank - (self_rank < rank ? 1 : 0);
+                if (e < capacity) {
+                    src[e] = a;
+                    edge_tgt[e] = y;
+                    if (edge_dist) edge_dist[e] = sqrtf(s_d2[w][i]);
+                }
+            }
+        }
+    }
 }
 
 // Exclusive scan of deg[0..n) into out[0..n]; single CTA, 1024 threads, chunked with a running carry.
@@ -314,9 +500,24 @@ int geossl_rowptr_from_sorted(const int64_t* keys, int64_t n_keys, int64_t n_row
     return geossl_graph_ptr(keys, n_keys, n_rows, rowptr, stream);
 }
 
+int geossl_radius_cell_keys(const float* pos, const int64_t* batch, const int32_t* graph_ptr, int64_t n_atoms, int64_t n_graphs,
+                            float r, float* box, int64_t* keys, void* stream) {
+    if (n_atoms == 0 || n_graphs == 0) return 0;
+    GEOSSL_REQUIRE(pos && batch && graph_ptr && box && keys && r > 0.f, "null pointer / bad radius");
+    GEOSSL_REQUIRE(n_graphs < (1ll << 32), "too many graphs for the 64-bit cell key");
+    cudaStream_t st = as_stream(stream);
+    cell_bbox_kernel<<<(unsigned)((n_graphs * 32 + 255) / 256), 256, 0, st>>>(pos, graph_ptr, (int)n_graphs, r, box);
+    GEOSSL_LAUNCH_CHECK();
+    cell_key_kernel<<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(pos, batch, (int)n_atoms, box, keys);
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
 int geossl_radius_csr(const float* pos, const int64_t* batch, const int32_t* graph_ptr, int64_t n_atoms,
                       float r, int max_num_neighbors, int64_t capacity, int32_t* scratch,
-                      int32_t* rowptr, int32_t* src, int32_t* edge_tgt, float* edge_dist, void* stream) {
+                      int32_t* rowptr, int32_t* src, int32_t* edge_tgt, float* edge_dist, int flags,
+                      const float* cell_box, const int64_t* sorted_keys, const int64_t* sorted_atoms, int cell_min_atoms,
+                      void* stream) {
     GEOSSL_REQUIRE(rowptr && scratch, "null rowptr/scratch");
     GEOSSL_REQUIRE(n_atoms >= 0 && n_atoms < (1ll << 26), "n_atoms out of range");
     GEOSSL_REQUIRE(max_num_neighbors >= 1, "max_num_neighbors must be >= 1");
@@ -331,12 +532,25 @@ int geossl_radius_csr(const float* pos, const int64_t* batch, const int32_t* gra
     const int threads = 256;
     const int blocks = (int)((n_atoms * 32 + threads - 1) / threads);
     int32_t* deg = scratch;
-    radius_scan_kernel<0><<<blocks, threads, 0, st>>>(pos, batch, graph_ptr, (int)n_atoms, r2, limit, deg, nullptr, 0,
+    const int fma = (flags & GEOSSL_RADIUS_FMA) ? 1 : 0;
+    if (cell_box != nullptr) {
+        GEOSSL_REQUIRE(sorted_keys && sorted_atoms, "cell list: sorted keys / atoms missing");
+        radius_cell_kernel<0><<<blocks, threads, 0, st>>>(pos, batch, graph_ptr, (int)n_atoms, r2, limit, fma, cell_min_atoms, cell_box,
+                                                          sorted_keys, sorted_atoms, deg, nullptr, 0, nullptr, nullptr, nullptr);
+        GEOSSL_LAUNCH_CHECK();
+        exclusive_scan_kernel<<<1, 1024, 0, st>>>(deg, (int)n_atoms, rowptr);
+        GEOSSL_LAUNCH_CHECK();
+        radius_cell_kernel<1><<<blocks, threads, 0, st>>>(pos, batch, graph_ptr, (int)n_atoms, r2, limit, fma, cell_min_atoms, cell_box,
+                                                          sorted_keys, sorted_atoms, nullptr, rowptr, capacity, src, edge_tgt, edge_dist);
+        GEOSSL_LAUNCH_CHECK();
+        return 0;
+    }
+    radius_scan_kernel<0><<<blocks, threads, 0, st>>>(pos, batch, graph_ptr, (int)n_atoms, r2, limit, fma, deg, nullptr, 0,
                                                       nullptr, nullptr, nullptr);
     GEOSSL_LAUNCH_CHECK();
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(deg, (int)n_atoms, rowptr);
     GEOSSL_LAUNCH_CHECK();
-    radius_scan_kernel<1><<<blocks, threads, 0, st>>>(pos, batch, graph_ptr, (int)n_atoms, r2, limit, nullptr, rowptr,
+    radius_scan_kernel<1><<<blocks, threads, 0, st>>>(pos, batch, graph_ptr, (int)n_atoms, r2, limit, fma, nullptr, rowptr,
                                                       capacity, src, edge_tgt, edge_dist);
     GEOSSL_LAUNCH_CHECK();
     return 0;

@@ -4,7 +4,9 @@ Everything here is plumbing -- allocation through torch's caching allocator, the
 and ``torch.autograd.Function`` wrappers that pair each forward kernel with its backward kernel.  No
 numerics happen in Python and there is no CPU path: a non-CUDA tensor raises.
 """
+import contextlib
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -13,6 +15,7 @@ from . import _lib
 from ._lib import DdmPtrs, check
 
 MAX_NEIGHBORS_DEFAULT = 32      # torch_cluster.radius_graph default, never overridden (schnet.py:91)
+CFCONV_PERSISTENT = True        # cfconv aggregate (F = 128): persistent grid with dynamic row hand-out (False: one warp per row)
 
 
 class _KernelTimers:
@@ -64,10 +67,32 @@ class _KernelTimers:
 KERNEL_TIMERS = _KernelTimers()
 
 
+# NVTX ranges (the reference has no tracing at all): GEOSSL_NVTX=1 (or ops.NVTX = True) brackets every
+# named C-ABI call and the phases of the training step (pretrain.train_step) with torch.cuda.nvtx ranges, which Nsight
+# Systems / Compute show next to the kernels.  Off by default: one flag test per call.
+NVTX = os.environ.get("GEOSSL_NVTX", "0") not in ("", "0")
+
+
+@contextlib.contextmanager
+def nvtx_range(name):
+    if not NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
+
+
 def _timed(name, rc_fn):
     """Run ``rc_fn()`` (a C-ABI call returning rc) between two events if ``name`` is being timed."""
     end = KERNEL_TIMERS.start(name) if KERNEL_TIMERS.names else None
+    if NVTX:
+        torch.cuda.nvtx.range_push("geossl/" + name)
     rc = rc_fn()
+    if NVTX:
+        torch.cuda.nvtx.range_pop()
     if end is not None:
         end.record()
     check(rc, name)
@@ -112,6 +137,16 @@ class RadiusCSR:
         self.pair_rowptr = self.pair_of_edge = self.pair_e1 = self.pair_e2 = self.pair_atoms = self.pair_dist = None
         self._n_edges = None
         self._exact = None
+        self._sched = None
+
+    # Scheduler counters of the persistent cfconv kernels (two for the forward, two for the adjoint), zeroed once here;
+    # the kernels leave them at zero.  CFCONV_PERSISTENT = False falls back to the one-warp-per-row grid.
+    def sched(self, which):
+        if not CFCONV_PERSISTENT:
+            return None
+        if self._sched is None:
+            self._sched = torch.zeros(4, dtype=torch.int32, device=self.rowptr.device)
+        return ctypes.c_void_p(self._sched.data_ptr() + 8 * which)
 
     @property
     def n_edges_dev(self):
@@ -202,9 +237,19 @@ def super_edges(graph_ptr, pair_ptr, n_graphs, n_atoms, n_pairs, permutation=Fal
     return sei, batch
 
 
+# Distance rounding of the neighbour search: False = ((dx*dx)+dy*dy)+dz*dz rounded per operation (the survey's reading of the
+# torch_cluster kernel), True = the FMA-contracted form nvcc's default -fmad=true would emit for it.  The third-party
+# binary the reference ran is not available, so this stays a documented switch (tests enumerate where the two differ).
+RADIUS_FMA = False
+# Mean atoms per graph from which the neighbour search builds a spatial cell list (bit-identical output; the index-order
+# scan is faster for molecules and ~600-atom pockets).  None disables the cell list.
+CELL_LIST_MIN_ATOMS = 2048
+
+
 def radius_csr(pos, batch, r, max_num_neighbors=MAX_NEIGHBORS_DEFAULT, *, graph_ptr=None, num_graphs=None,
-               capacity=None, transpose=True):
-    """Neighbour search -> RadiusCSR (torch_cluster.radius_graph semantics, see include/geossl_b200.h)."""
+               capacity=None, transpose=True, cell_list=None):
+    """Neighbour search -> RadiusCSR (torch_cluster.radius_graph semantics, see include/geossl_b200.h).
+    ``cell_list``: None = automatic (graphs of at least CELL_LIST_MIN_ATOMS atoms on average), True / False force it."""
     pos = _req(pos.detach(), torch.float32, "pos", 2)
     if pos.size(1) != 3:
         raise RuntimeError("geossl_b200: `pos` must be (N,3)")
@@ -224,9 +269,22 @@ def radius_csr(pos, batch, r, max_num_neighbors=MAX_NEIGHBORS_DEFAULT, *, graph_
     tgt = torch.empty(capacity, dtype=torch.int32, device=dev)
     dist = torch.empty(capacity, dtype=torch.float32, device=dev)
     scratch = torch.empty(2 * n + 2, dtype=torch.int32, device=dev)
-    check(_lib.load().geossl_radius_csr(_p(pos), _p(batch), _p(graph_ptr), n, float(r), int(max_num_neighbors),
-                                        capacity, _p(scratch), _p(rowptr), _p(src), _p(tgt), _p(dist), _stream()),
-          "radius_csr")
+    n_graphs = graph_ptr.numel() - 1
+    if cell_list is None:
+        cell_list = CELL_LIST_MIN_ATOMS is not None and n_graphs > 0 and n >= CELL_LIST_MIN_ATOMS * n_graphs
+    box = keys = order = None
+    min_atoms = 0
+    lib = _lib.load()
+    if cell_list and n > 0 and n_graphs > 0:
+        box = torch.empty((n_graphs, 8), dtype=torch.float32, device=dev)
+        keys = torch.empty(n, dtype=torch.int64, device=dev)
+        check(lib.geossl_radius_cell_keys(_p(pos), _p(batch), _p(graph_ptr), n, n_graphs, float(r), _p(box), _p(keys), _stream()),
+              "radius_cell_keys")
+        keys, order = torch.sort(keys, stable=True)          # library radix sort: atoms of one cell stay in ascending index
+        min_atoms = 0 if cell_list is True else int(CELL_LIST_MIN_ATOMS or 0)
+    _timed("radius_csr", lambda: lib.geossl_radius_csr(
+        _p(pos), _p(batch), _p(graph_ptr), n, float(r), int(max_num_neighbors), capacity, _p(scratch), _p(rowptr), _p(src),
+        _p(tgt), _p(dist), 1 if RADIUS_FMA else 0, _p(box), _p(keys), _p(order), min_atoms, _stream()))
     g = RadiusCSR(n, capacity, rowptr, src, tgt, dist, batch, graph_ptr)
     if transpose:
         g.ensure_transpose()
@@ -263,7 +321,7 @@ def csr_from_edge_index(edge_index, n_atoms, batch, graph_ptr=None, num_graphs=N
 def _cfconv_fwd(x, filt, g, filt_row=None):
     out = torch.empty((g.n_atoms, x.size(1)), dtype=torch.float32, device=x.device)
     _timed("cfconv_fwd", lambda: _lib.load().geossl_cfconv_fwd(_p(x), _p(filt), _p(filt_row), _p(g.rowptr), _p(g.src), g.n_atoms,
-                                                               x.size(1), _p(out), _stream()))
+                                                               x.size(1), _p(out), g.sched(0), _stream()))
     return out
 
 
@@ -272,7 +330,7 @@ def _cfconv_bwd_x(filt, grad_out, g, filt_row=None):
     dx = torch.empty((g.n_atoms, grad_out.size(1)), dtype=torch.float32, device=grad_out.device)
     _timed("cfconv_bwd_x", lambda: _lib.load().geossl_cfconv_bwd_x(_p(filt), _p(filt_row), _p(grad_out), _p(g.t_rowptr),
                                                                    _p(g.t_eid), _p(g.t_tgt), g.n_atoms, grad_out.size(1), _p(dx),
-                                                                   _stream()))
+                                                                   g.sched(1), _stream()))
     return dx
 
 

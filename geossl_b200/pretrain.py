@@ -258,14 +258,17 @@ def train_step(args, batch, model, heads, optimizer, mu=0.0, sigma=0.3, grad_syn
                draws=None, positions_02=None):
     """One iteration of train() (pretrain_GeoSSL.py:234-260) without its per-step ``.item()`` host sync:
     returns the loss tensor (still on the device)."""
-    loss, _ = do_DDM(args, batch, model, None, mu, sigma, heads=heads, device_noise=device_noise, draws=draws,
-                     positions_02=positions_02)
+    with ops.nvtx_range("ddm/forward"):
+        loss, _ = do_DDM(args, batch, model, None, mu, sigma, heads=heads, device_noise=device_noise, draws=draws,
+                         positions_02=positions_02)
     optimizer.zero_grad(set_to_none=True)
-    with ops.side_stream_wgrads():          # small weight-gradient kernels overlap the backward chain; joined on exit
+    with ops.nvtx_range("ddm/backward"), ops.side_stream_wgrads():   # small weight-gradient kernels overlap the backward chain
         loss.backward()
     if grad_sync is not None:
-        grad_sync()
-    optimizer.step()
+        with ops.nvtx_range("ddm/allreduce"):
+            grad_sync()
+    with ops.nvtx_range("ddm/adam"):
+        optimizer.step()
     return loss.detach()
 
 

@@ -49,10 +49,24 @@ int geossl_graph_ptr(const int64_t* batch, int64_t n_atoms, int64_t n_graphs, in
  *   rowptr (n_atoms+1) int32, rowptr[n_atoms] = E;  src (capacity) int32 ascending within a row;
  *   edge_tgt (capacity) int32 = row of each edge;  edge_dist (capacity) fp32 = ||pos[src]-pos[tgt]||
  *   (schnet.py:92-93), may be NULL.  capacity >= E is required; (max_num_neighbors+1)*n_atoms always
- *   suffices.  scratch: (2*n_atoms + 2) int32. */
+ *   suffices.  scratch: (2*n_atoms + 2) int32.
+ * flags: GEOSSL_RADIUS_FMA evaluates the distance as fma(dz,dz, fma(dy,dy, dx*dx)) -- what `dist += (x-y)*(x-y)` becomes
+ *   under the compiler's default FMA contraction; torch_cluster is an un-vendored, unpinned dependency of the reference,
+ *   so which rounding its binary used cannot be checked here: both are provided, the default is the uncontracted form
+ *   (SURVEY.md Appendix B.1).  The two differ only when dist is within an ulp of r*r.
+ * Cell list (optional, for graphs of >= cell_min_atoms atoms): cell_box / sorted_keys / sorted_atoms from
+ *   geossl_radius_cell_keys + ONE stable ascending sort of the keys (sorted_atoms = the sort's permutation).  NULL
+ *   cell_box => every graph takes the index-order scan.  The output is bit-identical either way. */
+#define GEOSSL_RADIUS_FMA 1
 int geossl_radius_csr(const float* pos, const int64_t* batch, const int32_t* graph_ptr, int64_t n_atoms,
                       float r, int max_num_neighbors, int64_t capacity, int32_t* scratch,
-                      int32_t* rowptr, int32_t* src, int32_t* edge_tgt, float* edge_dist, void* stream);
+                      int32_t* rowptr, int32_t* src, int32_t* edge_tgt, float* edge_dist, int flags,
+                      const float* cell_box, const int64_t* sorted_keys, const int64_t* sorted_atoms, int cell_min_atoms,
+                      void* stream);
+/* Per-graph bounding box -> uniform grid with cell edge 1.001 r (coarser if a box would need more than 1023 cells per
+ * dimension): box (n_graphs,8) fp32 scratch, keys (n_atoms) int64 = graph << 30 | cx << 20 | cy << 10 | cz. */
+int geossl_radius_cell_keys(const float* pos, const int64_t* batch, const int32_t* graph_ptr, int64_t n_atoms, int64_t n_graphs,
+                            float r, float* box, int64_t* keys, void* stream);
 
 /* (2,E) int64 `edge_index` = [source; target] exactly as radius_graph returns it (host already knows E). */
 int geossl_csr_to_edge_index(const int32_t* src, const int32_t* edge_tgt, int64_t n_edges,
@@ -131,13 +145,17 @@ int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K
 
 /* m_i = sum_{e in row i} x[src_e] * W_row(e)   (atomic-free segmented reduction, one warp per row).
  * filt_row: NULL => row(e) = e (one filter row per directed edge); else row(e) = filt_row[e] (the pair_of_edge map of
- * geossl_pair_index: both directions of an undirected pair read ONE shared filter row). */
+ * geossl_pair_index: both directions of an undirected pair read ONE shared filter row).
+ * sched: NULL, or two int32 counters in device memory, ZERO before the first launch: the F = 128 kernel then runs as a
+ * persistent grid (3 CTAs per SM) that hands rows out dynamically -- no wave tail, the next row's indices are prefetched;
+ * the kernel leaves the counters at zero again (safe to reuse launch after launch on one stream). */
 int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src,
-                      int64_t n_atoms, int F, float* out, void* stream);
+                      int64_t n_atoms, int F, float* out, int32_t* sched, void* stream);
 
-/* dx_j = sum_{e: src_e = j} W_e * g[tgt_e]   over the source-sorted view. */
+/* dx_j = sum_{e: src_e = j} W_e * g[tgt_e]   over the source-sorted view (sched as above, its own two counters). */
 int geossl_cfconv_bwd_x(const float* filt, const int32_t* filt_row, const float* grad_out, const int32_t* t_rowptr,
-                        const int32_t* t_eid, const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream);
+                        const int32_t* t_eid, const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, int32_t* sched,
+                        void* stream);
 
 /* dW_e = x[src_e] * g[tgt_e]  materialised (E,F)  (second-order path and the unfused comparison). */
 int geossl_cfconv_bwd_w(const float* x, const float* grad_out, const int32_t* rowptr, const int32_t* src,

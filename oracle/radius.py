@@ -27,7 +27,21 @@ def _graph_ptr(batch_np, num_graphs=None):
     return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
 
 
-def radius_neighbors(pos, r, batch=None, max_num_neighbors=32):
+def dist2(d, fma=False):
+    """Squared length of the fp32 difference vectors ``d`` (...,3).  Default: ((dx*dx) + dy*dy) + dz*dz, one fp32 rounding
+    per operation.  ``fma=True``: fma(dz, dz, fma(dy, dy, dx*dx)) -- what `dist += (x-y)*(x-y)` becomes when the compiler
+    contracts it (nvcc -fmad=true).  The fused steps are emulated in float64 (a 24 x 24-bit product is exact there; the
+    following addition can, very rarely, round twice -- acceptable for test data, noted here)."""
+    if not fma:
+        sq = d * d
+        return (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+    d64 = d.astype(np.float64)
+    t = (d[..., 0] * d[..., 0]).astype(np.float32)                              # dx*dx rounded to fp32
+    t = (d64[..., 1] * d64[..., 1] + t.astype(np.float64)).astype(np.float32)   # fma(dy, dy, t)
+    return (d64[..., 2] * d64[..., 2] + t.astype(np.float64)).astype(np.float32)
+
+
+def radius_neighbors(pos, r, batch=None, max_num_neighbors=32, fma=False):
     """Returns (rowptr int64 (N+1,), src int64 (E,)) -- the destination-sorted CSR."""
     p = np.ascontiguousarray(pos.detach().cpu().numpy() if torch.is_tensor(pos) else pos, dtype=np.float32)
     n_atoms = p.shape[0]
@@ -46,8 +60,7 @@ def radius_neighbors(pos, r, batch=None, max_num_neighbors=32):
             continue
         x = p[lo:hi]                                   # candidates (ascending index)
         d = x[None, :, :] - x[:, None, :]              # d[y, x] = pos[x] - pos[y]
-        sq = d * d                                     # fp32, one rounding per product
-        dist = (sq[..., 0] + sq[..., 1]) + sq[..., 2]  # fp32, sequential adds
+        dist = dist2(d, fma)                           # fp32, see dist2
         hit = dist < r2
         rank = np.cumsum(hit, axis=1)                  # 1-based rank among hits
         keep = hit & (rank <= limit)
@@ -61,10 +74,10 @@ def radius_neighbors(pos, r, batch=None, max_num_neighbors=32):
     return rowptr, src
 
 
-def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32, flow="source_to_target"):
+def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32, flow="source_to_target", fma=False):
     """Same signature as ``torch_geometric.nn.radius_graph``; (2,E) int64 ``[source; target]``."""
     assert not loop and flow == "source_to_target"
-    rowptr, src = radius_neighbors(x, r, batch, max_num_neighbors)
+    rowptr, src = radius_neighbors(x, r, batch, max_num_neighbors, fma)
     deg = np.diff(rowptr)
     tgt = np.repeat(np.arange(deg.size, dtype=np.int64), deg)
     ei = torch.from_numpy(np.stack([src, tgt]).astype(np.int64))

@@ -1,0 +1,55 @@
+"""A/B of the cfconv aggregate kernels alone, on the bench workload's graph (two stacked views of 256 x 30 atoms):
+persistent grid (dynamic row hand-out) vs one warp per row, with one filter row per atom pair (shared) and per edge.
+Back-to-back launches cycle over 4 filter tensors (4 x 112/225 MB > L2), CUDA events, mean of 40 launches.
+
+    python profiles/bench_cfconv.py > profiles/rNN_vK_cfconv_ab.txt
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from geossl_b200 import ops  # noqa: E402
+from geossl_b200.data import synthetic_batch  # noqa: E402
+
+dev = "cuda:0"
+b = synthetic_batch(256, 30, seed=0).to(dev)
+pos = torch.cat([b.positions, b.positions + 0.3 * torch.randn_like(b.positions)])
+g = ops.radius_csr(pos, torch.cat([b.batch, b.batch + 256]), 10.0, num_graphs=512)
+g.ensure_pairs()
+n, e, u = g.n_atoms, g.num_edges, int(g.n_pairs_dev.item())
+print(f"atoms {n}, edges {e}, pairs {u}")
+x = torch.randn(n, 128, device=dev)
+filts = [torch.randn(g.capacity, 128, device=dev) for _ in range(4)]
+
+
+def run(fn, reps=40):
+    for i in range(4):
+        fn(filts[i % 4])
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(reps):
+        fn(filts[i % 4])
+    t1.record()
+    torch.cuda.synchronize()
+    return 1e3 * t0.elapsed_time(t1) / reps
+
+
+ref = {}
+for persistent in (False, True):
+    ops.CFCONV_PERSISTENT = persistent
+    g._sched = None
+    for shared in (True, False):
+        fr = g.pair_of_edge if shared else None
+        rows = u if shared else e
+        fwd = run(lambda f: ops._cfconv_fwd(x, f, g, fr))
+        bwd = run(lambda f: ops._cfconv_bwd_x(f, x, g, fr))
+        byt = 4 * 128 * rows + 2 * 4 * 128 * n + 4 * e * (2 if shared else 1) + 4 * (n + 1)
+        out = (ops._cfconv_fwd(x, filts[0], g, fr), ops._cfconv_bwd_x(filts[0], x, g, fr))
+        key = shared
+        if key in ref:
+            assert torch.equal(out[0], ref[key][0]) and torch.equal(out[1], ref[key][1]), "editions must agree bit for bit"
+        ref[key] = out
+        print(f"persistent={int(persistent)} shared={int(shared)}: fwd {fwd:6.1f} us ({byt / fwd / 1e3:6.0f} GB/s algorithmic), bwd_x {bwd:6.1f} us")

@@ -49,3 +49,23 @@ def test_no_cpu_fallback():
         m(torch.zeros(6, dtype=torch.long), pos, torch.zeros(6, dtype=torch.long))
     with pytest.raises(AssertionError):                              # schnet.py:86
         m(torch.zeros(6, dtype=torch.int32), pos)
+
+
+def test_torch_ops_are_registered_and_cuda_only():
+    """``torch.ops.geossl_b200.*`` (geossl_b200/torch_ops.py): every op has a schema, and a CPU tensor is refused by the
+    dispatcher -- there is no CPU kernel to fall back to."""
+    from geossl_b200 import torch_ops
+    for name in torch_ops.OP_NAMES:
+        assert hasattr(torch.ops.geossl_b200, name), name
+    with pytest.raises(NotImplementedError, match="CPU"):
+        torch.ops.geossl_b200.pair_distance(torch.zeros(3, 3), torch.zeros((2, 1), dtype=torch.long))
+    with pytest.raises(NotImplementedError, match="CPU"):
+        torch.ops.geossl_b200.cfconv(torch.zeros(2, 128), torch.zeros(1, 128), torch.zeros(3, dtype=torch.int32),
+                                     torch.zeros(1, dtype=torch.int32))
+
+
+def test_nvtx_switch_is_off_by_default_and_harmless():
+    from geossl_b200 import ops
+    assert ops.NVTX is False or os.environ.get("GEOSSL_NVTX")
+    with ops.nvtx_range("noop"):
+        pass

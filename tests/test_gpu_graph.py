@@ -182,3 +182,71 @@ def test_pair_index_matches_oracle(ng, lo, hi, density, owner_small, monkeypatch
         assert torch.equal(g.dist[:e][rev[has]], g.pair_dist[:u][has])          # both directions: the same length, bitwise
     if hi >= 40:
         assert (e2 < 0).any() and u > e // 2                                     # truncation produced orphans
+
+
+def _same_csr(a, b):
+    e = a.num_edges
+    assert b.num_edges == e
+    assert torch.equal(a.rowptr, b.rowptr) and torch.equal(a.src[:e], b.src[:e]) and torch.equal(a.tgt[:e], b.tgt[:e])
+    assert torch.equal(a.dist[:e], b.dist[:e])                       # same fp32 expression -> same bits
+
+
+@pytest.mark.parametrize("seed,ng,lo,hi,r,density", [
+    (0, 7, 1, 9, 10.0, 0.05), (1, 16, 10, 60, 10.0, 0.05), (2, 5, 40, 90, 10.0, 0.08), (3, 6, 25, 70, 3.0, 0.05),
+    (4, 3, 200, 600, 6.0, 0.05), (7, 2, 560, 640, 10.0, 0.05), (8, 2, 3000, 5000, 5.0, 0.05), (9, 1, 900, 900, 2.5, 0.4)])
+def test_cell_list_is_bit_identical_to_the_index_order_scan(seed, ng, lo, hi, r, density):
+    """The spatial cell list (27 cells around the query, index-order select of the 33 smallest in-range atoms) against the
+    index-order scan and the CPU oracle: same rowptr / sources / distances, including rows that truncate at 32/33
+    neighbours (dense 600-atom pockets at 10 A), rows too dense for the per-warp hit list (density 0.4: scan fall-back),
+    tiny graphs, and 5000-atom graphs."""
+    b = synthetic_batch(ng, lo, hi, seed=seed, density=density, with_pairs=False)
+    pos, bt = b.positions.to(DEV), b.batch.to(DEV)
+    g_scan = ops.radius_csr(pos, bt, r, num_graphs=ng, cell_list=False)
+    g_cell = ops.radius_csr(pos, bt, r, num_graphs=ng, cell_list=True)
+    _same_csr(g_scan, g_cell)
+    if b.positions.size(0) <= 2500:
+        rowptr, src = radius_neighbors(b.positions, r, b.batch)
+        e = int(rowptr[-1])
+        assert g_cell.num_edges == e and np.array_equal(g_cell.src[:e].cpu().numpy(), src.astype(np.int32))
+
+
+def test_cell_list_automatic_threshold_mixes_paths_in_one_batch():
+    old = ops.CELL_LIST_MIN_ATOMS
+    try:
+        ops.CELL_LIST_MIN_ATOMS = 300
+        b = synthetic_batch(6, 100, 900, seed=21, with_pairs=False)        # graphs on both sides of the threshold
+        pos, bt = b.positions.to(DEV), b.batch.to(DEV)
+        _same_csr(ops.radius_csr(pos, bt, 6.0, num_graphs=6, cell_list=False), ops.radius_csr(pos, bt, 6.0, num_graphs=6))
+    finally:
+        ops.CELL_LIST_MIN_ATOMS = old
+
+
+def test_fma_contracted_distance_switch():
+    """torch_cluster's binary is not available, so both roundings of `dist += (x-y)*(x-y)` are built: per-operation rounding
+    (default) and FMA contraction (ops.RADIUS_FMA).  Enumerate atom pairs whose squared distance sits within an ulp of
+    r*r: the two variants must disagree on some of them, and each must agree with the oracle evaluated the same way."""
+    from oracle.radius import dist2
+    rng = np.random.default_rng(0)
+    r = np.float32(5.0)
+    n_pairs = 60000
+    a = (rng.random((n_pairs, 3)) * 20).astype(np.float32)
+    u = rng.normal(size=(n_pairs, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    bpts = (a.astype(np.float64) + u * float(r) * (1 + rng.uniform(-2e-7, 2e-7, size=(n_pairs, 1)))).astype(np.float32)
+    d = bpts - a
+    in_rn, in_fma = dist2(d, False) < r * r, dist2(d, True) < r * r
+    differ = np.nonzero(in_rn != in_fma)[0]
+    assert differ.size > 10, "the enumeration must reach pairs where the two roundings decide differently"
+    sel = np.concatenate([differ, np.arange(200)])
+    pos = torch.from_numpy(np.stack([a[sel], bpts[sel]], axis=1).reshape(-1, 3))       # graph k = the two atoms of pair k
+    batch = torch.arange(sel.size).repeat_interleave(2)
+    old = ops.RADIUS_FMA
+    try:
+        for fma, expect in ((False, in_rn[sel]), (True, in_fma[sel])):
+            ops.RADIUS_FMA = fma
+            g = ops.radius_csr(pos.to(DEV), batch.to(DEV), float(r), num_graphs=sel.size, transpose=False)
+            deg = (g.rowptr[1:] - g.rowptr[:-1]).cpu().numpy().reshape(-1, 2)
+            assert np.array_equal(deg[:, 0] == 1, expect) and np.array_equal(deg[:, 1] == 1, expect)
+            assert torch.equal(g.edge_index.cpu(), oracle_radius_graph(pos, float(r), batch, fma=fma))
+    finally:
+        ops.RADIUS_FMA = old

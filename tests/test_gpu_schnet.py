@@ -251,3 +251,26 @@ def test_graphed_finetune_step_pads_pockets_of_different_size():
         with torch.no_grad():
             ref = lba_loss(targs, b, m, lin, crit)
         assert rel_err(step(b), ref) <= 1e-6
+
+
+def test_torch_custom_ops_match_the_autograd_layer():
+    """torch.ops.geossl_b200.{radius_csr, cfconv, cfconv_transpose, linear128, pair_distance} call the same C-ABI entry points
+    as geossl_b200.ops: identical results."""
+    from geossl_b200 import torch_ops  # noqa: F401
+    b = synthetic_batch(5, 20, 40, seed=4)
+    pos, bt = b.positions.to(DEV), b.batch.to(DEV)
+    g = ops.radius_csr(pos, bt, 10.0, num_graphs=5)
+    rowptr, src, tgt, dist = torch.ops.geossl_b200.radius_csr(pos, bt, 10.0, 32, 5)
+    e = g.num_edges
+    assert torch.equal(rowptr, g.rowptr) and torch.equal(src[:e], g.src[:e]) and torch.equal(dist[:e], g.dist[:e])
+    assert torch.equal(torch.ops.geossl_b200.radius_graph(pos, bt, 10.0, 32), g.edge_index)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(pos.size(0), 128, device=DEV, generator=gen)
+    filt = torch.randn(g.capacity, 128, device=DEV, generator=gen)
+    assert torch.equal(torch.ops.geossl_b200.cfconv(x, filt, g.rowptr, g.src), ops.CFConvAggregate.apply(x, filt, g))
+    assert torch.equal(torch.ops.geossl_b200.cfconv_transpose(filt, x, g.t_rowptr, g.t_eid, g.t_tgt),
+                       ops.CFConvAggregateT.apply(filt, x, g))
+    lin = torch.nn.Linear(128, 128).to(DEV)
+    y = torch.ops.geossl_b200.linear128(x, lin.weight, lin.bias, True, x)
+    assert rel_err(y, x + F.linear(F.softplus(x) - 0.6931471824645996, lin.weight, lin.bias)) <= 1e-5
+    assert torch.equal(torch.ops.geossl_b200.pair_distance(pos, b.super_edge_index.to(DEV)), ops.pair_distance(pos, b.super_edge_index.to(DEV)))
