@@ -892,10 +892,10 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
             tmem_ld16(tD1 + lane_base + col0, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float z = fmaxf(fmaf(sEmb[col0 + j], wl, v[j]) + b0n, 0.f);
-                if (z > 0.f) mask1 |= 1u << j;
-                store_split1<FP16>(smem + L::Z1 + (Ln >> 6) * kHBlkT, smem + L::Z1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0 + j, Ln & 63, z);
+                v[j] = fmaxf(fmaf(sEmb[col0 + j], wl, v[j]) + b0n, 0.f);
+                if (v[j] > 0.f) mask1 |= 1u << j;
             }
+            store_split16_paired<FP16>(smem + L::Z1 + (Ln >> 6) * kHBlkT, smem + L::Z1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0, Ln & 63, v, lane);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -945,15 +945,16 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
         if (!BWD) { __syncthreads(); trace_h(done, 7); continue; }
         __syncthreads();
         trace_h(done, 7);
-        if (Ln < 64) {
+        if (Ln < 64) {                                         // (whole warps: quadrants 0 and 1)
+            float dzv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float dsr = sDsr[col0 + j];
-                const float dz = z2[j] > 0.f ? dsr * w2n : 0.f;
+                dzv[j] = z2[j] > 0.f ? dsr * w2n : 0.f;
                 a_dw2 = fmaf(dsr, z2[j], a_dw2);
-                a_db1 += dz;
-                store_split1<FP16>(smem + L::DZ2, smem + L::DZ2 + kHBlkT, col0 + j, Ln, dz);
+                a_db1 += dzv[j];
             }
+            store_split16_paired<FP16>(smem + L::DZ2, smem + L::DZ2 + kHBlkT, col0, Ln, dzv, lane);
         }
         if (tid < kHP) a_db2 += sDsr[tid];
         fence_proxy_async();
@@ -985,12 +986,12 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
             float pd[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float dz = ((mask1 >> j) & 1u) ? v[j] : 0.f;
-                a_db0 += dz;
-                a_dwl = fmaf(dz, sEmb[col0 + j], a_dwl);
-                pd[j] = dz * wl;
-                store_split1<FP16>(smem + L::DZ1 + (Ln >> 6) * kHBlkT, smem + L::DZ1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0 + j, Ln & 63, dz);
+                v[j] = ((mask1 >> j) & 1u) ? v[j] : 0.f;
+                a_db0 += v[j];
+                a_dwl = fmaf(v[j], sEmb[col0 + j], a_dwl);
+                pd[j] = v[j] * wl;
             }
+            store_split16_paired<FP16>(smem + L::DZ1 + (Ln >> 6) * kHBlkT, smem + L::DZ1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0, Ln & 63, v, lane);
             const float tot = warp_reduce16(pd, lane);
             if ((lane & 1) == 0) sRed[q * 64 + col0 + reduce16_index(lane)] = tot;
         }

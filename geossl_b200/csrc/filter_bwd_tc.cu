@@ -57,14 +57,6 @@ struct Part {
     static constexpr int kW2 = 0, kW1 = 128 * 128, kB2 = kW1 + 64 * 128, kB1 = kB2 + 128, kFloats = kB1 + 128;
 };
 
-__device__ __forceinline__ void store_split_bf16(uint8_t* hi_block, uint8_t* lo_block, uint32_t row, uint32_t k, float x) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-    const uint32_t off = sw128_offset(row, k);
-    *reinterpret_cast<__nv_bfloat16*>(hi_block + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(lo_block + off) = l;
-}
-
 // PAIRS: the tile rows are undirected pairs (geossl_pair_index): edge_dist / n_edges_dev describe the pairs, and
 // dU_u = C(d_u) * (x[s] * g[t] + x[t] * g[s]) sums both directions of pair u = (s -> t) (second term only if the reverse
 // edge exists: pair_atoms[u] = (s, t) or (s, ~t)).  Everything downstream of dU is linear in it, so the parameter gradients are unchanged.
@@ -389,8 +381,7 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             mbar_wait(bar(S_FREE_ + b), ((i >> 1) & 1) ^ 1);             // WG2(i-2) has consumed this S buffer
             uint8_t* s_hi = smem + L::S + b * 4 * kBlkT + blk;
             uint8_t* s_lo = s_hi + 2 * kBlkT;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) store_split_bf16(s_hi, s_lo, eq * 16 + j, kcol, a[j]);
+            store_split16_paired<kBwdFP16>(s_hi, s_lo, eq * 16, kcol, a, lane);
             fence_proxy_async();
             warp_arrive(bar(S_FULL_ + b));
             if (warp == 0) trace_b(i, 10);
@@ -409,7 +400,8 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
             if (i > 0) mbar_wait(bar(DA_FREE_), (i - 1) & 1);             // WG1(i-1) has consumed dA
             if (warp == 0) trace_b(i, 12);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) store_split_bf16(da_hi, da_lo, eq * 16 + j, kcol, ds[j] * sig[j]);
+            for (int j = 0; j < 16; ++j) ds[j] *= sig[j];
+            store_split16_paired<kBwdFP16>(da_hi, da_lo, eq * 16, kcol, ds, lane);
             fence_proxy_async();
             warp_arrive(bar(DA_FULL_));
             if (warp == 0) trace_b(i, 13);

@@ -197,6 +197,31 @@ __device__ __forceinline__ void store_split1(uint8_t* hi_block, uint8_t* lo_bloc
     }
 }
 
+// Transposed epilogues (TMEM lane = K index of the operand tile being produced, registers = 16 consecutive rows): each lane
+// holds v[j] = element (row0 + j, k).  Writing them one by one is a 2-byte store per element with two lanes landing in
+// every 32-bit shared-memory word -- ncu counts one bank conflict per store instruction (2.7 M per launch of the filter
+// backward kernel, L1TEX the busiest unit).  Here lanes 2m / 2m+1 (k even / odd) swap half of their rows first, so that
+// every lane owns BOTH k values of 8 rows and stores packed 32-bit words: half the store instructions, no conflicts.
+// The even lane keeps rows {0-3, 8-11}, the odd lane rows {4-7, 12-15}: rows written by one instruction differ by 4,
+// which the 128-byte swizzle maps to disjoint bank groups.  `k` must be even on even lanes and k+1 on their partners.
+template <bool FP16>
+__device__ __forceinline__ void store_split16_paired(uint8_t* hi_block, uint8_t* lo_block, uint32_t row0, uint32_t k,
+                                                     const float (&v)[16], int lane) {
+    const bool odd = lane & 1;
+    const uint32_t kpair = k & ~1u;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int r = (t & 3) + ((t >> 2) << 3);                    // 0-3, 8-11
+        const float keep = odd ? v[r + 4] : v[r], send = odd ? v[r] : v[r + 4];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        uint32_t h, l;
+        Split<FP16>::pair(odd ? recv : keep, odd ? keep : recv, h, l);
+        const uint32_t off = sw128_offset(row0 + r + (odd ? 4 : 0), kpair);
+        *reinterpret_cast<uint32_t*>(hi_block + off) = h;
+        *reinterpret_cast<uint32_t*>(lo_block + off) = l;
+    }
+}
+
 // Store 8 consecutive K values (k0 % 8 == 0) of `row` into the hi and lo images of a SW128 block.
 template <bool FP16>
 __device__ __forceinline__ void store_chunk8(uint8_t* hi_block, uint8_t* lo_block, uint32_t row, uint32_t k0, const float* x) {
