@@ -600,7 +600,7 @@ def run_finetune(args):
     import torch.distributed as dist
     from geossl_b200 import _lib, ops
     from geossl_b200.Geom3D.models import SchNet
-    from geossl_b200.finetune import GraphedFinetuneStep, lba_train_step, md17_train_step
+    from geossl_b200.finetune import GraphedFinetuneStep, GraphedMD17Step, lba_train_step, md17_train_step
     from geossl_b200.pretrain import FlatGradAllReduce, broadcast_parameters, default_args
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -651,8 +651,14 @@ def run_finetune(args):
     same_shape = len({tuple(b.positions.shape) for b in dev_pool}) == 1
     if not args.no_graph:
         try:
-            step = GraphedFinetuneStep(lambda b: step_fn(targs, b, model, lin, crit, opt, grad_sync=sync, zero_grad=False), dev_pool, opt)
-            launch = "whole step captured in one CUDA graph (batches padded to one atom capacity)"
+            if kind == "md17":
+                step = GraphedMD17Step(targs, dev_pool[0], model, lin, crit, opt, grad_sync=sync)
+                step(dev_pool[0])
+                launch = ("neighbour search + edge count eager per batch, then forward / force / double backward / Adam replayed "
+                          "from one CUDA graph per edge count")
+            else:
+                step = GraphedFinetuneStep(lambda b: step_fn(targs, b, model, lin, crit, opt, grad_sync=sync, zero_grad=False), dev_pool, opt)
+                launch = "whole step captured in one CUDA graph (batches padded to one atom capacity)"
         except Exception as exc:                              # noqa: BLE001 -- report, never hide
             launch = f"eager launches (graph capture refused: {type(exc).__name__}: {str(exc)[:120]})"
             step = eager

@@ -9,8 +9,6 @@
 //
 // HBM roofline: bytes = 4F*U (every filter row once) + 2*4F*N (x, out) + 8E (src, filt_row) + 4(N+1) (rowptr);
 // U = E without pair sharing (551 B/edge), U = E/2 for untruncated graphs (300 B/edge).
-#include <algorithm>
-
 #include "common.cuh"
 
 namespace geossl {
@@ -165,131 +163,15 @@ cfconv_gather_async_kernel(const float* __restrict__ filt, const int32_t* __rest
     *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
 }
 
-// Persistent edition (F = 128, used when the caller supplies scheduler counters): the same cp.async ring, but the grid is
-// 3 CTAs per SM and rows are handed out dynamically (one atomic per row on a self-resetting counter), so there is no wave
-// tail (the one-warp-per-row grid runs 4.3 waves: ncu shows SMs idle for 15 % of the kernel), and the next row's id, row
-// pointers and gather indices are fetched while the current row's filter rows are in flight.
-// (Negative result kept out of the tree: the same kernel with one cp.async.bulk per 512-byte filter row -- to take the
-// copies off the L1TEX pipe, which ncu shows busier (61 %) than DRAM (44 %) -- ran 55 us instead of 35 us,
-// profiles/r02_v5_launches.txt: the bulk-copy engine serialises on ~3000 small copies per SM.)
-template <bool TRANSPOSED>
-__global__ void __launch_bounds__(256, 3)
-cfconv_gather_persistent_kernel(const float* __restrict__ filt, const int32_t* __restrict__ filt_row, const float* __restrict__ v,
-                                const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx_a, const int32_t* __restrict__ idx_b,
-                                int n_atoms, float* __restrict__ out, int* __restrict__ counters) {
-    constexpr int F = 128, U = 8;
-    extern __shared__ float4 sW_raw[];                                // 64 KB: [warp][stage][row of the step][lane]
-    float4 (*sW)[2][U][32] = reinterpret_cast<float4 (*)[2][U][32]>(sW_raw);
-    pdl_launch_dependents();
-    pdl_wait();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int f = lane * 4;
-    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(&sW[w][0][0][lane]);
-    constexpr uint32_t kRowB = 32 * 16, kStageB = U * kRowB;
-
-    auto next_item = [&]() {
-        int it = 0;
-        if (lane == 0) it = atomicAdd(counters, 1);
-        return __shfl_sync(0xffffffffu, it, 0);
-    };
-    auto load_idx = [&](int base, int end, int& a, int& b) {
-        const int mine = base + lane;
-        a = 0; b = 0;
-        if (mine < end) {
-            const int e = TRANSPOSED ? __ldg(idx_a + mine) : mine;
-            a = filt_row ? __ldg(filt_row + e) : e;
-            b = __ldg(idx_b + mine);
-        }
-    };
-
-    // rows are walked LAST to first (see the async edition); item k -> row n_atoms - 1 - k
-    int item = next_item();
-    int rb = 0, rend = 0, my_a = 0, my_b = 0;
-    if (item < n_atoms) {
-        const int row = n_atoms - 1 - item;
-        rb = __ldg(ptr + row);
-        rend = __ldg(ptr + row + 1);
-        load_idx(rb, rend, my_a, my_b);
-    }
-    while (item < n_atoms) {
-        const int row = n_atoms - 1 - item;
-        int item_n = n_atoms, b_n = 0, end_n = 0, a_n = 0, bb_n = 0;
-        int prefetch = 0;                                             // 0: nothing yet, 1: next row's pointers requested, 2: indices too
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int base = rb; base < rend; base += 32) {
-            if (base != rb) load_idx(base, rend, my_a, my_b);         // rows beyond 32 edges (33-neighbour rows)
-            const int cnt = min(32, rend - base);
-            const int n_steps = (cnt + U - 1) / U;
-            auto issue = [&](int step) {                              // rows step*U .. +U-1 of this chunk -> stage step & 1
-                const uint32_t dst = s0 + (step & 1) * kStageB;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int k = step * U + u;
-                    const int ra = __shfl_sync(0xffffffffu, my_a, k & 31);
-                    if (k < cnt) cp_async16(dst + u * kRowB, filt + (int64_t)ra * F + f);
-                }
-                cp_async_commit();
-            };
-            issue(0);
-            for (int step = 0; step < n_steps; ++step) {
-                if (step + 1 < n_steps) issue(step + 1);
-                else cp_async_commit();                               // empty group keeps the wait count uniform
-                if (prefetch == 0) {                                  // behind the first copies of this row: the next row's id + pointers
-                    item_n = next_item();
-                    if (item_n < n_atoms) {
-                        b_n = __ldg(ptr + n_atoms - 1 - item_n);
-                        end_n = __ldg(ptr + n_atoms - item_n);
-                    }
-                    prefetch = 1;
-                } else if (prefetch == 1) {
-                    load_idx(b_n, end_n, a_n, bb_n);
-                    prefetch = 2;
-                }
-                int rbk[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int k = step * U + u;
-                    rbk[u] = __shfl_sync(0xffffffffu, my_b, (k < cnt ? k : 0) & 31);
-                }
-                float4 xv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) xv[u] = ldg4(v + (int64_t)rbk[u] * F + f);
-                cp_async_wait<1>();                                   // this step's rows have landed (next step's may not)
-                const float4* sp = &sW[w][step & 1][0][lane];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (step * U + u < cnt) fma4(acc, xv[u], sp[u * 32]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) xv[u] = ldg4(v + (int64_t)rbk[4 + u] * F + f);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (step * U + 4 + u < cnt) fma4(acc, xv[u], sp[(4 + u) * 32]);
-            }
-            cp_async_wait<0>();
-        }
-        *reinterpret_cast<float4*>(out + (int64_t)row * F + f) = acc;
-        if (prefetch == 0) {                                          // (row without edges)
-            item_n = next_item();
-            if (item_n < n_atoms) {
-                b_n = __ldg(ptr + n_atoms - 1 - item_n);
-                end_n = __ldg(ptr + n_atoms - item_n);
-            }
-            prefetch = 1;
-        }
-        if (prefetch == 1) load_idx(b_n, end_n, a_n, bb_n);
-        item = item_n; rb = b_n; rend = end_n; my_a = a_n; my_b = bb_n;
-    }
-    // self-resetting scheduler: the last warp of the grid to leave puts both counters back to zero for the next launch
-    if (lane == 0) {
-        __threadfence();
-        const int total = (int)gridDim.x * (int)(blockDim.x >> 5);
-        if (atomicAdd(counters + 1, 1) == total - 1) {
-            counters[0] = 0;
-            counters[1] = 0;
-            __threadfence();
-        }
-    }
-}
+// Negative results of round 2, kept out of the tree (numbers: profiles/r02_v5_launches.txt, profiles/r02_v6_cfconv_ab.txt):
+//  * one cp.async.bulk (TMA) copy per 512-byte filter row instead of 32 x cp.async, to take the copies off the L1TEX pipe
+//    (ncu: L1/TEX 61 % busy vs DRAM 44 %): 55 us instead of 35 us -- the bulk-copy engine serialises on ~3000 small copies
+//    per SM;
+//  * a persistent grid (3 CTAs per SM) with dynamic row hand-out (one atomic per row) and next-row index prefetch, to remove
+//    the 15 % wave tail: 41.6 us instead of 37.5 us (61.7 vs 44.5 us with one filter row per edge) -- the dependent
+//    atomic -> row pointer -> index chain costs more than the tail it removes.
+// With one filter row per directed edge the kernel below streams 5.4 TB/s (83 % of the HBM copy peak); with one row per atom
+// pair half of the row reads are L2 hits, DRAM traffic halves but the L2 -> SM path (the same 224 MB) now sets the time.
 
 template <int F>
 __global__ void __launch_bounds__(256)
@@ -310,20 +192,6 @@ cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, co
 }
 
 template <bool TRANSPOSED>
-static void launch_persistent(cudaStream_t st, const float* filt, const int32_t* filt_row, const float* v, const int32_t* ptr,
-                        const int32_t* idx_a, const int32_t* idx_b, int n, float* out, int* counters) {
-    constexpr int kSmem = 8 * 2 * 8 * 32 * 16;
-    static PerDeviceFlag configured;
-    if (!configured.get()) {
-        cudaFuncSetAttribute(cfconv_gather_persistent_kernel<TRANSPOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        configured.set();
-    }
-    const int blocks = (int)std::min<int64_t>(((int64_t)n + 7) / 8, 3 * kNumSM);          // persistent: 3 CTAs per SM
-    launch_pdl(cfconv_gather_persistent_kernel<TRANSPOSED>, dim3(blocks), dim3(256), (size_t)kSmem, st, filt, filt_row, v, ptr, idx_a, idx_b, n, out,
-               counters);
-}
-
-template <bool TRANSPOSED>
 static void launch_async(int blocks, cudaStream_t st, const float* filt, const int32_t* filt_row, const float* v, const int32_t* ptr,
                          const int32_t* idx_a, const int32_t* idx_b, int n, float* out) {
     constexpr int kSmem = 8 * 2 * 8 * 32 * 16;
@@ -335,29 +203,25 @@ static void launch_async(int blocks, cudaStream_t st, const float* filt, const i
     launch_pdl(cfconv_gather_async_kernel<TRANSPOSED>, dim3(blocks), dim3(256), (size_t)kSmem, st, filt, filt_row, v, ptr, idx_a, idx_b, n, out);
 }
 
-// F = 128 takes the persistent edition when the caller supplies scheduler counters (else one warp per row), narrower models
-// the deep register edition; all accumulate in edge order and agree bit for bit.  (Round-1 A/B of four editions: profiles/r01_v26_tune_cfconv.txt, r01_v32_tune_cfconv.txt -- the kernel is
+// F = 128 takes the cp.async edition, narrower models the deep register edition; both accumulate in edge order and agree
+// bit for bit.  (Round-1 A/B of four editions: profiles/r01_v26_tune_cfconv.txt, r01_v32_tune_cfconv.txt -- the kernel is
 // latency bound, what pays is filter rows in flight, not less L2 traffic for the gather operand.)
 template <int F>
 int launch_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src, int64_t n,
-               float* out, int* counters, cudaStream_t st) {
+               float* out, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    if constexpr (F == 128) {
-        if (counters) launch_persistent<false>(st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out, counters);
-        else launch_async<false>(blocks, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
-    } else launch_pdl(cfconv_gather_deep_kernel<F, false>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
+    if constexpr (F == 128) launch_async<false>(blocks, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
+    else launch_pdl(cfconv_gather_deep_kernel<F, false>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, x, rowptr, nullptr, src, (int)n, out);
     return 0;
 }
 template <int F>
 int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, const int32_t* tr, const int32_t* te, const int32_t* tt,
-                 int64_t n, float* dx, int* counters, cudaStream_t st) {
+                 int64_t n, float* dx, cudaStream_t st) {
     const int threads = 256;
     const int blocks = (int)((n * 32 + threads - 1) / threads);
-    if constexpr (F == 128) {
-        if (counters) launch_persistent<true>(st, filt, filt_row, g, tr, te, tt, (int)n, dx, counters);
-        else launch_async<true>(blocks, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
-    } else launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
+    if constexpr (F == 128) launch_async<true>(blocks, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
+    else launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
     return 0;
 }
 template <int F>
@@ -383,19 +247,19 @@ using namespace geossl;
 extern "C" {
 
 int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src,
-                      int64_t n_atoms, int F, float* out, int32_t* sched, void* stream) {
+                      int64_t n_atoms, int F, float* out, void* stream) {
     if (n_atoms == 0) return 0;
     GEOSSL_REQUIRE(x && filt && rowptr && src && out && n_atoms > 0, "null pointer");
-    DISPATCH_F(F, launch_fwd<kF>(x, filt, filt_row, rowptr, src, n_atoms, out, sched, as_stream(stream)));
+    DISPATCH_F(F, launch_fwd<kF>(x, filt, filt_row, rowptr, src, n_atoms, out, as_stream(stream)));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
 
 int geossl_cfconv_bwd_x(const float* filt, const int32_t* filt_row, const float* grad_out, const int32_t* t_rowptr, const int32_t* t_eid,
-                        const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, int32_t* sched, void* stream) {
+                        const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream) {
     if (n_atoms == 0) return 0;
     GEOSSL_REQUIRE(filt && grad_out && t_rowptr && t_eid && t_tgt && grad_x && n_atoms > 0, "null pointer");
-    DISPATCH_F(F, launch_bwd_x<kF>(filt, filt_row, grad_out, t_rowptr, t_eid, t_tgt, n_atoms, grad_x, sched, as_stream(stream)));
+    DISPATCH_F(F, launch_bwd_x<kF>(filt, filt_row, grad_out, t_rowptr, t_eid, t_tgt, n_atoms, grad_x, as_stream(stream)));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -14,7 +14,8 @@ from . import ops
 def _readout(args, model, batch_data, positions):
     x = batch_data.x[:, 0] if batch_data.x.dim() == 2 else batch_data.x
     if args.model_3d == "schnet":
-        out = model(x, positions, batch_data.batch, num_graphs=getattr(batch_data, "n_graphs", None))
+        out = model(x, positions, batch_data.batch, num_graphs=getattr(batch_data, "n_graphs", None),
+                    graph=getattr(batch_data, "extras", {}).get("graph"))
     elif args.model_3d == "painn":
         out = model(x, positions, batch_data.radius_edge_index, batch_data.batch,
                     num_graphs=getattr(batch_data, "n_graphs", None))
@@ -122,3 +123,73 @@ class GraphedFinetuneStep:
             d.copy_(t, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+
+class GraphedMD17Step:
+    """The MD17 force-training iteration (finetune_md17.py::train :30-56: energy, force = -dE/dpos with create_graph=True,
+    weighted L1, loss.backward() through the force -- double backward -- and the optimizer) replayed from a CUDA graph.
+
+    The second-order path trims its edge list to the exact edge count, which is one host read (``RadiusCSR.exact``).  That
+    read stays OUTSIDE the graph: per batch the neighbour search runs eagerly, its CSR (+ transpose) is copied into static
+    buffers, and the captured forward / force / double-backward / optimizer sequence is replayed on them.  One graph is
+    captured per distinct edge count (conformers of one molecule inside the cutoff share one complete graph, so MD17
+    needs exactly one); ``max_graphs`` bounds the cache, beyond it the step runs eagerly."""
+
+    def __init__(self, args, example_batch, model, graph_pred_linear, criterion, optimizer, grad_sync=None, max_graphs=4, **coeffs):
+        self.args, self.model, self.lin, self.crit, self.opt, self.sync, self.coeffs = args, model, graph_pred_linear, criterion, optimizer, grad_sync, coeffs
+        self.max_graphs = max_graphs
+        self.graphs = {}
+        self.template = example_batch
+
+    def _structure(self, batch):
+        g = ops.radius_csr(batch.positions.detach(), batch.batch, self.model.cutoff, num_graphs=batch.num_graphs)
+        return g.exact()                                           # host read of the edge count (outside any capture)
+
+    def _capture(self, batch, ge):
+        e = ge.num_edges
+        sg = ops.RadiusCSR(ge.n_atoms, e, ge.rowptr.clone(), ge.src.clone(), ge.tgt.clone(), None, batch.batch.clone(), ge.graph_ptr.clone())
+        sg.t_rowptr, sg.t_eid, sg.t_tgt = ge.t_rowptr.clone(), ge.t_eid.clone(), ge.t_tgt.clone()
+        sg._n_edges, sg._exact = e, sg
+        extras = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.extras.items() if k != "graph"}
+        extras["graph"] = sg
+        static = type(batch)(batch.x.clone(), batch.positions.detach().clone(), sg.batch, None, None, batch.num_graphs, sg.graph_ptr, extras)
+
+        def run():
+            return md17_train_step(self.args, static, self.model, self.lin, self.crit, self.opt, grad_sync=self.sync, zero_grad=False,
+                                   **self.coeffs)
+        dev = static.positions.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.opt.zero_grad(set_to_none=True)
+                static.positions.grad = None
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        static.positions.grad = None
+        with torch.cuda.graph(graph):
+            loss = run()
+        return graph, static, sg, loss
+
+    def __call__(self, batch):
+        ge = self._structure(batch)
+        e = ge.num_edges
+        entry = self.graphs.get(e)
+        if entry is None:
+            if len(self.graphs) >= self.max_graphs:
+                return md17_train_step(self.args, batch, self.model, self.lin, self.crit, self.opt, grad_sync=self.sync, **self.coeffs)
+            entry = self.graphs[e] = self._capture(batch, ge)
+        graph, static, sg, loss = entry
+        with torch.no_grad():
+            static.x.copy_(batch.x, non_blocking=True)
+            static.positions.copy_(batch.positions.detach(), non_blocking=True)
+            sg.batch.copy_(batch.batch, non_blocking=True)
+            for k in ("y", "force"):
+                static.extras[k].copy_(batch.extras[k], non_blocking=True)
+            for name in ("rowptr", "src", "tgt", "t_rowptr", "t_eid", "t_tgt", "graph_ptr"):
+                getattr(sg, name).copy_(getattr(ge, name), non_blocking=True)
+        graph.replay()
+        return loss

@@ -15,7 +15,6 @@ from . import _lib
 from ._lib import DdmPtrs, check
 
 MAX_NEIGHBORS_DEFAULT = 32      # torch_cluster.radius_graph default, never overridden (schnet.py:91)
-CFCONV_PERSISTENT = True        # cfconv aggregate (F = 128): persistent grid with dynamic row hand-out (False: one warp per row)
 
 
 class _KernelTimers:
@@ -137,16 +136,6 @@ class RadiusCSR:
         self.pair_rowptr = self.pair_of_edge = self.pair_e1 = self.pair_e2 = self.pair_atoms = self.pair_dist = None
         self._n_edges = None
         self._exact = None
-        self._sched = None
-
-    # Scheduler counters of the persistent cfconv kernels (two for the forward, two for the adjoint), zeroed once here;
-    # the kernels leave them at zero.  CFCONV_PERSISTENT = False falls back to the one-warp-per-row grid.
-    def sched(self, which):
-        if not CFCONV_PERSISTENT:
-            return None
-        if self._sched is None:
-            self._sched = torch.zeros(4, dtype=torch.int32, device=self.rowptr.device)
-        return ctypes.c_void_p(self._sched.data_ptr() + 8 * which)
 
     @property
     def n_edges_dev(self):
@@ -321,7 +310,7 @@ def csr_from_edge_index(edge_index, n_atoms, batch, graph_ptr=None, num_graphs=N
 def _cfconv_fwd(x, filt, g, filt_row=None):
     out = torch.empty((g.n_atoms, x.size(1)), dtype=torch.float32, device=x.device)
     _timed("cfconv_fwd", lambda: _lib.load().geossl_cfconv_fwd(_p(x), _p(filt), _p(filt_row), _p(g.rowptr), _p(g.src), g.n_atoms,
-                                                               x.size(1), _p(out), g.sched(0), _stream()))
+                                                               x.size(1), _p(out), _stream()))
     return out
 
 
@@ -330,7 +319,7 @@ def _cfconv_bwd_x(filt, grad_out, g, filt_row=None):
     dx = torch.empty((g.n_atoms, grad_out.size(1)), dtype=torch.float32, device=grad_out.device)
     _timed("cfconv_bwd_x", lambda: _lib.load().geossl_cfconv_bwd_x(_p(filt), _p(filt_row), _p(grad_out), _p(g.t_rowptr),
                                                                    _p(g.t_eid), _p(g.t_tgt), g.n_atoms, grad_out.size(1), _p(dx),
-                                                                   g.sched(1), _stream()))
+                                                                   _stream()))
     return dx
 
 

@@ -242,7 +242,10 @@ class FlatGradAllReduce:
         else:
             self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)
-        torch._foreach_copy_(grads, self.views)
+        # no copy back: the optimizer reads the reduced gradients straight from the flat buffer (p.grad becomes a view of it;
+        # the next backward assigns fresh gradient tensors after zero_grad(set_to_none=True))
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
 
 def broadcast_parameters(modules, src=0):

@@ -31,9 +31,6 @@ class _G:
         self.n_atoms, self.capacity = n_atoms, capacity
         self.__dict__.update(kw)
 
-    def sched(self, which):
-        return None
-
     def ensure_transpose(self):
         return self
 

@@ -145,17 +145,13 @@ int geossl_tc_selftest(int mode, int fp16, const float* a, const float* b, int K
 
 /* m_i = sum_{e in row i} x[src_e] * W_row(e)   (atomic-free segmented reduction, one warp per row).
  * filt_row: NULL => row(e) = e (one filter row per directed edge); else row(e) = filt_row[e] (the pair_of_edge map of
- * geossl_pair_index: both directions of an undirected pair read ONE shared filter row).
- * sched: NULL, or two int32 counters in device memory, ZERO before the first launch: the F = 128 kernel then runs as a
- * persistent grid (3 CTAs per SM) that hands rows out dynamically -- no wave tail, the next row's indices are prefetched;
- * the kernel leaves the counters at zero again (safe to reuse launch after launch on one stream). */
+ * geossl_pair_index: both directions of an undirected pair read ONE shared filter row). */
 int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* filt_row, const int32_t* rowptr, const int32_t* src,
-                      int64_t n_atoms, int F, float* out, int32_t* sched, void* stream);
+                      int64_t n_atoms, int F, float* out, void* stream);
 
-/* dx_j = sum_{e: src_e = j} W_e * g[tgt_e]   over the source-sorted view (sched as above, its own two counters). */
+/* dx_j = sum_{e: src_e = j} W_e * g[tgt_e]   over the source-sorted view. */
 int geossl_cfconv_bwd_x(const float* filt, const int32_t* filt_row, const float* grad_out, const int32_t* t_rowptr,
-                        const int32_t* t_eid, const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, int32_t* sched,
-                        void* stream);
+                        const int32_t* t_eid, const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream);
 
 /* dW_e = x[src_e] * g[tgt_e]  materialised (E,F)  (second-order path and the unfused comparison). */
 int geossl_cfconv_bwd_w(const float* x, const float* grad_out, const int32_t* rowptr, const int32_t* src,

@@ -1,5 +1,6 @@
-"""A/B of the cfconv aggregate kernels alone, on the bench workload's graph (two stacked views of 256 x 30 atoms):
-persistent grid (dynamic row hand-out) vs one warp per row, with one filter row per atom pair (shared) and per edge.
+"""The cfconv aggregate kernels alone, on the bench workload's graph (two stacked views of 256 x 30 atoms), with one filter
+row per atom pair (shared) and per edge.  (Round 2 used this script to A/B a persistent-grid edition, see the negative
+results noted in csrc/cfconv.cu; `persistent` is now always 0.)
 Back-to-back launches cycle over 4 filter tensors (4 x 112/225 MB > L2), CUDA events, mean of 40 launches.
 
     python profiles/bench_cfconv.py > profiles/rNN_vK_cfconv_ab.txt
@@ -38,9 +39,7 @@ def run(fn, reps=40):
 
 
 ref = {}
-for persistent in (False, True):
-    ops.CFCONV_PERSISTENT = persistent
-    g._sched = None
+for persistent in (False,):
     for shared in (True, False):
         fr = g.pair_of_edge if shared else None
         rows = u if shared else e

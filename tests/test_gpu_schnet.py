@@ -274,3 +274,39 @@ def test_torch_custom_ops_match_the_autograd_layer():
     y = torch.ops.geossl_b200.linear128(x, lin.weight, lin.bias, True, x)
     assert rel_err(y, x + F.linear(F.softplus(x) - 0.6931471824645996, lin.weight, lin.bias)) <= 1e-5
     assert torch.equal(torch.ops.geossl_b200.pair_distance(pos, b.super_edge_index.to(DEV)), ops.pair_distance(pos, b.super_edge_index.to(DEV)))
+
+
+def test_graphed_md17_step_equals_eager_loss():
+    """finetune.GraphedMD17Step: neighbour search + edge count eager, energy / autograd force / double backward / optimizer
+    replayed from a CUDA graph.  With lr = 0 the replayed loss of every batch equals the eager loss of the same batch; a
+    batch with another edge count captures a second graph."""
+    from geossl_b200.Geom3D.models import SchNet
+    from geossl_b200.finetune import GraphedMD17Step, md17_losses
+    from geossl_b200.pretrain import default_args
+    torch.manual_seed(5)
+    m = SchNet(hidden_channels=128, num_filters=128, num_interactions=2, num_gaussians=50, cutoff=10.0, node_class=9).to(DEV)
+    lin = torch.nn.Linear(128, 1).to(DEV)
+    crit = torch.nn.L1Loss()
+    opt = torch.optim.Adam(list(m.parameters()) + list(lin.parameters()), lr=0.0, fused=True, capturable=True)
+
+    def make(n_graphs, atoms, seed):
+        b = synthetic_batch(n_graphs, atoms, seed=seed, density=0.08, with_pairs=False)
+        g = torch.Generator().manual_seed(seed)
+        b.extras["y"] = torch.randn(n_graphs, generator=g)
+        b.extras["force"] = torch.randn(b.positions.shape, generator=g)
+        return b.to(DEV)
+
+    pool = [make(6, 21, s) for s in range(3)]
+    step = GraphedMD17Step(default_args("schnet"), pool[0], m, lin, crit, opt)
+    for b in pool:
+        got = step(b).clone()
+        ref, _, _ = md17_losses(default_args("schnet"), make(6, 21, 0) if False else b, m, lin, crit)
+        assert rel_err(got, ref) <= 1e-6, rel_err(got, ref)
+    assert len(step.graphs) == 1
+    sparse = synthetic_batch(6, 21, seed=9, density=0.002, with_pairs=False)          # spread out: fewer edges inside the cutoff
+    g = torch.Generator().manual_seed(1)
+    sparse.extras["y"], sparse.extras["force"] = torch.randn(6, generator=g), torch.randn(sparse.positions.shape, generator=g)
+    sparse = sparse.to(DEV)
+    got = step(sparse).clone()
+    ref, _, _ = md17_losses(default_args("schnet"), sparse, m, lin, crit)
+    assert rel_err(got, ref) <= 1e-6 and len(step.graphs) == 2
