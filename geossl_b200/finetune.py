@@ -155,7 +155,11 @@ class GraphedMD17Step:
         static = type(batch)(batch.x.clone(), batch.positions.detach().clone(), sg.batch, None, None, batch.num_graphs, sg.graph_ptr, extras)
 
         def run():
-            return md17_train_step(self.args, static, self.model, self.lin, self.crit, self.opt, grad_sync=self.sync, zero_grad=False,
+            # a FRESH leaf over the static coordinates every time: its AccumulateGrad node then belongs to the stream of this
+            # run (a leaf reused from the warm-up would carry the warm-up stream's node into the capture and invalidate it)
+            view = type(batch)(static.x, static.positions.detach().requires_grad_(), static.batch, None, None, static.n_graphs,
+                               static.graph_ptr, static.extras)
+            return md17_train_step(self.args, view, self.model, self.lin, self.crit, self.opt, grad_sync=self.sync, zero_grad=False,
                                    **self.coeffs)
         dev = static.positions.device
         side = torch.cuda.Stream(device=dev)
@@ -163,13 +167,11 @@ class GraphedMD17Step:
         with torch.cuda.stream(side):
             for _ in range(2):
                 self.opt.zero_grad(set_to_none=True)
-                static.positions.grad = None
                 run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
-        static.positions.grad = None
         with torch.cuda.graph(graph):
             loss = run()
         return graph, static, sg, loss

@@ -290,7 +290,7 @@ def test_graphed_md17_step_equals_eager_loss():
     opt = torch.optim.Adam(list(m.parameters()) + list(lin.parameters()), lr=0.0, fused=True, capturable=True)
 
     def make(n_graphs, atoms, seed):
-        b = synthetic_batch(n_graphs, atoms, seed=seed, density=0.08, with_pairs=False)
+        b = synthetic_batch(n_graphs, atoms, seed=seed, density=0.12, with_pairs=False)       # complete graphs (5.6 A cube)
         g = torch.Generator().manual_seed(seed)
         b.extras["y"] = torch.randn(n_graphs, generator=g)
         b.extras["force"] = torch.randn(b.positions.shape, generator=g)
@@ -300,7 +300,7 @@ def test_graphed_md17_step_equals_eager_loss():
     step = GraphedMD17Step(default_args("schnet"), pool[0], m, lin, crit, opt)
     for b in pool:
         got = step(b).clone()
-        ref, _, _ = md17_losses(default_args("schnet"), make(6, 21, 0) if False else b, m, lin, crit)
+        ref, _, _ = md17_losses(default_args("schnet"), b, m, lin, crit)
         assert rel_err(got, ref) <= 1e-6, rel_err(got, ref)
     assert len(step.graphs) == 1
     sparse = synthetic_batch(6, 21, seed=9, density=0.002, with_pairs=False)          # spread out: fewer edges inside the cutoff
