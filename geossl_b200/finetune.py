@@ -170,10 +170,16 @@ class GraphedMD17Step:
                 run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # create_graph=True leaves reference cycles behind (the force graph references itself through its saved tensors): until
+        # they are collected, the AccumulateGrad nodes of earlier iterations -- tied to THEIR streams -- stay alive and the
+        # autograd engine would synchronise the capture stream with them, which invalidates the capture
+        import gc
+        gc.collect()
         graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph):
             loss = run()
+        gc.collect()
         return graph, static, sg, loss
 
     def __call__(self, batch):
