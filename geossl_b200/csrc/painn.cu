@@ -169,7 +169,7 @@ painn_message_bwd_kernel(const float* __restrict__ gq_out, const float* __restri
                          const float* __restrict__ dist, const float* __restrict__ dir, const float* __restrict__ fcut,
                          const int32_t* __restrict__ j_rowptr, const int32_t* __restrict__ j_ctr,
                          int n_atoms, float* __restrict__ gx, float* __restrict__ gmu_in, float* __restrict__ gfilt,
-                         const float* __restrict__ wpre) {
+                         const float* __restrict__ wpre, int64_t zero_tail_cap) {
     constexpr int CPL = F / 32;
     extern __shared__ __align__(16) float smem[];
     float* sW = smem;
@@ -235,6 +235,13 @@ painn_message_bwd_kernel(const float* __restrict__ gq_out, const float* __restri
                 gx[o] = agx[b][j];
                 gmu_in[o] = __ldg(gmu_out + o) + agm[b][j];
             }
+    }
+    // capacity-padded edge lists: rows [live, n_edges_cap) of the per-edge gradient are padding and never written above; the
+    // filter GEMM's weight-gradient kernel contracts over ALL rows, so they must be zeros (cheaper here than a full memset)
+    if (zero_tail_cap > 0) {
+        const int64_t live = (int64_t)__ldg(j_rowptr + n_atoms);
+        const int64_t first = live * 3 * F, last = zero_tail_cap * 3 * F;
+        for (int64_t o = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < last; o += (int64_t)gridDim.x * blockDim.x) gfilt[o] = 0.f;
     }
 }
 
@@ -359,7 +366,7 @@ int launch_msg_bwd(const float* gq_out, const float* gmu_out, const float* mu, c
     int64_t blocks = (n_atoms + 7) / 8;
     if (blocks > kNumSM * 4) blocks = kNumSM * 4;
     painn_message_bwd_kernel<F><<<(int)blocks, 256, smem, st>>>(gq_out, gmu_out, mu, x, wf, bf, offsets, widths, R, dist, dir,
-                                                                 fcut, j_rowptr, j_ctr, (int)n_atoms, gx, gmu_in, gfilt, wpre);
+                                                                 fcut, j_rowptr, j_ctr, (int)n_atoms, gx, gmu_in, gfilt, wpre, wpre ? n_edges : (int64_t)0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (wpre != nullptr) return 0;     // gfilt IS the gradient of the materialised filter: its GEMM's weight-gradient kernel takes over

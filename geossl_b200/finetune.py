@@ -177,7 +177,7 @@ class GraphedMD17Step:
         gc.collect()
         graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):          # the warm-up stream: leaves' AccumulateGrad nodes already live there
             loss = run()
         gc.collect()
         return graph, static, sg, loss

@@ -1043,9 +1043,9 @@ class PaiNNMessage(torch.autograd.Function):
         if ctx.has_pre:
             mu, x, wpre = ctx.saved_tensors
             gx, gmu = torch.empty_like(x), torch.empty_like(mu)
-            # rows past the live edge count (capacity-padded lists) are never written by the kernel: they must be zeros,
-            # because the filter GEMM's weight-gradient kernel contracts over ALL rows
-            gpre = (torch.zeros if e > 0 else torch.empty)((max(e, 1), 3 * Fd), dtype=torch.float32, device=x.device)
+            # (rows past the live edge count of a capacity-padded list are zeroed by the kernel itself: the filter GEMM's
+            #  weight-gradient kernel contracts over ALL rows)
+            gpre = torch.empty((max(e, 1), 3 * Fd), dtype=torch.float32, device=x.device)
             _timed("painn_message_bwd", lambda: lib.geossl_painn_message_bwd(
                 _p(gq_out), _p(gmu_out), _p(mu), _p(x), None, None, _p(edges.offsets), _p(edges.widths), R, Fd, _p(edges.dist),
                 _p(edges.dir), _p(edges.fcut), _p(s.rowptr), _p(s.src), n, e, _p(gx), _p(gmu), _p(gpre), None, None, None,
