@@ -64,8 +64,8 @@ _SIGNATURES = {
     "geossl_weight_image_bytes": (c_i64, []),
     "geossl_pack_weight": (c_int, [c_p, c_int, c_int, c_p, c_p]),
     "geossl_pack_weights_batched": (c_int, [c_p, c_p, c_int, c_p, c_p]),
-    "geossl_linear_tc_block": (c_int, [c_p, c_i64, c_i64, c_p, c_p, c_int, c_int, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_int, c_p]),
-    "geossl_linear_wgrad_tc_block": (c_int, [c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_int, c_p, c_p]),
+    "geossl_linear_tc_block": (c_int, [c_p, c_i64, c_i64, c_p, c_p, c_int, c_int, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_int, c_int, c_p]),
+    "geossl_linear_wgrad_tc_block": (c_int, [c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_int, c_p, c_int, c_p]),
     "geossl_linear_tc": (c_int, [c_p, c_i64, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p]),
     "geossl_linear_wgrad_tc_workspace": (c_i64, [c_i64]),
     "geossl_linear_wgrad_tc": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
@@ -85,7 +85,7 @@ _SIGNATURES = {
     "geossl_painn_edge_geometry": (c_int, [c_p, c_p, c_i64, c_i64, c_f, c_p, c_p, c_p, c_p]),
     "geossl_painn_message_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_p,
                                          c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p]),
-    "geossl_painn_rbf_pad": (c_int, [c_p, c_p, c_i64, c_p, c_p, c_int, c_p, c_p]),
+    "geossl_painn_rbf_pad": (c_int, [c_p, c_p, c_i64, c_p, c_p, c_int, c_int, c_p, c_p]),
     "geossl_painn_workspace": (c_i64, [c_int, c_int]),
     "geossl_painn_message_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_p,
                                          c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),

@@ -98,14 +98,14 @@ pack_weights_batched_kernel(const float* const* __restrict__ weights, const int3
 // (full 32-byte sectors) and all eight loads of a thread are in flight before the first conversion.
 template <bool FP16, int NR>
 __device__ __forceinline__ void stage_rows_kmajor(const float* __restrict__ X, int64_t ldx, int64_t row0, int64_t n_rows, int pre_act,
-                                                  uint8_t* hi, uint8_t* lo) {
+                                                  uint8_t* hi, uint8_t* lo, int k_cols = 128) {
     constexpr int kBlkT = NR * 128, kRowsPerPass = NR / 4;
     const int tid = threadIdx.x, c = tid & 15, r0 = tid >> 4;
     float4 a[4][2];
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int64_t row = row0 + r0 + it * kRowsPerPass;
-        if (row < n_rows) {
+        if (row < n_rows && c * 8 < k_cols) {                 // (k_cols < 128: a K-padded operand, only its live columns exist)
             const float* p = X + row * ldx + c * 8;
             a[it][0] = ldg4(p);
             a[it][1] = ldg4(p + 4);
@@ -129,7 +129,7 @@ template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R, int NR>
 __global__ void __launch_bounds__(4 * NR, NR == 64 ? 2 : 1)
 linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __restrict__ w_image, const float* __restrict__ bias,
                  const float* __restrict__ Z, const float* __restrict__ R, float* __restrict__ Y,
-                 int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act) {
+                 int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act, int k_cols) {
     // ld*: row strides in floats (128 for the plain 128 -> 128 layer; wider layers are tiled into 128 x 128 blocks by the
     // host, each block one launch over a column window of the wider tensors).  act: kActSsp / kActSilu where PRE_SSP / HAS_Z apply.
     extern __shared__ uint8_t smem_raw[];
@@ -170,7 +170,7 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
     trace_l(1);
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t row0 = t * NR;
-        stage_rows_kmajor<FP16, NR>(X, ldx, row0, n_rows, PRE_SSP ? act : 0, smem + L::X, smem + L::X + 2 * kBlkT);
+        stage_rows_kmajor<FP16, NR>(X, ldx, row0, n_rows, PRE_SSP ? act : 0, smem + L::X, smem + L::X + 2 * kBlkT, k_cols);
         trace_l(2);
         // epilogue operands do not depend on the MMA: fetch them now so their latency hides behind it
         const bool full = row0 + NR <= n_rows;                 // warp-uniform: no per-row bounds checks on full tiles
@@ -197,6 +197,7 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
             if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
+                    if (ks * 16 >= k_cols) break;              // K-padded operand: the remaining k-steps multiply zeros
                     const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kBlkT >> 4) + 2 * (ks & 3);
                     mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, ks > 0);
                 }
@@ -253,13 +254,13 @@ constexpr int kWgPart = 128 * 128 + 128;              // per-CTA partial: DW [o]
 // thread = (8 columns 8cg.., rows ro + 16 s); returns the per-thread column sums in acc when requested.
 template <bool FP16, bool SUM>
 __device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64_t ldx, int64_t row0, int64_t n_rows, int pre_act,
-                                              uint8_t* hi, uint8_t* lo, float (&acc)[8]) {
+                                              uint8_t* hi, uint8_t* lo, float (&acc)[8], int x_cols = 128) {
     const int tid = threadIdx.x, cg = tid & 15, ro = tid >> 4;
     float4 a[4][2];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const int64_t row = row0 + s * 16 + ro;
-        if (row < n_rows) {
+        if (row < n_rows && cg * 8 < x_cols) {
             const float* p = X + row * ldx + cg * 8;
             a[s][0] = ldg4(p); a[s][1] = ldg4(p + 4);
         } else {
@@ -285,7 +286,7 @@ __device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64
 template <bool FP16>
 __global__ void __launch_bounds__(256, 2)
 linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, int64_t n_rows, int pre_act,
-                       float* __restrict__ workspace, int64_t ld_dy, int64_t ld_x) {
+                       float* __restrict__ workspace, int64_t ld_dy, int64_t ld_x, int x_cols) {
     extern __shared__ uint8_t smem_raw[];
     pdl_launch_dependents();
     pdl_wait();
@@ -311,7 +312,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++done) {
         const int64_t row0 = t * kNR;
         stage_rows_mn<FP16, true>(dY, ld_dy, row0, n_rows, 0, smem + L::DY, smem + L::DY + 2 * kNBlkT, acc);
-        stage_rows_mn<FP16, false>(X, ld_x, row0, n_rows, pre_act, smem + L::XT, smem + L::XT + 2 * kNBlkT, dummy);
+        stage_rows_mn<FP16, false>(X, ld_x, row0, n_rows, pre_act, smem + L::XT, smem + L::XT + 2 * kNBlkT, dummy, x_cols);
         fence_proxy_async();
         __syncthreads();
         if (warp == 0) {
@@ -420,7 +421,7 @@ using namespace geossl;
 
 template <bool FP16, bool PRE_SSP, bool HAS_Z, bool HAS_R>
 static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weight, const float* bias, const float* z, const float* r,
-                            float* y, int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act, cudaStream_t st) {
+                            float* y, int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act, int k_cols, cudaStream_t st) {
     static const int wide_min = [] { const char* e = getenv("GEOSSL_LINEAR_WIDE_MIN"); return e ? atoi(e) : 64 * kNumSM; }();
     if (n_rows >= wide_min) {
         // enough rows for every SM: 128-row tiles, one 512-thread CTA per SM (no co-resident CTA competing for the
@@ -435,7 +436,7 @@ static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weigh
         }
         const int64_t tiles = (n_rows + NR - 1) / NR;
         GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, dim3((unsigned)(tiles < kNumSM ? tiles : kNumSM)),
-                               dim3(4 * NR), smem, st, x, n_rows, weight, bias, z, r, y, ldx, ldz, ldr, ldy, act));
+                               dim3(4 * NR), smem, st, x, n_rows, weight, bias, z, r, y, ldx, ldz, ldr, ldy, act, k_cols));
         GEOSSL_LAUNCH_CHECK();
         return 0;
     }
@@ -448,7 +449,7 @@ static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weigh
         configured.set();
     }
     GEOSSL_CUDA(launch_pdl(tc::linear_tc_kernel<FP16, PRE_SSP, HAS_Z, HAS_R, NR>, dim3(tc::node_grid(n_rows)), dim3(4 * NR), smem, st,
-                           x, n_rows, weight, bias, z, r, y, ldx, ldz, ldr, ldy, act));
+                           x, n_rows, weight, bias, z, r, y, ldx, ldz, ldr, ldy, act, k_cols));
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }
@@ -483,9 +484,9 @@ int geossl_debug_set_trace_linear(long long* device_buffer) {
 
 static int linear_tc_dispatch(const float* x, int64_t n_rows, const uint8_t* weight, const float* bias, int pre_act,
                               const float* act_grad_input, const float* residual, float* y, int bf16_parts,
-                              int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act, cudaStream_t st) {
+                              int64_t ldx, int64_t ldz, int64_t ldr, int64_t ldy, int act, int k_cols, cudaStream_t st) {
     const int key = (bf16_parts ? 0 : 8) | (pre_act ? 4 : 0) | (act_grad_input ? 2 : 0) | (residual ? 1 : 0);
-#define GEOSSL_LIN_CASE(K, A, B, C, D) case K: return launch_linear_tc<A, B, C, D>(x, n_rows, weight, bias, act_grad_input, residual, y, ldx, ldz, ldr, ldy, act, st);
+#define GEOSSL_LIN_CASE(K, A, B, C, D) case K: return launch_linear_tc<A, B, C, D>(x, n_rows, weight, bias, act_grad_input, residual, y, ldx, ldz, ldr, ldy, act, k_cols, st);
     switch (key) {
         GEOSSL_LIN_CASE(0, false, false, false, false) GEOSSL_LIN_CASE(1, false, false, false, true)
         GEOSSL_LIN_CASE(2, false, false, true, false)  GEOSSL_LIN_CASE(3, false, false, true, true)
@@ -505,39 +506,41 @@ int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, c
     if (n_rows == 0) return 0;
     GEOSSL_REQUIRE(x && weight_image && y && n_rows > 0, "null pointer");
     return linear_tc_dispatch(x, n_rows, (const uint8_t*)weight_image, bias, pre_ssp, act_grad_input, residual, y, bf16_parts,
-                              128, 128, 128, 128, tc::kActSsp, as_stream(stream));
+                              128, 128, 128, 128, tc::kActSsp, 128, as_stream(stream));
 }
 
 int geossl_linear_tc_block(const float* x, int64_t ldx, int64_t n_rows, const void* weight_image, const float* bias, int act,
                            int pre_act, const float* act_grad_input, int64_t ldz, const float* residual, int64_t ldr,
-                           float* y, int64_t ldy, int bf16_parts, void* stream) {
+                           float* y, int64_t ldy, int bf16_parts, int k_cols, void* stream) {
     if (n_rows == 0) return 0;
     GEOSSL_REQUIRE(x && weight_image && y && n_rows > 0, "null pointer");
-    GEOSSL_REQUIRE(ldx >= 128 && ldy >= 128 && ldx % 4 == 0 && (!act_grad_input || ldz >= 128) && (!residual || ldr >= 128), "bad leading dimension");
+    GEOSSL_REQUIRE(k_cols >= 16 && k_cols <= 128 && k_cols % 16 == 0, "k_cols must be a multiple of 16 in [16,128]");
+    GEOSSL_REQUIRE(ldx >= k_cols && ldy >= 128 && ldx % 4 == 0 && (!act_grad_input || ldz >= 128) && (!residual || ldr >= 128), "bad leading dimension");
     GEOSSL_REQUIRE(act == tc::kActSsp || act == tc::kActSilu || !(pre_act || act_grad_input), "act must be 1 (ssp) or 2 (silu)");
     return linear_tc_dispatch(x, n_rows, (const uint8_t*)weight_image, bias, pre_act, act_grad_input, residual, y, bf16_parts,
-                              ldx, ldz, ldr, ldy, act, as_stream(stream));
+                              ldx, ldz, ldr, ldy, act, k_cols, as_stream(stream));
 }
 
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::wgrad_grid(n_rows) * tc::kWgPart; }
 
 static int wgrad_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act, float* workspace,
-                       float* grad_weight, int ld_gw, float* grad_bias, void* stream);
+                       float* grad_weight, int ld_gw, float* grad_bias, int x_cols, void* stream);
 
 int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, int pre_ssp, float* workspace,
                            float* grad_weight, float* grad_bias, void* stream) {
-    return wgrad_block(grad_y, 128, x, 128, n_rows, pre_ssp ? tc::kActSsp : 0, workspace, grad_weight, 128, grad_bias, stream);
+    return wgrad_block(grad_y, 128, x, 128, n_rows, pre_ssp ? tc::kActSsp : 0, workspace, grad_weight, 128, grad_bias, 128, stream);
 }
 
 int geossl_linear_wgrad_tc_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act,
-                                 float* workspace, float* grad_weight, int ld_gw, float* grad_bias, void* stream) {
-    GEOSSL_REQUIRE(ld_dy >= 128 && ld_x >= 128 && ld_gw >= 128 && ld_dy % 4 == 0 && ld_x % 4 == 0, "bad leading dimension");
+                                 float* workspace, float* grad_weight, int ld_gw, float* grad_bias, int x_cols, void* stream) {
+    GEOSSL_REQUIRE(x_cols >= 8 && x_cols <= 128 && x_cols % 8 == 0, "x_cols must be a multiple of 8 in [8,128]");
+    GEOSSL_REQUIRE(ld_dy >= 128 && ld_x >= x_cols && ld_gw >= 128 && ld_dy % 4 == 0 && ld_x % 4 == 0, "bad leading dimension");
     GEOSSL_REQUIRE(pre_act >= 0 && pre_act <= 2, "pre_act must be 0, 1 (ssp) or 2 (silu)");
-    return wgrad_block(grad_y, ld_dy, x, ld_x, n_rows, pre_act, workspace, grad_weight, ld_gw, grad_bias, stream);
+    return wgrad_block(grad_y, ld_dy, x, ld_x, n_rows, pre_act, workspace, grad_weight, ld_gw, grad_bias, x_cols, stream);
 }
 
 static int wgrad_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act, float* workspace,
-                       float* grad_weight, int ld_gw, float* grad_bias, void* stream) {
+                       float* grad_weight, int ld_gw, float* grad_bias, int x_cols, void* stream) {
     GEOSSL_REQUIRE(grad_y && x && workspace && grad_weight && n_rows > 0, "null pointer or empty input");
     const size_t smem = tc::WgLayout::kBytes + 1024;
     static PerDeviceFlag configured;
@@ -546,7 +549,7 @@ static int wgrad_block(const float* grad_y, int64_t ld_dy, const float* x, int64
         configured.set();
     }
     const int grid = tc::wgrad_grid(n_rows);
-    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid), dim3(256), smem, as_stream(stream), grad_y, x, n_rows, pre_act, workspace, ld_dy, ld_x));
+    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid), dim3(256), smem, as_stream(stream), grad_y, x, n_rows, pre_act, workspace, ld_dy, ld_x, x_cols));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_reduce_kernel, dim3((tc::kWgPart + 31) / 32), dim3(256), 0, as_stream(stream), workspace, grid, grad_weight, grad_bias, ld_gw));
     GEOSSL_LAUNCH_CHECK();

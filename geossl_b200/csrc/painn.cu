@@ -20,11 +20,11 @@ constexpr int kMaxRbf = 32;
 // phi_pad (E,128), optional: [rbf_0 .. rbf_{R-1}, 1, 0 ...] -- the K-padded operand of the tensor-core filter GEMM
 // (column R carries the bias of filter_net); one warp-coalesced 512-byte row per edge.
 __global__ void painn_rbf_pad_kernel(const float* __restrict__ dist, const float* __restrict__ fcut, int64_t n_edges,
-                                     const float* __restrict__ offsets, const float* __restrict__ widths, int R,
+                                     const float* __restrict__ offsets, const float* __restrict__ widths, int R, int ld,
                                      float* __restrict__ phi_pad) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t e = idx >> 7;
-    const int c = (int)(idx & 127);
+    const int64_t e = idx / ld;
+    const int c = (int)(idx - e * ld);
     if (e >= n_edges) return;
     float v = 0.f;
     if (c < R) {
@@ -397,12 +397,12 @@ int geossl_painn_edge_geometry(const float* pos, const int64_t* radius_edge_inde
 }
 
 int geossl_painn_rbf_pad(const float* dist, const float* fcut, int64_t n_edges, const float* offsets, const float* widths, int n_rbf,
-                         float* phi_pad, void* stream) {
+                         int ld, float* phi_pad, void* stream) {
     if (n_edges == 0) return 0;
     GEOSSL_REQUIRE(dist && fcut && offsets && widths && phi_pad, "null pointer");
-    GEOSSL_REQUIRE(n_rbf >= 1 && n_rbf < 128, "n_rbf must be in [1,127]");
-    const int64_t n = n_edges * 128;
-    painn_rbf_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(dist, fcut, n_edges, offsets, widths, n_rbf, phi_pad);
+    GEOSSL_REQUIRE((ld == 32 || ld == 64 || ld == 128) && n_rbf >= 1 && n_rbf < ld, "ld must be 32/64/128 and larger than n_rbf");
+    const int64_t n = n_edges * ld;
+    painn_rbf_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(dist, fcut, n_edges, offsets, widths, n_rbf, ld, phi_pad);
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -162,6 +162,8 @@ class GraphedMD17Step:
             return md17_train_step(self.args, view, self.model, self.lin, self.crit, self.opt, grad_sync=self.sync, zero_grad=False,
                                    **self.coeffs)
         dev = static.positions.device
+        self.opt.zero_grad(set_to_none=True)
+        run()                                               # once on the caller's stream (library handles, allocator pools)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -177,7 +179,7 @@ class GraphedMD17Step:
         gc.collect()
         graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph, stream=side):          # the warm-up stream: leaves' AccumulateGrad nodes already live there
+        with torch.cuda.graph(graph):
             loss = run()
         gc.collect()
         return graph, static, sg, loss

@@ -703,8 +703,11 @@ class DenseTC(torch.autograd.Function):
     def forward(ctx, x, weight, bias, pre_act, images):
         x, weight = _req(x, torch.float32, "x", 2), _req(weight, torch.float32, "weight", 2)
         N, K = weight.shape
-        if x.size(1) != K or N % 128 or K % 128:
+        # K-padded operand (PaiNN's rbf matrix): x may hold only the first 32 / 64 live columns of a K = 128 layer
+        k_cols = x.size(1) if (K == 128 and x.size(1) in (32, 64)) else 128
+        if (x.size(1) != K and k_cols == 128) or N % 128 or K % 128:
             raise RuntimeError(f"geossl_b200: DenseTC needs in/out features in multiples of 128, got {tuple(weight.shape)}")
+        ctx.k_cols = k_cols
         bias = None if bias is None else _req(bias, torch.float32, "bias", 1)
         n = x.size(0)
         ctx.pre_act, ctx.images, ctx.params = int(pre_act), images, (weight, bias)
@@ -717,8 +720,9 @@ class DenseTC(torch.autograd.Function):
         for ob in range(N // 128):
             for ib in range(K // 128):
                 _timed("dense_fwd", lambda: lib.geossl_linear_tc_block(
-                    _off(x, ib * 128), K, n, _p(images[ob, ib, 0]), None if (bias is None or ib) else _off(bias, ob * 128), act,
-                    1 if ctx.pre_act else 0, None, 128, _off(y, ob * 128) if ib else None, N, _off(y, ob * 128), N, 0, _stream()))
+                    _off(x, ib * 128), x.size(1), n, _p(images[ob, ib, 0]), None if (bias is None or ib) else _off(bias, ob * 128), act,
+                    1 if ctx.pre_act else 0, None, 128, _off(y, ob * 128) if ib else None, N, _off(y, ob * 128), N, 0, k_cols,
+                    _stream()))
         return y
 
     @staticmethod
@@ -740,7 +744,7 @@ class DenseTC(torch.autograd.Function):
                     _timed("dense_dgrad", lambda: lib.geossl_linear_tc_block(
                         _off(gy, ob * 128), N, n, _p(images[ob, ib, 1]), None, act, 0,
                         _off(x, ib * 128) if ctx.pre_act else None, K, _off(gx, ib * 128) if ob else None, K, _off(gx, ib * 128), K, 1,
-                        _stream()))
+                        128, _stream()))
         gw = gb = None
         wp, bp = ctx.params
         if ctx.needs_input_grad[1] or (bp is not None and ctx.needs_input_grad[2]):
@@ -751,8 +755,8 @@ class DenseTC(torch.autograd.Function):
                 for ob in range(N // 128):
                     for ib in range(K // 128):
                         _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
-                            _off(gy, ob * 128), N, _off(x, ib * 128), K, n, ctx.pre_act, _p(ws), _off(gw_, ob * 128 * K + ib * 128), K,
-                            None if (gb_ is None or ib) else _off(gb_, ob * 128), _stream()))
+                            _off(gy, ob * 128), N, _off(x, ib * 128), x.size(1), n, ctx.pre_act, _p(ws), _off(gw_, ob * 128 * K + ib * 128), K,
+                            None if (gb_ is None or ib) else _off(gb_, ob * 128), ctx.k_cols, _stream()))
                 return gw_, gb_
 
             deferrable = wp.is_leaf and wp.requires_grad and (bp is None or (bp.is_leaf and bp.requires_grad))
@@ -952,12 +956,13 @@ class PaiNNEdges:
         self._phi_pad = None
 
     def phi_pad(self):
-        """(E,128) = [rbf values, 1, 0...]: K-padded operand of the tensor-core filter GEMM (built once per forward)."""
+        """(E,32|64|128) = [rbf values, 1, 0...]: K-padded operand of the tensor-core filter GEMM (built once per forward)."""
         if self._phi_pad is None:
-            e = self.dist.numel()
-            self._phi_pad = torch.empty((e, 128), dtype=torch.float32, device=self.dist.device)
+            e, R = self.dist.numel(), self.offsets.numel()
+            ld = 32 if R < 32 else (64 if R < 64 else 128)
+            self._phi_pad = torch.empty((e, ld), dtype=torch.float32, device=self.dist.device)
             check(_lib.load().geossl_painn_rbf_pad(_p(self.dist), _p(self.fcut), e, _p(self.offsets), _p(self.widths),
-                                                   self.offsets.numel(), _p(self._phi_pad), _stream()), "painn_rbf_pad")
+                                                   R, ld, _p(self._phi_pad), _stream()), "painn_rbf_pad")
         return self._phi_pad
 
 

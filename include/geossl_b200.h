@@ -211,13 +211,16 @@ int geossl_linear_tc(const float* x, int64_t n_rows, const void* weight_image, c
  * painn_utils.py:9-35): the same kernel over column windows of wider row-major tensors.  x / act_grad_input / residual / y
  * point at the first element of their 128-column window; ld* are the row strides in floats.  act selects the
  * pre-activation (pre_act != 0) and its derivative (act_grad_input != NULL): 1 = shifted softplus, 2 = SiLU.  A K > 128
- * layer is the sum of its K-blocks: pass the partial result as `residual` (it may alias y). */
+ * layer is the sum of its K-blocks: pass the partial result as `residual` (it may alias y).
+ * k_cols (multiple of 16, <= 128): x has only k_cols live columns (a K-padded operand such as PaiNN's 20 rbf values + the
+ * bias column): only those are read and only k_cols/16 MMA k-steps are issued. */
 int geossl_linear_tc_block(const float* x, int64_t ldx, int64_t n_rows, const void* weight_image, const float* bias, int act,
                            int pre_act, const float* act_grad_input, int64_t ldz, const float* residual, int64_t ldr,
-                           float* y, int64_t ldy, int bf16_parts, void* stream);
-/* grad_weight block [o][i] (row stride ld_gw) = sum_r grad_y[r][o] * pre(x[r][i]), pre_act in {0, 1 = ssp, 2 = SiLU}. */
+                           float* y, int64_t ldy, int bf16_parts, int k_cols, void* stream);
+/* grad_weight block [o][i] (row stride ld_gw) = sum_r grad_y[r][o] * pre(x[r][i]), pre_act in {0, 1 = ssp, 2 = SiLU};
+ * x_cols (multiple of 8, <= 128): live columns of x, the others count as zeros (their gradient columns come out zero). */
 int geossl_linear_wgrad_tc_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act,
-                                 float* workspace, float* grad_weight, int ld_gw, float* grad_bias, void* stream);
+                                 float* workspace, float* grad_weight, int ld_gw, float* grad_bias, int x_cols, void* stream);
 
 /* grad_weight[o][i] = sum_r grad_y[r][o] * pre(x[r][i]);  grad_bias[o] = sum_r grad_y[r][o] (may be NULL). */
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows);
@@ -329,10 +332,10 @@ int geossl_painn_message_fwd(const float* q, const float* mu, const float* ctx, 
  * filter GEMM (geossl_painn_rbf_pad + geossl_linear_tc_block over the K-padded rbf matrix); the kernels stream them and
  * multiply by fcut.  In the backward, edge_scratch then IS the gradient w.r.t. filter_pre and the filter_net gradients come
  * from that GEMM's weight-gradient kernel (geossl_linear_wgrad_tc_block); filter_w/b, workspace, grad_filter_* may be NULL. */
-/* phi_pad (E,128) = [rbf_0(d_e) .. rbf_{R-1}(d_e), 1, 0, ...]: the K-padded A operand of the filter GEMM (column R carries
- * the bias of filter_net).  GaussianRBF, painn_utils.py:99-103. */
+/* phi_pad (E,ld) = [rbf_0(d_e) .. rbf_{R-1}(d_e), 1, 0, ...], ld in {32,64,128} > n_rbf: the K-padded A operand of the filter
+ * GEMM (column R carries the bias of filter_net).  GaussianRBF, painn_utils.py:99-103. */
 int geossl_painn_rbf_pad(const float* dist, const float* fcut, int64_t n_edges, const float* offsets, const float* widths, int n_rbf,
-                         float* phi_pad, void* stream);
+                         int ld, float* phi_pad, void* stream);
 
 /* Backward.  (j_rowptr, j_ctr): rowptr over the idx_j-sorted edge list and idx_i of each edge (int32).
  * Outputs: grad_ctx (N,3F), grad_mu_in (N,3,F) (includes the identity path), grad_filter_w (3F,n_rbf),
