@@ -10,7 +10,7 @@ What runs where
   radius graph ............ geossl_radius_csr (+ transpose)        [was torch_cluster.radius_graph, :91]
   rbf + filter MLP + cutoff  geossl_filter_fwd / geossl_filter_bwd  [was :94, :141-145, :186-187]
   gather * W, scatter-add .. geossl_cfconv_fwd / _bwd_x / _bwd_w    [was PyG propagate, :190,194-195]
-  node-level Linear layers . cuBLAS through torch (plain library GEMMs)
+  node-level Linear layers . geossl_linear_tc / _wgrad_tc (tcgen05, fused bias / ssp / residual)  [was :99-101,165-166,189,191]
 When ``pos.requires_grad`` (force training, finetune_md17.py:32-54) the geometry and the filter MLP run as
 differentiable torch ops around the CFConvAggregate primitive, which is closed under differentiation.
 """

@@ -139,6 +139,7 @@ class GraphedMD17Step:
         self.args, self.model, self.lin, self.crit, self.opt, self.sync, self.coeffs = args, model, graph_pred_linear, criterion, optimizer, grad_sync, coeffs
         self.max_graphs = max_graphs
         self.graphs = {}
+        self.capture_error = None
         self.template = example_batch
 
     def _structure(self, batch):
@@ -189,9 +190,14 @@ class GraphedMD17Step:
         e = ge.num_edges
         entry = self.graphs.get(e)
         if entry is None:
-            if len(self.graphs) >= self.max_graphs:
+            if len(self.graphs) >= self.max_graphs or self.capture_error is not None:
                 return md17_train_step(self.args, batch, self.model, self.lin, self.crit, self.opt, grad_sync=self.sync, **self.coeffs)
-            entry = self.graphs[e] = self._capture(batch, ge)
+            try:
+                entry = self.graphs[e] = self._capture(batch, ge)
+            except RuntimeError as exc:                     # a refused capture is reported, and the step stays correct (eager)
+                self.capture_error = exc
+                torch.cuda.synchronize()
+                return md17_train_step(self.args, batch, self.model, self.lin, self.crit, self.opt, grad_sync=self.sync, **self.coeffs)
         graph, static, sg, loss = entry
         with torch.no_grad():
             static.x.copy_(batch.x, non_blocking=True)
