@@ -311,7 +311,7 @@ def run_product(args):
     n_k = min(args.steps, 10)
     timer_names = ("cfconv_fwd", "filter_fwd", "filter_bwd", "cfconv_bwd_x", "ddm_head_fwd", "ddm_head_bwd", "ddm_head_fused",
                    "linear_fwd", "linear_dgrad", "linear_wgrad", "painn_message_fwd", "painn_message_bwd", "dense_fwd", "dense_dgrad",
-                   "dense_wgrad")
+                   "dense_wgrad", "dense_chain_fwd", "dense_chain_bwd")
     if step is not eager_step:
         _lib.launch_count(reset=True)
         probe = GraphedTrainStep(targs, dev_pool[0], model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync, warmup=0,
@@ -477,12 +477,13 @@ def run_product(args):
                                       "frac": bb / tt / 1e9 / peaks["hbm_gbs"], "mean_ms": 1e3 * tt,
                                       "share_of_step": ktimes["cfconv_bwd_x"]["total_ms"] / n_k / (ms / args.steps)}
         roof["share_of_step"] = ktimes["cfconv_fwd"]["total_ms"] / n_k / (ms / args.steps)
-        for k in ("linear_fwd", "linear_dgrad", "linear_wgrad"):
+        for k in ("linear_fwd", "linear_dgrad", "linear_wgrad", "dense_chain_fwd", "dense_chain_bwd"):
             if k in ktimes:
                 tt = ktimes[k]["mean_ms"] / 1e3
                 others[k] = {"bound": "latency", "mean_ms": 1e3 * tt, "launches_per_step": ktimes[k]["n"] // n_k,
                              "share_of_step": ktimes[k]["total_ms"] / n_k / (ms / args.steps),
-                             "note": "128->128 atom-wise layer on tcgen05 (0.5 GFLOP per launch); linear_wgrad runs on the side stream"}
+                             "note": "128->128 atom-wise layers on tcgen05 (0.5 GFLOP per layer; dense_chain_* = 2-3 layers per launch); "
+                                     "linear_wgrad runs on the side stream"}
 
     # whole-step floor: every kernel at its own roofline, back to back (the kernels are serial on the critical path).
     # Tensor work is counted with the 3 split-precision MMAs per product the fp32-grade path issues.

@@ -190,6 +190,7 @@ class SchNet(torch.nn.Module):
         h = ops.embedding(self.embedding, z)
         if graph is None:
             graph = ops.radius_csr(pos, batch, self.cutoff, num_graphs=num_graphs)
+        fused = False
         if pos.requires_grad and torch.is_grad_enabled():
             ge = graph.exact()
             row, col = ge.src.long(), ge.tgt.long()
@@ -202,12 +203,29 @@ class SchNet(torch.nn.Module):
             for interaction in self.interactions:
                 layers += [interaction.conv.lin1, interaction.conv.lin2, interaction.lin]
             images = ops.prepack_linear_weights(layers)
-            for interaction in self.interactions:
-                h = interaction.forward_graph(h, graph, self.distance_expansion, residual=h, images=images)
+            blocks = list(self.interactions)
+            fused = h.size(1) == 128 and ops.chain_applies(layers, images) and len(blocks) > 0
+            if fused:
+                # one launch per interaction block for its three atom-wise layers (conv.lin2 -> ssp -> lin + residual -> the
+                # NEXT block's conv.lin1), one for the head; filter network + cfconv in between (ops.CFConvLayer)
+                x = ops.linear(h, blocks[0].conv.lin1, images=images)
+                for i, blk in enumerate(blocks):
+                    mlp = blk.conv.nn
+                    m = ops.CFConvLayer.apply(x, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias,
+                                              self.distance_expansion.offset, graph, self.distance_expansion.coeff, blk.conv.cutoff)
+                    nxt = blocks[i + 1].conv.lin1 if i + 1 < len(blocks) else None
+                    h, x = ops.InteractionTail.apply(m, h, blk.conv.lin2.weight, blk.conv.lin2.bias, blk.lin.weight, blk.lin.bias,
+                                                     None if nxt is None else nxt.weight, images[blk.conv.lin2], images[blk.lin],
+                                                     None if nxt is None else images[nxt])
+                h = ops.HeadChain.apply(h, self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias,
+                                        images[self.lin1], images[self.lin2])
+            else:
+                for interaction in self.interactions:
+                    h = interaction.forward_graph(h, graph, self.distance_expansion, residual=h, images=images)
 
         if pos.requires_grad and torch.is_grad_enabled():
             h = self.lin2(self.act(self.lin1(h)))
-        else:
+        elif not fused:
             h = ops.linear(ops.linear(h, self.lin1, images=images), self.lin2, pre_ssp=True, images=images)
 
         n_graphs = graph.graph_ptr.numel() - 1

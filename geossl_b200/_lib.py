@@ -31,6 +31,11 @@ class DdmPtrs(ctypes.Structure):
                                    "out_w2", "out_b2")]
 
 
+class ChainStage(ctypes.Structure):
+    """geossl_chain_stage (include/geossl_b200.h)."""
+    _fields_ = [("weight_image", c_p), ("bias", c_p), ("act_grad_input", c_p), ("residual", c_p), ("store", c_p), ("act_next", c_int)]
+
+
 ABI_VERSION = 3          # must equal GEOSSL_ABI_VERSION in include/geossl_b200.h
 
 _SIGNATURES = {
@@ -67,6 +72,7 @@ _SIGNATURES = {
     "geossl_linear_tc_block": (c_int, [c_p, c_i64, c_i64, c_p, c_p, c_int, c_int, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_int, c_int, c_p]),
     "geossl_linear_wgrad_tc_block": (c_int, [c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_int, c_p, c_int, c_p]),
     "geossl_linear_tc": (c_int, [c_p, c_i64, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p]),
+    "geossl_linear_chain_tc": (c_int, [c_p, c_i64, ctypes.POINTER(ChainStage), c_int, c_int, c_int, c_p]),
     "geossl_linear_wgrad_tc_workspace": (c_i64, [c_i64]),
     "geossl_linear_wgrad_tc": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
     "geossl_pair_distance": (c_int, [c_p, c_p, c_i64, c_p, c_p]),

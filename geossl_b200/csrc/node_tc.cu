@@ -239,6 +239,171 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
     trace_l(7);
 }
 
+// ------------------------------------------------------------------------------------------ chained layers
+// Several 128 -> 128 layers applied to the SAME row tile without leaving the SM.  An interaction block of SchNet applies
+// conv.lin2 -> ssp -> lin (+ residual) and then the next block's conv.lin1 to every atom row (schnet.py:191,165-166,97,189);
+// the head applies lin1 -> ssp -> lin2 (:99-101).  As separate launches each of these ~0.5 GFLOP layers is latency bound
+// (launch + weight fetch + row staging + one MMA burst + store: 12 us inside the step for ~1 us of tensor work).  Here the
+// row tile is staged once, each stage's accumulator is read back from TMEM, finished (bias / activation gradient / residual),
+// optionally stored, and written straight back into shared memory as the next stage's operand (paired 4-byte stores,
+// tc.cuh), while the weight images stream through a two-slot ring of bulk copies.  The data-gradient chain of the backward
+// pass (next lin1^T -> + residual gradient -> lin^T -> * sigmoid(y1) -> lin2^T) is the same kernel with transposed images.
+struct ChainStage {
+    const uint8_t* w_image;   // packed weight image (orientation / parts chosen when it was packed)
+    const float* bias;        // NULL or (128)
+    const float* z;           // NULL or (n_rows,128): v *= act'(z)
+    const float* residual;    // NULL or (n_rows,128): v += residual
+    float* store;             // NULL or (n_rows,128): store = v
+    int act_next;             // 0 | kActSsp | kActSilu: activation applied to v before it becomes the next stage's operand
+};
+constexpr int kMaxChain = 4;
+struct ChainArgs { ChainStage st[kMaxChain]; int n; };
+
+struct ChainLayout {
+    static constexpr int NR = 128;
+    static constexpr int W = 0;                       // two slots x (hi 2 k-blocks | lo 2 k-blocks)   128 KB
+    static constexpr int X = W + 2 * kWImage;         // hi (2 k-blocks) | lo (2 k-blocks)             64 KB
+    static constexpr int BAR = X + 4 * NR * 128;      // [0] MMA done, [1..2] weight slot landed
+    static constexpr int TMEM_PTR = BAR + 32;
+    static constexpr int kBytes = TMEM_PTR + 16;
+};
+static_assert(ChainLayout::kBytes + 1024 <= 227 * 1024, "shared memory budget");
+
+template <bool FP16>
+__global__ void __launch_bounds__(512, 1)
+linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs args, int act) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    using L = ChainLayout;
+    constexpr int NR = L::NR, kBlkT = NR * 128;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar = sbase + L::BAR;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 8, 1);
+        mbar_init(bar + 16, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(sbase + L::TMEM_PTR, NR);
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR);
+    const uint32_t idesc = idesc_f16(Split<FP16>::kFmt, 128, NR);
+    const int q = warp & 3, eh = warp >> 2, f = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int n_st = args.n;
+
+    auto fetch_weights = [&](int stage, int slot) {           // one thread: 64 KB image -> ring slot, completion on its mbarrier
+        mbar_expect_tx(bar + 8 + 8 * slot, kWImage);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bulk_g2s(sbase + L::W + slot * kWImage + c * kNBlkW, args.st[stage].w_image + c * kNBlkW, kNBlkW, bar + 8 + 8 * slot);
+    };
+
+    const int64_t n_tiles = (n_rows + NR - 1) / NR;
+    uint32_t mma_phase = 0, w_uses[2] = {0, 0};
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t row0 = t * NR;
+        const bool full = row0 + NR <= n_rows;
+        if (tid == 0) {
+            fetch_weights(0, 0);
+            if (n_st > 1) fetch_weights(1, 1);
+        }
+        stage_rows_kmajor<FP16, NR>(X, 128, row0, n_rows, 0, smem + L::X, smem + L::X + 2 * kBlkT);
+        const int64_t erow = row0 + eh * 32;
+        for (int s = 0; s < n_st; ++s) {
+            const ChainStage& S = args.st[s];
+            const int slot = s & 1;
+            // epilogue operands that do not depend on the MMA: fetched now, their latency hides behind it
+            float zr[32], rr[32];
+            const bool has_z = S.z != nullptr, has_r = S.residual != nullptr;
+            if (has_z) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) zr[j] = (full || erow + j < n_rows) ? __ldg(S.z + (erow + j) * 128 + f) : 0.f;
+            }
+            if (has_r) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rr[j] = (full || erow + j < n_rows) ? __ldg(S.residual + (erow + j) * 128 + f) : 0.f;
+            }
+            const float bf = S.bias ? __ldg(S.bias + f) : 0.f;
+            fence_proxy_async();
+            __syncthreads();                                    // operand tile of this stage is complete
+            if (warp == 0) {
+                mbar_wait(bar + 8 + 8 * slot, w_uses[slot] & 1);
+                tc_fence_after();
+                const uint32_t wb = sbase + L::W + slot * kWImage;
+                const uint64_t wh = desc_k_sw128(wb), wl = desc_k_sw128(wb + 2 * kNBlkW);
+                const uint64_t xh = desc_k_sw128(sbase + L::X), xl = desc_k_sw128(sbase + L::X + 2 * kBlkT);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kBlkT >> 4) + 2 * (ks & 3);
+                        mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, ks > 0);
+                    }
+                    tc_commit(bar);
+                }
+                __syncwarp();
+            }
+            ++w_uses[slot];
+            mbar_wait(bar, mma_phase);
+            mma_phase ^= 1;
+            tc_fence_after();
+            // the MMAs have consumed this slot's image and the operand tile: refill the slot two stages ahead
+            if (tid == 0 && s + 2 < n_st) fetch_weights(s + 2, slot);
+            float v[32];
+            tmem_ld32(tmem + lane_base + eh * 32, v);              // lane = output feature f, columns = rows eh*32..+31
+            tc_fence_before();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float y = v[j] + bf;
+                if (has_z) y *= act_grad(zr[j], act);
+                if (has_r) y += rr[j];
+                v[j] = y;
+            }
+            if (S.store != nullptr) {
+                float* out = S.store + erow * 128 + f;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) out[j * 128] = v[j];  // 128 contiguous bytes per warp store
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (erow + j < n_rows) out[j * 128] = v[j];
+                }
+            }
+            if (s + 1 < n_st) {
+                // next stage's operand: element (row = eh*32 + j, k = f) of the K-major tile
+                if (S.act_next) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (full || erow + j < n_rows) ? act_fwd(v[j], S.act_next) : 0.f;
+                } else if (!full) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (erow + j < n_rows) ? v[j] : 0.f;
+                }
+                uint8_t* hi = smem + L::X + (f >> 6) * kBlkT;
+                uint8_t* lo = hi + 2 * kBlkT;
+                float half[16];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) half[j] = v[h2 * 16 + j];
+                    store_split16_paired<FP16>(hi, lo, eh * 32 + h2 * 16, f & 63, half, lane);
+                }
+            }
+        }
+        __syncthreads();                                           // TMEM / tile / barrier reuse by the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem, NR);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ weight gradient
 struct WgLayout {
     static constexpr int DY = 0;                      // [64 r][128 o] hi (2 MN blocks) | lo                32 KB
@@ -519,6 +684,47 @@ int geossl_linear_tc_block(const float* x, int64_t ldx, int64_t n_rows, const vo
     GEOSSL_REQUIRE(act == tc::kActSsp || act == tc::kActSilu || !(pre_act || act_grad_input), "act must be 1 (ssp) or 2 (silu)");
     return linear_tc_dispatch(x, n_rows, (const uint8_t*)weight_image, bias, pre_act, act_grad_input, residual, y, bf16_parts,
                               ldx, ldz, ldr, ldy, act, k_cols, as_stream(stream));
+}
+
+int geossl_linear_chain_tc(const float* x, int64_t n_rows, const geossl_chain_stage* stages, int n_stages, int bf16_parts, int act,
+                           void* stream) {
+    if (n_rows == 0) return 0;
+    GEOSSL_REQUIRE(x && stages && n_rows > 0, "null pointer");
+    GEOSSL_REQUIRE(n_stages >= 1 && n_stages <= tc::kMaxChain, "1..4 stages");
+    GEOSSL_REQUIRE(act == tc::kActSsp || act == tc::kActSilu, "act must be 1 (ssp) or 2 (silu)");
+    tc::ChainArgs a;
+    a.n = n_stages;
+    for (int i = 0; i < n_stages; ++i) {
+        GEOSSL_REQUIRE(stages[i].weight_image != nullptr, "stage without a weight image");
+        GEOSSL_REQUIRE(stages[i].act_next >= 0 && stages[i].act_next <= 2, "act_next must be 0, 1 or 2");
+        a.st[i].w_image = (const uint8_t*)stages[i].weight_image;
+        a.st[i].bias = stages[i].bias;
+        a.st[i].z = stages[i].act_grad_input;
+        a.st[i].residual = stages[i].residual;
+        a.st[i].store = stages[i].store;
+        a.st[i].act_next = stages[i].act_next;
+    }
+    GEOSSL_REQUIRE(stages[n_stages - 1].store != nullptr, "the last stage must store its result");
+    const size_t smem = tc::ChainLayout::kBytes + 1024;
+    const int64_t tiles = (n_rows + 127) / 128;
+    const dim3 grid((unsigned)(tiles < kNumSM ? tiles : kNumSM));
+    if (bf16_parts) {
+        static PerDeviceFlag configured;
+        if (!configured.get()) {
+            GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured.set();
+        }
+        GEOSSL_CUDA(launch_pdl(tc::linear_chain_tc_kernel<false>, grid, dim3(512), smem, as_stream(stream), x, n_rows, a, act));
+    } else {
+        static PerDeviceFlag configured;
+        if (!configured.get()) {
+            GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured.set();
+        }
+        GEOSSL_CUDA(launch_pdl(tc::linear_chain_tc_kernel<true>, grid, dim3(512), smem, as_stream(stream), x, n_rows, a, act));
+    }
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
 }
 
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::wgrad_grid(n_rows) * tc::kWgPart; }

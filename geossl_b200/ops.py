@@ -528,6 +528,40 @@ def join_side_stream():
             param.grad.add_(buf)
 
 
+def _linear_wgrad(gy, x, pre_ssp, wp, bp):
+    """Weight / bias gradient of one 128 -> 128 layer (geossl_linear_wgrad_tc): dW = gy^T [ssp](x), db = colsum(gy).
+    Inside ``side_stream_wgrads()`` (and for leaf parameters) the kernels run on the side stream and the results are handed to
+    ``join_side_stream()`` instead of autograd: returns (None, None) then."""
+    lib = _lib.load()
+    n = x.size(0)
+
+    def wgrad():
+        gw_ = torch.empty((128, 128), dtype=torch.float32, device=x.device)
+        gb_ = torch.empty(128, dtype=torch.float32, device=x.device) if bp is not None else None
+        ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
+        _timed("linear_wgrad", lambda: lib.geossl_linear_wgrad_tc(_p(gy), _p(x), n, 1 if pre_ssp else 0, _p(ws), _p(gw_),
+                                                                  _p(gb_), _stream()))
+        return gw_, gb_
+
+    deferrable = wp.is_leaf and wp.requires_grad and (bp is None or (bp.is_leaf and bp.requires_grad))
+    if _SIDE["on"] and deferrable:
+        main, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            gw, gb = wgrad()
+        for t in (gy, x):
+            t.record_stream(side)
+        for t in (gw, gb):
+            if t is not None:
+                t.record_stream(main)
+        _SIDE["dirty"] = True
+        _SIDE["pending"].append((wp, gw))
+        if gb is not None:
+            _SIDE["pending"].append((bp, gb))
+        return None, None                  # handed to join_side_stream(), not to autograd
+    return wgrad()
+
+
 class LinearTC(torch.autograd.Function):
     """y = [ssp](x) @ W^T + b [+ residual] for 128 -> 128 atom-wise layers (geossl_linear_tc / _wgrad_tc).
     Forward operands are split into fp16 parts, gradient operands into bf16 parts (see tc.cuh)."""
@@ -561,36 +595,112 @@ class LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = _linear_tc(gy, weight, True, None, False, x if ctx.pre_ssp else None, None, True, "linear_dgrad", ctx.image_t)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            lib = _lib.load()
-
-            def wgrad():
-                gw_ = torch.empty_like(weight)
-                gb_ = torch.empty(128, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-                ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
-                _timed("linear_wgrad", lambda: lib.geossl_linear_wgrad_tc(_p(gy), _p(x), n, 1 if ctx.pre_ssp else 0, _p(ws), _p(gw_),
-                                                                          _p(gb_), _stream()))
-                return gw_, gb_
-
-            wp, bp = ctx.params
-            deferrable = wp.is_leaf and wp.requires_grad and (bp is None or (bp.is_leaf and bp.requires_grad))
-            if _SIDE["on"] and deferrable:
-                main, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    gw, gb = wgrad()
-                for t in (gy, x):
-                    t.record_stream(side)
-                for t in (gw, gb):
-                    if t is not None:
-                        t.record_stream(main)
-                _SIDE["dirty"] = True
-                _SIDE["pending"].append((wp, gw))
-                if gb is not None:
-                    _SIDE["pending"].append((bp, gb))
-                gw = gb = None                  # handed to join_side_stream(), not to autograd
-            else:
-                gw, gb = wgrad()
+            gw, gb = _linear_wgrad(gy, x, ctx.pre_ssp, *ctx.params)
         return gx, gw, gb, (gy if ctx.has_res else None), None, None
+
+
+# The three atom-wise layers between two cfconv aggregations (conv.lin2 -> ssp -> lin (+ residual) -> next conv.lin1) and the
+# head (lin1 -> ssp -> lin2) run as ONE launch each (geossl_linear_chain_tc): the row tile never leaves the SM between the
+# GEMMs.  False restores one launch per layer (ops.linear).
+FUSE_DENSE_CHAIN = True
+
+
+def _chain(x, stages, bf16_parts, name):
+    """stages: [(weight_image, bias, act_grad_input, residual, store, act_next)]; runs geossl_linear_chain_tc over x (n,128)."""
+    arr = (_lib.ChainStage * len(stages))()
+    for a, (img, bias, z, res, store, act_next) in zip(arr, stages):
+        a.weight_image, a.bias, a.act_grad_input = img.data_ptr(), (bias.data_ptr() if bias is not None else None), \
+            (z.data_ptr() if z is not None else None)
+        a.residual, a.store, a.act_next = (res.data_ptr() if res is not None else None), \
+            (store.data_ptr() if store is not None else None), act_next
+    _timed(name, lambda: _lib.load().geossl_linear_chain_tc(_p(x), x.size(0), arr, len(stages), 1 if bf16_parts else 0, ACT_SSP, _stream()))
+
+
+class InteractionTail(torch.autograd.Function):
+    """(m, h) -> (h', x'):  y1 = m W2^T + b2;  h' = h + ssp(y1) W3^T + b3;  x' = h' W1n^T  (x' only when the next block's
+    conv.lin1 weight W1n is given) -- schnet.py:191,165-166,97,189 in one launch.  y1 is kept for the backward, which is one
+    launch too: g = g_x' W1n + g_h';  g_y1 = (g W3) * sigmoid(y1);  g_m = g_y1 W2;  the weight gradients are three
+    geossl_linear_wgrad_tc launches (side stream inside ``side_stream_wgrads()``)."""
+
+    @staticmethod
+    def forward(ctx, m, h, w2, b2, w3, b3, w1n, img2, img3, img1n):
+        m, h = _req(m, torch.float32, "m", 2), _req(h, torch.float32, "h", 2)
+        n = m.size(0)
+        y1, h_next = torch.empty_like(m), torch.empty_like(m)
+        x_next = torch.empty_like(m) if w1n is not None else None
+        stages = [(img2[0], b2, None, None, y1, ACT_SSP), (img3[0], b3, None, h, h_next, ACT_NONE)]
+        if w1n is not None:
+            stages.append((img1n[0], None, None, None, x_next, ACT_NONE))
+        if n:
+            _chain(m, stages, False, "dense_chain_fwd")
+        ctx.imgs = (img2, img3, img1n)
+        ctx.params = ((w2, b2), (w3, b3), (w1n, None))
+        ctx.save_for_backward(m, y1, h_next)
+        return h_next, x_next
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_hn, g_xn):
+        m, y1, h_next = ctx.saved_tensors
+        img2, img3, img1n = ctx.imgs
+        (w2, b2), (w3, b3), (w1n, _) = ctx.params
+        n = m.size(0)
+        if g_hn is None:
+            g_hn = torch.zeros_like(m)
+        g_hn = g_hn.contiguous()
+        g_y1, g_m = torch.empty_like(m), torch.empty_like(m)
+        if w1n is not None and g_xn is not None:
+            g_xn = g_xn.contiguous()
+            g_tot = torch.empty_like(m)
+            stages = [(img1n[1], None, None, g_hn, g_tot, ACT_NONE), (img3[1], None, y1, None, g_y1, ACT_NONE),
+                      (img2[1], None, None, None, g_m, ACT_NONE)]
+            x0 = g_xn
+        else:
+            g_tot = g_hn
+            stages = [(img3[1], None, y1, None, g_y1, ACT_NONE), (img2[1], None, None, None, g_m, ACT_NONE)]
+            x0 = g_hn
+        if n:
+            _chain(x0, stages, True, "dense_chain_bwd")
+        gw1n = None
+        if w1n is not None and g_xn is not None and n:
+            gw1n, _ = _linear_wgrad(g_xn, h_next, False, w1n, None)
+        gw3, gb3 = _linear_wgrad(g_tot, y1, True, w3, b3) if n else (torch.zeros_like(w3), torch.zeros_like(b3))
+        gw2, gb2 = _linear_wgrad(g_y1, m, False, w2, b2) if n else (torch.zeros_like(w2), torch.zeros_like(b2))
+        return g_m, g_tot, gw2, gb2, gw3, gb3, gw1n, None, None, None
+
+
+class HeadChain(torch.autograd.Function):
+    """out = ssp(h W1^T + b1) W2^T + b2  (schnet.py:99-101) in one launch; backward: g_z = (g W2) * sigmoid(z), g_h = g_z W1."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, w2, b2, img1, img2):
+        h = _req(h, torch.float32, "h", 2)
+        z, out = torch.empty_like(h), torch.empty_like(h)
+        if h.size(0):
+            _chain(h, [(img1[0], b1, None, None, z, ACT_SSP), (img2[0], b2, None, None, out, ACT_NONE)], False, "dense_chain_fwd")
+        ctx.imgs, ctx.params = (img1, img2), ((w1, b1), (w2, b2))
+        ctx.save_for_backward(h, z)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        h, z = ctx.saved_tensors
+        img1, img2 = ctx.imgs
+        (w1, b1), (w2, b2) = ctx.params
+        g = g.contiguous()
+        g_z, g_h = torch.empty_like(h), torch.empty_like(h)
+        if not h.size(0):
+            return g_h, torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2), torch.zeros_like(b2), None, None
+        _chain(g, [(img2[1], None, z, None, g_z, ACT_NONE), (img1[1], None, None, None, g_h, ACT_NONE)], True, "dense_chain_bwd")
+        gw2, gb2 = _linear_wgrad(g, z, True, w2, b2)
+        gw1, gb1 = _linear_wgrad(g_z, h, False, w1, b1)
+        return g_h, gw1, gb1, gw2, gb2, None, None
+
+
+def chain_applies(layers, images):
+    """True when every layer of the list has packed tensor-core images (128 -> 128, tensor-core mode) and fusion is on."""
+    return bool(FUSE_DENSE_CHAIN and images) and all(l in images for l in layers)
 
 
 def linear_tc_applies(layer):

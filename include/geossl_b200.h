@@ -222,6 +222,23 @@ int geossl_linear_tc_block(const float* x, int64_t ldx, int64_t n_rows, const vo
 int geossl_linear_wgrad_tc_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act,
                                  float* workspace, float* grad_weight, int ld_gw, float* grad_bias, int x_cols, void* stream);
 
+/* Up to four 128 -> 128 layers applied to the same row tile without leaving the SM (an interaction block's
+ * conv.lin2 -> ssp -> lin (+ residual) -> next conv.lin1, schnet.py:191,165-166,97,189; the head lin1 -> ssp -> lin2, :99-101;
+ * and the data-gradient chains of their backward with transposed images).  Stage s computes
+ *   v = operand_s . W_s^T + bias_s;  v *= act'(act_grad_input_s);  v += residual_s;  store_s = v;  operand_{s+1} = act_next_s(v)
+ * with every optional piece NULL / 0 when absent; operand_0 = x (n_rows,128).  act selects the activation family of
+ * act' (1 = shifted softplus, 2 = SiLU); act_next is 0 (identity), 1 or 2 per stage.  The last stage must store. */
+typedef struct {
+    const void* weight_image;      /* packed by geossl_pack_weight(s_batched) with the orientation / parts this stage needs */
+    const float* bias;             /* (128) or NULL */
+    const float* act_grad_input;   /* (n_rows,128) or NULL */
+    const float* residual;         /* (n_rows,128) or NULL */
+    float* store;                  /* (n_rows,128) or NULL */
+    int act_next;
+} geossl_chain_stage;
+int geossl_linear_chain_tc(const float* x, int64_t n_rows, const geossl_chain_stage* stages /*host*/, int n_stages, int bf16_parts,
+                           int act, void* stream);
+
 /* grad_weight[o][i] = sum_r grad_y[r][o] * pre(x[r][i]);  grad_bias[o] = sum_r grad_y[r][o] (may be NULL). */
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows);
 int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, int pre_ssp, float* workspace,

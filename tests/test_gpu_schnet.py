@@ -309,3 +309,29 @@ def test_graphed_md17_step_equals_eager_loss():
         del ref
     assert step.capture_error is None, step.capture_error
     assert len(step.graphs) == 1
+
+
+@pytest.mark.parametrize("n_graphs,lo,hi", [(7, 5, 40), (1, 1, 1), (40, 30, 30)])
+def test_fused_dense_chain_equals_layer_by_layer(n_graphs, lo, hi):
+    """geossl_linear_chain_tc (conv.lin2 -> ssp -> lin + residual -> next conv.lin1 and the head in one launch each, forward
+    and data-gradient chains) against one launch per layer: same representations and parameter gradients to fp32 round-off of
+    the split-precision MMAs, including ragged last tiles and a single-atom graph."""
+    from geossl_b200.Geom3D.models import SchNet
+    torch.manual_seed(3)
+    m = SchNet(hidden_channels=128, num_filters=128, num_interactions=3, num_gaussians=50, cutoff=10.0, node_class=9).to(DEV)
+    b = synthetic_batch(n_graphs, lo, hi if hi > lo else None, seed=2, with_pairs=False).to(DEV)
+    w = torch.randn(b.positions.size(0), 128, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    res = {}
+    old = ops.FUSE_DENSE_CHAIN
+    try:
+        for fused in (True, False):
+            ops.FUSE_DENSE_CHAIN = fused
+            m.zero_grad(set_to_none=True)
+            out, h = m(b.x[:, 0].contiguous(), b.positions, b.batch, return_latent=True, num_graphs=n_graphs)
+            ((h * w).sum() + out.sum()).backward()
+            res[fused] = (h.detach().clone(), {k: v.clone() for k, v in grads_of(m).items()})
+    finally:
+        ops.FUSE_DENSE_CHAIN = old
+    assert rel_err(res[True][0], res[False][0]) <= 2e-6
+    for k in res[False][1]:
+        assert rel_err(res[True][1][k], res[False][1][k]) <= 2e-5, (k, rel_err(res[True][1][k], res[False][1][k]))
