@@ -293,7 +293,7 @@ def run_product(args):
     if not args.no_graph:
         graphed = GraphedTrainStep(targs, dev_pool[0], model, heads, opt, 0.0, CFG["pos_sigma"], grad_sync=sync)
         step = graphed
-        for i in range(2):
+        for i in range(max(10, args.warmup)):                # replays of the captured graph are part of the warm-up too
             step(dev_pool[i % args.pool])
         barrier()
 
