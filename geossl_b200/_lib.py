@@ -68,6 +68,9 @@ _SIGNATURES = {
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "geossl_weight_image_bytes": (c_i64, []),
     "geossl_pack_weight": (c_int, [c_p, c_int, c_int, c_p, c_p]),
+    "geossl_pack_weight_ld": (c_int, [c_p, c_int, c_int, c_int, c_p, c_p]),
+    "geossl_pack_weight_pair": (c_int, [c_p, c_int, c_p, c_p]),
+    "geossl_ddm_workspace_fused": (c_i64, [c_i64, c_i64]),
     "geossl_pack_weights_batched": (c_int, [c_p, c_p, c_int, c_p, c_p]),
     "geossl_linear_tc_block": (c_int, [c_p, c_i64, c_i64, c_p, c_p, c_int, c_int, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_int, c_int, c_p]),
     "geossl_linear_wgrad_tc_block": (c_int, [c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_int, c_p, c_int, c_p]),

@@ -549,6 +549,7 @@ int geossl_pair_distance(const float* pos, const int64_t* sei, int64_t n_pairs, 
 int64_t geossl_ddm_workspace(int H) { return head_workspace(H); }
 
 static int64_t head_pad(int64_t n_pairs) { return (n_pairs + 63) / 64 * 64; }
+constexpr int kPrepRowsHost = 8;          // == tc::kPrepRows (rows of per-pair scalars in the workspace)
 static int64_t head_loss_offset() { return (head_workspace(128) + 63) / 64 * 64; }            // fused mode: 2 floats per CTA
 static int64_t head_prep_offset() { return head_loss_offset() + (2 * kNumSM + 63) / 64 * 64; }
 // parameter partial sums | loss partials (fused mode) | per-pair scalars (8 rows of n_pairs rounded up to the tile size)
@@ -747,7 +748,13 @@ template <bool FP16, bool BWD>
 __global__ void __launch_bounds__(kHThreads, 1)
 ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, const float* __restrict__ loss_aux,
                    const float* __restrict__ grad_loss, float* __restrict__ grad_h, float* __restrict__ workspace,
-                   float* __restrict__ loss_part) {
+                   float* __restrict__ loss_part, const float* __restrict__ projA, float* __restrict__ gradA) {
+    // Atom-projected mode (projA != NULL; one-pass training path): the first layer of the score MLP is linear in
+    // feat_p = h[u_p] + h[v_p], so W0[:, :128] . feat_p = A[u_p] + A[v_p] with A = h W0[:, :128]^T computed once per ATOM
+    // by the dense-layer kernel (7.7 k rows instead of 111 k pairs).  MMA1 becomes a gather-add in E1, MMA4 + E4 (dfeat per
+    // pair, scattered to both atoms) become a scatter of dz1 into gradA followed by one per-atom GEMM dh = gradA W0[:, :128],
+    // and WG0 becomes the per-atom weight gradient gradA^T h: three of the six MMA groups and the feat tile leave this kernel.
+    const bool proj = BWD && projA != nullptr;
     using K = HeadCfg<128>;
     using L = HeadSmem;
     extern __shared__ uint8_t smem_raw[];
@@ -765,7 +772,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
     float* sRed = reinterpret_cast<float*>(smem + L::RED);
 
     // ---- weights: W0[:, :128] rows n, W1 rows n2 (K-major images, split)
-    for (int idx = tid; idx < 128 * 16; idx += kHThreads) {
+    for (int idx = tid; idx < (proj ? 0 : 128 * 16); idx += kHThreads) {
         const int n = idx >> 4, c = idx & 15;
         float v[8];
 #pragma unroll
@@ -849,7 +856,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
             mbar_wait(bar_wg, phase_wg); phase_wg ^= 1;
             tc_fence_after();
         }
-        {
+        if (!proj) {
             const int cg = tid & 15, ro = tid >> 4;             // 8 columns 8cg.., rows ro and ro + 32
 #pragma unroll
             for (int s2 = 0; s2 < 2; ++s2) {
@@ -868,7 +875,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
         __syncthreads();
         trace_h(done, 3);
         // ---- 2. MMA1: D1^T = W0h . feat^T
-        if (warp == 0) {                                      // uniform operands; the elected lane issues
+        if (!proj && warp == 0) {                             // uniform operands; the elected lane issues
             tc_fence_after();
             if (elect_one_sync()) {
                 const uint64_t ah = desc_k_sw128(sbase + L::W0), al = desc_k_sw128(sbase + L::W0 + 2 * kHBlkW);
@@ -882,14 +889,27 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
             }
             __syncwarp();
         }
-        mbar_wait(bar, phase); phase ^= 1;
-        tc_fence_after();
+        if (!proj) {
+            mbar_wait(bar, phase); phase ^= 1;
+            tc_fence_after();
+        }
         trace_h(done, 4);
         // ---- 3. E1: z1 = relu(D1^T + emb_p * wl + b0) -> Z1 tile [p][n]
         uint32_t mask1 = 0;
         {
             float v[16];
-            tmem_ld16(tD1 + lane_base + col0, v);
+            if (!proj) {
+                tmem_ld16(tD1 + lane_base + col0, v);
+            } else {                                           // lanes = hidden units: 128 contiguous bytes per warp load
+                float au[16], av[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    au[j] = __ldg(projA + (int64_t)sU[col0 + j] * 128 + Ln);
+                    av[j] = __ldg(projA + (int64_t)sV[col0 + j] * 128 + Ln);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = (au[j] + av[j]) * sValid[col0 + j];
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 v[j] = fmaxf(fmaf(sEmb[col0 + j], wl, v[j]) + b0n, 0.f);
@@ -973,6 +993,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
                 const uint64_t dh = desc_mn_sw128(sbase + L::DZ2, kHBlkT), dl = desc_mn_sw128(sbase + L::DZ2 + kHBlkT, kHBlkT);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) mma3(tDW1, zh + ks * 128, zl + ks * 128, dh + ks * 128, dl + ks * 128, id_wg1, (done | ks) > 0);
+                if (proj) tc_commit(bar_wg);                   // (no WG0 in this mode: WG1 alone retires behind the critical path)
             }
             __syncwarp();
         }
@@ -991,7 +1012,28 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
                 a_dwl = fmaf(v[j], sEmb[col0 + j], a_dwl);
                 pd[j] = v[j] * wl;
             }
-            store_split16_paired<FP16>(smem + L::DZ1 + (Ln >> 6) * kHBlkT, smem + L::DZ1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0, Ln & 63, v, lane);
+            if (!proj) {
+                store_split16_paired<FP16>(smem + L::DZ1 + (Ln >> 6) * kHBlkT, smem + L::DZ1 + 2 * kHBlkT + (Ln >> 6) * kHBlkT, col0, Ln & 63, v, lane);
+            } else {
+                // d/dA[u_p] = d/dA[v_p] = dz1_p: coalesced RED (lanes = hidden units), runs of equal first atom collapsed
+                int cur_u = -1;
+                float run = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (sValid[col0 + j] != 0.f) {
+                        const int uj = sU[col0 + j];
+                        atomicAdd(gradA + (int64_t)sV[col0 + j] * 128 + Ln, v[j]);
+                        if (uj != cur_u) {
+                            if (cur_u >= 0) atomicAdd(gradA + (int64_t)cur_u * 128 + Ln, run);
+                            cur_u = uj;
+                            run = v[j];
+                        } else {
+                            run += v[j];
+                        }
+                    }
+                }
+                if (cur_u >= 0) atomicAdd(gradA + (int64_t)cur_u * 128 + Ln, run);
+            }
             const float tot = warp_reduce16(pd, lane);
             if ((lane & 1) == 0) sRed[q * 64 + col0 + reduce16_index(lane)] = tot;
         }
@@ -1000,7 +1042,7 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
         __syncthreads();
         trace_h(done, 10);
         // ---- 8. MMA4: D4^T = W0h^T . dz1^T (A = MN-major view of the W0 image, K = 128) ; WG0: DW0 += dz1^T feat
-        if (warp == 0) {                                      // uniform operands; the elected lane issues
+        if (!proj && warp == 0) {                             // uniform operands; the elected lane issues
             tc_fence_after();
             if (elect_one_sync()) {
                 const uint64_t ah = desc_mn_sw128(sbase + L::W0, kHBlkW), al = desc_mn_sw128(sbase + L::W0 + 2 * kHBlkW, kHBlkW);
@@ -1020,12 +1062,14 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
             __syncwarp();
         }
         if (tid < kHP) sDemb[tid] = sRed[tid] + sRed[64 + tid] + sRed[128 + tid] + sRed[192 + tid];
-        mbar_wait(bar, phase); phase ^= 1;
-        tc_fence_after();
+        if (!proj) {
+            mbar_wait(bar, phase); phase ^= 1;
+            tc_fence_after();
+        }
         __syncthreads();
         trace_h(done, 11);
         // ---- 9. E4: scatter dfeat to both endpoints (lanes = features: 128 contiguous bytes per warp instruction)
-        {
+        if (!proj) {
             float v[16];
             tmem_ld16(tD4 + lane_base + col0, v);
             // consecutive pairs of a molecule share their first atom (itertools order): one RED per run of equal u
@@ -1091,9 +1135,9 @@ ddm_head_tc_kernel(HeadIn in, const float* __restrict__ prep, int64_t n_pad, con
         tc_fence_after();
         {   // DW0 [n][k]: lane n, this warp's column group covers k = cg4*32 .. +31
             float v[32];
-            if (done > 0) tmem_ld32(tDW0 + lane_base + cg4 * 32, v);
+            if (done > 0 && !proj) tmem_ld32(tDW0 + lane_base + cg4 * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ws[K::pW0 + Ln * K::LD + cg4 * 32 + j] = done > 0 ? v[j] : 0.f;
+            for (int j = 0; j < 32; ++j) ws[K::pW0 + Ln * K::LD + cg4 * 32 + j] = (done > 0 && !proj) ? v[j] : 0.f;   // (proj: per-atom wgrad)
         }
         {   // DW1^T [n][n2] -> pW1 [n2][n]
             float v[16];
@@ -1187,7 +1231,7 @@ int geossl_ddm_head_fwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(tc::ddm_head_tc_kernel<true, false>, dim3(grid), dim3(tc::kHThreads), smem, as_stream(stream), in,
                            (const float*)prep, n_pad, (const float*)nullptr, (const float*)nullptr, (float*)nullptr, workspace,
-                           (float*)nullptr));
+                           (float*)nullptr, (const float*)nullptr, (float*)nullptr));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(ddm_loss_finalize_kernel, dim3(1), dim3(32), 0, as_stream(stream), (const float*)workspace, grid, loss));
     GEOSSL_LAUNCH_CHECK();
@@ -1221,7 +1265,8 @@ int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* ba
     GEOSSL_CUDA(launch_pdl(tc::ddm_pair_prep_kernel, dim3((unsigned)((n_pad + 255) / 256)), dim3(256), 0, as_stream(stream), in, n_pad, prep));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(tc::ddm_head_tc_kernel<false, true>, dim3(grid), dim3(tc::kHThreads), smem, as_stream(stream), in,
-                           (const float*)prep, n_pad, loss_aux, grad_loss, grad_h, workspace, (float*)nullptr));
+                           (const float*)prep, n_pad, loss_aux, grad_loss, grad_h, workspace, (float*)nullptr,
+                           (const float*)nullptr, (float*)nullptr));
     GEOSSL_LAUNCH_CHECK();
     const int n = HeadCfg<128>::kPartial;
     GEOSSL_CUDA(launch_pdl(ddm_head_reduce_kernel<128>, dim3((n + 255) / 256), dim3(256), 0, as_stream(stream), (const float*)workspace, grid, g));
@@ -1249,22 +1294,41 @@ int geossl_ddm_head_fwd_bwd_tc(const float* h, const int64_t* sei, const int64_t
         configured.set();
     }
     cudaStream_t st = as_stream(stream);
-    GEOSSL_CUDA(cudaMemsetAsync(grad_h, 0, sizeof(float) * (size_t)n_atoms * 128, st));
     const int grid = head_grid(n_pairs);
     const int64_t n_pad = head_pad(n_pairs);
     float* prep = workspace + head_prep_offset();
     float* loss_part = workspace + head_loss_offset();
+    // atom-projected first layer (see the kernel): A = h W0[:, :128]^T per atom, gradA scattered per pair, then per atom
+    // grad_h = gradA W0[:, :128] and dW0[:, :128] = gradA^T h
+    float* projA = prep + kPrepRowsHost * n_pad + 64;
+    float* gradA = projA + (size_t)n_atoms * 128;
+    uint8_t* images = reinterpret_cast<uint8_t*>(gradA + (size_t)n_atoms * 128);              // forward (fp16) | transposed (bf16)
+    float* wg_ws = reinterpret_cast<float*>(images + 2 * geossl_weight_image_bytes());
+    int rc = geossl_pack_weight_pair(params->out_w0, 129, images, stream);
+    if (rc) return rc;
+    rc = geossl_linear_tc(h, n_atoms, images, nullptr, 0, nullptr, nullptr, projA, 0, stream);
+    if (rc) return rc;
+    GEOSSL_CUDA(cudaMemsetAsync(gradA, 0, sizeof(float) * (size_t)n_atoms * 128, st));
     GEOSSL_CUDA(launch_pdl(tc::ddm_pair_prep_kernel, dim3((unsigned)((n_pad + 255) / 256)), dim3(256), 0, st, in, n_pad, prep));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(tc::ddm_head_tc_kernel<false, true>, dim3(grid), dim3(tc::kHThreads), smem, st, in,
-                           (const float*)prep, n_pad, (const float*)nullptr, (const float*)nullptr, grad_h, workspace, loss_part));
+                           (const float*)prep, n_pad, (const float*)nullptr, (const float*)nullptr, grad_h, workspace, loss_part,
+                           (const float*)projA, gradA));
     GEOSSL_LAUNCH_CHECK();
     GEOSSL_CUDA(launch_pdl(ddm_loss_finalize_kernel, dim3(1), dim3(32), 0, st, (const float*)loss_part, grid, loss));
     GEOSSL_LAUNCH_CHECK();
     const int n = HeadCfg<128>::kPartial;
     GEOSSL_CUDA(launch_pdl(ddm_head_reduce_kernel<128>, dim3((n + 255) / 256), dim3(256), 0, st, (const float*)workspace, grid, g));
     GEOSSL_LAUNCH_CHECK();
-    return 0;
+    // per-atom tail of the projected first layer (after the reduction has written out_w0, whose [:, :128] block is replaced)
+    rc = geossl_linear_tc(gradA, n_atoms, images + geossl_weight_image_bytes(), nullptr, 0, nullptr, nullptr, grad_h, 1, stream);
+    if (rc) return rc;
+    return geossl_linear_wgrad_tc_block(gradA, 128, h, 128, n_atoms, 0, wg_ws, g.out_w0, 129, nullptr, 128, stream);
+}
+
+int64_t geossl_ddm_workspace_fused(int64_t n_pairs, int64_t n_atoms) {
+    const int64_t na = n_atoms > 0 ? n_atoms : 0;
+    return geossl_ddm_workspace_tc(n_pairs) + 2 * na * 128 + 2 * geossl_weight_image_bytes() / 4 + geossl_linear_wgrad_tc_workspace(na > 0 ? na : 1) + 64;
 }
 
 }  // extern "C"

@@ -61,8 +61,13 @@ __device__ __forceinline__ void pack_weight_body(const float* __restrict__ Wt, i
         int n, c;
         if (!trans) {
             n = idx >> 4; c = idx & 15;
-            const float4 a = ldg4(Wt + (size_t)n * ldw + c * 8), b = ldg4(Wt + (size_t)n * ldw + c * 8 + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            if ((ldw & 3) == 0) {
+                const float4 a = ldg4(Wt + (size_t)n * ldw + c * 8), b = ldg4(Wt + (size_t)n * ldw + c * 8 + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {                                       // rows not 16-byte aligned (the (128,129) first layer of the DDM head)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldg(Wt + (size_t)n * ldw + c * 8 + j);
+            }
         } else {
             n = idx & 127; c = idx >> 7;
 #pragma unroll
@@ -75,10 +80,19 @@ __device__ __forceinline__ void pack_weight_body(const float* __restrict__ Wt, i
 
 template <bool FP16>
 __global__ void __launch_bounds__(256)
-pack_weight_kernel(const float* __restrict__ Wt, int trans, uint8_t* __restrict__ image) {
+pack_weight_kernel(const float* __restrict__ Wt, int ldw, int trans, uint8_t* __restrict__ image) {
     pdl_launch_dependents();
     pdl_wait();
-    pack_weight_body<FP16>(Wt, 128, trans, image);
+    pack_weight_body<FP16>(Wt, ldw, trans, image);
+}
+
+// Both images of ONE 128 x 128 block (forward, fp16 parts | transposed, bf16 parts) in one launch: blockIdx.y = orientation.
+__global__ void __launch_bounds__(256)
+pack_weight_pair_kernel(const float* __restrict__ Wt, int ldw, uint8_t* __restrict__ images) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (blockIdx.y == 0) pack_weight_body<true>(Wt, ldw, 0, images);
+    else pack_weight_body<false>(Wt, ldw, 1, images + kWImage);
 }
 
 // All layers of a model in ONE launch: blockIdx.y = layer, blockIdx.z = 0: forward image (fp16 parts, nn.Linear
@@ -623,15 +637,26 @@ extern "C" {
 
 int64_t geossl_weight_image_bytes(void) { return tc::kWImage; }
 
-int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts, void* image, void* stream) {
-    GEOSSL_REQUIRE(weight && image, "null pointer");
+int geossl_pack_weight_ld(const float* weight, int ldw, int transpose_weight, int bf16_parts, void* image, void* stream) {
+    GEOSSL_REQUIRE(weight && image && ldw >= 128, "null pointer / leading dimension < 128");
     if (bf16_parts) {
-        GEOSSL_CUDA(launch_pdl(tc::pack_weight_kernel<false>, dim3(8), dim3(256), 0, as_stream(stream), weight, transpose_weight, (uint8_t*)image));
+        GEOSSL_CUDA(launch_pdl(tc::pack_weight_kernel<false>, dim3(8), dim3(256), 0, as_stream(stream), weight, ldw, transpose_weight, (uint8_t*)image));
     } else {
-        GEOSSL_CUDA(launch_pdl(tc::pack_weight_kernel<true>, dim3(8), dim3(256), 0, as_stream(stream), weight, transpose_weight, (uint8_t*)image));
+        GEOSSL_CUDA(launch_pdl(tc::pack_weight_kernel<true>, dim3(8), dim3(256), 0, as_stream(stream), weight, ldw, transpose_weight, (uint8_t*)image));
     }
     GEOSSL_LAUNCH_CHECK();
     return 0;
+}
+
+int geossl_pack_weight_pair(const float* weight, int ldw, void* images, void* stream) {
+    GEOSSL_REQUIRE(weight && images && ldw >= 128, "null pointer / leading dimension < 128");
+    GEOSSL_CUDA(launch_pdl(tc::pack_weight_pair_kernel, dim3(8, 2), dim3(256), 0, as_stream(stream), weight, ldw, (uint8_t*)images));
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts, void* image, void* stream) {
+    return geossl_pack_weight_ld(weight, 128, transpose_weight, bf16_parts, image, stream);
 }
 
 int geossl_pack_weights_batched(const float* const* weights, const int32_t* lds, int n_weights, void* images, void* stream) {

@@ -1004,7 +1004,8 @@ class DDMHead(torch.autograd.Function):
         # needs_input_grad ignores torch.no_grad()): evaluation takes the forward-only kernel
         ctx.fused = bool(ctx.tc and FUSE_DDM_HEAD and n_pairs > 0 and train_pass
                          and any(ctx.needs_input_grad[i] for i in (0, *range(10, 10 + len(params)))))
-        ws = torch.empty(max(lib.geossl_ddm_workspace_tc(n_pairs) if ctx.tc else lib.geossl_ddm_workspace(H), 1),
+        ws = torch.empty(max(lib.geossl_ddm_workspace_fused(n_pairs, h.size(0)) if ctx.fused else
+                             (lib.geossl_ddm_workspace_tc(n_pairs) if ctx.tc else lib.geossl_ddm_workspace(H)), 1),
                          dtype=torch.float32, device=h.device)
         loss = torch.empty(2, dtype=torch.float32, device=h.device)
         pp = _ddm_ptrs(params)

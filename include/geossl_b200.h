@@ -199,6 +199,10 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
  * one bulk async copy (cp.async.bulk). */
 int64_t geossl_weight_image_bytes(void);
 int geossl_pack_weight(const float* weight, int transpose_weight, int bf16_parts, void* image, void* stream);
+/* The same for a 128 x 128 block of a wider row-major matrix (ldw = its row stride in floats, any value >= 128). */
+int geossl_pack_weight_ld(const float* weight, int ldw, int transpose_weight, int bf16_parts, void* image, void* stream);
+/* Both images of one block in one launch: images[0] = forward (fp16 parts), images[1] = transposed (bf16 parts). */
+int geossl_pack_weight_pair(const float* weight, int ldw, void* images, void* stream);
 /* Every 128 x 128 weight BLOCK of a model in one launch: `weights` = DEVICE array of n_weights device pointers to the first
  * element of a block, `lds` = DEVICE array of the leading dimensions (in_features) of the matrices the blocks live in
  * (NULL => 128: plain 128 x 128 layers); images = n_weights x 2 x geossl_weight_image_bytes(): [b][0] forward image
@@ -312,7 +316,11 @@ int geossl_ddm_head_bwd_tc(const float* h, const int64_t* sei, const int64_t* ba
 /* Forward AND backward of the head in ONE pass over the pairs (training: the backward kernel recomputes the forward per
  * tile anyway, so a separate forward launch is redundant work).  loss (2,) as geossl_ddm_head_fwd_tc.  grad_h and the
  * parameter gradients are the gradients of the UNSCALED sum over pairs (the number of graphs is only known once every
- * CTA has finished): the caller multiplies them by grad_loss / loss[1] (ops.DDMHead.backward: one multi-tensor scale). */
+ * CTA has finished): the caller multiplies them by grad_loss / loss[1] (ops.DDMHead.backward: one multi-tensor scale).
+ * The first layer of the score MLP is applied per ATOM (it is linear in h[u] + h[v]): A = h W0[:, :128]^T by the dense-layer
+ * kernel, gathered per pair; its data / weight gradients are one per-atom GEMM each after the pair kernel has scattered dz1.
+ * workspace: geossl_ddm_workspace_fused(n_pairs, n_atoms) floats. */
+int64_t geossl_ddm_workspace_fused(int64_t n_pairs, int64_t n_atoms);
 int geossl_ddm_head_fwd_bwd_tc(const float* h, const int64_t* sei, const int64_t* batch, int64_t n_pairs, const int32_t* n_pairs_live,
                                int64_t n_atoms, const float* dist, const float* noise, const int64_t* noise_level,
                                const float* sigmas, int n_levels, float anneal_power, int H,
