@@ -9,8 +9,8 @@ if [ "$2" != "nocap" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_$TAG.csv \
     python profiles/profile_step.py --steps 1 > gpurun_out/ncu_l_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:"filter_bwd_tc_kernel|ddm_head_tc_kernel|cfconv_gather_async_kernel|linear_wgrad_tc_kernel|filter_fwd_tc_kernel" \
-    -c 40 -o gpurun_out/prof_$TAG python profiles/profile_step.py --steps 1 > gpurun_out/ncu_f_$TAG.log 2>&1
+    -k regex:"filter_bwd_tc_kernel|ddm_head_tc_kernel|cfconv_gather|linear_wgrad_tc_kernel|filter_fwd_tc_kernel|linear_chain_tc_kernel" \
+    -c 44 -o gpurun_out/prof_$TAG python profiles/profile_step.py --steps 1 > gpurun_out/ncu_f_$TAG.log 2>&1
 fi
 python bench.py --steps 20 --warmup 5 --atoms-max 60 --no-cpu-baseline > gpurun_out/bench_var_$TAG.json 2> gpurun_out/bench_var_$TAG.err
 tail -3 gpurun_out/pytest_$TAG.txt; head -c 300 gpurun_out/bench_var_$TAG.json; echo; tail -2 gpurun_out/bench_var_$TAG.err; head -c 400 gpurun_out/bench_$TAG.json; echo; tail -2 gpurun_out/bench_$TAG.err

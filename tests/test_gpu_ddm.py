@@ -325,9 +325,10 @@ def test_fused_head_equals_two_kernel_head():
         # (the one-pass kernel recomputes the forward with bf16-split operands, the forward-only kernel uses fp16 parts:
         #  both are within 1e-5 of the reference, they differ from each other by a few 1e-6)
         assert rel_err(res[True][0], res[False][0]) <= 5e-6
-        assert rel_err(res[True][1], res[False][1]) <= 1e-5
+        # (the one-pass kernel also applies the first score-MLP layer per atom instead of per pair: another summation order)
+        assert rel_err(res[True][1], res[False][1]) <= 5e-5
         for k in res[True][2]:
-            assert rel_err(res[True][2][k], res[False][2][k]) <= 1e-5, k
+            assert rel_err(res[True][2][k], res[False][2][k]) <= 5e-5, k
         with torch.no_grad():                                   # evaluation: forward-only kernel, same value
             ops.FUSE_DDM_HEAD = True
             head = head_from(g, device=DEV)
