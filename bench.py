@@ -226,6 +226,10 @@ def run_product(args):
     groups = [{"params": model.parameters()}] + [{"params": [p for p in h.parameters() if p.requires_grad]} for h in heads]
     opt = torch.optim.Adam(groups, lr=CFG["lr"], fused=True, capturable=not args.no_graph)
     sync = FlatGradAllReduce([p for g in groups for p in g["params"]]) if world > 1 else None
+    if os.environ.get("GEOSSL_CFCONV_PAIRS"):             # A/B only: "0" = row-gather cfconv kernels, else the tuning code
+        from geossl_b200 import ops as _o
+        _o.CFCONV_PAIRS = os.environ["GEOSSL_CFCONV_PAIRS"] != "0"
+        _o.CFCONV_PAIRS_TUNING = int(os.environ["GEOSSL_CFCONV_PAIRS"])
     if os.environ.get("GEOSSL_PAIR_OWNER_SMALL"):         # tuning only
         from geossl_b200 import ops as _o
         _o.PAIR_OWNER_SMALL = os.environ["GEOSSL_PAIR_OWNER_SMALL"] != "0"
@@ -245,7 +249,7 @@ def run_product(args):
         n_cap = -(-int(1.02 * max(hb.positions.size(0) for hb in host_pool)) // 128) * 128
         p_cap = -(-int(1.02 * max(hb.super_edge_index.size(1) for hb in host_pool)) // 1024) * 1024
         live_atoms = [hb.positions.size(0) for hb in host_pool]
-        host_pool = [pad_batch(hb, n_cap, p_cap) for hb in host_pool]
+        host_pool = [pad_batch(hb, n_cap, p_cap, max_graph_atoms_cap=args.atoms_max) for hb in host_pool]
     if args.model == "painn":
         # dataset-time radius graph (datasets_3D_Radius.py:120) on the clean coordinates, reused for both views
         from geossl_b200 import ops as _ops

@@ -182,14 +182,15 @@ class SchNet(torch.nn.Module):
         if self.atomref is not None:
             self.atomref.weight.data.copy_(self.initial_atomref)
 
-    def forward(self, z, pos, batch=None, return_latent=False, num_graphs=None, graph=None):
-        """``num_graphs`` / ``graph`` are optional extensions: passing the graph count avoids the host sync
-        on ``batch[-1]``; ``graph`` reuses a prebuilt RadiusCSR."""
+    def forward(self, z, pos, batch=None, return_latent=False, num_graphs=None, graph=None, max_graph_atoms=None):
+        """``num_graphs`` / ``graph`` / ``max_graph_atoms`` are optional extensions: passing the graph count avoids the
+        host sync on ``batch[-1]``; ``graph`` reuses a prebuilt RadiusCSR; a host-known bound on the atoms per graph
+        selects the pair-centric cfconv kernel for batches of small molecules (ops.CFCONV_PAIRS)."""
         assert z.dim() == 1 and z.dtype == torch.long
         batch = torch.zeros_like(z) if batch is None else batch
         h = ops.embedding(self.embedding, z)
         if graph is None:
-            graph = ops.radius_csr(pos, batch, self.cutoff, num_graphs=num_graphs)
+            graph = ops.radius_csr(pos, batch, self.cutoff, num_graphs=num_graphs, max_graph_atoms=max_graph_atoms)
         fused = False
         if pos.requires_grad and torch.is_grad_enabled():
             ge = graph.exact()

@@ -9,6 +9,8 @@
 //
 // HBM roofline: bytes = 4F*U (every filter row once) + 2*4F*N (x, out) + 8E (src, filt_row) + 4(N+1) (rowptr);
 // U = E without pair sharing (551 B/edge), U = E/2 for untruncated graphs (300 B/edge).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace geossl {
@@ -173,6 +175,222 @@ cfconv_gather_async_kernel(const float* __restrict__ filt, const int32_t* __rest
 // With one filter row per directed edge the kernel below streams 5.4 TB/s (83 % of the HBM copy peak); with one row per atom
 // pair half of the row reads are L2 hits, DRAM traffic halves but the L2 -> SM path (the same 224 MB) now sets the time.
 
+// Pair-centric edition for small graphs (molecules): with one filter row per atom PAIR, the row-gather kernels above
+// still move every filter row L2 -> SM twice (once per direction), and that path, not DRAM, sets their time.  Here one
+// CTA owns one graph, keeps the graph's operand rows v and its accumulators in shared memory, and streams the graph's
+// contiguous block of filter rows ONCE: for pair u = (s, t) it adds W_u * v[s] to row t and W_u * v[t] to row s.
+// G warps split the block into G contiguous chunks; a warp owns a private accumulator copy (lane = 4 features), so there
+// are no atomics and the summation order is fixed: results are run-to-run identical (they differ from the row-gather
+// editions by fp32 summation order only).  The pairs of a chunk are sorted by their owner row t, whose running sum stays
+// in registers and is flushed on a row change; 2 x UNR filter rows per warp are in flight in registers (ping-pong).
+// Orphan pairs (reverse direction cut by the neighbour limit, pair_atoms = (s, ~t)) contribute to one side only:
+// forward to row t, transposed (d/dx) to row s.  That is folded into the pair's shared-memory ROW numbers once per 32
+// pairs (each lane decodes one pair, the packed word is broadcast by shuffle): the missing side reads v from an all-zero
+// row / accumulates into a dump row, so the inner loop has no selects.  A graph with more than n_max atoms (host-side
+// bound wrong, or the edge-less padding graph of data.pad_batch) is still summed correctly by one warp accumulating
+// straight into `out` (pair_chunk_global).
+// fire-and-forget L2 prefetch of a contiguous block (no destination register, so no scoreboard): bytes % 16 == 0
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+template <bool TRANSPOSED>
+__device__ __noinline__ void pair_chunk_global(const float* __restrict__ filt, const int2* __restrict__ pair_atoms, int lo, int hi,
+                                               int a0, int lane, float4* acc, const float4* vv) {
+    // acc / vv: this lane's float4 column of row 0 of the graph in global memory; rows are 32 float4 apart
+    for (int u = lo; u < hi; ++u) {
+        const int2 st = __ldg(pair_atoms + u);
+        const bool both = st.y >= 0;
+        const int t = (both ? st.y : ~st.y) - a0, s = st.x - a0;
+        const float4 w = ld_stream4(filt + (int64_t)u * 128 + lane * 4);
+        if (!TRANSPOSED || both) { float4 a = acc[t * 32]; fma4(a, vv[s * 32], w); acc[t * 32] = a; }
+        if (TRANSPOSED || both) { float4 a = acc[s * 32]; fma4(a, vv[t * 32], w); acc[s * 32] = a; }
+    }
+}
+
+// One warp's state while it walks its chunk of a graph's pair block.  Pairs are consumed four at a time: when all four
+// belong to the running row t (the common case, rows hold ~n/2 pairs) their accumulator rows are distinct, so the four
+// shared-memory read-modify-writes are issued together instead of as one dependent chain; a group that crosses a row
+// boundary takes the pair-by-pair path.
+struct PairWalk {
+    uint32_t cur_t = 0xffffffffu;
+    float4 acc_t = make_float4(0.f, 0.f, 0.f, 0.f), v_t = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    __device__ __forceinline__ void flush(float4* acc) {
+        if (cur_t != 0xffffffffu) { float4 a = acc[cur_t * 32]; add4(a, acc_t); acc[cur_t * 32] = a; }
+    }
+    __device__ __forceinline__ void one(const float4& wk, uint32_t m, float4* acc, const float4* vv) {
+        const uint32_t t = m & 0xffu;
+        if (t != cur_t) {
+            flush(acc);
+            cur_t = t;
+            acc_t = make_float4(0.f, 0.f, 0.f, 0.f);
+            v_t = vv[t * 32];
+        }
+        fma4(acc_t, vv[((m >> 8) & 0xffu) * 32], wk);
+        float4* ap = acc + (m >> 16) * 32;
+        float4 as = *ap;
+        fma4(as, v_t, wk);
+        *ap = as;
+    }
+    __device__ __forceinline__ void change_row(uint32_t t, float4* acc, const float4* vv) {
+        flush(acc);
+        cur_t = t;
+        acc_t = make_float4(0.f, 0.f, 0.f, 0.f);
+        v_t = vv[t * 32];
+    }
+    __device__ __forceinline__ void four(const float4& w0, const float4& w1, const float4& w2, const float4& w3, uint4 m,
+                                         float4* acc, const float4* vv) {
+        const uint32_t r0 = m.x >> 16, r1 = m.y >> 16, r2 = m.z >> 16, r3 = m.w >> 16;
+        float4* p0 = acc + r0 * 32;
+        float4* p1 = acc + r1 * 32;
+        float4* p2 = acc + r2 * 32;
+        float4* p3 = acc + r3 * 32;
+        const float4 x0 = vv[((m.x >> 8) & 0xffu) * 32], x1 = vv[((m.y >> 8) & 0xffu) * 32];
+        const float4 x2 = vv[((m.z >> 8) & 0xffu) * 32], x3 = vv[((m.w >> 8) & 0xffu) * 32];
+        if ((((m.x ^ m.y) | (m.x ^ m.z) | (m.x ^ m.w)) & 0xffu) == 0u) {
+            // one owner row: the four accumulator rows are distinct (or the dump row), their updates are independent
+            if ((m.x & 0xffu) != cur_t) change_row(m.x & 0xffu, acc, vv);
+            float4 a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;
+            fma4(acc_t, x0, w0); fma4(acc_t, x1, w1); fma4(acc_t, x2, w2); fma4(acc_t, x3, w3);
+            fma4(a0, v_t, w0); fma4(a1, v_t, w1); fma4(a2, v_t, w2); fma4(a3, v_t, w3);
+            *p0 = a0; *p1 = a1; *p2 = a2; *p3 = a3;
+        } else if (r0 != r1 && r0 != r2 && r0 != r3 && r1 != r2 && r1 != r3 && r2 != r3) {
+            // the group crosses a row boundary but still updates four different accumulator rows: same independent
+            // updates with each pair's own v[t]; the owner-row sums follow in order (a flush is a later read-modify-write)
+            const float4 t0 = vv[(m.x & 0xffu) * 32], t1 = vv[(m.y & 0xffu) * 32];
+            const float4 t2 = vv[(m.z & 0xffu) * 32], t3 = vv[(m.w & 0xffu) * 32];
+            float4 a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;
+            fma4(a0, t0, w0); fma4(a1, t1, w1); fma4(a2, t2, w2); fma4(a3, t3, w3);
+            *p0 = a0; *p1 = a1; *p2 = a2; *p3 = a3;
+            if ((m.x & 0xffu) != cur_t) change_row(m.x & 0xffu, acc, vv);
+            fma4(acc_t, x0, w0);
+            if ((m.y & 0xffu) != cur_t) change_row(m.y & 0xffu, acc, vv);
+            fma4(acc_t, x1, w1);
+            if ((m.z & 0xffu) != cur_t) change_row(m.z & 0xffu, acc, vv);
+            fma4(acc_t, x2, w2);
+            if ((m.w & 0xffu) != cur_t) change_row(m.w & 0xffu, acc, vv);
+            fma4(acc_t, x3, w3);
+        } else {
+            one(w0, m.x, acc, vv); one(w1, m.y, acc, vv); one(w2, m.z, acc, vv); one(w3, m.w, acc, vv);
+        }
+    }
+};
+
+// Shared memory: v rows [n_max + 1][32] float4 (last row: zeros) | G accumulator copies [n_max + 1][32] (last row: dump)
+// | meta_cap packed pair records (t | row of v[s] << 8 | row gaining W v[t] << 16), decoded once by the whole CTA.
+// The only long-latency loads inside the loop are the filter rows, in two register buffers of UNR rows that are waited
+// for as a whole (one scoreboard each): a load that shares a scoreboard with younger loads would wait for those too.
+template <int G, int UNR, bool TRANSPOSED>
+__global__ void __launch_bounds__(32 * G)
+cfconv_pairs_kernel(const float* __restrict__ filt, const int2* __restrict__ pair_atoms, const int32_t* __restrict__ pair_rowptr,
+                    const int32_t* __restrict__ graph_ptr, const float* __restrict__ v, int n_max, int meta_cap,
+                    float* __restrict__ out) {
+    extern __shared__ float4 sP[];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);            // provably warp-uniform
+    const int a0 = __ldg(graph_ptr + blockIdx.x), n = __ldg(graph_ptr + blockIdx.x + 1) - a0;
+    if (n <= 0) return;
+    const int p0 = __ldg(pair_rowptr + a0), p1 = __ldg(pair_rowptr + a0 + n);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n > n_max || p1 - p0 > meta_cap) {
+        if (wid == 0) {
+            float4* o = reinterpret_cast<float4*>(out + (int64_t)a0 * 128) + lane;
+            for (int i = 0; i < n; ++i) o[i * 32] = z4;
+            if (p1 > p0)
+                pair_chunk_global<TRANSPOSED>(filt, pair_atoms, p0, p1, a0, lane, o,
+                                              reinterpret_cast<const float4*>(v + (int64_t)a0 * 128) + lane);
+        }
+        return;
+    }
+    const int per = (((p1 - p0 + G - 1) / G) + 3) & ~3;                // multiple of 4: the records of a group are one 16-byte load
+    const int lo = min(p0 + wid * per, p1), hi = min(lo + per, p1);
+    // ---- the first two buffers of filter rows are requested before anything else
+    float4 wa[UNR], wb[UNR];
+    auto load = [&](float4 (&w)[UNR], int u0) {
+#pragma unroll
+        for (int k = 0; k < UNR; ++k)     // plain loads: inline-asm loads all land on ONE scoreboard, and a wait on it drains both buffers
+            w[k] = (u0 + k < hi) ? __ldcs(reinterpret_cast<const float4*>(filt + (int64_t)(u0 + k) * 128) + lane) : z4;
+    };
+    constexpr int PD = 32 / UNR;                                      // prefetch distance in buffers: 16 KB per warp
+    auto prefetch = [&](int u0, int count) {                          // rows [u0, u0 + count) clipped to the chunk -> L2
+        const int end = min(u0 + count, hi);
+        if (lane == 0 && end > u0) prefetch_l2_bulk(filt + (int64_t)u0 * 128, (uint32_t)(end - u0) * 512u);
+    };
+    load(wa, lo);
+    load(wb, lo + UNR);
+    prefetch(lo + 2 * UNR, PD * UNR);
+    // ---- stage the graph's operand rows and pair records (every load is issued before the first store), clear the accumulators
+    const int rows = n_max + 1;
+    float4* sv = sP;
+    float4* sacc = sP + rows * 32;
+    uint32_t* smeta = reinterpret_cast<uint32_t*>(sacc + G * rows * 32);
+    const float4* vg = reinterpret_cast<const float4*>(v + (int64_t)a0 * 128);
+    constexpr int VR = 32 / G, MR = 16 / G;                           // per round: 32 rows of v, 512 pair records
+    for (int i0 = 0, j0 = 0; i0 < n * 32 || j0 < p1 - p0; i0 += 32 * G * VR, j0 += 32 * G * MR) {
+        float4 tv[VR];
+        int2 tm[MR];
+#pragma unroll
+        for (int j = 0; j < VR; ++j) { const int i = i0 + j * 32 * G + tid; tv[j] = (i < n * 32) ? __ldg(vg + i) : z4; }
+#pragma unroll
+        for (int j = 0; j < MR; ++j) { const int i = j0 + j * 32 * G + tid; tm[j] = (i < p1 - p0) ? __ldg(pair_atoms + p0 + i) : make_int2(a0, a0); }
+#pragma unroll
+        for (int j = 0; j < VR; ++j) { const int i = i0 + j * 32 * G + tid; if (i < n * 32) sv[i] = tv[j]; }
+#pragma unroll
+        for (int j = 0; j < MR; ++j) {
+            const int i = j0 + j * 32 * G + tid;
+            if (i < p1 - p0) {
+                const bool both = tm[j].y >= 0;
+                const uint32_t t = (uint32_t)((both ? tm[j].y : ~tm[j].y) - a0), s_ = (uint32_t)(tm[j].x - a0);
+                const uint32_t v_row = (TRANSPOSED && !both) ? (uint32_t)n_max : s_;     // missing side: zero operand row ...
+                const uint32_t a_row = (!TRANSPOSED && !both) ? (uint32_t)n_max : s_;    // ... or the dump accumulator row
+                smeta[i] = t | (v_row << 8) | (a_row << 16);
+            }
+        }
+    }
+    for (int i = tid; i < n * 32; i += 32 * G) {
+#pragma unroll
+        for (int c = 0; c < G; ++c) sacc[c * rows * 32 + i] = z4;
+    }
+    if (tid < 32) sv[n_max * 32 + tid] = z4;
+    __syncthreads();
+    float4* acc = sacc + wid * rows * 32 + lane;
+    const float4* vv = sv + lane;
+    const uint32_t* sm = smeta - p0;
+    PairWalk walk;
+    auto consume = [&](const float4 (&w)[UNR], int u0) {
+        if (u0 + UNR <= hi) {
+#pragma unroll
+            for (int k = 0; k < UNR; k += 4)
+                walk.four(w[k], w[k + 1], w[k + 2], w[k + 3], *reinterpret_cast<const uint4*>(sm + u0 + k), acc, vv);
+        } else {
+#pragma unroll
+            for (int k = 0; k < UNR; ++k)
+                if (u0 + k < hi) walk.one(w[k], sm[u0 + k], acc, vv);
+        }
+    };
+    for (int u0 = lo; u0 < hi; u0 += 2 * UNR) {
+        consume(wa, u0);
+        load(wa, u0 + 2 * UNR);
+        if (u0 + UNR < hi) consume(wb, u0 + UNR);
+        load(wb, u0 + 3 * UNR);
+        prefetch(u0 + (2 + PD) * UNR, 2 * UNR);
+    }
+    walk.flush(acc);
+    __syncthreads();
+    float4* og = reinterpret_cast<float4*>(out + (int64_t)a0 * 128);
+    for (int i = tid; i < n * 32; i += 32 * G) {
+        float4 s = sacc[i];
+#pragma unroll
+        for (int c = 1; c < G; ++c) add4(s, sacc[c * rows * 32 + i]);
+        og[i] = s;
+    }
+}
+
 template <int F>
 __global__ void __launch_bounds__(256)
 cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, const int32_t* __restrict__ rowptr,
@@ -224,6 +442,30 @@ int launch_bwd_x(const float* filt, const int32_t* filt_row, const float* g, con
     else launch_pdl(cfconv_gather_deep_kernel<F, true>, dim3(blocks), dim3(threads), 0, st, filt, filt_row, g, tr, te, tt, (int)n, dx);
     return 0;
 }
+inline int pairs_meta_cap(int n_max) {                              // pair records per graph: <= 32 neighbours per row, <= n(n-1)
+    const int cap = n_max * 32 < n_max * (n_max - 1) ? n_max * 32 : n_max * (n_max - 1);
+    return (cap + 7) & ~3;
+}
+inline size_t pairs_smem(int groups, int n_max) { return (size_t)(1 + groups) * (n_max + 1) * 512 + 4 * (size_t)pairs_meta_cap(n_max); }
+
+template <int G, int UNR>
+int launch_pairs(const float* filt, const int2* pair_atoms, const int32_t* pair_rowptr, const int32_t* graph_ptr, int n_graphs,
+                 const float* v, int n_max, bool transposed, float* out, cudaStream_t st) {
+    const size_t smem = pairs_smem(G, n_max);
+    const int meta_cap = pairs_meta_cap(n_max);
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
+        cudaFuncSetAttribute(cfconv_pairs_kernel<G, UNR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(cfconv_pairs_kernel<G, UNR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured.set();
+    }
+    if (transposed)
+        launch_pdl(cfconv_pairs_kernel<G, UNR, true>, dim3(n_graphs), dim3(32 * G), smem, st, filt, pair_atoms, pair_rowptr, graph_ptr, v, n_max, meta_cap, out);
+    else
+        launch_pdl(cfconv_pairs_kernel<G, UNR, false>, dim3(n_graphs), dim3(32 * G), smem, st, filt, pair_atoms, pair_rowptr, graph_ptr, v, n_max, meta_cap, out);
+    return 0;
+}
+
 template <int F>
 int launch_bwd_w(const float* x, const float* g, const int32_t* rowptr, const int32_t* src, int64_t n, float* dfilt, cudaStream_t st) {
     const int threads = 256;
@@ -260,6 +502,35 @@ int geossl_cfconv_bwd_x(const float* filt, const int32_t* filt_row, const float*
     if (n_atoms == 0) return 0;
     GEOSSL_REQUIRE(filt && grad_out && t_rowptr && t_eid && t_tgt && grad_x && n_atoms > 0, "null pointer");
     DISPATCH_F(F, launch_bwd_x<kF>(filt, filt_row, grad_out, t_rowptr, t_eid, t_tgt, n_atoms, grad_x, as_stream(stream)));
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_cfconv_pairs_max_atoms(int groups) {
+    if (groups < 1) groups = 2;
+    int n = 254;                                                     // row numbers travel as bytes
+    while (n > 1 && pairs_smem(groups, n) > 226 * 1024) --n;
+    return n;
+}
+
+int geossl_cfconv_pairs(const float* v, const float* filt, const int32_t* pair_atoms, const int32_t* pair_rowptr,
+                        const int32_t* graph_ptr, int64_t n_graphs, int max_graph_atoms, int transposed, int tuning,
+                        float* out, void* stream) {
+    if (n_graphs == 0) return 0;
+    GEOSSL_REQUIRE(v && filt && pair_atoms && pair_rowptr && graph_ptr && out && n_graphs > 0, "null pointer");
+    GEOSSL_REQUIRE((reinterpret_cast<uintptr_t>(pair_atoms) & 7) == 0, "pair_atoms must be 8-byte aligned");
+    if (tuning <= 0) tuning = 208;
+    const int groups = tuning / 100, unroll = tuning % 100;
+    GEOSSL_REQUIRE(max_graph_atoms >= 1 && max_graph_atoms <= geossl_cfconv_pairs_max_atoms(groups),
+                   "max_graph_atoms exceeds the shared-memory window (use geossl_cfconv_fwd / geossl_cfconv_bwd_x)");
+    const int2* pa = reinterpret_cast<const int2*>(pair_atoms);
+    cudaStream_t st = as_stream(stream);
+#define PAIRS_CASE(G_, U_) case G_ * 100 + U_: launch_pairs<G_, U_>(filt, pa, pair_rowptr, graph_ptr, (int)n_graphs, v, max_graph_atoms, transposed != 0, out, st); break;
+    switch (groups * 100 + unroll) {
+        PAIRS_CASE(1, 16) PAIRS_CASE(2, 8) PAIRS_CASE(2, 16) PAIRS_CASE(3, 8) PAIRS_CASE(3, 16) PAIRS_CASE(4, 8) PAIRS_CASE(4, 16)
+        default: set_error("%s: unsupported tuning %d (groups*100 + unroll)", __func__, tuning); return GEOSSL_EINVAL;
+    }
+#undef PAIRS_CASE
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

@@ -122,7 +122,7 @@ def synthetic_batch(num_graphs=32, atoms=30, atoms_max=None, *, seed=0, option="
     sei = super_edges_host(counts, option) if with_pairs else torch.empty((2, 0), dtype=torch.long)
     ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     return AtomTupleBatch(torch.from_numpy(x), torch.from_numpy(pos), torch.from_numpy(batch), sei,
-                          None, int(num_graphs), torch.from_numpy(ptr))
+                          None, int(num_graphs), torch.from_numpy(ptr), {"max_graph_atoms": int(counts.max())})
 
 
 def assemble_batch_device(counts, z, positions, option="combination", device="cuda", ratio=1.0, selection=None,
@@ -162,14 +162,15 @@ def assemble_batch_device(counts, z, positions, option="combination", device="cu
         sei = sei[:, cols].contiguous()
     z = z.to(device)
     x = torch.stack([z, torch.zeros_like(z)], dim=1)
-    return AtomTupleBatch(x, positions.to(device), batch, sei, None, n_graphs, ptr)
+    return AtomTupleBatch(x, positions.to(device), batch, sei, None, n_graphs, ptr,
+                          {"max_graph_atoms": int(counts.max()) if len(counts) else 0})
 
 
 # ------------------------------------------------------------------------------------------ capacity padding
 PAD_SPACING = 128.0      # Angstrom between padding atoms: larger than any cutoff, so they never gain an edge
 
 
-def pad_batch(batch, n_atoms_cap, n_pairs_cap, n_edges_cap=None):
+def pad_batch(batch, n_atoms_cap, n_pairs_cap, n_edges_cap=None, max_graph_atoms_cap=None):
     """Capacity-padded copy of ``batch`` (same device): fixed tensor shapes for every batch of a stream, which is what
     lets ONE captured CUDA graph serve variable-size Molecule3D batches (10-60 atoms per molecule,
     datasets_utils.py:112-176; the collate is dataloaders_AtomTuple.py:45-78).
@@ -185,6 +186,8 @@ def pad_batch(batch, n_atoms_cap, n_pairs_cap, n_edges_cap=None):
       count on the device (geossl_painn_edge_geometry).  Because two stacked views cannot simply be concatenated any
       more (the sentinel of view 1 is a real atom of view 2), ``extras['rei_stacked']`` (2, 2 n_edges_cap) holds the
       stacked list ready made: live edges of view 1, live edges of view 2 (+ N_cap), padding ``[0; 2 N_cap]``.
+    * ``extras['max_graph_atoms']`` (host-known bound on the atoms of a molecule) is replaced by ``max_graph_atoms_cap``
+      when given: the bound of the whole stream, since a captured graph bakes the kernel configuration in.
     """
     has_pairs = batch.super_edge_index is not None
     n, p, b = batch.positions.size(0), (batch.super_edge_index.size(1) if has_pairs else 0), batch.num_graphs
@@ -206,6 +209,8 @@ def pad_batch(batch, n_atoms_cap, n_pairs_cap, n_edges_cap=None):
         sei = torch.zeros((2, n_pairs_cap), dtype=batch.super_edge_index.dtype, device=dev)
         sei[:, :p] = batch.super_edge_index
         extras["n_pairs_live"] = torch.tensor([p], dtype=torch.int32, device=dev)
+    if max_graph_atoms_cap is not None:                # one bound for the whole stream (a captured graph bakes it in); the
+        extras["max_graph_atoms"] = int(max_graph_atoms_cap)   # edge-less padding graph may exceed it (geossl_cfconv_pairs)
     extras["n_atoms_live"] = n
     extras["n_graphs_live"] = b                     # fine-tune readouts drop the padding graph's row (finetune._readout)
     rei = batch.radius_edge_index

@@ -136,6 +136,9 @@ class RadiusCSR:
         self.pair_rowptr = self.pair_of_edge = self.pair_e1 = self.pair_e2 = self.pair_atoms = self.pair_dist = None
         self._n_edges = None
         self._exact = None
+        # host-known bound on the atoms of any graph that has edges (None = unknown): what lets the pair-centric cfconv
+        # kernel (geossl_cfconv_pairs) size its shared-memory window without a device sync
+        self.max_graph_atoms = None
 
     @property
     def n_edges_dev(self):
@@ -236,7 +239,7 @@ CELL_LIST_MIN_ATOMS = 2048
 
 
 def radius_csr(pos, batch, r, max_num_neighbors=MAX_NEIGHBORS_DEFAULT, *, graph_ptr=None, num_graphs=None,
-               capacity=None, transpose=True, cell_list=None):
+               capacity=None, transpose=True, cell_list=None, max_graph_atoms=None):
     """Neighbour search -> RadiusCSR (torch_cluster.radius_graph semantics, see include/geossl_b200.h).
     ``cell_list``: None = automatic (graphs of at least CELL_LIST_MIN_ATOMS atoms on average), True / False force it."""
     pos = _req(pos.detach(), torch.float32, "pos", 2)
@@ -275,8 +278,9 @@ def radius_csr(pos, batch, r, max_num_neighbors=MAX_NEIGHBORS_DEFAULT, *, graph_
         _p(pos), _p(batch), _p(graph_ptr), n, float(r), int(max_num_neighbors), capacity, _p(scratch), _p(rowptr), _p(src),
         _p(tgt), _p(dist), 1 if RADIUS_FMA else 0, _p(box), _p(keys), _p(order), min_atoms, _stream()))
     g = RadiusCSR(n, capacity, rowptr, src, tgt, dist, batch, graph_ptr)
-    if transpose:
-        g.ensure_transpose()
+    g.max_graph_atoms = None if max_graph_atoms is None else int(max_graph_atoms)
+    if transpose and not (max_graph_atoms is not None and _pairs_kernel_applies(g)):
+        g.ensure_transpose()              # the pair-centric cfconv kernels never read the source-sorted view
     return g
 
 
@@ -321,6 +325,27 @@ def _cfconv_bwd_x(filt, grad_out, g, filt_row=None):
                                                                    _p(g.t_eid), _p(g.t_tgt), g.n_atoms, grad_out.size(1), _p(dx),
                                                                    _stream()))
     return dx
+
+
+# Pair-centric cfconv (geossl_cfconv_pairs): used by the fused layer when filter rows are shared per atom pair and the batch
+# carries a host-known bound on its graph sizes that fits the shared-memory window.
+CFCONV_PAIRS = True
+CFCONV_PAIRS_MAX_ATOMS = 32         # one CTA walks a graph's n(n-1)/2 pairs with two warps: larger graphs take the row-gather kernels
+CFCONV_PAIRS_TUNING = 0           # 0 = library default; groups * 100 + unroll (profiles/bench_cfconv.py sweeps it)
+
+
+def _pairs_kernel_applies(g):
+    return (CFCONV_PAIRS and SHARE_PAIR_FILTERS and FILTER_MODE != "simt" and g.max_graph_atoms is not None
+            and 1 <= g.max_graph_atoms <= CFCONV_PAIRS_MAX_ATOMS and g.dist is not None)
+
+
+def _cfconv_pairs(v, filt, g, transposed):
+    g.ensure_pairs()
+    out = torch.empty((g.n_atoms, 128), dtype=torch.float32, device=v.device)
+    _timed("cfconv_bwd_x" if transposed else "cfconv_fwd", lambda: _lib.load().geossl_cfconv_pairs(
+        _p(v), _p(filt), _p(g.pair_atoms), _p(g.pair_rowptr), _p(g.graph_ptr), g.graph_ptr.numel() - 1,
+        int(g.max_graph_atoms), 1 if transposed else 0, int(CFCONV_PAIRS_TUNING), _p(out), _stream()))
+    return out
 
 
 def _cfconv_bwd_w(x, grad_out, g):
@@ -436,7 +461,11 @@ class CFConvLayer(torch.autograd.Function):
         pairs = (SHARE_PAIR_FILTERS and FILTER_MODE != "simt" and w1.size(0) == 128 and w1.size(1) <= 63
                  and graph.dist is not None)
         filt = filter_forward(graph, offset, coeff, cutoff, w1, b1, w2, b2, pairs=pairs)
-        out = _cfconv_fwd(x, filt, graph, graph.pair_of_edge if pairs else None)
+        ctx.pair_kernel = pairs and x.size(1) == 128 and _pairs_kernel_applies(graph)
+        if ctx.pair_kernel:
+            out = _cfconv_pairs(x, filt, graph, False)
+        else:
+            out = _cfconv_fwd(x, filt, graph, graph.pair_of_edge if pairs else None)
         ctx.graph, ctx.coeff, ctx.cutoff, ctx.mode, ctx.pairs = graph, coeff, cutoff, FILTER_MODE, pairs
         ctx.save_for_backward(x, filt, w1, b1, w2, b2, offset)
         return out
@@ -449,7 +478,10 @@ class CFConvLayer(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         lib = _lib.load()
         F_, G = w1.size(0), w1.size(1)
-        gx = _cfconv_bwd_x(filt, grad_out, g, g.pair_of_edge if ctx.pairs else None) if ctx.needs_input_grad[0] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = (_cfconv_pairs(grad_out, filt, g, True) if ctx.pair_kernel
+                  else _cfconv_bwd_x(filt, grad_out, g, g.pair_of_edge if ctx.pairs else None))
         gw1, gb1, gw2, gb2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
         if ctx.mode != "simt" and F_ == 128 and G <= 63:
             ws = torch.empty(lib.geossl_filter_bwd_tc_workspace(), dtype=torch.float32, device=x.device)

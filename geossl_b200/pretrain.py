@@ -29,10 +29,17 @@ def perturb(x, positions, mu, sigma, device_noise=False):
     return x, positions + noise
 
 
+def _max_graph_atoms(batch):
+    """Host-known bound on the atoms per graph (``extras['max_graph_atoms']``, set by the collate helpers in
+    ``data`` / ``datasets``) or None: lets SchNet pick the pair-centric cfconv kernel without a device sync."""
+    return (getattr(batch, "extras", None) or {}).get("max_graph_atoms")
+
+
 def _encode(args, model, x, positions, batch):
     n_graphs = getattr(batch, "n_graphs", None)
     if args.model_3d == "schnet":
-        _, rep = model(x, positions, batch.batch, return_latent=True, num_graphs=n_graphs)
+        _, rep = model(x, positions, batch.batch, return_latent=True, num_graphs=n_graphs,
+                       max_graph_atoms=_max_graph_atoms(batch))
     elif args.model_3d == "painn":
         _, rep = model(x, positions, batch.radius_edge_index, batch.batch, return_latent=True, num_graphs=n_graphs,
                        assume_sorted=bool(getattr(batch, "extras", {}).get("rei_sorted", False)))
@@ -49,7 +56,7 @@ def _encode_stacked(args, model, x_01, positions_01, x_02, positions_02, batch):
     pos = torch.cat([positions_01, positions_02])
     bvec = torch.cat([batch.batch, batch.batch + b])
     if args.model_3d == "schnet":
-        _, rep = model(x, pos, bvec, return_latent=True, num_graphs=2 * b)
+        _, rep = model(x, pos, bvec, return_latent=True, num_graphs=2 * b, max_graph_atoms=_max_graph_atoms(batch))
     else:
         rei = batch.radius_edge_index
         stacked = getattr(batch, "extras", {}).get("rei_stacked")         # capacity-padded batches carry it ready made
@@ -122,7 +129,7 @@ def _two_view_molecule_repr(args, batch, model, mu, sigma, positions_02=None, de
         x, pos = torch.cat([x_01, x_02]), torch.cat([positions_01, positions_02])
         bvec = torch.cat([batch.batch, batch.batch + b])
         if args.model_3d == "schnet":
-            out = model(x, pos, bvec, num_graphs=2 * b)
+            out = model(x, pos, bvec, num_graphs=2 * b, max_graph_atoms=_max_graph_atoms(batch))
         elif args.model_3d == "painn":
             rei = batch.radius_edge_index
             out = model(x, pos, torch.cat([rei, rei + n], dim=1), bvec, num_graphs=2 * b)
@@ -130,8 +137,8 @@ def _two_view_molecule_repr(args, batch, model, mu, sigma, positions_02=None, de
             raise Exception("3D model {} not included.".format(args.model_3d))
         repr_01, repr_02 = out[:b], out[b:]
     elif args.model_3d == "schnet":
-        repr_01 = model(x_01, positions_01, batch.batch, num_graphs=b)
-        repr_02 = model(x_02, positions_02, batch.batch, num_graphs=b)
+        repr_01 = model(x_01, positions_01, batch.batch, num_graphs=b, max_graph_atoms=_max_graph_atoms(batch))
+        repr_02 = model(x_02, positions_02, batch.batch, num_graphs=b, max_graph_atoms=_max_graph_atoms(batch))
     elif args.model_3d == "painn":
         repr_01 = model(x_01, positions_01, batch.radius_edge_index, batch.batch, num_graphs=b)
         repr_02 = model(x_02, positions_02, batch.radius_edge_index, batch.batch, num_graphs=b)

@@ -153,6 +153,20 @@ int geossl_cfconv_fwd(const float* x, const float* filt, const int32_t* filt_row
 int geossl_cfconv_bwd_x(const float* filt, const int32_t* filt_row, const float* grad_out, const int32_t* t_rowptr,
                         const int32_t* t_eid, const int32_t* t_tgt, int64_t n_atoms, int F, float* grad_x, void* stream);
 
+/* Pair-centric cfconv aggregate for batches of SMALL graphs (F = 128, one filter row per atom pair, geossl_pair_index):
+ * one CTA per graph keeps the graph's operand rows and accumulators in shared memory and streams the graph's contiguous
+ * block of filter rows ONCE, adding W_u * v[s] to row t and W_u * v[t] to row s for pair u = (s, t)  -- the same sums as
+ * geossl_cfconv_fwd (transposed = 0, v = x) / geossl_cfconv_bwd_x (transposed = 1, v = grad_out) with filt_row =
+ * pair_of_edge, in a different (fixed) fp32 summation order; every filter row crosses L2 -> SM once instead of twice
+ * (schnet.py:190,194-195).  graph_ptr (n_graphs+1) int32 atom offsets, pair_rowptr (n_atoms+1), pair_atoms (capacity,2).
+ * max_graph_atoms: host-known bound on the atoms of any graph that has edges (<= geossl_cfconv_pairs_max_atoms(groups));
+ * a larger graph is still summed correctly, by one warp straight in global memory.  tuning: 0 = default, else
+ * groups * 100 + rows (warps per graph; filter rows per register buffer, 8 or 16, two buffers in flight per warp). */
+int geossl_cfconv_pairs_max_atoms(int groups);
+int geossl_cfconv_pairs(const float* v, const float* filt, const int32_t* pair_atoms, const int32_t* pair_rowptr,
+                        const int32_t* graph_ptr, int64_t n_graphs, int max_graph_atoms, int transposed, int tuning,
+                        float* out, void* stream);
+
 /* dW_e = x[src_e] * g[tgt_e]  materialised (E,F)  (second-order path and the unfused comparison). */
 int geossl_cfconv_bwd_w(const float* x, const float* grad_out, const int32_t* rowptr, const int32_t* src,
                         int64_t n_atoms, int F, float* grad_filt, void* stream);

@@ -80,6 +80,69 @@ def test_cfconv_is_deterministic_and_linear():
     assert abs(lhs - rhs) / abs(lhs) < 1e-5
 
 
+@pytest.mark.parametrize("ng,lo,hi,density,n_max,owner_small", [
+    (64, 10, 60, 0.05, 60, False),        # Molecule3D-like sizes
+    (37, 25, 31, 0.05, 31, True),
+    (6, 50, 64, 0.3, 64, False),          # dense: rows truncated at 32 neighbours => orphan pairs (one direction only)
+    (5, 40, 70, 0.3, 48, False),          # graphs above the bound take the in-kernel global-memory path
+    (3, 1, 2, 0.05, 8, False),            # single atoms / one pair
+])
+def test_pair_centric_cfconv_matches_row_gather(ng, lo, hi, density, n_max, owner_small, monkeypatch):
+    """geossl_cfconv_pairs (one CTA per graph, every filter row read once, both endpoints updated) against the row-gather
+    kernels with shared filter rows: same sums in another fp32 order.  Covers orphan pairs, the oversize-graph path,
+    both adjoint directions, every tuning code, and bitwise repeatability (no atomics)."""
+    monkeypatch.setattr(ops, "PAIR_OWNER_SMALL", owner_small)
+    b = synthetic_batch(ng, lo, hi, seed=3 * ng + lo, with_pairs=False, density=density)
+    graph = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), 10.0, num_graphs=ng).ensure_pairs()
+    n = b.positions.shape[0]
+    u, e = int(graph.n_pairs_dev.item()), graph.num_edges
+    if density > 0.2:
+        assert u > e // 2                                            # some pair lost its reverse direction
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(n, 128, device=DEV, generator=gen)
+    W = torch.randn(graph.capacity, 128, device=DEV, generator=gen)
+    want_f = ops._cfconv_fwd(x, W, graph, graph.pair_of_edge)
+    want_t = ops._cfconv_bwd_x(W, x, graph, graph.pair_of_edge)
+    graph.max_graph_atoms = n_max
+    for tuning in (0, 116, 208, 216, 308, 316, 408, 416):
+        monkeypatch.setattr(ops, "CFCONV_PAIRS_TUNING", tuning)
+        got_f = ops._cfconv_pairs(x, W, graph, False)
+        got_t = ops._cfconv_pairs(x, W, graph, True)
+        assert rel_err(got_f, want_f) <= 2e-6, tuning
+        assert rel_err(got_t, want_t) <= 2e-6, tuning
+        assert torch.equal(got_f, ops._cfconv_pairs(x, W, graph, False))
+    # adjoint identity <A x, g> = <x, A^T g> between the two directions of the new kernel
+    monkeypatch.setattr(ops, "CFCONV_PAIRS_TUNING", 0)
+    gq = torch.randn(n, 128, device=DEV, generator=gen)
+    lhs = (ops._cfconv_pairs(x, W, graph, False).double() * gq.double()).sum()
+    rhs = (x.double() * ops._cfconv_pairs(gq, W, graph, True).double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+def test_fused_layer_takes_the_pair_centric_kernel_when_graph_sizes_are_known():
+    """CFConvLayer forward + backward with and without the host-side bound on the graph size: identical results up to
+    summation order; the bound is what selects geossl_cfconv_pairs (no source-sorted view is built then)."""
+    b = synthetic_batch(16, 12, 30, seed=4, with_pairs=False)
+    assert b.extras["max_graph_atoms"] == int(torch.bincount(b.batch).max())
+    w1, b1, w2, b2 = _layer_params(128, 50, 1)
+    offset = torch.linspace(0.0, 10.0, 50)
+    coeff = O.smearing_coeff(offset)
+    gen = torch.Generator().manual_seed(2)
+    x, gout = torch.randn(b.positions.shape[0], 128, generator=gen), torch.randn(b.positions.shape[0], 128, generator=gen)
+    res = []
+    for bound in (None, b.extras["max_graph_atoms"]):
+        graph = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), 10.0, num_graphs=16, max_graph_atoms=bound)
+        if ops.FILTER_MODE != "simt":
+            assert (graph.t_rowptr is None) == (bound is not None)
+        cw = [t.to(DEV).requires_grad_() for t in (w1, b1, w2, b2)]
+        xc = x.to(DEV).requires_grad_()
+        out = ops.CFConvLayer.apply(xc, *cw, offset.to(DEV), graph, coeff, 10.0)
+        out.backward(gout.to(DEV))
+        res.append([out.detach(), xc.grad] + [t.grad for t in cw])
+    for a, c in zip(*res):
+        assert rel_err(a, c) <= 2e-6
+
+
 @pytest.mark.parametrize("name", ["schnet_small", "schnet_trunc"])
 def test_schnet_module_vs_golden(name, filter_mode):
     g = Golden(name)
