@@ -440,27 +440,33 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
     }
 }
 
-__global__ void filter_bwd_tc_reduce_kernel(const float* __restrict__ workspace, int n_parts, int G,
-                                            float* __restrict__ gw1, float* __restrict__ gb1,
-                                            float* __restrict__ gw2, float* __restrict__ gb2) {
+// Sum of the per-CTA partials in a fixed order (deterministic).  Four adjacent lanes share one output and take every fourth
+// partial each (two independent chains per lane keep loads in flight), then combine by two shuffles: 4x the parallelism of
+// one thread per output for the same 15 MB read (the kernel sits on the critical path of every layer's backward).
+__global__ void __launch_bounds__(256)
+filter_bwd_tc_reduce_kernel(const float* __restrict__ workspace, int n_parts, int G,
+                            float* __restrict__ gw1, float* __restrict__ gb1,
+                            float* __restrict__ gw2, float* __restrict__ gb2) {
     pdl_launch_dependents();
     pdl_wait();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= Part::kFloats) return;
-    const bool w1_slot = idx >= Part::kW1 && idx < Part::kB2;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = gid >> 2, part = gid & 3;
+    const bool live = idx < Part::kFloats;
+    const bool w1_slot = live && idx >= Part::kW1 && idx < Part::kB2;
     const int g = w1_slot ? (idx - Part::kW1) / 128 : 0;
-    if (w1_slot && g >= G) return;                                      // padded gaussians are never written
-    // four independent chains (fixed association order => still deterministic) keep enough loads in flight
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int p = 0;
-    for (; p + 3 < n_parts; p += 4) {
-        s0 += workspace[(int64_t)p * Part::kFloats + idx];
-        s1 += workspace[(int64_t)(p + 1) * Part::kFloats + idx];
-        s2 += workspace[(int64_t)(p + 2) * Part::kFloats + idx];
-        s3 += workspace[(int64_t)(p + 3) * Part::kFloats + idx];
+    float s0 = 0.f, s1 = 0.f;
+    if (live && !(w1_slot && g >= G)) {                                  // padded gaussians are never written
+        int p = part;
+        for (; p + 4 < n_parts; p += 8) {
+            s0 += workspace[(int64_t)p * Part::kFloats + idx];
+            s1 += workspace[(int64_t)(p + 4) * Part::kFloats + idx];
+        }
+        if (p < n_parts) s0 += workspace[(int64_t)p * Part::kFloats + idx];
     }
-    for (; p < n_parts; ++p) s0 += workspace[(int64_t)p * Part::kFloats + idx];
-    const float s = (s0 + s1) + (s2 + s3);
+    float s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (!live || part != 0 || (w1_slot && g >= G)) return;
     if (idx < Part::kW1) gw2[idx] = s;
     else if (w1_slot) gw1[((idx - Part::kW1) % 128) * G + g] = s;
     else if (idx < Part::kB1) gb2[idx - Part::kB2] = s;
@@ -508,7 +514,7 @@ int geossl_filter_bwd_tc(const float* edge_dist, const int32_t* n_edges_dev, int
                                (const int2*)nullptr, workspace));
     }
     GEOSSL_LAUNCH_CHECK();
-    GEOSSL_CUDA(launch_pdl(tc::filter_bwd_tc_reduce_kernel, dim3((tc::Part::kFloats + 255) / 256), dim3(256), 0, as_stream(stream),
+    GEOSSL_CUDA(launch_pdl(tc::filter_bwd_tc_reduce_kernel, dim3((4 * tc::Part::kFloats + 255) / 256), dim3(256), 0, as_stream(stream),
                            workspace, (int)kNumSM, G, gw1, gb1, gw2, gb2));
     GEOSSL_LAUNCH_CHECK();
     return 0;

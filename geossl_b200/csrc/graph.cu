@@ -289,7 +289,16 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
         // (two barriers in all instead of four per 1024 elements)
         const int c = (n + 1023) / 1024, lo = min(tid * c, n), hi = min(lo + c, n);
         int sum = 0;
-        for (int i = lo; i < hi; ++i) sum += deg[i];
+        int d16[16];                                            // c <= 16 (n <= 16384): the thread's elements stay in registers,
+        const bool cached = c <= 16;                            // all loads in flight at once instead of c dependent round trips
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d16[j] = (lo + j < hi) ? deg[lo + j] : 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum += d16[j];
+        } else {
+            for (int i = lo; i < hi; ++i) sum += deg[i];
+        }
         int v = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -310,7 +319,12 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
         __syncthreads();
         int run = (w == 0 ? 0 : warp_tot[w - 1]) + v - sum;       // exclusive prefix of this thread's first element
         if (tid == 0) out[0] = 0;
-        for (int i = lo; i < hi; ++i) { run += deg[i]; out[i + 1] = run; }
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { run += d16[j]; if (lo + j < hi) out[lo + j + 1] = run; }
+        } else {
+            for (int i = lo; i < hi; ++i) { run += deg[i]; out[i + 1] = run; }
+        }
         return;
     }
     if (tid == 0) { carry_s = 0; out[0] = 0; }

@@ -588,7 +588,7 @@ static int node_grid(int64_t n_rows) {
 // a smaller grid (several row tiles per CTA, accumulated in TMEM) cuts the partial traffic and leaves SMs to the main chain.
 static int wgrad_grid(int64_t n_rows) {
     int64_t tiles = (n_rows + kNR - 1) / kNR;
-    static const int cap = [] { const char* e = getenv("GEOSSL_WGRAD_CTAS"); return e ? atoi(e) : 80; }();
+    static const int cap = [] { const char* e = getenv("GEOSSL_WGRAD_CTAS"); return e ? atoi(e) : 120; }();
     if (tiles >= 8 * kNumSM) return kNumSM;                  // edge-sized inputs (PaiNN's filter GEMM): a full persistent grid
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
