@@ -24,7 +24,8 @@ import torch  # noqa: E402
 METRIC = "GeoSSL-DDM SchNet train molecules/s at 1/2/4/8 B200; cfconv % HBM roofline"
 CFG = dict(batch_per_gpu=256, atoms=30, cutoff=10.0, num_gaussians=50, hidden=128, filters=128, interactions=6,
            sigma_levels=50, anneal_power=2.0, pos_sigma=0.3, lr=5e-4)
-NCU_TRAFFIC_CFCONV_FWD = 123.69e6 + 6.86e6     # bytes per launch of the bench workload (profiles/r01_v32_ncu_full.txt)
+NCU_TRAFFIC_CFCONV_FWD = 123.69e6 + 6.86e6     # bytes per launch of the bench workload, row-gather kernel (profiles/r01_v32_ncu_full.txt)
+NCU_TRAFFIC_CFCONV_PAIRS = 121.96e6 + 4.25e6   # pair-centric kernel: dram read + mean write per launch (profiles/r02_v22_ncu_full.txt)
 PAINN_METRIC = "GeoSSL-DDM PaiNN train molecules/s (BASELINE configs[2], secondary)"
 PAINN_WORKLOAD = ("configs[2]: PaiNN GeoSSL-DDM pretraining step, F=128, 3 interactions, 20 RBF, cutoff 5 A, synthetic Molecule3D-shaped "
                   "conformers, batch 256 per GPU x 30 atoms, data-parallel")
@@ -448,24 +449,32 @@ def run_product(args):
     # one encoder launch processes BOTH views stacked as 2B graphs (pretrain._encode_stacked): size the work from that graph
     b0 = dev_pool[0]
     pos2 = torch.cat([b0.positions, b0.positions + CFG["pos_sigma"] * torch.randn_like(b0.positions)])
-    g = ops.radius_csr(pos2, torch.cat([b0.batch, b0.batch + B]), CFG["cutoff"], num_graphs=2 * B)
+    g = ops.radius_csr(pos2, torch.cat([b0.batch, b0.batch + B]), CFG["cutoff"], num_graphs=2 * B,
+                       max_graph_atoms=b0.extras.get("max_graph_atoms"))
     n_atoms, n_edges, F_, G = pos2.shape[0], g.num_edges, CFG["filters"], CFG["num_gaussians"]
     n_pairs = int(b0.extras["n_pairs_live"]) if args.atoms_max else b0.super_edge_index.shape[1]
     # filter rows: one per undirected atom pair when the two directions share it (ops.SHARE_PAIR_FILTERS), else one per edge
     shared = ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE != "simt"
     n_rows_w = int(g.ensure_pairs().n_pairs_dev.item()) if shared else n_edges
-    # algorithmic bytes of cfconv forward: every filter row once + x in + m out + src ids (+ the pair map) + rowptr
-    cf_bytes = 4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + 4 * n_edges * (2 if shared else 1) + 4 * (n_atoms + 1)
+    pair_kernel = shared and ops._pairs_kernel_applies(g)       # geossl_cfconv_pairs: one CTA per molecule, rows read once
+    # algorithmic bytes of cfconv forward: every filter row once + x in + m out + the index arrays the kernel reads
+    # (row gather: src ids (+ the pair map) + rowptr; pair-centric: the (s, t) pair records + pair_rowptr + graph_ptr)
+    idx_bytes = (8 * n_rows_w + 4 * (n_atoms + 1) + 4 * (2 * B + 1)) if pair_kernel else (4 * n_edges * (2 if shared else 1) + 4 * (n_atoms + 1))
+    cf_bytes = 4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + idx_bytes
     cf_bytes_per_edge_form = 4 * F_ * n_edges + 2 * 4 * F_ * n_atoms + 4 * n_edges + 4 * (n_atoms + 1)   # 551 B/edge
     roof = None
     others = {}
     if "cfconv_fwd" in ktimes:
         t = ktimes["cfconv_fwd"]["mean_ms"] / 1e3
         ach = cf_bytes / t / 1e9
-        roof = {"kernel": "cfconv_gather_async_kernel<false> (cfconv forward, F = 128)", "bound": "hbm", "achieved": ach,
+        full_size = shared and n_edges > 400_000 and not args.atoms_max
+        roof = {"kernel": ("cfconv_pairs_kernel<2, 8, false> (cfconv forward, F = 128, one CTA per molecule)" if pair_kernel
+                           else "cfconv_gather_async_kernel<false> (cfconv forward, F = 128)"), "bound": "hbm", "achieved": ach,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_CFCONV_FWD if (shared and n_edges > 400_000) else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_v32_ncu_full.txt",
+                "frac": ach / peaks["hbm_gbs"],
+                "traffic": (NCU_TRAFFIC_CFCONV_PAIRS if pair_kernel else NCU_TRAFFIC_CFCONV_FWD) if full_size else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
+                                  + ("profiles/r02_v22_ncu_full.txt" if pair_kernel else "profiles/r01_v32_ncu_full.txt"),
                 "peak_source": peaks["src"],
                 "algorithmic_bytes_per_launch": cf_bytes, "filter_rows_per_launch": n_rows_w, "mean_ms": 1e3 * t,
                 "launches_timed": ktimes["cfconv_fwd"]["n"],
@@ -487,7 +496,7 @@ def run_product(args):
                              if k.startswith("filter") else "3 split-precision MMAs per product; useful FLOPs against the bf16 tensor peak"}
         if "cfconv_bwd_x" in ktimes:
             tt = ktimes["cfconv_bwd_x"]["mean_ms"] / 1e3
-            bb = 4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + 4 * n_edges * (3 if shared else 2) + 4 * (n_atoms + 1)
+            bb = cf_bytes if pair_kernel else 4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + 4 * n_edges * (3 if shared else 2) + 4 * (n_atoms + 1)
             others["cfconv_bwd_x"] = {"bound": "hbm", "achieved": bb / tt / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                       "frac": bb / tt / 1e9 / peaks["hbm_gbs"], "mean_ms": 1e3 * tt,
                                       "share_of_step": ktimes["cfconv_bwd_x"]["total_ms"] / n_k / (ms / args.steps)}
@@ -506,7 +515,7 @@ def run_product(args):
     fl_filter = n_rows_w * (2 * G * F_ + 2 * F_ * F_ + 2 * (2 * F_ * F_) + 2 * G * F_) * L            # fwd + bwd, per step
     fl_dense = n_atoms * 2 * F_ * F_ * 3 * (3 * L + 2)                                                # fwd + dgrad + wgrad
     fl_head = n_pairs * 50_048 * 3 * 2                                                                # two heads, fwd + bwd
-    bytes_hbm = L * (cf_bytes + (4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + 4 * n_edges * (3 if shared else 2))   # cfconv fwd + dx
+    bytes_hbm = L * (cf_bytes + (cf_bytes if pair_kernel else 4 * F_ * n_rows_w + 2 * 4 * F_ * n_atoms + 4 * n_edges * (3 if shared else 2))   # cfconv fwd + dx
                      + 4 * F_ * n_rows_w)                                                             # filter rows written once
     t_tensor = 3 * (fl_filter + fl_dense + fl_head) / (peaks["bf16_tflops_sustained"] * 1e12)
     t_hbm = bytes_hbm / (peaks["hbm_gbs"] * 1e9)
