@@ -80,11 +80,15 @@ class CFConv(torch.nn.Module):
         return ops.linear(x, self.lin2, images=images)
 
     # ---- composable path (any derivative order): filter from torch ops, aggregate from the CUDA primitive
-    def forward_composed(self, x, graph, edge_weight, edge_attr):
+    def forward_composed(self, x, graph, edge_weight, edge_attr, pairs=False):
+        """``pairs``: ``edge_weight`` / ``edge_attr`` hold one row per undirected atom pair (ops.pair_endpoints)."""
         C = 0.5 * (torch.cos(edge_weight * PI / self.cutoff) + 1.0)
-        W = self.nn(edge_attr) * C.view(-1, 1)
+        if ops.filter_mlp_applies(self.nn[0], self.nn[2], edge_attr):
+            W = ops.filter_mlp(edge_attr, self.nn[0], self.nn[2]) * C.view(-1, 1)      # tensor-core products, any order
+        else:
+            W = self.nn(edge_attr) * C.view(-1, 1)
         x = self.lin1(x)
-        x = ops.CFConvAggregate.apply(x, W, graph)
+        x = (ops.CFConvAggregateP if pairs else ops.CFConvAggregate).apply(x, W, graph)
         return self.lin2(x)
 
     def forward(self, x, edge_index, edge_weight, edge_attr, batch=None):
@@ -131,8 +135,8 @@ class InteractionBlock(torch.nn.Module):
         return ops.linear(self.conv.forward_graph(x, graph, smearing, images), self.lin, pre_ssp=True, residual=residual,
                           images=images)
 
-    def forward_composed(self, x, graph, edge_weight, edge_attr):
-        return self.lin(self.act(self.conv.forward_composed(x, graph, edge_weight, edge_attr)))
+    def forward_composed(self, x, graph, edge_weight, edge_attr, pairs=False):
+        return self.lin(self.act(self.conv.forward_composed(x, graph, edge_weight, edge_attr, pairs)))
 
     def forward(self, x, edge_index, edge_weight, edge_attr, batch=None):
         return self.lin(self.act(self.conv(x, edge_index, edge_weight, edge_attr, batch)))
@@ -194,11 +198,18 @@ class SchNet(torch.nn.Module):
         fused = False
         if pos.requires_grad and torch.is_grad_enabled():
             ge = graph.exact()
-            row, col = ge.src.long(), ge.tgt.long()
+            # one filter row per atom PAIR (|pos_j - pos_i| == |pos_i - pos_j| bit for bit): half the edge-sized work of
+            # the double-backward path; needs the per-pair index, which the exact copy builds from its edge lengths
+            pairs = (ops.COMPOSED_PAIRS and ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE != "simt"
+                     and (ge.pair_rowptr is not None or ge.dist is not None))
+            if pairs:
+                row, col = ops.pair_endpoints(ge.ensure_pairs())
+            else:
+                row, col = ge.src.long(), ge.tgt.long()
             edge_weight = (pos[row] - pos[col]).norm(dim=-1)
             edge_attr = self.distance_expansion(edge_weight)
             for interaction in self.interactions:
-                h = h + interaction.forward_composed(h, ge, edge_weight, edge_attr)
+                h = h + interaction.forward_composed(h, ge, edge_weight, edge_attr, pairs=pairs)
         else:
             layers = [self.lin1, self.lin2]
             for interaction in self.interactions:

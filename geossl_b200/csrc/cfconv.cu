@@ -409,6 +409,31 @@ cfconv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ g, co
     }
 }
 
+// Edge product of the shared-row aggregate: dW_u = x[s] * g[t] (+ x[t] * g[s] when the reverse direction exists), one row
+// per atom pair u = (s, t) -- the filter gradient of geossl_cfconv_fwd with filt_row = pair_of_edge, materialised (U,F) for
+// the composed double-backward path.
+template <int F>
+__global__ void __launch_bounds__(256)
+cfconv_pair_product_kernel(const float* __restrict__ x, const float* __restrict__ g, const int2* __restrict__ pair_atoms,
+                           int64_t n_pairs, float* __restrict__ dfilt) {
+    constexpr int LPR = F / 4, EPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int f = (lane % LPR) * 4, sub = lane / LPR;
+    const int64_t u = warp * EPW + sub;
+    if (u >= n_pairs) return;
+    const int2 st = __ldg(pair_atoms + u);
+    const bool both = st.y >= 0;
+    const int s = st.x, t = both ? st.y : ~st.y;
+    const float4 xs = ldg4(x + (int64_t)s * F + f), gt = ldg4(g + (int64_t)t * F + f);
+    float4 r = make_float4(xs.x * gt.x, xs.y * gt.y, xs.z * gt.z, xs.w * gt.w);
+    if (both) {
+        const float4 xt = ldg4(x + (int64_t)t * F + f), gs = ldg4(g + (int64_t)s * F + f);
+        fma4(r, xt, gs);
+    }
+    st_stream4(dfilt + u * F + f, r);
+}
+
 template <bool TRANSPOSED>
 static void launch_async(int blocks, cudaStream_t st, const float* filt, const int32_t* filt_row, const float* v, const int32_t* ptr,
                          const int32_t* idx_a, const int32_t* idx_b, int n, float* out) {
@@ -502,6 +527,23 @@ int geossl_cfconv_bwd_x(const float* filt, const int32_t* filt_row, const float*
     if (n_atoms == 0) return 0;
     GEOSSL_REQUIRE(filt && grad_out && t_rowptr && t_eid && t_tgt && grad_x && n_atoms > 0, "null pointer");
     DISPATCH_F(F, launch_bwd_x<kF>(filt, filt_row, grad_out, t_rowptr, t_eid, t_tgt, n_atoms, grad_x, as_stream(stream)));
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+int geossl_cfconv_pair_product(const float* x, const float* grad_out, const int32_t* pair_atoms, int64_t n_pairs, int F,
+                               float* grad_filt, void* stream) {
+    if (n_pairs == 0) return 0;
+    GEOSSL_REQUIRE(x && grad_out && pair_atoms && grad_filt && n_pairs > 0, "null pointer");
+    GEOSSL_REQUIRE((reinterpret_cast<uintptr_t>(pair_atoms) & 7) == 0, "pair_atoms must be 8-byte aligned");
+    const int2* pa = reinterpret_cast<const int2*>(pair_atoms);
+    cudaStream_t st = as_stream(stream);
+    switch (F) {
+        case 32: cfconv_pair_product_kernel<32><<<(int)((n_pairs * 8 + 255) / 256), 256, 0, st>>>(x, grad_out, pa, n_pairs, grad_filt); break;
+        case 64: cfconv_pair_product_kernel<64><<<(int)((n_pairs * 16 + 255) / 256), 256, 0, st>>>(x, grad_out, pa, n_pairs, grad_filt); break;
+        case 128: cfconv_pair_product_kernel<128><<<(int)((n_pairs * 32 + 255) / 256), 256, 0, st>>>(x, grad_out, pa, n_pairs, grad_filt); break;
+        default: set_error("%s: unsupported width F=%d (32/64/128)", __func__, F); return GEOSSL_EINVAL;
+    }
     GEOSSL_LAUNCH_CHECK();
     return 0;
 }

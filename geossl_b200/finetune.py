@@ -144,13 +144,19 @@ class GraphedMD17Step:
 
     def _structure(self, batch):
         g = ops.radius_csr(batch.positions.detach(), batch.batch, self.model.cutoff, num_graphs=batch.num_graphs)
-        return g.exact()                                           # host read of the edge count (outside any capture)
+        ge = g.exact()                                             # host read of the edge count (outside any capture)
+        if ops.COMPOSED_PAIRS and ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE != "simt":
+            ge.num_pairs                                           # ... and of the pair count (builds the pair index)
+        return ge
 
     def _capture(self, batch, ge):
         e = ge.num_edges
         sg = ops.RadiusCSR(ge.n_atoms, e, ge.rowptr.clone(), ge.src.clone(), ge.tgt.clone(), None, batch.batch.clone(), ge.graph_ptr.clone())
         sg.t_rowptr, sg.t_eid, sg.t_tgt = ge.t_rowptr.clone(), ge.t_eid.clone(), ge.t_tgt.clone()
         sg._n_edges, sg._exact = e, sg
+        if ge.pair_rowptr is not None:
+            sg.pair_rowptr, sg.pair_of_edge, sg.pair_atoms = ge.pair_rowptr.clone(), ge.pair_of_edge.clone(), ge.pair_atoms.clone()
+            sg._n_pairs = ge.num_pairs
         extras = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.extras.items() if k != "graph"}
         extras["graph"] = sg
         static = type(batch)(batch.x.clone(), batch.positions.detach().clone(), sg.batch, None, None, batch.num_graphs, sg.graph_ptr, extras)
@@ -187,7 +193,7 @@ class GraphedMD17Step:
 
     def __call__(self, batch):
         ge = self._structure(batch)
-        e = ge.num_edges
+        e = (ge.num_edges, ge.num_pairs if ge.pair_rowptr is not None else -1)
         entry = self.graphs.get(e)
         if entry is None:
             if len(self.graphs) >= self.max_graphs or self.capture_error is not None:
@@ -205,7 +211,10 @@ class GraphedMD17Step:
             sg.batch.copy_(batch.batch, non_blocking=True)
             for k in ("y", "force"):
                 static.extras[k].copy_(batch.extras[k], non_blocking=True)
-            for name in ("rowptr", "src", "tgt", "t_rowptr", "t_eid", "t_tgt", "graph_ptr"):
+            names = ("rowptr", "src", "tgt", "t_rowptr", "t_eid", "t_tgt", "graph_ptr")
+            if sg.pair_rowptr is not None:
+                names += ("pair_rowptr", "pair_of_edge", "pair_atoms")
+            for name in names:
                 getattr(sg, name).copy_(getattr(ge, name), non_blocking=True)
         graph.replay()
         return loss

@@ -195,6 +195,15 @@ class RadiusCSR:
                                                 _p(self.pair_dist), _stream()), "pair_index")
         return self
 
+    @property
+    def num_pairs(self):
+        """Host-side count of undirected pairs (one sync, cached) -- the composed double-backward path sizes its per-pair
+        tensors with it, like ``num_edges`` for the per-edge form."""
+        if getattr(self, "_n_pairs", None) is None:
+            self.ensure_pairs()
+            self._n_pairs = int(self.pair_rowptr[self.n_atoms].item())
+        return self._n_pairs
+
     def exact(self):
         """Copy trimmed to exactly E edges (host sync) -- used by the general double-backward path."""
         if self._exact is None:
@@ -407,6 +416,76 @@ class CFConvEdgeProduct(torch.autograd.Function):
         gx = CFConvAggregateT.apply(v, grad_out, ctx.graph) if ctx.needs_input_grad[0] else None
         gg = CFConvAggregate.apply(x, v, ctx.graph) if ctx.needs_input_grad[1] else None
         return gx, gg, None
+
+
+# ---- the same three primitives with ONE filter row per atom pair (rows indexed through graph.pair_of_edge): the composed
+# double-backward path then builds and differentiates U = E/2 filter rows instead of E (COMPOSED_PAIRS)
+COMPOSED_PAIRS = True
+
+
+class CFConvAggregateP(torch.autograd.Function):
+    """m_i = sum_{e in row i} x[src_e] * W[pair(e)]  with W (U,F), differentiable to any order."""
+
+    @staticmethod
+    def forward(ctx, x, filt, graph):
+        x, filt = _req(x, torch.float32, "x", 2), _req(filt, torch.float32, "filt", 2)
+        ctx.graph = graph
+        ctx.save_for_backward(x, filt)
+        return _cfconv_fwd(x, filt, graph, graph.pair_of_edge)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, filt = ctx.saved_tensors
+        gx = CFConvAggregateTP.apply(filt, grad_out, ctx.graph) if ctx.needs_input_grad[0] else None
+        gw = CFConvPairProduct.apply(x, grad_out, ctx.graph) if ctx.needs_input_grad[1] else None
+        return gx, gw, None
+
+
+class CFConvAggregateTP(torch.autograd.Function):
+    """dx_j = sum_{e: src_e = j} W[pair(e)] * g[tgt_e]."""
+
+    @staticmethod
+    def forward(ctx, filt, grad_out, graph):
+        filt, grad_out = _req(filt, torch.float32, "filt", 2), _req(grad_out, torch.float32, "grad_out", 2)
+        ctx.graph = graph
+        ctx.save_for_backward(filt, grad_out)
+        return _cfconv_bwd_x(filt, grad_out, graph, graph.pair_of_edge)
+
+    @staticmethod
+    def backward(ctx, v):
+        filt, grad_out = ctx.saved_tensors
+        gw = CFConvPairProduct.apply(v, grad_out, ctx.graph) if ctx.needs_input_grad[0] else None
+        gg = CFConvAggregateP.apply(v, filt, ctx.graph) if ctx.needs_input_grad[1] else None
+        return gw, gg, None
+
+
+class CFConvPairProduct(torch.autograd.Function):
+    """dW_u = x[s] * g[t] + x[t] * g[s]  (U,F)  (second term only where the reverse edge exists)."""
+
+    @staticmethod
+    def forward(ctx, x, grad_out, graph):
+        x, grad_out = _req(x, torch.float32, "x", 2), _req(grad_out, torch.float32, "grad_out", 2)
+        ctx.graph = graph
+        ctx.save_for_backward(x, grad_out)
+        u = graph.num_pairs
+        dw = torch.empty((u, x.size(1)), dtype=torch.float32, device=x.device)
+        check(_lib.load().geossl_cfconv_pair_product(_p(x), _p(grad_out), _p(graph.pair_atoms), u, x.size(1), _p(dw), _stream()),
+              "cfconv_pair_product")
+        return dw
+
+    @staticmethod
+    def backward(ctx, v):
+        x, grad_out = ctx.saved_tensors
+        gx = CFConvAggregateTP.apply(v, grad_out, ctx.graph) if ctx.needs_input_grad[0] else None
+        gg = CFConvAggregateP.apply(x, v, ctx.graph) if ctx.needs_input_grad[1] else None
+        return gx, gg, None
+
+
+def pair_endpoints(graph):
+    """(s, t) int64 atom ids of the graph's undirected pairs, (U,) each -- the composed path's per-pair geometry."""
+    pa = graph.pair_atoms[:graph.num_pairs]
+    t = pa[:, 1]
+    return pa[:, 0].long(), torch.where(t < 0, torch.bitwise_not(t), t).long()
 
 
 # =====================================================================================================
@@ -951,6 +1030,134 @@ def dense(x, layer, images=None, pre_act=ACT_NONE):
     elif pre_act == ACT_SSP:
         x = torch.nn.functional.softplus(x) - 0.6931471824645996
     return torch.nn.functional.linear(x, w, layer.bias)
+
+
+# =====================================================================================================
+# tensor-core products closed under differentiation (the edge-sized filter MLP of the double-backward path)
+# =====================================================================================================
+# Force training (finetune_md17.py:32-54) differentiates the backward pass again, so the fused once-differentiable filter
+# kernels do not apply and the filter MLP (schnet.py:141-145) runs as separate products over ~10^5 edge rows.  The three
+# forms below are each other's derivatives, so autograd can differentiate them to any order while every product stays on the
+# 128 x 128 tcgen05 block kernels (split-precision operands, fp32 accumulate):
+#   MatXWt : y = x[:, :k] @ W[:, :k]^T (+ b)     geossl_linear_tc_block, weight image as stored
+#   MatXW  : y = g @ W                          geossl_linear_tc_block, transposed weight image
+#   MatTX  : G = a^T @ b[:, :k]                 geossl_linear_wgrad_tc_block (reduction over the rows)
+# W and G are (128,128); x / b may be K-padded operands with k in {32, 64, 128} live columns (the 50 gaussians, padded to 64).
+def _mm_image(w, transpose, bf16_parts):
+    lib = _lib.load()
+    image = torch.empty(lib.geossl_weight_image_bytes(), dtype=torch.uint8, device=w.device)
+    check(lib.geossl_pack_weight(_p(w), 1 if transpose else 0, 1 if bf16_parts else 0, _p(image), _stream()), "pack_weight")
+    return image
+
+
+def _mm_check(t, name, cols=None):
+    t = _req(t, torch.float32, name, 2)
+    if cols is not None and t.size(1) not in cols:
+        raise RuntimeError(f"geossl_b200: `{name}` must have {cols} columns, got {t.size(1)}")
+    return t
+
+
+class MatXWt(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, fp16_parts):
+        x, w = _mm_check(x, "x", (32, 64, 128)), _mm_check(w, "w", (128,))
+        if w.size(0) != 128:
+            raise RuntimeError("geossl_b200: MatXWt is built for (128,128) weights")
+        bias = None if bias is None else _req(bias, torch.float32, "bias", 1)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w)
+        n, k = x.shape
+        y = torch.empty((n, 128), dtype=torch.float32, device=x.device)
+        if n:
+            image = _mm_image(w, False, not fp16_parts)
+            _timed("mm_xwt", lambda: _lib.load().geossl_linear_tc_block(
+                _p(x), k, n, _p(image), _p(bias), ACT_SSP, 0, None, 128, None, 128, _p(y), 128, 0 if fp16_parts else 1, k, _stream()))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = MatXW.apply(gy, w)[:, :x.size(1)] if ctx.needs_input_grad[0] else None
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        gw = gb = None
+        if ctx.needs_input_grad[1]:
+            gw, colsum = MatTX.apply(gy, x, want_b)          # the bias gradient is the kernel's column sum of gy: no extra pass
+            gb = colsum if want_b else None
+        elif want_b:
+            gb = gy.sum(0)
+        return gx, gw, gb, None
+
+
+class MatXW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, w):
+        g, w = _mm_check(g, "g", (128,)), _mm_check(w, "w", (128,))
+        ctx.save_for_backward(g, w)
+        n = g.size(0)
+        y = torch.empty((n, 128), dtype=torch.float32, device=g.device)
+        if n:
+            image = _mm_image(w, True, True)
+            _timed("mm_xw", lambda: _lib.load().geossl_linear_tc_block(
+                _p(g), 128, n, _p(image), None, ACT_SSP, 0, None, 128, None, 128, _p(y), 128, 1, 128, _stream()))
+        return y
+
+    @staticmethod
+    def backward(ctx, go):
+        g, w = ctx.saved_tensors
+        go = go.contiguous()
+        gg = MatXWt.apply(go, w, None, False) if ctx.needs_input_grad[0] else None
+        gw = MatTX.apply(g, go, False)[0] if ctx.needs_input_grad[1] else None
+        return gg, gw
+
+
+class MatTX(torch.autograd.Function):
+    """(a^T @ b[:, :k], column sums of a) -- the second output only when ``want_colsum`` (else an empty tensor)."""
+
+    @staticmethod
+    def forward(ctx, a, b, want_colsum):
+        a, b = _mm_check(a, "a", (128,)), _mm_check(b, "b", (32, 64, 128))
+        ctx.save_for_backward(a, b)
+        ctx.set_materialize_grads(False)
+        n, k = b.shape
+        out = torch.zeros((128, 128), dtype=torch.float32, device=a.device)
+        colsum = torch.zeros(128 if want_colsum else 0, dtype=torch.float32, device=a.device)
+        if n:
+            lib = _lib.load()
+            ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=a.device)
+            _timed("mm_tx", lambda: lib.geossl_linear_wgrad_tc_block(_p(a), 128, _p(b), k, n, 0, _p(ws), _p(out), 128,
+                                                                     _p(colsum) if want_colsum else None, k, _stream()))
+        return out, colsum
+
+    @staticmethod
+    def backward(ctx, gG, gcol):
+        a, b = ctx.saved_tensors
+        ga = gb = None
+        if gG is not None:
+            gG = gG.contiguous()
+            ga = MatXWt.apply(b, gG, None, False) if ctx.needs_input_grad[0] else None
+            gb = MatXW.apply(a, gG)[:, :b.size(1)] if ctx.needs_input_grad[1] else None
+        if gcol is not None and gcol.numel() and ctx.needs_input_grad[0]:
+            ga = gcol.unsqueeze(0).expand_as(a) if ga is None else ga + gcol.unsqueeze(0)
+        return ga, gb, None
+
+
+def filter_mlp_applies(lin0, lin2, edge_attr):
+    return (FILTER_MODE != "simt" and edge_attr.is_cuda and edge_attr.dim() == 2 and edge_attr.dtype == torch.float32
+            and tuple(lin2.weight.shape) == (128, 128) and lin0.weight.size(0) == 128 and lin0.weight.size(1) <= 128
+            and lin0.bias is not None and lin2.bias is not None)
+
+
+def filter_mlp(edge_attr, lin0, lin2):
+    """``lin2(ssp(lin0(edge_attr)))`` (the filter-generating network, schnet.py:141-145) differentiable to any order with
+    both products on the tensor cores; the activation stays a torch op between them."""
+    G = edge_attr.size(1)
+    k = 32 if G <= 32 else (64 if G <= 64 else 128)
+    x = torch.nn.functional.pad(edge_attr, (0, k - G)) if k != G else edge_attr
+    w1 = torch.nn.functional.pad(lin0.weight, (0, 128 - G)) if G != 128 else lin0.weight
+    h = MatXWt.apply(x, w1, lin0.bias, True)
+    h = torch.nn.functional.softplus(h) - 0.6931471824645996
+    return MatXWt.apply(h, lin2.weight, lin2.bias, True)
 
 
 # =====================================================================================================

@@ -171,6 +171,12 @@ int geossl_cfconv_pairs(const float* v, const float* filt, const int32_t* pair_a
 int geossl_cfconv_bwd_w(const float* x, const float* grad_out, const int32_t* rowptr, const int32_t* src,
                         int64_t n_atoms, int F, float* grad_filt, void* stream);
 
+/* dW_u = x[s] * g[t] (+ x[t] * g[s] when the reverse edge exists) for every atom pair u = (s, t) of geossl_pair_index:
+ * the edge product of the shared-row aggregate, materialised (n_pairs,F) (composed double-backward path with one filter
+ * row per pair; schnet.py:190,194-195 differentiated w.r.t. W). */
+int geossl_cfconv_pair_product(const float* x, const float* grad_out, const int32_t* pair_atoms, int64_t n_pairs, int F,
+                               float* grad_filt, void* stream);
+
 /* Backward of the filter network fused with dW_e = x[src_e]*g[tgt_e] (never materialised):
  * recomputes rbf / Lin1 / ssp from d_e and accumulates gw1 (F,G), gb1 (F), gw2 (F,F), gb2 (F).
  * If grad_filt != NULL it is used as dW_e instead of x/g (then x, grad_out, src, edge_tgt may be NULL).

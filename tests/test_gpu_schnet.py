@@ -198,6 +198,101 @@ def test_md17_double_backward_vs_golden():
         assert rel_err(dict(lin.named_parameters())[k].grad, ref) <= 2e-4
 
 
+def test_md17_force_step_at_full_width_vs_oracle(filter_mode):
+    """finetune_md17.py:32-54 at the real model width (hidden = filters = 128, 50 gaussians): energy, autograd force and the
+    parameter gradients of the force loss (double backward) against the CPU oracle computed in the test.  In the
+    tensor-core modes the edge-sized filter MLP runs on ops.MatXWt / MatXW / MatTX (tcgen05 blocks closed under
+    differentiation) instead of library GEMMs; the 32-wide golden fixture ``md17_small`` cannot reach that path."""
+    from geossl_b200.Geom3D.models import SchNet
+    torch.manual_seed(3)
+    m = SchNet(hidden_channels=128, num_filters=128, num_interactions=3, num_gaussians=50, cutoff=10.0, node_class=9, readout="mean")
+    lin = torch.nn.Linear(128, 1)
+    b = synthetic_batch(6, 21, seed=8, with_pairs=False)
+    gen = torch.Generator().manual_seed(4)
+    y, ft = torch.randn(6, generator=gen), torch.randn(b.positions.shape, generator=gen)
+    # oracle (CPU, torch fp32)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and v.dtype == torch.float32) for k, v in m.state_dict().items()}
+    sdl = {k: v.clone().requires_grad_() for k, v in lin.state_dict().items()}
+    pos = b.positions.clone().requires_grad_()
+    out, _ = O.schnet_forward(sd, b.x[:, 0].contiguous(), pos, b.batch, cutoff=10.0, readout="mean")
+    e_ref = F.linear(out, sdl["weight"], sdl["bias"]).squeeze(1)
+    f_ref = -torch.autograd.grad(e_ref, pos, grad_outputs=torch.ones_like(e_ref), create_graph=True, retain_graph=True)[0]
+    l_ref = 0.05 * F.l1_loss(e_ref, y) + 0.95 * F.l1_loss(f_ref, ft)
+    l_ref.backward()
+    # product
+    m.to(DEV), lin.to(DEV)
+    used = []
+    orig = ops.filter_mlp
+    ops.filter_mlp = lambda *a: used.append(1) or orig(*a)
+    try:
+        posd = b.positions.to(DEV).requires_grad_()
+        rep = m(b.x[:, 0].contiguous().to(DEV), posd, b.batch.to(DEV), num_graphs=6)
+        energy = lin(rep).squeeze(1)
+        force = -torch.autograd.grad(energy, posd, grad_outputs=torch.ones_like(energy), create_graph=True, retain_graph=True)[0]
+        loss = 0.05 * F.l1_loss(energy, y.to(DEV)) + 0.95 * F.l1_loss(force, ft.to(DEV))
+        loss.backward()
+    finally:
+        ops.filter_mlp = orig
+    assert bool(used) == (filter_mode != "simt")
+    assert rel_err(energy, e_ref) <= TOL_OUT and rel_err(force, f_ref) <= TOL_GRAD, (rel_err(energy, e_ref), rel_err(force, f_ref))
+    assert rel_err(loss, l_ref) <= TOL_OUT
+    for k, g in grads_of(m).items():
+        if ".conv.nn." not in k:
+            assert rel_err(g, sd[k].grad) <= 2e-4, (k, rel_err(g, sd[k].grad))
+    for k, g in grads_of(lin).items():
+        assert rel_err(g, sdl[k].grad) <= 2e-4, (k, rel_err(g, sdl[k].grad))
+
+
+@pytest.mark.parametrize("density", [0.05, 0.3])
+def test_pair_row_primitives_match_per_edge_primitives_to_second_order(density):
+    """CFConvAggregateP / TP / PairProduct (one filter row per atom pair) against the per-edge trio fed with
+    W_e = W_u[pair_of_edge]: value, first derivatives and a second derivative.  density 0.3 truncates rows at 32
+    neighbours, so some pairs exist in one direction only."""
+    b = synthetic_batch(5, 30, 60, seed=12, with_pairs=False, density=density)
+    ge = ops.radius_csr(b.positions.to(DEV), b.batch.to(DEV), 10.0, num_graphs=5).exact().ensure_pairs()
+    n, u = b.positions.shape[0], ge.num_pairs
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x0 = torch.randn(n, 128, device=DEV, generator=gen)
+    w0 = torch.randn(u, 128, device=DEV, generator=gen)
+    c = torch.randn(n, 128, device=DEV, generator=gen)
+    poe = ge.pair_of_edge[:ge.num_edges].long()
+
+    def run(agg):
+        x, w = x0.clone().requires_grad_(), w0.clone().requires_grad_()
+        m = agg(x, w)
+        gx, gw = torch.autograd.grad((torch.tanh(m) * c).sum(), (x, w), create_graph=True)
+        second = torch.autograd.grad(gx.square().sum() + gw.square().sum(), (x, w))
+        return m, gx, gw, second[0], second[1]
+
+    got = run(lambda x, w: ops.CFConvAggregateP.apply(x, w, ge))
+    want = run(lambda x, w: ops.CFConvAggregate.apply(x, w[poe], ge))
+    for a, r in zip(got, want):
+        assert rel_err(a, r) <= 1e-5, rel_err(a, r)
+
+
+def test_tensor_core_products_are_closed_under_differentiation():
+    """ops.MatXWt / MatXW / MatTX against torch matmul in float64: values, first derivatives and a second derivative
+    (gradient of a gradient norm), with a K-padded operand (64 live columns)."""
+    gen = torch.Generator(device=DEV).manual_seed(6)
+    n = 1000
+    x = torch.randn(n, 64, device=DEV, generator=gen).requires_grad_()
+    w = (0.2 * torch.randn(128, 128, device=DEV, generator=gen))
+    w[:, 64:] = 0
+    w.requires_grad_()
+    bias = torch.randn(128, device=DEV, generator=gen).requires_grad_()
+    x64, w64, b64 = (t.detach().double().requires_grad_() for t in (x, w, bias))
+
+    def second(xv, wv, bv, mm):
+        yv = torch.tanh(mm(xv, wv, bv))
+        gx, = torch.autograd.grad(yv.square().sum(), xv, create_graph=True)
+        return yv, gx, torch.autograd.grad(gx.square().sum(), (wv, bv))
+
+    y, gx, (gw2, gb2) = second(x, w, bias, lambda a, b_, c: ops.MatXWt.apply(a, b_, c, True))
+    yr, gxr, (gw2r, gb2r) = second(x64, w64, b64, lambda a, b_, c: a @ b_[:, :64].t() + c)
+    assert rel_err(y, yr.float()) <= 1e-5 and rel_err(gx, gxr.float()) <= 1e-4
+    assert rel_err(gw2[:, :64], gw2r[:, :64].float()) <= 2e-4 and rel_err(gb2, gb2r.float()) <= 2e-4
+
+
 def test_full_size_forward_properties_config2(filter_mode):
     """Config 2 (256 x 30 atoms, H=F=128, G=50, L=6): permuting whole molecules permutes the result."""
     torch.manual_seed(0)
