@@ -87,9 +87,9 @@ class CFConv(torch.nn.Module):
             W = ops.filter_mlp(edge_attr, self.nn[0], self.nn[2]) * C.view(-1, 1)      # tensor-core products, any order
         else:
             W = self.nn(edge_attr) * C.view(-1, 1)
-        x = self.lin1(x)
+        x = ops.linear_any_order(x, self.lin1)
         x = (ops.CFConvAggregateP if pairs else ops.CFConvAggregate).apply(x, W, graph)
-        return self.lin2(x)
+        return ops.linear_any_order(x, self.lin2)
 
     def forward(self, x, edge_index, edge_weight, edge_attr, batch=None):
         """Reference signature (schnet.py:185).  ``edge_index`` must be target-sorted with ascending sources
@@ -136,7 +136,7 @@ class InteractionBlock(torch.nn.Module):
                           images=images)
 
     def forward_composed(self, x, graph, edge_weight, edge_attr, pairs=False):
-        return self.lin(self.act(self.conv.forward_composed(x, graph, edge_weight, edge_attr, pairs)))
+        return ops.linear_any_order(self.act(self.conv.forward_composed(x, graph, edge_weight, edge_attr, pairs)), self.lin)
 
     def forward(self, x, edge_index, edge_weight, edge_attr, batch=None):
         return self.lin(self.act(self.conv(x, edge_index, edge_weight, edge_attr, batch)))

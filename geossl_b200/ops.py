@@ -1142,6 +1142,16 @@ class MatTX(torch.autograd.Function):
         return ga, gb, None
 
 
+def linear_any_order(x, layer):
+    """``layer(x)`` for a 128 -> 128 nn.Linear, differentiable to any order on the tensor cores (MatXWt); other shapes,
+    CPU tensors and the exact ``simt`` mode take torch's linear."""
+    w = layer.weight
+    if (FILTER_MODE != "simt" and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and tuple(w.shape) == (128, 128)
+            and x.size(1) == 128):
+        return MatXWt.apply(x, w, layer.bias, True)
+    return layer(x)
+
+
 def filter_mlp_applies(lin0, lin2, edge_attr):
     return (FILTER_MODE != "simt" and edge_attr.is_cuda and edge_attr.dim() == 2 and edge_attr.dtype == torch.float32
             and tuple(lin2.weight.shape) == (128, 128) and lin0.weight.size(0) == 128 and lin0.weight.size(1) <= 128
