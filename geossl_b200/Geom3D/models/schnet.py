@@ -197,6 +197,9 @@ class SchNet(torch.nn.Module):
             graph = ops.radius_csr(pos, batch, self.cutoff, num_graphs=num_graphs, max_graph_atoms=max_graph_atoms)
         fused = False
         if pos.requires_grad and torch.is_grad_enabled():
+            if (ops.COMPOSED_PAIRS and ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE != "simt" and graph.dist is not None
+                    and graph._exact is None):
+                graph.ensure_pairs()                               # before exact(): edge and pair count share one host read
             ge = graph.exact()
             # one filter row per atom PAIR (|pos_j - pos_i| == |pos_i - pos_j| bit for bit): half the edge-sized work of
             # the double-backward path; needs the per-pair index, which the exact copy builds from its edge lengths

@@ -144,10 +144,9 @@ class GraphedMD17Step:
 
     def _structure(self, batch):
         g = ops.radius_csr(batch.positions.detach(), batch.batch, self.model.cutoff, num_graphs=batch.num_graphs)
-        ge = g.exact()                                             # host read of the edge count (outside any capture)
         if ops.COMPOSED_PAIRS and ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE != "simt":
-            ge.num_pairs                                           # ... and of the pair count (builds the pair index)
-        return ge
+            g.ensure_pairs()                                       # pair index on the device first: both counts come back ...
+        return g.exact()                                           # ... in ONE host read (outside any capture)
 
     def _capture(self, batch, ge):
         e = ge.num_edges

@@ -204,15 +204,30 @@ class RadiusCSR:
             self._n_pairs = int(self.pair_rowptr[self.n_atoms].item())
         return self._n_pairs
 
+    def sync_counts(self):
+        """Edge count (and pair count, if the pair index exists) with ONE host read."""
+        if self.pair_rowptr is not None and (self._n_edges is None or getattr(self, "_n_pairs", None) is None):
+            e, u = torch.stack([self.rowptr[self.n_atoms], self.pair_rowptr[self.n_atoms]]).tolist()
+            if e > self.capacity:
+                raise RuntimeError(f"radius graph has {e} edges but capacity is {self.capacity}")
+            self._n_edges, self._n_pairs = int(e), int(u)
+        return self.num_edges
+
     def exact(self):
-        """Copy trimmed to exactly E edges (host sync) -- used by the general double-backward path."""
+        """Copy trimmed to exactly E edges (host sync) -- used by the general double-backward path.  A pair index built
+        before the call is carried over (trimmed to E rows as well)."""
         if self._exact is None:
-            e = self.num_edges
+            e = self.sync_counts()
             self.ensure_transpose()
             g = RadiusCSR(self.n_atoms, e, self.rowptr, self.src[:e].contiguous(), self.tgt[:e].contiguous(),
                           None if self.dist is None else self.dist[:e].contiguous(), self.batch, self.graph_ptr)
             g.t_rowptr, g.t_eid, g.t_tgt = self.t_rowptr, self.t_eid[:e].contiguous(), self.t_tgt[:e].contiguous()
             g._n_edges = e
+            if self.pair_rowptr is not None:
+                g.pair_rowptr, g._n_pairs = self.pair_rowptr, self._n_pairs
+                g.pair_of_edge, g.pair_atoms = self.pair_of_edge[:e].contiguous(), self.pair_atoms[:e].contiguous()
+                g.pair_e1, g.pair_e2, g.pair_dist = self.pair_e1[:e], self.pair_e2[:e], self.pair_dist[:e]
+            g.max_graph_atoms = self.max_graph_atoms
             g._exact = g
             self._exact = g
         return self._exact

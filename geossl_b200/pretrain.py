@@ -349,13 +349,8 @@ class GraphedTrainStep:
         optimizer.zero_grad(set_to_none=True)
         if kernel_timers:
             ops.KERNEL_TIMERS.enable(kernel_timers, in_graph=True)
-        # The chain of kernels on the critical path is captured on a HIGH-priority stream; the weight-gradient kernels of
-        # ops.side_stream_wgrads() run on a default-priority stream, so wherever both have thread blocks pending the
-        # scheduler hands SMs to the critical path first (kernel nodes keep the priority of the stream they were captured on).
-        import os
-        cap_stream = torch.cuda.Stream(device=dev, priority=-1) if os.environ.get("GEOSSL_GRAPH_PRIORITY", "1") != "0" else None
         try:
-            with torch.cuda.graph(self.graph, stream=cap_stream):
+            with torch.cuda.graph(self.graph):
                 self.loss = run()
         finally:
             if kernel_timers:
