@@ -695,6 +695,10 @@ def run_finetune(args):
             step = eager
     for i in range(2):
         step(dev_pool[i % args.pool])
+    if getattr(step, "capture_error", None) is not None:      # GraphedMD17Step keeps running eagerly after a refused capture: say so
+        launch = f"eager launches (graph capture refused: {type(step.capture_error).__name__}: {str(step.capture_error)[:160]})"
+    elif kind == "md17" and not args.no_graph and hasattr(step, "graphs"):
+        launch += f" ({len(step.graphs)} graph(s) captured)"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -84,7 +84,7 @@ class CFConv(torch.nn.Module):
         """``pairs``: ``edge_weight`` / ``edge_attr`` hold one row per undirected atom pair (ops.pair_endpoints)."""
         C = 0.5 * (torch.cos(edge_weight * PI / self.cutoff) + 1.0)
         if ops.filter_mlp_applies(self.nn[0], self.nn[2], edge_attr):
-            W = ops.filter_mlp(edge_attr, self.nn[0], self.nn[2]) * C.view(-1, 1)      # tensor-core products, any order
+            W = ops.row_scale(ops.filter_mlp(edge_attr, self.nn[0], self.nn[2]), C)    # tensor-core products, any order
         else:
             W = self.nn(edge_attr) * C.view(-1, 1)
         x = ops.linear_any_order(x, self.lin1)
@@ -136,7 +136,8 @@ class InteractionBlock(torch.nn.Module):
                           images=images)
 
     def forward_composed(self, x, graph, edge_weight, edge_attr, pairs=False):
-        return ops.linear_any_order(self.act(self.conv.forward_composed(x, graph, edge_weight, edge_attr, pairs)), self.lin)
+        return ops.linear_any_order(ops.ssp_any_order(self.conv.forward_composed(x, graph, edge_weight, edge_attr, pairs),
+                                                      self.act.shift), self.lin)
 
     def forward(self, x, edge_index, edge_weight, edge_attr, batch=None):
         return self.lin(self.act(self.conv(x, edge_index, edge_weight, edge_attr, batch)))

@@ -58,6 +58,9 @@ _SIGNATURES = {
     "geossl_tc_selftest": (c_int, [c_int, c_int, c_p, c_p, c_int, c_int, c_p, c_p]),
     "geossl_cfconv_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
     "geossl_cfconv_bwd_x": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
+    "geossl_ssp_family": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p]),
+    "geossl_row_scale": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p]),
+    "geossl_row_dot": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p]),
     "geossl_cfconv_pair_product": (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_p]),
     "geossl_cfconv_pairs_max_atoms": (c_int, [c_int]),
     "geossl_cfconv_pairs": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_int, c_int, c_p, c_p]),

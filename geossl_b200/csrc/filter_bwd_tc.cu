@@ -254,6 +254,9 @@ filter_bwd_tc_kernel(const float* __restrict__ edge_dist, const int32_t* __restr
         }
         // db2[o] = sum over the 16 row groups; scratch = dU buffer 0 once every MMA has retired
         mbar_wait(bar(DONE_), 0);
+        // (every producer's tile stores are ordered before this point through DU_FULL -> MMA -> DONE; the named barrier makes
+        // that ordering explicit among the eight producer warps, which is also what compute-sanitizer's racecheck can see)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         float* red = reinterpret_cast<float*>(smem + L::DU);
 #pragma unroll
         for (int k = 0; k < 8; ++k) red[ro * 128 + cg * 8 + k] = acc[k];

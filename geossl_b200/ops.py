@@ -1157,6 +1157,88 @@ class MatTX(torch.autograd.Function):
         return ga, gb, None
 
 
+class SspFamily(torch.autograd.Function):
+    """E_k(a, g) = g * ssp^(k)(a) (geossl_ssp_family), k = 0 the activation itself: each member's derivatives are members,
+    so the activation of the double-backward path costs one launch per use instead of torch's expanded formulas."""
+
+    @staticmethod
+    def forward(ctx, a, g, k):
+        a = _req(a, torch.float32, "a")
+        g = None if g is None else _req(g, torch.float32, "g")
+        ctx.k = int(k)
+        ctx.save_for_backward(a, g)
+        out = torch.empty_like(a)
+        check(_lib.load().geossl_ssp_family(_p(a), _p(g), a.numel(), ctx.k, _p(out), _stream()), "ssp_family")
+        return out
+
+    @staticmethod
+    def backward(ctx, v):
+        a, g = ctx.saved_tensors
+        if ctx.k >= 3 and ctx.needs_input_grad[0]:
+            raise RuntimeError("geossl_b200: SspFamily is built up to the third derivative of the activation")
+        ga = SspFamily.apply(a, v if g is None else v * g, ctx.k + 1) if ctx.needs_input_grad[0] else None
+        gg = SspFamily.apply(a, v.contiguous(), ctx.k) if (g is not None and ctx.needs_input_grad[1]) else None
+        return ga, gg, None
+
+
+def _closed_elementwise_applies(x):
+    return FILTER_MODE != "simt" and x.is_cuda and x.dtype == torch.float32 and x.numel() > 0
+
+
+def ssp_any_order(x, shift=0.6931471824645996):
+    """Shifted softplus (schnet.py:215-216), differentiable to any order the force training needs, one launch per use."""
+    if _closed_elementwise_applies(x):
+        return SspFamily.apply(x.contiguous(), None, 0)
+    return torch.nn.functional.softplus(x) - shift
+
+
+class RowScale(torch.autograd.Function):
+    """out[r][f] = x[r][f] * c[r]."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        x, c = _req(x, torch.float32, "x", 2), _req(c, torch.float32, "c", 1)
+        ctx.save_for_backward(x, c)
+        out = torch.empty_like(x)
+        check(_lib.load().geossl_row_scale(_p(x), _p(c), x.size(0), x.size(1), _p(out), _stream()), "row_scale")
+        return out
+
+    @staticmethod
+    def backward(ctx, v):
+        x, c = ctx.saved_tensors
+        v = v.contiguous()
+        gx = RowScale.apply(v, c) if ctx.needs_input_grad[0] else None
+        gc = RowDot.apply(v, x) if ctx.needs_input_grad[1] else None
+        return gx, gc
+
+
+class RowDot(torch.autograd.Function):
+    """out[r] = sum_f a[r][f] * b[r][f]."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _req(a, torch.float32, "a", 2), _req(b, torch.float32, "b", 2)
+        ctx.save_for_backward(a, b)
+        out = torch.empty(a.size(0), dtype=torch.float32, device=a.device)
+        check(_lib.load().geossl_row_dot(_p(a), _p(b), a.size(0), a.size(1), _p(out), _stream()), "row_dot")
+        return out
+
+    @staticmethod
+    def backward(ctx, v):
+        a, b = ctx.saved_tensors
+        v = v.contiguous()
+        ga = RowScale.apply(b, v) if ctx.needs_input_grad[0] else None
+        gb = RowScale.apply(a, v) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+def row_scale(x, c):
+    """``x * c.view(-1, 1)`` (the cutoff product of schnet.py:187) with derivatives that stay single launches."""
+    if _closed_elementwise_applies(x) and x.dim() == 2 and x.size(1) in (32, 64, 128):
+        return RowScale.apply(x.contiguous(), c.contiguous())
+    return x * c.view(-1, 1)
+
+
 def linear_any_order(x, layer):
     """``layer(x)`` for a 128 -> 128 nn.Linear, differentiable to any order on the tensor cores (MatXWt); other shapes,
     CPU tensors and the exact ``simt`` mode take torch's linear."""
@@ -1181,8 +1263,7 @@ def filter_mlp(edge_attr, lin0, lin2):
     x = torch.nn.functional.pad(edge_attr, (0, k - G)) if k != G else edge_attr
     w1 = torch.nn.functional.pad(lin0.weight, (0, 128 - G)) if G != 128 else lin0.weight
     h = MatXWt.apply(x, w1, lin0.bias, True)
-    h = torch.nn.functional.softplus(h) - 0.6931471824645996
-    return MatXWt.apply(h, lin2.weight, lin2.bias, True)
+    return MatXWt.apply(ssp_any_order(h), lin2.weight, lin2.bias, True)
 
 
 # =====================================================================================================

@@ -177,6 +177,14 @@ int geossl_cfconv_bwd_w(const float* x, const float* grad_out, const int32_t* ro
 int geossl_cfconv_pair_product(const float* x, const float* grad_out, const int32_t* pair_atoms, int64_t n_pairs, int F,
                                float* grad_filt, void* stream);
 
+/* Elementwise families closed under differentiation (composed double-backward path, finetune_md17.py:32-54):
+ *   geossl_ssp_family: out = g * s^(order)(a), s = shifted softplus (schnet.py:215-216), order 0..3 (order 0: the activation, g unused);
+ *   geossl_row_scale:  out[r][f] = x[r][f] * c[r]  (the cutoff product of schnet.py:187);  geossl_row_dot: out[r] = sum_f a[r][f] b[r][f].
+ * n = element count; operands 16-byte aligned, rows contiguous (F in {32, 64, 128}). */
+int geossl_ssp_family(const float* a, const float* g, int64_t n, int order, float* out, void* stream);
+int geossl_row_scale(const float* x, const float* c, int64_t n_rows, int F, float* out, void* stream);
+int geossl_row_dot(const float* a, const float* b, int64_t n_rows, int F, float* out, void* stream);
+
 /* Backward of the filter network fused with dW_e = x[src_e]*g[tgt_e] (never materialised):
  * recomputes rbf / Lin1 / ssp from d_e and accumulates gw1 (F,G), gb1 (F), gw2 (F,F), gb2 (F).
  * If grad_filt != NULL it is used as dW_e instead of x/g (then x, grad_out, src, edge_tgt may be NULL).

@@ -270,6 +270,30 @@ def test_pair_row_primitives_match_per_edge_primitives_to_second_order(density):
         assert rel_err(a, r) <= 1e-5, rel_err(a, r)
 
 
+def test_closed_elementwise_families_match_torch_to_third_order():
+    """ops.SspFamily (shifted softplus and its derivatives) and ops.RowScale / RowDot against torch's own formulas in float64:
+    value, gradient, gradient of a gradient norm, and one more order for the activation (incl. inputs above torch's
+    softplus threshold of 20, where the derivative is exactly 1)."""
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    a = 6 * torch.randn(777, 128, device=DEV, generator=gen)
+    a[0, :4] = torch.tensor([25.0, 20.5, -30.0, 0.0], device=DEV)
+    c = torch.randn(777, device=DEV, generator=gen)
+    w = torch.randn(777, 128, device=DEV, generator=gen)
+
+    def chain(av, cv, act, scale):
+        y = scale(act(av), cv)
+        g1a, g1c = torch.autograd.grad((y * w.to(y.dtype)).sum(), (av, cv), create_graph=True)
+        g2a, g2c = torch.autograd.grad(g1a.square().sum() + g1c.square().sum(), (av, cv), create_graph=True)
+        g3a, = torch.autograd.grad(g2a.square().sum(), av)
+        return y, g1a, g1c, g2a, g2c, g3a
+
+    got = chain(a.clone().requires_grad_(), c.clone().requires_grad_(), ops.ssp_any_order, ops.row_scale)
+    want = chain(a.double().requires_grad_(), c.double().requires_grad_(),
+                 lambda t: F.softplus(t) - 0.6931471805599453, lambda t, cv: t * cv.view(-1, 1))
+    for g, r in zip(got, want):
+        assert rel_err(g, r.float()) <= 2e-5, rel_err(g, r.float())
+
+
 def test_tensor_core_products_are_closed_under_differentiation():
     """ops.MatXWt / MatXW / MatTX against torch matmul in float64: values, first derivatives and a second derivative
     (gradient of a gradient norm), with a K-padded operand (64 live columns)."""
