@@ -64,7 +64,9 @@ def test_ddm_head_rng_contract():
 TC_TOL_ENCODER, TC_TOL_HEAD = 2e-4, 1e-3
 
 
-def _ddm_case(name, stack):
+def _ddm_case(name, stack, size_bound=False):
+    """``size_bound``: the batch carries the host-known largest molecule (``extras['max_graph_atoms']``, what the collate
+    helpers of data / datasets set and bench.py's batches have), which selects the pair-centric cfconv kernel."""
     g = Golden(name)
     c, i = g.cfg, g["in"]
     model = schnet_from(g, DEV) if c["model_3d"] == "schnet" else painn_from(g, DEV)
@@ -72,6 +74,8 @@ def _ddm_case(name, stack):
     batch = AtomTupleBatch(i["x"].to(DEV), i["pos"].to(DEV), i["batch"].to(DEV), i["super_edge_index"].to(DEV),
                            i["radius_edge_index"].to(DEV) if "radius_edge_index" in i else None,
                            n_graphs=int(i["batch"][-1]) + 1)
+    if size_bound:
+        batch.extras["max_graph_atoms"] = int(torch.bincount(i["batch"]).max())
     draws = ((i["noise_level_1"].to(DEV), i["distance_noise_1"].to(DEV)),
              (i["noise_level_2"].to(DEV), i["distance_noise_2"].to(DEV)))
     loss, acc = do_DDM(default_args(c["model_3d"]), batch, model, None, 0.0, c["sigma"], heads=heads, draws=draws,
@@ -100,13 +104,20 @@ def test_do_ddm_vs_golden(name, filter_mode, stack):
 
 @pytest.mark.parametrize("stack", [True, False])
 @pytest.mark.parametrize("name", ["ddm_schnet_cfg1", "ddm_schnet_cfg2"])
-def test_do_ddm_at_benchmarked_shapes(name, filter_mode, stack):
+@pytest.mark.parametrize("cfconv", ["pairs", "gather"])
+def test_do_ddm_at_benchmarked_shapes(name, filter_mode, stack, cfconv, monkeypatch):
     """Value-level parity at the shapes bench.py runs: BASELINE.json configs[0] (32 molecules x 30 atoms) and configs[1]
     (256 x 30 -- the headline workload: stacked views, tensor-core kernels, one filter row per atom pair, every
     persistent CTA walking many tiles).  The fixtures hold the loss and every parameter gradient computed by the
-    UNMODIFIED reference modules (tests/golden/make_golden.py)."""
+    UNMODIFIED reference modules (tests/golden/make_golden.py).  ``cfconv``: "pairs" = the batch carries its largest
+    molecule like bench.py's batches do, so the aggregate runs on the pair-centric kernel (geossl_cfconv_pairs, the bench
+    default); "gather" = a reference-style batch without it (row-gather kernels)."""
     assert filter_mode == "simt" or (ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE == "tc_fp16")
-    g, model, heads, loss, _ = _ddm_case(name, stack)
+    calls = []
+    orig = ops._cfconv_pairs
+    monkeypatch.setattr(ops, "_cfconv_pairs", lambda *a: calls.append(1) or orig(*a))
+    g, model, heads, loss, _ = _ddm_case(name, stack, size_bound=cfconv == "pairs")
+    assert bool(calls) == (cfconv == "pairs" and filter_mode != "simt")
     assert rel_err(loss, g["out"]["loss"]) <= TOL_OUT, rel_err(loss, g["out"]["loss"])
     for k in ("loss_01", "loss_02"):
         assert k in g["out"]
@@ -117,7 +128,7 @@ def test_do_ddm_at_benchmarked_shapes(name, filter_mode, stack):
 def test_cfg2_matches_cpu_oracle_in_test():
     """The same 256 x 30 step against the CPU restatement computed here (oracle/models.py, ~3 s): loss 1e-5, every
     gradient within the tensor-core bounds; guards the fixture and the in-test oracle against each other."""
-    g, model, heads, loss, _ = _ddm_case("ddm_schnet_cfg2", True)
+    g, model, heads, loss, _ = _ddm_case("ddm_schnet_cfg2", True, size_bound=True)     # as bench.py runs it: pair-centric cfconv
     loss.backward()
     c, i = g.cfg, g["in"]
     leaf = lambda sd: {k: v.clone().requires_grad_(v.is_floating_point() and v.dtype == torch.float32 and k != "sigmas")
