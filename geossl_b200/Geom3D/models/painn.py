@@ -56,9 +56,19 @@ class PaiNNMixing(nn.Module):
         n, _, Fd = mu.shape
         net = self.intraatomic_context_net
         if images and id(self.mu_channel_mix.weight) in images:
-            mu_mix = ops.dense(mu.reshape(3 * n, Fd), self.mu_channel_mix, images).view(n, 3, 2 * Fd)
+            mix, mu_rows = self.mu_channel_mix, mu.reshape(3 * n, Fd)
+            if ops.dense_chain2_applies(mu_rows, mix, None, images) and mix.bias is None:
+                # both 128-column blocks of mu_channel_mix in one launch (the row tile is staged once)
+                mu_mix = ops.DenseChain2.apply(mu_rows, mix.weight, None, None, None, images[id(mix.weight)], None).view(n, 3, 2 * Fd)
+            else:
+                mu_mix = ops.dense(mu_rows, mix, images).view(n, 3, 2 * Fd)
             ctx, dot = ops.PaiNNMixPre.apply(q, mu_mix, self.epsilon)
-            y = ops.dense(ops.dense(ctx, net[0], images), net[1], images, pre_act=ops.ACT_SILU)
+            if ops.dense_chain2_applies(ctx, net[0], net[1], images):
+                # 256 -> 128 (two K-blocks summed in the accumulator) -> SiLU -> 384 (three blocks) without leaving the SM
+                y = ops.DenseChain2.apply(ctx, net[0].weight, net[0].bias, net[1].weight, net[1].bias,
+                                          images[id(net[0].weight)], images[id(net[1].weight)])
+            else:
+                y = ops.dense(ops.dense(ctx, net[0], images), net[1], images, pre_act=ops.ACT_SILU)
         else:
             mu_mix = self.mu_channel_mix(mu)
             ctx, dot = ops.PaiNNMixPre.apply(q, mu_mix, self.epsilon)
@@ -140,7 +150,11 @@ class PaiNN(nn.Module):
             fo = 0 if self.share_filters else i * 3 * Fd
             if tc:
                 net = interaction.interatomic_context_net
-                ctx = ops.dense(ops.dense(q, net[0], images), net[1], images, pre_act=ops.ACT_SILU)          # (N,3F)
+                if ops.dense_chain2_applies(q, net[0], net[1], images):
+                    ctx = ops.DenseChain2.apply(q, net[0].weight, net[0].bias, net[1].weight, net[1].bias,
+                                                images[id(net[0].weight)], images[id(net[1].weight)])             # (N,3F), one launch
+                else:
+                    ctx = ops.dense(ops.dense(q, net[0], images), net[1], images, pre_act=ops.ACT_SILU)      # (N,3F)
                 wpre = ops.DenseTC.apply(edges.phi_pad(), wf_pad[fo:fo + 3 * Fd], None, ops.ACT_NONE,
                                          images[id(wf_pad)][3 * i:3 * i + 3])                                   # (E,3F)
                 q, mu = ops.PaiNNMessage.apply(q, mu, ctx, None, None, edges, wpre)

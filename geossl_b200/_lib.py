@@ -36,6 +36,13 @@ class ChainStage(ctypes.Structure):
     _fields_ = [("weight_image", c_p), ("bias", c_p), ("act_grad_input", c_p), ("residual", c_p), ("store", c_p), ("act_next", c_int)]
 
 
+class ChainStageEx(ctypes.Structure):
+    """geossl_chain_stage_ex (include/geossl_b200.h)."""
+    _fields_ = [("weight_image", c_p), ("bias", c_p), ("act_grad_input", c_p), ("ldz", c_i64), ("residual", c_p), ("ldr", c_i64),
+                ("store", c_p), ("ld_store", c_i64), ("x", c_p), ("ldx", c_i64), ("act_next", c_int), ("x_act", c_int),
+                ("keep", c_int), ("accumulate", c_int), ("partial", c_int)]
+
+
 ABI_VERSION = 3          # must equal GEOSSL_ABI_VERSION in include/geossl_b200.h
 
 _SIGNATURES = {
@@ -82,6 +89,7 @@ _SIGNATURES = {
     "geossl_linear_wgrad_tc_block": (c_int, [c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_int, c_p, c_int, c_p]),
     "geossl_linear_tc": (c_int, [c_p, c_i64, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p]),
     "geossl_linear_chain_tc": (c_int, [c_p, c_i64, ctypes.POINTER(ChainStage), c_int, c_int, c_int, c_p]),
+    "geossl_linear_chain_ex": (c_int, [c_i64, ctypes.POINTER(ChainStageEx), c_int, c_int, c_int, c_p]),
     "geossl_linear_wgrad_tc_workspace": (c_i64, [c_i64]),
     "geossl_linear_wgrad_tc": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
     "geossl_pair_distance": (c_int, [c_p, c_p, c_i64, c_p, c_p]),

@@ -265,12 +265,19 @@ linear_tc_kernel(const float* __restrict__ X, int64_t n_rows, const uint8_t* __r
 struct ChainStage {
     const uint8_t* w_image;   // packed weight image (orientation / parts chosen when it was packed)
     const float* bias;        // NULL or (128)
-    const float* z;           // NULL or (n_rows,128): v *= act'(z)
-    const float* residual;    // NULL or (n_rows,128): v += residual
-    float* store;             // NULL or (n_rows,128): store = v
+    const float* z;           // NULL or rows of 128 (stride ldz): v *= act'(z)
+    const float* residual;    // NULL or rows of 128 (stride ldr): v += residual
+    float* store;             // NULL or rows of 128 (stride lds): store = v
+    const float* x;           // NULL: the operand is the previous stage's result (or, with `keep`, the previous stage's operand);
+                              // else this stage's operand tile is loaded from here (stride ldx, pre-activation x_act)
+    int64_t ldz, ldr, lds, ldx;
     int act_next;             // 0 | kActSsp | kActSilu: activation applied to v before it becomes the next stage's operand
+    int x_act;                // pre-activation applied to a loaded operand (0 | kActSsp | kActSilu)
+    int keep;                 // the operand tile of the previous stage is used again (fan-out: one input, several weight blocks)
+    int accumulate;           // the MMAs add to the previous (partial) stage's accumulator (fan-in: K > 128)
+    int partial;              // no epilogue: the next stage accumulates onto this one
 };
-constexpr int kMaxChain = 4;
+constexpr int kMaxChain = 6;
 struct ChainArgs { ChainStage st[kMaxChain]; int n; };
 
 struct ChainLayout {
@@ -326,21 +333,25 @@ linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs ar
             fetch_weights(0, 0);
             if (n_st > 1) fetch_weights(1, 1);
         }
-        stage_rows_kmajor<FP16, NR>(X, 128, row0, n_rows, 0, smem + L::X, smem + L::X + 2 * kBlkT);
+        stage_rows_kmajor<FP16, NR>(X, args.st[0].x ? args.st[0].ldx : 128, row0, n_rows, args.st[0].x_act, smem + L::X,
+                                    smem + L::X + 2 * kBlkT);
         const int64_t erow = row0 + eh * 32;
         for (int s = 0; s < n_st; ++s) {
             const ChainStage& S = args.st[s];
             const int slot = s & 1;
+            // a stage that brings its own operand: every thread has passed the previous stage's MMA wait, the tile is free
+            if (s > 0 && S.x != nullptr)
+                stage_rows_kmajor<FP16, NR>(S.x, S.ldx, row0, n_rows, S.x_act, smem + L::X, smem + L::X + 2 * kBlkT);
             // epilogue operands that do not depend on the MMA: fetched now, their latency hides behind it
             float zr[32], rr[32];
-            const bool has_z = S.z != nullptr, has_r = S.residual != nullptr;
+            const bool has_z = S.z != nullptr && !S.partial, has_r = S.residual != nullptr && !S.partial;
             if (has_z) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) zr[j] = (full || erow + j < n_rows) ? __ldg(S.z + (erow + j) * 128 + f) : 0.f;
+                for (int j = 0; j < 32; ++j) zr[j] = (full || erow + j < n_rows) ? __ldg(S.z + (erow + j) * S.ldz + f) : 0.f;
             }
             if (has_r) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) rr[j] = (full || erow + j < n_rows) ? __ldg(S.residual + (erow + j) * 128 + f) : 0.f;
+                for (int j = 0; j < 32; ++j) rr[j] = (full || erow + j < n_rows) ? __ldg(S.residual + (erow + j) * S.ldr + f) : 0.f;
             }
             const float bf = S.bias ? __ldg(S.bias + f) : 0.f;
             fence_proxy_async();
@@ -355,7 +366,7 @@ linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs ar
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kBlkT >> 4) + 2 * (ks & 3);
-                        mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, ks > 0);
+                        mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, (ks > 0) || S.accumulate);
                     }
                     tc_commit(bar);
                 }
@@ -367,6 +378,7 @@ linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs ar
             tc_fence_after();
             // the MMAs have consumed this slot's image and the operand tile: refill the slot two stages ahead
             if (tid == 0 && s + 2 < n_st) fetch_weights(s + 2, slot);
+            if (S.partial) continue;                               // the next stage accumulates onto this result
             float v[32];
             tmem_ld32(tmem + lane_base + eh * 32, v);              // lane = output feature f, columns = rows eh*32..+31
             tc_fence_before();
@@ -378,17 +390,17 @@ linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs ar
                 v[j] = y;
             }
             if (S.store != nullptr) {
-                float* out = S.store + erow * 128 + f;
+                float* out = S.store + erow * S.lds + f;
                 if (full) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) out[j * 128] = v[j];  // 128 contiguous bytes per warp store
+                    for (int j = 0; j < 32; ++j) out[j * S.lds] = v[j];  // 128 contiguous bytes per warp store
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (erow + j < n_rows) out[j * 128] = v[j];
+                        if (erow + j < n_rows) out[j * S.lds] = v[j];
                 }
             }
-            if (s + 1 < n_st) {
+            if (s + 1 < n_st && args.st[s + 1].x == nullptr && !args.st[s + 1].keep) {
                 // next stage's operand: element (row = eh*32 + j, k = f) of the K-major tile
                 if (S.act_next) {
 #pragma unroll
@@ -711,25 +723,7 @@ int geossl_linear_tc_block(const float* x, int64_t ldx, int64_t n_rows, const vo
                               ldx, ldz, ldr, ldy, act, k_cols, as_stream(stream));
 }
 
-int geossl_linear_chain_tc(const float* x, int64_t n_rows, const geossl_chain_stage* stages, int n_stages, int bf16_parts, int act,
-                           void* stream) {
-    if (n_rows == 0) return 0;
-    GEOSSL_REQUIRE(x && stages && n_rows > 0, "null pointer");
-    GEOSSL_REQUIRE(n_stages >= 1 && n_stages <= tc::kMaxChain, "1..4 stages");
-    GEOSSL_REQUIRE(act == tc::kActSsp || act == tc::kActSilu, "act must be 1 (ssp) or 2 (silu)");
-    tc::ChainArgs a;
-    a.n = n_stages;
-    for (int i = 0; i < n_stages; ++i) {
-        GEOSSL_REQUIRE(stages[i].weight_image != nullptr, "stage without a weight image");
-        GEOSSL_REQUIRE(stages[i].act_next >= 0 && stages[i].act_next <= 2, "act_next must be 0, 1 or 2");
-        a.st[i].w_image = (const uint8_t*)stages[i].weight_image;
-        a.st[i].bias = stages[i].bias;
-        a.st[i].z = stages[i].act_grad_input;
-        a.st[i].residual = stages[i].residual;
-        a.st[i].store = stages[i].store;
-        a.st[i].act_next = stages[i].act_next;
-    }
-    GEOSSL_REQUIRE(stages[n_stages - 1].store != nullptr, "the last stage must store its result");
+static int launch_chain(const float* x, int64_t n_rows, const tc::ChainArgs& a, int bf16_parts, int act, void* stream) {
     const size_t smem = tc::ChainLayout::kBytes + 1024;
     const int64_t tiles = (n_rows + 127) / 128;
     const dim3 grid((unsigned)(tiles < kNumSM ? tiles : kNumSM));
@@ -750,6 +744,61 @@ int geossl_linear_chain_tc(const float* x, int64_t n_rows, const geossl_chain_st
     }
     GEOSSL_LAUNCH_CHECK();
     return 0;
+}
+
+int geossl_linear_chain_tc(const float* x, int64_t n_rows, const geossl_chain_stage* stages, int n_stages, int bf16_parts, int act,
+                           void* stream) {
+    if (n_rows == 0) return 0;
+    GEOSSL_REQUIRE(x && stages && n_rows > 0, "null pointer");
+    GEOSSL_REQUIRE(n_stages >= 1 && n_stages <= 4, "1..4 stages");
+    GEOSSL_REQUIRE(act == tc::kActSsp || act == tc::kActSilu, "act must be 1 (ssp) or 2 (silu)");
+    tc::ChainArgs a = {};
+    a.n = n_stages;
+    for (int i = 0; i < n_stages; ++i) {
+        GEOSSL_REQUIRE(stages[i].weight_image != nullptr, "stage without a weight image");
+        GEOSSL_REQUIRE(stages[i].act_next >= 0 && stages[i].act_next <= 2, "act_next must be 0, 1 or 2");
+        a.st[i].w_image = (const uint8_t*)stages[i].weight_image;
+        a.st[i].bias = stages[i].bias;
+        a.st[i].z = stages[i].act_grad_input;
+        a.st[i].residual = stages[i].residual;
+        a.st[i].store = stages[i].store;
+        a.st[i].act_next = stages[i].act_next;
+        a.st[i].ldz = a.st[i].ldr = a.st[i].lds = 128;
+    }
+    GEOSSL_REQUIRE(stages[n_stages - 1].store != nullptr, "the last stage must store its result");
+    return launch_chain(x, n_rows, a, bf16_parts, act, stream);
+}
+
+int geossl_linear_chain_ex(int64_t n_rows, const geossl_chain_stage_ex* stages, int n_stages, int bf16_parts, int act, void* stream) {
+    if (n_rows == 0) return 0;
+    GEOSSL_REQUIRE(stages && n_rows > 0, "null pointer");
+    GEOSSL_REQUIRE(n_stages >= 1 && n_stages <= tc::kMaxChain, "1..6 stages");
+    GEOSSL_REQUIRE(act == tc::kActSsp || act == tc::kActSilu, "act must be 1 (ssp) or 2 (silu)");
+    tc::ChainArgs a = {};
+    a.n = n_stages;
+    for (int i = 0; i < n_stages; ++i) {
+        const geossl_chain_stage_ex& S = stages[i];
+        GEOSSL_REQUIRE(S.weight_image != nullptr, "stage without a weight image");
+        GEOSSL_REQUIRE(S.act_next >= 0 && S.act_next <= 2 && S.x_act >= 0 && S.x_act <= 2, "activations must be 0, 1 or 2");
+        GEOSSL_REQUIRE(i > 0 || S.x != nullptr, "the first stage needs an operand");
+        GEOSSL_REQUIRE(!(S.x && S.keep), "a stage either loads its operand or keeps the previous one");
+        GEOSSL_REQUIRE(i > 0 || !(S.keep || S.accumulate), "the first stage cannot keep / accumulate");
+        GEOSSL_REQUIRE(!S.accumulate || stages[i - 1].partial, "an accumulating stage must follow a partial stage");
+        GEOSSL_REQUIRE(!S.partial || (i + 1 < n_stages && stages[i + 1].accumulate), "a partial stage must be followed by an accumulating one");
+        GEOSSL_REQUIRE((!S.x || (S.ldx >= 128 && S.ldx % 4 == 0)) && (!S.store || S.ld_store >= 128) && (!S.act_grad_input || S.ldz >= 128)
+                       && (!S.residual || S.ldr >= 128), "bad leading dimension");
+        a.st[i].w_image = (const uint8_t*)S.weight_image;
+        a.st[i].bias = S.bias;
+        a.st[i].z = S.act_grad_input;
+        a.st[i].residual = S.residual;
+        a.st[i].store = S.store;
+        a.st[i].x = S.x;
+        a.st[i].ldz = S.ldz; a.st[i].ldr = S.ldr; a.st[i].lds = S.ld_store; a.st[i].ldx = S.ldx;
+        a.st[i].act_next = S.act_next; a.st[i].x_act = S.x_act;
+        a.st[i].keep = S.keep; a.st[i].accumulate = S.accumulate; a.st[i].partial = S.partial;
+    }
+    GEOSSL_REQUIRE(stages[n_stages - 1].store != nullptr, "the last stage must store its result");
+    return launch_chain(stages[0].x, n_rows, a, bf16_parts, act, stream);
 }
 
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::wgrad_grid(n_rows) * tc::kWgPart; }

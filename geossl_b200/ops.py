@@ -1016,6 +1016,174 @@ class DenseTC(torch.autograd.Function):
         return gx, gw, gb, None, None
 
 
+def _chain_ex(n_rows, stages, bf16_parts, act, name):
+    """stages: list of dicts with the fields of geossl_chain_stage_ex (tensors or None; missing = 0 / None); every tensor
+    argument is (pointer to its first used element, row stride) given as ``(tensor, column_offset)``."""
+    arr = (_lib.ChainStageEx * len(stages))()
+
+    def ptr(spec):
+        if spec is None:
+            return None, 0
+        t, col = spec
+        return t.data_ptr() + 4 * col, t.stride(0) if t.dim() == 2 else 0
+
+    for a, st in zip(arr, stages):
+        a.weight_image = st["image"].data_ptr()
+        b = st.get("bias")
+        a.bias = None if b is None else b[0].data_ptr() + 4 * b[1]
+        a.act_grad_input, a.ldz = ptr(st.get("z"))
+        a.residual, a.ldr = ptr(st.get("residual"))
+        a.store, a.ld_store = ptr(st.get("store"))
+        a.x, a.ldx = ptr(st.get("x"))
+        a.act_next, a.x_act = int(st.get("act_next", 0)), int(st.get("x_act", 0))
+        a.keep, a.accumulate, a.partial = int(st.get("keep", 0)), int(st.get("accumulate", 0)), int(st.get("partial", 0))
+    _timed(name, lambda: _lib.load().geossl_linear_chain_ex(n_rows, arr, len(stages), 1 if bf16_parts else 0, act, _stream()))
+
+
+def _deferred_wgrads(compute, params, inputs):
+    """Run ``compute() -> [grad tensors]`` (weight-gradient launches) on the side stream inside ``side_stream_wgrads()`` when every
+    parameter is a leaf, handing the results to ``join_side_stream()``; otherwise run it in place.  Returns the list of
+    gradients for autograd (all None when deferred)."""
+    live = [p for p in params if p is not None]
+    if _SIDE["on"] and all(p.is_leaf and p.requires_grad for p in live):
+        dev = live[0].device
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            grads = compute()
+        for t in inputs:
+            t.record_stream(side)
+        for p, g in zip(params, grads):
+            if p is not None and g is not None:
+                g.record_stream(main)
+                _SIDE["pending"].append((p, g))
+        _SIDE["dirty"] = True
+        return [None] * len(params)
+    return compute()
+
+
+class DenseChain2(torch.autograd.Function):
+    """y (n,N2) = silu(x (n,K) @ Wa (128,K)^T + ba) @ Wb (N2,128)^T + bb -- PaiNN's two-layer context nets (painn.py:21-24: K = 128,
+    N2 = 384; :76-79: K = 256, N2 = 384) as ONE launch forward (K-blocks summed in the accumulator, the hidden tile handed to
+    the three output blocks through shared memory) and ONE launch for the data gradient (geossl_linear_chain_ex); the hidden
+    pre-activation z (n,128) is the only tensor kept besides x.  ``Wb = None``: a single bias-free Dense with N = Wa rows wider
+    than 128 (mu_channel_mix, painn.py:83) -- fan-out only."""
+
+    @staticmethod
+    def forward(ctx, x, wa, ba, wb, bb, img_a, img_b):
+        x = _req(x, torch.float32, "x", 2)
+        n, K = x.shape
+        ctx.two = wb is not None
+        ctx.params = (wa, ba, wb, bb)
+        ctx.images = (img_a, img_b)
+        stages = []
+        if ctx.two:
+            nk, no = K // 128, wb.size(0) // 128
+            z = torch.empty((n, 128), dtype=torch.float32, device=x.device)
+            y = torch.empty((n, wb.size(0)), dtype=torch.float32, device=x.device)
+            for kb in range(nk):
+                st = {"image": img_a[0, kb, 0], "x": (x, kb * 128), "partial": kb < nk - 1, "accumulate": kb > 0}
+                if kb == nk - 1:
+                    st.update(bias=None if ba is None else (ba, 0), store=(z, 0), act_next=ACT_SILU)
+                stages.append(st)
+            for ob in range(no):
+                stages.append({"image": img_b[ob, 0, 0], "bias": None if bb is None else (bb, ob * 128), "store": (y, ob * 128),
+                               "keep": ob > 0})
+            ctx.save_for_backward(x, z)
+        else:
+            no = wa.size(0) // 128
+            y = torch.empty((n, wa.size(0)), dtype=torch.float32, device=x.device)
+            for ob in range(no):
+                st = {"image": img_a[ob, 0, 0], "bias": None if ba is None else (ba, ob * 128), "store": (y, ob * 128), "keep": ob > 0}
+                if ob == 0:
+                    st["x"] = (x, 0)
+                stages.append(st)
+            ctx.save_for_backward(x)
+        if n:
+            _chain_ex(n, stages, False, ACT_SILU, "dense_chain_fwd")
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        wa, ba, wb, bb = ctx.params
+        img_a, img_b = ctx.images
+        gy = gy.contiguous()
+        lib = _lib.load()
+        if ctx.two:
+            x, z = ctx.saved_tensors
+        else:
+            (x,) = ctx.saved_tensors
+        n, K = x.shape
+        if n == 0:
+            return (torch.zeros_like(x), torch.zeros_like(wa), None if ba is None else torch.zeros_like(ba),
+                    None if wb is None else torch.zeros_like(wb), None if bb is None else torch.zeros_like(bb), None, None)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        stages = []
+        if ctx.two:
+            nk, no = K // 128, wb.size(0) // 128
+            gz = torch.empty((n, 128), dtype=torch.float32, device=x.device)
+            for ob in range(no):
+                st = {"image": img_b[ob, 0, 1], "x": (gy, ob * 128), "partial": ob < no - 1, "accumulate": ob > 0}
+                if ob == no - 1:
+                    st.update(z=(z, 0), store=(gz, 0))
+                stages.append(st)
+            if gx is not None:
+                for kb in range(nk):
+                    stages.append({"image": img_a[0, kb, 1], "store": (gx, kb * 128), "keep": kb > 0})
+            _chain_ex(n, stages, True, ACT_SILU, "dense_chain_bwd")
+
+            def wgrads():
+                gwa, gwb = torch.empty_like(wa), torch.empty_like(wb)
+                gba = torch.empty_like(ba) if ba is not None else None
+                gbb = torch.empty_like(bb) if bb is not None else None
+                ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
+                for ob in range(no):
+                    _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
+                        _off(gy, ob * 128), gy.size(1), _p(z), 128, n, ACT_SILU, _p(ws), _off(gwb, ob * 128 * 128), 128,
+                        None if gbb is None else _off(gbb, ob * 128), 128, _stream()))
+                for kb in range(nk):
+                    _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
+                        _p(gz), 128, _off(x, kb * 128), K, n, ACT_NONE, _p(ws), _off(gwa, kb * 128), K,
+                        None if (gba is None or kb) else _p(gba), 128, _stream()))
+                return [gwa, gba, gwb, gbb]
+
+            gwa, gba, gwb, gbb = _deferred_wgrads(wgrads, [wa, ba, wb, bb], [gy, z, gz, x])
+            return gx, gwa, gba, gwb, gbb, None, None
+        no = wa.size(0) // 128
+        if gx is not None:
+            for ob in range(no):
+                st = {"image": img_a[ob, 0, 1], "x": (gy, ob * 128), "partial": ob < no - 1, "accumulate": ob > 0}
+                if ob == no - 1:
+                    st["store"] = (gx, 0)
+                stages.append(st)
+            _chain_ex(n, stages, True, ACT_SILU, "dense_chain_bwd")
+
+        def wgrads1():
+            gwa = torch.empty_like(wa)
+            gba = torch.empty_like(ba) if ba is not None else None
+            ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
+            for ob in range(no):
+                _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
+                    _off(gy, ob * 128), gy.size(1), _p(x), 128, n, ACT_NONE, _p(ws), _off(gwa, ob * 128 * 128), 128,
+                    None if gba is None else _off(gba, ob * 128), 128, _stream()))
+            return [gwa, gba, None, None]
+
+        gwa, gba, _, _ = _deferred_wgrads(wgrads1, [wa, ba, None, None], [gy, x])
+        return gx, gwa, gba, None, None, None, None
+
+
+def dense_chain2_applies(x, la, lb, images):
+    """Two Dense layers (la with SiLU, then lb) as one chain launch: 128-wide hidden layer, K and N2 multiples of 128, at most
+    six 128 x 128 blocks in all; ``lb = None``: one bias-free fan-out layer with 128 inputs."""
+    if not images or id(la.weight) not in images or not x.is_cuda or x.dim() != 2:
+        return False
+    if lb is None:
+        return la.weight.size(1) == 128 and 2 <= la.weight.size(0) // 128 <= 6
+    return (id(lb.weight) in images and la.weight.size(0) == 128 and lb.weight.size(1) == 128
+            and la.weight.size(1) // 128 + lb.weight.size(0) // 128 <= 6)
+
+
 class FilterPad(torch.autograd.Function):
     """[W_f | b_f | 0] (C,128) written into a PERSISTENT buffer (its address must not change between forwards: the packed
     block pointer table is cached, and a captured CUDA graph replays fixed addresses).  Backward slices the gradient."""

@@ -271,6 +271,25 @@ typedef struct {
 int geossl_linear_chain_tc(const float* x, int64_t n_rows, const geossl_chain_stage* stages /*host*/, int n_stages, int bf16_parts,
                            int act, void* stream);
 
+/* The same kernel with fan-out, fan-in and strided tensors, for the wider Dense layers of PaiNN (painn.py:21-24,76-83:
+ * 128 -> 128 SiLU -> 384, 256 -> 128 SiLU -> 384, 128 -> 256 on the 3N vector rows) and their data gradients in ONE launch each:
+ *   x != NULL : this stage loads its own operand tile (128 columns starting at x, row stride ldx, pre-activation x_act);
+ *               required for the first stage.  keep = 1 : the previous stage's operand tile is used again (fan-out over
+ *               several 128-column weight blocks).  partial = 1 / accumulate = 1 : consecutive stages sum into one
+ *               accumulator (fan-in over the K-blocks of a K > 128 layer); only the last of them has an epilogue.
+ *   z, residual, store: windows of wider tensors (row strides ldz, ldr, ld_store).  Up to 6 stages. */
+typedef struct {
+    const void* weight_image;
+    const float* bias;
+    const float* act_grad_input; int64_t ldz;
+    const float* residual;       int64_t ldr;
+    float* store;                int64_t ld_store;
+    const float* x;              int64_t ldx;
+    int act_next, x_act, keep, accumulate, partial;
+} geossl_chain_stage_ex;
+int geossl_linear_chain_ex(int64_t n_rows, const geossl_chain_stage_ex* stages /*host*/, int n_stages, int bf16_parts, int act,
+                           void* stream);
+
 /* grad_weight[o][i] = sum_r grad_y[r][o] * pre(x[r][i]);  grad_bias[o] = sum_r grad_y[r][o] (may be NULL). */
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows);
 int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, int pre_ssp, float* workspace,
