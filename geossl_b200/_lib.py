@@ -43,6 +43,12 @@ class ChainStageEx(ctypes.Structure):
                 ("keep", c_int), ("accumulate", c_int), ("partial", c_int)]
 
 
+class WgradProblem(ctypes.Structure):
+    """geossl_wgrad_problem (include/geossl_b200.h)."""
+    _fields_ = [("grad_y", c_p), ("ld_dy", c_i64), ("x", c_p), ("ld_x", c_i64), ("workspace", c_p), ("grad_weight", c_p),
+                ("ld_gw", c_int), ("grad_bias", c_p), ("pre_act", c_int), ("x_cols", c_int)]
+
+
 ABI_VERSION = 3          # must equal GEOSSL_ABI_VERSION in include/geossl_b200.h
 
 _SIGNATURES = {
@@ -90,6 +96,7 @@ _SIGNATURES = {
     "geossl_linear_tc": (c_int, [c_p, c_i64, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p]),
     "geossl_linear_chain_tc": (c_int, [c_p, c_i64, ctypes.POINTER(ChainStage), c_int, c_int, c_int, c_p]),
     "geossl_linear_chain_ex": (c_int, [c_i64, ctypes.POINTER(ChainStageEx), c_int, c_int, c_int, c_p]),
+    "geossl_linear_wgrad_tc_batch": (c_int, [ctypes.POINTER(WgradProblem), c_int, c_i64, c_p]),
     "geossl_linear_wgrad_tc_workspace": (c_i64, [c_i64]),
     "geossl_linear_wgrad_tc": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
     "geossl_pair_distance": (c_int, [c_p, c_p, c_i64, c_p, c_p]),

@@ -290,9 +290,11 @@ struct ChainLayout {
 };
 static_assert(ChainLayout::kBytes + 1024 <= 227 * 1024, "shared memory budget");
 
-template <bool FP16>
+// EX = false: the plain chain (every tensor (n_rows,128) contiguous, operands handed on from stage to stage) compiles without
+// the stride / fan-out / fan-in machinery -- it is the kernel of SchNet's step and runs 14 times in it.
+template <bool FP16, bool EX>
 __global__ void __launch_bounds__(512, 1)
-linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs args, int act) {
+linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, const __grid_constant__ ChainArgs args, int act) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     using L = ChainLayout;
@@ -333,25 +335,27 @@ linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs ar
             fetch_weights(0, 0);
             if (n_st > 1) fetch_weights(1, 1);
         }
-        stage_rows_kmajor<FP16, NR>(X, args.st[0].x ? args.st[0].ldx : 128, row0, n_rows, args.st[0].x_act, smem + L::X,
+        stage_rows_kmajor<FP16, NR>(X, EX ? args.st[0].ldx : 128, row0, n_rows, EX ? args.st[0].x_act : 0, smem + L::X,
                                     smem + L::X + 2 * kBlkT);
         const int64_t erow = row0 + eh * 32;
         for (int s = 0; s < n_st; ++s) {
             const ChainStage& S = args.st[s];
             const int slot = s & 1;
             // a stage that brings its own operand: every thread has passed the previous stage's MMA wait, the tile is free
-            if (s > 0 && S.x != nullptr)
+            if (EX && s > 0 && S.x != nullptr)
                 stage_rows_kmajor<FP16, NR>(S.x, S.ldx, row0, n_rows, S.x_act, smem + L::X, smem + L::X + 2 * kBlkT);
+            const bool partial = EX && S.partial;
+            const int64_t ldz = EX ? S.ldz : 128, ldr = EX ? S.ldr : 128, lds = EX ? S.lds : 128;
             // epilogue operands that do not depend on the MMA: fetched now, their latency hides behind it
             float zr[32], rr[32];
-            const bool has_z = S.z != nullptr && !S.partial, has_r = S.residual != nullptr && !S.partial;
+            const bool has_z = S.z != nullptr && !partial, has_r = S.residual != nullptr && !partial;
             if (has_z) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) zr[j] = (full || erow + j < n_rows) ? __ldg(S.z + (erow + j) * S.ldz + f) : 0.f;
+                for (int j = 0; j < 32; ++j) zr[j] = (full || erow + j < n_rows) ? __ldg(S.z + (erow + j) * ldz + f) : 0.f;
             }
             if (has_r) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) rr[j] = (full || erow + j < n_rows) ? __ldg(S.residual + (erow + j) * S.ldr + f) : 0.f;
+                for (int j = 0; j < 32; ++j) rr[j] = (full || erow + j < n_rows) ? __ldg(S.residual + (erow + j) * ldr + f) : 0.f;
             }
             const float bf = S.bias ? __ldg(S.bias + f) : 0.f;
             fence_proxy_async();
@@ -366,7 +370,7 @@ linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs ar
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t ow = (ks >> 2) * (kNBlkW >> 4) + 2 * (ks & 3), ox = (ks >> 2) * (kBlkT >> 4) + 2 * (ks & 3);
-                        mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, (ks > 0) || S.accumulate);
+                        mma3(tmem, wh + ow, wl + ow, xh + ox, xl + ox, idesc, (ks > 0) || (EX && S.accumulate));
                     }
                     tc_commit(bar);
                 }
@@ -378,7 +382,7 @@ linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs ar
             tc_fence_after();
             // the MMAs have consumed this slot's image and the operand tile: refill the slot two stages ahead
             if (tid == 0 && s + 2 < n_st) fetch_weights(s + 2, slot);
-            if (S.partial) continue;                               // the next stage accumulates onto this result
+            if (partial) continue;                                 // the next stage accumulates onto this result
             float v[32];
             tmem_ld32(tmem + lane_base + eh * 32, v);              // lane = output feature f, columns = rows eh*32..+31
             tc_fence_before();
@@ -390,17 +394,17 @@ linear_chain_tc_kernel(const float* __restrict__ X, int64_t n_rows, ChainArgs ar
                 v[j] = y;
             }
             if (S.store != nullptr) {
-                float* out = S.store + erow * S.lds + f;
+                float* out = S.store + erow * lds + f;
                 if (full) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) out[j * S.lds] = v[j];  // 128 contiguous bytes per warp store
+                    for (int j = 0; j < 32; ++j) out[j * lds] = v[j];  // 128 contiguous bytes per warp store
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (erow + j < n_rows) out[j * S.lds] = v[j];
+                        if (erow + j < n_rows) out[j * lds] = v[j];
                 }
             }
-            if (s + 1 < n_st && args.st[s + 1].x == nullptr && !args.st[s + 1].keep) {
+            if (s + 1 < n_st && (!EX || (args.st[s + 1].x == nullptr && !args.st[s + 1].keep))) {
                 // next stage's operand: element (row = eh*32 + j, k = f) of the K-major tile
                 if (S.act_next) {
 #pragma unroll
@@ -474,10 +478,27 @@ __device__ __forceinline__ void stage_rows_mn(const float* __restrict__ X, int64
     }
 }
 
+// Up to kMaxWgBatch independent weight-gradient products over the SAME rows in one launch (blockIdx.y = problem): the three
+// layers of an interaction tail, the blocks of PaiNN's wider Dense layers, ... -- each of them is a ~10 us latency-bound
+// launch on its own, and they come in groups that are ready at the same time.
+constexpr int kMaxWgBatch = 6;
+struct WgProblem {
+    const float* dY; const float* X;
+    float* workspace; float* gw; float* gb;
+    int64_t ld_dy, ld_x;
+    int pre_act, x_cols, ld_gw;
+};
+struct WgBatch { WgProblem p[kMaxWgBatch]; };
+
 template <bool FP16>
 __global__ void __launch_bounds__(256, 2)
-linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X, int64_t n_rows, int pre_act,
-                       float* __restrict__ workspace, int64_t ld_dy, int64_t ld_x, int x_cols) {
+linear_wgrad_tc_kernel(const __grid_constant__ WgBatch batch, int64_t n_rows) {
+    const WgProblem& P = batch.p[blockIdx.y];
+    const float* __restrict__ dY = P.dY;
+    const float* __restrict__ X = P.X;
+    float* __restrict__ workspace = P.workspace;
+    const int64_t ld_dy = P.ld_dy, ld_x = P.ld_x;
+    const int pre_act = P.pre_act, x_cols = P.x_cols;
     extern __shared__ uint8_t smem_raw[];
     pdl_launch_dependents();
     pdl_wait();
@@ -563,7 +584,12 @@ linear_wgrad_tc_kernel(const float* __restrict__ dY, const float* __restrict__ X
 
 // 256 threads = 32 outputs x 8 slices of the partial list; slices are combined in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
-linear_wgrad_reduce_kernel(const float* __restrict__ workspace, int n_parts, float* __restrict__ gw, float* __restrict__ gb, int ld_gw) {
+linear_wgrad_reduce_kernel(const __grid_constant__ WgBatch batch, int n_parts) {
+    const WgProblem& P = batch.p[blockIdx.y];
+    const float* __restrict__ workspace = P.workspace;
+    float* __restrict__ gw = P.gw;
+    float* __restrict__ gb = P.gb;
+    const int ld_gw = P.ld_gw;
     __shared__ float red[8][33];
     pdl_launch_dependents();
     pdl_wait();
@@ -645,6 +671,26 @@ static int launch_linear_tc(const float* x, int64_t n_rows, const uint8_t* weigh
     return 0;
 }
 
+template <bool FP16, bool EX>
+static int launch_chain_t(const float* x, int64_t n_rows, const tc::ChainArgs& a, int act, void* stream) {
+    const size_t smem = tc::ChainLayout::kBytes + 1024;
+    const int64_t tiles = (n_rows + 127) / 128;
+    const dim3 grid((unsigned)(tiles < kNumSM ? tiles : kNumSM));
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
+        GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_chain_tc_kernel<FP16, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.set();
+    }
+    GEOSSL_CUDA(launch_pdl(tc::linear_chain_tc_kernel<FP16, EX>, grid, dim3(512), smem, as_stream(stream), x, n_rows, a, act));
+    GEOSSL_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_chain(const float* x, int64_t n_rows, const tc::ChainArgs& a, int bf16_parts, int act, bool ex, void* stream) {
+    if (ex) return bf16_parts ? launch_chain_t<false, true>(x, n_rows, a, act, stream) : launch_chain_t<true, true>(x, n_rows, a, act, stream);
+    return bf16_parts ? launch_chain_t<false, false>(x, n_rows, a, act, stream) : launch_chain_t<true, false>(x, n_rows, a, act, stream);
+}
+
 extern "C" {
 
 int64_t geossl_weight_image_bytes(void) { return tc::kWImage; }
@@ -723,29 +769,6 @@ int geossl_linear_tc_block(const float* x, int64_t ldx, int64_t n_rows, const vo
                               ldx, ldz, ldr, ldy, act, k_cols, as_stream(stream));
 }
 
-static int launch_chain(const float* x, int64_t n_rows, const tc::ChainArgs& a, int bf16_parts, int act, void* stream) {
-    const size_t smem = tc::ChainLayout::kBytes + 1024;
-    const int64_t tiles = (n_rows + 127) / 128;
-    const dim3 grid((unsigned)(tiles < kNumSM ? tiles : kNumSM));
-    if (bf16_parts) {
-        static PerDeviceFlag configured;
-        if (!configured.get()) {
-            GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured.set();
-        }
-        GEOSSL_CUDA(launch_pdl(tc::linear_chain_tc_kernel<false>, grid, dim3(512), smem, as_stream(stream), x, n_rows, a, act));
-    } else {
-        static PerDeviceFlag configured;
-        if (!configured.get()) {
-            GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured.set();
-        }
-        GEOSSL_CUDA(launch_pdl(tc::linear_chain_tc_kernel<true>, grid, dim3(512), smem, as_stream(stream), x, n_rows, a, act));
-    }
-    GEOSSL_LAUNCH_CHECK();
-    return 0;
-}
-
 int geossl_linear_chain_tc(const float* x, int64_t n_rows, const geossl_chain_stage* stages, int n_stages, int bf16_parts, int act,
                            void* stream) {
     if (n_rows == 0) return 0;
@@ -766,7 +789,7 @@ int geossl_linear_chain_tc(const float* x, int64_t n_rows, const geossl_chain_st
         a.st[i].ldz = a.st[i].ldr = a.st[i].lds = 128;
     }
     GEOSSL_REQUIRE(stages[n_stages - 1].store != nullptr, "the last stage must store its result");
-    return launch_chain(x, n_rows, a, bf16_parts, act, stream);
+    return launch_chain(x, n_rows, a, bf16_parts, act, false, stream);
 }
 
 int geossl_linear_chain_ex(int64_t n_rows, const geossl_chain_stage_ex* stages, int n_stages, int bf16_parts, int act, void* stream) {
@@ -798,7 +821,7 @@ int geossl_linear_chain_ex(int64_t n_rows, const geossl_chain_stage_ex* stages, 
         a.st[i].keep = S.keep; a.st[i].accumulate = S.accumulate; a.st[i].partial = S.partial;
     }
     GEOSSL_REQUIRE(stages[n_stages - 1].store != nullptr, "the last stage must store its result");
-    return launch_chain(stages[0].x, n_rows, a, bf16_parts, act, stream);
+    return launch_chain(stages[0].x, n_rows, a, bf16_parts, act, true, stream);
 }
 
 int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows) { return (int64_t)tc::wgrad_grid(n_rows) * tc::kWgPart; }
@@ -819,21 +842,45 @@ int geossl_linear_wgrad_tc_block(const float* grad_y, int64_t ld_dy, const float
     return wgrad_block(grad_y, ld_dy, x, ld_x, n_rows, pre_act, workspace, grad_weight, ld_gw, grad_bias, x_cols, stream);
 }
 
-static int wgrad_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act, float* workspace,
-                       float* grad_weight, int ld_gw, float* grad_bias, int x_cols, void* stream) {
-    GEOSSL_REQUIRE(grad_y && x && workspace && grad_weight && n_rows > 0, "null pointer or empty input");
+static int wgrad_launch(const tc::WgBatch& b, int n_problems, int64_t n_rows, void* stream) {
     const size_t smem = tc::WgLayout::kBytes + 1024;
     static PerDeviceFlag configured;
     if (!configured.get()) {
         GEOSSL_CUDA(cudaFuncSetAttribute(tc::linear_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured.set();
     }
-    const int grid = tc::wgrad_grid(n_rows);
-    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid), dim3(256), smem, as_stream(stream), grad_y, x, n_rows, pre_act, workspace, ld_dy, ld_x, x_cols));
+    // the launch shares the SMs with the main backward chain: the CTA budget of ONE weight-gradient launch is split among
+    // the problems (a 3 x 120-CTA burst measurably slows the chain: 2.33 vs 2.22 ms per SchNet step)
+    int grid = (tc::wgrad_grid(n_rows) + n_problems - 1) / n_problems;
+    if (grid < 1) grid = 1;
+    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_tc_kernel<false>, dim3(grid, n_problems), dim3(256), smem, as_stream(stream), b, n_rows));
     GEOSSL_LAUNCH_CHECK();
-    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_reduce_kernel, dim3((tc::kWgPart + 31) / 32), dim3(256), 0, as_stream(stream), workspace, grid, grad_weight, grad_bias, ld_gw));
+    GEOSSL_CUDA(launch_pdl(tc::linear_wgrad_reduce_kernel, dim3((tc::kWgPart + 31) / 32, n_problems), dim3(256), 0, as_stream(stream), b, grid));
     GEOSSL_LAUNCH_CHECK();
     return 0;
+}
+
+static int wgrad_block(const float* grad_y, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int pre_act, float* workspace,
+                       float* grad_weight, int ld_gw, float* grad_bias, int x_cols, void* stream) {
+    GEOSSL_REQUIRE(grad_y && x && workspace && grad_weight && n_rows > 0, "null pointer or empty input");
+    tc::WgBatch b = {};
+    b.p[0] = tc::WgProblem{grad_y, x, workspace, grad_weight, grad_bias, ld_dy, ld_x, pre_act, x_cols, ld_gw};
+    return wgrad_launch(b, 1, n_rows, stream);
+}
+
+int geossl_linear_wgrad_tc_batch(const geossl_wgrad_problem* problems, int n_problems, int64_t n_rows, void* stream) {
+    if (n_problems == 0 || n_rows == 0) return 0;
+    GEOSSL_REQUIRE(problems && n_problems >= 1 && n_problems <= tc::kMaxWgBatch && n_rows > 0, "1..6 problems over a non-empty row range");
+    tc::WgBatch b = {};
+    for (int i = 0; i < n_problems; ++i) {
+        const geossl_wgrad_problem& P = problems[i];
+        GEOSSL_REQUIRE(P.grad_y && P.x && P.workspace && P.grad_weight, "null pointer");
+        GEOSSL_REQUIRE(P.x_cols >= 8 && P.x_cols <= 128 && P.x_cols % 8 == 0, "x_cols must be a multiple of 8 in [8,128]");
+        GEOSSL_REQUIRE(P.ld_dy >= 128 && P.ld_x >= P.x_cols && P.ld_gw >= 128 && P.ld_dy % 4 == 0 && P.ld_x % 4 == 0, "bad leading dimension");
+        GEOSSL_REQUIRE(P.pre_act >= 0 && P.pre_act <= 2, "pre_act must be 0, 1 (ssp) or 2 (silu)");
+        b.p[i] = tc::WgProblem{P.grad_y, P.x, P.workspace, P.grad_weight, P.grad_bias, P.ld_dy, P.ld_x, P.pre_act, P.x_cols, P.ld_gw};
+    }
+    return wgrad_launch(b, n_problems, n_rows, stream);
 }
 
 }  // extern "C"

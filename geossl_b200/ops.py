@@ -688,6 +688,56 @@ def _linear_wgrad(gy, x, pre_ssp, wp, bp):
     return wgrad()
 
 
+def _wgrad_batch(n, problems, name="linear_wgrad"):
+    """One geossl_linear_wgrad_tc_batch launch (+ one reduction) for up to six weight-gradient products over the same ``n``
+    rows.  problems: dicts with gy=(tensor, column), x=(tensor, column), pre_act, x_cols, gw=(tensor, element offset, row
+    stride), gb=(tensor, element offset) or None."""
+    lib = _lib.load()
+    ws_floats = lib.geossl_linear_wgrad_tc_workspace(n)
+    dev = problems[0]["gy"][0].device
+    ws = torch.empty(ws_floats * len(problems), dtype=torch.float32, device=dev)
+    for i0 in range(0, len(problems), 6):
+        chunk = problems[i0:i0 + 6]
+        arr = (_lib.WgradProblem * len(chunk))()
+        for k, (a, pr) in enumerate(zip(arr, chunk)):
+            gy, gyc = pr["gy"]
+            x, xc = pr["x"]
+            gw, gwo, ldgw = pr["gw"]
+            a.grad_y, a.ld_dy = gy.data_ptr() + 4 * gyc, gy.stride(0)
+            a.x, a.ld_x = x.data_ptr() + 4 * xc, x.stride(0)
+            a.workspace = ws.data_ptr() + 4 * ws_floats * (i0 + k)
+            a.grad_weight, a.ld_gw = gw.data_ptr() + 4 * gwo, ldgw
+            gb = pr.get("gb")
+            a.grad_bias = None if gb is None else gb[0].data_ptr() + 4 * gb[1]
+            a.pre_act, a.x_cols = int(pr.get("pre_act", 0)), int(pr.get("x_cols", 128))
+        _timed(name, lambda: lib.geossl_linear_wgrad_tc_batch(arr, len(chunk), n, _stream()))
+
+
+def _linear_wgrads(items):
+    """Weight / bias gradients of several 128 -> 128 layers over the same rows in ONE launch: items = [(gy, x, pre_ssp, weight
+    param, bias param or None)].  Returns [(gw, gb)] for autograd -- (None, None) for every layer when the launch went to the
+    side stream (see ``side_stream_wgrads``)."""
+    n = items[0][1].size(0)
+    params = []
+    for _, _, _, wp, bp in items:
+        params += [wp, bp]
+
+    def compute():
+        out, probs = [], []
+        for gy, x, pre, wp, bp in items:
+            gw = torch.empty((128, 128), dtype=torch.float32, device=x.device)
+            gb = torch.empty(128, dtype=torch.float32, device=x.device) if bp is not None else None
+            probs.append({"gy": (gy, 0), "x": (x, 0), "pre_act": ACT_SSP if pre else ACT_NONE, "gw": (gw, 0, 128),
+                          "gb": None if gb is None else (gb, 0)})
+            out += [gw, gb]
+        _wgrad_batch(n, probs)
+        return out
+
+    inputs = [t for gy, x, _, _, _ in items for t in (gy, x)]
+    flat = _deferred_wgrads(compute, params, inputs)
+    return [(flat[2 * i], flat[2 * i + 1]) for i in range(len(items))]
+
+
 class LinearTC(torch.autograd.Function):
     """y = [ssp](x) @ W^T + b [+ residual] for 128 -> 128 atom-wise layers (geossl_linear_tc / _wgrad_tc).
     Forward operands are split into fp16 parts, gradient operands into bf16 parts (see tc.cuh)."""
@@ -788,10 +838,15 @@ class InteractionTail(torch.autograd.Function):
         if n:
             _chain(x0, stages, True, "dense_chain_bwd")
         gw1n = None
-        if w1n is not None and g_xn is not None and n:
+        if not n:
+            return (g_m, g_tot, torch.zeros_like(w2), torch.zeros_like(b2), torch.zeros_like(w3), torch.zeros_like(b3),
+                    None if w1n is None else torch.zeros_like(w1n), None, None, None)
+        # three separate launches on purpose: batched into one (ops._linear_wgrads) the step is slower (2.33-2.37 vs 2.22 ms) --
+        # the longer kernel holds SMs against the main chain and lengthens the tail that the final stream join waits for
+        if w1n is not None and g_xn is not None:
             gw1n, _ = _linear_wgrad(g_xn, h_next, False, w1n, None)
-        gw3, gb3 = _linear_wgrad(g_tot, y1, True, w3, b3) if n else (torch.zeros_like(w3), torch.zeros_like(b3))
-        gw2, gb2 = _linear_wgrad(g_y1, m, False, w2, b2) if n else (torch.zeros_like(w2), torch.zeros_like(b2))
+        gw3, gb3 = _linear_wgrad(g_tot, y1, True, w3, b3)
+        gw2, gb2 = _linear_wgrad(g_y1, m, False, w2, b2)
         return g_m, g_tot, gw2, gb2, gw3, gb3, gw1n, None, None, None
 
 
@@ -987,12 +1042,9 @@ class DenseTC(torch.autograd.Function):
             def wgrad():
                 gw_ = torch.empty_like(weight)
                 gb_ = torch.empty(N, dtype=torch.float32, device=x.device) if bp is not None else None
-                ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
-                for ob in range(N // 128):
-                    for ib in range(K // 128):
-                        _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
-                            _off(gy, ob * 128), N, _off(x, ib * 128), x.size(1), n, ctx.pre_act, _p(ws), _off(gw_, ob * 128 * K + ib * 128), K,
-                            None if (gb_ is None or ib) else _off(gb_, ob * 128), ctx.k_cols, _stream()))
+                _wgrad_batch(n, [{"gy": (gy, ob * 128), "x": (x, ib * 128), "pre_act": ctx.pre_act, "x_cols": ctx.k_cols,
+                                  "gw": (gw_, ob * 128 * K + ib * 128, K), "gb": None if (gb_ is None or ib) else (gb_, ob * 128)}
+                                 for ob in range(N // 128) for ib in range(K // 128)], "dense_wgrad")   # all blocks: one launch per six
                 return gw_, gb_
 
             deferrable = wp.is_leaf and wp.requires_grad and (bp is None or (bp.is_leaf and bp.requires_grad))
@@ -1137,15 +1189,11 @@ class DenseChain2(torch.autograd.Function):
                 gwa, gwb = torch.empty_like(wa), torch.empty_like(wb)
                 gba = torch.empty_like(ba) if ba is not None else None
                 gbb = torch.empty_like(bb) if bb is not None else None
-                ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
-                for ob in range(no):
-                    _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
-                        _off(gy, ob * 128), gy.size(1), _p(z), 128, n, ACT_SILU, _p(ws), _off(gwb, ob * 128 * 128), 128,
-                        None if gbb is None else _off(gbb, ob * 128), 128, _stream()))
-                for kb in range(nk):
-                    _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
-                        _p(gz), 128, _off(x, kb * 128), K, n, ACT_NONE, _p(ws), _off(gwa, kb * 128), K,
-                        None if (gba is None or kb) else _p(gba), 128, _stream()))
+                probs = [{"gy": (gy, ob * 128), "x": (z, 0), "pre_act": ACT_SILU, "gw": (gwb, ob * 128 * 128, 128),
+                          "gb": None if gbb is None else (gbb, ob * 128)} for ob in range(no)]
+                probs += [{"gy": (gz, 0), "x": (x, kb * 128), "gw": (gwa, kb * 128, K),
+                           "gb": None if (gba is None or kb) else (gba, 0)} for kb in range(nk)]
+                _wgrad_batch(n, probs, "dense_wgrad")          # every block of both layers: one launch
                 return [gwa, gba, gwb, gbb]
 
             gwa, gba, gwb, gbb = _deferred_wgrads(wgrads, [wa, ba, wb, bb], [gy, z, gz, x])
@@ -1162,11 +1210,8 @@ class DenseChain2(torch.autograd.Function):
         def wgrads1():
             gwa = torch.empty_like(wa)
             gba = torch.empty_like(ba) if ba is not None else None
-            ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=x.device)
-            for ob in range(no):
-                _timed("dense_wgrad", lambda: lib.geossl_linear_wgrad_tc_block(
-                    _off(gy, ob * 128), gy.size(1), _p(x), 128, n, ACT_NONE, _p(ws), _off(gwa, ob * 128 * 128), 128,
-                    None if gba is None else _off(gba, ob * 128), 128, _stream()))
+            _wgrad_batch(n, [{"gy": (gy, ob * 128), "x": (x, 0), "gw": (gwa, ob * 128 * 128, 128),
+                              "gb": None if gba is None else (gba, ob * 128)} for ob in range(no)], "dense_wgrad")
             return [gwa, gba, None, None]
 
         gwa, gba, _, _ = _deferred_wgrads(wgrads1, [wa, ba, None, None], [gy, x])

@@ -295,6 +295,19 @@ int64_t geossl_linear_wgrad_tc_workspace(int64_t n_rows);
 int geossl_linear_wgrad_tc(const float* grad_y, const float* x, int64_t n_rows, int pre_ssp, float* workspace,
                            float* grad_weight, float* grad_bias, void* stream);
 
+/* Up to 6 weight-gradient products over the SAME n_rows rows in one launch (+ one reduction launch): the three layers of an
+ * interaction tail, the 128 x 128 blocks of a wider Dense layer, ...  Each problem has its own workspace
+ * (geossl_linear_wgrad_tc_workspace(n_rows) floats) and the argument meaning of geossl_linear_wgrad_tc_block. */
+typedef struct {
+    const float* grad_y; int64_t ld_dy;
+    const float* x;      int64_t ld_x;
+    float* workspace;
+    float* grad_weight;  int ld_gw;
+    float* grad_bias;    /* may be NULL */
+    int pre_act, x_cols;
+} geossl_wgrad_problem;
+int geossl_linear_wgrad_tc_batch(const geossl_wgrad_problem* problems /*host*/, int n_problems, int64_t n_rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * DDM head.  Replaces the distance block of do_DDM (examples/pretrain_GeoSSL.py:197-205) and
  * NCSN_version_03.forward (examples/NCSN.py:183-212) + MultiLayerPerceptron (NCSN.py:9-43) and their
