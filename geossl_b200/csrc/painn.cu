@@ -117,6 +117,61 @@ painn_message_fwd_kernel(const float* __restrict__ q, const float* __restrict__ 
     }
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    if constexpr (CPL == 4) {
+        if (wpre != nullptr) {
+            // F = 128 with materialised filter rows: lane owns four CONSECUTIVE features (128-bit loads: 9 per edge instead of
+            // 36); the edge records of a row (edge id, neighbour, cutoff, direction) are fetched by the lanes in parallel and
+            // broadcast by shuffle, so the row loads of consecutive edges do not wait on per-edge index loads
+            const int f4 = lane * 4;
+            for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_atoms; i += warps_per_grid) {
+                float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), a0 = aq, a1 = aq, a2 = aq;
+                const int kb = __ldg(i_rowptr + i), ke = __ldg(i_rowptr + i + 1);
+                for (int base = kb; base < ke; base += 32) {
+                    const int cnt = min(32, ke - base);
+                    int my_e = 0, my_nb = 0;
+                    float my_fc = 0.f, my_dx = 0.f, my_dy = 0.f, my_dz = 0.f;
+                    if (lane < cnt) {
+                        my_e = __ldg(i_eid + base + lane);
+                        my_nb = __ldg(i_nbr + base + lane);
+                        my_fc = __ldg(fcut + my_e);
+                        my_dx = __ldg(dir + 3 * (int64_t)my_e); my_dy = __ldg(dir + 3 * (int64_t)my_e + 1); my_dz = __ldg(dir + 3 * (int64_t)my_e + 2);
+                    }
+#pragma unroll 2
+                    for (int k = 0; k < cnt; ++k) {
+                        const int e = __shfl_sync(0xffffffffu, my_e, k), nb = __shfl_sync(0xffffffffu, my_nb, k);
+                        const float fc = __shfl_sync(0xffffffffu, my_fc, k);
+                        const float dx = __shfl_sync(0xffffffffu, my_dx, k), dy = __shfl_sync(0xffffffffu, my_dy, k),
+                                    dz = __shfl_sync(0xffffffffu, my_dz, k);
+                        const float* wr = wpre + (int64_t)e * 3 * F + f4;
+                        const float* xj = x + (int64_t)nb * 3 * F + f4;
+                        const float* mj = mu + (int64_t)nb * 3 * F + f4;
+                        const float4 w0 = ldg4(wr), w1 = ldg4(wr + F), w2 = ldg4(wr + 2 * F);
+                        const float4 x0 = ldg4(xj), x1 = ldg4(xj + F), x2 = ldg4(xj + 2 * F);
+                        const float4 m0 = ldg4(mj), m1 = ldg4(mj + F), m2 = ldg4(mj + 2 * F);
+#define GEOSSL_MSG_LANE(c)                                                                                   \
+                        {                                                                                    \
+                            aq.c = fmaf(w0.c * fc, x0.c, aq.c);                                               \
+                            const float dmuR = (w1.c * fc) * x1.c, dmumu = (w2.c * fc) * x2.c;                \
+                            a0.c += dmuR * dx + dmumu * m0.c;                                                 \
+                            a1.c += dmuR * dy + dmumu * m1.c;                                                 \
+                            a2.c += dmuR * dz + dmumu * m2.c;                                                 \
+                        }
+                        GEOSSL_MSG_LANE(x) GEOSSL_MSG_LANE(y) GEOSSL_MSG_LANE(z) GEOSSL_MSG_LANE(w)
+#undef GEOSSL_MSG_LANE
+                    }
+                }
+                const float4 q4 = ldg4(q + (int64_t)i * F + f4);
+                *reinterpret_cast<float4*>(q_out + (int64_t)i * F + f4) = make_float4(q4.x + aq.x, q4.y + aq.y, q4.z + aq.z, q4.w + aq.w);
+                const float* mi = mu + (int64_t)i * 3 * F + f4;
+                float* mo = mu_out + (int64_t)i * 3 * F + f4;
+                const float4 u0 = ldg4(mi), u1 = ldg4(mi + F), u2 = ldg4(mi + 2 * F);
+                *reinterpret_cast<float4*>(mo) = make_float4(u0.x + a0.x, u0.y + a0.y, u0.z + a0.z, u0.w + a0.w);
+                *reinterpret_cast<float4*>(mo + F) = make_float4(u1.x + a1.x, u1.y + a1.y, u1.z + a1.z, u1.w + a1.w);
+                *reinterpret_cast<float4*>(mo + 2 * F) = make_float4(u2.x + a2.x, u2.y + a2.y, u2.z + a2.z, u2.w + a2.w);
+            }
+            return;
+        }
+    }
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_atoms; i += warps_per_grid) {
         float aq[CPL], amu[3][CPL];
 #pragma unroll
@@ -180,7 +235,75 @@ painn_message_bwd_kernel(const float* __restrict__ gq_out, const float* __restri
     }
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    for (int jn = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jn < n_atoms; jn += warps_per_grid) {
+    bool fast = false;
+    if constexpr (CPL == 4) fast = wpre != nullptr;
+    if (fast) {
+        // same layout as the forward fast path: four consecutive features per lane, edge records broadcast by shuffle
+        const int f4 = lane * 4;
+        for (int jn = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jn < n_atoms; jn += warps_per_grid) {
+            const float* xp = x + (int64_t)jn * 3 * F + f4;
+            const float* mp = mu + (int64_t)jn * 3 * F + f4;
+            const float4 x0 = ldg4(xp), x1 = ldg4(xp + F), x2 = ldg4(xp + 2 * F);
+            const float4 m0 = ldg4(mp), m1 = ldg4(mp + F), m2 = ldg4(mp + 2 * F);
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 gx0 = z4, gx1 = z4, gx2 = z4, gm0 = z4, gm1 = z4, gm2 = z4;
+            const int eb = __ldg(j_rowptr + jn), ee = __ldg(j_rowptr + jn + 1);
+            for (int base = eb; base < ee; base += 32) {
+                const int cnt = min(32, ee - base);
+                int my_i = 0;
+                float my_fc = 0.f, my_dx = 0.f, my_dy = 0.f, my_dz = 0.f;
+                if (lane < cnt) {
+                    const int64_t e = base + lane;
+                    my_i = __ldg(j_ctr + e);
+                    my_fc = __ldg(fcut + e);
+                    my_dx = __ldg(dir + 3 * e); my_dy = __ldg(dir + 3 * e + 1); my_dz = __ldg(dir + 3 * e + 2);
+                }
+#pragma unroll 2
+                for (int k = 0; k < cnt; ++k) {
+                    const int64_t e = base + k;
+                    const int i = __shfl_sync(0xffffffffu, my_i, k);
+                    const float fc = __shfl_sync(0xffffffffu, my_fc, k);
+                    const float dx = __shfl_sync(0xffffffffu, my_dx, k), dy = __shfl_sync(0xffffffffu, my_dy, k),
+                                dz = __shfl_sync(0xffffffffu, my_dz, k);
+                    const float* wr = wpre + e * 3 * F + f4;
+                    const float4 w0 = ldg4(wr), w1 = ldg4(wr + F), w2 = ldg4(wr + 2 * F);
+                    const float4 gq = ldg4(gq_out + (int64_t)i * F + f4);
+                    const float* gp = gmu_out + (int64_t)i * 3 * F + f4;
+                    const float4 g0 = ldg4(gp), g1 = ldg4(gp + F), g2 = ldg4(gp + 2 * F);
+                    float4 o0, o1, o2;
+#define GEOSSL_MSG_LANE(c)                                                                                       \
+                    {                                                                                            \
+                        const float br = g0.c * dx + g1.c * dy + g2.c * dz;                                       \
+                        const float bm = g0.c * m0.c + g1.c * m1.c + g2.c * m2.c;                                 \
+                        const float wa = w0.c * fc, wb = w1.c * fc, wc = w2.c * fc;                               \
+                        gx0.c = fmaf(wa, gq.c, gx0.c);                                                            \
+                        gx1.c = fmaf(wb, br, gx1.c);                                                              \
+                        gx2.c = fmaf(wc, bm, gx2.c);                                                              \
+                        const float dmumu = wc * x2.c;                                                            \
+                        gm0.c = fmaf(dmumu, g0.c, gm0.c);                                                         \
+                        gm1.c = fmaf(dmumu, g1.c, gm1.c);                                                         \
+                        gm2.c = fmaf(dmumu, g2.c, gm2.c);                                                         \
+                        o0.c = x0.c * gq.c * fc; o1.c = x1.c * br * fc; o2.c = x2.c * bm * fc;                    \
+                    }
+                    GEOSSL_MSG_LANE(x) GEOSSL_MSG_LANE(y) GEOSSL_MSG_LANE(z) GEOSSL_MSG_LANE(w)
+#undef GEOSSL_MSG_LANE
+                    float* go = gfilt + e * 3 * F + f4;
+                    *reinterpret_cast<float4*>(go) = o0;
+                    *reinterpret_cast<float4*>(go + F) = o1;
+                    *reinterpret_cast<float4*>(go + 2 * F) = o2;
+                }
+            }
+            const int64_t o = (int64_t)jn * 3 * F + f4;
+            *reinterpret_cast<float4*>(gx + o) = gx0;
+            *reinterpret_cast<float4*>(gx + o + F) = gx1;
+            *reinterpret_cast<float4*>(gx + o + 2 * F) = gx2;
+            const float4 h0 = ldg4(gmu_out + o), h1 = ldg4(gmu_out + o + F), h2 = ldg4(gmu_out + o + 2 * F);
+            *reinterpret_cast<float4*>(gmu_in + o) = make_float4(h0.x + gm0.x, h0.y + gm0.y, h0.z + gm0.z, h0.w + gm0.w);
+            *reinterpret_cast<float4*>(gmu_in + o + F) = make_float4(h1.x + gm1.x, h1.y + gm1.y, h1.z + gm1.z, h1.w + gm1.w);
+            *reinterpret_cast<float4*>(gmu_in + o + 2 * F) = make_float4(h2.x + gm2.x, h2.y + gm2.y, h2.z + gm2.z, h2.w + gm2.w);
+        }
+    }
+    for (int jn = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jn < n_atoms && !fast; jn += warps_per_grid) {
         float xj[3][CPL], mj[3][CPL], agx[3][CPL], agm[3][CPL];
 #pragma unroll
         for (int b = 0; b < 3; ++b)
