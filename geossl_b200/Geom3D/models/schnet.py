@@ -198,6 +198,7 @@ class SchNet(torch.nn.Module):
             graph = ops.radius_csr(pos, batch, self.cutoff, num_graphs=num_graphs, max_graph_atoms=max_graph_atoms)
         fused = False
         if pos.requires_grad and torch.is_grad_enabled():
+            ops.begin_composed_pass()                              # packed operand images live for this pass only
             if (ops.COMPOSED_PAIRS and ops.SHARE_PAIR_FILTERS and ops.FILTER_MODE != "simt" and graph.dist is not None
                     and graph._exact is None):
                 graph.ensure_pairs()                               # before exact(): edge and pair count share one host read

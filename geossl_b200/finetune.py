@@ -32,8 +32,9 @@ def md17_losses(args, batch_data, model, graph_pred_linear, criterion, energy_co
     positions.requires_grad_()
     molecule_3D_repr = _readout(args, model, batch_data, positions)
     pred_energy = (graph_pred_linear(molecule_3D_repr) if graph_pred_linear is not None else molecule_3D_repr).squeeze(1)
-    pred_force = -grad(outputs=pred_energy, inputs=positions, grad_outputs=torch.ones_like(pred_energy),
-                       create_graph=True, retain_graph=True)[0]
+    with ops.param_grads_disabled():        # only d/dpos is asked for: no (discarded) weight-gradient launches in the force pass
+        pred_force = -grad(outputs=pred_energy, inputs=positions, grad_outputs=torch.ones_like(pred_energy),
+                           create_graph=True, retain_graph=True)[0]
     y = getattr(batch_data, "y", None)
     y = batch_data.extras["y"] if y is None else y
     f = getattr(batch_data, "force", None)

@@ -1271,10 +1271,45 @@ def dense(x, layer, images=None, pre_act=ACT_NONE):
 #   MatXW  : y = g @ W                          geossl_linear_tc_block, transposed weight image
 #   MatTX  : G = a^T @ b[:, :k]                 geossl_linear_wgrad_tc_block (reduction over the rows)
 # W and G are (128,128); x / b may be K-padded operands with k in {32, 64, 128} live columns (the 50 gaussians, padded to 64).
+# Packed operand images of the composed path, valid for ONE forward and its backward passes: SchNet.forward clears the table
+# (``begin_composed_pass``), so an image is never reused across an optimizer step; inside the pass a weight is packed once per
+# orientation instead of once per product (118 -> ~30 pack launches per MD17 step).  Entries keep their source tensor alive,
+# so a recycled address cannot alias.
+_mm_images = {}
+
+
+def begin_composed_pass():
+    _mm_images.clear()
+
+
+class _param_grads_off:
+    """Inside this context the backward of MatXWt / MatXW skips weight and bias gradients.  For ``autograd.grad(energy,
+    positions, create_graph=True)`` (finetune_md17.py:40-44): only d/dpos is requested there, torch prunes the parameter
+    branches of its own ops in that case, and a custom Function cannot see the pruning -- without the flag every product of
+    the force pass would also launch a (discarded) edge-sized weight-gradient GEMM."""
+    on = False
+
+    def __enter__(self):
+        self.prev = _param_grads_off.on
+        _param_grads_off.on = True
+
+    def __exit__(self, *exc):
+        _param_grads_off.on = self.prev
+
+
+def param_grads_disabled():
+    return _param_grads_off()
+
+
 def _mm_image(w, transpose, bf16_parts):
+    key = (w.data_ptr(), w._version, bool(transpose), bool(bf16_parts))
+    hit = _mm_images.get(key)
+    if hit is not None:                       # (the entry holds the source tensor, so this address + version is still that tensor's data)
+        return hit[1]
     lib = _lib.load()
     image = torch.empty(lib.geossl_weight_image_bytes(), dtype=torch.uint8, device=w.device)
     check(lib.geossl_pack_weight(_p(w), 1 if transpose else 0, 1 if bf16_parts else 0, _p(image), _stream()), "pack_weight")
+    _mm_images[key] = (w, image)
     return image
 
 
@@ -1307,9 +1342,9 @@ class MatXWt(torch.autograd.Function):
         x, w = ctx.saved_tensors
         gy = gy.contiguous()
         gx = MatXW.apply(gy, w)[:, :x.size(1)] if ctx.needs_input_grad[0] else None
-        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        want_b = ctx.has_bias and ctx.needs_input_grad[2] and not _param_grads_off.on
         gw = gb = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and not _param_grads_off.on:
             gw, colsum = MatTX.apply(gy, x, want_b)          # the bias gradient is the kernel's column sum of gy: no extra pass
             gb = colsum if want_b else None
         elif want_b:
@@ -1335,7 +1370,7 @@ class MatXW(torch.autograd.Function):
         g, w = ctx.saved_tensors
         go = go.contiguous()
         gg = MatXWt.apply(go, w, None, False) if ctx.needs_input_grad[0] else None
-        gw = MatTX.apply(g, go, False)[0] if ctx.needs_input_grad[1] else None
+        gw = MatTX.apply(g, go, False)[0] if (ctx.needs_input_grad[1] and not _param_grads_off.on) else None
         return gg, gw
 
 
@@ -1348,8 +1383,9 @@ class MatTX(torch.autograd.Function):
         ctx.save_for_backward(a, b)
         ctx.set_materialize_grads(False)
         n, k = b.shape
-        out = torch.zeros((128, 128), dtype=torch.float32, device=a.device)
-        colsum = torch.zeros(128 if want_colsum else 0, dtype=torch.float32, device=a.device)
+        # (the kernel writes all 128 x 128 entries -- columns past k come out zero -- and the 128 column sums)
+        out = torch.empty((128, 128), dtype=torch.float32, device=a.device) if n else torch.zeros((128, 128), dtype=torch.float32, device=a.device)
+        colsum = (torch.empty if n else torch.zeros)(128 if want_colsum else 0, dtype=torch.float32, device=a.device)
         if n:
             lib = _lib.load()
             ws = torch.empty(lib.geossl_linear_wgrad_tc_workspace(n), dtype=torch.float32, device=a.device)
