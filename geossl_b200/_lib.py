@@ -49,7 +49,7 @@ class WgradProblem(ctypes.Structure):
                 ("ld_gw", c_int), ("grad_bias", c_p), ("pre_act", c_int), ("x_cols", c_int)]
 
 
-ABI_VERSION = 3          # must equal GEOSSL_ABI_VERSION in include/geossl_b200.h
+ABI_VERSION = 4          # must equal GEOSSL_ABI_VERSION in include/geossl_b200.h
 
 _SIGNATURES = {
     "geossl_abi_version": (c_int, []),

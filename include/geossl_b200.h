@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GEOSSL_ABI_VERSION 3   /* 2: filt_row / pair-index / batched-pack entry points; 3: round-2 entry points */
+#define GEOSSL_ABI_VERSION 4   /* 2: filt_row / pair-index / batched-pack entry points; 3: round-2 entry points; 4: cfconv_pairs, pair product, chain_ex, wgrad batch, elementwise families */
 #define GEOSSL_EINVAL (-1)   /* bad argument (null pointer, unsupported width, ...) */
 #define GEOSSL_ECAP   (-2)   /* capacity too small */
 

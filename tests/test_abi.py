@@ -26,7 +26,7 @@ def test_library_builds_and_exports_all_symbols():
     lib = _lib.load()
     for name in header_symbols():
         assert hasattr(lib, name), name
-    assert lib.geossl_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.geossl_abi_version() == _lib.ABI_VERSION == 4
     assert lib.geossl_filter_bwd_workspace(50, 128) > 0 and lib.geossl_ddm_workspace(128) > 0
     assert lib.geossl_filter_bwd_workspace(50, 48) == -1          # unsupported width is reported, not guessed
 
