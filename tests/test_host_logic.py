@@ -107,6 +107,25 @@ def test_synthetic_batch_contract():
     assert int(b.graph_ptr[-1]) == n
 
 
+def test_batches_carry_the_largest_molecule_and_padding_keeps_or_replaces_it():
+    """``extras['max_graph_atoms']`` is the host-side bound that selects the pair-centric cfconv kernel without a device sync
+    (ops.CFCONV_PAIRS): set at collate time, kept by ``to`` / ``pin_memory`` / ``pad_batch``, replaced by the capacity of a
+    padded stream when one is given, and read back by ``pretrain._max_graph_atoms``."""
+    from geossl_b200.data import pad_batch
+    from geossl_b200.pretrain import _max_graph_atoms
+    b = synthetic_batch(8, 10, 20, seed=3)
+    largest = int(torch.bincount(b.batch).max())
+    assert b.extras["max_graph_atoms"] == largest == _max_graph_atoms(b)
+    assert b.to("cpu").extras["max_graph_atoms"] == largest
+    n, p = b.positions.shape[0], b.super_edge_index.shape[1]
+    padded = pad_batch(b, n + 40, p + 100)
+    assert padded.extras["max_graph_atoms"] == largest and padded.num_graphs == 9          # + the edge-less padding graph
+    assert int(padded.graph_ptr[-1]) == n + 40 and int(padded.extras["n_pairs_live"]) == p
+    assert pad_batch(b, n + 40, p + 100, max_graph_atoms_cap=32).extras["max_graph_atoms"] == 32
+    ref_style = type(b)(b.x, b.positions, b.batch, b.super_edge_index)                     # a reference batch has no bound
+    assert _max_graph_atoms(ref_style) is None
+
+
 def _dp_worker(rank, world, port, tmp):
     import torch.distributed as dist
     from geossl_b200.pretrain import FlatGradAllReduce, broadcast_parameters
