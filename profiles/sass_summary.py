@@ -3,7 +3,7 @@
     python profiles/sass_summary.py > profiles/rNN_sass_summary.txt
 
 Counts, per kernel function, the mnemonics that prove tcgen05 / TMEM / TMA / async-copy use (B200_PROFILING.md):
-UTCHMMA (tcgen05.mma kind::f16), LDTM / STTM (tcgen05.ld / .st), UTCBAR (tcgen05.commit), UBLKCP (cp.async.bulk),
+UTCHMMA (tcgen05.mma kind::f16), LDTM / STTM (tcgen05.ld / .st), UTCBAR (tcgen05.commit), UBLKCP (cp.async.bulk), UBLKPF (cp.async.bulk.prefetch.L2),
 LDGSTS (cp.async), SYNCS (mbarrier), MUFU, and prints the first UTCHMMA / LDTM / UBLKCP line of each kernel as an excerpt."""
 import collections
 import os
@@ -12,7 +12,7 @@ import subprocess
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "geossl_b200", "libgeossl_b200.so")
-MNEMONICS = ("UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "LDGSTS", "SYNCS", "MUFU", "ATOMG", "REDG", "RED.")
+MNEMONICS = ("UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UBLKPF", "LDGSTS", "SYNCS", "MUFU", "ATOMG", "REDG", "RED.")
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
@@ -40,7 +40,7 @@ for name, k in kernels.items():
     if not k["c"]:
         continue
     print(f"{name}\n    {k['n']} instructions; " + ", ".join(f"{m} {c}" for m, c in k["c"].items()))
-    for m in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "LDGSTS"):
+    for m in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UBLKPF", "LDGSTS"):
         if m in k["ex"]:
             print(f"        {k['ex'][m]}")
 print("# library totals: " + ", ".join(f"{m} {c}" for m, c in tot.items()))
