@@ -231,17 +231,10 @@ def run_product(args):
         from geossl_b200 import ops as _o
         _o.CFCONV_PAIRS = os.environ["GEOSSL_CFCONV_PAIRS"] != "0"
         _o.CFCONV_PAIRS_TUNING = int(os.environ["GEOSSL_CFCONV_PAIRS"])
-    if os.environ.get("GEOSSL_EXPERIMENT_WGRAD"):         # experiments only (the printed line is NOT a valid bench value):
-        from geossl_b200 import ops as _o                 # "main" = weight gradients on the main stream, "skip" = not launched
+    if os.environ.get("GEOSSL_WGRAD_MAIN_STREAM"):        # A/B only: weight-gradient kernels on the main stream (same work, no overlap)
         import contextlib
-        if os.environ["GEOSSL_EXPERIMENT_WGRAD"] == "main":
-            _o.side_stream_wgrads = contextlib.nullcontext
-            import geossl_b200.pretrain as _pt
-            _pt.ops.side_stream_wgrads = contextlib.nullcontext
-        else:
-            _lib0 = _o._lib.load()
-            _o_timed = _o._timed
-            _o._timed = lambda name, fn: None if name in ("linear_wgrad", "dense_wgrad") else _o_timed(name, fn)
+        import geossl_b200.pretrain as _pt
+        _pt.ops.side_stream_wgrads = contextlib.nullcontext
     if os.environ.get("GEOSSL_PAIR_OWNER_SMALL"):         # tuning only
         from geossl_b200 import ops as _o
         _o.PAIR_OWNER_SMALL = os.environ["GEOSSL_PAIR_OWNER_SMALL"] != "0"
